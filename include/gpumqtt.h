@@ -1,0 +1,149 @@
+/* libgpumqtt — C ABI of the B200-native MQTT topic-filter matching engine.
+ *
+ * This is the drop-in boundary for ONE hot path of rmqtt (reference commit 4f9f2185):
+ *
+ *   Router::matches -> DefaultRouter::_matches -> TopicTree::matches      (PUBLISH, rmqtt/src/router.rs:162-248,
+ *                                                                           rmqtt/src/trie.rs:143-145, 299-347)
+ *   RetainStorage::get -> RetainTree::matches                              (SUBSCRIBE, rmqtt/src/retain.rs:152-169,
+ *                                                                           291-367)
+ *
+ * A Rust plugin (`GpuRouter` / `GpuRetainer`) keeps the reference's `Router` /
+ * `RetainStorage` traits and forwards exactly these calls through `extern "C"`.  Plain pointers and
+ * sizes only; no exceptions or aborts cross this boundary: every function returns a gm_status
+ * (0 = ok, < 0 = error) and gm_last_error() gives the text.  Every handle is thread-safe (the
+ * reference's objects are `Sync + Send`, router.rs:59).
+ *
+ * Values are u32 handles chosen by the caller (the host keeps handle -> (ClientId, Id, opts) /
+ * handle -> Retain, i.e. today's `relations` DashMap and the retained payloads stay on the host).
+ */
+#ifndef GPUMQTT_H
+#define GPUMQTT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gm_engine gm_engine;
+
+typedef enum gm_status {
+    GM_OK = 0,
+    GM_ERR_INVALID_ARG = -1,
+    GM_ERR_INVALID_TOPIC = -2, /* Topic::from_str would return Err (rmqtt/src/topic.rs:348-363) */
+    GM_ERR_CAPACITY = -3,      /* out_ids too small; *needed tells how many ids the batch produces */
+    GM_ERR_CUDA = -4,
+    GM_ERR_TOO_DEEP = -5,      /* filter has more levels than gm_config.max_levels (cf. listener max_topic_levels, rmqtt/src/session.rs:1275) */
+    GM_ERR_NO_DEVICE = -6,     /* no CUDA device: there is NO CPU fallback */
+    GM_ERR_TOO_LARGE = -7,     /* batch exceeds a 32-bit offset (blob >= 4 GiB or ids >= 2^32) */
+    GM_ERR_INTERNAL = -8
+} gm_status;
+
+typedef struct gm_config {
+    uint32_t struct_size;      /* = sizeof(gm_config) */
+    int32_t device;            /* CUDA device ordinal; -1 = current device */
+    uint32_t max_levels;       /* deepest accepted filter (0 = default 128) */
+    uint32_t flags;            /* GM_FLAG_* */
+    uint64_t filters_hint;     /* expected number of filters (pre-sizes the tables), 0 = unknown */
+} gm_config;
+
+#define GM_FLAG_MANUAL_FLUSH 1u /* matches do NOT flush pending mutations implicitly (caller fences with gm_flush) */
+#define GM_FLAG_HOST_ONLY 2u    /* staging mirror only, no CUDA context: add/remove/stats work, every match returns
+                                   GM_ERR_NO_DEVICE (used by the CPU-side tests of the host logic) */
+
+/* (offset, count) of one topic's result list inside out_ids */
+typedef struct gm_span {
+    uint32_t off;
+    uint32_t cnt;
+} gm_span;
+
+typedef struct gm_stats {
+    uint64_t values;           /* TopicTree::values_size  (rmqtt/src/trie.rs:148-151) — backs Router::topics_tree */
+    uint64_t nodes;            /* TopicTree::nodes_size   (rmqtt/src/trie.rs:154-157) */
+    uint64_t device_nodes;     /* node records resident on the device (includes pruned, not yet compacted ones) */
+    uint64_t edges, edge_slots;
+    uint64_t dict_entries, dict_slots;
+    uint64_t plus_nodes;
+    uint64_t value_words, garbage_value_words;
+    uint64_t device_bytes;
+    uint32_t max_depth;
+    uint32_t pending;          /* 1 if mutations are staged and not yet flushed */
+    uint64_t retained_values, retained_nodes;
+} gm_stats;
+
+/* exact work counters of the LAST gm_match_batch*_stats call — inputs of the roofline formula */
+typedef struct gm_work {
+    uint64_t visited;          /* V: trie nodes visited  (MatchedIter::prepare calls) */
+    uint64_t probed;           /* E: visited nodes with a non-empty remaining path */
+    uint64_t filters;          /* F: matched filter nodes */
+    uint64_t ids;              /* M: matched values */
+    uint64_t levels;           /* L: topic levels */
+    uint64_t bytes;            /* topic text bytes */
+    uint64_t deferred;         /* topics handled by the generic (slow) kernel */
+} gm_work;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+int32_t gm_create(const gm_config* cfg, gm_engine** out);
+void gm_destroy(gm_engine* e);
+const char* gm_last_error(gm_engine* e); /* valid until the next call on `e` from the same thread */
+const char* gm_version(void);
+
+/* ---- subscription trie: TopicTree<u32>::insert / remove (rmqtt/src/trie.rs:99-135), driven by
+ *      Router::add / Router::remove (rmqtt/src/router.rs:417-479).  `*changed` mirrors the reference's bool.
+ *      Mutations are staged on the host and shipped to HBM by gm_flush (side stream).                     */
+int32_t gm_sub_add(gm_engine* e, const char* filter, uint32_t len, uint32_t value, int32_t* changed);
+int32_t gm_sub_remove(gm_engine* e, const char* filter, uint32_t len, uint32_t value, int32_t* changed);
+/* n filters at once (cluster restore re-inserts every filter, rmqtt-cluster-raft/src/router.rs:557-561).
+ * Invalid filters are skipped; *n_changed = number of inserts that changed the tree.                      */
+int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets /* n+1 */, const uint32_t* values,
+                     uint64_t n, uint64_t* n_changed);
+int32_t gm_flush(gm_engine* e);
+
+/* ---- Router::matches for a batch of PUBLISH topic names (host buffers).
+ *      topics_blob/topic_offsets: n topic names back to back, topic i = blob[offsets[i] .. offsets[i+1]).
+ *      out_spans[i] = where topic i's matched values sit in out_ids (multiset, order unspecified — the
+ *      reference's order is hash-map iteration order too).  status[i] = GM_OK or GM_ERR_INVALID_TOPIC
+ *      (that topic alone yields an empty list, like the per-call Err at rmqtt/src/router.rs:165).
+ *      Returns GM_ERR_CAPACITY with *needed set when cap_ids is too small (nothing usable written).      */
+int32_t gm_match_batch(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
+                       gm_span* out_spans, uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed,
+                       int32_t* status);
+
+/* Same, with every buffer already in device memory, asynchronous on `stream` (a cudaStream_t).
+ * d_needed (device u64) receives the number of ids produced; nothing is copied to the host.            */
+int32_t gm_match_batch_device(gm_engine* e, const void* d_topics_blob, uint64_t blob_bytes,
+                              const uint32_t* d_topic_offsets, uint64_t n, gm_span* d_out_spans,
+                              uint32_t* d_out_ids, uint64_t cap_ids, uint64_t* d_needed, int32_t* d_status,
+                              void* stream);
+/* Instrumented variant of gm_match_batch_device: also accumulates the exact work counters (slower).    */
+int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_topics_blob, uint64_t blob_bytes,
+                                    const uint32_t* d_topic_offsets, uint64_t n, gm_span* d_out_spans,
+                                    uint32_t* d_out_ids, uint64_t cap_ids, uint64_t* d_needed,
+                                    int32_t* d_status, void* stream, gm_work* work);
+
+/* ---- tokeniser only (Topic::from_str for a batch) — used by tests to pin the device dictionary.
+ *      out_tokens: [max_tok][n] u32 (level-major), out_meta: [n] (bits 0..23 levels, bit 30 '$', bit 31 invalid) */
+int32_t gm_tokenize_batch(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
+                          uint32_t max_tok, uint32_t* out_tokens, uint32_t* out_meta);
+
+/* ---- misc ------------------------------------------------------------------------------------------- */
+int32_t gm_get_stats(gm_engine* e, gm_stats* out);
+/* device time (ms) of the kernels of the last gm_match_batch call: [0]=tokenise [1]=match [2]=deferred */
+int32_t gm_last_kernel_ms(gm_engine* e, float out_ms[3]);
+/* number of kernels the engine has launched since creation */
+uint64_t gm_kernel_launches(gm_engine* e);
+/* shard of a topic / filter by its level-0 string (multi-GPU root-hash partitioning); 0xFFFFFFFF for a
+ * filter whose level 0 is a wildcard (those are replicated on every shard)                               */
+uint32_t gm_shard_of(const char* topic_or_filter, uint32_t len, uint32_t n_shards);
+/* DEBUG/TEST: read-only view of the host mirror of a device table, in device layout (rmqtt_b200/csrc/layout.h).
+ * which: 0 edges(32 B) 1 plus(32 B) 2 ranges(8 B) 3 values(4 B) 4 dict(32 B) 5 long-string pool(1 B)
+ *        6 root record {plus, hash_ref, mask, max_depth}.  Valid until the next mutating call.           */
+int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t* count);
+/* pinned host memory for the host-buffer entry points */
+void* gm_host_alloc(uint64_t bytes);
+void gm_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUMQTT_H */

@@ -1,0 +1,84 @@
+"""ctypes binding of libgpumqtt.so (include/gpumqtt.h).  Fails loudly when the library is missing:
+there is no Python or CPU fallback for the matching path."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libgpumqtt.so"
+
+GM_OK = 0
+GM_ERR_INVALID_ARG = -1
+GM_ERR_INVALID_TOPIC = -2
+GM_ERR_CAPACITY = -3
+GM_ERR_CUDA = -4
+GM_ERR_TOO_DEEP = -5
+GM_ERR_NO_DEVICE = -6
+GM_ERR_TOO_LARGE = -7
+GM_ERR_INTERNAL = -8
+GM_FLAG_MANUAL_FLUSH = 1
+GM_FLAG_HOST_ONLY = 2
+
+
+class GmConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_levels", C.c_uint32), ("flags", C.c_uint32),
+                ("filters_hint", C.c_uint64)]
+
+
+class GmStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("values", "nodes", "device_nodes", "edges", "edge_slots", "dict_entries",
+                                           "dict_slots", "plus_nodes", "value_words", "garbage_value_words", "device_bytes")] + \
+               [("max_depth", C.c_uint32), ("pending", C.c_uint32), ("retained_values", C.c_uint64), ("retained_nodes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class GmWork(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("visited", "probed", "filters", "ids", "levels", "bytes", "deferred")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+# every symbol include/gpumqtt.h declares: name -> (restype, argtypes)
+_vp, _cp, _u32, _u64, _i32 = C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_int32
+_P = C.POINTER
+SIGNATURES = {
+    "gm_create": (_i32, [_P(GmConfig), _P(_vp)]),
+    "gm_destroy": (None, [_vp]),
+    "gm_last_error": (_cp, [_vp]),
+    "gm_version": (_cp, []),
+    "gm_sub_add": (_i32, [_vp, _cp, _u32, _u32, _P(_i32)]),
+    "gm_sub_remove": (_i32, [_vp, _cp, _u32, _u32, _P(_i32)]),
+    "gm_bulk_load": (_i32, [_vp, _vp, _vp, _vp, _u64, _P(_u64)]),
+    "gm_flush": (_i32, [_vp]),
+    "gm_match_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
+    "gm_match_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "gm_match_batch_device_stats": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp, _P(GmWork)]),
+    "gm_tokenize_batch": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp]),
+    "gm_get_stats": (_i32, [_vp, _P(GmStats)]),
+    "gm_last_kernel_ms": (_i32, [_vp, _P(C.c_float * 3)]),
+    "gm_kernel_launches": (_u64, [_vp]),
+    "gm_shard_of": (_u32, [_cp, _u32, _u32]),
+    "gm_debug_table": (_i32, [_vp, _u32, _P(_vp), _P(_u64)]),
+    "gm_host_alloc": (_vp, [_u64]),
+    "gm_host_free": (None, [_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libgpumqtt.so.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no fallback path")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib

@@ -1,0 +1,506 @@
+// libgpumqtt: C ABI (include/gpumqtt.h) over the host mirror (host_trie.cpp) and the sm_100a kernels
+// (kernels.cuh).  There is no CPU fallback: without a CUDA device every entry point that would match
+// returns GM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gpumqtt.h"
+#include "host_trie.h"
+#include "kernels.cuh"
+
+using namespace gm;
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            g_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                             \
+            return (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? GM_ERR_NO_DEVICE : GM_ERR_CUDA; \
+        }                                                                                           \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t s = nullptr) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = std::max(bytes, cap + cap / 2);
+        ncap = (ncap + 255) & ~size_t(255);
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) { e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; cudaStreamSynchronize(s); }
+        if (p) cudaFree(p);
+        p = np; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Ctrl {                       // device control block, zeroed before every match
+    unsigned long long cursor;
+    unsigned long long stats[4];
+    u32 slow_count;
+    u32 tile_counter;
+};
+
+// fast-path geometry: 32 topics per warp, 8 warps per CTA
+constexpr int K2_FAST_L = 8;
+constexpr int K2_POOL = 1536;
+constexpr int K2_STACK = 384;      // >= 64 + 32*FAST_L: the LIFO walk of 32 topics cannot overflow it
+constexpr int K2_WARPS = 8;
+using K2Smem = WarpSmem<K2_FAST_L, K2_POOL, K2_STACK>;
+
+}  // namespace
+
+struct gm_engine {
+    std::mutex mu;
+    int device = 0;
+    u32 flags = 0;
+    int num_sms = 0;
+    HostTrie trie;
+    cudaStream_t stream = nullptr;   // host-buffer matches
+    cudaStream_t side = nullptr;     // flush
+    cudaEvent_t ev_flush = nullptr, ev_match = nullptr, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool match_recorded = false;
+    // device tables
+    DevBuf d_edges, d_plus, d_ranges, d_values, d_dict, d_pool;
+    size_t up_plus = 0, up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
+    // scratch
+    DevBuf d_tok, d_meta, d_slow, d_ctrl, d_gstack, d_patch_idx, d_patch_data;
+    DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
+    u64 launches = 0;
+    float last_ms[3] = {0, 0, 0};
+    bool k2_attr_set = false;
+
+    explicit gm_engine(u32 max_levels) : trie(max_levels) {}
+
+    TrieView view() const {
+        TrieView v{};
+        v.edges = d_edges.as<EdgeSlot>(); v.plus = d_plus.as<PlusRec>(); v.ranges = d_ranges.as<Range>();
+        v.values = d_values.as<u32>(); v.dict = d_dict.as<DictSlot>(); v.pool = d_pool.as<u8>();
+        v.edge_mask = static_cast<u32>(trie.edges.size() - 1);
+        v.dict_mask = static_cast<u32>(trie.dict.size() - 1);
+        v.root_plus = trie.root_plus; v.root_hash_ref = trie.root_hash_ref; v.root_mask = trie.root_mask;
+        v.max_depth = trie.max_depth;
+        return v;
+    }
+
+    // ---- flush: ship the staged mutations to HBM on the side stream -------------------------------
+    // Scatter the listed (already final) host slots into the device copy of the table.
+    template <class T>
+    int patch_table(DevBuf& buf, const std::vector<T>& host, std::vector<u32>& dirty) {
+        std::sort(dirty.begin(), dirty.end());
+        dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
+        const u32 nd = static_cast<u32>(dirty.size());
+        if (nd == 0) return GM_OK;
+        std::vector<T> data(nd);
+        for (u32 i = 0; i < nd; ++i) data[i] = host[dirty[i]];
+        CUDA_TRY(d_patch_idx.ensure(nd * sizeof(u32)));
+        CUDA_TRY(d_patch_data.ensure(nd * sizeof(T)));
+        CUDA_TRY(cudaMemcpyAsync(d_patch_idx.p, dirty.data(), nd * sizeof(u32), cudaMemcpyHostToDevice, side));
+        CUDA_TRY(cudaMemcpyAsync(d_patch_data.p, data.data(), nd * sizeof(T), cudaMemcpyHostToDevice, side));
+        k_apply_patches<T><<<(nd + 255) / 256, 256, 0, side>>>(buf.as<T>(), d_patch_idx.as<u32>(), d_patch_data.as<T>(), nd);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(side));   // the staging vectors go out of scope
+        dirty.clear();
+        return GM_OK;
+    }
+
+    // Hash tables (edges, dict): whole-table copy after a re-hash or when most of it changed, else patches.
+    template <class Slot>
+    int upload_table(DevBuf& buf, const std::vector<Slot>& host, bool& full, std::vector<u32>& dirty, size_t& up_slots) {
+        const size_t bytes = host.size() * sizeof(Slot);
+        if (full || up_slots != host.size() || dirty.size() * 8 > host.size()) {
+            CUDA_TRY(buf.ensure(bytes));
+            CUDA_TRY(cudaMemcpyAsync(buf.p, host.data(), bytes, cudaMemcpyHostToDevice, side));
+            up_slots = host.size();
+            dirty.clear();
+        } else {
+            int st = patch_table(buf, host, dirty);
+            if (st != GM_OK) return st;
+        }
+        full = false;
+        return GM_OK;
+    }
+
+    // Append-only arrays (plus, ranges, values, pool): copy the new tail; patch older entries that changed.
+    template <class T>
+    int upload_appendable(DevBuf& buf, const std::vector<T>& host, size_t& up, std::vector<u32>* dirty) {
+        const size_t bytes = host.size() * sizeof(T);
+        if (bytes > buf.cap) {   // grow: re-ship the whole array from the mirror
+            CUDA_TRY(buf.ensure(std::max(bytes * 2, size_t(4096))));
+            up = 0;
+        }
+        const size_t before = up;
+        if (host.size() > up) {
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(buf.p) + up * sizeof(T), host.data() + up, (host.size() - up) * sizeof(T), cudaMemcpyHostToDevice, side));
+            up = host.size();
+        }
+        if (dirty) {
+            dirty->erase(std::remove_if(dirty->begin(), dirty->end(), [&](u32 i) { return i >= before; }), dirty->end());
+            int st = patch_table(buf, host, *dirty);
+            if (st != GM_OK) return st;
+            dirty->clear();
+        }
+        return GM_OK;
+    }
+
+    int flush_locked() {
+        if (flags & GM_FLAG_HOST_ONLY) { trie.sync(); return GM_OK; }
+        if (!trie.any_dirty()) return GM_OK;
+        CUDA_TRY(cudaSetDevice(device));
+        trie.sync();
+        if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(side, ev_match, 0));   // never patch under a running match
+        int st;
+        if ((st = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return st;
+        if ((st = upload_table(d_dict, trie.dict, trie.full_dict, trie.dirty_dict, up_dict_slots)) != GM_OK) return st;
+        if ((st = upload_appendable(d_plus, trie.plus, up_plus, &trie.dirty_plus)) != GM_OK) return st;
+        if ((st = upload_appendable(d_ranges, trie.ranges, up_ranges, &trie.dirty_ranges)) != GM_OK) return st;
+        if ((st = upload_appendable<u32>(d_values, trie.values, up_values, nullptr)) != GM_OK) return st;
+        if ((st = upload_appendable<u8>(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return st;
+        trie.root_dirty = false;
+        CUDA_TRY(cudaEventRecord(ev_flush, side));
+        CUDA_TRY(cudaStreamSynchronize(side));
+        return GM_OK;
+    }
+
+    // ---- the match pipeline, all on `s`, all buffers on the device ---------------------------------
+    int enqueue_match(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids,
+                      u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool timed) {
+        if (n == 0) { if (d_needed) CUDA_TRY(cudaMemsetAsync(d_needed, 0, sizeof(u64), s)); return GM_OK; }
+        if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
+        if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
+        const u32 n32 = static_cast<u32>(n);
+        const u32 S = std::max<u32>(1u, trie.max_depth);
+        CUDA_TRY(d_tok.ensure(static_cast<size_t>(S) * n32 * sizeof(u32)));
+        CUDA_TRY(d_meta.ensure(n32 * sizeof(u32)));
+        CUDA_TRY(d_slow.ensure(n32 * sizeof(u32)));
+        CUDA_TRY(d_ctrl.ensure(sizeof(Ctrl)));
+        const int k3_blocks = num_sms * 4;
+        const u32 stack_cap = 32u * (trie.max_depth + 2u) + 64u;
+        CUDA_TRY(d_gstack.ensure(static_cast<size_t>(k3_blocks) * 8 * stack_cap * sizeof(u64)));
+        if (!k2_attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(K2Smem) * K2_WARPS)));
+            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(K2Smem) * K2_WARPS)));
+            k2_attr_set = true;
+        }
+        CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
+        if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(s, ev_match, 0));   // scratch is shared: one match in flight
+        CUDA_TRY(cudaMemsetAsync(d_ctrl.p, 0, sizeof(Ctrl), s));
+        Ctrl* ctrl = d_ctrl.as<Ctrl>();
+        const TrieView tv = view();
+
+        if (timed) CUDA_TRY(cudaEventRecord(ev_t[0], s));
+        k_tokenize<<<(n32 + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
+            static_cast<const u8*>(d_blob_), d_offs_, n32, tv, S, d_tok.as<u32>(), d_meta.as<u32>(), d_status_);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(ev_t[1], s));
+
+        MatchParams mp{};
+        mp.tv = tv; mp.tok = d_tok.as<u32>(); mp.meta = d_meta.as<u32>(); mp.n = n32; mp.tok_levels = S;
+        mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = d_ids_; mp.cap_ids = cap_ids;
+        mp.cursor = &ctrl->cursor; mp.slow_list = d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
+        mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
+        const int k2_grid = num_sms * 2;
+        const size_t k2_smem = sizeof(K2Smem) * K2_WARPS;
+        if (stats) k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, true><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp);
+        else k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, false><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(ev_t[2], s));
+        if (stats) k_match_slow<true><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
+        else k_match_slow<false><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
+        CUDA_TRY(cudaGetLastError());
+        if (timed) CUDA_TRY(cudaEventRecord(ev_t[3], s));
+        launches += 3;
+        if (d_needed) CUDA_TRY(cudaMemcpyAsync(d_needed, &ctrl->cursor, sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaEventRecord(ev_match, s));
+        match_recorded = true;
+        return GM_OK;
+    }
+};
+
+// =====================================================================================================
+extern "C" {
+
+const char* gm_version(void) { return "libgpumqtt 0.1 (sm_100a)"; }
+const char* gm_last_error(gm_engine*) { return g_err.c_str(); }
+
+int32_t gm_create(const gm_config* cfg, gm_engine** out) {
+    if (!out) return GM_ERR_INVALID_ARG;
+    *out = nullptr;
+    gm_config c{};
+    c.struct_size = sizeof(gm_config); c.device = -1;
+    if (cfg) std::memcpy(&c, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(gm_config), sizeof(gm_config)));
+    if (c.flags & GM_FLAG_HOST_ONLY) {   // staging mirror only (tests, off-device shard preparation): nothing can match
+        gm_engine* eng = new gm_engine(c.max_levels ? c.max_levels : 128u);
+        eng->flags = c.flags;
+        eng->device = -1;
+        if (c.filters_hint) eng->trie.reserve(c.filters_hint);
+        *out = eng;
+        return GM_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_err = "no CUDA device: libgpumqtt has no CPU fallback"; return GM_ERR_NO_DEVICE; }
+    int dev = c.device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) { g_err = "device ordinal out of range"; return GM_ERR_INVALID_ARG; }
+    CUDA_TRY(cudaSetDevice(dev));
+    gm_engine* eng = new gm_engine(c.max_levels ? c.max_levels : 128u);
+    eng->device = dev;
+    eng->flags = c.flags;
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    eng->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_flush, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_match, cudaEventDisableTiming));
+    for (auto& ev : eng->ev_t) CUDA_TRY(cudaEventCreate(&ev));
+    CUDA_TRY(cudaEventRecord(eng->ev_flush, eng->side));
+    if (c.filters_hint) eng->trie.reserve(c.filters_hint);
+    *out = eng;
+    return GM_OK;
+}
+
+void gm_destroy(gm_engine* e) {
+    if (!e) return;
+    if (e->flags & GM_FLAG_HOST_ONLY) { delete e; return; }
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
+                      &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
+                      &e->d_spans, &e->d_ids, &e->d_status})
+        b->release();
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->side) cudaStreamDestroy(e->side);
+    if (e->ev_flush) cudaEventDestroy(e->ev_flush);
+    if (e->ev_match) cudaEventDestroy(e->ev_match);
+    for (auto& ev : e->ev_t) if (ev) cudaEventDestroy(ev);
+    delete e;
+}
+
+static int32_t map_parse(int st, const char* what) {
+    if (st == PARSE_OK) return GM_OK;
+    if (st == PARSE_TOO_DEEP) { g_err = std::string(what) + ": filter deeper than max_levels"; return GM_ERR_TOO_DEEP; }
+    g_err = std::string(what) + ": invalid topic filter";
+    return GM_ERR_INVALID_TOPIC;
+}
+
+int32_t gm_sub_add(gm_engine* e, const char* filter, uint32_t len, uint32_t value, int32_t* changed) {
+    if (!e || (!filter && len)) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    bool ch = false;
+    int st = e->trie.insert(filter, len, value, &ch);
+    if (changed) *changed = ch ? 1 : 0;
+    return map_parse(st, "gm_sub_add");
+}
+
+int32_t gm_sub_remove(gm_engine* e, const char* filter, uint32_t len, uint32_t value, int32_t* changed) {
+    if (!e || (!filter && len)) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    bool ch = false;
+    int st = e->trie.remove(filter, len, value, &ch);
+    if (changed) *changed = ch ? 1 : 0;
+    return map_parse(st, "gm_sub_remove");
+}
+
+int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets, const uint32_t* values, uint64_t n, uint64_t* n_changed) {
+    if (!e || (n && (!blob || !offsets || !values))) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->trie.reserve(n);
+    uint64_t ok = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        bool ch = false;
+        e->trie.insert(blob + offsets[i], offsets[i + 1] - offsets[i], values[i], &ch);
+        ok += ch;
+    }
+    if (n_changed) *n_changed = ok;
+    return GM_OK;
+}
+
+int32_t gm_flush(gm_engine* e) {
+    if (!e) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->flush_locked();
+}
+
+int32_t gm_match_batch_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
+                              gm_span* d_spans, uint32_t* d_ids, uint64_t cap_ids, uint64_t* d_needed, int32_t* d_status, void* stream) {
+    if (!e || (n && (!d_offs || !d_spans || !d_status))) return GM_ERR_INVALID_ARG;
+    if (blob_bytes > 0xFFFFFFFFull) { g_err = "topic blob >= 4 GiB"; return GM_ERR_TOO_LARGE; }
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    return e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, static_cast<cudaStream_t>(stream), false, false);
+}
+
+int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
+                                    gm_span* d_spans, uint32_t* d_ids, uint64_t cap_ids, uint64_t* d_needed, int32_t* d_status,
+                                    void* stream, gm_work* work) {
+    if (!e || !work || (n && (!d_offs || !d_spans || !d_status))) return GM_ERR_INVALID_ARG;
+    if (blob_bytes > 0xFFFFFFFFull) { g_err = "topic blob >= 4 GiB"; return GM_ERR_TOO_LARGE; }
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int st = e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, s, true, false);
+    if (st != GM_OK) return st;
+    std::memset(work, 0, sizeof(*work));
+    if (n == 0) return GM_OK;
+    Ctrl h{};
+    std::vector<u32> meta(n), offs(n + 1);
+    CUDA_TRY(cudaMemcpyAsync(&h, e->d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(meta.data(), e->d_meta.p, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(offs.data(), d_offs, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    work->visited = h.stats[0]; work->probed = h.stats[1]; work->filters = h.stats[2]; work->ids = h.stats[3];
+    work->deferred = h.slow_count;
+    for (uint64_t i = 0; i < n; ++i)
+        if (!(meta[i] & META_INVALID)) { work->levels += meta[i] & META_NLEV_MASK; work->bytes += offs[i + 1] - offs[i]; }
+    return GM_OK;
+}
+
+int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, uint32_t* out_ids,
+                       uint64_t cap_ids, uint64_t* needed, int32_t* status) {
+    if (!e || (n && (!offsets || !out_spans || !status)) || (cap_ids && !out_ids)) return GM_ERR_INVALID_ARG;
+    if (needed) *needed = 0;
+    if (n == 0) return GM_OK;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    const u64 blob_bytes = offsets[n];
+    cudaStream_t s = e->stream;
+    CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
+    CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
+    CUDA_TRY(e->d_spans.ensure(n * sizeof(gm_span)));
+    CUDA_TRY(e->d_status.ensure(n * sizeof(int32_t)));
+    CUDA_TRY(e->d_ids.ensure(std::max<u64>(cap_ids, 1) * sizeof(u32)));
+    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
+    int st = e->enqueue_match(e->d_blob.p, e->d_offs.as<u32>(), n, e->d_spans.as<gm_span>(), e->d_ids.as<u32>(), cap_ids, nullptr,
+                              e->d_status.as<int32_t>(), s, false, true);
+    if (st != GM_OK) return st;
+    u64 total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, &e->d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status, e->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_spans, e->d_spans.p, n * sizeof(gm_span), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev_t[k], e->ev_t[k + 1]);
+    if (needed) *needed = total;
+    for (uint64_t i = 0; i < n; ++i) if (status[i]) status[i] = GM_ERR_INVALID_TOPIC;
+    if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
+    if (total > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
+    if (total) {
+        CUDA_TRY(cudaMemcpyAsync(out_ids, e->d_ids.p, total * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return GM_OK;
+}
+
+int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, uint32_t max_tok, uint32_t* out_tokens, uint32_t* out_meta) {
+    if (!e || !max_tok || (n && (!offsets || !out_tokens || !out_meta))) return GM_ERR_INVALID_ARG;
+    if (n == 0) return GM_OK;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    cudaStream_t s = e->stream;
+    const u64 blob_bytes = offsets[n];
+    DevBuf tok, meta, stat;
+    CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
+    CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
+    CUDA_TRY(tok.ensure(static_cast<size_t>(max_tok) * n * sizeof(u32)));
+    CUDA_TRY(meta.ensure(n * sizeof(u32)));
+    CUDA_TRY(stat.ensure(n * sizeof(int)));
+    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(tok.p, 0, static_cast<size_t>(max_tok) * n * sizeof(u32), s));
+    CUDA_TRY(cudaStreamWaitEvent(s, e->ev_flush, 0));
+    k_tokenize<<<(static_cast<u32>(n) + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
+        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->view(), max_tok, tok.as<u32>(), meta.as<u32>(), stat.as<int>());
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_tokens, tok.p, static_cast<size_t>(max_tok) * n * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_meta, meta.p, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    tok.release(); meta.release(); stat.release();
+    return GM_OK;
+}
+
+int32_t gm_get_stats(gm_engine* e, gm_stats* out) {
+    if (!e || !out) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    std::memset(out, 0, sizeof(*out));
+    const HostTrie& t = e->trie;
+    out->values = t.values_size(); out->nodes = t.nodes_size(); out->device_nodes = t.node_count() - 1;
+    out->edges = t.edge_count(); out->edge_slots = t.edges.size();
+    out->dict_entries = t.dict_count(); out->dict_slots = t.dict.size();
+    out->plus_nodes = t.plus.size() - 1;
+    out->value_words = t.values.size(); out->garbage_value_words = t.garbage_values;
+    out->device_bytes = e->d_edges.cap + e->d_plus.cap + e->d_ranges.cap + e->d_values.cap + e->d_dict.cap + e->d_pool.cap;
+    out->max_depth = t.max_depth;
+    out->pending = t.any_dirty() ? 1 : 0;
+    return GM_OK;
+}
+
+int32_t gm_last_kernel_ms(gm_engine* e, float out_ms[3]) {
+    if (!e || !out_ms) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    for (int k = 0; k < 3; ++k) out_ms[k] = e->last_ms[k];
+    return GM_OK;
+}
+
+uint64_t gm_kernel_launches(gm_engine* e) { return e ? e->launches : 0; }
+
+int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t* count) {
+    if (!e || !ptr || !count) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->trie.sync();
+    const HostTrie& t = e->trie;
+    static thread_local uint32_t root[4];
+    switch (which) {
+        case 0: *ptr = t.edges.data(); *count = t.edges.size(); break;
+        case 1: *ptr = t.plus.data(); *count = t.plus.size(); break;
+        case 2: *ptr = t.ranges.data(); *count = t.ranges.size(); break;
+        case 3: *ptr = t.values.data(); *count = t.values.size(); break;
+        case 4: *ptr = t.dict.data(); *count = t.dict.size(); break;
+        case 5: *ptr = t.pool.data(); *count = t.pool.size(); break;
+        case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; *ptr = root; *count = 4; break;
+        default: return GM_ERR_INVALID_ARG;
+    }
+    return GM_OK;
+}
+
+uint32_t gm_shard_of(const char* s, uint32_t len, uint32_t n_shards) {
+    if (!s || n_shards == 0) return 0xFFFFFFFFu;
+    uint32_t l0 = 0;
+    while (l0 < len && s[l0] != '/') ++l0;
+    if (l0 == 1 && (s[0] == '+' || s[0] == '#')) return 0xFFFFFFFFu;
+    return shard_of_hash(HostTrie::level0_hash(s, len), n_shards);
+}
+
+void* gm_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void gm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// Host mirror of the device trie — see host_trie.h.  Mutation semantics follow
+// rmqtt/src/trie.rs:99-135 (insert / remove with bottom-up pruning) and the filter validation of
+// rmqtt/src/topic.rs:326-363 (Level::from_str, Topic::from_str, Topic::is_valid).
+#include "host_trie.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace gm {
+
+namespace {
+constexpr u32 NOSLOT = 0xFFFFFFFFu;
+
+inline u32 fnv(const char* s, u32 len) {
+    u32 h = FNV_INIT;
+    for (u32 i = 0; i < len; ++i) h = fnv_step(h, static_cast<u8>(s[i]));
+    return h;
+}
+
+inline bool dict_slot_equals(const DictSlot& d, const u8* pool, const char* s, u32 len, u32 h) {
+    const u8* b = reinterpret_cast<const u8*>(&d.w[1]);
+    if (len <= DICT_INLINE_MAX) return b[0] == len && std::memcmp(b + 1, s, len) == 0;
+    return b[0] == 0xFF && d.w[2] == len && d.w[4] == h && std::memcmp(pool + d.w[3], s, len) == 0;
+}
+}  // namespace
+
+HostTrie::HostTrie(u32 max_levels) : max_levels_(max_levels) {
+    edges.assign(1u << 10, EdgeSlot{});
+    dict.assign(1u << 10, DictSlot{});
+    plus.assign(1, PlusRec{});
+    ranges.assign(1, Range{0, 0});
+    nodes_.emplace_back();   // root = node 0
+    nodes_[0].alive = 1;
+}
+
+void HostTrie::reserve(u64 n_filters) {
+    // ~2.5 edges and ~0.15 new level strings per filter on IoT-shaped sets; tables keep load <= 0.5
+    u64 want_e = 1; while (want_e < n_filters * 6) want_e <<= 1;
+    u64 want_d = 1; while (want_d < n_filters / 2 + 1024) want_d <<= 1;
+    while (edges.size() < want_e && edges.size() < (1ull << 31)) grow_edges();
+    while (dict.size() < want_d && dict.size() < (1ull << 31)) grow_dict();
+    nodes_.reserve(nodes_.size() + n_filters * 3);
+}
+
+u32 HostTrie::level0_hash(const char* s, u32 len) {
+    u32 l0 = 0;
+    while (l0 < len && s[l0] != '/') ++l0;
+    return dict_hash_finish(fnv(s, l0), l0);
+}
+
+// ------------------------------------------------------------------------------- dictionary
+u32 HostTrie::lookup_token(const char* s, u32 len) const {
+    if (len == 0) return TOK_BLANK;
+    if (len == 1 && s[0] == '+') return TOK_PLUS;
+    if (len == 1 && s[0] == '#') return TOK_HASH;
+    u32 h = fnv(s, len);
+    u32 mask = static_cast<u32>(dict.size() - 1);
+    for (u32 i = dict_hash_finish(h, len) & mask;; i = (i + 1) & mask) {
+        const DictSlot& d = dict[i];
+        if (d.w[0] == 0) return TOK_UNKNOWN;
+        if (dict_slot_equals(d, pool.data(), s, len, h)) return d.w[0];
+    }
+}
+
+u32 HostTrie::intern(const char* s, u32 len, bool create) {
+    u32 t = lookup_token(s, len);
+    if (t != TOK_UNKNOWN || !create) return t;
+    if ((dict_count_ + 1) * 2 > dict.size()) grow_dict();
+    u32 h = fnv(s, len);
+    u32 mask = static_cast<u32>(dict.size() - 1);
+    u32 i = dict_hash_finish(h, len) & mask;
+    while (dict[i].w[0] != 0) i = (i + 1) & mask;
+    DictSlot d{};
+    d.w[0] = next_token_++;
+    u8* b = reinterpret_cast<u8*>(&d.w[1]);
+    if (len <= DICT_INLINE_MAX) {
+        b[0] = static_cast<u8>(len);
+        std::memcpy(b + 1, s, len);
+    } else {
+        b[0] = 0xFF;
+        d.w[2] = len;
+        d.w[3] = static_cast<u32>(pool.size());
+        d.w[4] = h;
+        pool.insert(pool.end(), s, s + len);
+        while (pool.size() % 16) pool.push_back(0);
+    }
+    dict[i] = d;
+    dict_count_++;
+    if (!full_dict) dirty_dict.push_back(i);
+    return d.w[0];
+}
+
+void HostTrie::grow_dict() {
+    std::vector<DictSlot> old;
+    old.swap(dict);
+    dict.assign(old.size() * 2, DictSlot{});
+    u32 mask = static_cast<u32>(dict.size() - 1);
+    for (const DictSlot& d : old) {
+        if (d.w[0] == 0) continue;
+        const u8* b = reinterpret_cast<const u8*>(&d.w[1]);
+        u32 len, h;
+        if (b[0] == 0xFF) { len = d.w[2]; h = d.w[4]; }
+        else { len = b[0]; h = fnv(reinterpret_cast<const char*>(b + 1), len); }
+        u32 i = dict_hash_finish(h, len) & mask;
+        while (dict[i].w[0] != 0) i = (i + 1) & mask;
+        dict[i] = d;
+    }
+    full_dict = true;
+    dirty_dict.clear();
+}
+
+// ------------------------------------------------------------------------------- edges
+u32 HostTrie::find_edge(u32 parent, u32 token) const {
+    u32 mask = static_cast<u32>(edges.size() - 1);
+    for (u32 i = edge_hash(parent, token) & mask;; i = (i + 1) & mask) {
+        const EdgeSlot& e = edges[i];
+        if (e.child == 0) return NOSLOT;
+        if (e.parent == parent && e.token == token) return i;
+    }
+}
+
+void HostTrie::grow_edges() {
+    std::vector<EdgeSlot> old;
+    old.swap(edges);
+    edges.assign(old.size() * 2, EdgeSlot{});
+    u32 mask = static_cast<u32>(edges.size() - 1);
+    for (const EdgeSlot& e : old) {
+        if (e.child == 0) continue;
+        u32 i = edge_hash(e.parent, e.token) & mask;
+        while (edges[i].child != 0) i = (i + 1) & mask;
+        edges[i] = e;
+        nodes_[e.child].edge_slot = i;
+    }
+    full_edges = true;
+    dirty_edges.clear();
+}
+
+u32 HostTrie::add_edge(u32 parent, u32 token) {
+    if ((edge_count_ + 1) * 2 > edges.size()) grow_edges();
+    u32 id = static_cast<u32>(nodes_.size());
+    nodes_.emplace_back();
+    HNode& n = nodes_.back();
+    n.parent = parent;
+    n.token = token;
+    u32 mask = static_cast<u32>(edges.size() - 1);
+    u32 i = edge_hash(parent, token) & mask;
+    while (edges[i].child != 0) i = (i + 1) & mask;
+    EdgeSlot e{};
+    e.parent = parent; e.token = token; e.child = id;
+    e.plus = 0; e.hash_ref = REF_NONE; e.own_ref = REF_NONE; e.mask = 0;
+    edges[i] = e;
+    n.edge_slot = i;
+    edge_count_++;
+    if (!full_edges) dirty_edges.push_back(i);
+    HNode& p = nodes_[parent];
+    p.mask |= mask_bit(token);
+    if (token == TOK_PLUS) {
+        n.plus_idx = static_cast<u32>(plus.size());
+        PlusRec r{};
+        r.node = id; r.plus = 0; r.hash_ref = REF_NONE; r.own_ref = REF_NONE; r.mask = 0;
+        plus.push_back(r);
+        p.plus_child = id;
+    } else if (token == TOK_HASH) {
+        p.hash_child = id;
+    }
+    mark(parent);
+    return id;
+}
+
+void HostTrie::mark(u32 node) {
+    if (!nodes_[node].dirty) { nodes_[node].dirty = 1; dirty_nodes_.push_back(node); }
+}
+
+// ------------------------------------------------------------------------------- parsing
+// Topic::from_str for a *filter*: split on '/', classify every level, validate (topic.rs:326-363,
+// :204-216).  Produces tokens; creates dictionary entries when intern_new.
+int HostTrie::parse(const char* f, u32 len, bool intern_new, std::vector<u32>& toks) {
+    toks.clear();
+    u32 start = 0;
+    for (;;) {
+        u32 end = start;
+        bool wild = false;
+        while (end < len && f[end] != '/') { wild |= (f[end] == '+' || f[end] == '#'); ++end; }
+        u32 l = end - start;
+        bool last = end >= len;
+        u32 tok;
+        if (l == 0) tok = TOK_BLANK;
+        else if (l == 1 && f[start] == '+') tok = TOK_PLUS;
+        else if (l == 1 && f[start] == '#') { if (!last) return PARSE_INVALID; tok = TOK_HASH; }
+        else if (wild) return PARSE_INVALID;
+        else {
+            if (f[start] == '$' && !toks.empty()) return PARSE_INVALID;   // Metadata only at level 0
+            tok = 0xFFFFFFFFu;  // resolved below, after the whole filter validated
+        }
+        toks.push_back(tok);
+        if (toks.size() > max_levels_) return PARSE_TOO_DEEP;
+        if (last) break;
+        start = end + 1;
+    }
+    // second pass: dictionary (only now, so an invalid filter never pollutes the dictionary)
+    start = 0;
+    for (size_t k = 0; k < toks.size(); ++k) {
+        u32 end = start;
+        while (end < len && f[end] != '/') ++end;
+        if (toks[k] == 0xFFFFFFFFu) toks[k] = intern(f + start, end - start, intern_new);
+        start = end + 1;
+    }
+    return PARSE_OK;
+}
+
+// ------------------------------------------------------------------------------- mutations
+int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed) {
+    if (changed) *changed = false;
+    int st = parse(filter, len, true, scratch_toks_);
+    if (st != PARSE_OK) return st;
+    u32 node = 0;
+    for (u32 tok : scratch_toks_) {
+        u32 slot = find_edge(node, tok);
+        node = (slot == NOSLOT) ? add_edge(node, tok) : edges[slot].child;
+    }
+    max_depth = std::max<u32>(max_depth, static_cast<u32>(scratch_toks_.size()));
+    HNode& n = nodes_[node];
+    bool ch = false;
+    if (n.nvals == 0) { n.v0 = value; n.nvals = 1; ch = true; }
+    else if (n.nvals == 1) {
+        if (n.v0 != value) {
+            std::vector<u32>& m = multi_[node];
+            m = {std::min(n.v0, value), std::max(n.v0, value)};
+            n.nvals = 2; ch = true;
+        }
+    } else {
+        std::vector<u32>& m = multi_[node];
+        auto it = std::lower_bound(m.begin(), m.end(), value);
+        if (it == m.end() || *it != value) { m.insert(it, value); n.nvals++; ch = true; }
+    }
+    if (ch) {
+        values_size_++;
+        mark(node);
+        if (n.token == TOK_HASH) mark(n.parent);
+        // revive pruned ancestors
+        for (u32 x = node; x != 0 && !nodes_[x].alive; x = nodes_[x].parent) {
+            nodes_[x].alive = 1;
+            nodes_[nodes_[x].parent].live_children++;
+            live_nodes_++;
+        }
+    } else {
+        // trie.rs:_insert creates the path even when the value was already present; the path exists
+        // and is alive in that case by construction (a present value keeps it alive).
+    }
+    if (changed) *changed = ch;
+    return PARSE_OK;
+}
+
+int HostTrie::remove(const char* filter, u32 len, u32 value, bool* changed) {
+    if (changed) *changed = false;
+    int st = parse(filter, len, false, scratch_toks_);
+    if (st != PARSE_OK) return st;
+    u32 node = 0;
+    for (u32 tok : scratch_toks_) {
+        if (tok == TOK_UNKNOWN) return PARSE_OK;
+        u32 slot = find_edge(node, tok);
+        if (slot == NOSLOT) return PARSE_OK;
+        node = edges[slot].child;
+        if (!nodes_[node].alive) return PARSE_OK;      // pruned in the reference: branches.get_mut -> None
+    }
+    HNode& n = nodes_[node];
+    bool ch = false;
+    if (n.nvals == 1) { if (n.v0 == value) { n.nvals = 0; ch = true; } }
+    else if (n.nvals > 1) {
+        std::vector<u32>& m = multi_[node];
+        auto it = std::lower_bound(m.begin(), m.end(), value);
+        if (it != m.end() && *it == value) {
+            m.erase(it); n.nvals--; ch = true;
+            if (n.nvals == 1) { n.v0 = m[0]; multi_.erase(node); }
+        }
+    }
+    if (ch) {
+        values_size_--;
+        mark(node);
+        if (n.token == TOK_HASH) mark(n.parent);
+    }
+    // bottom-up pruning (trie.rs:126-128): a node with no values and no children disappears
+    for (u32 x = node; x != 0; x = nodes_[x].parent) {
+        HNode& c = nodes_[x];
+        if (!(c.alive && c.nvals == 0 && c.live_children == 0)) break;
+        c.alive = 0;
+        nodes_[c.parent].live_children--;
+        live_nodes_--;
+    }
+    if (changed) *changed = ch;
+    return PARSE_OK;
+}
+
+// ------------------------------------------------------------------------------- publishing
+u32 HostTrie::make_ref(u32 node) {
+    HNode& n = nodes_[node];
+    u32 old = n.ref;
+    if (n.nvals == 0) {
+        if (old != REF_NONE && (old & REF_RANGE)) garbage_values += ranges[old & ~REF_RANGE].cnt;
+        return REF_NONE;
+    }
+    if (n.nvals == 1 && n.v0 < REF_RANGE) {
+        if (old != REF_NONE && (old & REF_RANGE)) garbage_values += ranges[old & ~REF_RANGE].cnt;
+        return n.v0;
+    }
+    u32 off = static_cast<u32>(values.size());
+    if (n.nvals == 1) values.push_back(n.v0);
+    else { const std::vector<u32>& m = multi_[node]; values.insert(values.end(), m.begin(), m.end()); }
+    u32 idx;
+    if (old != REF_NONE && (old & REF_RANGE)) {
+        idx = old & ~REF_RANGE;
+        garbage_values += ranges[idx].cnt;
+        dirty_ranges.push_back(idx);
+        ranges[idx] = Range{off, n.nvals};
+    } else {
+        idx = static_cast<u32>(ranges.size());
+        ranges.push_back(Range{off, n.nvals});
+    }
+    return REF_RANGE | idx;
+}
+
+void HostTrie::write_record(u32 node) {
+    const HNode& n = nodes_[node];
+    u32 plus_idx = n.plus_child ? nodes_[n.plus_child].plus_idx : 0;
+    u32 hash_ref = n.hash_child ? nodes_[n.hash_child].ref : REF_NONE;
+    if (node == 0) {
+        root_plus = plus_idx; root_hash_ref = hash_ref; root_mask = n.mask;
+        root_dirty = true;
+        return;
+    }
+    EdgeSlot& e = edges[n.edge_slot];
+    e.plus = plus_idx; e.hash_ref = hash_ref; e.own_ref = n.ref; e.mask = n.mask;
+    if (!full_edges) dirty_edges.push_back(n.edge_slot);
+    if (n.plus_idx) {
+        PlusRec& r = plus[n.plus_idx];
+        r.node = node; r.plus = plus_idx; r.hash_ref = hash_ref; r.own_ref = n.ref; r.mask = n.mask;
+        dirty_plus.push_back(n.plus_idx);
+    }
+}
+
+void HostTrie::sync() {
+    // pass 1: value-set references (a '#' node's parent reads the child's fresh ref in pass 2)
+    for (u32 id : dirty_nodes_) nodes_[id].ref = make_ref(id);
+    for (u32 id : dirty_nodes_) { write_record(id); nodes_[id].dirty = 0; }
+    dirty_nodes_.clear();
+}
+
+}  // namespace gm

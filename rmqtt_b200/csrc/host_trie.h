@@ -1,0 +1,98 @@
+// Host mirror of the device-resident subscription trie.
+//
+// Mutations (Router::add / Router::remove -> TopicTree::insert / remove, rmqtt/src/trie.rs:99-135,
+// rmqtt/src/router.rs:417-479) are applied here first: the host owns an exact copy of every device
+// table in the device layout (layout.h), remembers which 32-byte slots changed, and `flush` ships only
+// those slots to HBM on a side stream (engine.cu).  Nothing in this file is on the match path.
+#pragma once
+#include <cstddef>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "layout.h"
+
+namespace gm {
+
+struct HNode {
+    u32 parent = 0;
+    u32 token = 0;
+    u32 edge_slot = 0;       // slot in `edges` holding this node's record (non-root)
+    u32 plus_idx = 0;        // index in `plus` when this node is a '+' child, else 0
+    u32 plus_child = 0;      // node id of the '+' child (0 = none)
+    u32 hash_child = 0;      // node id of the '#' child (0 = none)
+    u32 nvals = 0;           // size of the value set (BTreeSet<V>)
+    u32 v0 = 0;              // the value when nvals == 1
+    u32 ref = REF_NONE;      // value-set reference currently published to the device
+    u32 live_children = 0;
+    u32 mask = 0;
+    u8 alive = 0;            // reference semantics: pruned nodes (trie.rs:126-128) are "not alive"
+    u8 dirty = 0;
+};
+
+enum ParseStatus { PARSE_OK = 0, PARSE_INVALID = 1, PARSE_TOO_DEEP = 2 };
+
+class HostTrie {
+  public:
+    explicit HostTrie(u32 max_levels);
+
+    // TopicTree::insert / remove.  Return ParseStatus; *changed mirrors the reference's bool.
+    int insert(const char* filter, u32 len, u32 value, bool* changed);
+    int remove(const char* filter, u32 len, u32 value, bool* changed);
+    void reserve(u64 n_filters);
+
+    // Resolve dirty nodes into slot patches (called by flush).
+    void sync();
+
+    // reference-visible statistics
+    u64 values_size() const { return values_size_; }   // trie.rs:148-151
+    u64 nodes_size() const { return live_nodes_; }     // trie.rs:154-157
+
+    // ---- device mirror -------------------------------------------------------------------------
+    std::vector<EdgeSlot> edges;
+    std::vector<PlusRec> plus;       // [0] reserved
+    std::vector<Range> ranges;       // [0] reserved
+    std::vector<u32> values;
+    std::vector<DictSlot> dict;
+    std::vector<u8> pool;
+    u32 root_plus = 0, root_hash_ref = REF_NONE, root_mask = 0;
+    u32 max_depth = 0;
+
+    // ---- dirty tracking (consumed and cleared by the engine's flush) ---------------------------
+    std::vector<u32> dirty_edges, dirty_plus, dirty_ranges, dirty_dict;
+    bool full_edges = true, full_dict = true;   // table re-hashed / never uploaded: ship whole table
+    bool any_dirty() const { return !dirty_nodes_.empty() || !dirty_edges.empty() || !dirty_plus.empty() ||
+                                    !dirty_ranges.empty() || !dirty_dict.empty() || full_edges || full_dict || root_dirty; }
+    bool root_dirty = true;
+    u64 garbage_values = 0;
+
+    u64 edge_count() const { return edge_count_; }
+    u64 dict_count() const { return dict_count_; }
+    u64 node_count() const { return nodes_.size(); }
+
+    // host-side tokeniser (tests compare the device tokeniser against it)
+    u32 lookup_token(const char* s, u32 len) const;
+    static u32 level0_hash(const char* s, u32 len);
+
+  private:
+    int parse(const char* f, u32 len, bool intern_new, std::vector<u32>& toks);
+    u32 intern(const char* s, u32 len, bool create);
+    u32 find_edge(u32 parent, u32 token) const;         // returns slot index or ~0u
+    u32 add_edge(u32 parent, u32 token);                // creates the child node, returns its id
+    void grow_edges();
+    void grow_dict();
+    void mark(u32 node);
+    u32 make_ref(u32 node);
+    void write_record(u32 node);
+
+    u32 max_levels_;
+    std::vector<HNode> nodes_;
+    std::unordered_map<u32, std::vector<u32>> multi_;   // node -> sorted values when nvals > 1
+    std::vector<u32> dirty_nodes_;
+    std::vector<u32> scratch_toks_;
+    u64 edge_count_ = 0, dict_count_ = 0;
+    u32 next_token_ = TOK_FIRST;
+    u64 values_size_ = 0, live_nodes_ = 0;
+};
+
+}  // namespace gm

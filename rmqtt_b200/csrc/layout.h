@@ -1,0 +1,113 @@
+// Data layout shared by the host mirror (host_trie.cpp) and the sm_100a kernels (kernels.cuh).
+//
+// The reference keeps the subscription trie as HashMap<Level, Node> per node with a BTreeSet<V> of
+// values (rmqtt/src/trie.rs:69-73).  Here the whole trie lives in HBM as four flat arrays:
+//
+//   dict   : open-addressing table  level string -> u32 token          (32-B slots, string inline)
+//   edges  : open-addressing table  (parent node, token) -> child + the child's *node record*
+//            (32-B slots; ONE 256-bit load answers "does the child exist, what are its values, its
+//             '#'-child values, its '+'-child, which tokens can continue below it")
+//   plus   : node records of '+' children, addressed by index (reached by pointer, not by hashing)
+//   ranges / values : value sets with >1 element (single values are stored inline in the record)
+//
+// A node record = {plus, hash_ref, own_ref, mask}:
+//   plus     index into `plus` of this node's '+' child (0 = none)            trie.rs:330-334
+//   hash_ref value-set reference of this node's '#' child (REF_NONE = none)    trie.rs:302-308,321-327
+//   own_ref  value-set reference of the node itself                            trie.rs:309-310
+//   mask     32-bit Bloom mask over the tokens of all children (skips hopeless literal probes)
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define GM_HD __host__ __device__ __forceinline__
+#else
+#define GM_HD inline
+#endif
+
+namespace gm {
+
+using u8 = uint8_t;
+using u32 = uint32_t;
+using u64 = uint64_t;
+
+// ---- tokens -----------------------------------------------------------------------------------
+constexpr u32 TOK_UNKNOWN = 0;  // level string not in the dictionary: no literal child can match
+constexpr u32 TOK_PLUS = 1;     // "+"  (Level::SingleWildcard)
+constexpr u32 TOK_HASH = 2;     // "#"  (Level::MultiWildcard)
+constexpr u32 TOK_BLANK = 3;    // ""   (Level::Blank)
+constexpr u32 TOK_FIRST = 4;    // first dictionary-assigned token
+
+// ---- value-set references -----------------------------------------------------------------------
+constexpr u32 REF_NONE = 0xFFFFFFFFu;   // empty set
+constexpr u32 REF_RANGE = 0x80000000u;  // bit set: low 31 bits index `ranges`; clear: the single value itself
+
+struct alignas(32) EdgeSlot {
+    u32 parent;    // key
+    u32 token;     // key
+    u32 child;     // node id of the child; 0 = empty slot (node ids start at 1, the root is 0)
+    u32 plus;      // record of `child` ...
+    u32 hash_ref;
+    u32 own_ref;
+    u32 mask;
+    u32 aux;       // reserved
+};
+static_assert(sizeof(EdgeSlot) == 32, "EdgeSlot must be one 32-byte sector");
+
+struct alignas(32) PlusRec {
+    u32 node;      // node id of this '+' node (key for probing its literal children)
+    u32 plus;
+    u32 hash_ref;
+    u32 own_ref;
+    u32 mask;
+    u32 pad[3];
+};
+static_assert(sizeof(PlusRec) == 32, "PlusRec must be one 32-byte sector");
+
+// Dictionary slot: w[0] = token (0 = empty).  Bytes 4..31: byte 4 = length (0..27) followed by the
+// string, zero padded; or byte 4 = 0xFF for a long string: w[2] = length, w[3] = offset into the
+// long-string pool, w[4] = 32-bit hash.
+struct alignas(32) DictSlot {
+    u32 w[8];
+};
+static_assert(sizeof(DictSlot) == 32, "DictSlot must be one 32-byte sector");
+constexpr u32 DICT_INLINE_MAX = 27;
+
+struct Range { u32 off, cnt; };
+
+// Root record + table geometry handed to every kernel by value.
+struct TrieView {
+    const EdgeSlot* edges;
+    const PlusRec* plus;
+    const Range* ranges;
+    const u32* values;
+    const DictSlot* dict;
+    const u8* pool;
+    u32 edge_mask;      // capacity-1 (capacity is a power of two)
+    u32 dict_mask;
+    u32 root_plus, root_hash_ref, root_mask;
+    u32 max_depth;      // deepest filter in the trie (levels)
+};
+
+// Per-topic word written by the tokeniser: bits 0..23 level count, bit 30 level 0 is Metadata ('$...'),
+// bit 31 Topic::from_str would fail (topic.rs:348-363) -> the topic matches nothing.
+constexpr u32 META_INVALID = 0x80000000u;
+constexpr u32 META_DOLLAR = 0x40000000u;
+constexpr u32 META_NLEV_MASK = 0x00FFFFFFu;
+
+// ---- hashing (identical on host and device) -----------------------------------------------------
+GM_HD u32 fmix32(u32 h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+GM_HD u32 edge_hash(u32 parent, u32 token) {
+    return fmix32(parent * 0x9E3779B1u + (token ^ 0x7F4A7C15u) * 0x85EBCA77u);
+}
+constexpr u32 FNV_INIT = 0x811C9DC5u;
+GM_HD u32 fnv_step(u32 h, u32 byte) { return (h ^ byte) * 0x01000193u; }
+GM_HD u32 dict_hash_finish(u32 h, u32 len) { return fmix32(h ^ (len * 0x9E3779B1u)); }
+GM_HD u32 mask_bit(u32 token) { return 1u << ((token * 0x9E3779B1u) >> 27); }
+
+// Shard of a level-0 string (multi-GPU partitioning by topic root).
+GM_HD u32 shard_of_hash(u32 h, u32 nshards) { return static_cast<u32>((static_cast<u64>(fmix32(h ^ 0x5bd1e995u)) * nshards) >> 32); }
+
+}  // namespace gm

@@ -1,0 +1,210 @@
+"""Host-side handle over the C ABI (include/gpumqtt.h).
+
+`Engine` is the Python face of one `gm_engine`: the device-resident subscription trie with the
+`TopicTree<u32>` operations of the reference (`insert` / `remove` / `matches`,
+rmqtt/src/trie.rs:99-145) applied to whole batches.  Everything that matches runs in the CUDA
+library; if libgpumqtt.so or a CUDA device is missing the calls raise — there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class GpuMqttError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libgpumqtt error {code}: {msg}")
+        self.code = code
+
+
+def _b(s) -> bytes:
+    return s if isinstance(s, (bytes, bytearray)) else s.encode("utf-8")
+
+
+def _vp(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pack(strings):
+    """list[str|bytes] -> (blob uint8[], offsets uint32[n+1])"""
+    bs = [_b(s) for s in strings]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint32)
+    if bs:
+        offs[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64).astype(np.uint32)
+    blob = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    return blob, offs
+
+
+class MatchResult:
+    """Per-topic match lists: topic i -> ids[spans[i,0] : spans[i,0]+spans[i,1]] (multiset, unordered)."""
+
+    def __init__(self, spans: np.ndarray, ids: np.ndarray, status: np.ndarray, needed: int):
+        self.spans, self.ids, self.status, self.needed = spans, ids, status, needed
+
+    def __len__(self):
+        return len(self.spans)
+
+    def sorted_list(self, i: int):
+        """Sorted multiset of topic i, or None if the topic is invalid (reference: Err)."""
+        if self.status[i] != 0:
+            return None
+        off, cnt = int(self.spans[i, 0]), int(self.spans[i, 1])
+        return sorted(self.ids[off:off + cnt].tolist())
+
+    def counts(self) -> np.ndarray:
+        c = self.spans[:, 1].astype(np.int64)
+        c[self.status != 0] = -1
+        return c
+
+    def canonical(self):
+        """(counts int64[n] with -1 for invalid, ids sorted within each topic, concatenated in topic order)."""
+        counts = self.counts()
+        n = len(counts)
+        pos = np.maximum(counts, 0)
+        starts = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(pos, out=starts[1:])
+        total = int(starts[-1])
+        if total == 0:
+            return counts, np.zeros(0, dtype=np.uint32)
+        # gather each topic's ids into topic order, then sort within segments via a (segment, id) lexsort
+        seg = np.repeat(np.arange(n, dtype=np.int64), pos)
+        within = np.arange(total, dtype=np.int64) - np.repeat(starts[:-1], pos)
+        src = np.repeat(self.spans[:, 0].astype(np.int64), pos) + within
+        vals = self.ids[src]
+        order = np.lexsort((vals, seg))
+        return counts, vals[order]
+
+
+class Engine:
+    def __init__(self, device: int = -1, max_levels: int = 0, manual_flush: bool = False, filters_hint: int = 0,
+                 host_only: bool = False):
+        self._lib = N.lib()
+        flags = (N.GM_FLAG_MANUAL_FLUSH if manual_flush else 0) | (N.GM_FLAG_HOST_ONLY if host_only else 0)
+        cfg = N.GmConfig(C.sizeof(N.GmConfig), device, max_levels, flags, filters_hint)
+        h = C.c_void_p()
+        rc = self._lib.gm_create(C.byref(cfg), C.byref(h))
+        if rc != N.GM_OK:
+            raise GpuMqttError(rc, self._lib.gm_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != N.GM_OK:
+            raise GpuMqttError(rc, self._lib.gm_last_error(self._h).decode())
+
+    # ---- TopicTree::insert / remove ---------------------------------------------------------------
+    def add(self, filt, value: int) -> bool:
+        b = _b(filt)
+        ch = C.c_int32(0)
+        self._check(self._lib.gm_sub_add(self._h, b, len(b), value, C.byref(ch)))
+        return bool(ch.value)
+
+    def remove(self, filt, value: int) -> bool:
+        b = _b(filt)
+        ch = C.c_int32(0)
+        self._check(self._lib.gm_sub_remove(self._h, b, len(b), value, C.byref(ch)))
+        return bool(ch.value)
+
+    def bulk_load(self, blob: np.ndarray, offs: np.ndarray, values: np.ndarray) -> int:
+        assert blob.dtype == np.uint8 and offs.dtype == np.uint32 and values.dtype == np.uint32
+        n_changed = C.c_uint64(0)
+        self._check(self._lib.gm_bulk_load(self._h, _vp(blob), _vp(offs), _vp(values), len(values), C.byref(n_changed)))
+        return int(n_changed.value)
+
+    def flush(self):
+        self._check(self._lib.gm_flush(self._h))
+
+    # ---- Router::matches for a batch (host buffers) ---------------------------------------------------
+    def match_batch(self, blob: np.ndarray, offs: np.ndarray, cap_ids: int | None = None) -> MatchResult:
+        assert blob.dtype == np.uint8 and offs.dtype == np.uint32
+        n = len(offs) - 1
+        spans = np.zeros((n, 2), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        cap = int(cap_ids) if cap_ids is not None else max(1024, 32 * n)
+        while True:
+            ids = np.empty(cap, dtype=np.uint32)
+            needed = C.c_uint64(0)
+            rc = self._lib.gm_match_batch(self._h, _vp(blob), _vp(offs), n, _vp(spans), _vp(ids), cap, C.byref(needed), _vp(status))
+            if rc == N.GM_ERR_CAPACITY and cap_ids is None:
+                cap = int(needed.value)
+                continue
+            self._check(rc)
+            return MatchResult(spans, ids[:int(needed.value)], status, int(needed.value))
+
+    def match_topics(self, topics, cap_ids: int | None = None) -> MatchResult:
+        blob, offs = pack(topics)
+        return self.match_batch(blob, offs, cap_ids)
+
+    def matches(self, topic):
+        """TopicTree::matches for one topic -> sorted multiset (None if invalid)."""
+        return self.match_topics([topic]).sorted_list(0)
+
+    # ---- device-resident variant (torch tensors; asynchronous on the current torch stream) -----------
+    def match_batch_device(self, d_blob, d_offs, d_spans, d_ids, d_needed, d_status, stream: int, work: bool = False):
+        n = d_offs.numel() - 1
+        args = [self._h, d_blob.data_ptr(), d_blob.numel(), d_offs.data_ptr(), n, d_spans.data_ptr(), d_ids.data_ptr(),
+                d_ids.numel(), d_needed.data_ptr(), d_status.data_ptr(), stream]
+        if work:
+            w = N.GmWork()
+            self._check(self._lib.gm_match_batch_device_stats(*args, C.byref(w)))
+            return w.as_dict()
+        self._check(self._lib.gm_match_batch_device(*args))
+        return None
+
+    # ---- tokeniser hook -------------------------------------------------------------------------------
+    def tokenize(self, topics, max_tok: int = 16):
+        blob, offs = pack(topics)
+        n = len(offs) - 1
+        toks = np.zeros((max_tok, n), dtype=np.uint32)
+        meta = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.gm_tokenize_batch(self._h, _vp(blob), _vp(offs), n, max_tok, _vp(toks), _vp(meta)))
+        return toks, meta
+
+    # ---- introspection -----------------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = N.GmStats()
+        self._check(self._lib.gm_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def debug_tables(self) -> dict:
+        """Host mirror of the device tables as numpy arrays (copies).  Test/diagnostic use only."""
+        out = {}
+        spec = {0: ("edges", np.uint32, 8), 1: ("plus", np.uint32, 8), 2: ("ranges", np.uint32, 2), 3: ("values", np.uint32, 1),
+                4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1)}
+        for which, (name, dt, width) in spec.items():
+            ptr, cnt = C.c_void_p(), C.c_uint64(0)
+            self._check(self._lib.gm_debug_table(self._h, which, C.byref(ptr), C.byref(cnt)))
+            n = int(cnt.value) * width
+            if n == 0:
+                out[name] = np.zeros((0, width) if width > 1 else 0, dtype=dt)
+                continue
+            buf = (C.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(ptr.value)
+            a = np.frombuffer(buf, dtype=dt).copy()
+            out[name] = a.reshape(-1, width) if width > 1 else a
+        return out
+
+    def last_kernel_ms(self):
+        a = (C.c_float * 3)()
+        self._check(self._lib.gm_last_kernel_ms(self._h, C.byref(a)))
+        return [float(x) for x in a]
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.gm_kernel_launches(self._h))
+
+
+def shard_of(topic_or_filter, n_shards: int) -> int:
+    b = _b(topic_or_filter)
+    return int(N.lib().gm_shard_of(b, len(b), n_shards))

@@ -1,0 +1,132 @@
+"""TEST-ONLY model of what the CUDA kernels do with the device tables (rmqtt_b200/csrc/kernels.cuh),
+written as slow pure Python over the host mirror exported by gm_debug_table.  It lets the CPU test
+tier check the host-side trie builder (host_trie.cpp) and the table layout (layout.h) against the
+oracle without a GPU.  It is not importable from the product package and matches nothing at run time.
+"""
+import numpy as np
+
+M32 = 0xFFFFFFFF
+REF_NONE, REF_RANGE = 0xFFFFFFFF, 0x80000000
+TOK_UNKNOWN, TOK_PLUS, TOK_HASH, TOK_BLANK = 0, 1, 2, 3
+
+
+def fmix32(h):
+    h ^= h >> 16; h = (h * 0x85EBCA6B) & M32; h ^= h >> 13; h = (h * 0xC2B2AE35) & M32; h ^= h >> 16
+    return h
+
+
+def edge_hash(parent, token):
+    return fmix32((parent * 0x9E3779B1 + ((token ^ 0x7F4A7C15) * 0x85EBCA77)) & M32)
+
+
+def fnv(b):
+    h = 0x811C9DC5
+    for c in b:
+        h = ((h ^ c) * 0x01000193) & M32
+    return h
+
+
+def dict_hash(b):
+    return fmix32(fnv(b) ^ ((len(b) * 0x9E3779B1) & M32))
+
+
+def mask_bit(tok):
+    return 1 << (((tok * 0x9E3779B1) & M32) >> 27)
+
+
+class Tables:
+    def __init__(self, t):
+        self.edges, self.plus, self.ranges, self.values = t["edges"], t["plus"], t["ranges"], t["values"]
+        self.dict, self.pool = t["dict"], t["pool"]
+        self.root_plus, self.root_hash_ref, self.root_mask, self.max_depth = (int(x) for x in t["root"])
+        self.dict_bytes = self.dict.view(np.uint8).reshape(len(self.dict), 32)
+
+    def token(self, lv: bytes):
+        if lv == b"":
+            return TOK_BLANK
+        if lv == b"+":
+            return TOK_PLUS
+        if lv == b"#":
+            return TOK_HASH
+        mask = len(self.dict) - 1
+        i = dict_hash(lv) & mask
+        while True:
+            tok = int(self.dict[i, 0])
+            if tok == 0:
+                return TOK_UNKNOWN
+            row = self.dict_bytes[i]
+            if len(lv) <= 27:
+                if row[4] == len(lv) and bytes(row[5:5 + len(lv)]) == lv:
+                    return tok
+            elif row[4] == 0xFF and int(self.dict[i, 2]) == len(lv) and int(self.dict[i, 4]) == fnv(lv):
+                off = int(self.dict[i, 3])
+                if bytes(self.pool[off:off + len(lv)]) == lv:
+                    return tok
+            i = (i + 1) & mask
+
+    def tokenize(self, topic: bytes):
+        """-> (tokens, dollar) or None if invalid (mirrors k_tokenize)."""
+        toks, dollar = [], False
+        levels = topic.split(b"/")
+        for k, lv in enumerate(levels):
+            last = k == len(levels) - 1
+            if lv == b"#" and not last:
+                return None
+            if lv not in (b"+", b"#") and (b"+" in lv or b"#" in lv):
+                return None
+            if lv[:1] == b"$":
+                if k > 0:
+                    return None
+                dollar = True
+            toks.append(self.token(lv))
+        return toks, dollar
+
+    def probe(self, parent, tok):
+        mask = len(self.edges) - 1
+        i = edge_hash(parent, tok) & mask
+        while True:
+            e = self.edges[i]
+            if e[2] == 0:
+                return None
+            if e[0] == parent and e[1] == tok:
+                return dict(node=int(e[2]), plus=int(e[3]), hash_ref=int(e[4]), own_ref=int(e[5]), mask=int(e[6]))
+            i = (i + 1) & mask
+
+    def expand(self, ref, out):
+        if ref == REF_NONE:
+            return 0
+        if not ref & REF_RANGE:
+            out.append(ref)
+            return 1
+        off, cnt = (int(x) for x in self.ranges[ref & ~REF_RANGE & M32])
+        out.extend(int(v) for v in self.values[off:off + cnt])
+        return 1
+
+    def match(self, topic: bytes):
+        """-> (sorted ids, counters dict) or (None, None)."""
+        tk = self.tokenize(topic)
+        if tk is None:
+            return None, None
+        toks, dollar = tk
+        L = len(toks)
+        out = []
+        V = E = F = 0
+        stack = [(dict(node=0, plus=self.root_plus, hash_ref=self.root_hash_ref, own_ref=REF_NONE, mask=self.root_mask), 0, dollar)]
+        while stack:
+            r, d, dollar_root = stack.pop()
+            V += 1
+            if not dollar_root:
+                F += self.expand(r["hash_ref"], out)
+            if d == L:
+                F += self.expand(r["own_ref"], out)
+                continue
+            E += 1
+            if r["plus"] and not dollar_root:
+                p = self.plus[r["plus"]]
+                stack.append((dict(node=int(p[0]), plus=int(p[1]), hash_ref=int(p[2]), own_ref=int(p[3]), mask=int(p[4])), d + 1, False))
+            t = toks[d]
+            if t != TOK_UNKNOWN and r["mask"] & mask_bit(t):
+                c = self.probe(r["node"], t)
+                if c is not None:
+                    stack.append((c, d + 1, False))
+        return sorted(out), dict(V=V, E=E, F=F, M=len(out), L=L, B=len(topic))

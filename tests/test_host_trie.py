@@ -1,0 +1,100 @@
+"""CPU tier: the host-side trie builder (rmqtt_b200/csrc/host_trie.cpp) and the device table layout,
+checked against the oracle through a pure-Python model of the kernels' walk (tests/_tablewalk.py)."""
+import random
+
+import pytest
+
+from oracle import oracle as orc
+from rmqtt_b200.engine import Engine, GpuMqttError
+from rmqtt_b200 import _native as N
+
+from _gen import rand_filter, rand_topic
+from _tablewalk import Tables
+
+
+def _apply(eng, tree, f, v, op):
+    try:
+        got = eng.add(f, v) if op == "add" else eng.remove(f, v)
+    except GpuMqttError as ex:
+        assert ex.code == N.GM_ERR_INVALID_TOPIC
+        with pytest.raises(ValueError):
+            tree.insert(f, v) if op == "add" else tree.remove(f, v)
+        return
+    want = tree.insert(f, v) if op == "add" else tree.remove(f, v)
+    assert got == want, (op, f, v)
+
+
+def test_golden_through_tables(golden):
+    for key in ("trie_A1",):
+        g = golden[key]
+        eng, tree = Engine(host_only=True), orc.TopicTree()
+        for f, v in g["inserts"]:
+            _apply(eng, tree, f, v, "add")
+        T = Tables(eng.debug_tables())
+        for topic, want in g["matches"]:
+            assert T.match(topic.encode())[0] == sorted(want), topic
+        for f, v, want in g["removes"]:
+            assert eng.remove(f, v) is want
+        T = Tables(eng.debug_tables())
+        for topic, want in g["after_remove_matches"]:
+            assert T.match(topic.encode())[0] == sorted(want), topic
+    g = golden["derived_A5"]["trie"]
+    eng = Engine(host_only=True)
+    for f, v in g["inserts"]:
+        eng.add(f, v)
+    T = Tables(eng.debug_tables())
+    for topic, want in g["matches"]:
+        assert T.match(topic.encode())[0] == sorted(want), topic
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_differential_tables_vs_oracle(seed):
+    rng = random.Random(seed)
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    live = []
+    for step in range(600):
+        if live and rng.random() < 0.3:
+            f, v = rng.choice(live)
+            if rng.random() < 0.3:
+                v = rng.randint(0, 5)
+            _apply(eng, tree, f, v, "remove")
+        else:
+            f, v = rand_filter(rng), rng.choice([0, 1, 2, 3, 7, 2**31 + 5, 2**32 - 1, rng.randint(0, 50)])
+            _apply(eng, tree, f, v, "add")
+            live.append((f, v))
+        if step % 150 == 149:
+            st = eng.stats()
+            assert st["values"] == tree.values_size()
+            assert st["nodes"] == tree.nodes_size()
+            T = Tables(eng.debug_tables())
+            for _ in range(150):
+                t = rand_topic(rng)
+                got, ctr = T.match(t.encode())
+                want, wctr = tree.matches(t, with_counters=True)
+                assert got == want, t
+                if want is not None:
+                    # counters of the table walk equal the reference walk's, except that the device keeps pruned
+                    # (dead) nodes and skips probes through the Bloom mask: V/E may differ, F and M never do.
+                    assert (ctr["F"], ctr["M"], ctr["L"], ctr["B"]) == (wctr["F"], wctr["M"], wctr["L"], wctr["B"])
+
+
+def test_many_values_one_filter_and_growth():
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    for v in range(1, 3000):
+        assert eng.add("/iot/x", v) == tree.insert("/iot/x", v)
+        assert eng.add(f"/iot/{v}", v) == tree.insert(f"/iot/{v}", v)
+    eng.add("/iot/#", 3); tree.insert("/iot/#", 3)
+    T = Tables(eng.debug_tables())
+    assert T.match(b"/iot/x")[0] == tree.matches("/iot/x")
+    assert T.match(b"/iot/17")[0] == tree.matches("/iot/17") == [3, 17]
+    st = eng.stats()
+    assert st["values"] == tree.values_size() and st["nodes"] == tree.nodes_size()
+    assert st["edge_slots"] >= 2 * st["edges"]          # load factor <= 0.5 after growth
+
+
+def test_too_deep_filter_is_rejected():
+    eng = Engine(host_only=True, max_levels=4)
+    assert eng.add("a/b/c/d", 1)
+    with pytest.raises(GpuMqttError) as ei:
+        eng.add("a/b/c/d/e", 1)
+    assert ei.value.code == N.GM_ERR_TOO_DEEP

@@ -1,0 +1,41 @@
+"""CPU tier: the deterministic iot6 generator."""
+import numpy as np
+
+from rmqtt_b200 import workload as wl
+
+
+def test_deterministic_and_order_free():
+    a = wl.unpack(*wl.gen_subs(wl.C3, 1000)[:2])
+    b = wl.unpack(*wl.gen_subs(wl.C3, 500, first=500)[:2])
+    assert a[500:] == b
+    assert a == wl.unpack(*wl.gen_subs(wl.C3, 1000)[:2])
+
+
+def test_mix_fractions():
+    subs = wl.unpack(*wl.gen_subs(wl.C3, 200_000)[:2])
+    plus = sum(b"+" in s for s in subs) / len(subs)
+    hsh = sum(s.endswith(b"#") for s in subs) / len(subs)
+    root_plus = sum(s.startswith(b"+/") for s in subs) / len(subs)
+    assert abs(plus - 0.30) < 0.01 and abs(hsh - 0.05) < 0.005
+    assert abs(root_plus - 0.30 * 0.02) < 0.002
+    assert all(s.count(b"/") == 5 for s in subs if not s.endswith(b"#"))
+
+
+def test_c1_has_no_wildcards_and_half_hits():
+    subs = set(wl.unpack(*wl.gen_subs(wl.C1)[:2]))
+    assert not any(b"+" in s or b"#" in s for s in subs)
+    topics = wl.unpack(*wl.gen_topics(wl.C1))
+    assert len(topics) == 10_000
+    hit = sum(t in subs for t in topics) / len(topics)
+    assert 0.5 < hit < 0.9
+
+
+def test_retained_topics_are_distinct():
+    t = wl.unpack(*wl.gen_retained(wl.C4, 100_000)[:2])
+    assert len(set(t)) == len(t)
+
+
+def test_region_restriction():
+    b, o = wl.gen_topics(wl.C3, 2000, regions=[3, 9])
+    names = {t.split(b"/")[0] for t in wl.unpack(b, o)}
+    assert names == {wl.region_name(3), wl.region_name(9)}
