@@ -128,8 +128,10 @@ int32_t gm_tokenize_batch(gm_engine* e, const char* topics_blob, const uint32_t*
 
 /* ---- misc ------------------------------------------------------------------------------------------- */
 int32_t gm_get_stats(gm_engine* e, gm_stats* out);
-/* device time (ms) of the kernels of the last gm_match_batch call: [0]=tokenise [1]=match [2]=deferred */
-int32_t gm_last_kernel_ms(gm_engine* e, float out_ms[3]);
+/* device time (ms) of the three kernels — [0] tokenise [1] match [2] deferred — of the last <= 64 match calls
+ * (either entry point), oldest first, measured with CUDA events on the stream the kernels ran on.
+ * out_ms holds 3*max_calls floats; *n_calls receives how many calls were written.  Synchronises on them. */
+int32_t gm_kernel_ms_ring(gm_engine* e, float* out_ms, uint32_t max_calls, uint32_t* n_calls);
 /* number of kernels the engine has launched since creation */
 uint64_t gm_kernel_launches(gm_engine* e);
 /* shard of a topic / filter by its level-0 string (multi-GPU root-hash partitioning); 0xFFFFFFFF for a
@@ -137,7 +139,7 @@ uint64_t gm_kernel_launches(gm_engine* e);
 uint32_t gm_shard_of(const char* topic_or_filter, uint32_t len, uint32_t n_shards);
 /* DEBUG/TEST: read-only view of the host mirror of a device table, in device layout (rmqtt_b200/csrc/layout.h).
  * which: 0 edges(32 B) 1 plus(32 B) 2 ranges(8 B) 3 values(4 B) 4 dict(32 B) 5 long-string pool(1 B)
- *        6 root record {plus, hash_ref, mask, max_depth}.  Valid until the next mutating call.           */
+ *        6 root record {plus, hash_ref, mask, max_depth, hash_cnt}.  Valid until the next mutating call.           */
 int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t* count);
 /* pinned host memory for the host-buffer entry points */
 void* gm_host_alloc(uint64_t bytes);

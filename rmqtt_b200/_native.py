@@ -59,7 +59,7 @@ SIGNATURES = {
     "gm_match_batch_device_stats": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp, _P(GmWork)]),
     "gm_tokenize_batch": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gm_get_stats": (_i32, [_vp, _P(GmStats)]),
-    "gm_last_kernel_ms": (_i32, [_vp, _P(C.c_float * 3)]),
+    "gm_kernel_ms_ring": (_i32, [_vp, _vp, _u32, _P(_u32)]),
     "gm_kernel_launches": (_u64, [_vp]),
     "gm_shard_of": (_u32, [_cp, _u32, _u32]),
     "gm_debug_table": (_i32, [_vp, _u32, _P(_vp), _P(_u64)]),

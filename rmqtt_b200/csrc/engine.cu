@@ -55,12 +55,13 @@ struct Ctrl {                       // device control block, zeroed before every
     u32 tile_counter;
 };
 
-// fast-path geometry: 32 topics per warp, 8 warps per CTA
+// fast-path geometry: 32 topics per warp, 16 warps per CTA, 3 CTAs per SM
 constexpr int K2_FAST_L = 8;
-constexpr int K2_POOL = 1536;
 constexpr int K2_STACK = 384;      // >= 64 + 32*FAST_L: the LIFO walk of 32 topics cannot overflow it
-constexpr int K2_WARPS = 8;
-using K2Smem = WarpSmem<K2_FAST_L, K2_POOL, K2_STACK>;
+constexpr int K2_WARPS = 16;
+constexpr int K2_CTAS_PER_SM = 3;
+constexpr u32 K2_POOL = 1024;      // descriptors (matched value sets) per warp tile before topics are deferred
+using K2Smem = WarpSmem<K2_FAST_L, K2_STACK>;
 
 }  // namespace
 
@@ -72,16 +73,18 @@ struct gm_engine {
     HostTrie trie;
     cudaStream_t stream = nullptr;   // host-buffer matches
     cudaStream_t side = nullptr;     // flush
-    cudaEvent_t ev_flush = nullptr, ev_match = nullptr, ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int RING = 64;   // per-kernel timing events of the last RING match calls
+    cudaEvent_t ev_flush = nullptr, ev_match = nullptr;
+    cudaEvent_t ev_ring[RING][4] = {};
+    u64 ring_n = 0;
     bool match_recorded = false;
     // device tables
     DevBuf d_edges, d_plus, d_ranges, d_values, d_dict, d_pool;
     size_t up_plus = 0, up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
     // scratch
-    DevBuf d_tok, d_meta, d_slow, d_ctrl, d_gstack, d_patch_idx, d_patch_data;
+    DevBuf d_tok, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data;
     DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
     u64 launches = 0;
-    float last_ms[3] = {0, 0, 0};
     bool k2_attr_set = false;
 
     explicit gm_engine(u32 max_levels) : trie(max_levels) {}
@@ -92,7 +95,7 @@ struct gm_engine {
         v.values = d_values.as<u32>(); v.dict = d_dict.as<DictSlot>(); v.pool = d_pool.as<u8>();
         v.edge_mask = static_cast<u32>(trie.edges.size() - 1);
         v.dict_mask = static_cast<u32>(trie.dict.size() - 1);
-        v.root_plus = trie.root_plus; v.root_hash_ref = trie.root_hash_ref; v.root_mask = trie.root_mask;
+        v.root_plus = trie.root_plus; v.root_hash_ref = trie.root_hash_ref; v.root_hash_cnt = trie.root_hash_cnt; v.root_mask = trie.root_mask;
         v.max_depth = trie.max_depth;
         return v;
     }
@@ -168,7 +171,7 @@ struct gm_engine {
         if ((st = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return st;
         if ((st = upload_table(d_dict, trie.dict, trie.full_dict, trie.dirty_dict, up_dict_slots)) != GM_OK) return st;
         if ((st = upload_appendable(d_plus, trie.plus, up_plus, &trie.dirty_plus)) != GM_OK) return st;
-        if ((st = upload_appendable(d_ranges, trie.ranges, up_ranges, &trie.dirty_ranges)) != GM_OK) return st;
+        if ((st = upload_appendable<Range>(d_ranges, trie.ranges, up_ranges, nullptr)) != GM_OK) return st;
         if ((st = upload_appendable<u32>(d_values, trie.values, up_values, nullptr)) != GM_OK) return st;
         if ((st = upload_appendable<u8>(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return st;
         trie.root_dirty = false;
@@ -179,7 +182,7 @@ struct gm_engine {
 
     // ---- the match pipeline, all on `s`, all buffers on the device ---------------------------------
     int enqueue_match(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids,
-                      u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool timed) {
+                      u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats) {
         if (n == 0) { if (d_needed) CUDA_TRY(cudaMemsetAsync(d_needed, 0, sizeof(u64), s)); return GM_OK; }
         if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
@@ -192,9 +195,12 @@ struct gm_engine {
         const int k3_blocks = num_sms * 4;
         const u32 stack_cap = 32u * (trie.max_depth + 2u) + 64u;
         CUDA_TRY(d_gstack.ensure(static_cast<size_t>(k3_blocks) * 8 * stack_cap * sizeof(u64)));
+        const int k2_grid = num_sms * K2_CTAS_PER_SM;
+        const size_t k2_smem = sizeof(K2Smem) * K2_WARPS;
+        CUDA_TRY(d_gpool.ensure(static_cast<size_t>(k2_grid) * K2_WARPS * K2_POOL * sizeof(Desc)));
         if (!k2_attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(K2Smem) * K2_WARPS)));
-            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(K2Smem) * K2_WARPS)));
+            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
+            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
             k2_attr_set = true;
         }
         CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
@@ -203,27 +209,27 @@ struct gm_engine {
         Ctrl* ctrl = d_ctrl.as<Ctrl>();
         const TrieView tv = view();
 
-        if (timed) CUDA_TRY(cudaEventRecord(ev_t[0], s));
+        cudaEvent_t* ev_t = ev_ring[ring_n % RING];
+        CUDA_TRY(cudaEventRecord(ev_t[0], s));
         k_tokenize<<<(n32 + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
             static_cast<const u8*>(d_blob_), d_offs_, n32, tv, S, d_tok.as<u32>(), d_meta.as<u32>(), d_status_);
         CUDA_TRY(cudaGetLastError());
-        if (timed) CUDA_TRY(cudaEventRecord(ev_t[1], s));
+        CUDA_TRY(cudaEventRecord(ev_t[1], s));
 
         MatchParams mp{};
         mp.tv = tv; mp.tok = d_tok.as<u32>(); mp.meta = d_meta.as<u32>(); mp.n = n32; mp.tok_levels = S;
         mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = d_ids_; mp.cap_ids = cap_ids;
         mp.cursor = &ctrl->cursor; mp.slow_list = d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
-        const int k2_grid = num_sms * 2;
-        const size_t k2_smem = sizeof(K2Smem) * K2_WARPS;
-        if (stats) k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, true><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp);
-        else k_match_fast<K2_FAST_L, K2_POOL, K2_STACK, K2_WARPS, false><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp);
+        if (stats) k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, true><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL);
+        else k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, false><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL);
         CUDA_TRY(cudaGetLastError());
-        if (timed) CUDA_TRY(cudaEventRecord(ev_t[2], s));
+        CUDA_TRY(cudaEventRecord(ev_t[2], s));
         if (stats) k_match_slow<true><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
         else k_match_slow<false><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
         CUDA_TRY(cudaGetLastError());
-        if (timed) CUDA_TRY(cudaEventRecord(ev_t[3], s));
+        CUDA_TRY(cudaEventRecord(ev_t[3], s));
+        ring_n++;
         launches += 3;
         if (d_needed) CUDA_TRY(cudaMemcpyAsync(d_needed, &ctrl->cursor, sizeof(u64), cudaMemcpyDeviceToDevice, s));
         CUDA_TRY(cudaEventRecord(ev_match, s));
@@ -269,7 +275,7 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_flush, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_match, cudaEventDisableTiming));
-    for (auto& ev : eng->ev_t) CUDA_TRY(cudaEventCreate(&ev));
+    for (auto& q : eng->ev_ring) for (auto& ev : q) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaEventRecord(eng->ev_flush, eng->side));
     if (c.filters_hint) eng->trie.reserve(c.filters_hint);
     *out = eng;
@@ -282,14 +288,14 @@ void gm_destroy(gm_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
-                      &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
+                      &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_gpool, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
                       &e->d_spans, &e->d_ids, &e->d_status})
         b->release();
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->ev_flush) cudaEventDestroy(e->ev_flush);
     if (e->ev_match) cudaEventDestroy(e->ev_match);
-    for (auto& ev : e->ev_t) if (ev) cudaEventDestroy(ev);
+    for (auto& q : e->ev_ring) for (auto& ev : q) if (ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -346,7 +352,7 @@ int32_t gm_match_batch_device(gm_engine* e, const void* d_blob, uint64_t blob_by
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
     if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
-    return e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, static_cast<cudaStream_t>(stream), false, false);
+    return e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, static_cast<cudaStream_t>(stream), false);
 }
 
 int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
@@ -359,7 +365,7 @@ int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_blob, uint64_t b
     CUDA_TRY(cudaSetDevice(e->device));
     if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int st = e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, s, true, false);
+    int st = e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, s, true);
     if (st != GM_OK) return st;
     std::memset(work, 0, sizeof(*work));
     if (n == 0) return GM_OK;
@@ -395,14 +401,13 @@ int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, 
     if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
     int st = e->enqueue_match(e->d_blob.p, e->d_offs.as<u32>(), n, e->d_spans.as<gm_span>(), e->d_ids.as<u32>(), cap_ids, nullptr,
-                              e->d_status.as<int32_t>(), s, false, true);
+                              e->d_status.as<int32_t>(), s, false);
     if (st != GM_OK) return st;
     u64 total = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, &e->d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(status, e->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_spans, e->d_spans.p, n * sizeof(gm_span), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&e->last_ms[k], e->ev_t[k], e->ev_t[k + 1]);
     if (needed) *needed = total;
     for (uint64_t i = 0; i < n; ++i) if (status[i]) status[i] = GM_ERR_INVALID_TOPIC;
     if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
@@ -460,10 +465,20 @@ int32_t gm_get_stats(gm_engine* e, gm_stats* out) {
     return GM_OK;
 }
 
-int32_t gm_last_kernel_ms(gm_engine* e, float out_ms[3]) {
-    if (!e || !out_ms) return GM_ERR_INVALID_ARG;
+int32_t gm_kernel_ms_ring(gm_engine* e, float* out_ms, uint32_t max_calls, uint32_t* n_calls) {
+    if (!e || !out_ms || !n_calls) return GM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    for (int k = 0; k < 3; ++k) out_ms[k] = e->last_ms[k];
+    *n_calls = 0;
+    if (e->flags & GM_FLAG_HOST_ONLY) return GM_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const u64 have = std::min<u64>(e->ring_n, gm_engine::RING);
+    const u64 take = std::min<u64>(have, max_calls);
+    for (u64 k = 0; k < take; ++k) {                       // oldest first
+        cudaEvent_t* ev = e->ev_ring[(e->ring_n - take + k) % gm_engine::RING];
+        CUDA_TRY(cudaEventSynchronize(ev[3]));
+        for (int j = 0; j < 3; ++j) CUDA_TRY(cudaEventElapsedTime(&out_ms[3 * k + j], ev[j], ev[j + 1]));
+    }
+    *n_calls = static_cast<uint32_t>(take);
     return GM_OK;
 }
 
@@ -474,7 +489,7 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
     std::lock_guard<std::mutex> g(e->mu);
     e->trie.sync();
     const HostTrie& t = e->trie;
-    static thread_local uint32_t root[4];
+    static thread_local uint32_t root[5];
     switch (which) {
         case 0: *ptr = t.edges.data(); *count = t.edges.size(); break;
         case 1: *ptr = t.plus.data(); *count = t.plus.size(); break;
@@ -482,7 +497,7 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
         case 3: *ptr = t.values.data(); *count = t.values.size(); break;
         case 4: *ptr = t.dict.data(); *count = t.dict.size(); break;
         case 5: *ptr = t.pool.data(); *count = t.pool.size(); break;
-        case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; *ptr = root; *count = 4; break;
+        case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; root[4] = t.root_hash_cnt; *ptr = root; *count = 5; break;
         default: return GM_ERR_INVALID_ARG;
     }
     return GM_OK;

@@ -147,7 +147,7 @@ u32 HostTrie::add_edge(u32 parent, u32 token) {
     while (edges[i].child != 0) i = (i + 1) & mask;
     EdgeSlot e{};
     e.parent = parent; e.token = token; e.child = id;
-    e.plus = 0; e.hash_ref = REF_NONE; e.own_ref = REF_NONE; e.mask = 0;
+    e.plus = 0; e.hash_ref = 0; e.own_ref = 0; e.mask = 0; e.cnts = 0;
     edges[i] = e;
     n.edge_slot = i;
     edge_count_++;
@@ -157,7 +157,7 @@ u32 HostTrie::add_edge(u32 parent, u32 token) {
     if (token == TOK_PLUS) {
         n.plus_idx = static_cast<u32>(plus.size());
         PlusRec r{};
-        r.node = id; r.plus = 0; r.hash_ref = REF_NONE; r.own_ref = REF_NONE; r.mask = 0;
+        r.node = id; r.plus = 0; r.hash_ref = 0; r.own_ref = 0; r.mask = 0; r.cnts = 0;
         plus.push_back(r);
         p.plus_child = id;
     } else if (token == TOK_HASH) {
@@ -292,55 +292,43 @@ int HostTrie::remove(const char* filter, u32 len, u32 value, bool* changed) {
 }
 
 // ------------------------------------------------------------------------------- publishing
-u32 HostTrie::make_ref(u32 node) {
+void HostTrie::make_ref(u32 node) {
     HNode& n = nodes_[node];
-    u32 old = n.ref;
-    if (n.nvals == 0) {
-        if (old != REF_NONE && (old & REF_RANGE)) garbage_values += ranges[old & ~REF_RANGE].cnt;
-        return REF_NONE;
-    }
-    if (n.nvals == 1 && n.v0 < REF_RANGE) {
-        if (old != REF_NONE && (old & REF_RANGE)) garbage_values += ranges[old & ~REF_RANGE].cnt;
-        return n.v0;
-    }
+    if (n.cnt16 >= 2) garbage_values += (n.cnt16 == CNT_BIG) ? ranges[n.ref].cnt : n.cnt16;   // old copy becomes garbage
+    if (n.nvals == 0) { n.ref = 0; n.cnt16 = 0; return; }
+    if (n.nvals == 1) { n.ref = n.v0; n.cnt16 = 1; return; }
+    const std::vector<u32>& m = multi_[node];
     u32 off = static_cast<u32>(values.size());
-    if (n.nvals == 1) values.push_back(n.v0);
-    else { const std::vector<u32>& m = multi_[node]; values.insert(values.end(), m.begin(), m.end()); }
-    u32 idx;
-    if (old != REF_NONE && (old & REF_RANGE)) {
-        idx = old & ~REF_RANGE;
-        garbage_values += ranges[idx].cnt;
-        dirty_ranges.push_back(idx);
-        ranges[idx] = Range{off, n.nvals};
-    } else {
-        idx = static_cast<u32>(ranges.size());
-        ranges.push_back(Range{off, n.nvals});
-    }
-    return REF_RANGE | idx;
+    values.insert(values.end(), m.begin(), m.end());
+    if (n.nvals < CNT_BIG) { n.ref = off; n.cnt16 = n.nvals; return; }
+    n.ref = static_cast<u32>(ranges.size());
+    n.cnt16 = CNT_BIG;
+    ranges.push_back(Range{off, n.nvals});
 }
 
 void HostTrie::write_record(u32 node) {
     const HNode& n = nodes_[node];
     u32 plus_idx = n.plus_child ? nodes_[n.plus_child].plus_idx : 0;
-    u32 hash_ref = n.hash_child ? nodes_[n.hash_child].ref : REF_NONE;
+    u32 hash_ref = n.hash_child ? nodes_[n.hash_child].ref : 0;
+    u32 hash_cnt = n.hash_child ? nodes_[n.hash_child].cnt16 : 0;
     if (node == 0) {
-        root_plus = plus_idx; root_hash_ref = hash_ref; root_mask = n.mask;
+        root_plus = plus_idx; root_hash_ref = hash_ref; root_hash_cnt = hash_cnt; root_mask = n.mask;
         root_dirty = true;
         return;
     }
     EdgeSlot& e = edges[n.edge_slot];
-    e.plus = plus_idx; e.hash_ref = hash_ref; e.own_ref = n.ref; e.mask = n.mask;
+    e.plus = plus_idx; e.hash_ref = hash_ref; e.own_ref = n.ref; e.mask = n.mask; e.cnts = hash_cnt | (n.cnt16 << 16);
     if (!full_edges) dirty_edges.push_back(n.edge_slot);
     if (n.plus_idx) {
         PlusRec& r = plus[n.plus_idx];
-        r.node = node; r.plus = plus_idx; r.hash_ref = hash_ref; r.own_ref = n.ref; r.mask = n.mask;
+        r.node = node; r.plus = plus_idx; r.hash_ref = hash_ref; r.own_ref = n.ref; r.mask = n.mask; r.cnts = e.cnts;
         dirty_plus.push_back(n.plus_idx);
     }
 }
 
 void HostTrie::sync() {
     // pass 1: value-set references (a '#' node's parent reads the child's fresh ref in pass 2)
-    for (u32 id : dirty_nodes_) nodes_[id].ref = make_ref(id);
+    for (u32 id : dirty_nodes_) make_ref(id);
     for (u32 id : dirty_nodes_) { write_record(id); nodes_[id].dirty = 0; }
     dirty_nodes_.clear();
 }

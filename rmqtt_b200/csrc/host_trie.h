@@ -23,7 +23,8 @@ struct HNode {
     u32 hash_child = 0;      // node id of the '#' child (0 = none)
     u32 nvals = 0;           // size of the value set (BTreeSet<V>)
     u32 v0 = 0;              // the value when nvals == 1
-    u32 ref = REF_NONE;      // value-set reference currently published to the device
+    u32 ref = 0;             // value-set reference currently published to the device ...
+    u32 cnt16 = 0;           // ... and its 16-bit count (layout.h)
     u32 live_children = 0;
     u32 mask = 0;
     u8 alive = 0;            // reference semantics: pruned nodes (trie.rs:126-128) are "not alive"
@@ -55,7 +56,7 @@ class HostTrie {
     std::vector<u32> values;
     std::vector<DictSlot> dict;
     std::vector<u8> pool;
-    u32 root_plus = 0, root_hash_ref = REF_NONE, root_mask = 0;
+    u32 root_plus = 0, root_hash_ref = 0, root_hash_cnt = 0, root_mask = 0;
     u32 max_depth = 0;
 
     // ---- dirty tracking (consumed and cleared by the engine's flush) ---------------------------
@@ -82,7 +83,7 @@ class HostTrie {
     void grow_edges();
     void grow_dict();
     void mark(u32 node);
-    u32 make_ref(u32 node);
+    void make_ref(u32 node);
     void write_record(u32 node);
 
     u32 max_levels_;

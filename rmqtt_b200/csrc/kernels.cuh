@@ -143,14 +143,14 @@ __device__ __forceinline__ u64 make_item(u32 topic, u32 depth, u32 kind, u32 arg
     return (static_cast<u64>(topic | (depth << 5) | (kind << 21)) << 32) | arg;
 }
 
-struct NodeRec { u32 node, plus, hash_ref, own_ref, mask; };
+struct NodeRec { u32 node, plus, hash_ref, own_ref, mask, cnts; };
 
 // Loads the record an item points at.  Returns false when the literal child does not exist.
 __device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 arg, u32 token, NodeRec& r) {
     u32 s[8];
     if (kind == KIND_PLUS) {
         ld256(tv.plus + arg, s);
-        r.node = s[0]; r.plus = s[1]; r.hash_ref = s[2]; r.own_ref = s[3]; r.mask = s[4];
+        r.node = s[0]; r.plus = s[1]; r.hash_ref = s[2]; r.own_ref = s[3]; r.mask = s[4]; r.cnts = s[5];
         return true;
     }
     u32 idx = edge_hash(arg, token) & tv.edge_mask;
@@ -160,32 +160,37 @@ __device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 ar
         if (s[0] == arg && s[1] == token) break;
         idx = (idx + 1) & tv.edge_mask;
     }
-    r.node = s[2]; r.plus = s[3]; r.hash_ref = s[4]; r.own_ref = s[5]; r.mask = s[6];
+    r.node = s[2]; r.plus = s[3]; r.hash_ref = s[4]; r.own_ref = s[5]; r.mask = s[6]; r.cnts = s[7];
     return true;
 }
 
-template <int FAST_L, int POOL_CAP, int STACK_CAP>
+// A matched value set waiting to be expanded into the output: ref + (cnt16 | topic slot << 16).
+struct Desc { u32 ref, meta; };
+
+template <int FAST_L, int STACK_CAP>
 struct alignas(16) WarpSmem {
     u64 stack[STACK_CAP];
-    u32 pool_id[POOL_CAP];
     u32 tok[FAST_L][32];
     u32 cnt[32];
     u32 cur[32];
     u32 nlev[32];
-    u8 pool_tag[POOL_CAP];
+    u32 st[3][32];     // STATS instantiation only: per-topic V, E, F (so deferred topics are not double counted)
 };
 
-// K2: 32 topics per warp.
-template <int FAST_L, int POOL_CAP, int STACK_CAP, int WARPS, bool STATS>
-__global__ void __launch_bounds__(WARPS * 32)
-k_match_fast(MatchParams p) {
-    using WS = WarpSmem<FAST_L, POOL_CAP, STACK_CAP>;
+// K2: 32 topics per warp.  Matched value sets are staged as 8-byte descriptors in a per-warp slice of
+// a global scratch pool (written once, read twice, L2-resident), so that shared memory only holds
+// the frontier stack and the tokens and many warps fit on an SM (the walk is latency bound).
+template <int FAST_L, int STACK_CAP, int WARPS, int CTAS_PER_SM, bool STATS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
+k_match_fast(MatchParams p, Desc* __restrict__ gpool, u32 pool_cap) {
+    using WS = WarpSmem<FAST_L, STACK_CAP>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WS& W = reinterpret_cast<WS*>(smem_raw)[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31;
     const u32 lt = lanemask_lt();
     const TrieView& tv = p.tv;
     const u32 ntiles = (p.n + 31) >> 5;
+    Desc* pool = gpool + static_cast<size_t>(blockIdx.x * WARPS + (threadIdx.x >> 5)) * pool_cap;
     unsigned long long sV = 0, sE = 0, sF = 0, sM = 0;
 
     for (;;) {
@@ -203,6 +208,7 @@ k_match_fast(MatchParams p) {
         const bool slow_pre = in_range && !invalid && need > FAST_L;
         const bool active = in_range && !invalid && !slow_pre;
         W.nlev[lane] = L;
+        if (STATS) { W.st[0][lane] = 0; W.st[1][lane] = 0; W.st[2][lane] = 0; }
         if (active) {
 #pragma unroll
             for (int l = 0; l < FAST_L; ++l)
@@ -211,14 +217,14 @@ k_match_fast(MatchParams p) {
         __syncwarp();
 
         u32 pool_n = 0, stack_n = 0;   // warp-uniform
-        u32 ovf = 0;                   // warp-uniform bit mask of topic slots that overflowed a staging area
+        u32 ovf = 0;                   // warp-uniform bit mask of topic slots deferred to the slow path
 
         // Consumes one loaded record per lane (hit == false: lane idle).  Warp-collective.
         auto consume = [&](bool hit, u32 topic, u32 d, u32 Lt, const NodeRec& r, bool dollar_root) {
             // `#` child: matches the rest of the path (trie.rs:321-327) and, on path exhaustion, the
             // parent itself (trie.rs:302-308).  Skipped at the root for `$`-topics (trie.rs:312-318).
-            u32 e1 = (hit && !dollar_root) ? r.hash_ref : REF_NONE;
-            u32 e2 = (hit && d == Lt) ? r.own_ref : REF_NONE;                  // trie.rs:309-310
+            const u32 c1 = (hit && !dollar_root) ? (r.cnts & 0xFFFFu) : 0u;
+            const u32 c2 = (hit && d == Lt) ? (r.cnts >> 16) : 0u;              // own values, trie.rs:309-310
             u64 itA = 0, itB = 0;
             bool pA = false, pB = false;
             if (hit && d < Lt) {
@@ -228,38 +234,24 @@ k_match_fast(MatchParams p) {
                     if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) { pB = true; itB = make_item(topic, d + 1, KIND_PROBE, r.node); }  // trie.rs:338-342
                 }
             }
-            if (STATS) { sV += hit; sE += (hit && d < Lt); }
-            // ---- matched ids -> staging pool (ballot compaction)
+            if (STATS && hit) { atomicAdd(&W.st[0][topic], 1u); if (d < Lt) atomicAdd(&W.st[1][topic], 1u); }
+            // ---- matched value sets -> descriptor pool (ballot compaction)
 #pragma unroll
             for (int round = 0; round < 2; ++round) {
-                const u32 ref = round == 0 ? e1 : e2;
-                const bool some = ref != REF_NONE;
-                const bool single = some && !(ref & REF_RANGE);
-                if (STATS) { sF += some; sM += single; }
-                u32 b = __ballot_sync(0xFFFFFFFFu, single);
+                const u32 cn = round == 0 ? c1 : c2;
+                const u32 ref = round == 0 ? r.hash_ref : r.own_ref;
+                const bool some = cn != 0;
+                const bool big = cn == CNT_BIG;              // >= 65535 values in one set: deferred path
+                u32 b = __ballot_sync(0xFFFFFFFFu, some);
                 if (b) {
                     u32 tot = __popc(b);
-                    if (pool_n + tot <= POOL_CAP) {
-                        if (single) { u32 at = pool_n + __popc(b & lt); W.pool_id[at] = ref; W.pool_tag[at] = static_cast<u8>(topic); }
+                    const bool room = pool_n + tot <= pool_cap;
+                    if (room) {
+                        if (some) pool[pool_n + __popc(b & lt)] = Desc{ref, cn | (topic << 16)};
                         pool_n += tot;
-                    } else {
-                        ovf |= __reduce_or_sync(0xFFFFFFFFu, single ? (1u << topic) : 0u);
                     }
-                }
-                u32 rb = __ballot_sync(0xFFFFFFFFu, some && !single);
-                while (rb) {   // value sets with more than one element: warp-cooperative copy
-                    int leader = __ffs(rb) - 1;
-                    rb &= rb - 1;
-                    u32 rr = __shfl_sync(0xFFFFFFFFu, ref, leader);
-                    u32 tp = __shfl_sync(0xFFFFFFFFu, topic, leader);
-                    Range rg = tv.ranges[rr & ~REF_RANGE];
-                    if (STATS && lane == 0) sM += rg.cnt;
-                    if (pool_n + rg.cnt <= POOL_CAP) {
-                        for (u32 i = lane; i < rg.cnt; i += 32) { W.pool_id[pool_n + i] = tv.values[rg.off + i]; W.pool_tag[pool_n + i] = static_cast<u8>(tp); }
-                        pool_n += rg.cnt;
-                    } else {
-                        ovf |= 1u << tp;
-                    }
+                    u32 bad = __ballot_sync(0xFFFFFFFFu, some && (big || !room));
+                    if (bad) ovf |= __reduce_or_sync(0xFFFFFFFFu, (some && (big || !room)) ? (1u << topic) : 0u);
                 }
             }
             // ---- new frontier items -> LIFO stack (ballot compaction)
@@ -282,7 +274,7 @@ k_match_fast(MatchParams p) {
 
         // root of every topic (depth 0): the record comes from the kernel parameters
         {
-            NodeRec r{0u, tv.root_plus, tv.root_hash_ref, REF_NONE, tv.root_mask};
+            NodeRec r{0u, tv.root_plus, tv.root_hash_ref, 0u, tv.root_mask, tv.root_hash_cnt};
             consume(active, lane, 0u, L, r, active && (m & META_DOLLAR) != 0);
         }
 
@@ -306,12 +298,14 @@ k_match_fast(MatchParams p) {
             consume(hit, topic, d, Lt, r, false);
         }
 
-        // ---- group the staged ids by topic and publish them: one contiguous list per topic
+        // ---- publish: one contiguous list per topic inside one chunk per tile
+        __threadfence_block();   // descriptors written by other lanes of this warp
         W.cnt[lane] = 0;
         __syncwarp();
         for (u32 i = lane; i < pool_n; i += 32) {
-            u32 tg = W.pool_tag[i];
-            if (!((ovf >> tg) & 1u)) atomicAdd(&W.cnt[tg], 1u);
+            Desc dsc = pool[i];
+            u32 tg = (dsc.meta >> 16) & 31u;
+            if (!((ovf >> tg) & 1u)) { atomicAdd(&W.cnt[tg], dsc.meta & 0xFFFFu); if (STATS) atomicAdd(&W.st[2][tg], 1u); }
         }
         __syncwarp();
         const u32 c = W.cnt[lane];
@@ -326,14 +320,41 @@ k_match_fast(MatchParams p) {
         const bool fits = base + total <= p.cap_ids;
         W.cur[lane] = pre;
         __syncwarp();
-        if (fits) {
-            for (u32 i = lane; i < pool_n; i += 32) {
-                u32 tg = W.pool_tag[i];
-                if (!((ovf >> tg) & 1u)) p.out_ids[base + atomicAdd(&W.cur[tg], 1u)] = W.pool_id[i];
+        if (fits && total) {
+            for (u32 i0 = 0; i0 < pool_n; i0 += 32) {        // 32 descriptors at a time, one per lane
+                const u32 i = i0 + lane;
+                Desc dsc = i < pool_n ? pool[i] : Desc{0u, 0u};
+                const u32 tg = (dsc.meta >> 16) & 31u;
+                const u32 ni = (i < pool_n && !((ovf >> tg) & 1u)) ? (dsc.meta & 0xFFFFu) : 0u;
+                const u32 dst = ni ? atomicAdd(&W.cur[tg], ni) : 0u;      // position inside the tile chunk
+                u32 sc = ni;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, sc, o); if (lane >= o) sc += v; }
+                const u32 tot = __shfl_sync(0xFFFFFFFFu, sc, 31);
+                const u32 exc = sc - ni;
+                // load-balanced expansion: flat id index e -> (owner lane, k) by binary search over `exc`
+                for (u32 e0 = 0; e0 < tot; e0 += 32) {
+                    const u32 e = e0 + lane;
+                    u32 lo = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        u32 v = __shfl_sync(0xFFFFFFFFu, exc, lo + step);
+                        if (v <= e) lo += step;
+                    }
+                    const u32 o_exc = __shfl_sync(0xFFFFFFFFu, exc, lo);
+                    const u32 o_ref = __shfl_sync(0xFFFFFFFFu, dsc.ref, lo);
+                    const u32 o_n = __shfl_sync(0xFFFFFFFFu, ni, lo);
+                    const u32 o_dst = __shfl_sync(0xFFFFFFFFu, dst, lo);
+                    if (e < tot) {
+                        const u32 k = e - o_exc;
+                        p.out_ids[base + o_dst + k] = (o_n == 1) ? o_ref : tv.values[o_ref + k];
+                    }
+                }
             }
         }
         const bool deferred = slow_pre || (active && ((ovf >> lane) & 1u));
         if (in_range && !deferred) p.spans[t] = make_uint2(fits ? static_cast<u32>(base + pre) : 0u, c);
+        if (STATS && active && !deferred) { sV += W.st[0][lane]; sE += W.st[1][lane]; sF += W.st[2][lane]; sM += c; }
         u32 db = __ballot_sync(0xFFFFFFFFu, deferred);
         if (db) {
             u32 sb = 0;
@@ -356,6 +377,8 @@ k_match_fast(MatchParams p) {
 // ------------------------------------------------------------------------------------------------
 // K3: one warp per deferred topic; pass 0 counts, pass 1 writes.  The frontier stack lives in global
 // scratch (gstack, `stack_cap` items per warp: 32*(max_depth+2)+64 bounds the LIFO walk).
+// In STATS mode the counters of a deferred topic are taken here (the fast path's partial counts of
+// topics it later deferred are subtracted by never being added: see `stats_defer` below).
 template <bool STATS>
 __global__ void __launch_bounds__(256)
 k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
@@ -374,14 +397,15 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
         const u32 L = m & META_NLEV_MASK;
         const bool dollar = (m & META_DOLLAR) != 0;
         unsigned long long base = 0;
-        u32 count = 0;
+        unsigned long long count = 0;
         bool fits = true;
         for (int pass = 0; pass < 2; ++pass) {
-            u32 stack_n = 0, written = 0;
+            u32 stack_n = 0;
+            unsigned long long written = 0;
             bool bad = false;
             auto consume = [&](bool hit, u32 d, const NodeRec& r, bool dollar_root) {
-                u32 e1 = (hit && !dollar_root) ? r.hash_ref : REF_NONE;
-                u32 e2 = (hit && d == L) ? r.own_ref : REF_NONE;
+                const u32 c1 = (hit && !dollar_root) ? (r.cnts & 0xFFFFu) : 0u;
+                const u32 c2 = (hit && d == L) ? (r.cnts >> 16) : 0u;
                 u64 itA = 0, itB = 0;
                 bool pA = false, pB = false;
                 if (hit && d < L) {
@@ -394,23 +418,23 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                 if (STATS && pass == 0) { sV += hit; sE += (hit && d < L); }
 #pragma unroll
                 for (int round = 0; round < 2; ++round) {
-                    const u32 ref = round == 0 ? e1 : e2;
-                    const bool some = ref != REF_NONE;
-                    const bool single = some && !(ref & REF_RANGE);
-                    if (STATS && pass == 0) { sF += some; sM += single; }
-                    u32 b = __ballot_sync(0xFFFFFFFFu, single);
-                    if (pass == 1 && single) p.out_ids[base + written + __popc(b & lt)] = ref;
+                    const u32 cn = round == 0 ? c1 : c2;
+                    const u32 ref = round == 0 ? r.hash_ref : r.own_ref;
+                    if (STATS && pass == 0) sF += (cn != 0);
+                    u32 b = __ballot_sync(0xFFFFFFFFu, cn == 1);
+                    if (pass == 1 && cn == 1) p.out_ids[base + written + __popc(b & lt)] = ref;
                     written += __popc(b);
-                    u32 rb = __ballot_sync(0xFFFFFFFFu, some && !single);
-                    while (rb) {
+                    u32 rb = __ballot_sync(0xFFFFFFFFu, cn > 1);
+                    while (rb) {     // warp-cooperative copy of one value set at a time
                         int leader = __ffs(rb) - 1;
                         rb &= rb - 1;
                         u32 rr = __shfl_sync(0xFFFFFFFFu, ref, leader);
-                        Range rg = tv.ranges[rr & ~REF_RANGE];
-                        if (STATS && pass == 0 && lane == 0) sM += rg.cnt;
+                        u32 rc = __shfl_sync(0xFFFFFFFFu, cn, leader);
+                        u32 off = rr;
+                        if (rc == CNT_BIG) { Range rg = tv.ranges[rr]; off = rg.off; rc = rg.cnt; }
                         if (pass == 1)
-                            for (u32 i = lane; i < rg.cnt; i += 32) p.out_ids[base + written + i] = tv.values[rg.off + i];
-                        written += rg.cnt;
+                            for (u32 i = lane; i < rc; i += 32) p.out_ids[base + written + i] = tv.values[off + i];
+                        written += rc;
                     }
                 }
 #pragma unroll
@@ -428,12 +452,13 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                 __syncwarp();
             };
             {
-                NodeRec r{0u, tv.root_plus, tv.root_hash_ref, REF_NONE, tv.root_mask};
+                NodeRec r{0u, tv.root_plus, tv.root_hash_ref, 0u, tv.root_mask, tv.root_hash_cnt};
                 consume(lane == 0, 0u, r, dollar);
             }
             while (stack_n) {
                 const u32 take = min(stack_n, 32u);
                 const bool have = lane < take;
+                __threadfence_block();
                 u64 it = have ? stack[stack_n - 1 - lane] : 0ull;
                 stack_n -= take;
                 __syncwarp();
@@ -449,13 +474,14 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
             }
             if (pass == 0) {
                 count = written;
-                if (lane == 0 && count) base = atomicAdd(p.cursor, static_cast<unsigned long long>(count));
+                if (STATS) sM += (lane == 0) ? count : 0;
+                if (lane == 0 && count) base = atomicAdd(p.cursor, count);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                fits = !bad && (base + count <= p.cap_ids);
+                fits = !bad && (base + count <= p.cap_ids) && count <= 0xFFFFFFFFull;
                 if (!fits) break;
             }
         }
-        if (lane == 0) p.spans[t] = make_uint2(fits ? static_cast<u32>(base) : 0u, count);
+        if (lane == 0) p.spans[t] = make_uint2(fits ? static_cast<u32>(base) : 0u, static_cast<u32>(count));
     }
     if (STATS) {
 #pragma unroll

@@ -12,8 +12,8 @@
 //
 // A node record = {plus, hash_ref, own_ref, mask}:
 //   plus     index into `plus` of this node's '+' child (0 = none)            trie.rs:330-334
-//   hash_ref value-set reference of this node's '#' child (REF_NONE = none)    trie.rs:302-308,321-327
-//   own_ref  value-set reference of the node itself                            trie.rs:309-310
+//   hash_ref value set of this node's '#' child (with its 16-bit count in cnts)   trie.rs:302-308,321-327
+//   own_ref  value set of the node itself                                        trie.rs:309-310
 //   mask     32-bit Bloom mask over the tokens of all children (skips hopeless literal probes)
 #pragma once
 #include <cstdint>
@@ -38,8 +38,12 @@ constexpr u32 TOK_BLANK = 3;    // ""   (Level::Blank)
 constexpr u32 TOK_FIRST = 4;    // first dictionary-assigned token
 
 // ---- value-set references -----------------------------------------------------------------------
-constexpr u32 REF_NONE = 0xFFFFFFFFu;   // empty set
-constexpr u32 REF_RANGE = 0x80000000u;  // bit set: low 31 bits index `ranges`; clear: the single value itself
+// A value set (BTreeSet<V> of one trie node, trie.rs:70) is published as (ref, cnt16):
+//   cnt == 0            empty
+//   cnt == 1            ref IS the value                       (no second memory access)
+//   2 <= cnt < CNT_BIG  values[ref .. ref+cnt)                 (contiguous, coalesced copy)
+//   cnt == CNT_BIG      ranges[ref] = {off, cnt}: a set of >= 65535 values (deferred path only)
+constexpr u32 CNT_BIG = 0xFFFFu;
 
 struct alignas(32) EdgeSlot {
     u32 parent;    // key
@@ -49,7 +53,7 @@ struct alignas(32) EdgeSlot {
     u32 hash_ref;
     u32 own_ref;
     u32 mask;
-    u32 aux;       // reserved
+    u32 cnts;      // hash_cnt | own_cnt << 16
 };
 static_assert(sizeof(EdgeSlot) == 32, "EdgeSlot must be one 32-byte sector");
 
@@ -59,7 +63,8 @@ struct alignas(32) PlusRec {
     u32 hash_ref;
     u32 own_ref;
     u32 mask;
-    u32 pad[3];
+    u32 cnts;
+    u32 pad[2];
 };
 static_assert(sizeof(PlusRec) == 32, "PlusRec must be one 32-byte sector");
 
@@ -84,7 +89,7 @@ struct TrieView {
     const u8* pool;
     u32 edge_mask;      // capacity-1 (capacity is a power of two)
     u32 dict_mask;
-    u32 root_plus, root_hash_ref, root_mask;
+    u32 root_plus, root_hash_ref, root_hash_cnt, root_mask;
     u32 max_depth;      // deepest filter in the trie (levels)
 };
 

@@ -154,6 +154,40 @@ uint64_t wl_gen_subs(const wl_params* w, uint64_t first, uint64_t n, char* blob,
     return static_cast<uint64_t>(o - blob);
 }
 
+// Root-hash shard of the subscription set: keeps subscription i iff its level 0 is '+' (replicated on every
+// shard) or its region is flagged in region_keep[R].  values[k] = original subscription index.
+// Returns the number kept; *bytes = blob bytes written.
+uint64_t wl_gen_subs_sharded(const wl_params* w, uint64_t first, uint64_t n, const uint8_t* region_keep,
+                             char* blob, uint32_t* offs, uint32_t* values, uint64_t* bytes) {
+    Params p = cvt(w);
+    char* o = blob;
+    uint64_t kept = 0;
+    for (uint64_t k = 0; k < n; ++k) {
+        uint64_t i = first + k;
+        Rng g(p.seed, i, 1);
+        Tp t = decode(p, g.below(space(p)));
+        double u = g.uni();
+        uint32_t mask = 0; int depth = 6;
+        if (u < p.p_plus) {
+            uint32_t a = 1 + g.below(5);
+            mask |= 1u << a;
+            if (g.uni() < 0.20) { uint32_t b = 1 + g.below(4); if (b >= a) ++b; mask |= 1u << b; }
+            if (g.uni() < p.p_root_plus) mask |= 1u;
+        } else if (u < p.p_plus + p.p_hash) {
+            double v = g.uni();
+            depth = v < 0.05 ? 2 : v < 0.50 ? 3 : v < 0.80 ? 4 : 5;
+        }
+        if (!(mask & 1u) && !region_keep[t.r]) continue;
+        offs[kept] = static_cast<uint32_t>(o - blob);
+        values[kept] = static_cast<uint32_t>(i);
+        o = put_filter(o, t, mask, depth);
+        ++kept;
+    }
+    offs[kept] = static_cast<uint32_t>(o - blob);
+    if (bytes) *bytes = static_cast<uint64_t>(o - blob);
+    return kept;
+}
+
 // Publish topics [first, first+n).  frac_from_subs of them re-use the concrete topic of a uniformly drawn
 // subscription in [0, n_subs) (C1: 0.5); the rest are uniform over the topic space, optionally restricted to
 // the given regions (multi-GPU partitioning by root).  `stream` separates independent batches.

@@ -183,7 +183,7 @@ class Engine:
         """Host mirror of the device tables as numpy arrays (copies).  Test/diagnostic use only."""
         out = {}
         spec = {0: ("edges", np.uint32, 8), 1: ("plus", np.uint32, 8), 2: ("ranges", np.uint32, 2), 3: ("values", np.uint32, 1),
-                4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1)}
+                4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1)}  # root = {plus, hash_ref, mask, max_depth, hash_cnt}
         for which, (name, dt, width) in spec.items():
             ptr, cnt = C.c_void_p(), C.c_uint64(0)
             self._check(self._lib.gm_debug_table(self._h, which, C.byref(ptr), C.byref(cnt)))
@@ -196,10 +196,12 @@ class Engine:
             out[name] = a.reshape(-1, width) if width > 1 else a
         return out
 
-    def last_kernel_ms(self):
-        a = (C.c_float * 3)()
-        self._check(self._lib.gm_last_kernel_ms(self._h, C.byref(a)))
-        return [float(x) for x in a]
+    def kernel_ms(self, max_calls: int = 64) -> np.ndarray:
+        """[calls, 3] device milliseconds (tokenise, match, deferred) of the last match calls, oldest first."""
+        out = np.zeros((max_calls, 3), dtype=np.float32)
+        n = C.c_uint32(0)
+        self._check(self._lib.gm_kernel_ms_ring(self._h, _vp(out), max_calls, C.byref(n)))
+        return out[:int(n.value)]
 
     def kernel_launches(self) -> int:
         return int(self._lib.gm_kernel_launches(self._h))

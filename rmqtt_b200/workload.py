@@ -34,6 +34,7 @@ def _wl():
         L.wl_space.restype, L.wl_space.argtypes = u64, [P]
         L.wl_max_len.restype, L.wl_max_len.argtypes = u32, []
         L.wl_gen_subs.restype, L.wl_gen_subs.argtypes = u64, [P, u64, u64, vp, vp]
+        L.wl_gen_subs_sharded.restype, L.wl_gen_subs_sharded.argtypes = u64, [P, u64, u64, vp, vp, vp, vp, C.POINTER(u64)]
         L.wl_gen_topics.restype, L.wl_gen_topics.argtypes = u64, [P, u64, u64, C.c_double, u64, vp, u32, u64, vp, vp]
         L.wl_gen_retained.restype, L.wl_gen_retained.argtypes = u64, [P, u64, u64, vp, vp]
         L.wl_gen_retain_filters.restype, L.wl_gen_retain_filters.argtypes = u64, [P, u64, u64, vp, vp]
@@ -102,6 +103,20 @@ def gen_subs(cfg: Config, n: int | None = None, first: int = 0):
     p = cfg.params()
     used = _wl().wl_gen_subs(C.byref(p), first, n, _vp(blob), _vp(offs))
     return blob[:used].copy(), offs, np.arange(first, first + n, dtype=np.uint32)
+
+
+def gen_subs_sharded(cfg: Config, regions, n: int | None = None, first: int = 0):
+    """Shard of the subscription set: filters whose region is in `regions` plus every root-'+' filter.
+    -> (blob, offsets uint32[kept+1], values uint32[kept] = original subscription indices)"""
+    n = cfg.n_subs if n is None else int(n)
+    blob, offs = _alloc(n)
+    vals = np.empty(n, dtype=np.uint32)
+    keep = np.zeros(cfg.R, dtype=np.uint8)
+    keep[np.asarray(list(regions), dtype=np.int64)] = 1
+    p = cfg.params()
+    nbytes = C.c_uint64(0)
+    kept = int(_wl().wl_gen_subs_sharded(C.byref(p), first, n, _vp(keep), _vp(blob), _vp(offs), _vp(vals), C.byref(nbytes)))
+    return blob[:int(nbytes.value)].copy(), offs[:kept + 1].copy(), vals[:kept].copy()
 
 
 def gen_topics(cfg: Config, n: int | None = None, first: int = 0, regions=None, stream: int = 0):

@@ -6,7 +6,7 @@ oracle without a GPU.  It is not importable from the product package and matches
 import numpy as np
 
 M32 = 0xFFFFFFFF
-REF_NONE, REF_RANGE = 0xFFFFFFFF, 0x80000000
+CNT_BIG = 0xFFFF
 TOK_UNKNOWN, TOK_PLUS, TOK_HASH, TOK_BLANK = 0, 1, 2, 3
 
 
@@ -38,7 +38,7 @@ class Tables:
     def __init__(self, t):
         self.edges, self.plus, self.ranges, self.values = t["edges"], t["plus"], t["ranges"], t["values"]
         self.dict, self.pool = t["dict"], t["pool"]
-        self.root_plus, self.root_hash_ref, self.root_mask, self.max_depth = (int(x) for x in t["root"])
+        self.root_plus, self.root_hash_ref, self.root_mask, self.max_depth, self.root_hash_cnt = (int(x) for x in t["root"])
         self.dict_bytes = self.dict.view(np.uint8).reshape(len(self.dict), 32)
 
     def token(self, lv: bytes):
@@ -89,16 +89,18 @@ class Tables:
             if e[2] == 0:
                 return None
             if e[0] == parent and e[1] == tok:
-                return dict(node=int(e[2]), plus=int(e[3]), hash_ref=int(e[4]), own_ref=int(e[5]), mask=int(e[6]))
+                return dict(node=int(e[2]), plus=int(e[3]), hash_ref=int(e[4]), own_ref=int(e[5]), mask=int(e[6]), cnts=int(e[7]))
             i = (i + 1) & mask
 
-    def expand(self, ref, out):
-        if ref == REF_NONE:
+    def expand(self, ref, cnt, out):
+        if cnt == 0:
             return 0
-        if not ref & REF_RANGE:
+        if cnt == 1:
             out.append(ref)
             return 1
-        off, cnt = (int(x) for x in self.ranges[ref & ~REF_RANGE & M32])
+        off = ref
+        if cnt == CNT_BIG:
+            off, cnt = (int(x) for x in self.ranges[ref])
         out.extend(int(v) for v in self.values[off:off + cnt])
         return 1
 
@@ -111,19 +113,19 @@ class Tables:
         L = len(toks)
         out = []
         V = E = F = 0
-        stack = [(dict(node=0, plus=self.root_plus, hash_ref=self.root_hash_ref, own_ref=REF_NONE, mask=self.root_mask), 0, dollar)]
+        stack = [(dict(node=0, plus=self.root_plus, hash_ref=self.root_hash_ref, own_ref=0, mask=self.root_mask, cnts=self.root_hash_cnt), 0, dollar)]
         while stack:
             r, d, dollar_root = stack.pop()
             V += 1
             if not dollar_root:
-                F += self.expand(r["hash_ref"], out)
+                F += self.expand(r["hash_ref"], r["cnts"] & 0xFFFF, out)
             if d == L:
-                F += self.expand(r["own_ref"], out)
+                F += self.expand(r["own_ref"], r["cnts"] >> 16, out)
                 continue
             E += 1
             if r["plus"] and not dollar_root:
                 p = self.plus[r["plus"]]
-                stack.append((dict(node=int(p[0]), plus=int(p[1]), hash_ref=int(p[2]), own_ref=int(p[3]), mask=int(p[4])), d + 1, False))
+                stack.append((dict(node=int(p[0]), plus=int(p[1]), hash_ref=int(p[2]), own_ref=int(p[3]), mask=int(p[4]), cnts=int(p[5])), d + 1, False))
             t = toks[d]
             if t != TOK_UNKNOWN and r["mask"] & mask_bit(t):
                 c = self.probe(r["node"], t)

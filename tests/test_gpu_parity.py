@@ -92,7 +92,7 @@ def test_tokenizer_matches_host_dictionary():
     inv = (meta >> 31) & 1
     assert inv.tolist() == [0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]
     nlev = meta & 0xFFFFFF
-    assert nlev[0] == 3 and nlev[1] == 3 and nlev[8] == 1 and nlev[9] == 2 and nlev[15] == 44
+    assert nlev[0] == 3 and nlev[1] == 3 and nlev[8] == 1 and nlev[9] == 2 and nlev[15] == 43
     assert (meta[2] >> 30) & 1 == 1 and (meta[0] >> 30) & 1 == 0
     a, b, c = toks[0, 0], toks[1, 0], toks[2, 0]
     assert a >= 4 and b >= 4 and c >= 4 and len({a, b, c}) == 3

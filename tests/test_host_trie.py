@@ -98,3 +98,22 @@ def test_too_deep_filter_is_rejected():
     with pytest.raises(GpuMqttError) as ei:
         eng.add("a/b/c/d/e", 1)
     assert ei.value.code == N.GM_ERR_TOO_DEEP
+
+
+def test_huge_value_set_uses_the_range_table():
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    import numpy as np
+    from rmqtt_b200.engine import pack
+    n = 70_000                                   # >= 65535 values on one filter node -> CNT_BIG + ranges[]
+    blob, offs = pack(["big/+"] * n)
+    vals = np.arange(n, dtype=np.uint32)
+    assert eng.bulk_load(blob, offs, vals) == n
+    tree.bulk_insert(blob, offs, vals)
+    eng.add("big/#", 7); tree.insert("big/#", 7)
+    T = Tables(eng.debug_tables())
+    got, ctr = T.match(b"big/x")
+    assert got == tree.matches("big/x") and ctr["M"] == n + 1
+    assert eng.remove("big/+", 5) and tree.remove("big/+", 5)
+    T = Tables(eng.debug_tables())
+    assert T.match(b"big/x")[0] == tree.matches("big/x")
+    assert eng.stats()["garbage_value_words"] == n
