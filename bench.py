@@ -297,7 +297,8 @@ def run_own(args):
 
     # ---- roofline of the dominant kernel (k_match_fast) -------------------------------------------
     peak, peak_src = _peaks()
-    W = {k: sum(w[k] for w in works) / len(works) for k in works[0]}           # mean per launch over the rotated batches
+    W = {k: sum(w[k] for w in works) / len(works) for k in works[0] if not isinstance(works[0][k], list)}   # mean per launch over the rotated batches
+    diag = {"probes_by_depth": works[0]["probes_by_depth"], "misses_by_depth": works[0]["misses_by_depth"], "slot_loads": works[0]["slot_loads"]}
     k2_bytes = 16 * W["visited"] + 16 * W["probed"] + 8 * W["filters"] + 4 * W["ids"] + 8 * n     # SURVEY §8(d), walk terms
     k1_bytes = W["bytes"] + 8 * n + 16 * W["levels"]                                              # SURVEY §8(d), tokeniser terms
     k_mean = kms.mean(axis=0) if len(kms) else np.zeros(3)
@@ -342,7 +343,7 @@ def run_own(args):
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": _workload_desc(cfg, world), "l2": f"device tables {st['device_bytes'] / 1e9:.2f} GB >> 126 MB L2; {B} distinct topic batches rotated",
-                   "matched_ids_per_topic": W["ids"] / n, "visited_nodes_per_topic": W["visited"] / n, "deferred_topics_per_batch": W["deferred"],
+                   "matched_ids_per_topic": W["ids"] / n, "visited_nodes_per_topic": W["visited"] / n, "deferred_topics_per_batch": W["deferred"], "probe_diag": diag,
                    "trie": {k: st[k] for k in ("values", "nodes", "edges", "edge_slots", "dict_entries", "plus_nodes", "device_bytes", "max_depth")},
                    "build_s": round(build_s, 1), "e2e_timing": "perf_counter around synchronous gm_match_batch calls (pinned host buffers)"},
         "e2e": {"value": e2e_value, "unit": "topics/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},

@@ -80,6 +80,9 @@ typedef struct gm_work {
     uint64_t levels;           /* L: topic levels */
     uint64_t bytes;            /* topic text bytes */
     uint64_t deferred;         /* topics handled by the generic (slow) kernel */
+    uint64_t probes_by_depth[8]; /* diagnostics of the fast kernel: literal-child probes issued at depth d ... */
+    uint64_t misses_by_depth[8]; /* ... of which the child did not exist */
+    uint64_t slot_loads;         /* 32-byte edge-slot loads those probes cost (linear probing included) */
 } gm_work;
 
 /* ---- lifecycle -------------------------------------------------------------------------------------- */

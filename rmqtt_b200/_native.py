@@ -36,10 +36,14 @@ class GmStats(C.Structure):
 
 
 class GmWork(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("visited", "probed", "filters", "ids", "levels", "bytes", "deferred")]
+    _fields_ = [(n, C.c_uint64) for n in ("visited", "probed", "filters", "ids", "levels", "bytes", "deferred")] + \
+               [("probes_by_depth", C.c_uint64 * 8), ("misses_by_depth", C.c_uint64 * 8), ("slot_loads", C.c_uint64)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        d = {n: int(getattr(self, n)) for n in ("visited", "probed", "filters", "ids", "levels", "bytes", "deferred", "slot_loads")}
+        d["probes_by_depth"] = [int(x) for x in self.probes_by_depth]
+        d["misses_by_depth"] = [int(x) for x in self.misses_by_depth]
+        return d
 
 
 # every symbol include/gpumqtt.h declares: name -> (restype, argtypes)

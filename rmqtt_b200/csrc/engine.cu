@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -50,18 +51,16 @@ struct DevBuf {
 
 struct Ctrl {                       // device control block, zeroed before every match
     unsigned long long cursor;
-    unsigned long long stats[4];
+    unsigned long long stats[24];
     u32 slow_count;
     u32 tile_counter;
 };
 
-// fast-path geometry: 32 topics per warp, 16 warps per CTA, 3 CTAs per SM
-constexpr int K2_FAST_L = 8;
-constexpr int K2_STACK = 384;      // >= 64 + 32*FAST_L: the LIFO walk of 32 topics cannot overflow it
-constexpr int K2_WARPS = 16;
-constexpr int K2_CTAS_PER_SM = 3;
-constexpr u32 K2_POOL = 1024;      // descriptors (matched value sets) per warp tile before topics are deferred
-using K2Smem = WarpSmem<K2_FAST_L, K2_STACK>;
+// fast-path geometry: one topic per thread, 512 threads per CTA, 4 CTAs per SM (<= 32 registers)
+constexpr int K2_FAST_L = 8;       // levels staged in shared memory; deeper topics take the deferred kernel
+constexpr int K2_THREADS = 512;
+constexpr int K2_CTAS_PER_SM = 4;
+constexpr u32 K2_POOL_ROWS = 32;   // matched value sets per topic before the topic is deferred
 
 }  // namespace
 
@@ -85,7 +84,6 @@ struct gm_engine {
     DevBuf d_tok, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data;
     DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
     u64 launches = 0;
-    bool k2_attr_set = false;
 
     explicit gm_engine(u32 max_levels) : trie(max_levels) {}
 
@@ -195,14 +193,10 @@ struct gm_engine {
         const int k3_blocks = num_sms * 4;
         const u32 stack_cap = 32u * (trie.max_depth + 2u) + 64u;
         CUDA_TRY(d_gstack.ensure(static_cast<size_t>(k3_blocks) * 8 * stack_cap * sizeof(u64)));
-        const int k2_grid = num_sms * K2_CTAS_PER_SM;
-        const size_t k2_smem = sizeof(K2Smem) * K2_WARPS;
-        CUDA_TRY(d_gpool.ensure(static_cast<size_t>(k2_grid) * K2_WARPS * K2_POOL * sizeof(Desc)));
-        if (!k2_attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
-            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
-            k2_attr_set = true;
-        }
+        int k2_ctas = K2_CTAS_PER_SM;
+        if (const char* ev = getenv("GM_K2_CTAS")) { int v = atoi(ev); if (v >= 1 && v <= K2_CTAS_PER_SM) k2_ctas = v; }   // tuning knob
+        const int k2_grid = num_sms * k2_ctas;
+        CUDA_TRY(d_gpool.ensure(static_cast<size_t>(k2_grid) * K2_THREADS * K2_POOL_ROWS * sizeof(Desc)));
         CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
         if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(s, ev_match, 0));   // scratch is shared: one match in flight
         CUDA_TRY(cudaMemsetAsync(d_ctrl.p, 0, sizeof(Ctrl), s));
@@ -221,8 +215,10 @@ struct gm_engine {
         mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = d_ids_; mp.cap_ids = cap_ids;
         mp.cursor = &ctrl->cursor; mp.slow_list = d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
-        if (stats) k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, true><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL);
-        else k_match_fast<K2_FAST_L, K2_STACK, K2_WARPS, K2_CTAS_PER_SM, false><<<k2_grid, K2_WARPS * 32, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL);
+        mp.flags = MP_L2_HINTS;
+        if (const char* ev = getenv("GM_K2_HINTS")) mp.flags = atoi(ev) ? MP_L2_HINTS : 0u;   // tuning knob
+        if (stats) k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true><<<k2_grid, K2_THREADS, 0, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
+        else k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false><<<k2_grid, K2_THREADS, 0, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[2], s));
         if (stats) k_match_slow<true><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
@@ -377,6 +373,8 @@ int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_blob, uint64_t b
     CUDA_TRY(cudaStreamSynchronize(s));
     work->visited = h.stats[0]; work->probed = h.stats[1]; work->filters = h.stats[2]; work->ids = h.stats[3];
     work->deferred = h.slow_count;
+    for (int k = 0; k < 8; ++k) { work->probes_by_depth[k] = h.stats[4 + k]; work->misses_by_depth[k] = h.stats[12 + k]; }
+    work->slot_loads = h.stats[20];
     for (uint64_t i = 0; i < n; ++i)
         if (!(meta[i] & META_INVALID)) { work->levels += meta[i] & META_NLEV_MASK; work->bytes += offs[i + 1] - offs[i]; }
     return GM_OK;

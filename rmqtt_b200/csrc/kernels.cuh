@@ -2,10 +2,10 @@
 //
 //   k_tokenize     Topic::from_str (rmqtt/src/topic.rs:326-363) for a batch: split on '/', classify,
 //                  validate, and intern every level through the device dictionary -> u32 tokens.
-//   k_match_fast   TopicTree::matches (rmqtt/src/trie.rs:299-347, MatchedIter::prepare) for 32 topics
-//                  per warp: a warp-shared LIFO frontier of "load one node record" work items, one
-//                  256-bit load per item, warp-ballot compaction of the new frontier items and of the
-//                  matched subscriber ids, single pass, per-topic contiguous output.
+//   k_match_fast   TopicTree::matches (rmqtt/src/trie.rs:299-347, MatchedIter::prepare): one topic per
+//                  thread walks the trie depth-first (one 256-bit load per visited node), then the warp
+//                  publishes its 32 match lists with a scan + load-balanced (ballot/shuffle) expansion:
+//                  single pass, per-topic contiguous output.
 //   k_match_slow   the same walk for the topics the fast path defers (more levels than the fast
 //                  path stages in shared memory, or more matches than its staging pool): one warp per
 //                  topic, count pass + write pass, warp-cooperative value-range copies.
@@ -32,14 +32,24 @@ struct MatchParams {
     u32* slow_list;      // [n]
     u32* slow_count;
     u32* tile_counter;
-    unsigned long long* stats;    // [4] V,E,F,M  (only written by STATS instantiations)
+    unsigned long long* stats;    // [4] V,E,F,M + [4..] probe diagnostics (only written by STATS instantiations)
+    u32 flags;                    // MP_* tuning switches
 };
+constexpr u32 MP_L2_HINTS = 1u;   // L2 eviction priorities: hot upper levels / '+' subtrees evict_last, cold deep chain evict_first
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ld256(const void* p, u32 (&w)[8]) {
     asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                  : "l"(p));
+}
+// L2 eviction-priority policies (createpolicy) and a 256-bit load that carries one.
+__device__ __forceinline__ u64 l2_policy_evict_last() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 l2_policy_evict_first() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void ld256_hint(const void* p, u32 (&w)[8], u64 pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p), "l"(pol));
 }
 __device__ __forceinline__ u32 lanemask_lt() {
     u32 m;
@@ -146,16 +156,17 @@ __device__ __forceinline__ u64 make_item(u32 topic, u32 depth, u32 kind, u32 arg
 struct NodeRec { u32 node, plus, hash_ref, own_ref, mask, cnts; };
 
 // Loads the record an item points at.  Returns false when the literal child does not exist.
-__device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 arg, u32 token, NodeRec& r) {
+// pol != 0: L2 cache-policy operand for the slot loads.
+__device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 arg, u32 token, NodeRec& r, u64 pol = 0) {
     u32 s[8];
     if (kind == KIND_PLUS) {
-        ld256(tv.plus + arg, s);
+        if (pol) ld256_hint(tv.plus + arg, s, pol); else ld256(tv.plus + arg, s);
         r.node = s[0]; r.plus = s[1]; r.hash_ref = s[2]; r.own_ref = s[3]; r.mask = s[4]; r.cnts = s[5];
         return true;
     }
     u32 idx = edge_hash(arg, token) & tv.edge_mask;
     for (;;) {
-        ld256(tv.edges + idx, s);
+        if (pol) ld256_hint(tv.edges + idx, s, pol); else ld256(tv.edges + idx, s);
         if (s[2] == 0) return false;                       // empty slot: no such child
         if (s[0] == arg && s[1] == token) break;
         idx = (idx + 1) & tv.edge_mask;
@@ -164,34 +175,41 @@ __device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 ar
     return true;
 }
 
-// A matched value set waiting to be expanded into the output: ref + (cnt16 | topic slot << 16).
-struct Desc { u32 ref, meta; };
+// A matched value set waiting to be expanded into the output: values[ref .. ref+cnt) (or ref itself).
+struct Desc { u32 ref, cnt; };
 
-template <int FAST_L, int STACK_CAP>
-struct alignas(16) WarpSmem {
-    u64 stack[STACK_CAP];
-    u32 tok[FAST_L][32];
-    u32 cnt[32];
-    u32 cur[32];
-    u32 nlev[32];
-    u32 st[3][32];     // STATS instantiation only: per-topic V, E, F (so deferred topics are not double counted)
-};
-
-// K2: 32 topics per warp.  Matched value sets are staged as 8-byte descriptors in a per-warp slice of
-// a global scratch pool (written once, read twice, L2-resident), so that shared memory only holds
-// the frontier stack and the tokens and many warps fit on an SM (the walk is latency bound).
-template <int FAST_L, int STACK_CAP, int WARPS, int CTAS_PER_SM, bool STATS>
-__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
-k_match_fast(MatchParams p, Desc* __restrict__ gpool, u32 pool_cap) {
-    using WS = WarpSmem<FAST_L, STACK_CAP>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WS& W = reinterpret_cast<WS*>(smem_raw)[threadIdx.x >> 5];
-    const u32 lane = threadIdx.x & 31;
+// K2: TopicTree::matches, one topic per thread (depth-first), one tile of 32 topics per warp.
+//
+//   walk     every thread follows its own topic down the trie: at a node it records the matched value
+//            sets ('#' child always, own values on path exhaustion) as 8-byte descriptors, parks the
+//            '+' child of this depth in its shared-memory column, and descends through the literal
+//            child with ONE 256-bit load; when the literal path ends it resumes the deepest parked
+//            '+' child.  The dependent chain of a thread is one load long per visited node; latency is
+//            hidden by the other ~1.5 K resident threads of the SM.
+//   publish  warp-cooperative: per-lane totals -> warp scan -> one atomic reservation per tile ->
+//            load-balanced expansion of the descriptors (ballot/scan + binary search by shuffle) so
+//            that the id copies out of `values` and into out_ids are coalesced runs.
+//
+// (Round-1 history: a warp-shared ballot-compacted frontier queue ran at 344 warp-instructions per
+//  topic and 45 % issue utilisation — collective overhead, not memory, bound it; see profiles/.)
+template <int FAST_L, int THREADS, int CTAS_PER_SM, bool STATS>
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
+k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
+    __shared__ u32 s_tok[FAST_L][THREADS];    // tokens of this thread's topic (column = thread: conflict-free)
+    __shared__ u32 s_pend[FAST_L][THREADS];   // parked '+' child (index into tv.plus) per depth
+    const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 lt = lanemask_lt();
+    const u32 nthreads = gridDim.x * THREADS;
+    const u32 gtid = blockIdx.x * THREADS + tid;
     const TrieView& tv = p.tv;
     const u32 ntiles = (p.n + 31) >> 5;
-    Desc* pool = gpool + static_cast<size_t>(blockIdx.x * WARPS + (threadIdx.x >> 5)) * pool_cap;
     unsigned long long sV = 0, sE = 0, sF = 0, sM = 0;
+    // L2 residency: the upper two levels, every '+' record and everything below a '+' edge that replaced one
+    // of the first three levels is shared by many topics of a batch (hot: evict_last); the exact chain below
+    // a device is touched by ~1 topic per batch (cold: evict_first) and must not flush the hot set out of L2.
+    const bool hints = (p.flags & MP_L2_HINTS) != 0;
+    const u64 pol_hot = hints ? l2_policy_evict_last() : 0ull;
+    const u64 pol_cold = hints ? l2_policy_evict_first() : 0ull;
 
     for (;;) {
         u32 tile = 0;
@@ -201,132 +219,98 @@ k_match_fast(MatchParams p, Desc* __restrict__ gpool, u32 pool_cap) {
 
         const u32 t = tile * 32 + lane;
         const bool in_range = t < p.n;
-        const u32 m = in_range ? p.meta[t] : META_INVALID;
+        const u32 m = in_range ? __ldcs(p.meta + t) : META_INVALID;
         const bool invalid = (m & META_INVALID) != 0;
         const u32 L = m & META_NLEV_MASK;
         const u32 need = min(L, tv.max_depth);
         const bool slow_pre = in_range && !invalid && need > FAST_L;
         const bool active = in_range && !invalid && !slow_pre;
-        W.nlev[lane] = L;
-        if (STATS) { W.st[0][lane] = 0; W.st[1][lane] = 0; W.st[2][lane] = 0; }
+        bool defer = slow_pre;
+        u32 ndesc = 0, total = 0;
+
         if (active) {
 #pragma unroll
             for (int l = 0; l < FAST_L; ++l)
-                if (l < need) W.tok[l][lane] = p.tok[static_cast<size_t>(l) * p.n + t];
-        }
-        __syncwarp();
-
-        u32 pool_n = 0, stack_n = 0;   // warp-uniform
-        u32 ovf = 0;                   // warp-uniform bit mask of topic slots deferred to the slow path
-
-        // Consumes one loaded record per lane (hit == false: lane idle).  Warp-collective.
-        auto consume = [&](bool hit, u32 topic, u32 d, u32 Lt, const NodeRec& r, bool dollar_root) {
-            // `#` child: matches the rest of the path (trie.rs:321-327) and, on path exhaustion, the
-            // parent itself (trie.rs:302-308).  Skipped at the root for `$`-topics (trie.rs:312-318).
-            const u32 c1 = (hit && !dollar_root) ? (r.cnts & 0xFFFFu) : 0u;
-            const u32 c2 = (hit && d == Lt) ? (r.cnts >> 16) : 0u;              // own values, trie.rs:309-310
-            u64 itA = 0, itB = 0;
-            bool pA = false, pB = false;
-            if (hit && d < Lt) {
-                if (r.plus != 0 && !dollar_root) { pA = true; itA = make_item(topic, d + 1, KIND_PLUS, r.plus); }   // trie.rs:330-334
-                if (r.mask != 0) {
-                    u32 tk = W.tok[d][topic];
-                    if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) { pB = true; itB = make_item(topic, d + 1, KIND_PROBE, r.node); }  // trie.rs:338-342
-                }
-            }
-            if (STATS && hit) { atomicAdd(&W.st[0][topic], 1u); if (d < Lt) atomicAdd(&W.st[1][topic], 1u); }
-            // ---- matched value sets -> descriptor pool (ballot compaction)
-#pragma unroll
-            for (int round = 0; round < 2; ++round) {
-                const u32 cn = round == 0 ? c1 : c2;
-                const u32 ref = round == 0 ? r.hash_ref : r.own_ref;
-                const bool some = cn != 0;
-                const bool big = cn == CNT_BIG;              // >= 65535 values in one set: deferred path
-                u32 b = __ballot_sync(0xFFFFFFFFu, some);
-                if (b) {
-                    u32 tot = __popc(b);
-                    const bool room = pool_n + tot <= pool_cap;
-                    if (room) {
-                        if (some) pool[pool_n + __popc(b & lt)] = Desc{ref, cn | (topic << 16)};
-                        pool_n += tot;
-                    }
-                    u32 bad = __ballot_sync(0xFFFFFFFFu, some && (big || !room));
-                    if (bad) ovf |= __reduce_or_sync(0xFFFFFFFFu, (some && (big || !room)) ? (1u << topic) : 0u);
-                }
-            }
-            // ---- new frontier items -> LIFO stack (ballot compaction)
-#pragma unroll
-            for (int round = 0; round < 2; ++round) {
-                const bool push = round == 0 ? pA : pB;
-                u32 b = __ballot_sync(0xFFFFFFFFu, push);
-                if (b) {
-                    u32 tot = __popc(b);
-                    if (stack_n + tot <= STACK_CAP) {
-                        if (push) W.stack[stack_n + __popc(b & lt)] = round == 0 ? itA : itB;
-                        stack_n += tot;
-                    } else {
-                        ovf |= __reduce_or_sync(0xFFFFFFFFu, push ? (1u << topic) : 0u);
-                    }
-                }
-            }
-            __syncwarp();
-        };
-
-        // root of every topic (depth 0): the record comes from the kernel parameters
-        {
+                if (l < need) s_tok[l][tid] = __ldcs(p.tok + static_cast<size_t>(l) * p.n + t);
             NodeRec r{0u, tv.root_plus, tv.root_hash_ref, 0u, tv.root_mask, tv.root_hash_cnt};
-            consume(active, lane, 0u, L, r, active && (m & META_DOLLAR) != 0);
-        }
-
-        while (stack_n) {
-            const u32 take = min(stack_n, 32u);
-            bool have = lane < take;
-            u64 it = have ? W.stack[stack_n - 1 - lane] : 0ull;
-            stack_n -= take;
-            __syncwarp();
-            const u32 hi = static_cast<u32>(it >> 32), arg = static_cast<u32>(it);
-            const u32 topic = hi & 31u, d = (hi >> 5) & 0xFFFFu, kind = (hi >> 21) & 1u;
-            have = have && !((ovf >> topic) & 1u);
-            NodeRec r{};
-            bool hit = false;
-            u32 Lt = 0;
-            if (have) {
-                Lt = W.nlev[topic];
-                u32 tk = kind == KIND_PROBE ? W.tok[d - 1][topic] : 0u;
-                hit = load_record(tv, kind, arg, tk, r);
+            u32 d = 0, pmask = 0, hotmask = 0;
+            bool hot = false;                          // current branch lies below a shared '+' edge
+            bool droot = (m & META_DOLLAR) != 0;      // `$`-rule: root wildcards skipped (trie.rs:312-318)
+            u32 lV = 0, lE = 0, lF = 0;
+            for (;;) {
+                if (STATS) { lV++; lE += d < L; }
+                // '#' child matches the rest of the path and, on exhaustion, the parent (trie.rs:302-308, 321-327)
+                const u32 c1 = droot ? 0u : (r.cnts & 0xFFFFu);
+                const u32 c2 = (d == L) ? (r.cnts >> 16) : 0u;                       // own values (trie.rs:309-310)
+                if (c1) {
+                    if (c1 == CNT_BIG || ndesc >= pool_rows) { defer = true; break; }
+                    dpool[static_cast<size_t>(ndesc) * nthreads + gtid] = Desc{r.hash_ref, c1};
+                    ++ndesc; total += c1;
+                    if (STATS) lF++;
+                }
+                if (c2) {
+                    if (c2 == CNT_BIG || ndesc >= pool_rows) { defer = true; break; }
+                    dpool[static_cast<size_t>(ndesc) * nthreads + gtid] = Desc{r.own_ref, c2};
+                    ++ndesc; total += c2;
+                    if (STATS) lF++;
+                }
+                bool down = false;
+                if (d < L) {
+                    if (r.plus != 0 && !droot) {                                                 // '+' child (trie.rs:330-334)
+                        s_pend[d][tid] = r.plus; pmask |= 1u << d;
+                        if (hot || d <= 2) hotmask |= 1u << d; else hotmask &= ~(1u << d);
+                    }
+                    if (r.mask != 0) {
+                        const u32 tk = s_tok[d][tid];
+                        if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) {                      // literal child (trie.rs:338-342)
+                            NodeRec c;
+                            const bool hit = load_record(tv, KIND_PROBE, r.node, tk, c, (hot || d <= 1) ? pol_hot : pol_cold);
+                            if (STATS) {   // diagnostics: probes / misses per depth, slot loads per probe
+                                atomicAdd(p.stats + 4 + min(d, 7u), 1ull);
+                                if (!hit) atomicAdd(p.stats + 12 + min(d, 7u), 1ull);
+                                u32 idx = edge_hash(r.node, tk) & tv.edge_mask, steps = 1;
+                                while (tv.edges[idx].child != 0 && !(tv.edges[idx].parent == r.node && tv.edges[idx].token == tk)) { idx = (idx + 1) & tv.edge_mask; ++steps; }
+                                atomicAdd(p.stats + 20, static_cast<unsigned long long>(steps));
+                            }
+                            if (hit) { r = c; ++d; down = true; }
+                        }
+                    }
+                }
+                droot = false;
+                if (!down) {
+                    if (pmask == 0) break;
+                    const u32 pd = 31u - __clz(pmask);          // resume the deepest parked '+' child
+                    pmask &= ~(1u << pd);
+                    hot = (hotmask >> pd) & 1u;
+                    load_record(tv, KIND_PLUS, s_pend[pd][tid], 0u, r, hot ? pol_hot : pol_cold);
+                    d = pd + 1;
+                }
             }
-            consume(hit, topic, d, Lt, r, false);
+            if (STATS && !defer) { sV += lV; sE += lE; sF += lF; sM += total; }
         }
 
-        // ---- publish: one contiguous list per topic inside one chunk per tile
-        __threadfence_block();   // descriptors written by other lanes of this warp
-        W.cnt[lane] = 0;
-        __syncwarp();
-        for (u32 i = lane; i < pool_n; i += 32) {
-            Desc dsc = pool[i];
-            u32 tg = (dsc.meta >> 16) & 31u;
-            if (!((ovf >> tg) & 1u)) { atomicAdd(&W.cnt[tg], dsc.meta & 0xFFFFu); if (STATS) atomicAdd(&W.st[2][tg], 1u); }
-        }
-        __syncwarp();
-        const u32 c = W.cnt[lane];
-        u32 inc = c;
+        // ---- publish: one contiguous list per topic inside one chunk per tile ------------------------
+        const u32 mine = (active && !defer) ? total : 0u;
+        const u32 nd = (active && !defer) ? ndesc : 0u;
+        u32 inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
-        const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        const u32 pre = inc - c;
+        const u32 wtotal = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const u32 pre = inc - mine;
         unsigned long long base = 0;
-        if (lane == 0 && total) base = atomicAdd(p.cursor, static_cast<unsigned long long>(total));
+        if (lane == 0 && wtotal) base = atomicAdd(p.cursor, static_cast<unsigned long long>(wtotal));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        const bool fits = base + total <= p.cap_ids;
-        W.cur[lane] = pre;
-        __syncwarp();
-        if (fits && total) {
-            for (u32 i0 = 0; i0 < pool_n; i0 += 32) {        // 32 descriptors at a time, one per lane
-                const u32 i = i0 + lane;
-                Desc dsc = i < pool_n ? pool[i] : Desc{0u, 0u};
-                const u32 tg = (dsc.meta >> 16) & 31u;
-                const u32 ni = (i < pool_n && !((ovf >> tg) & 1u)) ? (dsc.meta & 0xFFFFu) : 0u;
-                const u32 dst = ni ? atomicAdd(&W.cur[tg], ni) : 0u;      // position inside the tile chunk
+        const bool fits = base + wtotal <= p.cap_ids;
+        if (in_range && !defer) p.spans[t] = make_uint2(fits ? static_cast<u32>(base + pre) : 0u, mine);
+        const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, nd);
+        if (fits && wtotal) {
+            u32* __restrict__ out = p.out_ids + base;
+            u32 cur = pre;                                    // this lane's write position inside the tile chunk
+            for (u32 k = 0; k < maxd; ++k) {                  // row k: the k-th descriptor of every lane
+                Desc dsc = k < nd ? dpool[static_cast<size_t>(k) * nthreads + gtid] : Desc{0u, 0u};
+                const u32 ni = dsc.cnt;
+                const u32 dst = cur;
+                cur += ni;
                 u32 sc = ni;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, sc, o); if (lane >= o) sc += v; }
@@ -346,15 +330,13 @@ k_match_fast(MatchParams p, Desc* __restrict__ gpool, u32 pool_cap) {
                     const u32 o_n = __shfl_sync(0xFFFFFFFFu, ni, lo);
                     const u32 o_dst = __shfl_sync(0xFFFFFFFFu, dst, lo);
                     if (e < tot) {
-                        const u32 k = e - o_exc;
-                        p.out_ids[base + o_dst + k] = (o_n == 1) ? o_ref : tv.values[o_ref + k];
+                        const u32 kk = e - o_exc;
+                        __stcs(out + o_dst + kk, (o_n == 1) ? o_ref : tv.values[o_ref + kk]);   // streaming store: written once
                     }
                 }
             }
         }
-        const bool deferred = slow_pre || (active && ((ovf >> lane) & 1u));
-        if (in_range && !deferred) p.spans[t] = make_uint2(fits ? static_cast<u32>(base + pre) : 0u, c);
-        if (STATS && active && !deferred) { sV += W.st[0][lane]; sE += W.st[1][lane]; sF += W.st[2][lane]; sM += c; }
+        const bool deferred = in_range && defer;
         u32 db = __ballot_sync(0xFFFFFFFFu, deferred);
         if (db) {
             u32 sb = 0;
@@ -362,7 +344,6 @@ k_match_fast(MatchParams p, Desc* __restrict__ gpool, u32 pool_cap) {
             sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
             if (deferred) p.slow_list[sb + __popc(db & lt)] = t;
         }
-        __syncwarp();
     }
     if (STATS) {
 #pragma unroll
