@@ -124,6 +124,23 @@ int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_topics_blob, uin
                                     uint32_t* d_out_ids, uint64_t cap_ids, uint64_t* d_needed,
                                     int32_t* d_status, void* stream, gm_work* work);
 
+/* ---- retained-message tree: RetainTree<u32> (rmqtt/src/retain.rs:202-257), driven by RetainStorage::set
+ *      (rmqtt-plugins/rmqtt-retainer/src/ram.rs:55-73 -> rmqtt/src/retain.rs:131-149: remove, then insert unless the
+ *      payload is empty).  `value` is the caller's handle of the retained message; set replaces (Option::replace).  */
+int32_t gm_retain_set(gm_engine* e, const char* topic, uint32_t len, uint32_t value, int32_t* had_old, uint32_t* old_value);
+int32_t gm_retain_remove(gm_engine* e, const char* topic, uint32_t len, int32_t* had_old, uint32_t* old_value);
+int32_t gm_retain_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets /* n+1 */, const uint32_t* values,
+                            uint64_t n, uint64_t* n_set);
+/* RetainStorage::get (rmqtt/src/retain.rs:152-169 -> RetainTree::matches :291-367) for a batch of SUBSCRIBE topic
+ * FILTERS: out_spans[i] locates the handles of the retained messages filter i matches (order unspecified).
+ * Same capacity / status protocol as gm_match_batch.                                                          */
+int32_t gm_retain_match_batch(gm_engine* e, const char* filters_blob, const uint32_t* filter_offsets, uint64_t n,
+                              gm_span* out_spans, uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed, int32_t* status);
+/* Same with device buffers on `stream`; synchronises the stream before returning (*needed is a host pointer). */
+int32_t gm_retain_match_batch_device(gm_engine* e, const void* d_filters_blob, uint64_t blob_bytes,
+                                     const uint32_t* d_filter_offsets, uint64_t n, gm_span* d_out_spans,
+                                     uint32_t* d_out_ids, uint64_t cap_ids, uint64_t* needed, int32_t* d_status, void* stream);
+
 /* ---- tokeniser only (Topic::from_str for a batch) — used by tests to pin the device dictionary.
  *      out_tokens: [max_tok][n] u32 (level-major), out_meta: [n] (bits 0..23 levels, bit 30 '$', bit 31 invalid) */
 int32_t gm_tokenize_batch(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
@@ -142,7 +159,8 @@ uint64_t gm_kernel_launches(gm_engine* e);
 uint32_t gm_shard_of(const char* topic_or_filter, uint32_t len, uint32_t n_shards);
 /* DEBUG/TEST: read-only view of the host mirror of a device table, in device layout (rmqtt_b200/csrc/layout.h).
  * which: 0 edges(32 B) 1 plus(32 B) 2 ranges(8 B) 3 values(4 B) 4 dict(32 B) 5 long-string pool(1 B)
- *        6 root record {plus, hash_ref, mask, max_depth, hash_cnt}.  Valid until the next mutating call.           */
+ *        6 root record {plus, hash_ref, mask, max_depth, hash_cnt}; retained tree: 7 nodes(32 B) 8 child blocks(16 B)
+ *        9 pre-order values(4 B).  Valid until the next mutating call.                                       */
 int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t* count);
 /* pinned host memory for the host-buffer entry points */
 void* gm_host_alloc(uint64_t bytes);

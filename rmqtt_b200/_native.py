@@ -61,6 +61,11 @@ SIGNATURES = {
     "gm_match_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
     "gm_match_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp]),
     "gm_match_batch_device_stats": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp, _P(GmWork)]),
+    "gm_retain_set": (_i32, [_vp, _cp, _u32, _u32, _P(_i32), _P(_u32)]),
+    "gm_retain_remove": (_i32, [_vp, _cp, _u32, _P(_i32), _P(_u32)]),
+    "gm_retain_bulk_load": (_i32, [_vp, _vp, _vp, _vp, _u64, _P(_u64)]),
+    "gm_retain_match_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
+    "gm_retain_match_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp, _vp]),
     "gm_tokenize_batch": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gm_get_stats": (_i32, [_vp, _P(GmStats)]),
     "gm_kernel_ms_ring": (_i32, [_vp, _vp, _u32, _P(_u32)]),

@@ -14,6 +14,8 @@
 #include "../../include/gpumqtt.h"
 #include "host_trie.h"
 #include "kernels.cuh"
+#include "retain_kernels.cuh"
+#include "retain_tree.h"
 
 using namespace gm;
 
@@ -70,6 +72,7 @@ struct gm_engine {
     u32 flags = 0;
     int num_sms = 0;
     HostTrie trie;
+    RetainTreeHost rtree{&trie};     // retained-message tree (shares the level dictionary)
     cudaStream_t stream = nullptr;   // host-buffer matches
     cudaStream_t side = nullptr;     // flush
     static constexpr int RING = 64;   // per-kernel timing events of the last RING match calls
@@ -83,6 +86,10 @@ struct gm_engine {
     // scratch
     DevBuf d_tok, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data;
     DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
+    // retained tree (device copy of the flattened arrays) + scratch of the retained lookup
+    DevBuf d_rnodes, d_rkids, d_redges, d_rvals;
+    DevBuf d_rfront[2], d_rdescs, d_rctl, d_rq;
+    u32 r_cap_items = 1u << 20, r_cap_desc = 1u << 20;
     u64 launches = 0;
 
     explicit gm_engine(u32 max_levels) : trie(max_levels) {}
@@ -159,12 +166,35 @@ struct gm_engine {
         return GM_OK;
     }
 
+    RetainView rview() const {
+        RetainView v{};
+        v.nodes = d_rnodes.as<RNode>(); v.kids = d_rkids.as<RKid>(); v.edges = d_redges.as<REdge>(); v.vals = d_rvals.as<u32>();
+        v.edge_mask = static_cast<u32>(rtree.redges.size() - 1);
+        v.root_plain_kids = rtree.root_plain_kids; v.root_plain_val_hi = rtree.root_plain_val_hi; v.max_depth = rtree.max_depth;
+        return v;
+    }
+
+    template <class T>
+    int upload_whole(DevBuf& buf, const std::vector<T>& host) {
+        CUDA_TRY(buf.ensure(std::max<size_t>(host.size() * sizeof(T), 256)));
+        if (!host.empty()) CUDA_TRY(cudaMemcpyAsync(buf.p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, side));
+        return GM_OK;
+    }
+
     int flush_locked() {
-        if (flags & GM_FLAG_HOST_ONLY) { trie.sync(); return GM_OK; }
-        if (!trie.any_dirty()) return GM_OK;
+        if (flags & GM_FLAG_HOST_ONLY) { trie.sync(); if (rtree.dirty) rtree.flatten(); return GM_OK; }
+        if (!trie.any_dirty() && !rtree.dirty) return GM_OK;
         CUDA_TRY(cudaSetDevice(device));
         trie.sync();
         if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(side, ev_match, 0));   // never patch under a running match
+        if (rtree.dirty) {   // retained tree: re-flattened and shipped whole (pre-order layout; delta overlay is future work)
+            rtree.flatten();
+            int rs;
+            if ((rs = upload_whole(d_rnodes, rtree.rnodes)) != GM_OK) return rs;
+            if ((rs = upload_whole(d_rkids, rtree.rkids)) != GM_OK) return rs;
+            if ((rs = upload_whole(d_redges, rtree.redges)) != GM_OK) return rs;
+            if ((rs = upload_whole(d_rvals, rtree.rvals)) != GM_OK) return rs;
+        }
         int st;
         if ((st = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return st;
         if ((st = upload_table(d_dict, trie.dict, trie.full_dict, trie.dirty_dict, up_dict_slots)) != GM_OK) return st;
@@ -232,6 +262,71 @@ struct gm_engine {
         match_recorded = true;
         return GM_OK;
     }
+
+    // ---- retained lookup: tokenise filters -> frontier BFS (one step kernel per tree level) -> publish ----
+    struct RCtl { unsigned long long grand; u32 n_desc; u32 err; u32 counts[1]; };   // counts[max_depth + 3] follow
+
+    int enqueue_retain(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s) {
+        const u32 nq = static_cast<u32>(n);
+        const u32 depth = rtree.max_depth;
+        const u32 S = depth + 2;                       // the walk reads filter levels pos and pos+1 with pos <= tree depth
+        const size_t ctl_bytes = sizeof(RCtl) + (depth + 3) * sizeof(u32);
+        CUDA_TRY(d_tok.ensure(static_cast<size_t>(S) * nq * sizeof(u32)));
+        CUDA_TRY(d_meta.ensure(nq * sizeof(u32)));
+        CUDA_TRY(d_rq.ensure(static_cast<size_t>(nq) * 3 * sizeof(u32)));
+        CUDA_TRY(d_rctl.ensure(ctl_bytes));
+        CUDA_TRY(d_rfront[0].ensure(static_cast<size_t>(r_cap_items) * sizeof(RItem)));
+        CUDA_TRY(d_rfront[1].ensure(static_cast<size_t>(r_cap_items) * sizeof(RItem)));
+        CUDA_TRY(d_rdescs.ensure(static_cast<size_t>(r_cap_desc) * sizeof(RDesc)));
+        CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
+        if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(s, ev_match, 0));
+        CUDA_TRY(cudaMemsetAsync(d_rctl.p, 0, ctl_bytes, s));
+        CUDA_TRY(cudaMemsetAsync(d_rq.p, 0, static_cast<size_t>(nq) * 3 * sizeof(u32), s));
+        RCtl* ctl = d_rctl.as<RCtl>();
+        u32* qtotal = d_rq.as<u32>();
+        u32* qbase = qtotal + nq;
+        u32* qcur = qbase + nq;
+        cudaEvent_t* ev_t = ev_ring[ring_n % RING];
+        CUDA_TRY(cudaEventRecord(ev_t[0], s));
+        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, view(), S, d_tok.as<u32>(), d_meta.as<u32>(), d_status_);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ev_t[1], s));
+        RetainParams rp{};
+        rp.v = rview(); rp.qtok = d_tok.as<u32>(); rp.qmeta = d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
+        rp.descs = d_rdescs.as<RDesc>(); rp.n_desc = &ctl->n_desc; rp.cap_items = r_cap_items; rp.cap_desc = r_cap_desc;
+        rp.qtotal = qtotal; rp.err = &ctl->err;
+        k_retain_init<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RItem>(), &ctl->counts[0]);
+        const int grid = num_sms * 8;
+        for (u32 lvl = 0; lvl <= depth; ++lvl)
+            k_retain_step<<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RItem>(), &ctl->counts[lvl], d_rfront[(lvl + 1) & 1].as<RItem>(), &ctl->counts[lvl + 1]);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ev_t[2], s));
+        k_retain_scan<<<1, 1024, 0, s>>>(qtotal, nq, qbase, reinterpret_cast<uint2*>(d_spans_), &ctl->grand);
+        k_retain_expand<<<grid, 256, 0, s>>>(d_rdescs.as<RDesc>(), &ctl->n_desc, r_cap_desc, d_rvals.as<u32>(), qbase, qcur, d_ids_, cap_ids);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ev_t[3], s));
+        ring_n++;
+        launches += 4 + depth + 1;
+        CUDA_TRY(cudaEventRecord(ev_match, s));
+        match_recorded = true;
+        return GM_OK;
+    }
+
+    // runs the pipeline, growing the frontier / descriptor scratch until nothing overflowed; leaves *total
+    int run_retain(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s, u64* total) {
+        for (int attempt = 0; attempt < 12; ++attempt) {
+            int st = enqueue_retain(d_blob_, d_offs_, n, d_spans_, d_ids_, cap_ids, d_status_, s);
+            if (st != GM_OK) return st;
+            RCtl h{};
+            CUDA_TRY(cudaMemcpyAsync(&h, d_rctl.p, sizeof(RCtl), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (h.err == 0) { *total = h.grand; return GM_OK; }
+            if (h.err & 1u) { if (r_cap_items > (1u << 30)) break; r_cap_items *= 4; }
+            if (h.err & 2u) { if (r_cap_desc > (1u << 30)) break; r_cap_desc *= 4; }
+        }
+        g_err = "retained lookup: frontier does not fit the scratch limits, split the batch";
+        return GM_ERR_TOO_LARGE;
+    }
 };
 
 // =====================================================================================================
@@ -285,7 +380,8 @@ void gm_destroy(gm_engine* e) {
     cudaDeviceSynchronize();
     for (DevBuf* b : {&e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
                       &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_gpool, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
-                      &e->d_spans, &e->d_ids, &e->d_status})
+                      &e->d_spans, &e->d_ids, &e->d_status, &e->d_rnodes, &e->d_rkids, &e->d_redges, &e->d_rvals, &e->d_rfront[0],
+                      &e->d_rfront[1], &e->d_rdescs, &e->d_rctl, &e->d_rq})
         b->release();
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->side) cudaStreamDestroy(e->side);
@@ -417,6 +513,93 @@ int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, 
     return GM_OK;
 }
 
+// ---- retained-message tree ----------------------------------------------------------------------------
+int32_t gm_retain_set(gm_engine* e, const char* topic, uint32_t len, uint32_t value, int32_t* had_old, uint32_t* old_value) {
+    if (!e || (!topic && len)) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    bool had = false; u32 old = 0;
+    int st = e->rtree.set(topic, len, value, &had, &old);
+    if (had_old) *had_old = had ? 1 : 0;
+    if (old_value && had) *old_value = old;
+    return map_parse(st, "gm_retain_set");
+}
+
+int32_t gm_retain_remove(gm_engine* e, const char* topic, uint32_t len, int32_t* had_old, uint32_t* old_value) {
+    if (!e || (!topic && len)) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    bool had = false; u32 old = 0;
+    int st = e->rtree.remove(topic, len, &had, &old);
+    if (had_old) *had_old = had ? 1 : 0;
+    if (old_value && had) *old_value = old;
+    return map_parse(st, "gm_retain_remove");
+}
+
+int32_t gm_retain_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets, const uint32_t* values, uint64_t n, uint64_t* n_set) {
+    if (!e || (n && (!blob || !offsets || !values))) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    uint64_t ok = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (e->rtree.set(blob + offsets[i], offsets[i + 1] - offsets[i], values[i], nullptr, nullptr) == PARSE_OK) ok++;
+    if (n_set) *n_set = ok;
+    return GM_OK;
+}
+
+int32_t gm_retain_match_batch_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
+                                     gm_span* d_spans, uint32_t* d_ids, uint64_t cap_ids, uint64_t* needed, int32_t* d_status, void* stream) {
+    if (!e || (n && (!d_offs || !d_spans || !d_status))) return GM_ERR_INVALID_ARG;
+    if (needed) *needed = 0;
+    if (n == 0) return GM_OK;
+    if (blob_bytes > 0xFFFFFFFFull || n > 0xFFFFFFF0ull) { g_err = "filter batch too large"; return GM_ERR_TOO_LARGE; }
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_rnodes.p || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    u64 total = 0;
+    int st = e->run_retain(d_blob, d_offs, n, d_spans, d_ids, std::min<u64>(cap_ids, 0xFFFFFFFFull), d_status, static_cast<cudaStream_t>(stream), &total);
+    if (st != GM_OK) return st;
+    if (needed) *needed = total;
+    if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
+    if (total > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
+    return GM_OK;
+}
+
+int32_t gm_retain_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, uint32_t* out_ids,
+                              uint64_t cap_ids, uint64_t* needed, int32_t* status) {
+    if (!e || (n && (!offsets || !out_spans || !status)) || (cap_ids && !out_ids)) return GM_ERR_INVALID_ARG;
+    if (needed) *needed = 0;
+    if (n == 0) return GM_OK;
+    if (n > 0xFFFFFFF0ull) { g_err = "filter batch too large"; return GM_ERR_TOO_LARGE; }
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_rnodes.p || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    const u64 blob_bytes = offsets[n];
+    cudaStream_t s = e->stream;
+    CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
+    CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
+    CUDA_TRY(e->d_spans.ensure(n * sizeof(gm_span)));
+    CUDA_TRY(e->d_status.ensure(n * sizeof(int32_t)));
+    CUDA_TRY(e->d_ids.ensure(std::max<u64>(cap_ids, 1) * sizeof(u32)));
+    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
+    u64 total = 0;
+    int st = e->run_retain(e->d_blob.p, e->d_offs.as<u32>(), n, e->d_spans.as<gm_span>(), e->d_ids.as<u32>(), std::min<u64>(cap_ids, 0xFFFFFFFFull),
+                           e->d_status.as<int32_t>(), s, &total);
+    if (st != GM_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(status, e->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_spans, e->d_spans.p, n * sizeof(gm_span), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (needed) *needed = total;
+    for (uint64_t i = 0; i < n; ++i) if (status[i]) status[i] = GM_ERR_INVALID_TOPIC;
+    if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
+    if (total > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
+    if (total) {
+        CUDA_TRY(cudaMemcpyAsync(out_ids, e->d_ids.p, total * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return GM_OK;
+}
+
 int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, uint32_t max_tok, uint32_t* out_tokens, uint32_t* out_meta) {
     if (!e || !max_tok || (n && (!offsets || !out_tokens || !out_meta))) return GM_ERR_INVALID_ARG;
     if (n == 0) return GM_OK;
@@ -459,7 +642,9 @@ int32_t gm_get_stats(gm_engine* e, gm_stats* out) {
     out->value_words = t.values.size(); out->garbage_value_words = t.garbage_values;
     out->device_bytes = e->d_edges.cap + e->d_plus.cap + e->d_ranges.cap + e->d_values.cap + e->d_dict.cap + e->d_pool.cap;
     out->max_depth = t.max_depth;
-    out->pending = t.any_dirty() ? 1 : 0;
+    out->pending = (t.any_dirty() || e->rtree.dirty) ? 1 : 0;
+    out->retained_values = e->rtree.values_size(); out->retained_nodes = e->rtree.nodes_size();
+    out->device_bytes += e->d_rnodes.cap + e->d_rkids.cap + e->d_redges.cap + e->d_rvals.cap;
     return GM_OK;
 }
 
@@ -496,6 +681,9 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
         case 4: *ptr = t.dict.data(); *count = t.dict.size(); break;
         case 5: *ptr = t.pool.data(); *count = t.pool.size(); break;
         case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; root[4] = t.root_hash_cnt; *ptr = root; *count = 5; break;
+        case 7: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rnodes.data(); *count = e->rtree.rnodes.size(); break;
+        case 8: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rkids.data(); *count = e->rtree.rkids.size(); break;
+        case 9: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rvals.data(); *count = e->rtree.rvals.size(); break;
         default: return GM_ERR_INVALID_ARG;
     }
     return GM_OK;

@@ -91,6 +91,8 @@ u32 HostTrie::intern(const char* s, u32 len, bool create) {
     }
     dict[i] = d;
     dict_count_++;
+    if (tok_dollar_.size() <= d.w[0]) tok_dollar_.resize(d.w[0] + 1, 0);
+    tok_dollar_[d.w[0]] = (len > 0 && s[0] == '$') ? 1 : 0;
     if (!full_dict) dirty_dict.push_back(i);
     return d.w[0];
 }

@@ -74,9 +74,11 @@ class HostTrie {
     // host-side tokeniser (tests compare the device tokeniser against it)
     u32 lookup_token(const char* s, u32 len) const;
     static u32 level0_hash(const char* s, u32 len);
+    // Topic::from_str -> tokens (shared with the retained tree, which interns into the same dictionary)
+    int parse(const char* f, u32 len, bool intern_new, std::vector<u32>& toks);
+    bool token_is_dollar(u32 tok) const { return tok < tok_dollar_.size() && tok_dollar_[tok]; }
 
   private:
-    int parse(const char* f, u32 len, bool intern_new, std::vector<u32>& toks);
     u32 intern(const char* s, u32 len, bool create);
     u32 find_edge(u32 parent, u32 token) const;         // returns slot index or ~0u
     u32 add_edge(u32 parent, u32 token);                // creates the child node, returns its id
@@ -91,6 +93,7 @@ class HostTrie {
     std::unordered_map<u32, std::vector<u32>> multi_;   // node -> sorted values when nvals > 1
     std::vector<u32> dirty_nodes_;
     std::vector<u32> scratch_toks_;
+    std::vector<u8> tok_dollar_;      // token -> level string starts with '$' (Level::Metadata)
     u64 edge_count_ = 0, dict_count_ = 0;
     u32 next_token_ = TOK_FIRST;
     u64 values_size_ = 0, live_nodes_ = 0;

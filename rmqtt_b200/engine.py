@@ -152,6 +152,51 @@ class Engine:
         """TopicTree::matches for one topic -> sorted multiset (None if invalid)."""
         return self.match_topics([topic]).sorted_list(0)
 
+    # ---- retained-message tree: RetainTree insert / remove / matches (rmqtt/src/retain.rs) ------------------
+    def retain_set(self, topic, value: int):
+        """Returns the replaced value or None."""
+        b = _b(topic)
+        had, old = C.c_int32(0), C.c_uint32(0)
+        self._check(self._lib.gm_retain_set(self._h, b, len(b), value, C.byref(had), C.byref(old)))
+        return int(old.value) if had.value else None
+
+    def retain_remove(self, topic):
+        b = _b(topic)
+        had, old = C.c_int32(0), C.c_uint32(0)
+        self._check(self._lib.gm_retain_remove(self._h, b, len(b), C.byref(had), C.byref(old)))
+        return int(old.value) if had.value else None
+
+    def retain_bulk_load(self, blob: np.ndarray, offs: np.ndarray, values: np.ndarray) -> int:
+        n_set = C.c_uint64(0)
+        self._check(self._lib.gm_retain_bulk_load(self._h, _vp(blob), _vp(offs), _vp(values), len(values), C.byref(n_set)))
+        return int(n_set.value)
+
+    def retain_match_batch(self, blob: np.ndarray, offs: np.ndarray, cap_ids: int | None = None) -> MatchResult:
+        n = len(offs) - 1
+        spans = np.zeros((n, 2), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        cap = int(cap_ids) if cap_ids is not None else max(1024, 64 * n)
+        while True:
+            ids = np.empty(cap, dtype=np.uint32)
+            needed = C.c_uint64(0)
+            rc = self._lib.gm_retain_match_batch(self._h, _vp(blob), _vp(offs), n, _vp(spans), _vp(ids), cap, C.byref(needed), _vp(status))
+            if rc == N.GM_ERR_CAPACITY and cap_ids is None:
+                cap = int(needed.value)
+                continue
+            self._check(rc)
+            return MatchResult(spans, ids[:int(needed.value)], status, int(needed.value))
+
+    def retain_matches(self, filt):
+        blob, offs = pack([filt])
+        return self.retain_match_batch(blob, offs).sorted_list(0)
+
+    def retain_match_batch_device(self, d_blob, d_offs, d_spans, d_ids, d_status, stream: int) -> int:
+        n = d_offs.numel() - 1
+        needed = C.c_uint64(0)
+        self._check(self._lib.gm_retain_match_batch_device(self._h, d_blob.data_ptr(), d_blob.numel(), d_offs.data_ptr(), n, d_spans.data_ptr(),
+                                                           d_ids.data_ptr(), d_ids.numel(), C.byref(needed), d_status.data_ptr(), stream))
+        return int(needed.value)
+
     # ---- device-resident variant (torch tensors; asynchronous on the current torch stream) -----------
     def match_batch_device(self, d_blob, d_offs, d_spans, d_ids, d_needed, d_status, stream: int, work: bool = False):
         n = d_offs.numel() - 1
@@ -183,7 +228,8 @@ class Engine:
         """Host mirror of the device tables as numpy arrays (copies).  Test/diagnostic use only."""
         out = {}
         spec = {0: ("edges", np.uint32, 8), 1: ("plus", np.uint32, 8), 2: ("ranges", np.uint32, 2), 3: ("values", np.uint32, 1),
-                4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1)}  # root = {plus, hash_ref, mask, max_depth, hash_cnt}
+                4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1),  # root = {plus, hash_ref, mask, max_depth, hash_cnt}
+                7: ("rnodes", np.uint32, 8), 8: ("rkids", np.uint32, 4), 9: ("rvals", np.uint32, 1)}
         for which, (name, dt, width) in spec.items():
             ptr, cnt = C.c_void_p(), C.c_uint64(0)
             self._check(self._lib.gm_debug_table(self._h, which, C.byref(ptr), C.byref(cnt)))

@@ -1,0 +1,92 @@
+"""CPU tier: retained-tree host mirror + pre-order flattening (rmqtt_b200/csrc/retain_tree.cpp) against the
+oracle's RetainTree restatement, through a pure-Python model of the retained-lookup kernels."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from rmqtt_b200.engine import Engine
+
+from _gen import rand_filter, rand_topic
+from _retainwalk import RetainTables
+
+
+def _tables(eng):
+    eng.flush()
+    t = eng.debug_tables()
+    R = RetainTables(t)
+    # root_plain_* are part of the view; recompute them the way flatten() defines them
+    nodes, kids, vals = t["rnodes"], t["rkids"], t["rvals"]
+    fk, nk = int(nodes[0, 0]), int(nodes[0, 1])
+    plain = 0
+    for j in range(nk):
+        child = int(kids[fk + j, 1])
+        # `$` children are ordered last: the first child whose token string starts with '$' ends the plain block
+        plain += 1
+    R.set_root_plain(plain, int(nodes[0, 4]))
+    return R, t
+
+
+def _plain_split(eng, R, t, dollar_roots):
+    """root_plain_kids / root_plain_val_hi given which level-0 strings start with '$'."""
+    nodes, kids = t["rnodes"], t["rkids"]
+    fk, nk = int(nodes[0, 0]), int(nodes[0, 1])
+    toks = {R.T.token(s.encode()) for s in dollar_roots}
+    plain = sum(1 for j in range(nk) if int(kids[fk + j, 0]) not in toks)
+    # children are ordered plain-first
+    assert all(int(kids[fk + j, 0]) not in toks for j in range(plain))
+    hi = int(nodes[int(kids[fk + plain, 1]), 3]) if plain < nk else int(nodes[0, 4])
+    R.set_root_plain(plain, hi)
+
+
+def test_golden_retain_rs_451_475(golden):
+    g = golden["retain_A3"]
+    eng, tree = Engine(host_only=True), orc.RetainTree()
+    for topic, v in g["inserts"] + g["more_inserts"]:
+        eng.retain_set(topic, v & 0xFFFFFFFF)
+        tree.insert(topic, v & 0xFFFFFFFF)
+    R, t = _tables(eng)
+    _plain_split(eng, R, t, [])
+    for f, _ in g["matches"] + g["more_matches"] + golden["derived_A5"]["retain_on_A3"]:
+        assert R.match(f.encode()) == tree.matches(f), f
+    st = eng.stats()
+    assert st["retained_values"] == tree.values_size() == 12 and st["retained_nodes"] == tree.nodes_size()
+
+
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_random_differential(seed):
+    rng = random.Random(seed)
+    eng, tree = Engine(host_only=True), orc.RetainTree()
+    topics = []
+    for step in range(700):
+        if topics and rng.random() < 0.25:
+            t = rng.choice(topics)
+            try:
+                got = eng.retain_remove(t)
+            except Exception:
+                continue
+            assert got == tree.remove(t)
+        else:
+            t = rand_topic(rng, max_depth=5) if rng.random() < 0.9 else rand_filter(rng, 5)   # literal '+' / '#' levels too
+            v = rng.randint(0, 2**32 - 2)
+            try:
+                old = eng.retain_set(t, v)
+            except Exception:
+                with pytest.raises(ValueError):
+                    tree.insert(t, v)
+                continue
+            prev = tree.remove(t)
+            tree.insert(t, v)
+            assert old == prev
+            topics.append(t)
+        if step % 175 == 174:
+            st = eng.stats()
+            assert st["retained_values"] == tree.values_size() and st["retained_nodes"] == tree.nodes_size()
+            R, t = _tables(eng)
+            _plain_split(eng, R, t, ["$SYS", "$q", "$share"])
+            for _ in range(200):
+                f = rand_filter(rng, 6)
+                want = tree.matches(f)
+                got = R.match(f.encode())
+                assert got == want, f
