@@ -58,6 +58,8 @@ struct Ctrl {                       // device control block, zeroed before every
     u32 tile_counter;
 };
 
+static_assert(GM_ERR_INVALID_TOPIC == -2, "k_tokenize writes the per-topic status code directly");
+
 // fast-path geometry: one topic per thread, 512 threads per CTA, 4 CTAs per SM (<= 32 registers)
 constexpr int K2_FAST_L = 8;       // levels staged in shared memory; deeper topics take the deferred kernel
 constexpr int K2_THREADS = 512;
@@ -75,6 +77,10 @@ struct gm_engine {
     RetainTreeHost rtree{&trie};     // retained-message tree (shares the level dictionary)
     cudaStream_t stream = nullptr;   // host-buffer matches
     cudaStream_t side = nullptr;     // flush
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host-buffer match
+    static constexpr int MAXC = 32;  // chunks per pipelined call
+    cudaEvent_t ev_h2d[MAXC] = {}, ev_comp[MAXC] = {};
+    unsigned long long* h_cur = nullptr;             // pinned: cursor snapshot after every chunk
     static constexpr int RING = 64;   // per-kernel timing events of the last RING match calls
     cudaEvent_t ev_flush = nullptr, ev_match = nullptr;
     cudaEvent_t ev_ring[RING][4] = {};
@@ -210,7 +216,7 @@ struct gm_engine {
 
     // ---- the match pipeline, all on `s`, all buffers on the device ---------------------------------
     int enqueue_match(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids,
-                      u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats) {
+                      u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool keep_cursor = false) {
         if (n == 0) { if (d_needed) CUDA_TRY(cudaMemsetAsync(d_needed, 0, sizeof(u64), s)); return GM_OK; }
         if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
@@ -229,7 +235,9 @@ struct gm_engine {
         CUDA_TRY(d_gpool.ensure(static_cast<size_t>(k2_grid) * K2_THREADS * K2_POOL_ROWS * sizeof(Desc)));
         CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
         if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(s, ev_match, 0));   // scratch is shared: one match in flight
-        CUDA_TRY(cudaMemsetAsync(d_ctrl.p, 0, sizeof(Ctrl), s));
+        // the bump cursor over out_ids survives between the chunks of one pipelined host call
+        if (keep_cursor) CUDA_TRY(cudaMemsetAsync(static_cast<char*>(d_ctrl.p) + sizeof(unsigned long long), 0, sizeof(Ctrl) - sizeof(unsigned long long), s));
+        else CUDA_TRY(cudaMemsetAsync(d_ctrl.p, 0, sizeof(Ctrl), s));
         Ctrl* ctrl = d_ctrl.as<Ctrl>();
         const TrieView tv = view();
 
@@ -364,6 +372,13 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     eng->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < gm_engine::MAXC; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_h2d[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_comp[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaMallocHost(&eng->h_cur, gm_engine::MAXC * sizeof(unsigned long long)));
     CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_flush, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_match, cudaEventDisableTiming));
     for (auto& q : eng->ev_ring) for (auto& ev : q) CUDA_TRY(cudaEventCreate(&ev));
@@ -385,6 +400,10 @@ void gm_destroy(gm_engine* e) {
         b->release();
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->side) cudaStreamDestroy(e->side);
+    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    for (int i = 0; i < gm_engine::MAXC; ++i) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]); }
+    if (e->h_cur) cudaFreeHost(e->h_cur);
     if (e->ev_flush) cudaEventDestroy(e->ev_flush);
     if (e->ev_match) cudaEventDestroy(e->ev_match);
     for (auto& q : e->ev_ring) for (auto& ev : q) if (ev) cudaEventDestroy(ev);
@@ -481,35 +500,59 @@ int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, 
     if (!e || (n && (!offsets || !out_spans || !status)) || (cap_ids && !out_ids)) return GM_ERR_INVALID_ARG;
     if (needed) *needed = 0;
     if (n == 0) return GM_OK;
+    if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
     std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
     if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
     const u64 blob_bytes = offsets[n];
-    cudaStream_t s = e->stream;
+    if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;
     CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
     CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
     CUDA_TRY(e->d_spans.ensure(n * sizeof(gm_span)));
     CUDA_TRY(e->d_status.ensure(n * sizeof(int32_t)));
     CUDA_TRY(e->d_ids.ensure(std::max<u64>(cap_ids, 1) * sizeof(u32)));
-    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
-    int st = e->enqueue_match(e->d_blob.p, e->d_offs.as<u32>(), n, e->d_spans.as<gm_span>(), e->d_ids.as<u32>(), cap_ids, nullptr,
-                              e->d_status.as<int32_t>(), s, false);
-    if (st != GM_OK) return st;
-    u64 total = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, &e->d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(status, e->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_spans, e->d_spans.p, n * sizeof(gm_span), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    // Pipelined in chunks over three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of
+    // chunk c.  All chunks share one bump cursor, so the ids of chunk c are the contiguous range
+    // [cursor after c-1, cursor after c) and can be copied out as soon as that chunk's kernels finished.
+    const u64 chunk = std::max<u64>(131072, (n + gm_engine::MAXC - 1) / gm_engine::MAXC);
+    const int nchunks = static_cast<int>((n + chunk - 1) / chunk);
+    cudaStream_t sc = e->stream;
+    if (e->match_recorded) CUDA_TRY(cudaStreamWaitEvent(e->s_h2d, e->ev_match, 0));   // previous call still reads d_blob / scratch
+    for (int c = 0; c < nchunks; ++c) {
+        const u64 c0 = c * chunk, c1 = std::min<u64>(n, c0 + chunk);
+        const u64 b0 = offsets[c0], b1 = offsets[c1];
+        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(e->d_blob.p) + b0, blob + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_h2d));
+        CUDA_TRY(cudaMemcpyAsync(e->d_offs.as<u32>() + c0, offsets + c0, (c1 - c0 + 1) * sizeof(u32), cudaMemcpyHostToDevice, e->s_h2d));
+        CUDA_TRY(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const u64 c0 = c * chunk, c1 = std::min<u64>(n, c0 + chunk);
+        CUDA_TRY(cudaStreamWaitEvent(sc, e->ev_h2d[c], 0));
+        int st = e->enqueue_match(e->d_blob.p, e->d_offs.as<u32>() + c0, c1 - c0, e->d_spans.as<gm_span>() + c0, e->d_ids.as<u32>(), cap_ids, nullptr,
+                                  e->d_status.as<int32_t>() + c0, sc, false, c != 0);
+        if (st != GM_OK) return st;
+        CUDA_TRY(cudaMemcpyAsync(&e->h_cur[c], &e->d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, sc));
+        CUDA_TRY(cudaEventRecord(e->ev_comp[c], sc));
+    }
+    u64 done = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const u64 c0 = c * chunk, c1 = std::min<u64>(n, c0 + chunk);
+        CUDA_TRY(cudaEventSynchronize(e->ev_comp[c]));
+        const u64 cur = e->h_cur[c];
+        CUDA_TRY(cudaMemcpyAsync(out_spans + c0, e->d_spans.as<gm_span>() + c0, (c1 - c0) * sizeof(gm_span), cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_TRY(cudaMemcpyAsync(status + c0, e->d_status.as<int32_t>() + c0, (c1 - c0) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+        const u64 hi = std::min<u64>(cur, cap_ids);
+        if (hi > done) {
+            CUDA_TRY(cudaMemcpyAsync(out_ids + done, e->d_ids.as<u32>() + done, (hi - done) * sizeof(u32), cudaMemcpyDeviceToHost, e->s_d2h));
+            done = hi;
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->s_d2h));
+    const u64 total = e->h_cur[nchunks - 1];
     if (needed) *needed = total;
-    for (uint64_t i = 0; i < n; ++i) if (status[i]) status[i] = GM_ERR_INVALID_TOPIC;
     if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
     if (total > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
-    if (total) {
-        CUDA_TRY(cudaMemcpyAsync(out_ids, e->d_ids.p, total * sizeof(u32), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-    }
     return GM_OK;
 }
 
@@ -590,7 +633,6 @@ int32_t gm_retain_match_batch(gm_engine* e, const char* blob, const uint32_t* of
     CUDA_TRY(cudaMemcpyAsync(out_spans, e->d_spans.p, n * sizeof(gm_span), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (needed) *needed = total;
-    for (uint64_t i = 0; i < n; ++i) if (status[i]) status[i] = GM_ERR_INVALID_TOPIC;
     if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
     if (total > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
     if (total) {

@@ -142,7 +142,7 @@ k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, Tri
         ++pos;   // skip '/'
     }
     meta[t] = invalid ? META_INVALID : (lev | (dollar ? META_DOLLAR : 0u));
-    status[t] = invalid ? 1 : 0;
+    status[t] = invalid ? -2 : 0;   // GM_ERR_INVALID_TOPIC: Topic::from_str would return Err
 }
 
 // ------------------------------------------------------------------------------------------------
