@@ -33,8 +33,8 @@ sys.path.insert(0, str(ROOT))
 def _args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--subs", type=int, default=None, help="override subscription count (non-default => not the headline config)")
     ap.add_argument("--topics", type=int, default=None, help="override topics per batch")
@@ -65,7 +65,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -134,7 +134,8 @@ def run_reference(args):
     t0 = time.time()
     router.bulk_add(sb, so, sv, nthreads=min(threads, 64))
     build_s = time.time() - t0
-    sample = min(cfg.n_topics, 250_000)
+    # bounded sample per step: sized so that warmup + steps stay within a few minutes on the host cores
+    sample = min(cfg.n_topics, max(2_000, 25_000_000 // max(1, args.steps + args.warmup)))
     tb, to = wl.gen_topics(cfg, sample)
     for _ in range(max(1, args.warmup)):
         router.match_batch(tb, to, nthreads=threads)
@@ -229,7 +230,7 @@ def run_own(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.2)
     launches0 = eng.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
