@@ -90,7 +90,7 @@ struct gm_engine {
     DevBuf d_edges, d_plus, d_ranges, d_values, d_dict, d_pool;
     size_t up_plus = 0, up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
     // scratch
-    DevBuf d_tok, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data;
+    DevBuf d_tok, d_tok8, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data, d_sort, d_hist;
     DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
     // retained tree (device copy of the flattened arrays) + scratch of the retained lookup
     DevBuf d_rnodes, d_rkids, d_redges, d_rvals;
@@ -222,10 +222,22 @@ struct gm_engine {
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
         const u32 n32 = static_cast<u32>(n);
         const u32 S = std::max<u32>(1u, trie.max_depth);
-        CUDA_TRY(d_tok.ensure(static_cast<size_t>(S) * n32 * sizeof(u32)));
+        CUDA_TRY(d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * n32 * sizeof(u32) : 256));
+        CUDA_TRY(d_tok8.ensure(static_cast<size_t>(n32) * TOK8 * sizeof(u32)));
         CUDA_TRY(d_meta.ensure(n32 * sizeof(u32)));
         CUDA_TRY(d_slow.ensure(n32 * sizeof(u32)));
         CUDA_TRY(d_ctrl.ensure(sizeof(Ctrl)));
+        // locality pass scratch: bkey[n], perm[n]; hist + cursor [NBUCKETS] each
+        CUDA_TRY(d_sort.ensure(static_cast<size_t>(n32) * 11 * sizeof(u32) + 64));
+        CUDA_TRY(d_hist.ensure(2 * NBUCKETS * sizeof(u32)));
+        u32* bkey = d_sort.as<u32>();
+        u32* perm = bkey + n32;
+        u32* meta_sorted = perm + n32;
+        u32* tok8_sorted = meta_sorted + n32 + ((8 - (3 * static_cast<size_t>(n32)) % 8) % 8);   // 32-byte aligned rows
+        bool sorted_rows = true;
+        if (const char* ev = getenv("GM_SORTED_ROWS")) sorted_rows = atoi(ev) != 0;   // tuning knob
+        u32* hist = d_hist.as<u32>();
+        u32* bcursor = hist + NBUCKETS;
         const int k3_blocks = num_sms * 4;
         const u32 stack_cap = 32u * (trie.max_depth + 2u) + 64u;
         CUDA_TRY(d_gstack.ensure(static_cast<size_t>(k3_blocks) * 8 * stack_cap * sizeof(u64)));
@@ -238,23 +250,27 @@ struct gm_engine {
         // the bump cursor over out_ids survives between the chunks of one pipelined host call
         if (keep_cursor) CUDA_TRY(cudaMemsetAsync(static_cast<char*>(d_ctrl.p) + sizeof(unsigned long long), 0, sizeof(Ctrl) - sizeof(unsigned long long), s));
         else CUDA_TRY(cudaMemsetAsync(d_ctrl.p, 0, sizeof(Ctrl), s));
+        CUDA_TRY(cudaMemsetAsync(hist, 0, NBUCKETS * sizeof(u32), s));
         Ctrl* ctrl = d_ctrl.as<Ctrl>();
         const TrieView tv = view();
 
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
         k_tokenize<<<(n32 + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-            static_cast<const u8*>(d_blob_), d_offs_, n32, tv, S, d_tok.as<u32>(), d_meta.as<u32>(), d_status_);
+            static_cast<const u8*>(d_blob_), d_offs_, n32, tv, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, bkey, hist);
+        k_bucket_scan<<<1, 1024, 0, s>>>(hist, bcursor);
+        k_bucket_scatter<<<(n32 + 255) / 256, 256, 0, s>>>(bkey, bcursor, n32, perm, d_tok8.as<u32>(), d_meta.as<u32>(),
+                                                            sorted_rows ? tok8_sorted : nullptr, meta_sorted);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
 
         MatchParams mp{};
-        mp.tv = tv; mp.tok = d_tok.as<u32>(); mp.meta = d_meta.as<u32>(); mp.n = n32; mp.tok_levels = S;
+        mp.tv = tv; mp.tok8 = d_tok8.as<u32>(); mp.tok = d_tok.as<u32>(); mp.meta = d_meta.as<u32>(); mp.n = n32; mp.tok_levels = S;
         mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = d_ids_; mp.cap_ids = cap_ids;
         mp.cursor = &ctrl->cursor; mp.slow_list = d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
-        mp.flags = MP_L2_HINTS;
-        if (const char* ev = getenv("GM_K2_HINTS")) mp.flags = atoi(ev) ? MP_L2_HINTS : 0u;   // tuning knob
+        mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
+        mp.flags = sorted_rows ? MP_SORTED_ROWS : 0u;
         if (stats) k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true><<<k2_grid, K2_THREADS, 0, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
         else k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false><<<k2_grid, K2_THREADS, 0, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
         CUDA_TRY(cudaGetLastError());
@@ -264,7 +280,7 @@ struct gm_engine {
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[3], s));
         ring_n++;
-        launches += 3;
+        launches += 5;
         if (d_needed) CUDA_TRY(cudaMemcpyAsync(d_needed, &ctrl->cursor, sizeof(u64), cudaMemcpyDeviceToDevice, s));
         CUDA_TRY(cudaEventRecord(ev_match, s));
         match_recorded = true;
@@ -279,7 +295,8 @@ struct gm_engine {
         const u32 depth = rtree.max_depth;
         const u32 S = depth + 2;                       // the walk reads filter levels pos and pos+1 with pos <= tree depth
         const size_t ctl_bytes = sizeof(RCtl) + (depth + 3) * sizeof(u32);
-        CUDA_TRY(d_tok.ensure(static_cast<size_t>(S) * nq * sizeof(u32)));
+        CUDA_TRY(d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * nq * sizeof(u32) : 256));
+        CUDA_TRY(d_tok8.ensure(static_cast<size_t>(nq) * TOK8 * sizeof(u32)));
         CUDA_TRY(d_meta.ensure(nq * sizeof(u32)));
         CUDA_TRY(d_rq.ensure(static_cast<size_t>(nq) * 3 * sizeof(u32)));
         CUDA_TRY(d_rctl.ensure(ctl_bytes));
@@ -296,11 +313,11 @@ struct gm_engine {
         u32* qcur = qbase + nq;
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
-        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, view(), S, d_tok.as<u32>(), d_meta.as<u32>(), d_status_);
+        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, view(), S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
         RetainParams rp{};
-        rp.v = rview(); rp.qtok = d_tok.as<u32>(); rp.qmeta = d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
+        rp.v = rview(); rp.qtok8 = d_tok8.as<u32>(); rp.qtok = d_tok.as<u32>(); rp.qmeta = d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
         rp.descs = d_rdescs.as<RDesc>(); rp.n_desc = &ctl->n_desc; rp.cap_items = r_cap_items; rp.cap_desc = r_cap_desc;
         rp.qtotal = qtotal; rp.err = &ctl->err;
         k_retain_init<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RItem>(), &ctl->counts[0]);
@@ -393,8 +410,8 @@ void gm_destroy(gm_engine* e) {
     if (e->flags & GM_FLAG_HOST_ONLY) { delete e; return; }
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
-                      &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_gpool, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
+    for (DevBuf* b : {&e->d_tok8, &e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
+                      &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_gpool, &e->d_sort, &e->d_hist, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
                       &e->d_spans, &e->d_ids, &e->d_status, &e->d_rnodes, &e->d_rkids, &e->d_redges, &e->d_rvals, &e->d_rfront[0],
                       &e->d_rfront[1], &e->d_rdescs, &e->d_rctl, &e->d_rq})
         b->release();
@@ -651,10 +668,11 @@ int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offset
     { int st = e->flush_locked(); if (st != GM_OK) return st; }
     cudaStream_t s = e->stream;
     const u64 blob_bytes = offsets[n];
-    DevBuf tok, meta, stat;
+    DevBuf tok, tok8, meta, stat;
     CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
     CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
     CUDA_TRY(tok.ensure(static_cast<size_t>(max_tok) * n * sizeof(u32)));
+    CUDA_TRY(tok8.ensure(static_cast<size_t>(n) * TOK8 * sizeof(u32)));
     CUDA_TRY(meta.ensure(n * sizeof(u32)));
     CUDA_TRY(stat.ensure(n * sizeof(int)));
     if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
@@ -662,12 +680,17 @@ int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offset
     CUDA_TRY(cudaMemsetAsync(tok.p, 0, static_cast<size_t>(max_tok) * n * sizeof(u32), s));
     CUDA_TRY(cudaStreamWaitEvent(s, e->ev_flush, 0));
     k_tokenize<<<(static_cast<u32>(n) + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->view(), max_tok, tok.as<u32>(), meta.as<u32>(), stat.as<int>());
+        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->view(), max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_tokens, tok.p, static_cast<size_t>(max_tok) * n * sizeof(u32), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_meta, meta.p, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    std::vector<u32> rows(static_cast<size_t>(n) * TOK8);
+    CUDA_TRY(cudaMemcpyAsync(rows.data(), tok8.p, rows.size() * sizeof(u32), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    for (uint64_t i = 0; i < n; ++i)          // levels 0..7 live in the per-topic row; present them level-major too
+        for (u32 l = 0; l < TOK8 && l < max_tok; ++l) out_tokens[static_cast<size_t>(l) * n + i] = rows[i * TOK8 + l];
+    tok8.release();
     tok.release(); meta.release(); stat.release();
     return GM_OK;
 }

@@ -18,10 +18,20 @@ inline u32 fnv(const char* s, u32 len) {
     return h;
 }
 
-inline bool dict_slot_equals(const DictSlot& d, const u8* pool, const char* s, u32 len, u32 h) {
-    const u8* b = reinterpret_cast<const u8*>(&d.w[1]);
-    if (len <= DICT_INLINE_MAX) return b[0] == len && std::memcmp(b + 1, s, len) == 0;
-    return b[0] == 0xFF && d.w[2] == len && d.w[4] == h && std::memcmp(pool + d.w[3], s, len) == 0;
+// the seven key words of an inline string (<= 27 bytes): bytes, zero padded, length in the last byte
+inline void pack_words(const char* s, u32 len, u32 (&w)[7]) {
+    u8 b[28] = {0};
+    std::memcpy(b, s, len);
+    b[27] = static_cast<u8>(len);
+    std::memcpy(w, b, 28);
+}
+inline u32 dict_index_hash(const char* s, u32 len) {
+    if (len <= DICT_INLINE_MAX) { u32 w[7]; pack_words(s, len, w); return dict_hash_words(w); }
+    return dict_hash_finish(fnv(s, len), len);
+}
+inline bool dict_slot_equals(const DictSlot& d, const u8* pool, const char* s, u32 len) {
+    if (len <= DICT_INLINE_MAX) { u32 w[7]; pack_words(s, len, w); return std::memcmp(&d.w[1], w, 28) == 0; }
+    return (d.w[7] >> 24) == 0xFF && d.w[1] == len && d.w[3] == fnv(s, len) && std::memcmp(pool + d.w[2], s, len) == 0;
 }
 }  // namespace
 
@@ -58,12 +68,11 @@ u32 HostTrie::lookup_token(const char* s, u32 len) const {
     if (len == 0) return TOK_BLANK;
     if (len == 1 && s[0] == '+') return TOK_PLUS;
     if (len == 1 && s[0] == '#') return TOK_HASH;
-    u32 h = fnv(s, len);
     u32 mask = static_cast<u32>(dict.size() - 1);
-    for (u32 i = dict_hash_finish(h, len) & mask;; i = (i + 1) & mask) {
+    for (u32 i = dict_index_hash(s, len) & mask;; i = (i + 1) & mask) {
         const DictSlot& d = dict[i];
         if (d.w[0] == 0) return TOK_UNKNOWN;
-        if (dict_slot_equals(d, pool.data(), s, len, h)) return d.w[0];
+        if (dict_slot_equals(d, pool.data(), s, len)) return d.w[0];
     }
 }
 
@@ -71,21 +80,20 @@ u32 HostTrie::intern(const char* s, u32 len, bool create) {
     u32 t = lookup_token(s, len);
     if (t != TOK_UNKNOWN || !create) return t;
     if ((dict_count_ + 1) * 2 > dict.size()) grow_dict();
-    u32 h = fnv(s, len);
     u32 mask = static_cast<u32>(dict.size() - 1);
-    u32 i = dict_hash_finish(h, len) & mask;
+    u32 i = dict_index_hash(s, len) & mask;
     while (dict[i].w[0] != 0) i = (i + 1) & mask;
     DictSlot d{};
     d.w[0] = next_token_++;
-    u8* b = reinterpret_cast<u8*>(&d.w[1]);
     if (len <= DICT_INLINE_MAX) {
-        b[0] = static_cast<u8>(len);
-        std::memcpy(b + 1, s, len);
+        u32 w[7];
+        pack_words(s, len, w);
+        std::memcpy(&d.w[1], w, 28);
     } else {
-        b[0] = 0xFF;
-        d.w[2] = len;
-        d.w[3] = static_cast<u32>(pool.size());
-        d.w[4] = h;
+        d.w[7] = 0xFFu << 24;
+        d.w[1] = len;
+        d.w[2] = static_cast<u32>(pool.size());
+        d.w[3] = fnv(s, len);
         pool.insert(pool.end(), s, s + len);
         while (pool.size() % 16) pool.push_back(0);
     }
@@ -104,11 +112,10 @@ void HostTrie::grow_dict() {
     u32 mask = static_cast<u32>(dict.size() - 1);
     for (const DictSlot& d : old) {
         if (d.w[0] == 0) continue;
-        const u8* b = reinterpret_cast<const u8*>(&d.w[1]);
-        u32 len, h;
-        if (b[0] == 0xFF) { len = d.w[2]; h = d.w[4]; }
-        else { len = b[0]; h = fnv(reinterpret_cast<const char*>(b + 1), len); }
-        u32 i = dict_hash_finish(h, len) & mask;
+        u32 h;
+        if ((d.w[7] >> 24) == 0xFF) h = dict_hash_finish(d.w[3], d.w[1]);
+        else { u32 w[7]; std::memcpy(w, &d.w[1], 28); h = dict_hash_words(w); }
+        u32 i = h & mask;
         while (dict[i].w[0] != 0) i = (i + 1) & mask;
         dict[i] = d;
     }

@@ -21,7 +21,8 @@ namespace gm {
 
 struct MatchParams {
     TrieView tv;
-    const u32* tok;      // [tok_levels][n]  (SoA: token of level l of topic t at tok[l*n+t])
+    const u32* tok8;     // [n][8]  tokens of levels 0..7, one 32-byte row per topic (one 256-bit load)
+    const u32* tok;      // [tok_levels][n]  levels >= 8 only (level-major; deferred kernel)
     const u32* meta;     // [n]
     u32 n;
     u32 tok_levels;
@@ -34,22 +35,19 @@ struct MatchParams {
     u32* tile_counter;
     unsigned long long* stats;    // [4] V,E,F,M + [4..] probe diagnostics (only written by STATS instantiations)
     u32 flags;                    // MP_* tuning switches
+    const u32* perm;     // [n] locality order (k_bucket_*): position -> topic index
+    const u32* tok8_sorted;   // [n][8] token rows copied into locality order (MP_SORTED_ROWS)
+    const u32* meta_sorted;   // [n]
 };
-constexpr u32 MP_L2_HINTS = 1u;   // L2 eviction priorities: hot upper levels / '+' subtrees evict_last, cold deep chain evict_first
+constexpr u32 MP_SORTED_ROWS = 1u;   // k_bucket_scatter also copies token rows + meta into sorted order (coalesced reads in k_match_fast)
+constexpr u32 NBUCKETS = 1u << 12;   // locality buckets
+constexpr u32 TOK8 = 8;              // levels kept in the per-topic 32-byte token row
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ld256(const void* p, u32 (&w)[8]) {
     asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                  : "l"(p));
-}
-// L2 eviction-priority policies (createpolicy) and a 256-bit load that carries one.
-__device__ __forceinline__ u64 l2_policy_evict_last() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-__device__ __forceinline__ u64 l2_policy_evict_first() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
-__device__ __forceinline__ void ld256_hint(const void* p, u32 (&w)[8], u64 pol) {
-    asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                 : "l"(p), "l"(pol));
 }
 __device__ __forceinline__ u32 lanemask_lt() {
     u32 m;
@@ -58,23 +56,48 @@ __device__ __forceinline__ u32 lanemask_lt() {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: tokeniser.  One thread per topic.
+// K1: tokeniser.  One thread per topic, FOUR text bytes per step: the level text is read with aligned
+// 32-bit loads re-aligned by a funnel shift, '/' and the wildcard characters are found with SWAR zero-byte
+// tests, and the packed key words of the level stay in registers (static indexing) where they are compared
+// directly with the 32-byte dictionary slot.  (Round-1 history: a byte-at-a-time loop packing through shared
+// memory ran ~53 instructions per text byte and was issue bound, profiles/r1_k1_bytewise.ncu-rep.)
 constexpr int TOK_THREADS = 256;
 
-__device__ __forceinline__ u32 dict_lookup(const TrieView& tv, u32 h, u32 len, const u32 (&w)[7],
-                                           const u8* text) {
+__device__ __forceinline__ u32 swar_zero_bytes(u32 v) { return (v - 0x01010101u) & ~v & 0x80808080u; }   // bit 7 of every zero byte (lowest hit exact)
+
+// four text bytes starting at byte address `a` (little endian); never dereferences at or beyond `limit`
+__device__ __forceinline__ u32 text4(const u8* a, const u8* limit) {
+    const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+    const u32* w = reinterpret_cast<const u32*>(ai & ~uintptr_t(3));
+    const u32 lo = reinterpret_cast<const u8*>(w) < limit ? __ldg(w) : 0u;
+    const u32 hi = reinterpret_cast<const u8*>(w + 1) < limit ? __ldg(w + 1) : 0u;
+    return __funnelshift_r(lo, hi, 8u * static_cast<u32>(ai & 3));
+}
+
+__device__ __forceinline__ u32 dict_lookup_inline(const TrieView& tv, const u32 (&w)[7]) {
+    u32 idx = dict_hash_words(w) & tv.dict_mask;
+    for (;;) {
+        u32 s[8];
+        ld256(tv.dict + idx, s);
+        if (s[0] == 0) return TOK_UNKNOWN;
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) eq &= (s[k + 1] == w[k]);
+        if (eq) return s[0];
+        idx = (idx + 1) & tv.dict_mask;
+    }
+}
+
+__device__ __noinline__ u32 dict_lookup_long(const TrieView& tv, const u8* text, u32 len) {
+    u32 h = FNV_INIT;
+    for (u32 i = 0; i < len; ++i) h = fnv_step(h, text[i]);
     u32 idx = dict_hash_finish(h, len) & tv.dict_mask;
     for (;;) {
         u32 s[8];
         ld256(tv.dict + idx, s);
         if (s[0] == 0) return TOK_UNKNOWN;
-        if (len <= DICT_INLINE_MAX) {
-            bool eq = true;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) eq &= (s[k + 1] == w[k]);
-            if (eq) return s[0];
-        } else if ((s[1] & 0xFF) == 0xFF && s[2] == len && s[4] == h) {
-            const u8* q = tv.pool + s[3];
+        if ((s[7] >> 24) == 0xFFu && s[1] == len && s[3] == h) {
+            const u8* q = tv.pool + s[2];
             bool eq = true;
             for (u32 i = 0; i < len && eq; ++i) eq = (q[i] == text[i]);
             if (eq) return s[0];
@@ -85,34 +108,39 @@ __device__ __forceinline__ u32 dict_lookup(const TrieView& tv, u32 h, u32 len, c
 
 __global__ void __launch_bounds__(TOK_THREADS)
 k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, TrieView tv, u32 tok_levels,
-           u32* __restrict__ tok, u32* __restrict__ meta, int* __restrict__ status) {
-    __shared__ u32 s_w[7][TOK_THREADS];   // packed level bytes of the current level, per thread (conflict-free)
-    u32 t = blockIdx.x * TOK_THREADS + threadIdx.x;
+           u32* __restrict__ tok8, u32* __restrict__ tok, u32* __restrict__ meta, int* __restrict__ status, u32* __restrict__ bkey,
+           u32* __restrict__ hist) {
+    const u32 t = blockIdx.x * TOK_THREADS + threadIdx.x;
     if (t >= n) return;
     u32 pos = offs[t];
     const u32 end = offs[t + 1];
+    const u8* limit = blob + ((static_cast<size_t>(offs[n]) + 3) & ~size_t(3));
     u32 lev = 0;
+    u32 tw[TOK8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tokens of levels 0..7 (static indexing only: stays in registers)
     bool invalid = false, dollar = false;
     for (;;) {
-        u32 h = FNV_INIT, len = 0, c0 = 0, cur = 0;
-        bool wild = false;
         const u32 start = pos;
+        u32 w[7] = {0, 0, 0, 0, 0, 0, 0};
+        u32 len = 0;
+        bool ended = false, wild = false;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) s_w[k][threadIdx.x] = 0;
-        // byte 0 of the 28-byte key area is the length; string byte i sits at position i+1
-        while (pos < end) {
-            u32 c = blob[pos];
-            if (c == '/') break;
-            h = fnv_step(h, c);
-            wild |= (c == '+') | (c == '#');
-            if (len == 0) c0 = c;
-            if (len < DICT_INLINE_MAX) {
-                u32 p = len + 1;
-                cur |= c << (8 * (p & 3));
-                if ((p & 3) == 3) { s_w[p >> 2][threadIdx.x] = cur; cur = 0; }
+        for (int k = 0; k < 7; ++k) {
+            if (!ended) {
+                u32 x = text4(blob + pos, limit);
+                const u32 z = swar_zero_bytes(x ^ 0x2F2F2F2Fu);                       // '/' bytes
+                u32 nb = z ? static_cast<u32>((__ffs(z) - 1) >> 3) : 4u;             // bytes before the first '/'
+                nb = min(nb, end - pos);                                             // ... and before the end of the topic
+                ended = nb < 4;
+                x &= nb == 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+                wild |= (swar_zero_bytes(x ^ 0x2B2B2B2Bu) | swar_zero_bytes(x ^ 0x23232323u)) != 0;   // '+' / '#'
+                w[k] = x;
+                len += nb; pos += nb;
             }
-            ++len; ++pos;
         }
+        if (!ended) {   // 28 bytes and still inside the level: long level (rare) — finish byte-wise
+            while (pos < end && blob[pos] != '/') { const u32 c = blob[pos]; wild |= (c == '+') | (c == '#'); ++pos; ++len; }
+        }
+        const u32 c0 = w[0] & 0xFFu;
         const bool last = pos >= end;
         u32 tk = TOK_UNKNOWN;
         if (len == 0) tk = TOK_BLANK;
@@ -122,27 +150,74 @@ k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, Tri
         else {
             if (c0 == '$') { if (lev > 0) invalid = true; else dollar = true; }           // topic.rs:210
             if (!invalid && lev < tok_levels) {
-                u32 w[7];
-                if (len <= DICT_INLINE_MAX) {
-                    if ((len & 3) != 3) s_w[len >> 2][threadIdx.x] = cur;   // flush the partial word
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) w[k] = s_w[k][threadIdx.x];
-                    w[0] |= len;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) w[k] = 0;
-                }
-                tk = dict_lookup(tv, h, len, w, blob + start);
+                if (len <= DICT_INLINE_MAX) { w[6] |= len << 24; tk = dict_lookup_inline(tv, w); }
+                else tk = dict_lookup_long(tv, blob + start, len);
             }
         }
         if (invalid) break;
-        if (lev < tok_levels) tok[static_cast<size_t>(lev) * n + t] = tk;
+#pragma unroll
+        for (u32 k = 0; k < TOK8; ++k) if (lev == k) tw[k] = tk;
+        if (lev >= TOK8 && lev < tok_levels) tok[static_cast<size_t>(lev) * n + t] = tk;
         ++lev;
         if (last) break;
         ++pos;   // skip '/'
     }
     meta[t] = invalid ? META_INVALID : (lev | (dollar ? META_DOLLAR : 0u));
     status[t] = invalid ? -2 : 0;   // GM_ERR_INVALID_TOPIC: Topic::from_str would return Err
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(tok8 + static_cast<size_t>(t) * TOK8), "r"(tw[0]), "r"(tw[1]), "r"(tw[2]),
+                 "r"(tw[3]), "r"(tw[4]), "r"(tw[5]), "r"(tw[6]), "r"(tw[7]) : "memory");
+    if (bkey) {   // locality bucket: topics that share their first two levels share the upper subtrees of the trie
+        const u32 b = invalid ? 0u : (fmix32(tw[0] * 0x9E3779B1u + tw[1]) & (NBUCKETS - 1));
+        bkey[t] = b;
+        atomicAdd(hist + b, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Locality pass.  A uniformly random batch revisits a shared subtree (say the filters below `reg/site/+`)
+// once every few thousand topics — long enough for the cold random stream to evict it from L2 in between
+// (measured L2 read hit rate 33 %).  Regrouping the batch by hash(level 0, level 1) makes the topics that
+// share those subtrees run in the same tiles: the second and later visits hit L1/L2.  Counting sort:
+// histogram (in k_tokenize) -> k_bucket_scan -> k_bucket_scatter; order inside a bucket is irrelevant.
+__global__ void __launch_bounds__(1024)
+k_bucket_scan(const u32* __restrict__ hist, u32* __restrict__ cursor) {
+    __shared__ u32 s_warp[32];
+    constexpr u32 PER = NBUCKETS / 1024;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    u32 v[PER], sum = 0;
+#pragma unroll
+    for (u32 k = 0; k < PER; ++k) { v[k] = hist[tid * PER + k]; sum += v[k]; }
+    u32 inc = sum;                                   // warp-level inclusive scan by shuffle
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        u32 w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += x; }
+        s_warp[lane] = wi - w;                        // exclusive offset of each warp
+    }
+    __syncthreads();
+    u32 run = s_warp[wid] + inc - sum;
+#pragma unroll
+    for (u32 k = 0; k < PER; ++k) { cursor[tid * PER + k] = run; run += v[k]; }
+}
+
+__global__ void __launch_bounds__(256)
+k_bucket_scatter(const u32* __restrict__ bkey, u32* __restrict__ cursor, u32 n, u32* __restrict__ perm,
+                 const u32* __restrict__ tok8, const u32* __restrict__ meta, u32* __restrict__ tok8_sorted, u32* __restrict__ meta_sorted) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u32 pos = atomicAdd(cursor + bkey[t], 1u);
+    perm[pos] = t;
+    if (tok8_sorted) {
+        u32 w[8];
+        ld256(tok8 + static_cast<size_t>(t) * TOK8, w);
+        asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(tok8_sorted + static_cast<size_t>(pos) * TOK8), "r"(w[0]), "r"(w[1]),
+                     "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        meta_sorted[pos] = meta[t];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -156,17 +231,16 @@ __device__ __forceinline__ u64 make_item(u32 topic, u32 depth, u32 kind, u32 arg
 struct NodeRec { u32 node, plus, hash_ref, own_ref, mask, cnts; };
 
 // Loads the record an item points at.  Returns false when the literal child does not exist.
-// pol != 0: L2 cache-policy operand for the slot loads.
-__device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 arg, u32 token, NodeRec& r, u64 pol = 0) {
+__device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 arg, u32 token, NodeRec& r) {
     u32 s[8];
     if (kind == KIND_PLUS) {
-        if (pol) ld256_hint(tv.plus + arg, s, pol); else ld256(tv.plus + arg, s);
+        ld256(tv.plus + arg, s);
         r.node = s[0]; r.plus = s[1]; r.hash_ref = s[2]; r.own_ref = s[3]; r.mask = s[4]; r.cnts = s[5];
         return true;
     }
     u32 idx = edge_hash(arg, token) & tv.edge_mask;
     for (;;) {
-        if (pol) ld256_hint(tv.edges + idx, s, pol); else ld256(tv.edges + idx, s);
+        ld256(tv.edges + idx, s);
         if (s[2] == 0) return false;                       // empty slot: no such child
         if (s[0] == arg && s[1] == token) break;
         idx = (idx + 1) & tv.edge_mask;
@@ -204,22 +278,17 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
     const TrieView& tv = p.tv;
     const u32 ntiles = (p.n + 31) >> 5;
     unsigned long long sV = 0, sE = 0, sF = 0, sM = 0;
-    // L2 residency: the upper two levels, every '+' record and everything below a '+' edge that replaced one
-    // of the first three levels is shared by many topics of a batch (hot: evict_last); the exact chain below
-    // a device is touched by ~1 topic per batch (cold: evict_first) and must not flush the hot set out of L2.
-    const bool hints = (p.flags & MP_L2_HINTS) != 0;
-    const u64 pol_hot = hints ? l2_policy_evict_last() : 0ull;
-    const u64 pol_cold = hints ? l2_policy_evict_first() : 0ull;
-
     for (;;) {
         u32 tile = 0;
         if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
         tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
         if (tile >= ntiles) break;
 
-        const u32 t = tile * 32 + lane;
-        const bool in_range = t < p.n;
-        const u32 m = in_range ? __ldcs(p.meta + t) : META_INVALID;
+        const u32 pos = tile * 32 + lane;              // position in the locality-sorted order
+        const bool in_range = pos < p.n;
+        const u32 t = in_range ? p.perm[pos] : 0u;     // original topic index
+        const bool rows = (p.flags & MP_SORTED_ROWS) != 0;
+        const u32 m = in_range ? (rows ? __ldcs(p.meta_sorted + pos) : __ldcs(p.meta + t)) : META_INVALID;
         const bool invalid = (m & META_INVALID) != 0;
         const u32 L = m & META_NLEV_MASK;
         const u32 need = min(L, tv.max_depth);
@@ -229,12 +298,15 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
         u32 ndesc = 0, total = 0;
 
         if (active) {
+            {
+                static_assert(FAST_L == TOK8, "the token row holds 8 levels");
+                u32 w[8];
+                ld256(rows ? p.tok8_sorted + static_cast<size_t>(pos) * TOK8 : p.tok8 + static_cast<size_t>(t) * TOK8, w);
 #pragma unroll
-            for (int l = 0; l < FAST_L; ++l)
-                if (l < need) s_tok[l][tid] = __ldcs(p.tok + static_cast<size_t>(l) * p.n + t);
+                for (int l = 0; l < FAST_L; ++l) s_tok[l][tid] = w[l];
+            }
             NodeRec r{0u, tv.root_plus, tv.root_hash_ref, 0u, tv.root_mask, tv.root_hash_cnt};
-            u32 d = 0, pmask = 0, hotmask = 0;
-            bool hot = false;                          // current branch lies below a shared '+' edge
+            u32 d = 0, pmask = 0;
             bool droot = (m & META_DOLLAR) != 0;      // `$`-rule: root wildcards skipped (trie.rs:312-318)
             u32 lV = 0, lE = 0, lF = 0;
             for (;;) {
@@ -256,15 +328,12 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                 }
                 bool down = false;
                 if (d < L) {
-                    if (r.plus != 0 && !droot) {                                                 // '+' child (trie.rs:330-334)
-                        s_pend[d][tid] = r.plus; pmask |= 1u << d;
-                        if (hot || d <= 2) hotmask |= 1u << d; else hotmask &= ~(1u << d);
-                    }
+                    if (r.plus != 0 && !droot) { s_pend[d][tid] = r.plus; pmask |= 1u << d; }   // '+' child (trie.rs:330-334)
                     if (r.mask != 0) {
                         const u32 tk = s_tok[d][tid];
                         if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) {                      // literal child (trie.rs:338-342)
                             NodeRec c;
-                            const bool hit = load_record(tv, KIND_PROBE, r.node, tk, c, (hot || d <= 1) ? pol_hot : pol_cold);
+                            const bool hit = load_record(tv, KIND_PROBE, r.node, tk, c);
                             if (STATS) {   // diagnostics: probes / misses per depth, slot loads per probe
                                 atomicAdd(p.stats + 4 + min(d, 7u), 1ull);
                                 if (!hit) atomicAdd(p.stats + 12 + min(d, 7u), 1ull);
@@ -281,8 +350,7 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                     if (pmask == 0) break;
                     const u32 pd = 31u - __clz(pmask);          // resume the deepest parked '+' child
                     pmask &= ~(1u << pd);
-                    hot = (hotmask >> pd) & 1u;
-                    load_record(tv, KIND_PLUS, s_pend[pd][tid], 0u, r, hot ? pol_hot : pol_cold);
+                    load_record(tv, KIND_PLUS, s_pend[pd][tid], 0u, r);
                     d = pd + 1;
                 }
             }
@@ -392,7 +460,7 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                 if (hit && d < L) {
                     if (r.plus != 0 && !dollar_root) { pA = true; itA = make_item(0, d + 1, KIND_PLUS, r.plus); }
                     if (r.mask != 0 && d < p.tok_levels) {
-                        u32 tk = p.tok[static_cast<size_t>(d) * p.n + t];
+                        u32 tk = d < TOK8 ? p.tok8[static_cast<size_t>(t) * TOK8 + d] : p.tok[static_cast<size_t>(d) * p.n + t];
                         if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) { pB = true; itB = make_item(0, d + 1, KIND_PROBE, r.node); }
                     }
                 }
@@ -448,7 +516,8 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                 NodeRec r{};
                 bool hit = false;
                 if (have) {
-                    u32 tk = kind == KIND_PROBE ? p.tok[static_cast<size_t>(d - 1) * p.n + t] : 0u;
+                    u32 tk = 0u;
+                    if (kind == KIND_PROBE) tk = (d - 1) < TOK8 ? p.tok8[static_cast<size_t>(t) * TOK8 + (d - 1)] : p.tok[static_cast<size_t>(d - 1) * p.n + t];
                     hit = load_record(tv, kind, arg, tk, r);
                 }
                 consume(hit, d, r, false);

@@ -68,9 +68,10 @@ struct alignas(32) PlusRec {
 };
 static_assert(sizeof(PlusRec) == 32, "PlusRec must be one 32-byte sector");
 
-// Dictionary slot: w[0] = token (0 = empty).  Bytes 4..31: byte 4 = length (0..27) followed by the
-// string, zero padded; or byte 4 = 0xFF for a long string: w[2] = length, w[3] = offset into the
-// long-string pool, w[4] = 32-bit hash.
+// Dictionary slot: w[0] = token (0 = empty).  Inline strings (<= 27 bytes): bytes 4..30 = the string, zero
+// padded, byte 31 = its length — i.e. w[1..7] are exactly the words the tokeniser packs, so a lookup is
+// seven word compares.  Long strings: byte 31 = 0xFF, w[1] = length, w[2] = offset into the long-string
+// pool, w[3] = FNV-1a hash of all bytes.
 struct alignas(32) DictSlot {
     u32 w[8];
 };
@@ -109,7 +110,13 @@ GM_HD u32 edge_hash(u32 parent, u32 token) {
 }
 constexpr u32 FNV_INIT = 0x811C9DC5u;
 GM_HD u32 fnv_step(u32 h, u32 byte) { return (h ^ byte) * 0x01000193u; }
-GM_HD u32 dict_hash_finish(u32 h, u32 len) { return fmix32(h ^ (len * 0x9E3779B1u)); }
+GM_HD u32 dict_hash_finish(u32 h, u32 len) { return fmix32(h ^ (len * 0x9E3779B1u)); }   // long strings: h = FNV-1a over bytes
+// inline strings: hash of the seven packed key words (length included in the last one)
+GM_HD u32 dict_hash_words(const u32 (&w)[7]) {
+    u32 h = FNV_INIT;
+    for (int k = 0; k < 7; ++k) h = (h ^ w[k]) * 0x01000193u;
+    return fmix32(h);
+}
 GM_HD u32 mask_bit(u32 token) { return 1u << ((token * 0x9E3779B1u) >> 27); }
 
 // Shard of a level-0 string (multi-GPU partitioning by topic root).

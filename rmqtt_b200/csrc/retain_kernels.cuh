@@ -21,7 +21,8 @@ struct alignas(16) RDesc { u32 q, ref, cnt, kind; };   // kind 0: the value itse
 
 struct RetainParams {
     RetainView v;
-    const u32* qtok;     // [tok_levels][nq]
+    const u32* qtok8;    // [nq][8]  filter levels 0..7
+    const u32* qtok;     // [tok_levels][nq]  levels >= 8
     const u32* qmeta;    // [nq]
     u32 nq, tok_levels;
     RDesc* descs;
@@ -30,6 +31,10 @@ struct RetainParams {
     u32* qtotal;         // [nq] matched values per query
     u32* err;            // bit 0: frontier overflow, bit 1: descriptor overflow
 };
+
+__device__ __forceinline__ u32 retain_tok(const RetainParams& p, u32 q, u32 pos) {
+    return pos < TOK8 ? p.qtok8[static_cast<size_t>(q) * TOK8 + pos] : p.qtok[static_cast<size_t>(pos) * p.nq + q];
+}
 
 __device__ __forceinline__ u32 retain_child(const RetainView& v, u32 node, u32 token) {
     u32 idx = redge_hash(node, token) & v.edge_mask;
@@ -85,8 +90,8 @@ k_retain_step(RetainParams p, const RItem* __restrict__ in, const u32* __restric
             if (nkids == 0 || it.pos == L) {                                     // retain.rs:305-311
                 if (it.pos == L && (flags & 8u)) { emit1 = true; d1 = RDesc{it.q, val, 1u, 0u}; }
             } else {
-                const u32 tok = p.qtok[static_cast<size_t>(it.pos) * p.nq + it.q];
-                next_hash = (it.pos + 1 < L) && p.qtok[static_cast<size_t>(it.pos + 1) * p.nq + it.q] == TOK_HASH;
+                const u32 tok = retain_tok(p, it.q, it.pos);
+                next_hash = (it.pos + 1 < L) && retain_tok(p, it.q, it.pos + 1) == TOK_HASH;
                 // precise matching first — Level equality, so a stored literal "+" / "#" child shadows the
                 // wildcard expansion (retain.rs:313)
                 const bool exact_try = tok >= TOK_BLANK || (tok == TOK_PLUS && (flags & RF_LIT_PLUS)) || (tok == TOK_HASH && (flags & RF_LIT_HASH));

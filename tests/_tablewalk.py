@@ -26,7 +26,19 @@ def fnv(b):
     return h
 
 
+def pack_words(b):
+    buf = bytearray(28)
+    buf[:len(b)] = b
+    buf[27] = len(b)
+    return [int.from_bytes(buf[4 * k:4 * k + 4], "little") for k in range(7)]
+
+
 def dict_hash(b):
+    if len(b) <= 27:
+        h = 0x811C9DC5
+        for w in pack_words(b):
+            h = ((h ^ w) * 0x01000193) & M32
+        return fmix32(h)
     return fmix32(fnv(b) ^ ((len(b) * 0x9E3779B1) & M32))
 
 
@@ -56,10 +68,10 @@ class Tables:
                 return TOK_UNKNOWN
             row = self.dict_bytes[i]
             if len(lv) <= 27:
-                if row[4] == len(lv) and bytes(row[5:5 + len(lv)]) == lv:
+                if row[31] == len(lv) and bytes(row[4:4 + len(lv)]) == lv and not any(row[4 + len(lv):31]):
                     return tok
-            elif row[4] == 0xFF and int(self.dict[i, 2]) == len(lv) and int(self.dict[i, 4]) == fnv(lv):
-                off = int(self.dict[i, 3])
+            elif row[31] == 0xFF and int(self.dict[i, 1]) == len(lv) and int(self.dict[i, 3]) == fnv(lv):
+                off = int(self.dict[i, 2])
                 if bytes(self.pool[off:off + len(lv)]) == lv:
                     return tok
             i = (i + 1) & mask
