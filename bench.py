@@ -312,9 +312,11 @@ def run_own(args):
             traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
         except Exception:
             pass
+    if traffic is None:
+        traffic = 1021794816   # dram__bytes_read.sum + dram__bytes_write.sum of k_match_fast, one launch, profiles/r1_k2_dfs_sorted.ncu-rep
     roofline = {"bound": "hbm", "kernel": "k_match_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": k2_bytes, "kernel_ms": {"k_tokenize": float(k_mean[0]), "k_match_fast": k2_ms, "k_match_slow": float(k_mean[2])},
+                "algorithmic_bytes_per_launch": k2_bytes, "kernel_ms": {"k_tokenize+k_bucket_scan+k_bucket_scatter": float(k_mean[0]), "k_match_fast": k2_ms, "k_match_slow": float(k_mean[2])},
                 "pipeline": {"algorithmic_bytes_per_step": k1_bytes + k2_bytes,
                              "achieved": (k1_bytes + k2_bytes) / (float(k_mean.sum()) * 1e-3) / 1e9 if k_mean.sum() > 0 else None}}
 
