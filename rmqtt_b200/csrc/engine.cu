@@ -60,11 +60,11 @@ struct Ctrl {                       // device control block, zeroed before every
 
 static_assert(GM_ERR_INVALID_TOPIC == -2, "k_tokenize writes the per-topic status code directly");
 
-// fast-path geometry: one topic per thread, 512 threads per CTA, 4 CTAs per SM (<= 32 registers)
+// fast-path geometry: one topic per thread, 512 threads per CTA, 3 CTAs per SM (64 KB of shared memory each)
 constexpr int K2_FAST_L = 8;       // levels staged in shared memory; deeper topics take the deferred kernel
 constexpr int K2_THREADS = 512;
-constexpr int K2_CTAS_PER_SM = 4;
-constexpr u32 K2_POOL_ROWS = 32;   // matched value sets per topic before the topic is deferred
+constexpr int K2_CTAS_PER_SM = 3;
+constexpr u32 K2_POOL_ROWS = 24;   // matched value sets per topic beyond the 8 held in shared memory, before the topic is deferred
 
 }  // namespace
 
@@ -87,7 +87,7 @@ struct gm_engine {
     u64 ring_n = 0;
     bool match_recorded = false;
     // device tables
-    DevBuf d_edges, d_plus, d_ranges, d_values, d_dict, d_pool;
+    DevBuf d_edges, d_plus, d_ranges, d_values, d_dict, d_pool, d_cfilter;
     size_t up_plus = 0, up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
     // scratch
     DevBuf d_tok, d_tok8, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data, d_sort, d_hist;
@@ -97,6 +97,7 @@ struct gm_engine {
     DevBuf d_rfront[2], d_rdescs, d_rctl, d_rq;
     u32 r_cap_items = 1u << 20, r_cap_desc = 1u << 20;
     u64 launches = 0;
+    bool k2_attr_set = false;
 
     explicit gm_engine(u32 max_levels) : trie(max_levels) {}
 
@@ -104,6 +105,7 @@ struct gm_engine {
         TrieView v{};
         v.edges = d_edges.as<EdgeSlot>(); v.plus = d_plus.as<PlusRec>(); v.ranges = d_ranges.as<Range>();
         v.values = d_values.as<u32>(); v.dict = d_dict.as<DictSlot>(); v.pool = d_pool.as<u8>();
+        v.cfilter = d_cfilter.as<u32>(); v.cfilter_mask = static_cast<u32>(trie.cfilter.size() - 1);
         v.edge_mask = static_cast<u32>(trie.edges.size() - 1);
         v.dict_mask = static_cast<u32>(trie.dict.size() - 1);
         v.root_plus = trie.root_plus; v.root_hash_ref = trie.root_hash_ref; v.root_hash_cnt = trie.root_hash_cnt; v.root_mask = trie.root_mask;
@@ -208,6 +210,10 @@ struct gm_engine {
         if ((st = upload_appendable<Range>(d_ranges, trie.ranges, up_ranges, nullptr)) != GM_OK) return st;
         if ((st = upload_appendable<u32>(d_values, trie.values, up_values, nullptr)) != GM_OK) return st;
         if ((st = upload_appendable<u8>(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return st;
+        if (trie.cfilter_dirty) {   // child filter of wide nodes: a few MB, shipped whole
+            if ((st = upload_whole(d_cfilter, trie.cfilter)) != GM_OK) return st;
+            trie.cfilter_dirty = false;
+        }
         trie.root_dirty = false;
         CUDA_TRY(cudaEventRecord(ev_flush, side));
         CUDA_TRY(cudaStreamSynchronize(side));
@@ -229,7 +235,10 @@ struct gm_engine {
         CUDA_TRY(d_ctrl.ensure(sizeof(Ctrl)));
         // locality pass scratch: bkey[n], perm[n]; hist + cursor [NBUCKETS] each
         CUDA_TRY(d_sort.ensure(static_cast<size_t>(n32) * 11 * sizeof(u32) + 64));
-        CUDA_TRY(d_hist.ensure(2 * NBUCKETS * sizeof(u32)));
+        u32 site_bits = 14, sub_bits = 0;
+        if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { site_bits = a; sub_bits = b; } }   // tuning knob
+        const u32 NBUCKETS = 1u << (site_bits + sub_bits);
+        CUDA_TRY(d_hist.ensure(2 * static_cast<size_t>(NBUCKETS) * sizeof(u32)));
         u32* bkey = d_sort.as<u32>();
         u32* perm = bkey + n32;
         u32* meta_sorted = perm + n32;
@@ -257,8 +266,8 @@ struct gm_engine {
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
         k_tokenize<<<(n32 + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-            static_cast<const u8*>(d_blob_), d_offs_, n32, tv, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, bkey, hist);
-        k_bucket_scan<<<1, 1024, 0, s>>>(hist, bcursor);
+            static_cast<const u8*>(d_blob_), d_offs_, n32, tv, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, bkey, hist, site_bits, sub_bits);
+        k_bucket_scan<<<1, 1024, 0, s>>>(hist, bcursor, NBUCKETS);
         k_bucket_scatter<<<(n32 + 255) / 256, 256, 0, s>>>(bkey, bcursor, n32, perm, d_tok8.as<u32>(), d_meta.as<u32>(),
                                                             sorted_rows ? tok8_sorted : nullptr, meta_sorted);
         CUDA_TRY(cudaGetLastError());
@@ -271,8 +280,16 @@ struct gm_engine {
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
         mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
         mp.flags = sorted_rows ? MP_SORTED_ROWS : 0u;
-        if (stats) k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true><<<k2_grid, K2_THREADS, 0, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
-        else k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false><<<k2_grid, K2_THREADS, 0, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
+        if (const char* ev = getenv("GM_DIAG_MAXDEPTH")) mp.flags |= (static_cast<u32>(atoi(ev)) & 0xFu) << MP_DIAG_DEPTH_SHIFT;   // timing diagnostics, wrong results
+        if (getenv("GM_DIAG_NO_PUBLISH")) mp.flags |= MP_DIAG_NO_PUBLISH;
+        constexpr size_t k2_smem = k2_smem_bytes<K2_FAST_L, K2_THREADS>();
+        if (!k2_attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
+            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
+            k2_attr_set = true;
+        }
+        if (stats) k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true><<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
+        else k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false><<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[2], s));
         if (stats) k_match_slow<true><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
@@ -313,7 +330,7 @@ struct gm_engine {
         u32* qcur = qbase + nq;
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
-        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, view(), S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr);
+        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, view(), S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr, 0u, 0u);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
         RetainParams rp{};
@@ -410,7 +427,7 @@ void gm_destroy(gm_engine* e) {
     if (e->flags & GM_FLAG_HOST_ONLY) { delete e; return; }
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->d_tok8, &e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
+    for (DevBuf* b : {&e->d_tok8, &e->d_cfilter, &e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
                       &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_gpool, &e->d_sort, &e->d_hist, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
                       &e->d_spans, &e->d_ids, &e->d_status, &e->d_rnodes, &e->d_rkids, &e->d_redges, &e->d_rvals, &e->d_rfront[0],
                       &e->d_rfront[1], &e->d_rdescs, &e->d_rctl, &e->d_rq})
@@ -680,7 +697,7 @@ int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offset
     CUDA_TRY(cudaMemsetAsync(tok.p, 0, static_cast<size_t>(max_tok) * n * sizeof(u32), s));
     CUDA_TRY(cudaStreamWaitEvent(s, e->ev_flush, 0));
     k_tokenize<<<(static_cast<u32>(n) + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->view(), max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr);
+        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->view(), max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr, 0u, 0u);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_tokens, tok.p, static_cast<size_t>(max_tok) * n * sizeof(u32), cudaMemcpyDeviceToHost, s));
@@ -746,6 +763,7 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
         case 4: *ptr = t.dict.data(); *count = t.dict.size(); break;
         case 5: *ptr = t.pool.data(); *count = t.pool.size(); break;
         case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; root[4] = t.root_hash_cnt; *ptr = root; *count = 5; break;
+        case 12: *ptr = t.cfilter.data(); *count = t.cfilter.size(); break;
         case 7: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rnodes.data(); *count = e->rtree.rnodes.size(); break;
         case 8: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rkids.data(); *count = e->rtree.rkids.size(); break;
         case 9: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rvals.data(); *count = e->rtree.rvals.size(); break;

@@ -40,6 +40,7 @@ HostTrie::HostTrie(u32 max_levels) : max_levels_(max_levels) {
     dict.assign(1u << 10, DictSlot{});
     plus.assign(1, PlusRec{});
     ranges.assign(1, Range{0, 0});
+    cfilter.assign(1u << 10, 0u);
     nodes_.emplace_back();   // root = node 0
     nodes_[0].alive = 1;
 }
@@ -168,6 +169,9 @@ u32 HostTrie::add_edge(u32 parent, u32 token) {
     if (!full_edges) dirty_edges.push_back(i);
     HNode& p = nodes_[parent];
     p.mask |= mask_bit(token);
+    if (token != TOK_PLUS && token != TOK_HASH) p.lit_children++;
+    if (p.wide) cfilter_insert(parent, token);
+    else if (p.lit_children > WIDE_FANOUT) { p.wide = 1; cfilter_rebuild_ = true; }   // its earlier children are back-filled by the rebuild
     if (token == TOK_PLUS) {
         n.plus_idx = static_cast<u32>(plus.size());
         PlusRec r{};
@@ -179,6 +183,35 @@ u32 HostTrie::add_edge(u32 parent, u32 token) {
     }
     mark(parent);
     return id;
+}
+
+// ------------------------------------------------------------------------------- child filter
+void HostTrie::cfilter_insert(u32 parent, u32 token) {
+    if (cfilter_rebuild_) return;                                   // a rebuild is pending anyway
+    if ((cfilter_keys_ + 1) * 16 > cfilter.size() * 32) { cfilter_rebuild_ = true; return; }   // keep >= 16 bits per edge
+    u32 w, bits;
+    cfilter_pos(parent, token, static_cast<u32>(cfilter.size() - 1), w, bits);
+    cfilter[w] |= bits;
+    cfilter_keys_++;
+    cfilter_dirty = true;
+}
+
+void HostTrie::cfilter_rebuild() {
+    u64 n = 0;
+    for (const EdgeSlot& e : edges) if (e.child != 0 && nodes_[e.parent].wide) ++n;
+    size_t words = 1u << 10;
+    while (words * 32 < n * 20) words <<= 1;                        // ~20 bits per edge after a rebuild
+    cfilter.assign(words, 0u);
+    const u32 mask = static_cast<u32>(words - 1);
+    for (const EdgeSlot& e : edges) {
+        if (e.child == 0 || !nodes_[e.parent].wide) continue;
+        u32 w, bits;
+        cfilter_pos(e.parent, e.token, mask, w, bits);
+        cfilter[w] |= bits;
+    }
+    cfilter_keys_ = n;
+    cfilter_rebuild_ = false;
+    cfilter_dirty = true;
 }
 
 void HostTrie::mark(u32 node) {
@@ -322,7 +355,7 @@ void HostTrie::make_ref(u32 node) {
 
 void HostTrie::write_record(u32 node) {
     const HNode& n = nodes_[node];
-    u32 plus_idx = n.plus_child ? nodes_[n.plus_child].plus_idx : 0;
+    u32 plus_idx = (n.plus_child ? nodes_[n.plus_child].plus_idx : 0) | (n.wide ? PLUS_WIDE_FLAG : 0u);
     u32 hash_ref = n.hash_child ? nodes_[n.hash_child].ref : 0;
     u32 hash_cnt = n.hash_child ? nodes_[n.hash_child].cnt16 : 0;
     if (node == 0) {
@@ -341,6 +374,11 @@ void HostTrie::write_record(u32 node) {
 }
 
 void HostTrie::sync() {
+    if (cfilter_rebuild_) {
+        // nodes that just became wide must republish their record (flag)
+        for (u32 id = 0; id < nodes_.size(); ++id) if (nodes_[id].wide && !nodes_[id].dirty) { nodes_[id].dirty = 1; dirty_nodes_.push_back(id); }
+        cfilter_rebuild();
+    }
     // pass 1: value-set references (a '#' node's parent reads the child's fresh ref in pass 2)
     for (u32 id : dirty_nodes_) make_ref(id);
     for (u32 id : dirty_nodes_) { write_record(id); nodes_[id].dirty = 0; }

@@ -26,9 +26,11 @@ struct HNode {
     u32 ref = 0;             // value-set reference currently published to the device ...
     u32 cnt16 = 0;           // ... and its 16-bit count (layout.h)
     u32 live_children = 0;
+    u32 lit_children = 0;    // literal child edges ever created
     u32 mask = 0;
     u8 alive = 0;            // reference semantics: pruned nodes (trie.rs:126-128) are "not alive"
     u8 dirty = 0;
+    u8 wide = 0;             // more than WIDE_FANOUT literal children: its child edges live in the child filter
 };
 
 enum ParseStatus { PARSE_OK = 0, PARSE_INVALID = 1, PARSE_TOO_DEEP = 2 };
@@ -56,6 +58,8 @@ class HostTrie {
     std::vector<u32> values;
     std::vector<DictSlot> dict;
     std::vector<u8> pool;
+    std::vector<u32> cfilter;        // child filter of wide nodes (layout.h)
+    bool cfilter_dirty = true;
     u32 root_plus = 0, root_hash_ref = 0, root_hash_cnt = 0, root_mask = 0;
     u32 max_depth = 0;
 
@@ -63,7 +67,8 @@ class HostTrie {
     std::vector<u32> dirty_edges, dirty_plus, dirty_ranges, dirty_dict;
     bool full_edges = true, full_dict = true;   // table re-hashed / never uploaded: ship whole table
     bool any_dirty() const { return !dirty_nodes_.empty() || !dirty_edges.empty() || !dirty_plus.empty() ||
-                                    !dirty_ranges.empty() || !dirty_dict.empty() || full_edges || full_dict || root_dirty; }
+                                    !dirty_ranges.empty() || !dirty_dict.empty() || full_edges || full_dict || root_dirty || cfilter_dirty ||
+                                    cfilter_rebuild_; }
     bool root_dirty = true;
     u64 garbage_values = 0;
 
@@ -87,6 +92,10 @@ class HostTrie {
     void mark(u32 node);
     void make_ref(u32 node);
     void write_record(u32 node);
+    void cfilter_insert(u32 parent, u32 token);
+    void cfilter_rebuild();
+    bool cfilter_rebuild_ = false;
+    u64 cfilter_keys_ = 0;
 
     u32 max_levels_;
     std::vector<HNode> nodes_;

@@ -39,9 +39,13 @@ struct MatchParams {
     const u32* tok8_sorted;   // [n][8] token rows copied into locality order (MP_SORTED_ROWS)
     const u32* meta_sorted;   // [n]
 };
+constexpr u32 MP_DIAG_DEPTH_SHIFT = 8;   // diagnostics only: (flags >> 8) & 0xF = deepest level the fast walk may descend to (0 = no limit; results are then WRONG)
+constexpr u32 MP_DIAG_NO_PUBLISH = 2u;   // diagnostics only: skip the publish phase
 constexpr u32 MP_SORTED_ROWS = 1u;   // k_bucket_scatter also copies token rows + meta into sorted order (coalesced reads in k_match_fast)
-constexpr u32 NBUCKETS = 1u << 12;   // locality buckets
+constexpr u32 MAX_BUCKET_BITS = 18;   // locality buckets: 2^bits, bits = site_bits + sub_bits (engine.cu)
 constexpr u32 TOK8 = 8;              // levels kept in the per-topic 32-byte token row
+constexpr u32 K2_SMEM_DESCS = 8;     // value-set descriptors per topic held in shared memory by k_match_fast
+template <int FAST_L, int THREADS> constexpr size_t k2_smem_bytes() { return (2 * sizeof(u32) * FAST_L + sizeof(uint2) * K2_SMEM_DESCS) * THREADS; }
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ld256(const void* p, u32 (&w)[8]) {
@@ -109,7 +113,7 @@ __device__ __noinline__ u32 dict_lookup_long(const TrieView& tv, const u8* text,
 __global__ void __launch_bounds__(TOK_THREADS)
 k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, TrieView tv, u32 tok_levels,
            u32* __restrict__ tok8, u32* __restrict__ tok, u32* __restrict__ meta, int* __restrict__ status, u32* __restrict__ bkey,
-           u32* __restrict__ hist) {
+           u32* __restrict__ hist, u32 site_bits, u32 sub_bits) {
     const u32 t = blockIdx.x * TOK_THREADS + threadIdx.x;
     if (t >= n) return;
     u32 pos = offs[t];
@@ -167,7 +171,9 @@ k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, Tri
     asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(tok8 + static_cast<size_t>(t) * TOK8), "r"(tw[0]), "r"(tw[1]), "r"(tw[2]),
                  "r"(tw[3]), "r"(tw[4]), "r"(tw[5]), "r"(tw[6]), "r"(tw[7]) : "memory");
     if (bkey) {   // locality bucket: topics that share their first two levels share the upper subtrees of the trie
-        const u32 b = invalid ? 0u : (fmix32(tw[0] * 0x9E3779B1u + tw[1]) & (NBUCKETS - 1));
+        // major key: the first two levels (shared upper subtrees); minor key: a few bits of the third (neighbouring
+        // tiles then also share the cold per-device chains when a device shows up more than once in the batch)
+        const u32 b = invalid ? 0u : (((fmix32(tw[0] * 0x9E3779B1u + tw[1]) & ((1u << site_bits) - 1u)) << sub_bits) | (fmix32(tw[2]) & ((1u << sub_bits) - 1u)));
         bkey[t] = b;
         atomicAdd(hist + b, 1u);
     }
@@ -180,13 +186,12 @@ k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, Tri
 // share those subtrees run in the same tiles: the second and later visits hit L1/L2.  Counting sort:
 // histogram (in k_tokenize) -> k_bucket_scan -> k_bucket_scatter; order inside a bucket is irrelevant.
 __global__ void __launch_bounds__(1024)
-k_bucket_scan(const u32* __restrict__ hist, u32* __restrict__ cursor) {
+k_bucket_scan(const u32* __restrict__ hist, u32* __restrict__ cursor, u32 nbuckets) {
     __shared__ u32 s_warp[32];
-    constexpr u32 PER = NBUCKETS / 1024;
+    const u32 per = nbuckets / 1024;                 // nbuckets is a power of two >= 1024
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    u32 v[PER], sum = 0;
-#pragma unroll
-    for (u32 k = 0; k < PER; ++k) { v[k] = hist[tid * PER + k]; sum += v[k]; }
+    u32 sum = 0;
+    for (u32 k = 0; k < per; ++k) sum += hist[tid * per + k];
     u32 inc = sum;                                   // warp-level inclusive scan by shuffle
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
@@ -200,8 +205,7 @@ k_bucket_scan(const u32* __restrict__ hist, u32* __restrict__ cursor) {
     }
     __syncthreads();
     u32 run = s_warp[wid] + inc - sum;
-#pragma unroll
-    for (u32 k = 0; k < PER; ++k) { cursor[tid * PER + k] = run; run += v[k]; }
+    for (u32 k = 0; k < per; ++k) { const u32 v = hist[tid * per + k]; cursor[tid * per + k] = run; run += v; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -249,6 +253,13 @@ __device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 ar
     return true;
 }
 
+// child filter of wide nodes (layout.h): false = the child certainly does not exist
+__device__ __forceinline__ bool cfilter_maybe(const TrieView& tv, u32 parent, u32 token) {
+    u32 w, bits;
+    cfilter_pos(parent, token, tv.cfilter_mask, w, bits);
+    return (__ldg(tv.cfilter + w) & bits) == bits;
+}
+
 // A matched value set waiting to be expanded into the output: values[ref .. ref+cnt) (or ref itself).
 struct Desc { u32 ref, cnt; };
 
@@ -269,8 +280,11 @@ struct Desc { u32 ref, cnt; };
 template <int FAST_L, int THREADS, int CTAS_PER_SM, bool STATS>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
-    __shared__ u32 s_tok[FAST_L][THREADS];    // tokens of this thread's topic (column = thread: conflict-free)
-    __shared__ u32 s_pend[FAST_L][THREADS];   // parked '+' child (index into tv.plus) per depth
+    constexpr u32 SD = K2_SMEM_DESCS;         // descriptors kept in shared memory per topic; later ones spill to dpool
+    extern __shared__ __align__(16) unsigned char k2_smem[];   // 64 KB: above the 48 KB static limit -> dynamic
+    u32 (*s_tok)[THREADS] = reinterpret_cast<u32 (*)[THREADS]>(k2_smem);                                  // tokens of this thread's topic (column = thread: conflict-free)
+    u32 (*s_pend)[THREADS] = reinterpret_cast<u32 (*)[THREADS]>(k2_smem + sizeof(u32) * FAST_L * THREADS);   // parked '+' child per depth
+    uint2 (*s_desc)[THREADS] = reinterpret_cast<uint2 (*)[THREADS]>(k2_smem + 2 * sizeof(u32) * FAST_L * THREADS);   // matched value sets (ref, cnt)
     const u32 tid = threadIdx.x, lane = tid & 31;
     const u32 lt = lanemask_lt();
     const u32 nthreads = gridDim.x * THREADS;
@@ -315,23 +329,28 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                 const u32 c1 = droot ? 0u : (r.cnts & 0xFFFFu);
                 const u32 c2 = (d == L) ? (r.cnts >> 16) : 0u;                       // own values (trie.rs:309-310)
                 if (c1) {
-                    if (c1 == CNT_BIG || ndesc >= pool_rows) { defer = true; break; }
-                    dpool[static_cast<size_t>(ndesc) * nthreads + gtid] = Desc{r.hash_ref, c1};
+                    if (c1 == CNT_BIG || ndesc >= SD + pool_rows) { defer = true; break; }
+                    if (ndesc < SD) s_desc[ndesc][tid] = make_uint2(r.hash_ref, c1);
+                    else dpool[static_cast<size_t>(ndesc - SD) * nthreads + gtid] = Desc{r.hash_ref, c1};
                     ++ndesc; total += c1;
                     if (STATS) lF++;
                 }
                 if (c2) {
-                    if (c2 == CNT_BIG || ndesc >= pool_rows) { defer = true; break; }
-                    dpool[static_cast<size_t>(ndesc) * nthreads + gtid] = Desc{r.own_ref, c2};
+                    if (c2 == CNT_BIG || ndesc >= SD + pool_rows) { defer = true; break; }
+                    if (ndesc < SD) s_desc[ndesc][tid] = make_uint2(r.own_ref, c2);
+                    else dpool[static_cast<size_t>(ndesc - SD) * nthreads + gtid] = Desc{r.own_ref, c2};
                     ++ndesc; total += c2;
                     if (STATS) lF++;
                 }
                 bool down = false;
-                if (d < L) {
-                    if (r.plus != 0 && !droot) { s_pend[d][tid] = r.plus; pmask |= 1u << d; }   // '+' child (trie.rs:330-334)
+                const u32 diag_max = (p.flags >> MP_DIAG_DEPTH_SHIFT) & 0xFu;
+                if (d < L && (diag_max == 0 || d < diag_max)) {
+                    const u32 plus_idx = r.plus & ~PLUS_WIDE_FLAG;
+                    if (plus_idx != 0 && !droot) { s_pend[d][tid] = plus_idx; pmask |= 1u << d; }   // '+' child (trie.rs:330-334)
                     if (r.mask != 0) {
                         const u32 tk = s_tok[d][tid];
-                        if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) {                      // literal child (trie.rs:338-342)
+                        if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk)) &&
+                            (!(r.plus & PLUS_WIDE_FLAG) || cfilter_maybe(tv, r.node, tk))) {        // literal child (trie.rs:338-342)
                             NodeRec c;
                             const bool hit = load_record(tv, KIND_PROBE, r.node, tk, c);
                             if (STATS) {   // diagnostics: probes / misses per depth, slot loads per probe
@@ -371,11 +390,15 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
         const bool fits = base + wtotal <= p.cap_ids;
         if (in_range && !defer) p.spans[t] = make_uint2(fits ? static_cast<u32>(base + pre) : 0u, mine);
         const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, nd);
-        if (fits && wtotal) {
+        if (fits && wtotal && !(p.flags & MP_DIAG_NO_PUBLISH)) {
             u32* __restrict__ out = p.out_ids + base;
             u32 cur = pre;                                    // this lane's write position inside the tile chunk
             for (u32 k = 0; k < maxd; ++k) {                  // row k: the k-th descriptor of every lane
-                Desc dsc = k < nd ? dpool[static_cast<size_t>(k) * nthreads + gtid] : Desc{0u, 0u};
+                Desc dsc{0u, 0u};
+                if (k < nd) {
+                    if (k < SD) { const uint2 v = s_desc[k][tid]; dsc = Desc{v.x, v.y}; }
+                    else dsc = dpool[static_cast<size_t>(k - SD) * nthreads + gtid];
+                }
                 const u32 ni = dsc.cnt;
                 const u32 dst = cur;
                 cur += ni;
@@ -458,10 +481,13 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                 u64 itA = 0, itB = 0;
                 bool pA = false, pB = false;
                 if (hit && d < L) {
-                    if (r.plus != 0 && !dollar_root) { pA = true; itA = make_item(0, d + 1, KIND_PLUS, r.plus); }
+                    const u32 plus_idx = r.plus & ~PLUS_WIDE_FLAG;
+                    if (plus_idx != 0 && !dollar_root) { pA = true; itA = make_item(0, d + 1, KIND_PLUS, plus_idx); }
                     if (r.mask != 0 && d < p.tok_levels) {
                         u32 tk = d < TOK8 ? p.tok8[static_cast<size_t>(t) * TOK8 + d] : p.tok[static_cast<size_t>(d) * p.n + t];
-                        if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) { pB = true; itB = make_item(0, d + 1, KIND_PROBE, r.node); }
+                        if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk)) && (!(r.plus & PLUS_WIDE_FLAG) || cfilter_maybe(tv, r.node, tk))) {
+                            pB = true; itB = make_item(0, d + 1, KIND_PROBE, r.node);
+                        }
                     }
                 }
                 if (STATS && pass == 0) { sV += hit; sE += (hit && d < L); }

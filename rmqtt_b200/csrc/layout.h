@@ -80,6 +80,18 @@ constexpr u32 DICT_INLINE_MAX = 27;
 
 struct Range { u32 off, cnt; };
 
+// ---- child filter of wide nodes -----------------------------------------------------------------
+// The 32-bit Bloom mask in a record saturates once a node has more than a few dozen children, yet exactly
+// those nodes (`reg/+`, `+/site`, ...) are probed by every topic for children that mostly do not exist —
+// each such probe is a cold HBM request that finds an empty slot (measured: 1.76 M of them per 1 M topics on
+// C3).  Nodes with more than WIDE_FANOUT literal children therefore register ALL their child edges in one
+// small blocked Bloom filter (16 bits per edge; a few MB, L2 resident) and announce it with a flag in the
+// top bit of the `plus` field of their record.  A negative answer skips the probe; stale bits after removals
+// only cost a wasted probe.
+constexpr u32 PLUS_WIDE_FLAG = 0x80000000u;
+constexpr u32 WIDE_FANOUT = 48;
+
+
 // Root record + table geometry handed to every kernel by value.
 struct TrieView {
     const EdgeSlot* edges;
@@ -88,6 +100,8 @@ struct TrieView {
     const u32* values;
     const DictSlot* dict;
     const u8* pool;
+    const u32* cfilter;     // child filter of wide nodes (words)
+    u32 cfilter_mask;       // #words - 1
     u32 edge_mask;      // capacity-1 (capacity is a power of two)
     u32 dict_mask;
     u32 root_plus, root_hash_ref, root_hash_cnt, root_mask;
@@ -118,6 +132,13 @@ GM_HD u32 dict_hash_words(const u32 (&w)[7]) {
     return fmix32(h);
 }
 GM_HD u32 mask_bit(u32 token) { return 1u << ((token * 0x9E3779B1u) >> 27); }
+// child filter of wide nodes: word index + the two bits of an edge
+GM_HD void cfilter_pos(u32 parent, u32 token, u32 word_mask, u32& word, u32& bits) {
+    const u32 h = fmix32((parent ^ 0x68E31DA4u) * 0x9E3779B1u + token * 0x85EBCA77u);
+    const u32 g = fmix32(h + 0x9E3779B9u);
+    word = h & word_mask;
+    bits = (1u << (g & 31u)) | (1u << ((g >> 5) & 31u));
+}
 
 // Shard of a level-0 string (multi-GPU partitioning by topic root).
 GM_HD u32 shard_of_hash(u32 h, u32 nshards) { return static_cast<u32>((static_cast<u64>(fmix32(h ^ 0x5bd1e995u)) * nshards) >> 32); }

@@ -7,6 +7,7 @@ import numpy as np
 
 M32 = 0xFFFFFFFF
 CNT_BIG = 0xFFFF
+PLUS_WIDE_FLAG = 0x80000000
 TOK_UNKNOWN, TOK_PLUS, TOK_HASH, TOK_BLANK = 0, 1, 2, 3
 
 
@@ -42,6 +43,12 @@ def dict_hash(b):
     return fmix32(fnv(b) ^ ((len(b) * 0x9E3779B1) & M32))
 
 
+def cfilter_pos(parent, token, word_mask):
+    h = fmix32((((parent ^ 0x68E31DA4) * 0x9E3779B1) + token * 0x85EBCA77) & M32)
+    g = fmix32((h + 0x9E3779B9) & M32)
+    return h & word_mask, (1 << (g & 31)) | (1 << ((g >> 5) & 31))
+
+
 def mask_bit(tok):
     return 1 << (((tok * 0x9E3779B1) & M32) >> 27)
 
@@ -50,6 +57,7 @@ class Tables:
     def __init__(self, t):
         self.edges, self.plus, self.ranges, self.values = t["edges"], t["plus"], t["ranges"], t["values"]
         self.dict, self.pool = t["dict"], t["pool"]
+        self.cfilter = t["cfilter"]
         self.root_plus, self.root_hash_ref, self.root_mask, self.max_depth, self.root_hash_cnt = (int(x) for x in t["root"])
         self.dict_bytes = self.dict.view(np.uint8).reshape(len(self.dict), 32)
 
@@ -135,12 +143,20 @@ class Tables:
                 F += self.expand(r["own_ref"], r["cnts"] >> 16, out)
                 continue
             E += 1
-            if r["plus"] and not dollar_root:
-                p = self.plus[r["plus"]]
+            plus_idx = r["plus"] & ~PLUS_WIDE_FLAG & M32
+            if plus_idx and not dollar_root:
+                p = self.plus[plus_idx]
                 stack.append((dict(node=int(p[0]), plus=int(p[1]), hash_ref=int(p[2]), own_ref=int(p[3]), mask=int(p[4]), cnts=int(p[5])), d + 1, False))
             t = toks[d]
+            maybe = True
+            if r["plus"] & PLUS_WIDE_FLAG:      # child filter of wide nodes: must never give a false negative
+                w, bits = cfilter_pos(r["node"], t, len(self.cfilter) - 1)
+                maybe = (int(self.cfilter[w]) & bits) == bits
             if t != TOK_UNKNOWN and r["mask"] & mask_bit(t):
                 c = self.probe(r["node"], t)
+                assert maybe or c is None, "child filter false negative"
+                if not maybe:
+                    c = None
                 if c is not None:
                     stack.append((c, d + 1, False))
         return sorted(out), dict(V=V, E=E, F=F, M=len(out), L=L, B=len(topic))

@@ -248,3 +248,73 @@ def test_full_size_properties_c3_shape():
     assert (eng.match_batch(tb, to).counts() == c1 + 1).all()
     eng.remove("#", 0xABCDEF)
     assert (eng.match_batch(tb, to).counts() == c1).all()
+
+
+def test_empty_engine_empty_batch_and_blank_topics():
+    eng = Engine()
+    assert eng.matches("a/b") == []                      # no filters at all
+    res = eng.match_topics([])
+    assert len(res) == 0 and res.needed == 0
+    eng.add("", 1)                                       # the empty filter is [Blank] (topic.rs:497)
+    eng.add("/", 2)
+    eng.add("+", 3)
+    eng.add("#", 4)
+    tree = orc.TopicTree()
+    for f, v in (("", 1), ("/", 2), ("+", 3), ("#", 4)):
+        tree.insert(f, v)
+    topics = ["", "/", "//", "a", "$", "$/", "+", "#"]
+    tb, to = pack(topics)
+    _assert_same(eng.match_batch(tb, to), tree.match_batch(tb, to))
+
+
+def test_capacity_error_reports_needed_across_pipeline_chunks():
+    cfg = wl.C2.scaled(n_subs=50_000, n_topics=300_000)   # > 2 chunks of the pipelined host path
+    sb, so, sv = wl.gen_subs(cfg)
+    tb, to = wl.gen_topics(cfg)
+    eng = Engine()
+    eng.bulk_load(sb, so, sv)
+    full = eng.match_batch(tb, to)
+    assert full.needed == int(full.counts().sum()) > 1000
+    with pytest.raises(GpuMqttError) as ei:
+        eng.match_batch(tb, to, cap_ids=full.needed // 3)
+    assert ei.value.code == N.GM_ERR_CAPACITY
+    again = eng.match_batch(tb, to, cap_ids=full.needed)          # exactly enough
+    assert (again.counts() == full.counts()).all()
+    c1, i1 = full.canonical(); c2, i2 = again.canonical()
+    assert (i1 == i2).all()
+
+
+def test_thread_safety_concurrent_matches_and_mutations():
+    import threading
+    cfg = wl.C2.scaled(n_subs=30_000, n_topics=20_000)
+    sb, so, sv = wl.gen_subs(cfg)
+    tb, to = wl.gen_topics(cfg)
+    eng = Engine()
+    eng.bulk_load(sb, so, sv)
+    base = eng.match_batch(tb, to).counts()
+    errors = []
+
+    def reader():
+        try:
+            for _ in range(6):
+                c = eng.match_batch(tb, to).counts()
+                # the writer only ever adds/removes the filter "zz/never/#", which matches no topic of the batch
+                assert (c == base).all()
+        except Exception as ex:          # noqa: BLE001
+            errors.append(ex)
+
+    def writer():
+        try:
+            for i in range(200):
+                eng.add("zz/never/#", i)
+                eng.remove("zz/never/#", i)
+        except Exception as ex:          # noqa: BLE001
+            errors.append(ex)
+
+    ths = [threading.Thread(target=reader) for _ in range(3)] + [threading.Thread(target=writer)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
+    assert eng.matches("zz/never/x") == []

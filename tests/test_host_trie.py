@@ -117,3 +117,26 @@ def test_huge_value_set_uses_the_range_table():
     T = Tables(eng.debug_tables())
     assert T.match(b"big/x")[0] == tree.matches("big/x")
     assert eng.stats()["garbage_value_words"] == n
+
+
+def test_wide_nodes_child_filter_has_no_false_negatives_across_flushes():
+    """Nodes with > 48 literal children register their edges in the child filter; edges added before the node
+    became wide are back-filled by the rebuild, later ones are inserted directly, and the filter grows."""
+    rng = random.Random(3)
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    names = [f"k{i}" for i in range(400)]
+    rng.shuffle(names)
+    v = 0
+    for chunk in range(8):                       # 8 flushes, the parent 'w' (and 'w/+') crosses the threshold in chunk 0
+        for nm in names[chunk * 50:(chunk + 1) * 50]:
+            for f in (f"w/{nm}", f"w/+/{nm}", f"{nm}/leaf"):
+                v += 1
+                assert eng.add(f, v) == tree.insert(f, v)
+        if chunk == 3:
+            for nm in names[:30]:
+                assert eng.remove(f"w/{nm}", 1 + 3 * names.index(nm)) == tree.remove(f"w/{nm}", 1 + 3 * names.index(nm))
+        T = Tables(eng.debug_tables())           # debug_tables() syncs like a flush
+        for nm in names[:(chunk + 1) * 50:7] + ["nope", "k9999"]:
+            for t in (f"w/{nm}", f"w/x/{nm}", f"{nm}/leaf", f"{nm}"):
+                assert T.match(t.encode())[0] == tree.matches(t), t
+    assert len(T.cfilter) >= 1024
