@@ -402,12 +402,14 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                 const u32 ni = dsc.cnt;
                 const u32 dst = cur;
                 cur += ni;
+                // load-balanced expansion: flat id index e -> (owner lane, k) by binary search over `exc`.
+                // (A/B, profiles/r1_ab_hints_loadfactor.txt: one cooperative copy per large set + per-lane copies of
+                //  the small ones is 10 % slower — the serial shuffle/copy chain per set costs more than the search.)
                 u32 sc = ni;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, sc, o); if (lane >= o) sc += v; }
                 const u32 tot = __shfl_sync(0xFFFFFFFFu, sc, 31);
                 const u32 exc = sc - ni;
-                // load-balanced expansion: flat id index e -> (owner lane, k) by binary search over `exc`
                 for (u32 e0 = 0; e0 < tot; e0 += 32) {
                     const u32 e = e0 + lane;
                     u32 lo = 0;
