@@ -141,6 +141,42 @@ int32_t gm_retain_match_batch_device(gm_engine* e, const void* d_filters_blob, u
                                      const uint32_t* d_filter_offsets, uint64_t n, gm_span* d_out_spans,
                                      uint32_t* d_out_ids, uint64_t cap_ids, uint64_t* needed, int32_t* d_status, void* stream);
 
+/* ---- GpuRouter: DefaultRouter's Router-level semantics above the engine (rmqtt/src/router.rs:109-115, 162-248,
+ *      417-479; rmqtt/src/types.rs:470-508).  This is what a Rust `GpuRouter` keeps on the host;
+ *      it is provided in C++ because the reference toolchain is absent from the build image.                  */
+typedef struct gm_router gm_router;
+typedef struct gm_id {            /* rmqtt::types::Id; equality = all fields (types.rs:1746-1757): `tag` stands for lid/addrs/username/create_time */
+    uint64_t node_id;
+    const char* client_id;
+    uint32_t client_len;
+    uint32_t _pad;
+    uint64_t tag;
+} gm_id;
+typedef struct gm_sub_opts {      /* rmqtt::types::SubscriptionOptions (types.rs:565-718) */
+    uint8_t qos, is_v5, no_local, _pad;
+    uint32_t sub_id;              /* v5 subscription identifier, 0 = none */
+    const char* shared_group;     /* NULL / empty = not a shared subscription */
+    uint32_t shared_group_len;
+} gm_sub_opts;
+typedef struct gm_sub_relation {  /* one element of SubRelations (types.rs:445-453) */
+    uint64_t node_id;
+    uint32_t handle;              /* -> (topic_filter, client_id) through gmr_relation */
+    uint32_t group;               /* 0, or the id of the (filter, shared group) this member belongs to: the caller chooses one member */
+    uint32_t sub_ids_off, sub_ids_cnt; /* v5: accumulated subscription identifiers in out_sub_ids */
+} gm_sub_relation;
+int32_t gmr_create(gm_engine* e, gm_router** out);   /* the router uses, but does not own, the engine */
+void gmr_destroy(gm_router* r);
+int32_t gmr_add(gm_router* r, const char* filter, uint32_t len, const gm_id* id, const gm_sub_opts* opts);   /* Router::add */
+int32_t gmr_remove(gm_router* r, const char* filter, uint32_t len, const gm_id* id, int32_t* removed);       /* Router::remove */
+int64_t gmr_topics(gm_router* r);
+int64_t gmr_routes(gm_router* r);
+/* Router::matches for a batch; publishers[i] is the `this_id` of PUBLISH i (NULL: no no_local filtering).
+ * Returns GM_ERR_CAPACITY with *needed_rels / *needed_sub_ids set when an output is too small.               */
+int32_t gmr_matches_batch(gm_router* r, const gm_id* publishers, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
+                          gm_span* out_spans, gm_sub_relation* out_rels, uint64_t cap_rels, uint32_t* out_sub_ids, uint64_t cap_sub_ids,
+                          uint64_t* needed_rels, uint64_t* needed_sub_ids, int32_t* status);
+int32_t gmr_relation(gm_router* r, uint32_t handle, const char** filter, uint32_t* filter_len, const char** client, uint32_t* client_len);
+
 /* ---- tokeniser only (Topic::from_str for a batch) — used by tests to pin the device dictionary.
  *      out_tokens: [max_tok][n] u32 (level-major), out_meta: [n] (bits 0..23 levels, bit 30 '$', bit 31 invalid) */
 int32_t gm_tokenize_batch(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,

@@ -254,7 +254,10 @@ static void trie_walk(const TrieNode<V>* node, const Topic& path, size_t i,
 }
 
 // ---------------------------------------------------------------- router.rs (DefaultRouter)
-struct Relation { uint32_t rel_id; uint64_t id_tag; };   // stands for (Id, SubscriptionOptions)
+struct Relation {                 // stands for (Id, SubscriptionOptions)
+    uint32_t rel_id; uint64_t id_tag;
+    uint64_t node_id = 0; bool is_v5 = false, no_local = false; uint32_t sub_id = 0; std::string group;
+};
 
 struct Router {
     TrieNode<char> topics;                                                       // TopicTree<()>
@@ -268,8 +271,56 @@ struct Router {
         topics.insert(t, 0, 0);
         auto it = relations.find(std::string(filter));
         if (it == relations.end()) { topics_count++; it = relations.emplace(std::string(filter), std::unordered_map<std::string, Relation>()).first; }
-        auto ins = it->second.insert_or_assign(std::string(client), Relation{rel_id, id_tag});
+        auto ins = it->second.insert_or_assign(std::string(client), Relation{rel_id, id_tag, 0, false, false, 0, {}});
         if (ins.second) relations_count++;
+        return true;
+    }
+    bool add_full(std::string_view filter, std::string_view client, const Relation& rel) {
+        if (!add(filter, client, rel.rel_id, rel.id_tag)) return false;
+        relations[std::string(filter)][std::string(client)] = rel;
+        return true;
+    }
+    // router.rs:162-248 + types.rs:470-508, canonicalised: one text line per result element, sorted.
+    //   "3|node|filter|client"            v3 relation
+    //   "5|node|client|id,id,..."         v5 relation after per-client de-dup, subscription identifiers sorted
+    //   "g|filter|group|node:client;..."  members of one shared group of one matched filter (the reference picks one at random)
+    bool matches_full(std::string_view topic, uint64_t pub_node, std::string_view pub_client, uint64_t pub_tag, std::vector<std::string>& lines) const {
+        Topic t;
+        if (!parse_topic(topic, t)) return false;
+        Counters c;
+        std::vector<const Level*> sp;
+        std::string fs;
+        std::unordered_map<std::string, std::vector<uint32_t>> v5;   // "node|client" -> sub ids
+        trie_walk(&topics, t, 0, sp, c, [&](const std::vector<const Level*>& fp, const std::set<char>&) {
+            fs.clear();
+            for (size_t k = 0; k < fp.size(); ++k) { if (k) fs += '/'; level_to_string(*fp[k], fs); }
+            auto it = relations.find(fs);
+            if (it == relations.end()) return;
+            std::unordered_map<std::string, std::vector<std::string>> groups;
+            for (auto& kv : it->second) {
+                const Relation& r = kv.second;
+                if (r.is_v5 && r.no_local && r.node_id == pub_node && r.id_tag == pub_tag && kv.first == pub_client) continue;   // router.rs:184-189
+                if (!r.group.empty()) { groups[r.group].push_back(std::to_string(r.node_id) + ":" + kv.first); continue; }
+                if (!r.is_v5) lines.push_back("3|" + std::to_string(r.node_id) + "|" + fs + "|" + kv.first);
+                else {
+                    auto& ids = v5[std::to_string(r.node_id) + "|" + kv.first];
+                    if (r.sub_id) ids.push_back(r.sub_id);
+                }
+            }
+            for (auto& g : groups) {
+                std::sort(g.second.begin(), g.second.end());
+                std::string l = "g|" + fs + "|" + g.first + "|";
+                for (size_t k = 0; k < g.second.size(); ++k) { if (k) l += ';'; l += g.second[k]; }
+                lines.push_back(l);
+            }
+        });
+        for (auto& kv : v5) {
+            std::sort(kv.second.begin(), kv.second.end());
+            std::string l = "5|" + kv.first + "|";
+            for (size_t k = 0; k < kv.second.size(); ++k) { if (k) l += ','; l += std::to_string(kv.second[k]); }
+            lines.push_back(l);
+        }
+        std::sort(lines.begin(), lines.end());
         return true;
     }
     // router.rs:439-479  (returns 1 removed, 0 not removed, -1 invalid filter on the prune path)
@@ -523,6 +574,22 @@ int32_t orc_router_add(void* r, const char* f, uint32_t flen, const char* c, uin
 }
 int32_t orc_router_remove(void* r, const char* f, uint32_t flen, const char* c, uint32_t clen, uint64_t id_tag) {
     return static_cast<Router*>(r)->remove(std::string_view(f, flen), std::string_view(c, clen), id_tag);
+}
+int32_t orc_router_add_full(void* r, const char* f, uint32_t flen, const char* c, uint32_t clen, uint32_t rel_id, uint64_t id_tag, uint64_t node_id,
+                            int32_t is_v5, int32_t no_local, uint32_t sub_id, const char* group, uint32_t glen) {
+    Relation rel{rel_id, id_tag, 0, false, false, 0, {}};
+    rel.node_id = node_id; rel.is_v5 = is_v5 != 0; rel.no_local = no_local != 0; rel.sub_id = sub_id;
+    if (group) rel.group.assign(group, glen);
+    return static_cast<Router*>(r)->add_full(std::string_view(f, flen), std::string_view(c, clen), rel) ? 1 : -1;
+}
+// canonical text (lines joined by '\n') into out (cap bytes); returns needed bytes, or -1 for an invalid topic
+int64_t orc_router_match_full(void* r, const char* s, uint32_t len, uint64_t pub_node, const char* pub_client, uint32_t pclen, uint64_t pub_tag, char* out, uint64_t cap) {
+    std::vector<std::string> lines;
+    if (!static_cast<Router*>(r)->matches_full(std::string_view(s, len), pub_node, std::string_view(pub_client, pclen), pub_tag, lines)) return -1;
+    std::string all;
+    for (size_t i = 0; i < lines.size(); ++i) { if (i) all += '\n'; all += lines[i]; }
+    if (all.size() <= cap) std::memcpy(out, all.data(), all.size());
+    return static_cast<int64_t>(all.size());
 }
 int64_t orc_router_topics(void* r) { return static_cast<Router*>(r)->topics_count; }
 int64_t orc_router_routes(void* r) { return static_cast<Router*>(r)->relations_count; }

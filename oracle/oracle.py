@@ -58,6 +58,8 @@ def lib():
         "orc_router_free": (None, [vp]),
         "orc_router_add": (i32, [vp, cp, u32, cp, u32, u32, u64]),
         "orc_router_remove": (i32, [vp, cp, u32, cp, u32, u64]),
+        "orc_router_add_full": (i32, [vp, cp, u32, cp, u32, u32, u64, u64, i32, i32, u32, cp, u32]),
+        "orc_router_match_full": (i64, [vp, cp, u32, u64, cp, u32, u64, vp, u64]),
         "orc_router_topics": (i64, [vp]),
         "orc_router_routes": (i64, [vp]),
         "orc_router_topics_tree": (u64, [vp]),
@@ -209,6 +211,24 @@ class Router:
     def remove(self, filt, client, id_tag: int = 0) -> int:
         f, c = _b(filt), _b(client)
         return int(lib().orc_router_remove(self._h, f, len(f), c, len(c), id_tag))
+
+    def add_full(self, filt, client, rel_id: int, id_tag: int, node_id: int, is_v5=False, no_local=False, sub_id=0, group="") -> bool:
+        f, c, g = _b(filt), _b(client), _b(group)
+        return lib().orc_router_add_full(self._h, f, len(f), c, len(c), rel_id, id_tag, node_id, int(is_v5), int(no_local), sub_id, g, len(g)) > 0
+
+    def matches_full(self, topic, pub_node=0, pub_client="", pub_tag=0):
+        """Canonical sorted text lines of DefaultRouter::_matches (see oracle.cpp Router::matches_full); None if invalid."""
+        t, pc = _b(topic), _b(pub_client)
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            n = lib().orc_router_match_full(self._h, t, len(t), pub_node, pc, len(pc), pub_tag, buf, cap)
+            if n < 0:
+                return None
+            if n <= cap:
+                txt = buf.raw[:n].decode()
+                return txt.split("\n") if txt else []
+            cap = int(n)
 
     def bulk_add(self, blob, offs, vals, nthreads: int = 1) -> int:
         return int(lib().orc_router_bulk_add(self._h, _ptr(blob), _ptr(offs), _ptr(vals), len(vals), nthreads))

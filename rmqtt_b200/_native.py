@@ -35,6 +35,19 @@ class GmStats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class GmId(C.Structure):
+    _fields_ = [("node_id", C.c_uint64), ("client_id", C.c_char_p), ("client_len", C.c_uint32), ("_pad", C.c_uint32), ("tag", C.c_uint64)]
+
+
+class GmSubOpts(C.Structure):
+    _fields_ = [("qos", C.c_uint8), ("is_v5", C.c_uint8), ("no_local", C.c_uint8), ("_pad", C.c_uint8), ("sub_id", C.c_uint32),
+                ("shared_group", C.c_char_p), ("shared_group_len", C.c_uint32)]
+
+
+class GmSubRelation(C.Structure):
+    _fields_ = [("node_id", C.c_uint64), ("handle", C.c_uint32), ("group", C.c_uint32), ("sub_ids_off", C.c_uint32), ("sub_ids_cnt", C.c_uint32)]
+
+
 class GmWork(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("visited", "probed", "filters", "ids", "levels", "bytes", "deferred")] + \
                [("probes_by_depth", C.c_uint64 * 8), ("misses_by_depth", C.c_uint64 * 8), ("slot_loads", C.c_uint64)]
@@ -66,6 +79,14 @@ SIGNATURES = {
     "gm_retain_bulk_load": (_i32, [_vp, _vp, _vp, _vp, _u64, _P(_u64)]),
     "gm_retain_match_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
     "gm_retain_match_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp, _vp]),
+    "gmr_create": (_i32, [_vp, _P(_vp)]),
+    "gmr_destroy": (None, [_vp]),
+    "gmr_add": (_i32, [_vp, _cp, _u32, _P(GmId), _P(GmSubOpts)]),
+    "gmr_remove": (_i32, [_vp, _cp, _u32, _P(GmId), _P(_i32)]),
+    "gmr_topics": (C.c_int64, [_vp]),
+    "gmr_routes": (C.c_int64, [_vp]),
+    "gmr_matches_batch": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _P(_u64), _P(_u64), _vp]),
+    "gmr_relation": (_i32, [_vp, _u32, _P(_cp), _P(_u32), _P(_cp), _P(_u32)]),
     "gm_tokenize_batch": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gm_get_stats": (_i32, [_vp, _P(GmStats)]),
     "gm_kernel_ms_ring": (_i32, [_vp, _vp, _u32, _P(_u32)]),

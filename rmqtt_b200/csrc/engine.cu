@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "retain_kernels.cuh"
 #include "retain_tree.h"
+#include "router_host.h"
 
 using namespace gm;
 
@@ -673,6 +674,68 @@ int32_t gm_retain_match_batch(gm_engine* e, const char* blob, const uint32_t* of
         CUDA_TRY(cudaMemcpyAsync(out_ids, e->d_ids.p, total * sizeof(u32), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
     }
+    return GM_OK;
+}
+
+// ---- GpuRouter (router_host.cpp) ------------------------------------------------------------------------
+struct gm_router { GpuRouter impl; explicit gm_router(gm_engine* e) : impl(e) {} };
+
+static GpuRouter::Id to_id(const gm_id* id) {
+    GpuRouter::Id r;
+    r.node_id = id->node_id; r.tag = id->tag;
+    if (id->client_id) r.client_id.assign(id->client_id, id->client_len);
+    return r;
+}
+
+int32_t gmr_create(gm_engine* e, gm_router** out) {
+    if (!e || !out) return GM_ERR_INVALID_ARG;
+    *out = new gm_router(e);
+    return GM_OK;
+}
+void gmr_destroy(gm_router* r) { delete r; }
+
+int32_t gmr_add(gm_router* r, const char* filter, uint32_t len, const gm_id* id, const gm_sub_opts* opts) {
+    if (!r || !id || (!filter && len)) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    GpuRouter::Opts o;
+    if (opts) { o.qos = opts->qos; o.is_v5 = opts->is_v5; o.no_local = opts->no_local; o.sub_id = opts->sub_id; if (opts->shared_group) o.group.assign(opts->shared_group, opts->shared_group_len); }
+    return r->impl.add(filter, len, to_id(id), o);
+}
+int32_t gmr_remove(gm_router* r, const char* filter, uint32_t len, const gm_id* id, int32_t* removed) {
+    if (!r || !id || (!filter && len)) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    bool rm = false;
+    int32_t rc = r->impl.remove(filter, len, to_id(id), &rm);
+    if (removed) *removed = rm ? 1 : 0;
+    return rc;
+}
+int64_t gmr_topics(gm_router* r) { return r ? r->impl.topics() : 0; }
+int64_t gmr_routes(gm_router* r) { return r ? r->impl.routes() : 0; }
+
+int32_t gmr_matches_batch(gm_router* r, const gm_id* publishers, const char* blob, const uint32_t* offs, uint64_t n, gm_span* out_spans,
+                          gm_sub_relation* out_rels, uint64_t cap_rels, uint32_t* out_sub_ids, uint64_t cap_sub_ids, uint64_t* needed_rels,
+                          uint64_t* needed_sub_ids, int32_t* status) {
+    if (!r || (n && (!offs || !out_spans || !status))) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    std::vector<gm_span> spans; std::vector<gm_sub_relation> rels; std::vector<uint32_t> ids; std::vector<int32_t> st;
+    int32_t rc = r->impl.matches_batch(publishers, blob, offs, n, spans, rels, ids, st);
+    if (rc != GM_OK) return rc;
+    if (needed_rels) *needed_rels = rels.size();
+    if (needed_sub_ids) *needed_sub_ids = ids.size();
+    std::copy(st.begin(), st.end(), status);
+    if (rels.size() > cap_rels || ids.size() > cap_sub_ids) { g_err = "gmr_matches_batch: output too small"; return GM_ERR_CAPACITY; }
+    std::copy(spans.begin(), spans.end(), out_spans);
+    std::copy(rels.begin(), rels.end(), out_rels);
+    std::copy(ids.begin(), ids.end(), out_sub_ids);
+    return GM_OK;
+}
+
+int32_t gmr_relation(gm_router* r, uint32_t handle, const char** filter, uint32_t* filter_len, const char** client, uint32_t* client_len) {
+    if (!r || !filter || !filter_len || !client || !client_len) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    const std::string *f, *c;
+    if (!r->impl.relation(handle, &f, &c)) return GM_ERR_INVALID_ARG;
+    *filter = f->data(); *filter_len = static_cast<uint32_t>(f->size()); *client = c->data(); *client_len = static_cast<uint32_t>(c->size());
     return GM_OK;
 }
 

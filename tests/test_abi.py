@@ -14,7 +14,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def _declared():
     src = (ROOT / "include" / "gpumqtt.h").read_text()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(gm_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(gmr?_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported_and_bound():

@@ -1,0 +1,99 @@
+"""GPU tier: the C++ GpuRouter (DefaultRouter semantics above the engine) against the oracle's restatement of
+rmqtt/src/router.rs:162-248, 417-479 and rmqtt/src/types.rs:470-508."""
+import random
+
+import pytest
+
+from oracle import oracle as orc
+from rmqtt_b200.engine import GpuMqttError
+from rmqtt_b200 import _native as N
+from rmqtt_b200.router import GpuRouter, Id, SubscriptionOptions
+
+from _gen import rand_filter, rand_topic
+
+pytestmark = pytest.mark.gpu
+
+
+def test_add_remove_counters_and_id_rule():
+    r, o = GpuRouter(), orc.Router()
+    a, b = Id(1, "c1", 11), Id(1, "c2", 22)
+    r.add("a/+", a); o.add_full("a/+", "c1", 0, 11, 1)
+    r.add("a/+", b); o.add_full("a/+", "c2", 1, 22, 1)
+    r.add("a/b", a); o.add_full("a/b", "c1", 2, 11, 1)
+    with pytest.raises(GpuMqttError) as ei:
+        r.add("a/#/b", a)
+    assert ei.value.code == N.GM_ERR_INVALID_TOPIC
+    assert (r.topics(), r.routes(), r.topics_tree()) == (o.topics(), o.routes(), 3) == (2, 3, 3)
+    assert not r.remove("a/+", Id(1, "c1", 99))            # Id mismatch (router.rs:444-451)
+    assert r.remove("a/+", a) and o.remove("a/+", "c1", 11) == 1
+    assert r.remove("a/+", b) and o.remove("a/+", "c2", 22) == 1
+    assert (r.topics(), r.routes()) == (o.topics(), o.routes()) == (1, 1)
+    got = r.matches(Id(9, "pub"), "a/b")
+    assert [(x.topic_filter, x.client_id) for x in got] == [("a/b", "c1")]
+    r.add("a/b", Id(1, "c1", 11), SubscriptionOptions(qos=1))   # re-subscribe replaces, count unchanged (router.rs:430-433)
+    assert r.routes() == 1
+    assert r.matches(Id(9, "pub"), "a/b+") is None
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_random_differential_vs_oracle_router(seed):
+    rng = random.Random(seed)
+    r, o = GpuRouter(), orc.Router()
+    subs = {}
+    clients = [Id(rng.randint(1, 3), f"c{k}", 100 + k) for k in range(25)]
+    v5flag = {}
+    rel = 0
+    for step in range(700):
+        cid = rng.choice(clients)
+        if subs and rng.random() < 0.25:
+            (f, c) = rng.choice(list(subs))
+            ident = subs[(f, c)]
+            wrong = rng.random() < 0.2
+            use = Id(ident.node_id, ident.client_id, 7) if wrong else ident
+            got = r.remove(f, use)
+            want = o.remove(f, ident.client_id, use.tag)
+            assert got == (want == 1)
+            if got:
+                del subs[(f, c)]
+        else:
+            f = rand_filter(rng, 5)
+            v5 = rng.random() < 0.5
+            opts = SubscriptionOptions(qos=rng.randint(0, 2), is_v5=v5, no_local=v5 and rng.random() < 0.5,
+                                       sub_id=rng.randint(1, 9) if v5 and rng.random() < 0.6 else 0,
+                                       shared_group=rng.choice(["", "", "", "g1", "g2"]))
+            rel += 1
+            try:
+                r.add(f, cid, opts)
+            except GpuMqttError as ex:
+                assert ex.code == N.GM_ERR_INVALID_TOPIC
+                assert not o.add_full(f, cid.client_id, rel, cid.tag, cid.node_id, opts.is_v5, opts.no_local, opts.sub_id, opts.shared_group)
+                continue
+            assert o.add_full(f, cid.client_id, rel, cid.tag, cid.node_id, opts.is_v5, opts.no_local, opts.sub_id, opts.shared_group)
+            subs[(f, cid.client_id)] = cid
+            v5flag[(f, cid.client_id)] = v5
+        if step % 100 == 99:
+            assert (r.topics(), r.routes()) == (o.topics(), o.routes())
+            topics = [rand_topic(rng, 6) for _ in range(300)]
+            pubs = [rng.choice(clients) for _ in topics]
+            got = r.matches_batch(topics, pubs)
+            for t, p, g in zip(topics, pubs, got):
+                want = o.matches_full(t, p.node_id, p.client_id, p.tag)
+                if want is None:
+                    assert g is None, t
+                    continue
+                lines, groups = [], {}
+                for x in g:
+                    if x.group:
+                        groups.setdefault((x.group, x.topic_filter), []).append(f"{x.node_id}:{x.client_id}")
+                    elif v5flag[(x.topic_filter, x.client_id)]:
+                        lines.append(f"5|{x.node_id}|{x.client_id}|" + ",".join(str(s) for s in sorted(x.sub_ids)))
+                    else:
+                        lines.append(f"3|{x.node_id}|{x.topic_filter}|{x.client_id}")
+                # shared groups: the oracle emits one line per matched-filter occurrence and group with all members
+                wl = [w for w in want if not w.startswith("g|")]
+                wg = sorted(w.split("|", 3)[3] for w in want if w.startswith("g|"))
+                assert sorted(lines) == wl, t
+                # members per (filter, group): an occurrence-multiset; compare flattened member multisets
+                got_members = sorted(m for ms in groups.values() for m in ms)
+                want_members = sorted(m for w in wg for m in w.split(";"))
+                assert got_members == want_members, t
