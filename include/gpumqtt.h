@@ -101,6 +101,10 @@ int32_t gm_sub_remove(gm_engine* e, const char* filter, uint32_t len, uint32_t v
 int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets /* n+1 */, const uint32_t* values,
                      uint64_t n, uint64_t* n_changed);
 int32_t gm_flush(gm_engine* e);
+/* Rebuilds the device tables from the live filters: drops the records of pruned nodes (rmqtt/src/trie.rs:126-128 removes
+ * them eagerly; here they linger as dead records until compaction) and the garbage left by replaced value sets.
+ * O(live filters).  Not available while retained topics are stored (the level dictionary is shared).          */
+int32_t gm_compact(gm_engine* e);
 
 /* ---- Router::matches for a batch of PUBLISH topic names (host buffers).
  *      topics_blob/topic_offsets: n topic names back to back, topic i = blob[offsets[i] .. offsets[i+1]).

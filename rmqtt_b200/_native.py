@@ -71,6 +71,7 @@ SIGNATURES = {
     "gm_sub_remove": (_i32, [_vp, _cp, _u32, _u32, _P(_i32)]),
     "gm_bulk_load": (_i32, [_vp, _vp, _vp, _vp, _u64, _P(_u64)]),
     "gm_flush": (_i32, [_vp]),
+    "gm_compact": (_i32, [_vp]),
     "gm_match_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
     "gm_match_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp]),
     "gm_match_batch_device_stats": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp, _P(GmWork)]),

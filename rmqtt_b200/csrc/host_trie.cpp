@@ -373,6 +373,33 @@ void HostTrie::write_record(u32 node) {
     }
 }
 
+void HostTrie::compact() {
+    // token -> level string, from the dictionary slots
+    std::vector<std::string> tok_str(next_token_);
+    for (const DictSlot& d : dict) {
+        if (d.w[0] == 0) continue;
+        if ((d.w[7] >> 24) == 0xFF) tok_str[d.w[0]].assign(reinterpret_cast<const char*>(pool.data() + d.w[2]), d.w[1]);
+        else { const char* b = reinterpret_cast<const char*>(&d.w[1]); tok_str[d.w[0]].assign(b, d.w[7] >> 24); }
+    }
+    tok_str[TOK_PLUS] = "+"; tok_str[TOK_HASH] = "#"; tok_str[TOK_BLANK] = "";
+    HostTrie fresh(max_levels_);
+    fresh.reserve(values_size_);
+    std::vector<u32> path;
+    std::string f;
+    for (u32 id = 1; id < nodes_.size(); ++id) {
+        const HNode& n = nodes_[id];
+        if (n.nvals == 0) continue;
+        path.clear();
+        for (u32 x = id; x != 0; x = nodes_[x].parent) path.push_back(nodes_[x].token);
+        f.clear();
+        for (size_t k = path.size(); k-- > 0;) { f += tok_str[path[k]]; if (k) f += '/'; }
+        bool ch;
+        if (n.nvals == 1) fresh.insert(f.data(), static_cast<u32>(f.size()), n.v0, &ch);
+        else for (u32 v : multi_[id]) fresh.insert(f.data(), static_cast<u32>(f.size()), v, &ch);
+    }
+    *this = std::move(fresh);
+}
+
 void HostTrie::sync() {
     if (cfilter_rebuild_) {
         // nodes that just became wide must republish their record (flag)

@@ -46,6 +46,9 @@ class HostTrie {
 
     // Resolve dirty nodes into slot patches (called by flush).
     void sync();
+    // Rebuild every table from the live content: drops pruned nodes, dead dictionary use and value garbage.
+    // Tokens are re-assigned; the caller must treat all device tables as new (everything is marked dirty).
+    void compact();
 
     // reference-visible statistics
     u64 values_size() const { return values_size_; }   // trie.rs:148-151

@@ -127,6 +127,9 @@ class Engine:
     def flush(self):
         self._check(self._lib.gm_flush(self._h))
 
+    def compact(self):
+        self._check(self._lib.gm_compact(self._h))
+
     # ---- Router::matches for a batch (host buffers) ---------------------------------------------------
     def match_batch(self, blob: np.ndarray, offs: np.ndarray, cap_ids: int | None = None) -> MatchResult:
         assert blob.dtype == np.uint8 and offs.dtype == np.uint32

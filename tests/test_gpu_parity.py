@@ -318,3 +318,28 @@ def test_thread_safety_concurrent_matches_and_mutations():
         t.join()
     assert not errors, errors
     assert eng.matches("zz/never/x") == []
+
+
+def test_compact_on_device_keeps_parity():
+    rng = random.Random(77)
+    eng, tree = Engine(), orc.TopicTree()
+    live = []
+    for _ in range(3000):
+        f, v = rand_filter(rng), rng.randint(0, 30)
+        try:
+            eng.add(f, v)
+        except GpuMqttError:
+            continue
+        tree.insert(f, v)
+        live.append((f, v))
+    for f, v in live[:2000]:
+        assert eng.remove(f, v) == tree.remove(f, v)
+    topics = [rand_topic(rng, 9) for _ in range(3000)]
+    tb, to = pack(topics)
+    _assert_same(eng.match_batch(tb, to), tree.match_batch(tb, to))
+    eng.compact()
+    st = eng.stats()
+    assert st["device_nodes"] == st["nodes"] == tree.nodes_size() and st["garbage_value_words"] == 0
+    _assert_same(eng.match_batch(tb, to), tree.match_batch(tb, to))
+    eng.add("q/+/r", 9); tree.insert("q/+/r", 9)
+    assert eng.matches("q/x/r") == tree.matches("q/x/r")

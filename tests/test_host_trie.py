@@ -140,3 +140,31 @@ def test_wide_nodes_child_filter_has_no_false_negatives_across_flushes():
             for t in (f"w/{nm}", f"w/x/{nm}", f"{nm}/leaf", f"{nm}"):
                 assert T.match(t.encode())[0] == tree.matches(t), t
     assert len(T.cfilter) >= 1024
+
+
+def test_compact_drops_dead_nodes_and_garbage_keeps_matches():
+    rng = random.Random(17)
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    live = []
+    for _ in range(1500):
+        f, v = rand_filter(rng), rng.randint(0, 40)
+        _apply(eng, tree, f, v, "add")
+        live.append((f, v))
+    for f, v in live[:1000]:
+        _apply(eng, tree, f, v, "remove")
+    eng.flush()
+    before = eng.stats()
+    assert before["device_nodes"] > before["nodes"]            # pruned nodes linger as dead records
+    eng.compact()
+    after = eng.stats()
+    assert after["nodes"] == after["device_nodes"] == tree.nodes_size()
+    assert after["values"] == tree.values_size() and after["garbage_value_words"] == 0
+    assert after["dict_entries"] <= before["dict_entries"]
+    T = Tables(eng.debug_tables())
+    for _ in range(300):
+        t = rand_topic(rng)
+        assert T.match(t.encode())[0] == tree.matches(t), t
+    # the compacted trie keeps working incrementally
+    _apply(eng, tree, "a/+/zz", 5, "add")
+    T = Tables(eng.debug_tables())
+    assert T.match(b"a/b/zz")[0] == tree.matches("a/b/zz")
