@@ -34,10 +34,13 @@ int RetainTreeHost::set(const char* topic, u32 len, u32 value, bool* had_old, u3
         node = c;
     }
     HN& n = nodes_[node];
+    // Re-publishing a retained message on a topic that keeps its handle changes nothing on the device: the
+    // device copy is only rebuilt when the set of retained topics (or a handle) actually changes.
+    const bool same = n.has_val && n.val == value;
     if (n.has_val) { if (had_old) *had_old = true; if (old) *old = n.val; }
     else n_values_++;
     n.has_val = true; n.val = value;
-    dirty = true;
+    if (!same) dirty = true;
     return PARSE_OK;
 }
 

@@ -90,3 +90,15 @@ def test_random_differential(seed):
                 want = tree.matches(f)
                 got = R.match(f.encode())
                 assert got == want, f
+
+
+def test_republish_with_the_same_handle_does_not_dirty_the_device_copy():
+    eng = Engine(host_only=True)
+    eng.retain_set("a/b", 7)
+    eng.flush()
+    assert eng.stats()["pending"] in (0, 1)        # root record of the subscription trie may still be pending in host-only mode
+    eng.retain_set("a/b", 7)                       # same topic, same handle (new payload lives on the host)
+    t1 = eng.debug_tables()["rvals"].tolist()
+    eng.retain_set("a/b", 8)
+    t2 = eng.debug_tables()["rvals"].tolist()
+    assert t1 == [7] and t2 == [8]
