@@ -1,7 +1,13 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 900 python bench.py > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err; tail -c 600 gpurun_out/bench_final_n1.json; tail -2 gpurun_out/bench_final_n1.err
-timeout 900 python bench.py --impl reference --steps 40 --warmup 3 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err; tail -c 700 gpurun_out/bench_final_ref.json
-timeout 900 python tools/bench_configs.py C1 C2 C4 > gpurun_out/configs_final.jsonl 2>gpurun_out/configs_final.err; cut -c1-400 gpurun_out/configs_final.jsonl
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_match_fast -s 5 -c 1 -o gpurun_out/prof_k2_final python bench.py --steps 2 --warmup 3 --no-cpu-baseline --batches 2 --e2e-steps 1 > gpurun_out/ncu_k2_final.log 2>&1; tail -1 gpurun_out/ncu_k2_final.log | cut -c1-80
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --batches 3 --e2e-steps 1 > /dev/null 2>&1
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+for N in 8 4; do
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$N bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_n$N.json").read().strip().splitlines()[-1])
+    print("N=$N", "value %.3e"%d["value"], "ms/step %.3f"%d["ms_per_step"], "e2e %.3e"%d["e2e"]["value"], d["roofline"]["kernel_ms"], d["config"]["trie"]["values"])
+except Exception as e: print("N=$N failed", e)
+PY
+tail -2 gpurun_out/bench_n$N.err | cut -c1-300
+done
