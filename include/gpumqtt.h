@@ -199,7 +199,7 @@ uint64_t gm_kernel_launches(gm_engine* e);
 uint32_t gm_shard_of(const char* topic_or_filter, uint32_t len, uint32_t n_shards);
 /* DEBUG/TEST: read-only view of the host mirror of a device table, in device layout (rmqtt_b200/csrc/layout.h).
  * which: 0 edges(32 B) 1 plus(32 B) 2 ranges(8 B) 3 values(4 B) 4 dict(32 B) 5 long-string pool(1 B)
- *        6 root record {plus, hash_ref, mask, max_depth, hash_cnt}; retained tree: 7 nodes(32 B) 8 child blocks(16 B)
+ *        6 root record {plus, hash_ref, mask, max_depth, hash_cnt}; retained tree: 7 nodes(32 B, host bookkeeping) 8 child blocks(32 B entries)
  *        9 pre-order values(4 B); 12 child filter of wide nodes (4 B words).  Valid until the next mutating call.                                       */
 int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t* count);
 /* pinned host memory for the host-buffer entry points */

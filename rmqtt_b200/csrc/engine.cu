@@ -33,9 +33,13 @@ thread_local std::string g_err;
         }                                                                                           \
     } while (0)
 
-struct DevBuf {
+struct DevBuf {   // owning device allocation (freed on destruction, also on the early-return error paths)
     void* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t s = nullptr) {
         if (bytes <= cap) return cudaSuccess;
         size_t ncap = std::max(bytes, cap + cap / 2);
@@ -96,7 +100,7 @@ struct gm_engine {
     // retained tree (device copy of the flattened arrays) + scratch of the retained lookup
     DevBuf d_rnodes, d_rkids, d_redges, d_rvals;
     DevBuf d_rfront[2], d_rdescs, d_rctl, d_rq;
-    u32 r_cap_items = 1u << 20, r_cap_desc = 1u << 20;
+    u32 r_cap_items = 1u << 22, r_cap_desc = 1u << 22;   // totals over the RQ slices of each queue
     u64 launches = 0;
     bool k2_attr_set = false;
 
@@ -177,8 +181,9 @@ struct gm_engine {
 
     RetainView rview() const {
         RetainView v{};
-        v.nodes = d_rnodes.as<RNode>(); v.kids = d_rkids.as<RKid>(); v.edges = d_redges.as<REdge>(); v.vals = d_rvals.as<u32>();
+        v.kids = d_rkids.as<RKid>(); v.edges = d_redges.as<REdge>(); v.vals = d_rvals.as<u32>();
         v.edge_mask = static_cast<u32>(rtree.redges.size() - 1);
+        if (!rtree.rnodes.empty()) { v.root_first_kid = rtree.rnodes[0].first_kid; v.root_nk_flags = rtree.rnodes[0].nkids | (rtree.rnodes[0].flags << 28); }
         v.root_plain_kids = rtree.root_plain_kids; v.root_plain_val_hi = rtree.root_plain_val_hi; v.max_depth = rtree.max_depth;
         return v;
     }
@@ -199,7 +204,7 @@ struct gm_engine {
         if (rtree.dirty) {   // retained tree: re-flattened and shipped whole (pre-order layout; delta overlay is future work)
             rtree.flatten();
             int rs;
-            if ((rs = upload_whole(d_rnodes, rtree.rnodes)) != GM_OK) return rs;
+            if ((rs = upload_whole(d_rnodes, std::vector<u32>{0u})) != GM_OK) return rs;   // marker: "retained tree shipped" (records travel in rkids / redges)
             if ((rs = upload_whole(d_rkids, rtree.rkids)) != GM_OK) return rs;
             if ((rs = upload_whole(d_redges, rtree.redges)) != GM_OK) return rs;
             if ((rs = upload_whole(d_rvals, rtree.rvals)) != GM_OK) return rs;
@@ -306,21 +311,22 @@ struct gm_engine {
     }
 
     // ---- retained lookup: tokenise filters -> frontier BFS (one step kernel per tree level) -> publish ----
-    struct RCtl { unsigned long long grand; u32 n_desc; u32 err; u32 counts[1]; };   // counts[max_depth + 3] follow
+    struct RCtl { unsigned long long grand; u32 err; u32 pad; u32 n_desc[RQ]; u32 counts[RQ]; };   // counts[(max_depth + 3) * RQ] follow
 
     int enqueue_retain(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s) {
         const u32 nq = static_cast<u32>(n);
         const u32 depth = rtree.max_depth;
         const u32 S = depth + 2;                       // the walk reads filter levels pos and pos+1 with pos <= tree depth
-        const size_t ctl_bytes = sizeof(RCtl) + (depth + 3) * sizeof(u32);
+        const size_t ctl_bytes = sizeof(RCtl) + static_cast<size_t>(depth + 3) * RQ * sizeof(u32);
         CUDA_TRY(d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * nq * sizeof(u32) : 256));
         CUDA_TRY(d_tok8.ensure(static_cast<size_t>(nq) * TOK8 * sizeof(u32)));
         CUDA_TRY(d_meta.ensure(nq * sizeof(u32)));
         CUDA_TRY(d_rq.ensure(static_cast<size_t>(nq) * 3 * sizeof(u32)));
         CUDA_TRY(d_rctl.ensure(ctl_bytes));
-        CUDA_TRY(d_rfront[0].ensure(static_cast<size_t>(r_cap_items) * sizeof(RItem)));
-        CUDA_TRY(d_rfront[1].ensure(static_cast<size_t>(r_cap_items) * sizeof(RItem)));
-        CUDA_TRY(d_rdescs.ensure(static_cast<size_t>(r_cap_desc) * sizeof(RDesc)));
+        const u32 slice_items = r_cap_items / RQ, slice_desc = r_cap_desc / RQ;   // queues are split into RQ slices
+        CUDA_TRY(d_rfront[0].ensure(static_cast<size_t>(slice_items) * RQ * sizeof(RItem)));
+        CUDA_TRY(d_rfront[1].ensure(static_cast<size_t>(slice_items) * RQ * sizeof(RItem)));
+        CUDA_TRY(d_rdescs.ensure(static_cast<size_t>(slice_desc) * RQ * sizeof(RDesc)));
         CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
         if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(s, ev_match, 0));
         CUDA_TRY(cudaMemsetAsync(d_rctl.p, 0, ctl_bytes, s));
@@ -336,16 +342,17 @@ struct gm_engine {
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
         RetainParams rp{};
         rp.v = rview(); rp.qtok8 = d_tok8.as<u32>(); rp.qtok = d_tok.as<u32>(); rp.qmeta = d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
-        rp.descs = d_rdescs.as<RDesc>(); rp.n_desc = &ctl->n_desc; rp.cap_items = r_cap_items; rp.cap_desc = r_cap_desc;
+        rp.descs = d_rdescs.as<RDesc>(); rp.n_desc = ctl->n_desc; rp.cap_items = slice_items; rp.cap_desc = slice_desc;
         rp.qtotal = qtotal; rp.err = &ctl->err;
         k_retain_init<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RItem>(), &ctl->counts[0]);
         const int grid = num_sms * 8;
         for (u32 lvl = 0; lvl <= depth; ++lvl)
-            k_retain_step<<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RItem>(), &ctl->counts[lvl], d_rfront[(lvl + 1) & 1].as<RItem>(), &ctl->counts[lvl + 1]);
+            k_retain_step<<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RItem>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RItem>(),
+                                               &ctl->counts[static_cast<size_t>(lvl + 1) * RQ]);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[2], s));
         k_retain_scan<<<1, 1024, 0, s>>>(qtotal, nq, qbase, reinterpret_cast<uint2*>(d_spans_), &ctl->grand);
-        k_retain_expand<<<grid, 256, 0, s>>>(d_rdescs.as<RDesc>(), &ctl->n_desc, r_cap_desc, d_rvals.as<u32>(), qbase, qcur, d_ids_, cap_ids);
+        k_retain_expand<<<grid, 256, 0, s>>>(d_rdescs.as<RDesc>(), ctl->n_desc, slice_desc, d_rvals.as<u32>(), qbase, qcur, d_ids_, cap_ids);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[3], s));
         ring_n++;
@@ -784,8 +791,6 @@ int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offset
     CUDA_TRY(cudaStreamSynchronize(s));
     for (uint64_t i = 0; i < n; ++i)          // levels 0..7 live in the per-topic row; present them level-major too
         for (u32 l = 0; l < TOK8 && l < max_tok; ++l) out_tokens[static_cast<size_t>(l) * n + i] = rows[i * TOK8 + l];
-    tok8.release();
-    tok.release(); meta.release(); stat.release();
     return GM_OK;
 }
 

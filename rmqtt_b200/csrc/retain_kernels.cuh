@@ -16,8 +16,12 @@
 
 namespace gm {
 
-struct alignas(16) RItem { u32 q, node, pos, pad; };
+struct alignas(32) RItem { u32 q, pos, node, first_kid, nk_flags, val, val_lo, val_hi; };   // the node's record travels with the item
 struct alignas(16) RDesc { u32 q, ref, cnt, kind; };   // kind 0: the value itself, 1: rvals[ref .. ref+cnt)
+
+// Work queues (frontier, descriptor list) are split into RQ slices with one counter each: with a single bump
+// counter, the ~10^7 warp-aggregated appends of a C4 batch serialise on one L2 atomic unit.
+constexpr u32 RQ = 64;
 
 struct RetainParams {
     RetainView v;
@@ -26,8 +30,8 @@ struct RetainParams {
     const u32* qmeta;    // [nq]
     u32 nq, tok_levels;
     RDesc* descs;
-    u32* n_desc;
-    u32 cap_items, cap_desc;
+    u32* n_desc;         // [RQ]
+    u32 cap_items, cap_desc;   // per SLICE
     u32* qtotal;         // [nq] matched values per query
     u32* err;            // bit 0: frontier overflow, bit 1: descriptor overflow
 };
@@ -36,35 +40,54 @@ __device__ __forceinline__ u32 retain_tok(const RetainParams& p, u32 q, u32 pos)
     return pos < TOK8 ? p.qtok8[static_cast<size_t>(q) * TOK8 + pos] : p.qtok[static_cast<size_t>(pos) * p.nq + q];
 }
 
-__device__ __forceinline__ u32 retain_child(const RetainView& v, u32 node, u32 token) {
+// exact child lookup: the slot carries the child's whole record
+__device__ __forceinline__ bool retain_child(const RetainView& v, u32 node, u32 token, u32 (&s)[8]) {
     u32 idx = redge_hash(node, token) & v.edge_mask;
     for (;;) {
-        const uint4 s = __ldg(reinterpret_cast<const uint4*>(v.edges + idx));
-        if (s.z == 0) return 0u;
-        if (s.x == node && s.y == token) return s.z;
+        ld256(v.edges + idx, s);
+        if (s[2] == 0) return false;
+        if (s[0] == node && s[1] == token) return true;
         idx = (idx + 1) & v.edge_mask;
     }
 }
 
-// warp-aggregated append of one element per flagged lane
+// warp-aggregated append of one element per flagged lane into slice `sq` of a sliced queue
 template <class T>
-__device__ __forceinline__ void warp_append(bool want, const T& item, T* arr, u32* counter, u32 cap, u32* err, u32 errbit, u32 lane, u32 lt) {
+__device__ __forceinline__ void warp_append(bool want, const T& item, T* arr, u32* counters, u32 slice_cap, u32 sq, u32* err, u32 errbit, u32 lane, u32 lt) {
     const u32 b = __ballot_sync(0xFFFFFFFFu, want);
     if (!b) return;
     u32 base = 0;
-    if (lane == static_cast<u32>(__ffs(b) - 1)) base = atomicAdd(counter, static_cast<u32>(__popc(b)));
+    if (lane == static_cast<u32>(__ffs(b) - 1)) base = atomicAdd(counters + sq, static_cast<u32>(__popc(b)));
     base = __shfl_sync(0xFFFFFFFFu, base, __ffs(b) - 1);
     if (want) {
         const u32 at = base + __popc(b & lt);
-        if (at < cap) arr[at] = item; else atomicOr(err, errbit);
+        if (at < slice_cap) arr[static_cast<size_t>(sq) * slice_cap + at] = item; else atomicOr(err, errbit);
     }
+}
+
+// block-wide: exclusive prefix of the (clamped) slice counts into s_pre[RQ + 1]; returns the total
+__device__ __forceinline__ u32 queue_prefix(const u32* __restrict__ counters, u32 slice_cap, u32* s_pre) {
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        for (u32 k = 0; k < RQ; ++k) { s_pre[k] = run; run += min(counters[k], slice_cap); }
+        s_pre[RQ] = run;
+    }
+    __syncthreads();
+    return s_pre[RQ];
+}
+// logical index g -> physical index inside the sliced array
+__device__ __forceinline__ size_t queue_locate(const u32* s_pre, u32 g, u32 slice_cap) {
+    u32 lo = 0;
+#pragma unroll
+    for (u32 step = RQ / 2; step; step >>= 1) if (s_pre[lo + step] <= g) lo += step;
+    return static_cast<size_t>(lo) * slice_cap + (g - s_pre[lo]);
 }
 
 __global__ void k_retain_init(RetainParams p, RItem* out, u32* n_out) {
     const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 lane = threadIdx.x & 31, lt = lanemask_lt();
     const bool ok = q < p.nq && !(p.qmeta[q] & META_INVALID);
-    warp_append(ok, RItem{q, 0u, 0u, 0u}, out, n_out, p.cap_items, p.err, 1u, lane, lt);
+    warp_append(ok, RItem{q, 0u, 0u, p.v.root_first_kid, p.v.root_nk_flags, 0u, 0u, p.v.root_plain_val_hi}, out, n_out, p.cap_items, (q >> 5) % RQ, p.err, 1u, lane, lt);
 }
 
 __global__ void __launch_bounds__(256)
@@ -72,11 +95,14 @@ k_retain_step(RetainParams p, const RItem* __restrict__ in, const u32* __restric
     const u32 lane = threadIdx.x & 31, lt = lanemask_lt();
     const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const RetainView& v = p.v;
-    const u32 n_in = min(*n_in_p, p.cap_items);
+    __shared__ u32 s_pre[RQ + 1];
+    const u32 n_in = queue_prefix(n_in_p, p.cap_items, s_pre);
+    const u32 sq = gwarp % RQ;                        // this warp appends to its own slice
     for (u32 base = gwarp * 32; base < n_in; base += nwarps * 32) {
         const u32 i = base + lane;
         const bool have = i < n_in;
-        RItem it = have ? in[i] : RItem{0, 0, 0, 0};
+        RItem it{};
+        if (have) { u32 w[8]; ld256(in + queue_locate(s_pre, i, p.cap_items), w); it = RItem{w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]}; }
         u32 exp_kb = 0, exp_n = 0, exp_mode = 0;      // child-block expansion request: 1 = '+', 2 = '#' level by level
         bool push1 = false, emit1 = false, next_hash = false;
         RItem pitem{};
@@ -84,41 +110,36 @@ k_retain_step(RetainParams p, const RItem* __restrict__ in, const u32* __restric
         u32 L = 0;
         if (have) {
             L = p.qmeta[it.q] & META_NLEV_MASK;
-            u32 w[8];
-            ld256(v.nodes + it.node, w);
-            const u32 first_kid = w[0], nkids = w[1], val = w[2], val_lo = w[3], val_hi = w[4], flags = w[5];
+            const u32 nkids = it.nk_flags & RNK_MASK, flags = it.nk_flags >> 28;
             if (nkids == 0 || it.pos == L) {                                     // retain.rs:305-311
-                if (it.pos == L && (flags & 8u)) { emit1 = true; d1 = RDesc{it.q, val, 1u, 0u}; }
+                if (it.pos == L && (flags & 8u)) { emit1 = true; d1 = RDesc{it.q, it.val, 1u, 0u}; }
             } else {
                 const u32 tok = retain_tok(p, it.q, it.pos);
                 next_hash = (it.pos + 1 < L) && retain_tok(p, it.q, it.pos + 1) == TOK_HASH;
                 // precise matching first — Level equality, so a stored literal "+" / "#" child shadows the
                 // wildcard expansion (retain.rs:313)
                 const bool exact_try = tok >= TOK_BLANK || (tok == TOK_PLUS && (flags & RF_LIT_PLUS)) || (tok == TOK_HASH && (flags & RF_LIT_HASH));
-                const u32 child = exact_try ? retain_child(v, it.node, tok) : 0u;
+                u32 c[8];
+                const bool found = exact_try && retain_child(v, it.node, tok, c);
                 const bool root = it.node == 0;
-                if (child) {
-                    if (next_hash) {                                             // '#' matches the parent, retain.rs:317-322
-                        u32 c[8];
-                        ld256(v.nodes + child, c);
-                        if (c[5] & 8u) { emit1 = true; d1 = RDesc{it.q, c[2], 1u, 0u}; }
-                    }
-                    push1 = true; pitem = RItem{it.q, child, it.pos + 1, 0u};
+                if (found) {
+                    if (next_hash && ((c[4] >> 28) & 8u)) { emit1 = true; d1 = RDesc{it.q, c[5], 1u, 0u}; }   // '#' matches the parent, retain.rs:317-322
+                    push1 = true; pitem = RItem{it.q, it.pos + 1, c[2], c[3], c[4], c[5], c[6], c[7]};
                 } else if (tok == TOK_PLUS) {                                    // retain.rs:324-342
-                    exp_kb = first_kid; exp_n = root ? v.root_plain_kids : nkids; exp_mode = 1;
+                    exp_kb = it.first_kid; exp_n = root ? v.root_plain_kids : nkids; exp_mode = 1;
                 } else if (tok == TOK_HASH) {                                    // retain.rs:343-365
                     if (!(flags & RF_SUB_LIT_HASH)) {       // every strict descendant (minus `$` subtrees at the root): one range
-                        const u32 lo = val_lo + ((flags & 8u) ? 1u : 0u), hi = root ? v.root_plain_val_hi : val_hi;
+                        const u32 lo = it.val_lo + ((flags & 8u) ? 1u : 0u), hi = root ? v.root_plain_val_hi : it.val_hi;
                         if (hi > lo) { emit1 = true; d1 = RDesc{it.q, lo, hi - lo, 1u}; }
                     } else {
-                        exp_kb = first_kid; exp_n = root ? v.root_plain_kids : nkids; exp_mode = 2;
+                        exp_kb = it.first_kid; exp_n = root ? v.root_plain_kids : nkids; exp_mode = 2;
                     }
                 }
             }
         }
         if (emit1) atomicAdd(p.qtotal + d1.q, d1.cnt);
-        warp_append(emit1, d1, p.descs, p.n_desc, p.cap_desc, p.err, 2u, lane, lt);
-        warp_append(push1, pitem, out, n_out, p.cap_items, p.err, 1u, lane, lt);
+        warp_append(emit1, d1, p.descs, p.n_desc, p.cap_desc, sq, p.err, 2u, lane, lt);
+        warp_append(push1, pitem, out, n_out, p.cap_items, sq, p.err, 1u, lane, lt);
 
         // ---- load-balanced expansion of the requested child blocks
         u32 sc = exp_n;
@@ -145,22 +166,23 @@ k_retain_step(RetainParams p, const RItem* __restrict__ in, const u32* __restric
             RDesc d{};
             RItem ni{};
             if (e < tot) {
-                const uint4 kd = __ldg(reinterpret_cast<const uint4*>(v.kids + o_kb + (e - o_exc)));   // {token, child, val, nkids|has<<31}
-                const bool has_val = (kd.w >> 31) != 0;
-                const u32 kn = kd.w & 0x7FFFFFFFu;
+                u32 kd[8];                                              // {token, child, first_kid, nk_flags, val, val_lo, val_hi, pad}
+                ld256(v.kids + o_kb + (e - o_exc), kd);
+                const bool has_val = ((kd[3] >> 28) & 8u) != 0;
+                const u32 kn = kd[3] & RNK_MASK;
                 if (o_mode == 1) {
                     if (o_pos + 1 == o_L) em = has_val;                 // filter ends here: the child's own value
                     else { em = o_nh && has_val; pu = kn > 0; }         // `.../+/#` parent match; descend only if the child has branches
-                    ni = RItem{o_q, kd.y, o_pos + 1, 0u};
+                    ni = RItem{o_q, o_pos + 1, kd[1], kd[2], kd[3], kd[4], kd[5], kd[6]};
                 } else {                                                // '#' one level at a time (a literal "#" child hides below)
                     em = has_val; pu = kn > 0;
-                    ni = RItem{o_q, kd.y, o_pos, 0u};
+                    ni = RItem{o_q, o_pos, kd[1], kd[2], kd[3], kd[4], kd[5], kd[6]};
                 }
-                d = RDesc{o_q, kd.z, 1u, 0u};
+                d = RDesc{o_q, kd[4], 1u, 0u};
             }
             if (em) atomicAdd(p.qtotal + d.q, 1u);
-            warp_append(em, d, p.descs, p.n_desc, p.cap_desc, p.err, 2u, lane, lt);
-            warp_append(pu, ni, out, n_out, p.cap_items, p.err, 1u, lane, lt);
+            warp_append(em, d, p.descs, p.n_desc, p.cap_desc, sq, p.err, 2u, lane, lt);
+            warp_append(pu, ni, out, n_out, p.cap_items, sq, p.err, 1u, lane, lt);
         }
     }
 }
@@ -198,10 +220,11 @@ k_retain_expand(const RDesc* __restrict__ descs, const u32* __restrict__ n_desc_
                 const u32* __restrict__ qbase, u32* __restrict__ qcur, u32* __restrict__ out, unsigned long long cap_ids) {
     const u32 lane = threadIdx.x & 31;
     const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const u32 nd = min(*n_desc_p, cap_desc);
+    __shared__ u32 s_pre[RQ + 1];
+    const u32 nd = queue_prefix(n_desc_p, cap_desc, s_pre);
     for (u32 base = gwarp * 32; base < nd; base += nwarps * 32) {
         const u32 i = base + lane;
-        RDesc d = i < nd ? descs[i] : RDesc{0, 0, 0, 0};
+        RDesc d = i < nd ? descs[queue_locate(s_pre, i, cap_desc)] : RDesc{0, 0, 0, 0};
         const u32 ni = d.cnt;
         const u32 dst = ni ? qbase[d.q] + atomicAdd(qcur + d.q, ni) : 0u;
         u32 sc = ni;

@@ -119,10 +119,7 @@ void RetainTreeHost::flatten() {
             u32 child_dev = static_cast<u32>(rnodes.size());
             RKid& k = rkids[rnodes[f.dev].first_kid + j];
             k.token = f.order[j].first;
-            k.child = child_dev;
-            const HN& ch = nodes_[child_host];
-            k.val = ch.has_val ? ch.val : RVAL_NONE;
-            k.nkids = static_cast<u32>(ch.kids.size()) | (ch.has_val ? 0x80000000u : 0u);
+            k.child = child_dev;                    // the child's record is copied in below, once its subtree is complete
             open(child_host, f.depth + 1);          // invalidates `f`
         } else {
             RNode& r = rnodes[f.dev];
@@ -136,10 +133,15 @@ void RetainTreeHost::flatten() {
             if (root && root_plain_kids == nodes_[0].kids.size()) root_plain_val_hi = static_cast<u32>(rvals.size());
         }
     }
+    // child entries carry the complete record of the child (flags and value ranges are final only now)
+    for (RKid& k : rkids) {
+        const RNode& c = rnodes[k.child];
+        k.first_kid = c.first_kid; k.nk_flags = c.nkids | (c.flags << 28); k.val = c.val; k.val_lo = c.val_lo; k.val_hi = c.val_hi; k.pad = 0;
+    }
     // exact-step hash table, load <= 0.25
     size_t cap = 1024;
     while (cap < rkids.size() * 4) cap <<= 1;
-    redges.assign(cap, REdge{0, 0, 0, 0});
+    redges.assign(cap, REdge{0, 0, 0, 0, 0, 0, 0, 0});
     const u32 mask = static_cast<u32>(cap - 1);
     for (u32 n = 0; n < rnodes.size(); ++n) {
         const RNode& r = rnodes[n];
@@ -147,7 +149,7 @@ void RetainTreeHost::flatten() {
             const RKid& k = rkids[r.first_kid + j];
             u32 i = redge_hash(n, k.token) & mask;
             while (redges[i].child != 0) i = (i + 1) & mask;
-            redges[i] = REdge{n, k.token, k.child, 0};
+            redges[i] = REdge{n, k.token, k.child, k.first_kid, k.nk_flags, k.val, k.val_lo, k.val_hi};
         }
     }
     dirty = false;

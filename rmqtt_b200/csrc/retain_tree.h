@@ -6,9 +6,9 @@
 //
 //   rnodes : nodes in DFS PRE-ORDER, so the subtree of node n is the index range [n, sub_end(n)) and the
 //            values below a node are ONE contiguous range of `rvals` -> a '#' match is a range copy
-//   rkids  : per node, its children as a contiguous block {token, child, child value, child #kids}
-//            -> a '+' match is a coalesced scan of one block
-//   redges : open-addressing hash (parent, token) -> child for the exact-level steps
+//   rkids  : per node, its children as a contiguous block of 32-byte entries {token, child, child's record}
+//            -> a '+' match is a coalesced scan of one block and yields complete work items
+//   redges : open-addressing hash (parent, token) -> child + the child's record for the exact-level steps
 //   rvals  : the values of all valued nodes, in pre-order
 #pragma once
 #include <vector>
@@ -32,15 +32,19 @@ struct alignas(32) RNode {
     u32 sub_end;
     u32 pad;
 };
-struct alignas(16) RKid { u32 token, child, val, nkids; };
-struct alignas(16) REdge { u32 parent, token, child, pad; };   // child == 0: empty (root is node 0)
+// A node's record as the walk needs it: {first_kid, nk_flags, val, val_lo, val_hi} where nk_flags = #kids (28 bits) |
+// flags << 28 (RF_* and 8 = has value).  It travels WITH the reference to the node — inside the parent's child
+// block entry and inside the (parent, token) hash slot — so visiting a node costs no extra memory access.
+constexpr u32 RNK_MASK = 0x0FFFFFFFu;
+struct alignas(32) RKid { u32 token, child, first_kid, nk_flags, val, val_lo, val_hi, pad; };
+struct alignas(32) REdge { u32 parent, token, child, first_kid, nk_flags, val, val_lo, val_hi; };   // child == 0: empty (root is node 0)
 
 struct RetainView {
-    const RNode* nodes;
     const RKid* kids;
     const REdge* edges;
     const u32* vals;
     u32 edge_mask;
+    u32 root_first_kid, root_nk_flags;
     u32 root_plain_kids;     // root children whose level does not start with '$' (ordered first)
     u32 root_plain_val_hi;   // rvals[0 .. root_plain_val_hi) = values below those children
     u32 max_depth;

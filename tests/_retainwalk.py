@@ -6,6 +6,9 @@ RF_LIT_PLUS, RF_LIT_HASH, RF_SUB_LIT_HASH, RF_HAS_VAL = 1, 2, 4, 8
 
 
 class RetainTables:
+    """Items carry the node's record {node, first_kid, nk_flags, val, val_lo, val_hi} exactly like the kernel's RItem;
+    records come from the child-block entries (8 words: token, child, first_kid, nk_flags, val, val_lo, val_hi, pad)."""
+
     def __init__(self, t):
         self.T = Tables(t)                      # shared dictionary
         self.nodes, self.kids, self.vals = t["rnodes"], t["rkids"], t["rvals"]
@@ -13,10 +16,11 @@ class RetainTables:
         for n in range(len(self.nodes)):
             fk, nk = int(self.nodes[n, 0]), int(self.nodes[n, 1])
             for j in range(nk):
-                self.edges[(n, int(self.kids[fk + j, 0]))] = int(self.kids[fk + j, 1])
-        # root bookkeeping as flatten() computes it
-        fk, nk = int(self.nodes[0, 0]), int(self.nodes[0, 1])
-        self.dollar = set()
+                k = self.kids[fk + j]
+                self.edges[(n, int(k[0]))] = tuple(int(x) for x in k[1:7])      # (child, first_kid, nk_flags, val, val_lo, val_hi)
+                c = self.nodes[int(k[1])]
+                # the copied record must equal the child's own record
+                assert (int(k[2]), int(k[3]) & 0x0FFFFFFF, int(k[3]) >> 28, int(k[5]), int(k[6])) == (int(c[0]), int(c[1]), int(c[5]), int(c[3]), int(c[4]))
 
     def set_root_plain(self, plain_kids, plain_val_hi):
         self.root_plain_kids, self.root_plain_val_hi = plain_kids, plain_val_hi
@@ -28,11 +32,12 @@ class RetainTables:
         toks, _ = tk
         L = len(toks)
         out = []
-        frontier = [(0, 0)]
+        root = (0, int(self.nodes[0, 0]), int(self.nodes[0, 1]) | (int(self.nodes[0, 5]) << 28), 0, 0, self.root_plain_val_hi)
+        frontier = [(root, 0)]
         while frontier:
             nxt = []
-            for node, pos in frontier:
-                fk, nk, val, vlo, vhi, flags = (int(x) for x in self.nodes[node, :6])
+            for (node, fk, nkf, val, vlo, vhi), pos in frontier:
+                nk, flags = nkf & 0x0FFFFFFF, nkf >> 28
                 if nk == 0 or pos == L:
                     if pos == L and flags & RF_HAS_VAL:
                         out.append(val)
@@ -40,34 +45,34 @@ class RetainTables:
                 tok = toks[pos]
                 next_hash = pos + 1 < L and toks[pos + 1] == TOK_HASH
                 exact_try = tok >= TOK_BLANK or (tok == TOK_PLUS and flags & RF_LIT_PLUS) or (tok == TOK_HASH and flags & RF_LIT_HASH)
-                child = self.edges.get((node, tok), 0) if exact_try else 0
-                root = node == 0
+                child = self.edges.get((node, tok)) if exact_try else None
+                is_root = node == 0
                 if child:
-                    if next_hash and int(self.nodes[child, 5]) & RF_HAS_VAL:
-                        out.append(int(self.nodes[child, 2]))
+                    if next_hash and (child[2] >> 28) & RF_HAS_VAL:
+                        out.append(child[3])
                     nxt.append((child, pos + 1))
                 elif tok == TOK_PLUS or (tok == TOK_HASH and flags & RF_SUB_LIT_HASH):
-                    n = self.root_plain_kids if root else nk
+                    n = self.root_plain_kids if is_root else nk
                     for j in range(n):
-                        ktok, kchild, kval, knk = (int(x) for x in self.kids[fk + j])
-                        has_val, kn = knk >> 31, knk & 0x7FFFFFFF
+                        k = tuple(int(x) for x in self.kids[fk + j][1:7])
+                        has_val, kn = (k[2] >> 28) & RF_HAS_VAL, k[2] & 0x0FFFFFFF
                         if tok == TOK_PLUS:
                             if pos + 1 == L:
                                 if has_val:
-                                    out.append(kval)
+                                    out.append(k[3])
                             else:
                                 if next_hash and has_val:
-                                    out.append(kval)
+                                    out.append(k[3])
                                 if kn:
-                                    nxt.append((kchild, pos + 1))
+                                    nxt.append((k, pos + 1))
                         else:
                             if has_val:
-                                out.append(kval)
+                                out.append(k[3])
                             if kn:
-                                nxt.append((kchild, pos))
+                                nxt.append((k, pos))
                 elif tok == TOK_HASH:
                     lo = vlo + (1 if flags & RF_HAS_VAL else 0)
-                    hi = self.root_plain_val_hi if root else vhi
+                    hi = self.root_plain_val_hi if is_root else vhi
                     out.extend(int(x) for x in self.vals[lo:hi])
             frontier = nxt
         return sorted(out)

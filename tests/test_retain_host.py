@@ -22,7 +22,7 @@ def _tables(eng):
     plain = 0
     for j in range(nk):
         child = int(kids[fk + j, 1])
-        # `$` children are ordered last: the first child whose token string starts with '$' ends the plain block
+        # placeholder; _plain_split() sets the real values
         plain += 1
     R.set_root_plain(plain, int(nodes[0, 4]))
     return R, t
