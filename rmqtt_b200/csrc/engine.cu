@@ -103,6 +103,15 @@ struct gm_engine {
     u32 r_cap_items = 1u << 22, r_cap_desc = 1u << 22;   // totals over the RQ slices of each queue
     u64 launches = 0;
     bool k2_attr_set = false;
+    // tuning / diagnostics knobs, read from the environment once at creation
+    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; } knobs;
+    void read_knobs() {
+        if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { knobs.site_bits = a; knobs.sub_bits = b; } }
+        if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
+        if (const char* ev = getenv("GM_K2_CTAS")) knobs.k2_ctas = atoi(ev);
+        if (const char* ev = getenv("GM_DIAG_MAXDEPTH")) knobs.diag_flags |= (static_cast<u32>(atoi(ev)) & 0xFu) << MP_DIAG_DEPTH_SHIFT;   // timing diagnostics: WRONG results
+        if (getenv("GM_DIAG_NO_PUBLISH")) knobs.diag_flags |= MP_DIAG_NO_PUBLISH;
+    }
 
     explicit gm_engine(u32 max_levels) : trie(max_levels) {}
 
@@ -241,23 +250,20 @@ struct gm_engine {
         CUDA_TRY(d_ctrl.ensure(sizeof(Ctrl)));
         // locality pass scratch: bkey[n], perm[n]; hist + cursor [NBUCKETS] each
         CUDA_TRY(d_sort.ensure(static_cast<size_t>(n32) * 11 * sizeof(u32) + 64));
-        u32 site_bits = 14, sub_bits = 0;
-        if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { site_bits = a; sub_bits = b; } }   // tuning knob
+        const u32 site_bits = knobs.site_bits, sub_bits = knobs.sub_bits;
         const u32 NBUCKETS = 1u << (site_bits + sub_bits);
         CUDA_TRY(d_hist.ensure(2 * static_cast<size_t>(NBUCKETS) * sizeof(u32)));
         u32* bkey = d_sort.as<u32>();
         u32* perm = bkey + n32;
         u32* meta_sorted = perm + n32;
         u32* tok8_sorted = meta_sorted + n32 + ((8 - (3 * static_cast<size_t>(n32)) % 8) % 8);   // 32-byte aligned rows
-        bool sorted_rows = true;
-        if (const char* ev = getenv("GM_SORTED_ROWS")) sorted_rows = atoi(ev) != 0;   // tuning knob
+        const bool sorted_rows = knobs.sorted_rows;
         u32* hist = d_hist.as<u32>();
         u32* bcursor = hist + NBUCKETS;
         const int k3_blocks = num_sms * 4;
         const u32 stack_cap = 32u * (trie.max_depth + 2u) + 64u;
         CUDA_TRY(d_gstack.ensure(static_cast<size_t>(k3_blocks) * 8 * stack_cap * sizeof(u64)));
-        int k2_ctas = K2_CTAS_PER_SM;
-        if (const char* ev = getenv("GM_K2_CTAS")) { int v = atoi(ev); if (v >= 1 && v <= K2_CTAS_PER_SM) k2_ctas = v; }   // tuning knob
+        const int k2_ctas = (knobs.k2_ctas >= 1 && knobs.k2_ctas <= K2_CTAS_PER_SM) ? knobs.k2_ctas : K2_CTAS_PER_SM;
         const int k2_grid = num_sms * k2_ctas;
         CUDA_TRY(d_gpool.ensure(static_cast<size_t>(k2_grid) * K2_THREADS * K2_POOL_ROWS * sizeof(Desc)));
         CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
@@ -285,9 +291,7 @@ struct gm_engine {
         mp.cursor = &ctrl->cursor; mp.slow_list = d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
         mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
-        mp.flags = sorted_rows ? MP_SORTED_ROWS : 0u;
-        if (const char* ev = getenv("GM_DIAG_MAXDEPTH")) mp.flags |= (static_cast<u32>(atoi(ev)) & 0xFu) << MP_DIAG_DEPTH_SHIFT;   // timing diagnostics, wrong results
-        if (getenv("GM_DIAG_NO_PUBLISH")) mp.flags |= MP_DIAG_NO_PUBLISH;
+        mp.flags = (sorted_rows ? MP_SORTED_ROWS : 0u) | knobs.diag_flags;
         constexpr size_t k2_smem = k2_smem_bytes<K2_FAST_L, K2_THREADS>();
         if (!k2_attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
@@ -409,6 +413,7 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     gm_engine* eng = new gm_engine(c.max_levels ? c.max_levels : 128u);
     eng->device = dev;
     eng->flags = c.flags;
+    eng->read_knobs();
     cudaDeviceProp prop{};
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     eng->num_sms = prop.multiProcessorCount;

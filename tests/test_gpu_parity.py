@@ -343,3 +343,35 @@ def test_compact_on_device_keeps_parity():
     _assert_same(eng.match_batch(tb, to), tree.match_batch(tb, to))
     eng.add("q/+/r", 9); tree.insert("q/+/r", 9)
     assert eng.matches("q/x/r") == tree.matches("q/x/r")
+
+
+def test_tokenizer_fuzz_against_topic_from_str():
+    """SWAR tokeniser vs the oracle's Topic::from_str on random byte soup: validity, level count, `$` flag."""
+    rng = random.Random(2024)
+    alphabet = [b"/", b"/", b"+", b"#", b"$", b"a", b"b", b"cd", b"\xc3\xa9", b"\x7f", b" ", b"0", b"xyz", b"-", b"\xf0\x9f\x98\x80"]
+    topics = []
+    for _ in range(20000):
+        n = rng.randint(0, 14)
+        topics.append(b"".join(rng.choice(alphabet) for _ in range(n)))
+    topics += [b"a" * 26 + b"/x", b"a" * 27 + b"/x", b"a" * 28 + b"/x", b"a" * 29 + b"+", b"/" * 40, b"a/" * 30 + b"#", b"$" * 3]
+    eng = Engine()
+    for i, f in enumerate(["a/b", "cd/+", "$/#", "a" * 27, "a" * 28]):
+        eng.add(f, i)
+    toks, meta = eng.tokenize(topics, max_tok=8)
+    for i, t in enumerate(topics):
+        want = orc.topic_parse(t)
+        inv = bool(meta[i] >> 31)
+        assert inv == (want is None), t
+        if want is not None:
+            assert int(meta[i] & 0xFFFFFF) == len(t.split(b"/")), t
+            assert bool((meta[i] >> 30) & 1) == (want[0] == "Metadata"), t
+            for l, kind in enumerate(want[:8]):
+                tk = int(toks[l, i])
+                if kind == "Single":
+                    assert tk == 1
+                elif kind == "Multi":
+                    assert tk == 2
+                elif kind == "Blank":
+                    assert tk == 3
+                else:
+                    assert tk == 0 or tk >= 4
