@@ -17,6 +17,7 @@ tmp = Path(tempfile.mkdtemp())
 subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "rmqtt_b200" / "libgpumqtt.so")], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 dis = subprocess.run(["nvdisasm", "-g", "-c", str(tmp / "engine.sm_100a.cubin")], capture_output=True, text=True).stdout
 addr2line, cur, infn = {}, None, False
+SRC = {}
 for ln in dis.splitlines():
     m = re.match(r"^\.text\.(\S+):", ln)
     if m:
@@ -26,7 +27,7 @@ for ln in dis.splitlines():
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
-        cur = int(m.group(2)) if m.group(1).endswith("kernels.cuh") else -int(m.group(2))
+        cur = (Path(m.group(1)).name, int(m.group(2)))
         continue
     m = re.search(r"/\*([0-9a-f]{4,})\*/\s+\S", ln)
     if m and cur is not None:
@@ -46,14 +47,19 @@ for r in rows[2:]:
         continue
     if base is None:
         base = a
-    line = addr2line.get(a - base, 0)
+    line = addr2line.get(a - base, ("?", 0))
     per[line][0] += int(r[ii] or 0)
     per[line][1] += int(r[si] or 0)
     per[line][2] += int(r[lsb] or 0)
-src = (ROOT / "rmqtt_b200" / "csrc" / "kernels.cuh").read_text().splitlines()
+def text_of(key):
+    name, ln = key
+    if name not in SRC:
+        cand = list((ROOT / "rmqtt_b200" / "csrc").glob(name))
+        SRC[name] = cand[0].read_text().splitlines() if cand else None
+    src = SRC[name]
+    return src[ln - 1].strip()[:100] if src and 0 < ln <= len(src) else ""
 ti, ts = sum(v[0] for v in per.values()), sum(v[1] for v in per.values())
 print(f"total warp-instructions {ti}, stall samples {ts}")
 print("  inst%  smp%  long_sb%  line  source")
 for line, v in sorted(per.items(), key=lambda kv: -(kv[1][0] / max(ti, 1) + kv[1][1] / max(ts, 1)))[:top]:
-    text = src[line - 1].strip()[:100] if 0 < line <= len(src) else f"<other file line {-line}>"
-    print(f"{100 * v[0] / ti:6.1f} {100 * v[1] / ts:6.1f} {100 * v[2] / max(ts, 1):6.1f}  {line:5d}  {text}")
+    print(f"{100 * v[0] / ti:6.1f} {100 * v[1] / ts:6.1f} {100 * v[2] / max(ts, 1):6.1f}  {line[0]}:{line[1]:<5d} {text_of(line)}")
