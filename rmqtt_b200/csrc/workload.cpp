@@ -6,6 +6,7 @@
 //   dictionary is realistically large (C3: ~1.05 M distinct level strings).
 //
 // Every item i draws from its own splitmix64 stream seeded by (seed, i): generation is order-free.
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -204,6 +205,27 @@ uint64_t wl_gen_topics(const wl_params* w, uint64_t first, uint64_t n, double fr
         else if (nreg) x = pick_region_restricted(p, g, regions, nreg);
         else x = g.below(space(p));
         o = put_filter(o, decode(p, x), 0, 6);
+    }
+    offs[n] = static_cast<uint32_t>(o - blob);
+    return static_cast<uint64_t>(o - blob);
+}
+
+// Publish topics with a Zipf(s = 1) popularity over DEVICES (secondary workload of SURVEY §8d): device rank k is
+// drawn with P(rank <= k) ~ ln(k+1)/ln(N+1) (continuous approximation of the harmonic CDF), ranks are mapped to
+// device ids by a fixed permutation; sensor / metric / channel stay uniform.
+uint64_t wl_gen_topics_zipf(const wl_params* w, uint64_t first, uint64_t n, uint64_t stream, char* blob, uint32_t* offs) {
+    Params p = cvt(w);
+    char* o = blob;
+    const uint64_t ndev = 1ull * p.R * p.S * p.D, per_dev = 1ull * p.K * p.M * p.F;
+    const double lnN = std::log(static_cast<double>(ndev) + 1.0);
+    for (uint64_t k = 0; k < n; ++k) {
+        uint64_t i = first + k;
+        offs[k] = static_cast<uint32_t>(o - blob);
+        Rng g(p.seed, i, 40 + stream);
+        uint64_t rank = static_cast<uint64_t>(std::exp(g.uni() * lnN)) - 1;
+        if (rank >= ndev) rank = ndev - 1;
+        const uint64_t dev = permute(rank, ndev, p.seed ^ 0x5A17);
+        o = put_filter(o, decode(p, dev * per_dev + g.below(per_dev)), 0, 6);
     }
     offs[n] = static_cast<uint32_t>(o - blob);
     return static_cast<uint64_t>(o - blob);

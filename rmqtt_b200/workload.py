@@ -36,6 +36,7 @@ def _wl():
         L.wl_gen_subs.restype, L.wl_gen_subs.argtypes = u64, [P, u64, u64, vp, vp]
         L.wl_gen_subs_sharded.restype, L.wl_gen_subs_sharded.argtypes = u64, [P, u64, u64, vp, vp, vp, vp, C.POINTER(u64)]
         L.wl_gen_topics.restype, L.wl_gen_topics.argtypes = u64, [P, u64, u64, C.c_double, u64, vp, u32, u64, vp, vp]
+        L.wl_gen_topics_zipf.restype, L.wl_gen_topics_zipf.argtypes = u64, [P, u64, u64, u64, vp, vp]
         L.wl_gen_retained.restype, L.wl_gen_retained.argtypes = u64, [P, u64, u64, vp, vp]
         L.wl_gen_retain_filters.restype, L.wl_gen_retain_filters.argtypes = u64, [P, u64, u64, vp, vp]
         L.wl_region_name.restype, L.wl_region_name.argtypes = u32, [u32, vp]
@@ -126,6 +127,15 @@ def gen_topics(cfg: Config, n: int | None = None, first: int = 0, regions=None, 
     reg = np.ascontiguousarray(regions, dtype=np.uint32) if regions is not None and len(regions) else None
     used = _wl().wl_gen_topics(C.byref(p), first, n, cfg.frac_from_subs, cfg.n_subs if cfg.frac_from_subs > 0 else 0,
                                _vp(reg) if reg is not None else None, len(reg) if reg is not None else 0, stream, _vp(blob), _vp(offs))
+    return blob[:used].copy(), offs
+
+
+def gen_topics_zipf(cfg: Config, n: int | None = None, first: int = 0, stream: int = 0):
+    """Publish topics whose DEVICE follows a Zipf(1.0) popularity (secondary workload)."""
+    n = cfg.n_topics if n is None else int(n)
+    blob, offs = _alloc(n)
+    p = cfg.params()
+    used = _wl().wl_gen_topics_zipf(C.byref(p), first, n, stream, _vp(blob), _vp(offs))
     return blob[:used].copy(), offs
 
 

@@ -39,3 +39,14 @@ def test_region_restriction():
     b, o = wl.gen_topics(wl.C3, 2000, regions=[3, 9])
     names = {t.split(b"/")[0] for t in wl.unpack(b, o)}
     assert names == {wl.region_name(3), wl.region_name(9)}
+
+
+def test_zipf_over_devices_is_skewed_and_deterministic():
+    b, o = wl.gen_topics_zipf(wl.C3, 50_000)
+    t = wl.unpack(b, o)
+    assert t == wl.unpack(*wl.gen_topics_zipf(wl.C3, 50_000))
+    from collections import Counter
+    c = Counter(x.split(b"/")[2] for x in t)
+    top = c.most_common(1)[0][1]
+    assert top > 0.02 * len(t) and len(c) > 5_000          # one hot device, a long tail
+    assert all(x.count(b"/") == 5 for x in t)

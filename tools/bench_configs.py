@@ -21,9 +21,9 @@ stream = torch.cuda.current_stream().cuda_stream
 threads = orc.hardware_threads()
 
 
-def publish_config(cfg, reps=20):
+def publish_config(cfg, reps=20, zipf=False):
     sb, so, sv = wl.gen_subs(cfg)
-    tb, to = wl.gen_topics(cfg)
+    tb, to = wl.gen_topics_zipf(cfg) if zipf else wl.gen_topics(cfg)
     n = len(to) - 1
     eng = Engine(filters_hint=len(sv))
     t0 = time.time(); eng.bulk_load(sb, so, sv); eng.flush(); build = time.time() - t0
@@ -46,7 +46,7 @@ def publish_config(cfg, reps=20):
     parity = bool((counts == o1["counts"]).all())
     alg = w["bytes"] + 8 * n + 16 * w["levels"] + 16 * w["visited"] + 16 * w["probed"] + 8 * w["filters"] + 4 * w["ids"] + 8 * n
     ms = float(k.sum())
-    return {"config": cfg.name, "subs": cfg.n_subs, "topics": n, "gpu_ms": {"tokenize": float(k[0]), "match": float(k[1]), "deferred": float(k[2])},
+    return {"config": cfg.name + ("-zipf" if zipf else ""), "subs": cfg.n_subs, "topics": n, "gpu_ms": {"tokenize": float(k[0]), "match": float(k[1]), "deferred": float(k[2])},
             "gpu_topics_per_s": n / (ms * 1e-3), "pairs_per_s": w["ids"] / (ms * 1e-3), "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
             "cpu_1thr_topics_per_s": n / o1["seconds"], f"cpu_{threads}thr_topics_per_s": n / oN["seconds"], "cpu_kind": "oracle TopicTree::matches restatement",
             "ids_per_topic": w["ids"] / n, "visited_per_topic": w["visited"] / n, "count_parity": parity, "build_s": round(build, 2)}
@@ -92,6 +92,7 @@ def retain_config(cfg, reps=10):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["C1", "C2", "C4"]
     for name in which:
-        cfg = wl.CONFIGS[name]
-        r = retain_config(cfg) if name == "C4" else publish_config(cfg)
+        zipf = name.endswith("Z")                   # e.g. C3Z: C3 subscriptions, Zipf(1.0)-over-devices publish batch
+        cfg = wl.CONFIGS[name.rstrip("Z")]
+        r = retain_config(cfg) if name == "C4" else publish_config(cfg, zipf=zipf)
         print(json.dumps(r), flush=True)
