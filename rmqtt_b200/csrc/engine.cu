@@ -92,8 +92,8 @@ struct gm_engine {
     u64 ring_n = 0;
     bool match_recorded = false;
     // device tables
-    DevBuf d_edges, d_plus, d_ranges, d_values, d_dict, d_pool, d_cfilter;
-    size_t up_plus = 0, up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
+    DevBuf d_edges, d_ranges, d_values, d_dict, d_pool, d_cfilter;
+    size_t up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
     // scratch
     DevBuf d_tok, d_tok8, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data, d_sort, d_hist;
     DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
@@ -104,11 +104,12 @@ struct gm_engine {
     u64 launches = 0;
     bool k2_attr_set = false;
     // tuning / diagnostics knobs, read from the environment once at creation
-    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; } knobs;
+    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; } knobs;
     void read_knobs() {
         if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { knobs.site_bits = a; knobs.sub_bits = b; } }
         if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
         if (const char* ev = getenv("GM_K2_CTAS")) knobs.k2_ctas = atoi(ev);
+        if (const char* ev = getenv("GM_TILE_CHUNK")) { int v = atoi(ev); if (v >= 1 && v <= 1024) knobs.tile_chunk = static_cast<u32>(v); }
         if (const char* ev = getenv("GM_DIAG_MAXDEPTH")) knobs.diag_flags |= (static_cast<u32>(atoi(ev)) & 0xFu) << MP_DIAG_DEPTH_SHIFT;   // timing diagnostics: WRONG results
         if (getenv("GM_DIAG_NO_PUBLISH")) knobs.diag_flags |= MP_DIAG_NO_PUBLISH;
     }
@@ -117,10 +118,11 @@ struct gm_engine {
 
     TrieView view() const {
         TrieView v{};
-        v.edges = d_edges.as<EdgeSlot>(); v.plus = d_plus.as<PlusRec>(); v.ranges = d_ranges.as<Range>();
+        v.edges = d_edges.as<EdgeSlot>(); v.ranges = d_ranges.as<Range>();
         v.values = d_values.as<u32>(); v.dict = d_dict.as<DictSlot>(); v.pool = d_pool.as<u8>();
         v.cfilter = d_cfilter.as<u32>(); v.cfilter_mask = static_cast<u32>(trie.cfilter.size() - 1);
         v.edge_mask = static_cast<u32>(trie.edges.size() - 1);
+        v.win_mask = trie.win_mask(); v.win_shift = trie.win_shift(); v.nwin_mask = trie.nwin_mask();
         v.dict_mask = static_cast<u32>(trie.dict.size() - 1);
         v.root_plus = trie.root_plus; v.root_hash_ref = trie.root_hash_ref; v.root_hash_cnt = trie.root_hash_cnt; v.root_mask = trie.root_mask;
         v.max_depth = trie.max_depth;
@@ -221,7 +223,6 @@ struct gm_engine {
         int st;
         if ((st = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return st;
         if ((st = upload_table(d_dict, trie.dict, trie.full_dict, trie.dirty_dict, up_dict_slots)) != GM_OK) return st;
-        if ((st = upload_appendable(d_plus, trie.plus, up_plus, &trie.dirty_plus)) != GM_OK) return st;
         if ((st = upload_appendable<Range>(d_ranges, trie.ranges, up_ranges, nullptr)) != GM_OK) return st;
         if ((st = upload_appendable<u32>(d_values, trie.values, up_values, nullptr)) != GM_OK) return st;
         if ((st = upload_appendable<u8>(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return st;
@@ -292,6 +293,7 @@ struct gm_engine {
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
         mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
         mp.flags = (sorted_rows ? MP_SORTED_ROWS : 0u) | knobs.diag_flags;
+        mp.tile_chunk = knobs.tile_chunk;
         constexpr size_t k2_smem = k2_smem_bytes<K2_FAST_L, K2_THREADS>();
         if (!k2_attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
@@ -440,7 +442,7 @@ void gm_destroy(gm_engine* e) {
     if (e->flags & GM_FLAG_HOST_ONLY) { delete e; return; }
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->d_tok8, &e->d_cfilter, &e->d_edges, &e->d_plus, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
+    for (DevBuf* b : {&e->d_tok8, &e->d_cfilter, &e->d_edges, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
                       &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_gpool, &e->d_sort, &e->d_hist, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
                       &e->d_spans, &e->d_ids, &e->d_status, &e->d_rnodes, &e->d_rkids, &e->d_redges, &e->d_rvals, &e->d_rfront[0],
                       &e->d_rfront[1], &e->d_rdescs, &e->d_rctl, &e->d_rq})
@@ -505,7 +507,7 @@ int32_t gm_compact(gm_engine* e) {
         return GM_ERR_INVALID_ARG;
     }
     e->trie.compact();
-    e->up_plus = e->up_ranges = e->up_values = e->up_pool = 0;
+    e->up_ranges = e->up_values = e->up_pool = 0;
     e->up_edges_slots = e->up_dict_slots = 0;
     return (e->flags & GM_FLAG_HOST_ONLY) ? GM_OK : e->flush_locked();
 }
@@ -807,9 +809,9 @@ int32_t gm_get_stats(gm_engine* e, gm_stats* out) {
     out->values = t.values_size(); out->nodes = t.nodes_size(); out->device_nodes = t.node_count() - 1;
     out->edges = t.edge_count(); out->edge_slots = t.edges.size();
     out->dict_entries = t.dict_count(); out->dict_slots = t.dict.size();
-    out->plus_nodes = t.plus.size() - 1;
+    out->plus_nodes = t.plus_count();
     out->value_words = t.values.size(); out->garbage_value_words = t.garbage_values;
-    out->device_bytes = e->d_edges.cap + e->d_plus.cap + e->d_ranges.cap + e->d_values.cap + e->d_dict.cap + e->d_pool.cap;
+    out->device_bytes = e->d_edges.cap + e->d_ranges.cap + e->d_values.cap + e->d_dict.cap + e->d_pool.cap;
     out->max_depth = t.max_depth;
     out->pending = (t.any_dirty() || e->rtree.dirty) ? 1 : 0;
     out->retained_values = e->rtree.values_size(); out->retained_nodes = e->rtree.nodes_size();
@@ -841,21 +843,33 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
     std::lock_guard<std::mutex> g(e->mu);
     e->trie.sync();
     const HostTrie& t = e->trie;
-    static thread_local uint32_t root[5];
+    static thread_local uint32_t root[8];
     switch (which) {
         case 0: *ptr = t.edges.data(); *count = t.edges.size(); break;
-        case 1: *ptr = t.plus.data(); *count = t.plus.size(); break;
         case 2: *ptr = t.ranges.data(); *count = t.ranges.size(); break;
         case 3: *ptr = t.values.data(); *count = t.values.size(); break;
         case 4: *ptr = t.dict.data(); *count = t.dict.size(); break;
         case 5: *ptr = t.pool.data(); *count = t.pool.size(); break;
-        case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; root[4] = t.root_hash_cnt; *ptr = root; *count = 5; break;
+        case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; root[4] = t.root_hash_cnt;
+                root[5] = t.win_mask(); root[6] = t.win_shift(); root[7] = t.nwin_mask(); *ptr = root; *count = 8; break;
         case 12: *ptr = t.cfilter.data(); *count = t.cfilter.size(); break;
         case 7: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rnodes.data(); *count = e->rtree.rnodes.size(); break;
         case 8: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rkids.data(); *count = e->rtree.rkids.size(); break;
         case 9: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rvals.data(); *count = e->rtree.rvals.size(); break;
         default: return GM_ERR_INVALID_ARG;
     }
+    return GM_OK;
+}
+
+int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value) {
+    if (!e || !name) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    const std::string k(name);
+    if (k == "tile_chunk" && value >= 1 && value <= 1024) e->knobs.tile_chunk = static_cast<u32>(value);
+    else if (k == "k2_ctas" && value >= 0 && value <= 8) e->knobs.k2_ctas = static_cast<int>(value);
+    else if (k == "sorted_rows") e->knobs.sorted_rows = value != 0;
+    else if (k == "diag_flags") e->knobs.diag_flags = static_cast<u32>(value);
+    else return GM_ERR_INVALID_ARG;
     return GM_OK;
 }
 

@@ -38,11 +38,15 @@ inline bool dict_slot_equals(const DictSlot& d, const u8* pool, const char* s, u
 HostTrie::HostTrie(u32 max_levels) : max_levels_(max_levels) {
     edges.assign(1u << 10, EdgeSlot{});
     dict.assign(1u << 10, DictSlot{});
-    plus.assign(1, PlusRec{});
     ranges.assign(1, Range{0, 0});
     cfilter.assign(1u << 10, 0u);
     nodes_.emplace_back();   // root = node 0
     nodes_[0].alive = 1;
+    tag_count_.assign(WTAG_COUNT, 0);
+    // tuning / test knobs: cap on log2(#windows) (0 = one window = plain open addressing) and the smallest window
+    if (const char* ev = getenv("GM_EDGE_WINDOWS_LOG2")) { int v = atoi(ev); if (v >= 0 && v <= static_cast<int>(WIN_MAX_LOG2)) nwin_cap_log2_ = static_cast<u32>(v); }
+    if (const char* ev = getenv("GM_WIN_MIN_SLOTS_LOG2")) { int v = atoi(ev); if (v >= 3 && v <= 30) win_min_log2_ = static_cast<u32>(v); }
+    rehash_edges(edges.size());
 }
 
 void HostTrie::reserve(u64 n_filters) {
@@ -53,7 +57,8 @@ void HostTrie::reserve(u64 n_filters) {
     if (const char* ev = getenv("GM_EDGE_SLOTS_PER_FILTER")) { int v = atoi(ev); if (v >= 3 && v <= 64) per_filter = static_cast<u64>(v); }   // tuning knob
     u64 want_e = 1; while (want_e < n_filters * per_filter) want_e <<= 1;
     u64 want_d = 1; while (want_d < n_filters / 2 + 1024) want_d <<= 1;
-    while (edges.size() < want_e && edges.size() < (1ull << 31)) grow_edges();
+    want_e = std::min<u64>(want_e, 1ull << 31);
+    if (edges.size() < want_e) rehash_edges(static_cast<size_t>(want_e));
     while (dict.size() < want_d && dict.size() < (1ull << 31)) grow_dict();
     nodes_.reserve(nodes_.size() + n_filters * 3);
 }
@@ -126,46 +131,81 @@ void HostTrie::grow_dict() {
 
 // ------------------------------------------------------------------------------- edges
 u32 HostTrie::find_edge(u32 parent, u32 token) const {
-    u32 mask = static_cast<u32>(edges.size() - 1);
-    for (u32 i = edge_hash(parent, token) & mask;; i = (i + 1) & mask) {
+    const u32 wm = win_mask();
+    for (u32 i = edge_slot0(parent, token, nodes_[parent].wtag, wm, win_shift(), nwin_mask());; i = edge_next(i, wm)) {
         const EdgeSlot& e = edges[i];
         if (e.child == 0) return NOSLOT;
         if (e.parent == parent && e.token == token) return i;
     }
 }
 
-void HostTrie::grow_edges() {
+// Re-place every edge into a table of `new_size` slots cut into as many windows as the cap and the minimum
+// window size allow.  Tags stay; the effective window is tag & (nwin - 1).
+void HostTrie::rehash_edges(size_t new_size) {
     std::vector<EdgeSlot> old;
     old.swap(edges);
-    edges.assign(old.size() * 2, EdgeSlot{});
-    u32 mask = static_cast<u32>(edges.size() - 1);
+    edges.assign(new_size, EdgeSlot{});
+    u32 bits = 0; while ((size_t(1) << bits) < new_size) ++bits;
+    nwin_log2 = std::min(nwin_cap_log2_, bits > win_min_log2_ ? bits - win_min_log2_ : 0u);
+    win_count_.assign(size_t(1) << nwin_log2, 0);
+    const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
     for (const EdgeSlot& e : old) {
         if (e.child == 0) continue;
-        u32 i = edge_hash(e.parent, e.token) & mask;
-        while (edges[i].child != 0) i = (i + 1) & mask;
+        const u32 tag = nodes_[e.parent].wtag;
+        u32 i = edge_slot0(e.parent, e.token, tag, wm, ws, nm);
+        while (edges[i].child != 0) i = edge_next(i, wm);
         edges[i] = e;
         nodes_[e.child].edge_slot = i;
+        win_count_[tag & nm]++;
     }
     full_edges = true;
     dirty_edges.clear();
+    root_dirty = true;       // the geometry travels with the root record
+    for (u32 id = 0; id < nodes_.size(); ++id)      // records name their '+' child by slot: republish them
+        if (nodes_[id].plus_child && !nodes_[id].dirty) { nodes_[id].dirty = 1; dirty_nodes_.push_back(id); }
+}
+
+// Keeps every window (and so the table) at most half full.  A window that fills while the table as a whole is
+// sparse means one subtree outgrew it: double the window size (half as many windows); otherwise double the table
+// (same window size, twice as many windows up to the cap).
+void HostTrie::make_room(u32 wtag) {
+    for (;;) {
+        const u64 win_slots = edges.size() >> nwin_log2;
+        if ((edge_count_ + 1) * 2 <= edges.size() && (win_count_[wtag & nwin_mask()] + 1) * 2 <= win_slots) return;
+        if ((edge_count_ + 1) * 4 > edges.size() || nwin_log2 == 0) rehash_edges(edges.size() * 2);
+        else { win_min_log2_ = win_shift() + 1; rehash_edges(edges.size()); }
+    }
+}
+
+u32 HostTrie::pick_tag() const {
+    u32 best = 1;                                    // tag 0 = the hot window of the top two levels
+    for (u32 t = 2; t < WTAG_COUNT; ++t) if (tag_count_[t] < tag_count_[best]) best = t;
+    return best;
 }
 
 u32 HostTrie::add_edge(u32 parent, u32 token) {
-    if ((edge_count_ + 1) * 2 > edges.size()) grow_edges();
+    const u32 ptag = nodes_[parent].wtag;
+    make_room(ptag);
     u32 id = static_cast<u32>(nodes_.size());
     nodes_.emplace_back();
     HNode& n = nodes_.back();
     n.parent = parent;
     n.token = token;
-    u32 mask = static_cast<u32>(edges.size() - 1);
-    u32 i = edge_hash(parent, token) & mask;
-    while (edges[i].child != 0) i = (i + 1) & mask;
+    n.depth = static_cast<uint16_t>(nodes_[parent].depth + 1);
+    // where this node's OWN children will live: depth 1 -> hot window 0; depth 2 -> a fresh least-loaded window
+    // for the whole subtree; deeper -> inherited
+    n.wtag = n.depth <= 1 ? 0 : (n.depth == 2 ? static_cast<u8>(pick_tag()) : static_cast<u8>(ptag));
+    const u32 wm = win_mask();
+    u32 i = edge_slot0(parent, token, ptag, wm, win_shift(), nwin_mask());
+    while (edges[i].child != 0) i = edge_next(i, wm);
     EdgeSlot e{};
     e.parent = parent; e.token = token; e.child = id;
-    e.plus = 0; e.hash_ref = 0; e.own_ref = 0; e.mask = 0; e.cnts = 0;
+    e.plus = 0; e.hash_ref = 0; e.own_ref = 0; e.mask = static_cast<u32>(n.wtag) << WTAG_SHIFT; e.cnts = 0;
     edges[i] = e;
     n.edge_slot = i;
     edge_count_++;
+    tag_count_[ptag]++;
+    win_count_[ptag & nwin_mask()]++;
     if (!full_edges) dirty_edges.push_back(i);
     HNode& p = nodes_[parent];
     p.mask |= mask_bit(token);
@@ -173,11 +213,8 @@ u32 HostTrie::add_edge(u32 parent, u32 token) {
     if (p.wide) cfilter_insert(parent, token);
     else if (p.lit_children > WIDE_FANOUT) { p.wide = 1; cfilter_rebuild_ = true; }   // its earlier children are back-filled by the rebuild
     if (token == TOK_PLUS) {
-        n.plus_idx = static_cast<u32>(plus.size());
-        PlusRec r{};
-        r.node = id; r.plus = 0; r.hash_ref = 0; r.own_ref = 0; r.mask = 0; r.cnts = 0;
-        plus.push_back(r);
         p.plus_child = id;
+        plus_count_++;
     } else if (token == TOK_HASH) {
         p.hash_child = id;
     }
@@ -355,22 +392,18 @@ void HostTrie::make_ref(u32 node) {
 
 void HostTrie::write_record(u32 node) {
     const HNode& n = nodes_[node];
-    u32 plus_idx = (n.plus_child ? nodes_[n.plus_child].plus_idx : 0) | (n.wide ? PLUS_WIDE_FLAG : 0u);
+    const u32 plus_idx = n.plus_child ? nodes_[n.plus_child].edge_slot + 1u : 0u;   // direct slot of the '+' child
     u32 hash_ref = n.hash_child ? nodes_[n.hash_child].ref : 0;
     u32 hash_cnt = n.hash_child ? nodes_[n.hash_child].cnt16 : 0;
+    const u32 mask = (n.mask & MASK_BLOOM) | (n.wide ? MASK_WIDE_FLAG : 0u) | (static_cast<u32>(n.wtag) << WTAG_SHIFT);
     if (node == 0) {
-        root_plus = plus_idx; root_hash_ref = hash_ref; root_hash_cnt = hash_cnt; root_mask = n.mask;
+        root_plus = plus_idx; root_hash_ref = hash_ref; root_hash_cnt = hash_cnt; root_mask = mask;
         root_dirty = true;
         return;
     }
     EdgeSlot& e = edges[n.edge_slot];
-    e.plus = plus_idx; e.hash_ref = hash_ref; e.own_ref = n.ref; e.mask = n.mask; e.cnts = hash_cnt | (n.cnt16 << 16);
+    e.plus = plus_idx; e.hash_ref = hash_ref; e.own_ref = n.ref; e.mask = mask; e.cnts = hash_cnt | (n.cnt16 << 16);
     if (!full_edges) dirty_edges.push_back(n.edge_slot);
-    if (n.plus_idx) {
-        PlusRec& r = plus[n.plus_idx];
-        r.node = node; r.plus = plus_idx; r.hash_ref = hash_ref; r.own_ref = n.ref; r.mask = n.mask; r.cnts = e.cnts;
-        dirty_plus.push_back(n.plus_idx);
-    }
 }
 
 void HostTrie::compact() {

@@ -18,7 +18,6 @@ struct HNode {
     u32 parent = 0;
     u32 token = 0;
     u32 edge_slot = 0;       // slot in `edges` holding this node's record (non-root)
-    u32 plus_idx = 0;        // index in `plus` when this node is a '+' child, else 0
     u32 plus_child = 0;      // node id of the '+' child (0 = none)
     u32 hash_child = 0;      // node id of the '#' child (0 = none)
     u32 nvals = 0;           // size of the value set (BTreeSet<V>)
@@ -31,6 +30,8 @@ struct HNode {
     u8 alive = 0;            // reference semantics: pruned nodes (trie.rs:126-128) are "not alive"
     u8 dirty = 0;
     u8 wide = 0;             // more than WIDE_FANOUT literal children: its child edges live in the child filter
+    u8 wtag = 0;             // window tag: which window of `edges` holds this node's child edges (layout.h)
+    uint16_t depth = 0;           // levels from the root (root = 0)
 };
 
 enum ParseStatus { PARSE_OK = 0, PARSE_INVALID = 1, PARSE_TOO_DEEP = 2 };
@@ -56,7 +57,6 @@ class HostTrie {
 
     // ---- device mirror -------------------------------------------------------------------------
     std::vector<EdgeSlot> edges;
-    std::vector<PlusRec> plus;       // [0] reserved
     std::vector<Range> ranges;       // [0] reserved
     std::vector<u32> values;
     std::vector<DictSlot> dict;
@@ -65,17 +65,23 @@ class HostTrie {
     bool cfilter_dirty = true;
     u32 root_plus = 0, root_hash_ref = 0, root_hash_cnt = 0, root_mask = 0;
     u32 max_depth = 0;
+    // window geometry of `edges` (layout.h): windows = 1 << nwin_log2, each edges.size() >> nwin_log2 slots
+    u32 nwin_log2 = 0;
+    u32 win_shift() const { u32 b = 0; while ((size_t(1) << b) < edges.size()) ++b; return b - nwin_log2; }
+    u32 win_mask() const { return (1u << win_shift()) - 1u; }
+    u32 nwin_mask() const { return (1u << nwin_log2) - 1u; }
 
     // ---- dirty tracking (consumed and cleared by the engine's flush) ---------------------------
-    std::vector<u32> dirty_edges, dirty_plus, dirty_ranges, dirty_dict;
+    std::vector<u32> dirty_edges, dirty_ranges, dirty_dict;
     bool full_edges = true, full_dict = true;   // table re-hashed / never uploaded: ship whole table
-    bool any_dirty() const { return !dirty_nodes_.empty() || !dirty_edges.empty() || !dirty_plus.empty() ||
+    bool any_dirty() const { return !dirty_nodes_.empty() || !dirty_edges.empty() ||
                                     !dirty_ranges.empty() || !dirty_dict.empty() || full_edges || full_dict || root_dirty || cfilter_dirty ||
                                     cfilter_rebuild_; }
     bool root_dirty = true;
     u64 garbage_values = 0;
 
     u64 edge_count() const { return edge_count_; }
+    u64 plus_count() const { return plus_count_; }
     u64 dict_count() const { return dict_count_; }
     u64 node_count() const { return nodes_.size(); }
 
@@ -90,7 +96,10 @@ class HostTrie {
     u32 intern(const char* s, u32 len, bool create);
     u32 find_edge(u32 parent, u32 token) const;         // returns slot index or ~0u
     u32 add_edge(u32 parent, u32 token);                // creates the child node, returns its id
-    void grow_edges();
+    void grow_edges() { rehash_edges(edges.size() * 2); }
+    void rehash_edges(size_t new_size);                 // re-places every edge (new size and / or new window count)
+    void make_room(u32 wtag);                           // before an insertion into the window of `wtag`
+    u32 pick_tag() const;                               // least-loaded window tag for a new depth-2 subtree
     void grow_dict();
     void mark(u32 node);
     void make_ref(u32 node);
@@ -106,7 +115,11 @@ class HostTrie {
     std::vector<u32> dirty_nodes_;
     std::vector<u32> scratch_toks_;
     std::vector<u8> tok_dollar_;      // token -> level string starts with '$' (Level::Metadata)
-    u64 edge_count_ = 0, dict_count_ = 0;
+    u64 edge_count_ = 0, dict_count_ = 0, plus_count_ = 0;
+    u32 nwin_cap_log2_ = WIN_MAX_LOG2;
+    u32 win_min_log2_ = WIN_MIN_SLOTS_LOG2;   // raised when one subtree outgrows its window
+    std::vector<u64> tag_count_;         // edges per window tag (WTAG_COUNT entries)
+    std::vector<u64> win_count_;         // edges per effective window
     u32 next_token_ = TOK_FIRST;
     u64 values_size_ = 0, live_nodes_ = 0;
 };

@@ -38,6 +38,7 @@ struct MatchParams {
     const u32* perm;     // [n] locality order (k_bucket_*): position -> topic index
     const u32* tok8_sorted;   // [n][8] token rows copied into locality order (MP_SORTED_ROWS)
     const u32* meta_sorted;   // [n]
+    u32 tile_chunk;           // tiles a CTA takes from the global counter at once (<= 1: one tile per warp per grab)
 };
 constexpr u32 MP_DIAG_DEPTH_SHIFT = 8;   // diagnostics only: (flags >> 8) & 0xF = deepest level the fast walk may descend to (0 = no limit; results are then WRONG)
 constexpr u32 MP_DIAG_NO_PUBLISH = 2u;   // diagnostics only: skip the publish phase
@@ -225,29 +226,30 @@ k_bucket_scatter(const u32* __restrict__ bkey, u32* __restrict__ cursor, u32 n, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Work items.  lo = argument (parent node id for a literal probe, index into `plus` for a '+' hop),
-// hi = topic slot (5 bits) | depth of the node being loaded << 5 | kind << 21.
+// Work items.  lo = argument (parent node id for a literal probe, 1 + edge slot of the '+' child for a '+' hop),
+// hi = topic slot (5 bits) | depth of the node being loaded << 5 | kind << 21 | window tag of the parent << 22.
 constexpr u32 KIND_PROBE = 0, KIND_PLUS = 1;
-__device__ __forceinline__ u64 make_item(u32 topic, u32 depth, u32 kind, u32 arg) {
-    return (static_cast<u64>(topic | (depth << 5) | (kind << 21)) << 32) | arg;
+__device__ __forceinline__ u64 make_item(u32 topic, u32 depth, u32 kind, u32 arg, u32 wtag = 0u) {
+    return (static_cast<u64>(topic | (depth << 5) | (kind << 21) | (wtag << 22)) << 32) | arg;
 }
 
 struct NodeRec { u32 node, plus, hash_ref, own_ref, mask, cnts; };
 
 // Loads the record an item points at.  Returns false when the literal child does not exist.
-__device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 arg, u32 token, NodeRec& r) {
+// `pmask_tag`: the mask word of the PARENT's record — its top byte names the window holding the parent's child edges.
+__device__ __forceinline__ bool load_record(const TrieView& tv, u32 kind, u32 arg, u32 token, u32 pmask_tag, NodeRec& r) {
     u32 s[8];
-    if (kind == KIND_PLUS) {
-        ld256(tv.plus + arg, s);
-        r.node = s[0]; r.plus = s[1]; r.hash_ref = s[2]; r.own_ref = s[3]; r.mask = s[4]; r.cnts = s[5];
+    if (kind == KIND_PLUS) {                               // arg = 1 + slot of the '+' child: no hashing, no key compare
+        ld256(tv.edges + (arg - 1u), s);
+        r.node = s[2]; r.plus = s[3]; r.hash_ref = s[4]; r.own_ref = s[5]; r.mask = s[6]; r.cnts = s[7];
         return true;
     }
-    u32 idx = edge_hash(arg, token) & tv.edge_mask;
+    u32 idx = edge_slot0(arg, token, pmask_tag >> WTAG_SHIFT, tv.win_mask, tv.win_shift, tv.nwin_mask);
     for (;;) {
         ld256(tv.edges + idx, s);
         if (s[2] == 0) return false;                       // empty slot: no such child
         if (s[0] == arg && s[1] == token) break;
-        idx = (idx + 1) & tv.edge_mask;
+        idx = edge_next(idx, tv.win_mask);
     }
     r.node = s[2]; r.plus = s[3]; r.hash_ref = s[4]; r.own_ref = s[5]; r.mask = s[6]; r.cnts = s[7];
     return true;
@@ -258,6 +260,31 @@ __device__ __forceinline__ bool cfilter_maybe(const TrieView& tv, u32 parent, u3
     u32 w, bits;
     cfilter_pos(parent, token, tv.cfilter_mask, w, bits);
     return (__ldg(tv.cfilter + w) & bits) == bits;
+}
+
+// Tile scheduling.  Tiles are in locality order; handing them out one by one from a global counter scatters
+// neighbouring tiles over all SMs.  Instead a CTA reserves `chunk` consecutive tiles at a time and its warps take
+// them from shared memory, so the warps of one SM work on neighbouring (level0, level1) subtrees at the same time:
+// shared upper-level slots hit L1/L2 and the cold probes of the SM stay inside few windows of the edge table.
+// s_chunk = next tile (low word) | end of the reserved run (high word); s_lock serialises refills.  No barrier:
+// a warp that finds the run exhausted either refills it (lock holder) or spins for the few hundred ns that takes.
+__device__ __forceinline__ u32 next_tile_chunked(unsigned long long* s_chunk, u32* s_lock, u32* gcounter, u32 chunk) {
+    for (;;) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_chunk);
+        if (static_cast<u32>(cur) < static_cast<u32>(cur >> 32)) {
+            if (atomicCAS(s_chunk, cur, cur + 1ull) == cur) return static_cast<u32>(cur);
+            continue;
+        }
+        if (atomicCAS(s_lock, 0u, 1u) == 0u) {
+            cur = *reinterpret_cast<volatile unsigned long long*>(s_chunk);
+            if (static_cast<u32>(cur) < static_cast<u32>(cur >> 32)) { atomicExch(s_lock, 0u); continue; }   // refilled in between
+            const u32 base = atomicAdd(gcounter, chunk);
+            atomicExch(s_chunk, (static_cast<unsigned long long>(base + chunk) << 32) | (base + 1u));
+            __threadfence_block();
+            atomicExch(s_lock, 0u);
+            return base;
+        }
+    }
 }
 
 // A matched value set waiting to be expanded into the output: values[ref .. ref+cnt) (or ref itself).
@@ -292,9 +319,16 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
     const TrieView& tv = p.tv;
     const u32 ntiles = (p.n + 31) >> 5;
     unsigned long long sV = 0, sE = 0, sF = 0, sM = 0;
+    __shared__ unsigned long long s_chunk;
+    __shared__ u32 s_lock;
+    const u32 chunk = p.tile_chunk;
+    if (chunk > 1) {
+        if (tid == 0) { s_chunk = 0ull; s_lock = 0u; }
+        __syncthreads();
+    }
     for (;;) {
         u32 tile = 0;
-        if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
+        if (lane == 0) tile = chunk > 1 ? next_tile_chunked(&s_chunk, &s_lock, p.tile_counter, chunk) : atomicAdd(p.tile_counter, 1u);
         tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
         if (tile >= ntiles) break;
 
@@ -342,36 +376,49 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                     ++ndesc; total += c2;
                     if (STATS) lF++;
                 }
-                bool down = false;
+                // ---- choose the ONE slot this thread loads next: the literal child's first probe slot, else the
+                // deepest parked '+' child (its record names the slot directly).  Both kinds are 32-B edge slots with
+                // the same layout, so all lanes of the warp meet again at a single 256-bit load.
+                u32 idx = 0, nd = 0, kp = 0, kt = 0;
+                bool probe = false;
                 const u32 diag_max = (p.flags >> MP_DIAG_DEPTH_SHIFT) & 0xFu;
                 if (d < L && (diag_max == 0 || d < diag_max)) {
-                    const u32 plus_idx = r.plus & ~PLUS_WIDE_FLAG;
-                    if (plus_idx != 0 && !droot) { s_pend[d][tid] = plus_idx; pmask |= 1u << d; }   // '+' child (trie.rs:330-334)
-                    if (r.mask != 0) {
+                    if (r.plus != 0 && !droot) { s_pend[d][tid] = r.plus; pmask |= 1u << d; }   // '+' child (trie.rs:330-334)
+                    if ((r.mask & MASK_BLOOM) != 0) {
                         const u32 tk = s_tok[d][tid];
                         if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk)) &&
-                            (!(r.plus & PLUS_WIDE_FLAG) || cfilter_maybe(tv, r.node, tk))) {        // literal child (trie.rs:338-342)
-                            NodeRec c;
-                            const bool hit = load_record(tv, KIND_PROBE, r.node, tk, c);
-                            if (STATS) {   // diagnostics: probes / misses per depth, slot loads per probe
-                                atomicAdd(p.stats + 4 + min(d, 7u), 1ull);
-                                if (!hit) atomicAdd(p.stats + 12 + min(d, 7u), 1ull);
-                                u32 idx = edge_hash(r.node, tk) & tv.edge_mask, steps = 1;
-                                while (tv.edges[idx].child != 0 && !(tv.edges[idx].parent == r.node && tv.edges[idx].token == tk)) { idx = (idx + 1) & tv.edge_mask; ++steps; }
-                                atomicAdd(p.stats + 20, static_cast<unsigned long long>(steps));
-                            }
-                            if (hit) { r = c; ++d; down = true; }
+                            (!(r.mask & MASK_WIDE_FLAG) || cfilter_maybe(tv, r.node, tk))) {        // literal child (trie.rs:338-342)
+                            probe = true; kp = r.node; kt = tk; nd = d + 1;
+                            idx = edge_slot0(kp, kt, r.mask >> WTAG_SHIFT, tv.win_mask, tv.win_shift, tv.nwin_mask);
+                            if (STATS) atomicAdd(p.stats + 4 + min(d, 7u), 1ull);
                         }
                     }
                 }
                 droot = false;
-                if (!down) {
-                    if (pmask == 0) break;
-                    const u32 pd = 31u - __clz(pmask);          // resume the deepest parked '+' child
-                    pmask &= ~(1u << pd);
-                    load_record(tv, KIND_PLUS, s_pend[pd][tid], 0u, r);
-                    d = pd + 1;
+                bool done = false;
+                u32 s[8];
+                for (;;) {
+                    if (!probe) {
+                        if (pmask == 0) { done = true; break; }
+                        const u32 pd = 31u - __clz(pmask);          // resume the deepest parked '+' child
+                        pmask &= ~(1u << pd);
+                        idx = s_pend[pd][tid] - 1u;
+                        nd = pd + 1;
+                    }
+                    ld256(tv.edges + idx, s);
+                    if (!probe) break;
+                    if (STATS) atomicAdd(p.stats + 20, 1ull);
+                    if (s[2] == 0) {                                 // empty slot: the literal child does not exist
+                        if (STATS) atomicAdd(p.stats + 12 + min(nd - 1u, 7u), 1ull);
+                        probe = false;
+                        continue;
+                    }
+                    if (s[0] == kp && s[1] == kt) break;
+                    idx = edge_next(idx, tv.win_mask);               // linear probing inside the window
                 }
+                if (done) break;
+                r.node = s[2]; r.plus = s[3]; r.hash_ref = s[4]; r.own_ref = s[5]; r.mask = s[6]; r.cnts = s[7];
+                d = nd;
             }
             if (STATS && !defer) { sV += lV; sE += lE; sF += lF; sM += total; }
         }
@@ -483,12 +530,12 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                 u64 itA = 0, itB = 0;
                 bool pA = false, pB = false;
                 if (hit && d < L) {
-                    const u32 plus_idx = r.plus & ~PLUS_WIDE_FLAG;
+                    const u32 plus_idx = r.plus;
                     if (plus_idx != 0 && !dollar_root) { pA = true; itA = make_item(0, d + 1, KIND_PLUS, plus_idx); }
-                    if (r.mask != 0 && d < p.tok_levels) {
+                    if ((r.mask & MASK_BLOOM) != 0 && d < p.tok_levels) {
                         u32 tk = d < TOK8 ? p.tok8[static_cast<size_t>(t) * TOK8 + d] : p.tok[static_cast<size_t>(d) * p.n + t];
-                        if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk)) && (!(r.plus & PLUS_WIDE_FLAG) || cfilter_maybe(tv, r.node, tk))) {
-                            pB = true; itB = make_item(0, d + 1, KIND_PROBE, r.node);
+                        if (tk != TOK_UNKNOWN && (r.mask & mask_bit(tk)) && (!(r.mask & MASK_WIDE_FLAG) || cfilter_maybe(tv, r.node, tk))) {
+                            pB = true; itB = make_item(0, d + 1, KIND_PROBE, r.node, r.mask >> WTAG_SHIFT);
                         }
                     }
                 }
@@ -546,7 +593,7 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                 if (have) {
                     u32 tk = 0u;
                     if (kind == KIND_PROBE) tk = (d - 1) < TOK8 ? p.tok8[static_cast<size_t>(t) * TOK8 + (d - 1)] : p.tok[static_cast<size_t>(d - 1) * p.n + t];
-                    hit = load_record(tv, kind, arg, tk, r);
+                    hit = load_record(tv, kind, arg, tk, ((hi >> 22) & 0xFFu) << WTAG_SHIFT, r);
                 }
                 consume(hit, d, r, false);
             }

@@ -7,14 +7,16 @@
 //   edges  : open-addressing table  (parent node, token) -> child + the child's *node record*
 //            (32-B slots; ONE 256-bit load answers "does the child exist, what are its values, its
 //             '#'-child values, its '+'-child, which tokens can continue below it")
-//   plus   : node records of '+' children, addressed by index (reached by pointer, not by hashing)
 //   ranges / values : value sets with >1 element (single values are stored inline in the record)
 //
 // A node record = {plus, hash_ref, own_ref, mask}:
-//   plus     index into `plus` of this node's '+' child (0 = none)            trie.rs:330-334
+//   plus     1 + the slot of `edges` that holds this node's '+' child (0 = none): the '+' hop is a direct
+//            load of that slot, no hashing                                      trie.rs:330-334
 //   hash_ref value set of this node's '#' child (with its 16-bit count in cnts)   trie.rs:302-308,321-327
 //   own_ref  value set of the node itself                                        trie.rs:309-310
-//   mask     32-bit Bloom mask over the tokens of all children (skips hopeless literal probes)
+//   mask     bits 0..22: Bloom mask over the tokens of all children (skips hopeless literal probes)
+//            bit 23: wide node (its child edges are registered in the child filter, below)
+//            bits 24..31: window tag — which WINDOW of the edge table holds this node's child edges (below)
 #pragma once
 #include <cstdint>
 
@@ -57,17 +59,6 @@ struct alignas(32) EdgeSlot {
 };
 static_assert(sizeof(EdgeSlot) == 32, "EdgeSlot must be one 32-byte sector");
 
-struct alignas(32) PlusRec {
-    u32 node;      // node id of this '+' node (key for probing its literal children)
-    u32 plus;
-    u32 hash_ref;
-    u32 own_ref;
-    u32 mask;
-    u32 cnts;
-    u32 pad[2];
-};
-static_assert(sizeof(PlusRec) == 32, "PlusRec must be one 32-byte sector");
-
 // Dictionary slot: w[0] = token (0 = empty).  Inline strings (<= 27 bytes): bytes 4..30 = the string, zero
 // padded, byte 31 = its length — i.e. w[1..7] are exactly the words the tokeniser packs, so a lookup is
 // seven word compares.  Long strings: byte 31 = 0xFF, w[1] = length, w[2] = offset into the long-string
@@ -86,16 +77,32 @@ struct Range { u32 off, cnt; };
 // each such probe is a cold HBM request that finds an empty slot (measured: 1.76 M of them per 1 M topics on
 // C3).  Nodes with more than WIDE_FANOUT literal children therefore register ALL their child edges in one
 // small blocked Bloom filter (16 bits per edge; a few MB, L2 resident) and announce it with a flag in the
-// top bit of the `plus` field of their record.  A negative answer skips the probe; stale bits after removals
+// mask word of their record.  A negative answer skips the probe; stale bits after removals
 // only cost a wasted probe.
-constexpr u32 PLUS_WIDE_FLAG = 0x80000000u;
+constexpr u32 MASK_WIDE_FLAG = 1u << 23;
 constexpr u32 WIDE_FANOUT = 48;
 
+
+// ---- windows of the edge table -------------------------------------------------------------------
+// Measured on B200 (tools/randbench5.cu, profiles/r1_randbench_e.txt): random 32-B fetches from a multi-GB
+// table top out at ~37 G/s when every SM roams the whole table, but reach ~48 G/s when each CTA stays inside
+// a window of <= 64 MiB (address-translation reach).  The edge table is therefore cut into `nwin` equal
+// windows (a power of two): the child edges of a node all live in ONE window, named by the 8-bit tag in the
+// node's record; trie nodes of depth >= 3 inherit the tag of their depth-2 ancestor, so a whole
+// `level0/level1/...` subtree hashes into one window — and since the batch is walked in (level0, level1)
+// order (k_bucket_*), the cold probes of neighbouring topics land in the same few windows.  The children of
+// the root and of its children live in window 0 (hot, L2 resident).  Effective window = tag & (nwin-1), so
+// the host can halve `nwin` (one subtree outgrew its window) or grow the table without re-tagging.
+constexpr u32 MASK_BLOOM_BITS = 23;
+constexpr u32 MASK_BLOOM = (1u << MASK_BLOOM_BITS) - 1u;
+constexpr u32 WTAG_SHIFT = 24;
+constexpr u32 WTAG_COUNT = 256;          // tags are assigned over the full 8-bit range
+constexpr u32 WIN_MIN_SLOTS_LOG2 = 12;   // never cut windows smaller than 4096 slots (128 KiB)
+constexpr u32 WIN_MAX_LOG2 = 8;          // at most 256 windows
 
 // Root record + table geometry handed to every kernel by value.
 struct TrieView {
     const EdgeSlot* edges;
-    const PlusRec* plus;
     const Range* ranges;
     const u32* values;
     const DictSlot* dict;
@@ -103,6 +110,9 @@ struct TrieView {
     const u32* cfilter;     // child filter of wide nodes (words)
     u32 cfilter_mask;       // #words - 1
     u32 edge_mask;      // capacity-1 (capacity is a power of two)
+    u32 win_mask;       // slots per window - 1
+    u32 win_shift;      // log2(slots per window)
+    u32 nwin_mask;      // windows - 1
     u32 dict_mask;
     u32 root_plus, root_hash_ref, root_hash_cnt, root_mask;
     u32 max_depth;      // deepest filter in the trie (levels)
@@ -131,7 +141,13 @@ GM_HD u32 dict_hash_words(const u32 (&w)[7]) {
     for (int k = 0; k < 7; ++k) h = (h ^ w[k]) * 0x01000193u;
     return fmix32(h);
 }
-GM_HD u32 mask_bit(u32 token) { return 1u << ((token * 0x9E3779B1u) >> 27); }
+GM_HD u32 mask_bit(u32 token) { return 1u << ((((token * 0x9E3779B1u) >> 16) * MASK_BLOOM_BITS) >> 16); }   // one of 23 bits
+// first slot of the probe sequence of edge (parent, token) whose parent carries window tag `wtag`, and the
+// successor of a slot: linear probing that wraps inside the window
+GM_HD u32 edge_slot0(u32 parent, u32 token, u32 wtag, u32 win_mask, u32 win_shift, u32 nwin_mask) {
+    return ((wtag & nwin_mask) << win_shift) | (edge_hash(parent, token) & win_mask);
+}
+GM_HD u32 edge_next(u32 idx, u32 win_mask) { return (idx & ~win_mask) | ((idx + 1u) & win_mask); }
 // child filter of wide nodes: word index + the two bits of an edge
 GM_HD void cfilter_pos(u32 parent, u32 token, u32 word_mask, u32& word, u32& bits) {
     const u32 h = fmix32((parent ^ 0x68E31DA4u) * 0x9E3779B1u + token * 0x85EBCA77u);

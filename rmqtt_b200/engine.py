@@ -230,8 +230,8 @@ class Engine:
     def debug_tables(self) -> dict:
         """Host mirror of the device tables as numpy arrays (copies).  Test/diagnostic use only."""
         out = {}
-        spec = {0: ("edges", np.uint32, 8), 1: ("plus", np.uint32, 8), 2: ("ranges", np.uint32, 2), 3: ("values", np.uint32, 1),
-                4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1),  # root = {plus, hash_ref, mask, max_depth, hash_cnt}
+        spec = {0: ("edges", np.uint32, 8), 2: ("ranges", np.uint32, 2), 3: ("values", np.uint32, 1),
+                4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1),  # root = {plus, hash_ref, mask, max_depth, hash_cnt, win_mask, win_shift, nwin_mask}
                 7: ("rnodes", np.uint32, 8), 8: ("rkids", np.uint32, 8), 9: ("rvals", np.uint32, 1), 12: ("cfilter", np.uint32, 1)}
         for which, (name, dt, width) in spec.items():
             ptr, cnt = C.c_void_p(), C.c_uint64(0)
@@ -244,6 +244,10 @@ class Engine:
             a = np.frombuffer(buf, dtype=dt).copy()
             out[name] = a.reshape(-1, width) if width > 1 else a
         return out
+
+    def debug_knob(self, name: str, value: int) -> None:
+        """Set a kernel-scheduling knob (gm_debug_knob): tuning / A-B measurements only, results never change."""
+        self._check(self._lib.gm_debug_knob(self._h, name.encode(), int(value)))
 
     def kernel_ms(self, max_calls: int = 64) -> np.ndarray:
         """[calls, 3] device milliseconds (tokenise, match, deferred) of the last match calls, oldest first."""

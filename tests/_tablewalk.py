@@ -7,7 +7,6 @@ import numpy as np
 
 M32 = 0xFFFFFFFF
 CNT_BIG = 0xFFFF
-PLUS_WIDE_FLAG = 0x80000000
 TOK_UNKNOWN, TOK_PLUS, TOK_HASH, TOK_BLANK = 0, 1, 2, 3
 
 
@@ -49,16 +48,23 @@ def cfilter_pos(parent, token, word_mask):
     return h & word_mask, (1 << (g & 31)) | (1 << ((g >> 5) & 31))
 
 
+MASK_BLOOM = 0x007FFFFF
+MASK_WIDE_FLAG = 1 << 23
+WTAG_SHIFT = 24
+
+
 def mask_bit(tok):
-    return 1 << (((tok * 0x9E3779B1) & M32) >> 27)
+    return 1 << ((((((tok * 0x9E3779B1) & M32) >> 16) * 23) & M32) >> 16)
 
 
 class Tables:
     def __init__(self, t):
-        self.edges, self.plus, self.ranges, self.values = t["edges"], t["plus"], t["ranges"], t["values"]
+        self.edges, self.ranges, self.values = t["edges"], t["ranges"], t["values"]
         self.dict, self.pool = t["dict"], t["pool"]
         self.cfilter = t["cfilter"]
-        self.root_plus, self.root_hash_ref, self.root_mask, self.max_depth, self.root_hash_cnt = (int(x) for x in t["root"])
+        (self.root_plus, self.root_hash_ref, self.root_mask, self.max_depth, self.root_hash_cnt,
+         self.win_mask, self.win_shift, self.nwin_mask) = (int(x) for x in t["root"])
+        assert (self.win_mask + 1) * (self.nwin_mask + 1) == len(self.edges) and self.win_mask + 1 == 1 << self.win_shift
         self.dict_bytes = self.dict.view(np.uint8).reshape(len(self.dict), 32)
 
     def token(self, lv: bytes):
@@ -101,16 +107,19 @@ class Tables:
             toks.append(self.token(lv))
         return toks, dollar
 
-    def probe(self, parent, tok):
-        mask = len(self.edges) - 1
-        i = edge_hash(parent, tok) & mask
+    def probe(self, parent, tok, parent_mask):
+        """Linear probing inside the window named by the top byte of the parent's mask word (layout.h)."""
+        wm = self.win_mask
+        base = ((parent_mask >> WTAG_SHIFT) & self.nwin_mask) << self.win_shift
+        i = base | (edge_hash(parent, tok) & wm)
+        self.windows_touched.add(base)
         while True:
             e = self.edges[i]
             if e[2] == 0:
                 return None
             if e[0] == parent and e[1] == tok:
                 return dict(node=int(e[2]), plus=int(e[3]), hash_ref=int(e[4]), own_ref=int(e[5]), mask=int(e[6]), cnts=int(e[7]))
-            i = (i + 1) & mask
+            i = base | ((i + 1) & wm)
 
     def expand(self, ref, cnt, out):
         if cnt == 0:
@@ -133,6 +142,7 @@ class Tables:
         L = len(toks)
         out = []
         V = E = F = 0
+        self.windows_touched = set()
         stack = [(dict(node=0, plus=self.root_plus, hash_ref=self.root_hash_ref, own_ref=0, mask=self.root_mask, cnts=self.root_hash_cnt), 0, dollar)]
         while stack:
             r, d, dollar_root = stack.pop()
@@ -143,17 +153,18 @@ class Tables:
                 F += self.expand(r["own_ref"], r["cnts"] >> 16, out)
                 continue
             E += 1
-            plus_idx = r["plus"] & ~PLUS_WIDE_FLAG & M32
-            if plus_idx and not dollar_root:
-                p = self.plus[plus_idx]
-                stack.append((dict(node=int(p[0]), plus=int(p[1]), hash_ref=int(p[2]), own_ref=int(p[3]), mask=int(p[4]), cnts=int(p[5])), d + 1, False))
+            plus_idx = r["plus"]
+            if plus_idx and not dollar_root:      # direct slot of the '+' child (1-based)
+                p = self.edges[plus_idx - 1]
+                assert int(p[0]) == r["node"] and int(p[1]) == TOK_PLUS and int(p[2]) != 0, "stale '+' slot"
+                stack.append((dict(node=int(p[2]), plus=int(p[3]), hash_ref=int(p[4]), own_ref=int(p[5]), mask=int(p[6]), cnts=int(p[7])), d + 1, False))
             t = toks[d]
             maybe = True
-            if r["plus"] & PLUS_WIDE_FLAG:      # child filter of wide nodes: must never give a false negative
+            if r["mask"] & MASK_WIDE_FLAG:      # child filter of wide nodes: must never give a false negative
                 w, bits = cfilter_pos(r["node"], t, len(self.cfilter) - 1)
                 maybe = (int(self.cfilter[w]) & bits) == bits
-            if t != TOK_UNKNOWN and r["mask"] & mask_bit(t):
-                c = self.probe(r["node"], t)
+            if t != TOK_UNKNOWN and r["mask"] & MASK_BLOOM & mask_bit(t):
+                c = self.probe(r["node"], t, r["mask"])
                 assert maybe or c is None, "child filter false negative"
                 if not maybe:
                     c = None

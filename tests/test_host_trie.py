@@ -168,3 +168,43 @@ def test_compact_drops_dead_nodes_and_garbage_keeps_matches():
     _apply(eng, tree, "a/+/zz", 5, "add")
     T = Tables(eng.debug_tables())
     assert T.match(b"a/b/zz")[0] == tree.matches("a/b/zz")
+
+
+@pytest.mark.parametrize("win_min,cap", [(3, 8), (4, 2), (5, 8)])
+def test_windowed_edge_table_vs_oracle(monkeypatch, win_min, cap):
+    """Edge table cut into many tiny windows (layout.h): subtrees outgrow their window, windows get halved, the
+    table grows — the table walk must stay identical to the oracle throughout, and one topic's probes stay in
+    few windows (its exact (level0, level1) subtree, the '+' variants and the hot window 0)."""
+    monkeypatch.setenv("GM_WIN_MIN_SLOTS_LOG2", str(win_min))
+    monkeypatch.setenv("GM_EDGE_WINDOWS_LOG2", str(cap))
+    rng = random.Random(100 + win_min)
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    fs = []
+    for i in range(3000):
+        a, b = rng.randrange(6), rng.randrange(6)
+        lv = [f"r{a}", f"s{b}"] + [f"x{rng.randrange(5)}" for _ in range(rng.randrange(0, 4))]
+        if rng.random() < 0.3:
+            lv[rng.randrange(len(lv))] = "+"
+        if rng.random() < 0.1:
+            lv.append("#")
+        fs.append(("/".join(lv), i))
+    fs += [(f"big/one/{i}/{j}", 10_000 + i * 40 + j) for i in range(40) for j in range(40)]   # one subtree >> a window
+    rng.shuffle(fs)
+    for k, (f, v) in enumerate(fs):
+        _apply(eng, tree, f, v, "add")
+        if k % 1500 == 1499 or k == len(fs) - 1:
+            T = Tables(eng.debug_tables())
+            for _ in range(120):
+                t = "/".join([f"r{rng.randrange(6)}", f"s{rng.randrange(6)}"] + [f"x{rng.randrange(5)}" for _ in range(rng.randrange(0, 4))])
+                assert T.match(t.encode())[0] == tree.matches(t), t
+                assert len(T.windows_touched) <= 5, (t, T.windows_touched)     # window 0 + {r,+} x {s,+}
+            for i in (0, 17, 39):
+                t = f"big/one/{i}/{i}"
+                assert T.match(t.encode())[0] == tree.matches(t), t
+    for f, v in fs[::3]:
+        _apply(eng, tree, f, v, "remove")
+    T = Tables(eng.debug_tables())
+    assert T.nwin_mask + 1 <= 1 << cap
+    for _ in range(200):
+        t = "/".join([f"r{rng.randrange(6)}", f"s{rng.randrange(6)}"] + [f"x{rng.randrange(5)}" for _ in range(rng.randrange(0, 4))])
+        assert T.match(t.encode())[0] == tree.matches(t), t

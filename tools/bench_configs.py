@@ -44,12 +44,21 @@ def publish_config(cfg, reps=20, zipf=False):
     oN = tree.match_batch(tb, to, nthreads=threads, want_ids=False)
     counts = d_spans.cpu().numpy()[:, 1].astype(np.int64)
     parity = bool((counts == o1["counts"]).all())
+    ids_exact = None
+    if FULL_PARITY:      # bit-exact sorted multisets of every topic at full size (slow: sorts all ids on the host)
+        from rmqtt_b200.engine import MatchResult
+        res = MatchResult(d_spans.cpu().numpy().view(np.uint32), d_ids.cpu().numpy().view(np.uint32)[:need], d_status.cpu().numpy(), need)
+        _, gids = res.canonical()
+        ow = tree.match_batch(tb, to, nthreads=threads, want_ids=True)
+        seg = np.repeat(np.arange(n, dtype=np.int64), np.maximum(ow["counts"], 0))
+        oids = ow["ids"][np.lexsort((ow["ids"], seg))]
+        ids_exact = bool(parity and len(gids) == len(oids) and (gids == oids).all())
     alg = w["bytes"] + 8 * n + 16 * w["levels"] + 16 * w["visited"] + 16 * w["probed"] + 8 * w["filters"] + 4 * w["ids"] + 8 * n
     ms = float(k.sum())
     return {"config": cfg.name + ("-zipf" if zipf else ""), "subs": cfg.n_subs, "topics": n, "gpu_ms": {"tokenize": float(k[0]), "match": float(k[1]), "deferred": float(k[2])},
             "gpu_topics_per_s": n / (ms * 1e-3), "pairs_per_s": w["ids"] / (ms * 1e-3), "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
             "cpu_1thr_topics_per_s": n / o1["seconds"], f"cpu_{threads}thr_topics_per_s": n / oN["seconds"], "cpu_kind": "oracle TopicTree::matches restatement",
-            "ids_per_topic": w["ids"] / n, "visited_per_topic": w["visited"] / n, "count_parity": parity, "build_s": round(build, 2)}
+            "ids_per_topic": w["ids"] / n, "visited_per_topic": w["visited"] / n, "count_parity": parity, "ids_bit_exact": ids_exact, "build_s": round(build, 2)}
 
 
 def retain_config(cfg, reps=10):
@@ -89,7 +98,12 @@ def retain_config(cfg, reps=10):
             "hits_per_filter": need / n, "visited_per_filter": c["V"] / n, "count_parity": parity, "build_s": round(build, 2)}
 
 
+FULL_PARITY = False
+
 if __name__ == "__main__":
+    if "--full-parity" in sys.argv:
+        FULL_PARITY = True
+        sys.argv.remove("--full-parity")
     which = sys.argv[1:] or ["C1", "C2", "C4"]
     for name in which:
         zipf = name.endswith("Z")                   # e.g. C3Z: C3 subscriptions, Zipf(1.0)-over-devices publish batch
