@@ -313,7 +313,7 @@ def run_own(args):
         except Exception:
             pass
     if traffic is None:
-        traffic = 735144448   # dram__bytes_read.sum + dram__bytes_write.sum of k_match_fast, one launch, profiles/r1_k2_final.ncu-rep
+        traffic = 771856128   # dram__bytes_read.sum + dram__bytes_write.sum of k_match_fast, one C3 launch, profiles/r1_k2_windows.ncu-rep
     roofline = {"bound": "hbm", "kernel": "k_match_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k2_bytes, "kernel_ms": {"k_tokenize+k_bucket_scan+k_bucket_scatter": float(k_mean[0]), "k_match_fast": k2_ms, "k_match_slow": float(k_mean[2])},

@@ -204,7 +204,7 @@ uint32_t gm_shard_of(const char* topic_or_filter, uint32_t len, uint32_t n_shard
 int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t* count);
 /* DEBUG/TUNING: set a kernel-scheduling knob of this engine at run time (A/B measurements; results never change).
  * "tile_chunk" (1..1024: consecutive 32-topic tiles a CTA of the match kernel reserves at once), "k2_ctas" (0 = default),
- * "sorted_rows" (0/1), "diag_flags" (timing diagnostics: see kernels.cuh MP_DIAG_*; results are WRONG when set).       */
+ * "sorted_rows" (0/1), "bucket_bits" (100*a+b: locality buckets = 2^(a+b)), "diag_flags" (timing diagnostics: see kernels.cuh MP_DIAG_*; results are WRONG when set).       */
 int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value);
 /* pinned host memory for the host-buffer entry points */
 void* gm_host_alloc(uint64_t bytes);

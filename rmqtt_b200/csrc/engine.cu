@@ -110,7 +110,6 @@ struct gm_engine {
         if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
         if (const char* ev = getenv("GM_K2_CTAS")) knobs.k2_ctas = atoi(ev);
         if (const char* ev = getenv("GM_TILE_CHUNK")) { int v = atoi(ev); if (v >= 1 && v <= 1024) knobs.tile_chunk = static_cast<u32>(v); }
-        if (const char* ev = getenv("GM_DIAG_MAXDEPTH")) knobs.diag_flags |= (static_cast<u32>(atoi(ev)) & 0xFu) << MP_DIAG_DEPTH_SHIFT;   // timing diagnostics: WRONG results
         if (getenv("GM_DIAG_NO_PUBLISH")) knobs.diag_flags |= MP_DIAG_NO_PUBLISH;
     }
 
@@ -868,6 +867,7 @@ int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value) {
     if (k == "tile_chunk" && value >= 1 && value <= 1024) e->knobs.tile_chunk = static_cast<u32>(value);
     else if (k == "k2_ctas" && value >= 0 && value <= 8) e->knobs.k2_ctas = static_cast<int>(value);
     else if (k == "sorted_rows") e->knobs.sorted_rows = value != 0;
+    else if (k == "bucket_bits" && value / 100 >= 10 && value % 100 + value / 100 <= int64_t(MAX_BUCKET_BITS)) { e->knobs.site_bits = static_cast<u32>(value / 100); e->knobs.sub_bits = static_cast<u32>(value % 100); }
     else if (k == "diag_flags") e->knobs.diag_flags = static_cast<u32>(value);
     else return GM_ERR_INVALID_ARG;
     return GM_OK;

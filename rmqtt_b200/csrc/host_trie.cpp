@@ -439,8 +439,19 @@ void HostTrie::sync() {
         for (u32 id = 0; id < nodes_.size(); ++id) if (nodes_[id].wide && !nodes_[id].dirty) { nodes_[id].dirty = 1; dirty_nodes_.push_back(id); }
         cfilter_rebuild();
     }
-    // pass 1: value-set references (a '#' node's parent reads the child's fresh ref in pass 2)
-    for (u32 id : dirty_nodes_) make_ref(id);
+    // pass 1: value-set references (a '#' node's parent reads the child's fresh ref in pass 2).  Sets with more than
+    // one value are appended to `values`; they are appended grouped by (window, depth-2 subtree) so that the sets
+    // one tile of the match kernel expands (same level0/level1 subtree) are neighbours in `values` as well.
+    std::vector<std::pair<u64, u32>> multi;
+    for (u32 id : dirty_nodes_) {
+        if (nodes_[id].nvals < 2) { make_ref(id); continue; }
+        u32 a = id;
+        while (nodes_[a].depth > 2) a = nodes_[a].parent;
+        const u32 tag = id == 0 ? 0u : nodes_[nodes_[id].parent].wtag;
+        multi.emplace_back((static_cast<u64>(tag) << 32) | a, id);
+    }
+    std::sort(multi.begin(), multi.end());
+    for (const auto& m : multi) make_ref(m.second);
     for (u32 id : dirty_nodes_) { write_record(id); nodes_[id].dirty = 0; }
     dirty_nodes_.clear();
 }

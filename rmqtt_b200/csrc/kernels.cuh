@@ -40,7 +40,6 @@ struct MatchParams {
     const u32* meta_sorted;   // [n]
     u32 tile_chunk;           // tiles a CTA takes from the global counter at once (<= 1: one tile per warp per grab)
 };
-constexpr u32 MP_DIAG_DEPTH_SHIFT = 8;   // diagnostics only: (flags >> 8) & 0xF = deepest level the fast walk may descend to (0 = no limit; results are then WRONG)
 constexpr u32 MP_DIAG_NO_PUBLISH = 2u;   // diagnostics only: skip the publish phase
 constexpr u32 MP_SORTED_ROWS = 1u;   // k_bucket_scatter also copies token rows + meta into sorted order (coalesced reads in k_match_fast)
 constexpr u32 MAX_BUCKET_BITS = 18;   // locality buckets: 2^bits, bits = site_bits + sub_bits (engine.cu)
@@ -189,10 +188,14 @@ k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, Tri
 __global__ void __launch_bounds__(1024)
 k_bucket_scan(const u32* __restrict__ hist, u32* __restrict__ cursor, u32 nbuckets) {
     __shared__ u32 s_warp[32];
-    const u32 per = nbuckets / 1024;                 // nbuckets is a power of two >= 1024
+    // thread t owns the 128-bit words [t*per4, (t+1)*per4) of the histogram; nbuckets is a power of two >= 1024
+    const u32 per4 = max(nbuckets / 4096u, 1u);
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool mine = static_cast<size_t>(tid) * per4 * 4 < nbuckets;
+    const uint4* __restrict__ h4 = reinterpret_cast<const uint4*>(hist) + static_cast<size_t>(tid) * per4;
     u32 sum = 0;
-    for (u32 k = 0; k < per; ++k) sum += hist[tid * per + k];
+    if (mine)
+        for (u32 k = 0; k < per4; ++k) { const uint4 v = h4[k]; sum += v.x + v.y + v.z + v.w; }
     u32 inc = sum;                                   // warp-level inclusive scan by shuffle
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
@@ -205,8 +208,15 @@ k_bucket_scan(const u32* __restrict__ hist, u32* __restrict__ cursor, u32 nbucke
         s_warp[lane] = wi - w;                        // exclusive offset of each warp
     }
     __syncthreads();
+    if (!mine) return;
     u32 run = s_warp[wid] + inc - sum;
-    for (u32 k = 0; k < per; ++k) { const u32 v = hist[tid * per + k]; cursor[tid * per + k] = run; run += v; }
+    uint4* __restrict__ c4 = reinterpret_cast<uint4*>(cursor) + static_cast<size_t>(tid) * per4;
+    for (u32 k = 0; k < per4; ++k) {
+        const uint4 v = h4[k];
+        uint4 o;
+        o.x = run; run += v.x; o.y = run; run += v.y; o.z = run; run += v.z; o.w = run; run += v.w;
+        c4[k] = o;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -381,8 +391,7 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                 // the same layout, so all lanes of the warp meet again at a single 256-bit load.
                 u32 idx = 0, nd = 0, kp = 0, kt = 0;
                 bool probe = false;
-                const u32 diag_max = (p.flags >> MP_DIAG_DEPTH_SHIFT) & 0xFu;
-                if (d < L && (diag_max == 0 || d < diag_max)) {
+                if (d < L) {
                     if (r.plus != 0 && !droot) { s_pend[d][tid] = r.plus; pmask |= 1u << d; }   // '+' child (trie.rs:330-334)
                     if ((r.mask & MASK_BLOOM) != 0) {
                         const u32 tk = s_tok[d][tid];
