@@ -156,7 +156,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "topics/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ======================================================================================================
@@ -355,13 +355,25 @@ def run_own(args):
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = sys.stdout
+
+
+def _emit(line: dict) -> None:
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
+
+
 if __name__ == "__main__":
     a = _args()
+    # stdout carries exactly ONE line (the JSON result): keep a private handle to it and point fd 1 at stderr so that
+    # library chatter written by native code (e.g. NCCL's "NCCL version ..." banner) cannot land on it.
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
