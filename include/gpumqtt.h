@@ -103,7 +103,7 @@ int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets /* 
 int32_t gm_flush(gm_engine* e);
 /* Rebuilds the device tables from the live filters: drops the records of pruned nodes (rmqtt/src/trie.rs:126-128 removes
  * them eagerly; here they linger as dead records until compaction) and the garbage left by replaced value sets.
- * O(live filters).  Not available while retained topics are stored (the level dictionary is shared).          */
+ * O(live filters + retained topics): the level dictionary is shared with the retained tree, whose nodes are re-labelled. */
 int32_t gm_compact(gm_engine* e);
 
 /* ---- Router::matches for a batch of PUBLISH topic names (host buffers).

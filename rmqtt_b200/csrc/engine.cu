@@ -500,12 +500,11 @@ int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets, co
 int32_t gm_compact(gm_engine* e) {
     if (!e) return GM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    if (e->rtree.values_size() != 0) {
-        // the retained tree interns its levels in the same dictionary; its tokens would dangle -> re-intern by re-flattening
-        g_err = "gm_compact: not supported while the retained tree is non-empty (tokens are shared)";
-        return GM_ERR_INVALID_ARG;
-    }
-    e->trie.compact();
+    // the retained tree interns its levels in the same dictionary: carry its tokens over and re-label its nodes
+    const std::vector<u32> keep = e->rtree.used_tokens();
+    std::vector<u32> remap;
+    e->trie.compact(&keep, &remap);
+    e->rtree.remap_tokens(remap);
     e->up_ranges = e->up_values = e->up_pool = 0;
     e->up_edges_slots = e->up_dict_slots = 0;
     return (e->flags & GM_FLAG_HOST_ONLY) ? GM_OK : e->flush_locked();

@@ -173,14 +173,22 @@ void HostTrie::make_room(u32 wtag) {
         const u64 win_slots = edges.size() >> nwin_log2;
         if ((edge_count_ + 1) * 2 <= edges.size() && (win_count_[wtag & nwin_mask()] + 1) * 2 <= win_slots) return;
         if ((edge_count_ + 1) * 4 > edges.size() || nwin_log2 == 0) rehash_edges(edges.size() * 2);
-        else { win_min_log2_ = win_shift() + 1; rehash_edges(edges.size()); }
+        else { win_min_log2_ = win_shift() + 2; rehash_edges(edges.size()); }   // x4 per step: at most 4 re-hashes down to one window
     }
 }
 
 u32 HostTrie::pick_tag() const {
-    u32 best = 1;                                    // tag 0 = the hot window of the top two levels
-    for (u32 t = 2; t < WTAG_COUNT; ++t) if (tag_count_[t] < tag_count_[best]) best = t;
-    return best;
+    // tag 0 = the hot window of the top two levels.  Exact least-loaded choice while depth-2 subtrees are few (they
+    // are created early in a bulk load, when all counts are still tiny: this is what spreads them evenly); the
+    // better of two hashed candidates once there are many (O(1) per new subtree, still balanced).
+    if (anchors_ < 4096) {
+        u32 best = 1;
+        for (u32 t = 2; t < WTAG_COUNT; ++t) if (tag_count_[t] < tag_count_[best]) best = t;
+        return best;
+    }
+    const u32 h = fmix32(static_cast<u32>(anchors_) * 0x9E3779B1u + 0x7F4A7C15u);
+    const u32 a = 1u + (h & 0xFFFFu) % (WTAG_COUNT - 1), b = 1u + (h >> 16) % (WTAG_COUNT - 1);
+    return tag_count_[b] < tag_count_[a] ? b : a;
 }
 
 u32 HostTrie::add_edge(u32 parent, u32 token) {
@@ -195,6 +203,7 @@ u32 HostTrie::add_edge(u32 parent, u32 token) {
     // where this node's OWN children will live: depth 1 -> hot window 0; depth 2 -> a fresh least-loaded window
     // for the whole subtree; deeper -> inherited
     n.wtag = n.depth <= 1 ? 0 : (n.depth == 2 ? static_cast<u8>(pick_tag()) : static_cast<u8>(ptag));
+    if (n.depth == 2) anchors_++;
     const u32 wm = win_mask();
     u32 i = edge_slot0(parent, token, ptag, wm, win_shift(), nwin_mask());
     while (edges[i].child != 0) i = edge_next(i, wm);
@@ -406,7 +415,7 @@ void HostTrie::write_record(u32 node) {
     if (!full_edges) dirty_edges.push_back(n.edge_slot);
 }
 
-void HostTrie::compact() {
+void HostTrie::compact(const std::vector<u32>* keep, std::vector<u32>* remap) {
     // token -> level string, from the dictionary slots
     std::vector<std::string> tok_str(next_token_);
     for (const DictSlot& d : dict) {
@@ -430,6 +439,13 @@ void HostTrie::compact() {
         if (n.nvals == 1) fresh.insert(f.data(), static_cast<u32>(f.size()), n.v0, &ch);
         else for (u32 v : multi_[id]) fresh.insert(f.data(), static_cast<u32>(f.size()), v, &ch);
     }
+    if (remap) remap->assign(next_token_, 0u);
+    if (keep)
+        for (u32 old : *keep) {
+            if (old < TOK_FIRST || old >= tok_str.size()) continue;
+            const u32 neu = fresh.intern(tok_str[old].data(), static_cast<u32>(tok_str[old].size()), true);
+            if (remap) (*remap)[old] = neu;
+        }
     *this = std::move(fresh);
 }
 

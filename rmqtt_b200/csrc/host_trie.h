@@ -49,7 +49,9 @@ class HostTrie {
     void sync();
     // Rebuild every table from the live content: drops pruned nodes, dead dictionary use and value garbage.
     // Tokens are re-assigned; the caller must treat all device tables as new (everything is marked dirty).
-    void compact();
+    // `keep` lists old tokens that other users of the dictionary (the retained tree) still hold: their strings are
+    // re-interned and `remap` (if given) receives old token -> new token for them (0 for every other token).
+    void compact(const std::vector<u32>* keep = nullptr, std::vector<u32>* remap = nullptr);
 
     // reference-visible statistics
     u64 values_size() const { return values_size_; }   // trie.rs:148-151
@@ -115,7 +117,7 @@ class HostTrie {
     std::vector<u32> dirty_nodes_;
     std::vector<u32> scratch_toks_;
     std::vector<u8> tok_dollar_;      // token -> level string starts with '$' (Level::Metadata)
-    u64 edge_count_ = 0, dict_count_ = 0, plus_count_ = 0;
+    u64 edge_count_ = 0, dict_count_ = 0, plus_count_ = 0, anchors_ = 0;
     u32 nwin_cap_log2_ = WIN_MAX_LOG2;
     u32 win_min_log2_ = WIN_MIN_SLOTS_LOG2;   // raised when one subtree outgrows its window
     std::vector<u64> tag_count_;         // edges per window tag (WTAG_COUNT entries)

@@ -77,6 +77,32 @@ int RetainTreeHost::remove(const char* topic, u32 len, bool* had_old, u32* old) 
     return PARSE_OK;
 }
 
+std::vector<u32> RetainTreeHost::used_tokens() const {
+    std::vector<u32> out;
+    std::vector<u32> todo{0u};
+    while (!todo.empty()) {
+        const u32 n = todo.back(); todo.pop_back();
+        for (const auto& kv : nodes_[n].kids) { if (kv.first >= TOK_FIRST) out.push_back(kv.first); todo.push_back(kv.second); }
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    return out;
+}
+
+void RetainTreeHost::remap_tokens(const std::vector<u32>& remap) {
+    std::vector<u32> todo{0u};
+    while (!todo.empty()) {
+        const u32 n = todo.back(); todo.pop_back();
+        for (auto& kv : nodes_[n].kids) {
+            if (kv.first >= TOK_FIRST) kv.first = remap[kv.first];
+            nodes_[kv.second].token = kv.first;
+            todo.push_back(kv.second);
+        }
+        std::sort(nodes_[n].kids.begin(), nodes_[n].kids.end());
+    }
+    dirty = true;
+}
+
 void RetainTreeHost::flatten() {
     rnodes.clear(); rkids.clear(); rvals.clear();
     rnodes.reserve(n_nodes_ + 1); rkids.reserve(n_nodes_ + 1); rvals.reserve(n_values_);

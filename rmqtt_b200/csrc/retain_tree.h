@@ -61,6 +61,10 @@ class RetainTreeHost {
     // RetainTree::remove (retain.rs:237-257) with bottom-up pruning.
     int remove(const char* topic, u32 len, bool* had_old, u32* old);
 
+    // Dictionary compaction (HostTrie::compact): the level tokens this tree holds, and their replacement.
+    std::vector<u32> used_tokens() const;
+    void remap_tokens(const std::vector<u32>& remap);
+
     u64 values_size() const { return n_values_; }     // retain.rs:385-392
     u64 nodes_size() const { return n_nodes_; }       // retain.rs:395-398
 

@@ -325,6 +325,15 @@ def test_thread_safety_concurrent_matches_and_mutations():
 def test_compact_on_device_keeps_parity():
     rng = random.Random(77)
     eng, tree = Engine(), orc.TopicTree()
+    rtree, rtopics = orc.RetainTree(), []
+    for i in range(800):                      # the retained tree shares the dictionary that compaction re-labels
+        t = rand_topic(rng, 6)
+        try:
+            eng.retain_set(t, i)
+        except GpuMqttError:
+            continue
+        rtree.insert(t, i)
+        rtopics.append(t)
     live = []
     for _ in range(3000):
         f, v = rand_filter(rng), rng.randint(0, 30)
@@ -345,6 +354,9 @@ def test_compact_on_device_keeps_parity():
     _assert_same(eng.match_batch(tb, to), tree.match_batch(tb, to))
     eng.add("q/+/r", 9); tree.insert("q/+/r", 9)
     assert eng.matches("q/x/r") == tree.matches("q/x/r")
+    filters = [f for f in (rand_filter(rng) for _ in range(600)) if orc.topic_parse(f) is not None]
+    fb, fo = pack(filters)
+    _assert_same(eng.retain_match_batch(fb, fo), rtree.match_batch(fb, fo))
 
 
 def test_tokenizer_fuzz_against_topic_from_str():

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from rmqtt_b200.engine import Engine
+from rmqtt_b200.engine import Engine, GpuMqttError
 
 from _gen import rand_filter, rand_topic
 from _retainwalk import RetainTables
@@ -102,3 +102,55 @@ def test_republish_with_the_same_handle_does_not_dirty_the_device_copy():
     eng.retain_set("a/b", 8)
     t2 = eng.debug_tables()["rvals"].tolist()
     assert t1 == [7] and t2 == [8]
+
+
+def test_compact_relabels_the_retained_tree():
+    """gm_compact re-assigns every dictionary token; the retained tree shares the dictionary and must be re-labelled:
+    both trees keep matching exactly like the oracle afterwards, and keep working incrementally."""
+    import random
+    from _gen import rand_filter, rand_topic
+    from _tablewalk import Tables
+    rng = random.Random(5)
+    eng, sub, ret = Engine(host_only=True), orc.TopicTree(), orc.RetainTree()
+    filters = []
+    for i in range(800):
+        f = rand_filter(rng)
+        try:
+            eng.add(f, i)
+        except GpuMqttError:
+            continue
+        sub.insert(f, i)
+        filters.append((f, i))
+    topics = []
+    for i in range(600):
+        t = rand_topic(rng)
+        try:
+            eng.retain_set(t, i)
+        except GpuMqttError:
+            continue
+        ret.insert(t, i)
+        topics.append(t)
+    for f, i in filters[:600]:            # most level strings of the subscription side become garbage
+        eng.remove(f, i); sub.remove(f, i)
+    for t in topics[::3]:
+        eng.retain_remove(t); ret.remove(t)
+    before = eng.stats()
+    eng.compact()
+    after = eng.stats()
+    assert after["dict_entries"] <= before["dict_entries"]
+    assert after["retained_values"] == ret.values_size() and after["retained_nodes"] == ret.nodes_size()
+    eng.retain_set("fresh/topic/after", 424242); ret.insert("fresh/topic/after", 424242)
+    eng.add("fresh/+/after", 7); sub.insert("fresh/+/after", 7)
+    R, t = _tables(eng)
+    _plain_split(eng, R, t, ["$SYS", "$q", "$share"])
+    T = Tables(t)
+    for _ in range(300):
+        q = rand_filter(rng)
+        want = ret.matches(q)
+        if want is not None:
+            assert R.match(q.encode()) == want, q
+        tp = rand_topic(rng)
+        assert T.match(tp.encode())[0] == sub.matches(tp), tp
+    assert R.match(b"fresh/+/after") == ret.matches("fresh/+/after") == [424242]
+    got = T.match(b"fresh/topic/after")[0]
+    assert got == sub.matches("fresh/topic/after") and 7 in got
