@@ -115,6 +115,9 @@ struct gm_engine {
 
     explicit gm_engine(u32 max_levels) : trie(max_levels) {}
 
+    // The view the kernels get is a SNAPSHOT taken when the tables were last shipped (flush): with
+    // GM_FLAG_MANUAL_FLUSH the host mirror may already have grown / re-hashed a table that the device has not seen yet.
+    TrieView dev_view{};
     TrieView view() const {
         TrieView v{};
         v.edges = d_edges.as<EdgeSlot>(); v.ranges = d_ranges.as<Range>();
@@ -230,6 +233,7 @@ struct gm_engine {
             trie.cfilter_dirty = false;
         }
         trie.root_dirty = false;
+        dev_view = view();
         CUDA_TRY(cudaEventRecord(ev_flush, side));
         CUDA_TRY(cudaStreamSynchronize(side));
         return GM_OK;
@@ -242,7 +246,7 @@ struct gm_engine {
         if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
         const u32 n32 = static_cast<u32>(n);
-        const u32 S = std::max<u32>(1u, trie.max_depth);
+        const u32 S = std::max<u32>(1u, dev_view.max_depth);
         CUDA_TRY(d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * n32 * sizeof(u32) : 256));
         CUDA_TRY(d_tok8.ensure(static_cast<size_t>(n32) * TOK8 * sizeof(u32)));
         CUDA_TRY(d_meta.ensure(n32 * sizeof(u32)));
@@ -261,7 +265,7 @@ struct gm_engine {
         u32* hist = d_hist.as<u32>();
         u32* bcursor = hist + NBUCKETS;
         const int k3_blocks = num_sms * 4;
-        const u32 stack_cap = 32u * (trie.max_depth + 2u) + 64u;
+        const u32 stack_cap = 32u * (dev_view.max_depth + 2u) + 64u;
         CUDA_TRY(d_gstack.ensure(static_cast<size_t>(k3_blocks) * 8 * stack_cap * sizeof(u64)));
         const int k2_ctas = (knobs.k2_ctas >= 1 && knobs.k2_ctas <= K2_CTAS_PER_SM) ? knobs.k2_ctas : K2_CTAS_PER_SM;
         const int k2_grid = num_sms * k2_ctas;
@@ -273,7 +277,7 @@ struct gm_engine {
         else CUDA_TRY(cudaMemsetAsync(d_ctrl.p, 0, sizeof(Ctrl), s));
         CUDA_TRY(cudaMemsetAsync(hist, 0, NBUCKETS * sizeof(u32), s));
         Ctrl* ctrl = d_ctrl.as<Ctrl>();
-        const TrieView tv = view();
+        const TrieView tv = dev_view;
 
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
@@ -342,7 +346,7 @@ struct gm_engine {
         u32* qcur = qbase + nq;
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
-        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, view(), S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr, 0u, 0u);
+        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, dev_view, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr, 0u, 0u);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
         RetainParams rp{};
@@ -786,7 +790,7 @@ int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offset
     CUDA_TRY(cudaMemsetAsync(tok.p, 0, static_cast<size_t>(max_tok) * n * sizeof(u32), s));
     CUDA_TRY(cudaStreamWaitEvent(s, e->ev_flush, 0));
     k_tokenize<<<(static_cast<u32>(n) + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->view(), max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr, 0u, 0u);
+        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->dev_view, max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr, 0u, 0u);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_tokens, tok.p, static_cast<size_t>(max_tok) * n * sizeof(u32), cudaMemcpyDeviceToHost, s));

@@ -221,6 +221,28 @@ def test_manual_flush_fence():
     assert eng.matches("a/b") == [2]
 
 
+def test_manual_flush_snapshot_survives_table_growth():
+    """With GM_FLAG_MANUAL_FLUSH the kernels must keep seeing the tables as of the last flush, even when the host
+    mirror has meanwhile re-hashed its edge table / dictionary (new geometry, new window count, deeper filters)."""
+    rng = random.Random(3)
+    eng, old, new = Engine(manual_flush=True), orc.TopicTree(), orc.TopicTree()
+    for i in range(60):
+        f = f"r{i % 5}/s{i % 7}/+/x{i}"
+        eng.add(f, i); old.insert(f, i); new.insert(f, i)
+    eng.flush()
+    before = eng.stats()
+    for i in range(6000):                       # grows edges (1 K slots -> >16 K), the dictionary and max_depth; nothing shipped
+        f = f"r{i % 5}/s{i % 7}/d{i}/x{i % 60}/deep/er/than/before" if i % 3 else f"+/s{i % 7}/n{i}"
+        eng.add(f, 1000 + i); new.insert(f, 1000 + i)
+    assert eng.stats()["edge_slots"] > before["edge_slots"]
+    topics = [f"r{rng.randrange(5)}/s{rng.randrange(7)}/d{rng.randrange(6000)}/x{rng.randrange(60)}" for _ in range(2000)]
+    topics += [f"q/s{rng.randrange(7)}/n{rng.randrange(6000)}" for _ in range(500)]
+    tb, to = pack(topics)
+    _assert_same(eng.match_batch(tb, to), old.match_batch(tb, to))       # staged, not visible
+    eng.flush()
+    _assert_same(eng.match_batch(tb, to), new.match_batch(tb, to))
+
+
 def test_full_size_properties_c3_shape():
     """Size-independent properties at a large size (no oracle): match counts are invariant under batch order;
     adding a `#` subscriber raises every non-`$` topic's count by exactly one; removing it restores them."""
