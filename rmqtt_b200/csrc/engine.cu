@@ -133,8 +133,8 @@ struct gm_engine {
 
     // ---- flush: ship the staged mutations to HBM on the side stream -------------------------------
     // Scatter the listed (already final) host slots into the device copy of the table.
-    template <class T>
-    int patch_table(DevBuf& buf, const std::vector<T>& host, std::vector<u32>& dirty) {
+    template <class T, class A>
+    int patch_table(DevBuf& buf, const std::vector<T, A>& host, std::vector<u32>& dirty) {
         std::sort(dirty.begin(), dirty.end());
         dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
         const u32 nd = static_cast<u32>(dirty.size());
@@ -154,8 +154,8 @@ struct gm_engine {
     }
 
     // Hash tables (edges, dict): whole-table copy after a re-hash or when most of it changed, else patches.
-    template <class Slot>
-    int upload_table(DevBuf& buf, const std::vector<Slot>& host, bool& full, std::vector<u32>& dirty, size_t& up_slots) {
+    template <class Slot, class A>
+    int upload_table(DevBuf& buf, const std::vector<Slot, A>& host, bool& full, std::vector<u32>& dirty, size_t& up_slots) {
         const size_t bytes = host.size() * sizeof(Slot);
         if (full || up_slots != host.size() || dirty.size() * 8 > host.size()) {
             CUDA_TRY(buf.ensure(bytes));
@@ -171,8 +171,8 @@ struct gm_engine {
     }
 
     // Append-only arrays (plus, ranges, values, pool): copy the new tail; patch older entries that changed.
-    template <class T>
-    int upload_appendable(DevBuf& buf, const std::vector<T>& host, size_t& up, std::vector<u32>* dirty) {
+    template <class T, class A>
+    int upload_appendable(DevBuf& buf, const std::vector<T, A>& host, size_t& up, std::vector<u32>* dirty) {
         const size_t bytes = host.size() * sizeof(T);
         if (bytes > buf.cap) {   // grow: re-ship the whole array from the mirror
             CUDA_TRY(buf.ensure(std::max(bytes * 2, size_t(4096))));
@@ -201,8 +201,8 @@ struct gm_engine {
         return v;
     }
 
-    template <class T>
-    int upload_whole(DevBuf& buf, const std::vector<T>& host) {
+    template <class T, class A>
+    int upload_whole(DevBuf& buf, const std::vector<T, A>& host) {
         CUDA_TRY(buf.ensure(std::max<size_t>(host.size() * sizeof(T), 256)));
         if (!host.empty()) CUDA_TRY(cudaMemcpyAsync(buf.p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, side));
         return GM_OK;
@@ -225,9 +225,9 @@ struct gm_engine {
         int st;
         if ((st = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return st;
         if ((st = upload_table(d_dict, trie.dict, trie.full_dict, trie.dirty_dict, up_dict_slots)) != GM_OK) return st;
-        if ((st = upload_appendable<Range>(d_ranges, trie.ranges, up_ranges, nullptr)) != GM_OK) return st;
-        if ((st = upload_appendable<u32>(d_values, trie.values, up_values, nullptr)) != GM_OK) return st;
-        if ((st = upload_appendable<u8>(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return st;
+        if ((st = upload_appendable(d_ranges, trie.ranges, up_ranges, nullptr)) != GM_OK) return st;
+        if ((st = upload_appendable(d_values, trie.values, up_values, nullptr)) != GM_OK) return st;
+        if ((st = upload_appendable(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return st;
         if (trie.cfilter_dirty) {   // child filter of wide nodes: a few MB, shipped whole
             if ((st = upload_whole(d_cfilter, trie.cfilter)) != GM_OK) return st;
             trie.cfilter_dirty = false;
@@ -492,11 +492,9 @@ int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets, co
     std::lock_guard<std::mutex> g(e->mu);
     e->trie.reserve(n);
     uint64_t ok = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        bool ch = false;
-        e->trie.insert(blob + offsets[i], offsets[i + 1] - offsets[i], values[i], &ch);
-        ok += ch;
-    }
+    if (getenv("GM_BULK_ONE_BY_ONE")) {       // A/B switch for the host-side bulk-load measurement
+        for (uint64_t i = 0; i < n; ++i) { bool ch = false; e->trie.insert(blob + offsets[i], offsets[i + 1] - offsets[i], values[i], &ch); ok += ch; }
+    } else ok = e->trie.insert_batch(blob, offsets, values, n);
     if (n_changed) *n_changed = ok;
     return GM_OK;
 }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 namespace gm {
 
@@ -43,6 +44,7 @@ HostTrie::HostTrie(u32 max_levels) : max_levels_(max_levels) {
     nodes_.emplace_back();   // root = node 0
     nodes_[0].alive = 1;
     tag_count_.assign(WTAG_COUNT, 0);
+    tag_anchors_.assign(WTAG_COUNT, 0);
     // tuning / test knobs: cap on log2(#windows) (0 = one window = plain open addressing) and the smallest window
     if (const char* ev = getenv("GM_EDGE_WINDOWS_LOG2")) { int v = atoi(ev); if (v >= 0 && v <= static_cast<int>(WIN_MAX_LOG2)) nwin_cap_log2_ = static_cast<u32>(v); }
     if (const char* ev = getenv("GM_WIN_MIN_SLOTS_LOG2")) { int v = atoi(ev); if (v >= 3 && v <= 30) win_min_log2_ = static_cast<u32>(v); }
@@ -60,7 +62,7 @@ void HostTrie::reserve(u64 n_filters) {
     want_e = std::min<u64>(want_e, 1ull << 31);
     if (edges.size() < want_e) rehash_edges(static_cast<size_t>(want_e));
     while (dict.size() < want_d && dict.size() < (1ull << 31)) grow_dict();
-    nodes_.reserve(nodes_.size() + n_filters * 3);
+    nodes_.reserve(nodes_.size() + n_filters * 3 + n_filters / 2);
 }
 
 u32 HostTrie::level0_hash(const char* s, u32 len) {
@@ -112,7 +114,7 @@ u32 HostTrie::intern(const char* s, u32 len, bool create) {
 }
 
 void HostTrie::grow_dict() {
-    std::vector<DictSlot> old;
+    std::vector<DictSlot, HugeAlloc<DictSlot>> old;
     old.swap(dict);
     dict.assign(old.size() * 2, DictSlot{});
     u32 mask = static_cast<u32>(dict.size() - 1);
@@ -130,9 +132,9 @@ void HostTrie::grow_dict() {
 }
 
 // ------------------------------------------------------------------------------- edges
-u32 HostTrie::find_edge(u32 parent, u32 token) const {
+u32 HostTrie::find_edge(u32 parent, u32 token, u32 wtag) const {
     const u32 wm = win_mask();
-    for (u32 i = edge_slot0(parent, token, nodes_[parent].wtag, wm, win_shift(), nwin_mask());; i = edge_next(i, wm)) {
+    for (u32 i = edge_slot0(parent, token, wtag, wm, win_shift(), nwin_mask());; i = edge_next(i, wm)) {
         const EdgeSlot& e = edges[i];
         if (e.child == 0) return NOSLOT;
         if (e.parent == parent && e.token == token) return i;
@@ -142,10 +144,11 @@ u32 HostTrie::find_edge(u32 parent, u32 token) const {
 // Re-place every edge into a table of `new_size` slots cut into as many windows as the cap and the minimum
 // window size allow.  Tags stay; the effective window is tag & (nwin - 1).
 void HostTrie::rehash_edges(size_t new_size) {
-    std::vector<EdgeSlot> old;
+    std::vector<EdgeSlot, HugeAlloc<EdgeSlot>> old;
     old.swap(edges);
     edges.assign(new_size, EdgeSlot{});
     u32 bits = 0; while ((size_t(1) << bits) < new_size) ++bits;
+    table_log2 = bits;
     nwin_log2 = std::min(nwin_cap_log2_, bits > win_min_log2_ ? bits - win_min_log2_ : 0u);
     win_count_.assign(size_t(1) << nwin_log2, 0);
     const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
@@ -172,23 +175,31 @@ void HostTrie::make_room(u32 wtag) {
     for (;;) {
         const u64 win_slots = edges.size() >> nwin_log2;
         if ((edge_count_ + 1) * 2 <= edges.size() && (win_count_[wtag & nwin_mask()] + 1) * 2 <= win_slots) return;
+        if (getenv("GM_DEBUG_REHASH")) fprintf(stderr, "make_room: tag %u window %u count %llu of %llu slots, edges %llu of %zu, nwin_log2 %u\n", wtag, wtag & nwin_mask(),
+                                               (unsigned long long)win_count_[wtag & nwin_mask()], (unsigned long long)win_slots, (unsigned long long)edge_count_, edges.size(), nwin_log2);
         if ((edge_count_ + 1) * 4 > edges.size() || nwin_log2 == 0) rehash_edges(edges.size() * 2);
         else { win_min_log2_ = win_shift() + 2; rehash_edges(edges.size()); }   // x4 per step: at most 4 re-hashes down to one window
     }
 }
 
-u32 HostTrie::pick_tag() const {
-    // tag 0 = the hot window of the top two levels.  Exact least-loaded choice while depth-2 subtrees are few (they
-    // are created early in a bulk load, when all counts are still tiny: this is what spreads them evenly); the
-    // better of two hashed candidates once there are many (O(1) per new subtree, still balanced).
+u32 HostTrie::pick_tag() {
+    // tag 0 = the hot window of the top two levels.  Load of a tag = its child edges + a nominal weight per subtree
+    // already assigned to it: a new subtree has no edges yet, and a bulk load creates many subtrees back to back
+    // (level-synchronously) before any of their children — counting edges alone would give them all the same tag.
+    // Exact least-loaded choice while subtrees are few; the better of two hashed candidates once there are many
+    // (O(1) per new subtree, still balanced).
+    auto load = [&](u32 t) { return tag_count_[t] + 64u * tag_anchors_[t]; };
+    u32 best = 1;
     if (anchors_ < 4096) {
-        u32 best = 1;
-        for (u32 t = 2; t < WTAG_COUNT; ++t) if (tag_count_[t] < tag_count_[best]) best = t;
-        return best;
+        for (u32 t = 2; t < WTAG_COUNT; ++t) if (load(t) < load(best)) best = t;
+    } else {
+        const u32 h = fmix32(static_cast<u32>(anchors_) * 0x9E3779B1u + 0x7F4A7C15u);
+        const u32 a = 1u + (h & 0xFFFFu) % (WTAG_COUNT - 1), b = 1u + (h >> 16) % (WTAG_COUNT - 1);
+        best = load(b) < load(a) ? b : a;
     }
-    const u32 h = fmix32(static_cast<u32>(anchors_) * 0x9E3779B1u + 0x7F4A7C15u);
-    const u32 a = 1u + (h & 0xFFFFu) % (WTAG_COUNT - 1), b = 1u + (h >> 16) % (WTAG_COUNT - 1);
-    return tag_count_[b] < tag_count_[a] ? b : a;
+    tag_anchors_[best]++;
+    anchors_++;
+    return best;
 }
 
 u32 HostTrie::add_edge(u32 parent, u32 token) {
@@ -203,7 +214,6 @@ u32 HostTrie::add_edge(u32 parent, u32 token) {
     // where this node's OWN children will live: depth 1 -> hot window 0; depth 2 -> a fresh least-loaded window
     // for the whole subtree; deeper -> inherited
     n.wtag = n.depth <= 1 ? 0 : (n.depth == 2 ? static_cast<u8>(pick_tag()) : static_cast<u8>(ptag));
-    if (n.depth == 2) anchors_++;
     const u32 wm = win_mask();
     u32 i = edge_slot0(parent, token, ptag, wm, win_shift(), nwin_mask());
     while (edges[i].child != 0) i = edge_next(i, wm);
@@ -302,16 +312,7 @@ int HostTrie::parse(const char* f, u32 len, bool intern_new, std::vector<u32>& t
 }
 
 // ------------------------------------------------------------------------------- mutations
-int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed) {
-    if (changed) *changed = false;
-    int st = parse(filter, len, true, scratch_toks_);
-    if (st != PARSE_OK) return st;
-    u32 node = 0;
-    for (u32 tok : scratch_toks_) {
-        u32 slot = find_edge(node, tok);
-        node = (slot == NOSLOT) ? add_edge(node, tok) : edges[slot].child;
-    }
-    max_depth = std::max<u32>(max_depth, static_cast<u32>(scratch_toks_.size()));
+bool HostTrie::add_value(u32 node, u32 value) {
     HNode& n = nodes_[node];
     bool ch = false;
     if (n.nvals == 0) { n.v0 = value; n.nvals = 1; ch = true; }
@@ -336,24 +337,92 @@ int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed) {
             nodes_[nodes_[x].parent].live_children++;
             live_nodes_++;
         }
-    } else {
-        // trie.rs:_insert creates the path even when the value was already present; the path exists
-        // and is alive in that case by construction (a present value keeps it alive).
     }
+    // else: trie.rs:_insert creates the path even when the value was already present; the path exists and is alive
+    // in that case by construction (a present value keeps it alive).
+    return ch;
+}
+
+int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed) {
+    if (changed) *changed = false;
+    int st = parse(filter, len, true, scratch_toks_);
+    if (st != PARSE_OK) return st;
+    u32 node = 0, tag = 0;     // the window tag of a node travels in its record (mask word): no lookup in nodes_ per level
+    for (u32 tok : scratch_toks_) {
+        u32 slot = find_edge(node, tok, tag);
+        if (slot == NOSLOT) { node = add_edge(node, tok); tag = nodes_[node].wtag; }
+        else { node = edges[slot].child; tag = edges[slot].mask >> WTAG_SHIFT; }
+    }
+    max_depth = std::max<u32>(max_depth, static_cast<u32>(scratch_toks_.size()));
+    const bool ch = add_value(node, value);
     if (changed) *changed = ch;
     return PARSE_OK;
+}
+
+// Bulk insert (Raft restore / start-up, rmqtt-cluster-raft/src/router.rs:557-561 re-inserts every filter): the same
+// result as n calls of insert(), but walked LEVEL-SYNCHRONOUSLY in groups of 64 filters so that the dependent
+// random probes of the multi-GB edge table overlap: pass 1 of a level prefetches every filter's first probe slot,
+// pass 2 resolves them in order (creating nodes exactly as the one-by-one path would).
+u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n) {
+    constexpr u32 G = 64;
+    u64 changed = 0;
+    std::vector<u32> toks;                    // tokens of the group, concatenated
+    u32 t_off[G + 1], node[G], tag[G];
+    u64 idx[G];
+    for (u64 base = 0; base < n; base += G) {
+        const u32 g = static_cast<u32>(std::min<u64>(G, n - base));
+        toks.clear();
+        u32 m = 0, deepest = 0;
+        t_off[0] = 0;
+        for (u32 j = 0; j < g; ++j) {           // dictionary slots of every level of the group: prefetch before the real parse
+            const char* f = blob + offsets[base + j];
+            const u32 len = offsets[base + j + 1] - offsets[base + j];
+            const u32 dmask = static_cast<u32>(dict.size() - 1);
+            for (u32 a = 0; a <= len;) {
+                u32 b = a;
+                while (b < len && f[b] != '/') ++b;
+                if (b > a) __builtin_prefetch(&dict[dict_index_hash(f + a, b - a) & dmask]);
+                a = b + 1;
+            }
+        }
+        for (u32 j = 0; j < g; ++j) {
+            const u64 i = base + j;
+            if (parse(blob + offsets[i], offsets[i + 1] - offsets[i], true, scratch_toks_) != PARSE_OK) continue;   // invalid: skipped like insert()
+            toks.insert(toks.end(), scratch_toks_.begin(), scratch_toks_.end());
+            idx[m] = i; node[m] = 0; tag[m] = 0;
+            t_off[m + 1] = static_cast<u32>(toks.size());
+            deepest = std::max<u32>(deepest, static_cast<u32>(scratch_toks_.size()));
+            ++m;
+        }
+        for (u32 d = 0; d < deepest; ++d) {
+            const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
+            for (u32 j = 0; j < m; ++j)
+                if (t_off[j] + d < t_off[j + 1]) __builtin_prefetch(&edges[edge_slot0(node[j], toks[t_off[j] + d], tag[j], wm, ws, nm)]);
+            for (u32 j = 0; j < m; ++j) {
+                if (t_off[j] + d >= t_off[j + 1]) continue;
+                const u32 tok = toks[t_off[j] + d];
+                const u32 slot = find_edge(node[j], tok, tag[j]);
+                if (slot == NOSLOT) { node[j] = add_edge(node[j], tok); tag[j] = nodes_[node[j]].wtag; }
+                else { node[j] = edges[slot].child; tag[j] = edges[slot].mask >> WTAG_SHIFT; __builtin_prefetch(&nodes_[node[j]]); }   // add_edge below it / add_value will touch it
+            }
+        }
+        max_depth = std::max<u32>(max_depth, deepest);
+        for (u32 j = 0; j < m; ++j) changed += add_value(node[j], values[idx[j]]) ? 1 : 0;
+    }
+    return changed;
 }
 
 int HostTrie::remove(const char* filter, u32 len, u32 value, bool* changed) {
     if (changed) *changed = false;
     int st = parse(filter, len, false, scratch_toks_);
     if (st != PARSE_OK) return st;
-    u32 node = 0;
+    u32 node = 0, tag = 0;
     for (u32 tok : scratch_toks_) {
         if (tok == TOK_UNKNOWN) return PARSE_OK;
-        u32 slot = find_edge(node, tok);
+        u32 slot = find_edge(node, tok, tag);
         if (slot == NOSLOT) return PARSE_OK;
         node = edges[slot].child;
+        tag = edges[slot].mask >> WTAG_SHIFT;
         if (!nodes_[node].alive) return PARSE_OK;      // pruned in the reference: branches.get_mut -> None
     }
     HNode& n = nodes_[node];
@@ -468,7 +537,12 @@ void HostTrie::sync() {
     }
     std::sort(multi.begin(), multi.end());
     for (const auto& m : multi) make_ref(m.second);
-    for (u32 id : dirty_nodes_) { write_record(id); nodes_[id].dirty = 0; }
+    for (size_t i = 0; i < dirty_nodes_.size(); ++i) {
+        if (i + 16 < dirty_nodes_.size()) __builtin_prefetch(&edges[nodes_[dirty_nodes_[i + 16]].edge_slot], 1);   // records land in random slots
+        const u32 id = dirty_nodes_[i];
+        write_record(id);
+        nodes_[id].dirty = 0;
+    }
     dirty_nodes_.clear();
 }
 

@@ -10,6 +10,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "huge_alloc.h"
 #include "layout.h"
 
 namespace gm {
@@ -43,6 +44,8 @@ class HostTrie {
     // TopicTree::insert / remove.  Return ParseStatus; *changed mirrors the reference's bool.
     int insert(const char* filter, u32 len, u32 value, bool* changed);
     int remove(const char* filter, u32 len, u32 value, bool* changed);
+    // n inserts (invalid filters are skipped); returns how many changed the set.  Same result as one-by-one insert().
+    u64 insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n);
     void reserve(u64 n_filters);
 
     // Resolve dirty nodes into slot patches (called by flush).
@@ -58,10 +61,10 @@ class HostTrie {
     u64 nodes_size() const { return live_nodes_; }     // trie.rs:154-157
 
     // ---- device mirror -------------------------------------------------------------------------
-    std::vector<EdgeSlot> edges;
+    std::vector<EdgeSlot, HugeAlloc<EdgeSlot>> edges;
     std::vector<Range> ranges;       // [0] reserved
     std::vector<u32> values;
-    std::vector<DictSlot> dict;
+    std::vector<DictSlot, HugeAlloc<DictSlot>> dict;
     std::vector<u8> pool;
     std::vector<u32> cfilter;        // child filter of wide nodes (layout.h)
     bool cfilter_dirty = true;
@@ -69,7 +72,8 @@ class HostTrie {
     u32 max_depth = 0;
     // window geometry of `edges` (layout.h): windows = 1 << nwin_log2, each edges.size() >> nwin_log2 slots
     u32 nwin_log2 = 0;
-    u32 win_shift() const { u32 b = 0; while ((size_t(1) << b) < edges.size()) ++b; return b - nwin_log2; }
+    u32 table_log2 = 10;      // log2(edges.size()), kept by rehash_edges
+    u32 win_shift() const { return table_log2 - nwin_log2; }
     u32 win_mask() const { return (1u << win_shift()) - 1u; }
     u32 nwin_mask() const { return (1u << nwin_log2) - 1u; }
 
@@ -96,12 +100,13 @@ class HostTrie {
 
   private:
     u32 intern(const char* s, u32 len, bool create);
-    u32 find_edge(u32 parent, u32 token) const;         // returns slot index or ~0u
+    u32 find_edge(u32 parent, u32 token, u32 wtag) const;   // returns slot index or ~0u; wtag = window tag of `parent`
     u32 add_edge(u32 parent, u32 token);                // creates the child node, returns its id
+    bool add_value(u32 node, u32 value);                // BTreeSet::insert on the node's value set
     void grow_edges() { rehash_edges(edges.size() * 2); }
     void rehash_edges(size_t new_size);                 // re-places every edge (new size and / or new window count)
     void make_room(u32 wtag);                           // before an insertion into the window of `wtag`
-    u32 pick_tag() const;                               // least-loaded window tag for a new depth-2 subtree
+    u32 pick_tag();                                     // least-loaded window tag for a new depth-2 subtree
     void grow_dict();
     void mark(u32 node);
     void make_ref(u32 node);
@@ -112,7 +117,7 @@ class HostTrie {
     u64 cfilter_keys_ = 0;
 
     u32 max_levels_;
-    std::vector<HNode> nodes_;
+    std::vector<HNode, HugeAlloc<HNode>> nodes_;
     std::unordered_map<u32, std::vector<u32>> multi_;   // node -> sorted values when nvals > 1
     std::vector<u32> dirty_nodes_;
     std::vector<u32> scratch_toks_;
@@ -121,6 +126,7 @@ class HostTrie {
     u32 nwin_cap_log2_ = WIN_MAX_LOG2;
     u32 win_min_log2_ = WIN_MIN_SLOTS_LOG2;   // raised when one subtree outgrows its window
     std::vector<u64> tag_count_;         // edges per window tag (WTAG_COUNT entries)
+    std::vector<u64> tag_anchors_;       // depth-2 subtrees assigned per window tag
     std::vector<u64> win_count_;         // edges per effective window
     u32 next_token_ = TOK_FIRST;
     u64 values_size_ = 0, live_nodes_ = 0;

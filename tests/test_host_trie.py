@@ -208,3 +208,34 @@ def test_windowed_edge_table_vs_oracle(monkeypatch, win_min, cap):
     for _ in range(200):
         t = "/".join([f"r{rng.randrange(6)}", f"s{rng.randrange(6)}"] + [f"x{rng.randrange(5)}" for _ in range(rng.randrange(0, 4))])
         assert T.match(t.encode())[0] == tree.matches(t), t
+
+
+def test_bulk_load_equals_one_by_one_inserts():
+    """gm_bulk_load walks groups of 64 filters level-synchronously (prefetching); the result must be the trie that
+    one-by-one inserts build: same reference statistics, same matches, invalid filters skipped, duplicates kept once."""
+    import numpy as np
+    from rmqtt_b200.engine import pack
+    rng = random.Random(41)
+    fs = [rand_filter(rng) for _ in range(5000)] + ["a/b/#/c", "x/+y", "dup/f", "dup/f", "r/s/t", "r/s/t"]
+    rng.shuffle(fs)
+    vals = [rng.randint(0, 20) for _ in fs]
+    tree = orc.TopicTree()
+    one = Engine(host_only=True)
+    n_changed = 0
+    for f, v in zip(fs, vals):
+        try:
+            n_changed += bool(one.add(f, v))
+        except GpuMqttError:
+            continue
+        tree.insert(f, v)
+    blob, offs = pack(fs)
+    bulk = Engine(host_only=True)
+    assert bulk.bulk_load(blob, offs, np.asarray(vals, dtype=np.uint32)) == n_changed
+    sa, sb = one.stats(), bulk.stats()
+    for k in ("values", "nodes", "edges", "dict_entries", "plus_nodes", "max_depth"):
+        assert sa[k] == sb[k], k
+    assert sb["values"] == tree.values_size() and sb["nodes"] == tree.nodes_size()
+    T = Tables(bulk.debug_tables())
+    for _ in range(400):
+        t = rand_topic(rng)
+        assert T.match(t.encode())[0] == tree.matches(t), t
