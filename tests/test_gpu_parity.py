@@ -243,6 +243,28 @@ def test_manual_flush_snapshot_survives_table_growth():
     _assert_same(eng.match_batch(tb, to), new.match_batch(tb, to))
 
 
+def test_acl_rule_tree_shape():
+    """SURVEY §8(f) rank 2 — other TopicTree<V> users ride the same ABI: an ACL rule set is a small tree of topic
+    filters (rmqtt-plugins/rmqtt-acl/src/config.rs:291-326) asked `is_match(topic)` on every PUBLISH / SUBSCRIBE;
+    one engine per rule tree, is_match == "the match list is non-empty" (trie.rs:138-140)."""
+    rng = random.Random(9)
+    allow, deny, o_allow, o_deny = Engine(), Engine(), orc.TopicTree(), orc.TopicTree()
+    for i in range(200):
+        f = rand_filter(rng, 4)
+        eng, tree = (allow, o_allow) if i % 3 else (deny, o_deny)
+        try:
+            eng.add(f, i)
+        except GpuMqttError:
+            continue
+        tree.insert(f, i)
+    topics = [rand_topic(rng, 5) for _ in range(4000)]
+    tb, to = pack(topics)
+    for eng, tree in ((allow, o_allow), (deny, o_deny)):
+        got = eng.match_batch(tb, to).counts()
+        want = tree.match_batch(tb, to, want_ids=False)["counts"]
+        assert ((got > 0) == (want > 0)).all() and (got == want).all()
+
+
 def test_full_size_properties_c3_shape():
     """Size-independent properties at a large size (no oracle): match counts are invariant under batch order;
     adding a `#` subscriber raises every non-`$` topic's count by exactly one; removing it restores them."""

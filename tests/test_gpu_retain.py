@@ -95,3 +95,32 @@ def test_capacity_protocol_and_subscription_trie_coexist():
     res = eng.retain_match_batch(fb, fo)
     assert res.sorted_list(0) == list(range(300)) and res.sorted_list(1) == [] and res.sorted_list(2) is None and res.sorted_list(3) == [5]
     assert eng.matches("a/17") == [7]
+
+
+def test_message_storage_shape():
+    """SURVEY §8(f) rank 3 — the message-storage plugin keeps a RetainTree<MsgID> keyed by `topic/<msg_id>`
+    (rmqtt-plugins/rmqtt-message-storage/src/ram.rs:268-269, 294) and looks it up with the SUBSCRIBE filter plus one
+    trailing `+` unless the filter ends in `#` (ram.rs:311-314): the same retained kernel with msg ids as values."""
+    rng = random.Random(31)
+    eng, tree = Engine(), orc.RetainTree()
+    msg_id = 1
+    stored = []
+    for _ in range(3000):
+        t = rand_topic(rng, 5)
+        if orc.topic_parse(t) is None or "#" in t.split("/"):     # the reference pushes the id level without re-validating;
+            continue                                              # through the string ABI a `#` level must stay last
+        for _ in range(rng.randint(1, 3)):                       # several stored messages per topic
+            key = f"{t}/{msg_id}"
+            eng.retain_set(key, msg_id); tree.insert(key, msg_id)
+            stored.append(key)
+            msg_id += 1
+    for key in stored[::4]:                                       # expiry (ram.rs:185)
+        eng.retain_remove(key); tree.remove(key)
+    filters = []
+    for _ in range(1500):
+        f = rand_filter(rng, 5)
+        if orc.topic_parse(f) is None:
+            continue
+        filters.append(f if f.split("/")[-1] == "#" else f + "/+")
+    fb, fo = pack(filters)
+    _assert_same(eng.retain_match_batch(fb, fo), tree.match_batch(fb, fo))
