@@ -200,7 +200,8 @@ uint32_t gm_shard_of(const char* topic_or_filter, uint32_t len, uint32_t n_shard
 /* DEBUG/TEST: read-only view of the host mirror of a device table, in device layout (rmqtt_b200/csrc/layout.h).
  * which: 0 edges(32 B) 2 ranges(8 B) 3 values(4 B) 4 dict(32 B) 5 long-string pool(1 B)
  *        6 root record {plus, hash_ref, mask, max_depth, hash_cnt, win_mask, win_shift, nwin_mask}; retained tree: 7 nodes(32 B, host bookkeeping) 8 child blocks(32 B entries)
- *        9 pre-order values(4 B); 12 child filter of wide nodes (4 B words).  Valid until the next mutating call.                                       */
+ *        9 pre-order values(4 B); 10 (parent, token) hash slots (32 B); 11 maintenance counters (6 x u64: full rebuilds, in-place
+ *        patches, garbage child entries, dead nodes, hash entries, image valid); 12 child filter of wide nodes (4 B words).  Valid until the next mutating call.                                       */
 int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t* count);
 /* DEBUG/TUNING: set a kernel-scheduling knob of this engine at run time (A/B measurements; results never change).
  * "tile_chunk" (1..1024: consecutive 32-topic tiles a CTA of the match kernel reserves at once), "k2_ctas" (0 = default),

@@ -118,6 +118,8 @@ struct gm_engine {
     // The view the kernels get is a SNAPSHOT taken when the tables were last shipped (flush): with
     // GM_FLAG_MANUAL_FLUSH the host mirror may already have grown / re-hashed a table that the device has not seen yet.
     TrieView dev_view{};
+    RetainView dev_rview{};
+    size_t up_rkids = 0, up_rvals = 0, up_redges_slots = 0;
     TrieView view() const {
         TrieView v{};
         v.edges = d_edges.as<EdgeSlot>(); v.ranges = d_ranges.as<Range>();
@@ -202,25 +204,34 @@ struct gm_engine {
     }
 
     template <class T, class A>
-    int upload_whole(DevBuf& buf, const std::vector<T, A>& host) {
-        CUDA_TRY(buf.ensure(std::max<size_t>(host.size() * sizeof(T), 256)));
+    int upload_whole(DevBuf& buf, const std::vector<T, A>& host, size_t slack_elems = 0) {
+        CUDA_TRY(buf.ensure(std::max<size_t>((host.size() + slack_elems) * sizeof(T), 256)));
         if (!host.empty()) CUDA_TRY(cudaMemcpyAsync(buf.p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, side));
         return GM_OK;
     }
 
     int flush_locked() {
-        if (flags & GM_FLAG_HOST_ONLY) { trie.sync(); if (rtree.dirty) rtree.flatten(); return GM_OK; }
+        if (flags & GM_FLAG_HOST_ONLY) { trie.sync(); if (rtree.dirty) { rtree.prepare_flush(); rtree.shipped(); } return GM_OK; }
         if (!trie.any_dirty() && !rtree.dirty) return GM_OK;
         CUDA_TRY(cudaSetDevice(device));
         trie.sync();
         if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(side, ev_match, 0));   // never patch under a running match
-        if (rtree.dirty) {   // retained tree: re-flattened and shipped whole (pre-order layout; delta overlay is future work)
-            rtree.flatten();
+        if (rtree.dirty) {   // retained tree: whole arrays after a (re)flatten, else only the entries set / remove edited in place
+            rtree.prepare_flush();
             int rs;
-            if ((rs = upload_whole(d_rnodes, std::vector<u32>{0u})) != GM_OK) return rs;   // marker: "retained tree shipped" (records travel in rkids / redges)
-            if ((rs = upload_whole(d_rkids, rtree.rkids)) != GM_OK) return rs;
-            if ((rs = upload_whole(d_redges, rtree.redges)) != GM_OK) return rs;
-            if ((rs = upload_whole(d_rvals, rtree.rvals)) != GM_OK) return rs;
+            if (rtree.full) {
+                if ((rs = upload_whole(d_rnodes, std::vector<u32>{0u})) != GM_OK) return rs;   // marker: "retained tree shipped" (records travel in rkids / redges)
+                if ((rs = upload_whole(d_rkids, rtree.rkids, rtree.rkids.size() / 4 + 1024)) != GM_OK) return rs;   // room for in-place appends
+                if ((rs = upload_whole(d_redges, rtree.redges)) != GM_OK) return rs;
+                if ((rs = upload_whole(d_rvals, rtree.rvals)) != GM_OK) return rs;
+                up_rkids = rtree.rkids.size(); up_rvals = rtree.rvals.size(); up_redges_slots = rtree.redges.size();
+            } else {
+                bool full_edges = false;
+                if ((rs = upload_appendable(d_rkids, rtree.rkids, up_rkids, &rtree.dirty_kids)) != GM_OK) return rs;
+                if ((rs = upload_table(d_redges, rtree.redges, full_edges, rtree.dirty_edges, up_redges_slots)) != GM_OK) return rs;
+                if ((rs = upload_appendable(d_rvals, rtree.rvals, up_rvals, &rtree.dirty_vals)) != GM_OK) return rs;
+            }
+            rtree.shipped();
         }
         int st;
         if ((st = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return st;
@@ -234,6 +245,7 @@ struct gm_engine {
         }
         trie.root_dirty = false;
         dev_view = view();
+        dev_rview = rview();
         CUDA_TRY(cudaEventRecord(ev_flush, side));
         CUDA_TRY(cudaStreamSynchronize(side));
         return GM_OK;
@@ -324,7 +336,7 @@ struct gm_engine {
 
     int enqueue_retain(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s) {
         const u32 nq = static_cast<u32>(n);
-        const u32 depth = rtree.max_depth;
+        const u32 depth = dev_rview.max_depth;
         const u32 S = depth + 2;                       // the walk reads filter levels pos and pos+1 with pos <= tree depth
         const size_t ctl_bytes = sizeof(RCtl) + static_cast<size_t>(depth + 3) * RQ * sizeof(u32);
         CUDA_TRY(d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * nq * sizeof(u32) : 256));
@@ -350,7 +362,7 @@ struct gm_engine {
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
         RetainParams rp{};
-        rp.v = rview(); rp.qtok8 = d_tok8.as<u32>(); rp.qtok = d_tok.as<u32>(); rp.qmeta = d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
+        rp.v = dev_rview; rp.qtok8 = d_tok8.as<u32>(); rp.qtok = d_tok.as<u32>(); rp.qmeta = d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
         rp.descs = d_rdescs.as<RDesc>(); rp.n_desc = ctl->n_desc; rp.cap_items = slice_items; rp.cap_desc = slice_desc;
         rp.qtotal = qtotal; rp.err = &ctl->err;
         k_retain_init<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RItem>(), &ctl->counts[0]);
@@ -844,6 +856,7 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
     e->trie.sync();
     const HostTrie& t = e->trie;
     static thread_local uint32_t root[8];
+    static thread_local uint64_t rstat[6];
     switch (which) {
         case 0: *ptr = t.edges.data(); *count = t.edges.size(); break;
         case 2: *ptr = t.ranges.data(); *count = t.ranges.size(); break;
@@ -853,9 +866,11 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
         case 6: root[0] = t.root_plus; root[1] = t.root_hash_ref; root[2] = t.root_mask; root[3] = t.max_depth; root[4] = t.root_hash_cnt;
                 root[5] = t.win_mask(); root[6] = t.win_shift(); root[7] = t.nwin_mask(); *ptr = root; *count = 8; break;
         case 12: *ptr = t.cfilter.data(); *count = t.cfilter.size(); break;
-        case 7: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rnodes.data(); *count = e->rtree.rnodes.size(); break;
-        case 8: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rkids.data(); *count = e->rtree.rkids.size(); break;
-        case 9: if (e->rtree.dirty) e->rtree.flatten(); *ptr = e->rtree.rvals.data(); *count = e->rtree.rvals.size(); break;
+        case 10: e->rtree.prepare_flush(); *ptr = e->rtree.redges.data(); *count = e->rtree.redges.size(); break;
+        case 11: e->rtree.debug_stats(rstat); *ptr = rstat; *count = 6; break;
+        case 7: e->rtree.prepare_flush(); *ptr = e->rtree.rnodes.data(); *count = e->rtree.rnodes.size(); break;
+        case 8: e->rtree.prepare_flush(); *ptr = e->rtree.rkids.data(); *count = e->rtree.rkids.size(); break;
+        case 9: e->rtree.prepare_flush(); *ptr = e->rtree.rvals.data(); *count = e->rtree.rvals.size(); break;
         default: return GM_ERR_INVALID_ARG;
     }
     return GM_OK;

@@ -21,6 +21,7 @@ int RetainTreeHost::set(const char* topic, u32 len, u32 value, bool* had_old, u3
     int st = parse(topic, len, true, toks_);
     if (st != PARSE_OK) return st;
     u32 node = 0;
+    bool created = false;
     for (u32 tok : toks_) {
         u32 c = child_of(node, tok);
         if (!c) {
@@ -30,17 +31,21 @@ int RetainTreeHost::set(const char* topic, u32 len, u32 value, bool* had_old, u3
             auto& k = nodes_[node].kids;
             k.insert(std::lower_bound(k.begin(), k.end(), std::make_pair(tok, 0u)), std::make_pair(tok, c));
             n_nodes_++;
+            created = true;
+            if (flat_valid_ && (tok == TOK_PLUS || tok == TOK_HASH)) give_up();   // a literal '+' / '#' level changes shadow flags: rebuild
         }
         node = c;
     }
     HN& n = nodes_[node];
-    // Re-publishing a retained message on a topic that keeps its handle changes nothing on the device: the
-    // device copy is only rebuilt when the set of retained topics (or a handle) actually changes.
+    // Re-publishing a retained message on a topic that keeps its handle changes nothing on the device.
     const bool same = n.has_val && n.val == value;
+    const bool had = n.has_val;
     if (n.has_val) { if (had_old) *had_old = true; if (old) *old = n.val; }
     else n_values_++;
     n.has_val = true; n.val = value;
-    if (!same) dirty = true;
+    if (same && !created) return PARSE_OK;
+    dirty = true;
+    if (flat_valid_) dev_set(node, had, value, static_cast<u32>(toks_.size()));
     return PARSE_OK;
 }
 
@@ -61,6 +66,7 @@ int RetainTreeHost::remove(const char* topic, u32 len, bool* had_old, u32* old) 
         n.has_val = false; n.val = RVAL_NONE;
         n_values_--;
         dirty = true;
+        if (flat_valid_) dev_unset(node);
     }
     // prune (retain.rs:247-249): value.is_none() && branches.is_empty()
     for (u32 x = node; x != 0;) {
@@ -69,12 +75,149 @@ int RetainTreeHost::remove(const char* topic, u32 len, bool* had_old, u32* old) 
         u32 p = c.parent;
         auto& k = nodes_[p].kids;
         k.erase(std::lower_bound(k.begin(), k.end(), std::make_pair(c.token, 0u)));
+        if (flat_valid_) {
+            // its device node stays behind as a dead leaf (revived if the path is set again); a literal '+' / '#'
+            // level would keep shadowing wildcard expansion -> rebuild
+            if (c.token == TOK_PLUS || c.token == TOK_HASH) give_up(); else dead_nodes_++;
+        }
         free_.push_back(x);
         n_nodes_--;
         dirty = true;
         x = p;
     }
     return PARSE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// In-place maintenance of the device image (see retain_tree.h)
+u32 RetainTreeHost::edge_slot_of(u32 parent_dev, u32 token) const {
+    const u32 mask = static_cast<u32>(redges.size() - 1);
+    for (u32 s = redge_hash(parent_dev, token) & mask;; s = (s + 1) & mask) {
+        const REdge& e = redges[s];
+        if (e.child == 0) return NODEV;
+        if (e.parent == parent_dev && e.token == token) return s;
+    }
+}
+
+void RetainTreeHost::write_record(u32 dev) {
+    if (dev == 0) return;                       // the root's record travels in the kernel parameters (rnodes[0])
+    const RNode& r = rnodes[dev];
+    const u32 pdev = rparent_[dev], tok = rtoken_[dev];
+    const RNode& p = rnodes[pdev];
+    for (u32 j = 0; j < p.nkids; ++j) {
+        RKid& k = rkids[p.first_kid + j];
+        if (k.child != dev) continue;
+        k.first_kid = r.first_kid; k.nk_flags = r.nkids | (r.flags << 28); k.val = r.val; k.val_lo = r.val_lo; k.val_hi = r.val_hi;
+        dirty_kids.push_back(p.first_kid + j);
+        break;
+    }
+    const u32 s = edge_slot_of(pdev, tok);
+    if (s != NODEV) {
+        REdge& e = redges[s];
+        e.first_kid = r.first_kid; e.nk_flags = r.nkids | (r.flags << 28); e.val = r.val; e.val_lo = r.val_lo; e.val_hi = r.val_hi;
+        dirty_edges.push_back(s);
+    }
+    patches++;
+}
+
+void RetainTreeHost::invalidate_ranges(u32 dev) {
+    for (u32 x = dev;; x = rparent_[x]) {
+        RNode& r = rnodes[x];
+        if (r.flags & RF_SUB_LIT_HASH) break;   // invariant: a flagged node has flagged ancestors
+        r.flags |= RF_SUB_LIT_HASH;
+        write_record(x);
+        if (x == 0) break;
+    }
+}
+
+u32 RetainTreeHost::dev_new_node(u32 parent_dev, u32 token) {
+    const u32 dev = static_cast<u32>(rnodes.size());
+    RNode r{};
+    r.val = RVAL_NONE;
+    r.flags = RF_SUB_LIT_HASH;                  // it has no value range of its own
+    rnodes.push_back(r);
+    rparent_.push_back(parent_dev); rtoken_.push_back(token); rcap_.push_back(0); in_rvals_.push_back(0);
+    return dev;
+}
+
+bool RetainTreeHost::dev_add_child(u32 pdev, u32 tok, u32 cdev) {
+    if ((live_edges_ + 1) * 2 > redges.size()) return false;                // keep the hash table at most half full
+    if (rcap_[pdev] == rnodes[pdev].nkids) {                                   // child block full: move it to the end, doubled
+        const u32 oldcap = rcap_[pdev], newcap = std::max<u32>(2u, oldcap * 2u);
+        if (rkids.size() + newcap > 0xFFFFFFF0ull) return false;
+        const u32 nf = static_cast<u32>(rkids.size());
+        rkids.resize(rkids.size() + newcap, RKid{0, 0, 0, 0, RVAL_NONE, 0, 0, 0});
+        const u32 of = rnodes[pdev].first_kid;
+        for (u32 j = 0; j < rnodes[pdev].nkids; ++j) rkids[nf + j] = rkids[of + j];
+        garbage_kids_ += oldcap;
+        rnodes[pdev].first_kid = nf;
+        rcap_[pdev] = newcap;
+    }
+    RNode& p = rnodes[pdev];
+    const RNode& c = rnodes[cdev];
+    u32 idx = p.first_kid + p.nkids;
+    if (pdev == 0 && !dict_->token_is_dollar(tok)) {                          // root children: plain first, `$...` last
+        if (root_plain_kids < p.nkids) { rkids[idx] = rkids[p.first_kid + root_plain_kids]; dirty_kids.push_back(idx); idx = p.first_kid + root_plain_kids; }
+        root_plain_kids++;
+    }
+    rkids[idx] = RKid{tok, cdev, c.first_kid, c.nkids | (c.flags << 28), c.val, c.val_lo, c.val_hi, 0};
+    dirty_kids.push_back(idx);
+    p.nkids++;
+    const u32 mask = static_cast<u32>(redges.size() - 1);
+    u32 s = redge_hash(pdev, tok) & mask;
+    while (redges[s].child != 0) s = (s + 1) & mask;
+    redges[s] = REdge{pdev, tok, cdev, c.first_kid, c.nkids | (c.flags << 28), c.val, c.val_lo, c.val_hi};
+    dirty_edges.push_back(s);
+    live_edges_++;
+    write_record(pdev);                          // its block moved / grew
+    invalidate_ranges(pdev);
+    return true;
+}
+
+void RetainTreeHost::dev_set(u32 node, bool had, u32 value, u32 depth) {
+    // device nodes for the part of the path that is new to the device (top-down)
+    std::vector<u32> missing;
+    for (u32 x = node; nodes_[x].dev == NODEV && x != 0; x = nodes_[x].parent) missing.push_back(x);
+    for (size_t i = missing.size(); i-- > 0 && flat_valid_;) {
+        const u32 m = missing[i];
+        const u32 pdev = nodes_[nodes_[m].parent].dev, tok = nodes_[m].token;
+        const u32 s = edge_slot_of(pdev, tok);
+        if (s != NODEV) { nodes_[m].dev = redges[s].child; if (dead_nodes_) dead_nodes_--; }          // a dead leaf left by an earlier prune
+        else {
+            const u32 cdev = dev_new_node(pdev, tok);
+            if (!dev_add_child(pdev, tok, cdev)) { give_up(); return; }
+            nodes_[m].dev = cdev;
+        }
+    }
+    if (!flat_valid_) return;
+    const u32 dev = nodes_[node].dev;
+    RNode& r = rnodes[dev];
+    r.val = value;
+    if (had) {                                   // value.replace(v): same shape, same ranges
+        if (in_rvals_[dev]) { rvals[r.val_lo] = value; dirty_vals.push_back(r.val_lo); }
+        write_record(dev);
+    } else {
+        r.flags |= 8u;
+        write_record(dev);
+        invalidate_ranges(dev);
+    }
+    max_depth = std::max(max_depth, depth);
+}
+
+void RetainTreeHost::dev_unset(u32 node) {
+    const u32 dev = nodes_[node].dev;
+    if (dev == NODEV) { give_up(); return; }
+    RNode& r = rnodes[dev];
+    r.val = RVAL_NONE;
+    r.flags &= ~8u;
+    in_rvals_[dev] = 0;
+    write_record(dev);
+    invalidate_ranges(dev);
+}
+
+void RetainTreeHost::prepare_flush() {
+    if (flat_valid_ && (garbage_kids_ + dead_nodes_) * 4 > rkids.size() + 4096) give_up();     // too much garbage: re-pack
+    if (!flat_valid_) flatten();
 }
 
 std::vector<u32> RetainTreeHost::used_tokens() const {
@@ -100,15 +243,23 @@ void RetainTreeHost::remap_tokens(const std::vector<u32>& remap) {
         }
         std::sort(nodes_[n].kids.begin(), nodes_[n].kids.end());
     }
-    dirty = true;
+    give_up();                                   // every token in the device image changed
 }
 
 void RetainTreeHost::flatten() {
     rnodes.clear(); rkids.clear(); rvals.clear();
-    rnodes.reserve(n_nodes_ + 1); rkids.reserve(n_nodes_ + 1); rvals.reserve(n_values_);
+    rparent_.clear(); rtoken_.clear(); rcap_.clear(); in_rvals_.clear();
+    rparent_.reserve(n_nodes_ + n_nodes_ / 4 + 1024); rtoken_.reserve(n_nodes_ + n_nodes_ / 4 + 1024);
+    rcap_.reserve(n_nodes_ + n_nodes_ / 4 + 1024); in_rvals_.reserve(n_nodes_ + n_nodes_ / 4 + 1024);
+    // a quarter of slack: in-place edits append device nodes and relocated child blocks until the next re-pack
+    const size_t room = n_nodes_ + n_nodes_ / 4 + 1024;
+    rnodes.reserve(room); rkids.reserve(room); rvals.reserve(n_values_);
     max_depth = 0;
     // iterative pre-order DFS; root children ordered plain-first, `$`-prefixed last (retain.rs:327-331, 345-349)
-    struct Frame { u32 host, dev, next, depth; std::vector<std::pair<u32, u32>> order; };
+    using Kids = std::vector<std::pair<u32, u32>>;
+    struct Frame { u32 host, dev, next, depth; const Kids* order; };
+    Kids root_order = nodes_[0].kids;
+    std::stable_partition(root_order.begin(), root_order.end(), [&](const std::pair<u32, u32>& kv) { return !dict_->token_is_dollar(kv.first); });
     std::vector<Frame> stack;
     auto open = [&](u32 host, u32 depth) {
         const HN& h = nodes_[host];
@@ -119,32 +270,33 @@ void RetainTreeHost::flatten() {
         r.val = h.has_val ? h.val : RVAL_NONE;
         r.val_lo = static_cast<u32>(rvals.size());
         r.flags = h.has_val ? 8u : 0u;
-        rnodes.push_back(r);
-        if (h.has_val) rvals.push_back(h.val);
-        Frame f{host, dev, 0, depth, h.kids};
-        if (host == 0)
-            std::stable_partition(f.order.begin(), f.order.end(), [&](const std::pair<u32, u32>& kv) { return !dict_->token_is_dollar(kv.first); });
-        for (auto& kv : f.order) {
-            if (kv.first == TOK_PLUS) rnodes[dev].flags |= RF_LIT_PLUS;
-            if (kv.first == TOK_HASH) rnodes[dev].flags |= RF_LIT_HASH | RF_SUB_LIT_HASH;
+        const Kids* order = host == 0 ? &root_order : &h.kids;       // no per-node copy: the host tree is not touched while flattening
+        for (const auto& kv : *order) {
+            if (kv.first == TOK_PLUS) r.flags |= RF_LIT_PLUS;
+            if (kv.first == TOK_HASH) r.flags |= RF_LIT_HASH | RF_SUB_LIT_HASH;
         }
-        rkids.resize(rkids.size() + f.order.size());
+        rnodes.push_back(r);
+        rparent_.push_back(host == 0 ? 0u : nodes_[h.parent].dev); rtoken_.push_back(h.token);
+        rcap_.push_back(r.nkids); in_rvals_.push_back(h.has_val ? 1 : 0);
+        nodes_[host].dev = dev;
+        if (h.has_val) rvals.push_back(h.val);
+        rkids.resize(rkids.size() + order->size());
         max_depth = std::max(max_depth, depth);
-        stack.push_back(std::move(f));
+        stack.push_back(Frame{host, dev, 0, depth, order});
     };
     open(0, 0);
     root_plain_kids = 0;
-    for (auto& kv : stack.back().order) if (!dict_->token_is_dollar(kv.first)) root_plain_kids++;
+    for (const auto& kv : root_order) if (!dict_->token_is_dollar(kv.first)) root_plain_kids++;
     root_plain_val_hi = 0;
     while (!stack.empty()) {
         Frame& f = stack.back();
-        if (f.next < f.order.size()) {
+        if (f.next < f.order->size()) {
             u32 j = f.next++;
             if (f.host == 0 && j == root_plain_kids) root_plain_val_hi = static_cast<u32>(rvals.size());
-            u32 child_host = f.order[j].second;
+            u32 child_host = (*f.order)[j].second;
             u32 child_dev = static_cast<u32>(rnodes.size());
             RKid& k = rkids[rnodes[f.dev].first_kid + j];
-            k.token = f.order[j].first;
+            k.token = (*f.order)[j].first;
             k.child = child_dev;                    // the child's record is copied in below, once its subtree is complete
             open(child_host, f.depth + 1);          // invalidates `f`
         } else {
@@ -169,16 +321,27 @@ void RetainTreeHost::flatten() {
     while (cap < rkids.size() * 4) cap <<= 1;
     redges.assign(cap, REdge{0, 0, 0, 0, 0, 0, 0, 0});
     const u32 mask = static_cast<u32>(cap - 1);
-    for (u32 n = 0; n < rnodes.size(); ++n) {
-        const RNode& r = rnodes[n];
-        for (u32 j = 0; j < r.nkids; ++j) {
-            const RKid& k = rkids[r.first_kid + j];
-            u32 i = redge_hash(n, k.token) & mask;
-            while (redges[i].child != 0) i = (i + 1) & mask;
-            redges[i] = REdge{n, k.token, k.child, k.first_kid, k.nk_flags, k.val, k.val_lo, k.val_hi};
-        }
+    // every child entry names its parent implicitly (block of node n): walk nodes, insert their blocks; the first
+    // probe slot of the entry 16 ahead is prefetched (the table is far larger than the caches)
+    std::vector<u32> parent_of(rkids.size());
+    for (u32 n = 0; n < rnodes.size(); ++n)
+        for (u32 j = 0; j < rnodes[n].nkids; ++j) parent_of[rnodes[n].first_kid + j] = n;
+    for (size_t i = 0; i < rkids.size(); ++i) {
+        if (i + 16 < rkids.size()) __builtin_prefetch(&redges[redge_hash(parent_of[i + 16], rkids[i + 16].token) & mask], 1);
+        const RKid& k = rkids[i];
+        const u32 n = parent_of[i];
+        u32 s = redge_hash(n, k.token) & mask;
+        while (redges[s].child != 0) s = (s + 1) & mask;
+        redges[s] = REdge{n, k.token, k.child, k.first_kid, k.nk_flags, k.val, k.val_lo, k.val_hi};
     }
-    dirty = false;
+    // the image is current and packed: ship it whole; from here on set / remove edit it in place
+    flat_valid_ = true;
+    full = true;
+    dirty = true;
+    dirty_kids.clear(); dirty_edges.clear(); dirty_vals.clear();
+    garbage_kids_ = 0; dead_nodes_ = 0;
+    live_edges_ = rkids.size();
+    flattens++;
 }
 
 }  // namespace gm

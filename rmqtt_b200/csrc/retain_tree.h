@@ -1,8 +1,8 @@
 // Host mirror + device layout of the retained-message tree (rmqtt/src/retain.rs:202-257).
 //
 // The tree is keyed by CONCRETE topics (one optional value per node); queries are topic FILTERS:
-// '+' = every child, '#' = the whole subtree (retain.rs:298-367).  Device layout (rebuilt by `flatten`
-// whenever the tree changed, shipped by the engine's flush):
+// '+' = every child, '#' = the whole subtree (retain.rs:298-367).  Device layout (built by `flatten`, then kept up to
+// date IN PLACE by set / remove — see "incremental updates" below — and shipped by the engine's flush):
 //
 //   rnodes : nodes in DFS PRE-ORDER, so the subtree of node n is the index range [n, sub_end(n)) and the
 //            values below a node are ONE contiguous range of `rvals` -> a '#' match is a range copy
@@ -10,6 +10,19 @@
 //            -> a '+' match is a coalesced scan of one block and yields complete work items
 //   redges : open-addressing hash (parent, token) -> child + the child's record for the exact-level steps
 //   rvals  : the values of all valued nodes, in pre-order
+//
+// Incremental updates.  After a flatten the arrays are a packed pre-order image.  A later set / remove edits them
+// in place and records which 32-byte entries / words changed (the flush ships only those):
+//   * value replaced on a node        -> its record (2 copies: parent's child block, hash slot) + its word in rvals
+//   * node gains / loses its value    -> its record; the '#' ranges of the node and of all its ancestors no longer
+//                                        describe the subtree, so they get RF_SUB_LIT_HASH ("walk, do not range-copy")
+//   * new nodes below an existing one -> appended to rnodes; the parent's child block moves to the end of rkids with
+//                                        doubled capacity when it is full (the old block becomes garbage); new
+//                                        hash slots; ancestors flagged as above
+//   * pruned nodes (retain.rs:247-249) stay behind as dead leaves (no value, no children: they cannot produce a
+//     hit) and are revived when the same path is set again
+// Anything involving a literal '+' / '#' level (they shadow wildcard expansion), a hash table more than half full,
+// or too much garbage falls back to a full flatten at the next flush.
 #pragma once
 #include <vector>
 
@@ -68,13 +81,19 @@ class RetainTreeHost {
     u64 values_size() const { return n_values_; }     // retain.rs:385-392
     u64 nodes_size() const { return n_nodes_; }       // retain.rs:395-398
 
-    bool dirty = true;
+    bool dirty = true;          // something to ship (whole arrays or patches)
+    bool full = true;           // the arrays were rebuilt: ship them whole
+    void prepare_flush();       // makes the arrays below current (flattens if in-place maintenance gave up)
+    void shipped() { dirty = false; full = false; dirty_kids.clear(); dirty_edges.clear(); dirty_vals.clear(); }
     void flatten();                                     // host tree -> device-layout arrays below
-    std::vector<RNode> rnodes;
-    std::vector<RKid> rkids;
-    std::vector<REdge> redges;
-    std::vector<u32> rvals;
+    std::vector<RNode, HugeAlloc<RNode>> rnodes;        // host bookkeeping, one per device node (not shipped)
+    std::vector<RKid, HugeAlloc<RKid>> rkids;
+    std::vector<REdge, HugeAlloc<REdge>> redges;
+    std::vector<u32, HugeAlloc<u32>> rvals;
+    std::vector<u32> dirty_kids, dirty_edges, dirty_vals;   // entries changed in place since the last flush
     u32 root_plain_kids = 0, root_plain_val_hi = 0, max_depth = 0;
+    u64 flattens = 0, patches = 0;                      // statistics: full rebuilds / in-place edits
+    void debug_stats(uint64_t (&o)[6]) const { o[0] = flattens; o[1] = patches; o[2] = garbage_kids_; o[3] = dead_nodes_; o[4] = live_edges_; o[5] = flat_valid_ ? 1 : 0; }
 
   private:
     struct HN {
@@ -82,7 +101,22 @@ class RetainTreeHost {
         u32 val = RVAL_NONE;
         bool has_val = false;
         u32 parent = 0, token = 0;
+        u32 dev = RVAL_NONE;                     // device node of this host node (valid while flat_valid_)
     };
+    // ---- in-place maintenance of the device image ----------------------------------------------
+    static constexpr u32 NODEV = 0xFFFFFFFFu;
+    bool flat_valid_ = false;                    // the arrays mirror the host tree (else: flatten at the next flush)
+    std::vector<u32> rparent_, rtoken_, rcap_;   // per device node: parent, level token, capacity of its child block
+    std::vector<u8> in_rvals_;                   // per device node: its value sits at rvals[val_lo] (it had one at flatten time)
+    u64 garbage_kids_ = 0, dead_nodes_ = 0, live_edges_ = 0;
+    void give_up() { flat_valid_ = false; dirty = true; }
+    u32 edge_slot_of(u32 parent_dev, u32 token) const;          // slot in redges or NODEV
+    void write_record(u32 dev);                                  // rnodes[dev] -> its two shipped copies
+    void invalidate_ranges(u32 dev);                             // dev and its ancestors: walk instead of range-copy
+    u32 dev_new_node(u32 parent_dev, u32 token);
+    bool dev_add_child(u32 parent_dev, u32 token, u32 child_dev);
+    void dev_set(u32 host_node, bool had_val, u32 value, u32 depth);
+    void dev_unset(u32 host_node);
     int parse(const char* s, u32 len, bool create, std::vector<u32>& toks);
     u32 child_of(u32 node, u32 token) const;
     HostTrie* dict_;

@@ -232,7 +232,9 @@ class Engine:
         out = {}
         spec = {0: ("edges", np.uint32, 8), 2: ("ranges", np.uint32, 2), 3: ("values", np.uint32, 1),
                 4: ("dict", np.uint32, 8), 5: ("pool", np.uint8, 1), 6: ("root", np.uint32, 1),  # root = {plus, hash_ref, mask, max_depth, hash_cnt, win_mask, win_shift, nwin_mask}
-                7: ("rnodes", np.uint32, 8), 8: ("rkids", np.uint32, 8), 9: ("rvals", np.uint32, 1), 12: ("cfilter", np.uint32, 1)}
+                7: ("rnodes", np.uint32, 8), 8: ("rkids", np.uint32, 8), 9: ("rvals", np.uint32, 1), 10: ("redges", np.uint32, 8),
+                11: ("rstats", np.uint64, 1),   # retained tree: {flattens, in-place patches, garbage child entries, dead nodes, hash entries, image valid}
+                12: ("cfilter", np.uint32, 1)}
         for which, (name, dt, width) in spec.items():
             ptr, cnt = C.c_void_p(), C.c_uint64(0)
             self._check(self._lib.gm_debug_table(self._h, which, C.byref(ptr), C.byref(cnt)))

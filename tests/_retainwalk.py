@@ -22,6 +22,30 @@ class RetainTables:
                 # the copied record must equal the child's own record
                 assert (int(k[2]), int(k[3]) & 0x0FFFFFFF, int(k[3]) >> 28, int(k[5]), int(k[6])) == (int(c[0]), int(c[1]), int(c[5]), int(c[3]), int(c[4]))
 
+        self.check_hash(t.get("redges"))
+
+    def check_hash(self, redges):
+        """The (parent, token) hash the exact steps of the kernel probe must hold exactly the child-block entries,
+        each with the same record (the kernels read records from either copy)."""
+        if redges is None or len(redges) == 0:
+            return
+        mask = len(redges) - 1
+        live = {(int(e[0]), int(e[1])): tuple(int(x) for x in e[2:8]) for e in redges if int(e[2]) != 0}
+        for key, rec in self.edges.items():
+            assert live.get(key) == rec, ("hash slot disagrees with the child block", key, live.get(key), rec)
+            n, tok = key
+            i = self.redge_hash(n, tok) & mask               # reachable by linear probing from its home slot
+            while not (int(redges[i][0]) == n and int(redges[i][1]) == tok and int(redges[i][2]) != 0):
+                assert int(redges[i][2]) != 0, ("probe hits an empty slot before the entry", key)
+                i = (i + 1) & mask
+        # entries of relocated (garbage) blocks never linger in the hash: one slot per live child entry
+        assert len(live) == len(self.edges), (len(live), len(self.edges))
+
+    @staticmethod
+    def redge_hash(parent, token):
+        from _tablewalk import fmix32, M32
+        return fmix32(((parent * 0x85EBCA77) + ((token ^ 0x2545F491) * 0x9E3779B1)) & M32)
+
     def set_root_plain(self, plain_kids, plain_val_hi):
         self.root_plain_kids, self.root_plain_val_hi = plain_kids, plain_val_hi
 

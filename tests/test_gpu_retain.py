@@ -124,3 +124,39 @@ def test_message_storage_shape():
         filters.append(f if f.split("/")[-1] == "#" else f + "/+")
     fb, fo = pack(filters)
     _assert_same(eng.retain_match_batch(fb, fo), tree.match_batch(fb, fo))
+
+
+def test_incremental_updates_on_device():
+    """Small groups of set / remove between lookups: the retained image on the device is edited in place (32-byte entry
+    and value-word patches shipped by the flush) instead of being re-flattened; every lookup stays bit-exact."""
+    rng = random.Random(55)
+    eng, tree = Engine(), orc.RetainTree()
+    lv = ["a", "b", "c", "d", "e", "", "x" * 30, "dev-0000001"]
+    def topic():
+        t = [rng.choice(lv) for _ in range(rng.randint(1, 6))]
+        if rng.random() < 0.1:
+            t[0] = rng.choice(["$SYS", "$q"])
+        return "/".join(t)
+    live, v = [], 0
+    for _ in range(2000):
+        t = topic(); v += 1
+        eng.retain_set(t, v); tree.remove(t); tree.insert(t, v); live.append(t)
+    filters = ["/".join(rng.choice(lv + ["+", "+", "#"]) for _ in range(rng.randint(1, 6))) for _ in range(800)]
+    filters = [f for f in filters if orc.topic_parse(f) is not None] + ["#", "+/#", "$SYS/#", "+/+/+"]
+    fb, fo = pack(filters)
+    _assert_same(eng.retain_match_batch(fb, fo), tree.match_batch(fb, fo))
+    flattens0 = int(eng.debug_tables()["rstats"][0])
+    for rnd in range(30):
+        for _ in range(rng.randint(1, 25)):
+            r = rng.random()
+            if r < 0.35:
+                t = rng.choice(live)
+                assert eng.retain_remove(t) == tree.remove(t)
+            else:
+                t = rng.choice(live) if r < 0.55 else topic()
+                v += 1
+                assert eng.retain_set(t, v) == tree.remove(t)
+                tree.insert(t, v); live.append(t)
+        _assert_same(eng.retain_match_batch(fb, fo), tree.match_batch(fb, fo))
+    st = eng.debug_tables()["rstats"]
+    assert int(st[0]) <= flattens0 + 1 and int(st[1]) > 100, st.tolist()     # edited in place, at most one re-pack

@@ -154,3 +154,56 @@ def test_compact_relabels_the_retained_tree():
     assert R.match(b"fresh/+/after") == ret.matches("fresh/+/after") == [424242]
     got = T.match(b"fresh/topic/after")[0]
     assert got == sub.matches("fresh/topic/after") and 7 in got
+
+
+def test_incremental_updates_edit_the_image_in_place():
+    """After the first flatten, set / remove must keep the device image current with in-place edits (no re-flatten)
+    for plain topics — new leaves, new deep paths, value replacement, removal with pruning, revival of pruned paths,
+    root children incl. `$` roots — and the image must match the oracle after every round; a literal `+` level or
+    too much garbage falls back to a full re-flatten."""
+    rng = random.Random(77)
+    eng, tree = Engine(host_only=True), orc.RetainTree()
+    lv = ["a", "b", "c", "d", "", "x" * 30]
+    def topic():
+        n = rng.randint(1, 5)
+        t = [rng.choice(lv) for _ in range(n)]
+        if rng.random() < 0.1:
+            t[0] = rng.choice(["$SYS", "$q"])
+        return "/".join(t)
+    live = []
+    for i in range(300):
+        t = topic(); eng.retain_set(t, i); tree.remove(t); tree.insert(t, i); live.append(t)
+    R, tb = _tables(eng)
+    base = tb["rstats"].tolist()
+    assert base[0] == 1 and base[5] == 1
+    v = 1000
+    for rnd in range(25):
+        for _ in range(rng.randint(1, 12)):
+            r = rng.random()
+            if r < 0.35 and live:
+                t = rng.choice(live)
+                assert eng.retain_remove(t) == tree.remove(t)
+            elif r < 0.55 and live:
+                t = rng.choice(live); v += 1                     # replace (or revive) an existing path
+                old = eng.retain_set(t, v); assert old == tree.remove(t); tree.insert(t, v)
+            else:
+                t = topic(); v += 1
+                old = eng.retain_set(t, v); assert old == tree.remove(t); tree.insert(t, v); live.append(t)
+        st = eng.stats()
+        assert st["retained_values"] == tree.values_size() and st["retained_nodes"] == tree.nodes_size()
+        R, tb = _tables(eng)
+        _plain_split(eng, R, tb, ["$SYS", "$q"])
+        for _ in range(120):
+            f = rand_filter(rng, 5) if rng.random() < 0.5 else "/".join(rng.choice(lv + ["+", "+", "#"]) for _ in range(rng.randint(1, 5)))
+            want = tree.matches(f)
+            if want is not None:
+                assert R.match(f.encode()) == want, (rnd, f)
+    s = tb["rstats"].tolist()
+    assert s[0] <= base[0] + 1 and s[1] > 0, s                   # at most one garbage-triggered re-pack; edits happened in place
+    # a literal '+' level changes the shadowing flags: rebuilt at the next flush, still exact
+    eng.retain_set("a/+/c", 5); tree.insert("a/+/c", 5)
+    R, tb = _tables(eng)
+    _plain_split(eng, R, tb, ["$SYS", "$q"])
+    assert tb["rstats"].tolist()[0] == s[0] + 1
+    for f in ("a/+/c", "a/#", "+/+/c", "#", "a/b/#"):
+        assert R.match(f.encode()) == tree.matches(f), f
