@@ -60,6 +60,29 @@ def partition_topics(blob, offs, rank: int, world: int):
     return b, o, idx
 
 
+def partition_retained(blob, offs, values, rank: int, world: int):
+    """Retained topics this rank stores: concrete topics sharded by their root.  A retained topic
+    whose level 0 is literally '+' or '#' (tolerated by the reference, never valid MQTT) cannot be sharded — it would
+    have to shadow the root-level wildcard expansion of every shard (retain.rs:313) — and is refused."""
+    sh = shard_ids(blob, offs, world)
+    if (sh == REPLICATED).any():
+        raise ValueError("a retained topic with a literal '+' / '#' root cannot be sharded")
+    idx = np.nonzero(sh == rank)[0]
+    b, o = select(blob, offs, idx)
+    return b, o, values[idx], idx
+
+
+def partition_retain_filters(blob, offs, rank: int, world: int):
+    """SUBSCRIBE filters this rank answers: a filter with a literal root goes to the shard of that root; a filter whose
+    level 0 is '+' or '#' is answered by EVERY shard for its own roots (the `$`-exclusion at the root, retain.rs:327-331
+    and 345-349, is local), and the complete hit list is the concatenation over ranks (all_gatherv_match_lists keeps one
+    entry per (rank, filter))."""
+    sh = shard_ids(blob, offs, world)
+    idx = np.nonzero((sh == rank) | (sh == REPLICATED))[0]
+    b, o = select(blob, offs, idx)
+    return b, o, idx
+
+
 def all_gatherv_match_lists(topic_index: torch.Tensor, counts: torch.Tensor, ids: torch.Tensor, group=None):
     """All-gatherv of per-rank match lists.
 

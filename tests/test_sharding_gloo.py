@@ -97,3 +97,71 @@ def test_shard_function_properties():
         assert set(sh) <= set(range(g))
         assert max(np.bincount(sh, minlength=g)) <= 64 // g * 2.5       # no pathological imbalance on 64 roots
         assert shard_of(names[3] + b"/x/y", g) == sh[3]
+
+
+# ---- retained path: retained topics sharded by root, root-wildcard filters answered by every shard ----
+def _retain_workload():
+    rng = random.Random(123)
+    cfg = wl.C4.scaled(n_subs=15_000, n_topics=1_500)
+    rb, ro, rv = wl.gen_retained(cfg)
+    fb, fo = wl.gen_retain_filters(cfg)
+    topics = wl.unpack(rb, ro) + [b"$SYS/broker/uptime", b"$SYS/x", b"$q/1", b"a//b", b"a"]
+    values = np.concatenate([rv, np.arange(10**6, 10**6 + 5, dtype=np.uint32)])
+    filters = wl.unpack(fb, fo) + [f.encode() for f in ["#", "+/#", "+", "$SYS/#", "$SYS/+", "+/+/+/+/+/+", "+/site-0002/#", "a/#", "a//+"]]
+    filters += [f.encode() for f in (rand_filter(rng) for _ in range(200)) if orc.topic_parse(f) is not None]
+    return topics, values, filters
+
+
+def _retain_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    topics, values, filters = _retain_workload()
+    rb, ro = pack(topics)
+    fb, fo = pack(filters)
+    srb, sro, sval, _ = sharding.partition_retained(rb, ro, values, rank, world)
+    sfb, sfo, fidx = sharding.partition_retain_filters(fb, fo, rank, world)
+    tree = orc.RetainTree()
+    for t, v in zip(wl.unpack(srb, sro), sval):
+        tree.insert(t, int(v))
+    res = tree.match_batch(sfb, sfo)
+    ti, ct, ia = sharding.all_gatherv_match_lists(torch.from_numpy(fidx.astype(np.int64)), torch.from_numpy(res["counts"].copy()),
+                                                  torch.from_numpy(res["ids"].astype(np.int64)))
+    q.put((rank, ti.numpy(), ct.numpy(), ia.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_retained_lookup_equals_unsharded_world2():
+    world, port = 2, 31000 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_retain_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got.sort(key=lambda g: g[0])
+    for a, b in zip(got[0][1:], got[1][1:]):
+        assert (a == b).all()
+    _, ti, ct, ia = got[0]
+    topics, values, filters = _retain_workload()
+    tree = orc.RetainTree()
+    for t, v in zip(topics, values):
+        tree.insert(t, int(v))
+    # union over ranks of the per-filter hit lists == the unsharded lookup (wildcard roots are answered by both shards)
+    merged = {i: [] for i in range(len(filters))}
+    starts = np.concatenate([[0], np.cumsum(np.maximum(ct, 0))])
+    answered = np.bincount(ti, minlength=len(filters))
+    for k, f in enumerate(ti):
+        merged[int(f)].extend(ia[starts[k]:starts[k + 1]].tolist())
+    n_wild = 0
+    for i, f in enumerate(filters):
+        wild_root = f.split(b"/", 1)[0] in (b"+", b"#")
+        n_wild += wild_root
+        assert answered[i] == (world if wild_root else 1), f
+        assert sorted(merged[i]) == tree.matches(f), f
+    assert n_wild >= 6
+    with pytest.raises(ValueError):
+        sharding.partition_retained(*pack(["+/x"]), np.zeros(1, np.uint32), 0, 2)
