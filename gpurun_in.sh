@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_retain.py tests/test_gpu_hypothesis.py tests/test_gpu_parity.py tests/test_gpu_router.py -x -q -m gpu 2>&1 | tail -6
+timeout 35 compute-sanitizer --tool memcheck --print-limit 5 python tools/memcheck_workload.py > gpurun_out/memcheck_workload.txt 2>&1; tail -5 gpurun_out/memcheck_workload.txt
