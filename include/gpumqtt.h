@@ -197,6 +197,8 @@ uint64_t gm_kernel_launches(gm_engine* e);
 /* shard of a topic / filter by its level-0 string (multi-GPU root-hash partitioning); 0xFFFFFFFF for a
  * filter whose level 0 is a wildcard (those are replicated on every shard)                               */
 uint32_t gm_shard_of(const char* topic_or_filter, uint32_t len, uint32_t n_shards);
+/* the same for a packed batch (blob + n+1 offsets): out_shard[i] = gm_shard_of(entry i); pure host function          */
+int32_t gm_shard_of_batch(const char* blob, const uint32_t* offsets, uint64_t n, uint32_t n_shards, uint32_t* out_shard);
 /* DEBUG/TEST: read-only view of the host mirror of a device table, in device layout (rmqtt_b200/csrc/layout.h).
  * which: 0 edges(32 B) 2 ranges(8 B) 3 values(4 B) 4 dict(32 B) 5 long-string pool(1 B)
  *        6 root record {plus, hash_ref, mask, max_depth, hash_cnt, win_mask, win_shift, nwin_mask}; retained tree: 7 nodes(32 B, host bookkeeping) 8 child blocks(32 B entries)

@@ -93,6 +93,7 @@ SIGNATURES = {
     "gm_kernel_ms_ring": (_i32, [_vp, _vp, _u32, _P(_u32)]),
     "gm_kernel_launches": (_u64, [_vp]),
     "gm_shard_of": (_u32, [_cp, _u32, _u32]),
+    "gm_shard_of_batch": (_i32, [_vp, _vp, _u64, _u32, _vp]),
     "gm_debug_table": (_i32, [_vp, _u32, _P(_vp), _P(_u64)]),
     "gm_debug_knob": (_i32, [_vp, C.c_char_p, C.c_int64]),
     "gm_host_alloc": (_vp, [_u64]),

@@ -897,6 +897,12 @@ uint32_t gm_shard_of(const char* s, uint32_t len, uint32_t n_shards) {
     return shard_of_hash(HostTrie::level0_hash(s, len), n_shards);
 }
 
+int32_t gm_shard_of_batch(const char* blob, const uint32_t* offsets, uint64_t n, uint32_t n_shards, uint32_t* out_shard) {
+    if ((n && (!blob || !offsets || !out_shard)) || n_shards == 0) return GM_ERR_INVALID_ARG;
+    for (uint64_t i = 0; i < n; ++i) out_shard[i] = gm_shard_of(blob + offsets[i], offsets[i + 1] - offsets[i], n_shards);
+    return GM_OK;
+}
+
 void* gm_host_alloc(uint64_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;

@@ -18,17 +18,19 @@ REPLICATED = 0xFFFFFFFF
 
 
 def shard_ids(blob: np.ndarray, offs: np.ndarray, n_shards: int) -> np.ndarray:
-    """Shard of every topic / filter in a packed batch (REPLICATED for root-wildcard filters)."""
-    b = blob.tobytes()
-    out = np.empty(len(offs) - 1, dtype=np.uint32)
-    cache = {}
-    for i in range(len(offs) - 1):
-        s = b[offs[i]:offs[i + 1]]
-        l0 = s.split(b"/", 1)[0]
-        v = cache.get(l0)
-        if v is None:
-            v = cache[l0] = shard_of(l0, n_shards)
-        out[i] = v
+    """Shard of every topic / filter in a packed batch (REPLICATED for root-wildcard filters): gm_shard_of_batch."""
+    from . import _native as N
+    n = len(offs) - 1
+    out = np.empty(n, dtype=np.uint32)
+    if n == 0:
+        return out
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.uint32)
+    if len(blob) == 0:
+        blob = np.zeros(1, dtype=np.uint8)
+    rc = N.lib().gm_shard_of_batch(blob.ctypes.data, offs.ctypes.data, n, int(n_shards), out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"gm_shard_of_batch failed: {rc}")
     return out
 
 
