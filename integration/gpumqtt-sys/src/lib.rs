@@ -44,6 +44,7 @@ extern "C" {
     pub fn gm_sub_remove(e: *mut gm_engine, filter: *const u8, len: u32, value: u32, changed: *mut i32) -> i32;
     pub fn gm_bulk_load(e: *mut gm_engine, blob: *const u8, offsets: *const u32, values: *const u32, n: u64, n_changed: *mut u64) -> i32;
     pub fn gm_flush(e: *mut gm_engine) -> i32;
+    pub fn gm_compact(e: *mut gm_engine) -> i32;
     pub fn gm_match_batch(
         e: *mut gm_engine, topics_blob: *const u8, topic_offsets: *const u32, n: u64, out_spans: *mut gm_span,
         out_ids: *mut u32, cap_ids: u64, needed: *mut u64, status: *mut i32,
@@ -56,6 +57,7 @@ extern "C" {
         out_ids: *mut u32, cap_ids: u64, needed: *mut u64, status: *mut i32,
     ) -> i32;
     pub fn gm_shard_of(topic_or_filter: *const u8, len: u32, n_shards: u32) -> u32;
+    pub fn gm_shard_of_batch(blob: *const u8, offsets: *const u32, n: u64, n_shards: u32, out_shard: *mut u32) -> i32;
     pub fn gm_host_alloc(bytes: u64) -> *mut c_void;
     pub fn gm_host_free(p: *mut c_void);
 }
