@@ -11,7 +11,7 @@ from oracle import oracle as orc
 from rmqtt_b200 import _native as N
 from rmqtt_b200.engine import Engine, GpuMqttError, pack
 
-from test_hypothesis_cpu import ops, path
+from test_hypothesis_cpu import ops, path, retain_ops
 
 pytestmark = pytest.mark.gpu
 COMMON = dict(deadline=None, max_examples=int(os.environ.get("GM_HYP_GPU_EXAMPLES", "60")), suppress_health_check=[HealthCheck.too_slow])
@@ -44,11 +44,13 @@ def test_subscription_trie_cuda_vs_oracle(ops, topics, tiny):
 
 
 @settings(**COMMON)
-@given(ops=st.lists(st.tuples(st.sampled_from(["set", "set", "set", "remove"]), path, st.integers(0, 2**32 - 2)), min_size=1, max_size=50),
-       filters=st.lists(path, min_size=1, max_size=40))
+@given(ops=retain_ops, filters=st.lists(path, min_size=1, max_size=40))
 def test_retained_tree_cuda_vs_oracle(ops, filters):
     eng, tree = Engine(), orc.RetainTree()
     for op, t, v in ops:
+        if op == "flush":              # ship what is staged: later operations patch the device image in place
+            eng.flush()
+            continue
         try:
             eng.retain_set(t, v) if op == "set" else eng.retain_remove(t)
         except GpuMqttError as ex:

@@ -49,12 +49,18 @@ def test_subscription_trie_tables_vs_oracle(ops, topics, win):
         assert T.match(t.encode())[0] == tree.matches(t), t
 
 
+retain_ops = st.lists(st.tuples(st.sampled_from(["set", "set", "set", "set", "remove", "remove", "flush"]), path, st.integers(0, 2**32 - 2)), min_size=1, max_size=60)
+
+
 @settings(**COMMON)
-@given(ops=st.lists(st.tuples(st.sampled_from(["set", "set", "set", "remove"]), path, st.integers(0, 2**32 - 2)), min_size=1, max_size=50),
-       filters=st.lists(path, min_size=1, max_size=25))
+@given(ops=retain_ops, filters=st.lists(path, min_size=1, max_size=25))
 def test_retained_tree_tables_vs_oracle(ops, filters):
+    """`flush` points in the sequence make the later operations edit the flattened image in place (retain_tree.h)."""
     eng, tree = Engine(host_only=True), orc.RetainTree()
     for op, t, v in ops:
+        if op == "flush":
+            eng.flush()
+            continue
         try:
             if op == "set":
                 eng.retain_set(t, v)
