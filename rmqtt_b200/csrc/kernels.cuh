@@ -628,7 +628,7 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Flush: scatter slot patches (EdgeSlot / DictSlot / PlusRec: 32 B, Range: 8 B) into a device table.
+// Flush: scatter patches (EdgeSlot / DictSlot / RKid / REdge: 32 B, Range: 8 B, retained value words: 4 B) into a device table.
 template <class T>
 __global__ void k_apply_patches(T* __restrict__ table, const u32* __restrict__ idx, const T* __restrict__ data, u32 n) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
