@@ -43,3 +43,38 @@ def test_no_cpu_fallback_without_a_device():
     h = C.c_void_p()
     assert lib.gm_create(None, C.byref(h)) == N.GM_ERR_NO_DEVICE
     assert b"no CPU fallback" in lib.gm_last_error(None)
+
+
+def test_error_codes_of_the_boundary_host_only():
+    """Status codes instead of exceptions / aborts across the boundary: bad arguments, invalid and too
+    deep filters, matching on an engine without a device, unknown knobs — and a readable gm_last_error each time."""
+    import numpy as np
+    from rmqtt_b200.engine import Engine, GpuMqttError, pack
+    lib = N.lib()
+    eng = Engine(host_only=True, max_levels=4)
+    h = eng._h
+    ch = C.c_int32(0)
+    assert lib.gm_sub_add(None, b"a", 1, 1, C.byref(ch)) == N.GM_ERR_INVALID_ARG
+    assert lib.gm_sub_add(h, None, 3, 1, C.byref(ch)) == N.GM_ERR_INVALID_ARG
+    assert lib.gm_sub_add(h, b"a/#/b", 5, 1, C.byref(ch)) == N.GM_ERR_INVALID_TOPIC and lib.gm_last_error(h)
+    assert lib.gm_sub_add(h, b"a/b/c/d/e", 9, 1, C.byref(ch)) == N.GM_ERR_TOO_DEEP
+    assert lib.gm_sub_add(h, b"a/b/c/d", 7, 1, C.byref(ch)) == N.GM_OK and ch.value == 1
+    assert lib.gm_sub_add(h, b"a/b/c/d", 7, 1, C.byref(ch)) == N.GM_OK and ch.value == 0       # already present
+    assert lib.gm_sub_remove(h, b"a/b/c/d", 7, 2, C.byref(ch)) == N.GM_OK and ch.value == 0    # other value
+    assert lib.gm_sub_remove(h, b"x+", 2, 1, C.byref(ch)) == N.GM_ERR_INVALID_TOPIC
+    had, old = C.c_int32(0), C.c_uint32(0)
+    assert lib.gm_retain_set(h, b"a/+x", 4, 1, C.byref(had), C.byref(old)) == N.GM_ERR_INVALID_TOPIC
+    assert lib.gm_retain_set(h, b"t/1", 3, 5, C.byref(had), C.byref(old)) == N.GM_OK and had.value == 0
+    assert lib.gm_retain_set(h, b"t/1", 3, 6, C.byref(had), C.byref(old)) == N.GM_OK and (had.value, old.value) == (1, 5)
+    assert lib.gm_retain_remove(h, b"t/2", 3, C.byref(had), C.byref(old)) == N.GM_OK and had.value == 0
+    blob, offs = pack(["a/b"])
+    spans, ids, status, needed = np.zeros((1, 2), np.uint32), np.zeros(8, np.uint32), np.zeros(1, np.int32), C.c_uint64(0)
+    args = (blob.ctypes.data, offs.ctypes.data, 1, spans.ctypes.data, ids.ctypes.data, 8, C.byref(needed), status.ctypes.data)
+    assert lib.gm_match_batch(h, *args) == N.GM_ERR_NO_DEVICE and b"no CPU fallback" in lib.gm_last_error(h)
+    assert lib.gm_retain_match_batch(h, *args) == N.GM_ERR_NO_DEVICE
+    assert lib.gm_match_batch(None, *args) == N.GM_ERR_INVALID_ARG
+    assert lib.gm_debug_knob(h, b"no_such_knob", 1) == N.GM_ERR_INVALID_ARG and lib.gm_debug_knob(h, b"tile_chunk", 16) == N.GM_OK
+    assert lib.gm_shard_of_batch(blob.ctypes.data, offs.ctypes.data, 1, 0, ids.ctypes.data) == N.GM_ERR_INVALID_ARG
+    assert lib.gm_flush(h) == N.GM_OK and lib.gm_compact(h) == N.GM_OK
+    with pytest.raises(GpuMqttError):
+        eng.add("$SYS/a/$b", 1)                 # Metadata level below the root (topic.rs:357-359)
