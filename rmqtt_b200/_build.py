@@ -36,7 +36,7 @@ def _newer(target: Path, sources) -> bool:
 
 def build_engine(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / "engine.cu", CSRC / "host_trie.cpp", CSRC / "retain_tree.cpp", CSRC / "router_host.cpp"]
-    deps = srcs + [CSRC / "kernels.cuh", CSRC / "retain_kernels.cuh", CSRC / "retain_tree.h", CSRC / "router_host.h", CSRC / "layout.h", CSRC / "host_trie.h", PKG.parent / "include" / "gpumqtt.h"]
+    deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "gpumqtt.h"]
     if force or _newer(LIB, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, srcs)]
         if verbose:

@@ -94,6 +94,7 @@ struct gm_engine {
     // device tables
     DevBuf d_edges, d_ranges, d_values, d_dict, d_pool, d_cfilter;
     size_t up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
+    u64 up_values_epoch = 0;
     // scratch
     DevBuf d_tok, d_tok8, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data, d_sort, d_hist;
     DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
@@ -211,10 +212,15 @@ struct gm_engine {
     }
 
     int flush_locked() {
-        if (flags & GM_FLAG_HOST_ONLY) { trie.sync(); if (rtree.dirty) { rtree.prepare_flush(); rtree.shipped(); } return GM_OK; }
+        if (flags & GM_FLAG_HOST_ONLY) {
+            if (!trie.sync()) { g_err = "more than 2^32 live value words"; return GM_ERR_TOO_LARGE; }
+            if (rtree.dirty) { rtree.prepare_flush(); rtree.shipped(); }
+            return GM_OK;
+        }
         if (!trie.any_dirty() && !rtree.dirty) return GM_OK;
         CUDA_TRY(cudaSetDevice(device));
-        trie.sync();
+        if (!trie.sync()) { g_err = "more than 2^32 live value words"; return GM_ERR_TOO_LARGE; }
+        if (trie.values_epoch != up_values_epoch) { up_values = up_ranges = 0; up_values_epoch = trie.values_epoch; }   // value sets were compacted: re-ship whole
         if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(side, ev_match, 0));   // never patch under a running match
         if (rtree.dirty) {   // retained tree: whole arrays after a (re)flatten, else only the entries set / remove edited in place
             rtree.prepare_flush();
@@ -520,6 +526,7 @@ int32_t gm_compact(gm_engine* e) {
     e->trie.compact(&keep, &remap);
     e->rtree.remap_tokens(remap);
     e->up_ranges = e->up_values = e->up_pool = 0;
+    e->up_values_epoch = e->trie.values_epoch;
     e->up_edges_slots = e->up_dict_slots = 0;
     return (e->flags & GM_FLAG_HOST_ONLY) ? GM_OK : e->flush_locked();
 }

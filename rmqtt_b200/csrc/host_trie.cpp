@@ -270,8 +270,15 @@ void HostTrie::cfilter_rebuild() {
     cfilter_dirty = true;
 }
 
+// dirty bit 0: the node's record must be re-published; bit 1: its VALUE SET changed (a new reference is needed).
+// Only the second kind appends to `values` — a node that merely gained a child edge keeps its published set.
 void HostTrie::mark(u32 node) {
-    if (!nodes_[node].dirty) { nodes_[node].dirty = 1; dirty_nodes_.push_back(node); }
+    if (!nodes_[node].dirty) dirty_nodes_.push_back(node);
+    nodes_[node].dirty |= 1;
+}
+void HostTrie::mark_vals(u32 node) {
+    if (!nodes_[node].dirty) dirty_nodes_.push_back(node);
+    nodes_[node].dirty |= 3;
 }
 
 // ------------------------------------------------------------------------------- parsing
@@ -329,7 +336,7 @@ bool HostTrie::add_value(u32 node, u32 value) {
     }
     if (ch) {
         values_size_++;
-        mark(node);
+        mark_vals(node);
         if (n.token == TOK_HASH) mark(n.parent);
         // revive pruned ancestors
         for (u32 x = node; x != 0 && !nodes_[x].alive; x = nodes_[x].parent) {
@@ -438,7 +445,7 @@ int HostTrie::remove(const char* filter, u32 len, u32 value, bool* changed) {
     }
     if (ch) {
         values_size_--;
-        mark(node);
+        mark_vals(node);
         if (n.token == TOK_HASH) mark(n.parent);
     }
     // bottom-up pruning (trie.rs:126-128): a node with no values and no children disappears
@@ -518,7 +525,32 @@ void HostTrie::compact(const std::vector<u32>* keep, std::vector<u32>* remap) {
     *this = std::move(fresh);
 }
 
-void HostTrie::sync() {
+// Drops the garbage copies of replaced value sets: `values` / `ranges` are rebuilt from the live multi-value sets
+// (every such node gets a fresh reference and re-publishes its record).  O(multi-value nodes), not O(filters).
+void HostTrie::compact_values() {
+    values.clear();
+    ranges.assign(1, Range{0, 0});
+    garbage_values = 0;
+    values_epoch++;
+    for (auto& kv : multi_) {
+        HNode& n = nodes_[kv.first];
+        n.ref = 0; n.cnt16 = 0;                       // the old copy is gone: nothing to count as garbage
+        mark_vals(kv.first);
+        if (n.token == TOK_HASH) mark(n.parent);
+    }
+}
+
+bool HostTrie::sync() {
+    // value words this flush appends; replaced copies become garbage.  Auto-compaction keeps both bounded: churn on
+    // one popular filter would otherwise grow `values` without limit and finally wrap the 32-bit references.
+    auto pending_words = [&]() { u64 w = 0; for (u32 id : dirty_nodes_) if ((nodes_[id].dirty & 2) && nodes_[id].nvals >= 2) w += nodes_[id].nvals; return w; };
+    u64 add_words = pending_words();
+    const u64 live_words = values.size() - std::min<u64>(garbage_values, values.size());
+    if (garbage_values > live_words + 65536 || values.size() + add_words > 0xFFFFFFF0ull) {
+        compact_values();
+        add_words = pending_words();
+        if (add_words > 0xFFFFFFF0ull) return false;   // more than 2^32 value words live: references would wrap
+    }
     if (cfilter_rebuild_) {
         // nodes that just became wide must republish their record (flag)
         for (u32 id = 0; id < nodes_.size(); ++id) if (nodes_[id].wide && !nodes_[id].dirty) { nodes_[id].dirty = 1; dirty_nodes_.push_back(id); }
@@ -529,6 +561,7 @@ void HostTrie::sync() {
     // one tile of the match kernel expands (same level0/level1 subtree) are neighbours in `values` as well.
     std::vector<std::pair<u64, u32>> multi;
     for (u32 id : dirty_nodes_) {
+        if (!(nodes_[id].dirty & 2)) continue;             // record-only change: the published set stays
         if (nodes_[id].nvals < 2) { make_ref(id); continue; }
         u32 a = id;
         while (nodes_[a].depth > 2) a = nodes_[a].parent;
@@ -544,6 +577,7 @@ void HostTrie::sync() {
         nodes_[id].dirty = 0;
     }
     dirty_nodes_.clear();
+    return true;
 }
 
 }  // namespace gm

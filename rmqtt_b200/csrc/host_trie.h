@@ -48,8 +48,9 @@ class HostTrie {
     u64 insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n);
     void reserve(u64 n_filters);
 
-    // Resolve dirty nodes into slot patches (called by flush).
-    void sync();
+    // Resolve dirty nodes into slot patches (called by flush).  false: more than 2^32 live value words (references would wrap).
+    bool sync();
+    u64 values_epoch = 0;     // bumped whenever `values` / `ranges` were rebuilt from scratch (the device copy must be re-shipped whole)
     // Rebuild every table from the live content: drops pruned nodes, dead dictionary use and value garbage.
     // Tokens are re-assigned; the caller must treat all device tables as new (everything is marked dirty).
     // `keep` lists old tokens that other users of the dictionary (the retained tree) still hold: their strings are
@@ -109,6 +110,8 @@ class HostTrie {
     u32 pick_tag();                                     // least-loaded window tag for a new depth-2 subtree
     void grow_dict();
     void mark(u32 node);
+    void mark_vals(u32 node);
+    void compact_values();
     void make_ref(u32 node);
     void write_record(u32 node);
     void cfilter_insert(u32 parent, u32 token);

@@ -239,3 +239,34 @@ def test_bulk_load_equals_one_by_one_inserts():
     for _ in range(400):
         t = rand_topic(rng)
         assert T.match(t.encode())[0] == tree.matches(t), t
+
+
+def test_child_adds_do_not_recopy_the_value_set_and_churn_is_compacted():
+    """ADVICE r1 (host_trie.cpp make_ref): a node's multi-value set is re-published only when the SET changed, not when
+    the node merely gained a child edge; replaced copies are garbage that auto-compaction bounds."""
+    import numpy as np
+    from rmqtt_b200.engine import pack
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    n = 1000
+    blob, offs = pack(["pop/+"] * n)
+    vals = np.arange(n, dtype=np.uint32)
+    assert eng.bulk_load(blob, offs, vals) == n
+    tree.bulk_insert(blob, offs, vals)
+    eng.flush()
+    assert eng.stats()["value_words"] == n
+    for k in range(200):                          # 200 child adds below the popular node, one flush each
+        f = f"pop/+/c{k}"
+        assert eng.add(f, 5000 + k) == tree.insert(f, 5000 + k)
+        eng.flush()
+    st = eng.stats()
+    assert st["value_words"] == n and st["garbage_value_words"] == 0, st
+    for k in range(300):                          # subscribe/unsubscribe churn on the popular filter
+        assert eng.add("pop/+", 10_000 + k) == tree.insert("pop/+", 10_000 + k)
+        eng.flush()
+        assert eng.remove("pop/+", 10_000 + k) == tree.remove("pop/+", 10_000 + k)
+        eng.flush()
+    st = eng.stats()
+    assert st["value_words"] <= 2 * n + 65536 + 2 * n and st["garbage_value_words"] <= n + 65536 + 2 * n, st   # bounded by auto-compaction
+    T = Tables(eng.debug_tables())
+    for t in ("pop/x", "pop/x/c7", "pop/x/c199", "pop"):
+        assert T.match(t.encode())[0] == tree.matches(t), t
