@@ -6,8 +6,11 @@
 One "step" = one pass of the hot path (tokenise -> trie walk -> per-topic match lists) over one batch of
 synthetic topics (workload C3 of BASELINE.json: 10 M subscriptions, 30 % '+', 5 % '#', 6-level IoT topics,
 1 M-topic batch).  N > 1 is launched by torchrun, one process per GPU: the subscription set is sharded by
-topic-root hash (root-wildcard filters replicated), every rank matches its own batch of topics that belong to
-its shard, there is no data-path collective -> "scaling": "weak".
+topic-root hash (root-wildcard filters replicated).  `value` is the weak-scaling leg (every rank matches its own
+batch of topics of its shard, no collective -> "scaling": "weak"); `multi_gpu` adds the collective on the data path:
+`value_with_gather` (the same plus ONE all-gatherv of all match lists, libgpumqtt's gm_allgatherv_device) and the
+strong-scaling leg (one mixed batch partitioned by a device kernel, matched, gathered), and `parity_check` verifies
+the gathered lists of a 60 K-topic sample against the oracle on rank 0.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §"Measurement" for every key.
 """
@@ -41,6 +44,7 @@ def _args():
     ap.add_argument("--batches", type=int, default=4, help="distinct topic batches rotated through the timed loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-c4", action="store_true", help="skip the retained-tree (config C4) leg")
     return ap.parse_args()
 
 
@@ -129,6 +133,7 @@ def run_reference(args):
     from rmqtt_b200 import workload as wl
     cfg = _cfg(args)
     threads = orc.hardware_threads()
+    orc.numa_interleave(True)          # tree pages spread over the sockets: the 128-reader baseline must not depend on page luck
     sb, so, sv = wl.gen_subs(cfg)
     router = orc.Router()
     t0 = time.time()
@@ -160,22 +165,92 @@ def run_reference(args):
 
 
 # ======================================================================================================
+class _Pinned:
+    """Pinned host buffers from the library's NUMA-aware allocator (placed next to the engine's GPU)."""
+
+    def __init__(self, lib, eng):
+        self.lib, self.eng, self.ptrs = lib, eng, []
+
+    def alloc(self, nbytes, dtype, shape):
+        p = self.lib.gm_host_alloc_near(self.eng._h, max(1, int(nbytes)))
+        assert p, "gm_host_alloc_near failed"
+        self.ptrs.append(p)
+        return p, np.frombuffer((C.c_uint8 * max(1, int(nbytes))).from_address(p), dtype=dtype)[:int(np.prod(shape))].reshape(shape)
+
+    def free(self):
+        for p in self.ptrs:
+            self.lib.gm_host_free(p)
+        self.ptrs = []
+
+
+def _c4_leg(torch, dev, stream, peak, small: bool):
+    """BASELINE.json config C4 (retained tree: 5 M retained topics, 100 K wildcard SUBSCRIBE filters) on this GPU:
+    device-resident filters, CUDA-event kernel times from the engine's ring, algorithmic bytes from the oracle's counters
+    of the same batch (retained form), count parity against the oracle."""
+    from oracle import oracle as orc
+    from rmqtt_b200 import workload as wl
+    from rmqtt_b200.engine import Engine
+    cfg = wl.C4.scaled(n_subs=500_000, n_topics=20_000, name="C4-scaled") if small else wl.C4
+    rb, ro, rv = wl.gen_retained(cfg)
+    fb, fo = wl.gen_retain_filters(cfg)
+    n = len(fo) - 1
+    eng = Engine()
+    t0 = time.time()
+    eng.retain_bulk_load(rb, ro, rv)
+    eng.flush()
+    build_s = time.time() - t0
+    d_blob, d_offs = torch.from_numpy(fb).to(dev), torch.from_numpy(fo.view(np.int32)).to(dev)
+    d_spans = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_ids = torch.empty(1 << 22, dtype=torch.int32, device=dev)
+    need = C.c_uint64(0)
+    from rmqtt_b200 import _native as N
+    rc = N.lib().gm_retain_match_batch_device(eng._h, d_blob.data_ptr(), d_blob.numel(), d_offs.data_ptr(), n, d_spans.data_ptr(), d_ids.data_ptr(), d_ids.numel(),
+                                              C.byref(need), d_status.data_ptr(), stream)
+    if rc == N.GM_ERR_CAPACITY:
+        d_ids = torch.empty(int(need.value) + 1024, dtype=torch.int32, device=dev)
+    reps = 10
+    for _ in range(reps + 3):
+        hits = eng.retain_match_batch_device(d_blob, d_offs, d_spans, d_ids, d_status, stream)
+    torch.cuda.synchronize()
+    k = eng.kernel_ms(reps).mean(axis=0)
+    tree = orc.RetainTree()
+    tree.bulk_insert(rb, ro, rv)
+    o = tree.match_batch(fb, fo, nthreads=orc.hardware_threads(), want_ids=False)
+    counts = d_spans.cpu().numpy()[:, 1].astype(np.int64)
+    c = o["counters"]
+    walk_bytes = 32 * c["V"] + 16 * c["E"] + 4 * c["M"] + 8 * n
+    ms = float(k.sum())
+    eng.close()
+    return {"workload": f"{cfg.name}: {cfg.n_subs} retained topics, {n} wildcard SUBSCRIBE filters (85% '+', 15% '#'), seed {cfg.seed:#x}",
+            "filters_per_s": n / (ms * 1e-3), "ms": ms, "kernel_ms": {"tokenize": float(k[0]), "walk": float(k[1]), "publish": float(k[2])},
+            "hits_per_filter": hits / n, "visited_nodes_per_filter": c["V"] / n,
+            "algorithmic_bytes": walk_bytes, "achieved_GBps": walk_bytes / (float(k[1] + k[2]) * 1e-3) / 1e9,
+            "frac": walk_bytes / (float(k[1] + k[2]) * 1e-3) / 1e9 / peak,
+            "cpu_filters_per_s": n / o["seconds"], "cpu_threads": orc.hardware_threads(),
+            "count_parity": bool((counts == o["counts"]).all()), "build_s": round(build_s, 1)}
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
     from rmqtt_b200 import workload as wl
     from rmqtt_b200 import _native as N
-    from rmqtt_b200.engine import Engine
+    from rmqtt_b200.engine import Engine, MatchResult
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    lib = N.lib()
+    if world > 1:
+        lib.gm_bind_thread_near_device(local)      # one process per GPU: its host threads and buffers live next to its GPU (2-socket hosts)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = _cfg(args)
     regions = _regions_of_rank(cfg, rank, world)
+    small = cfg.n_subs < 5_000_000                 # developer runs with --subs/--topics: shrink the secondary legs too
 
     # ---- build the device-resident trie for this rank's shard -------------------------------------
     t0 = time.time()
@@ -189,6 +264,10 @@ def run_own(args):
     build_s = time.time() - t0
     st = eng.stats()
     del sb, so
+    uid = [Engine.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(uid[0], rank, world)             # the library's own NCCL communicator (gm_allgatherv_device)
 
     # ---- topic batches, resident in HBM before the timed region ---------------------------------
     n = cfg.n_topics
@@ -213,16 +292,37 @@ def run_own(args):
         needed_max = max(needed_max, need)
     if d_ids.numel() > 2 * needed_max + 1024:
         d_ids = torch.empty(int(needed_max * 1.25) + 1024, dtype=torch.int32, device=dev)
-
-    def step(k):
-        tb, to = d_batches[k % B]
-        eng.match_batch_device(tb, to, d_spans, d_ids, d_needed, d_status, stream)
+    desc_max = int(max(w["filters"] for w in works))
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_device_loop(step, steps, warm):
+        for k in range(warm):
+            step(k)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            step(k)
+        e1.record()
+        sync_all()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- leg 1 (headline `value`): ids mode, inputs resident in HBM ------------------------------------------------
+    def step(k):
+        tb, to = d_batches[k % B]
+        eng.match_batch_device(tb, to, d_spans, d_ids, d_needed, d_status, stream)
 
     for k in range(max(3, args.warmup)):
         step(k)
@@ -232,64 +332,164 @@ def run_own(args):
         sampler.start()
         time.sleep(0.2)
     launches0 = eng.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for k in range(args.steps):
-        step(k)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
+    ms = timed_device_loop(step, args.steps, 0)
     launches = eng.kernel_launches() - launches0
     kms = eng.kernel_ms(min(64, args.steps))
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
     value = world * n * args.steps / (ms / 1e3)
 
-    # ---- end to end through the C ABI with (pinned) HOST buffers: H2D + kernels + D2H every step ---
-    lib = N.lib()
-    hb, ho = host_batches[0]
+    # the same loop in descriptor mode (8 B per matched filter instead of 4 B per matched id): explains the e2e number
+    d_desc = torch.empty((int(desc_max * 1.25) + 1024, 2), dtype=torch.int32, device=dev)
+
+    def step_desc(k):
+        tb, to = d_batches[k % B]
+        eng.match_batch_device_ex(tb, to, d_spans, d_desc, d_needed, d_status, stream, desc=True)
+
+    side_steps = max(5, min(args.steps, 50))
+    ms_desc = timed_device_loop(step_desc, side_steps, 3)
+    kms_desc = eng.kernel_ms(min(64, side_steps))
+    value_desc = world * n * side_steps / (ms_desc / 1e3)
+
+    # ---- leg 2 (e2e): through the C ABI with pinned HOST buffers: H2D + kernels + D2H inside the timed region, batches rotated
+    pin = _Pinned(lib, eng)
+    p_in = []
+    for hb, ho in host_batches:
+        pb, ab = pin.alloc(len(hb), np.uint8, (len(hb),))
+        po, ao = pin.alloc(4 * (n + 1), np.uint32, (n + 1,))
+        ab[:] = hb
+        ao[:] = ho
+        p_in.append((pb, po, len(hb)))
     ids_cap = int(needed_max * 1.25) + 1024
-
-    def pinned(nbytes, dtype, shape):
-        p = lib.gm_host_alloc(nbytes)
-        assert p, "gm_host_alloc failed"
-        return p, np.frombuffer((C.c_uint8 * nbytes).from_address(p), dtype=dtype).reshape(shape)
-
-    p_blob, a_blob = pinned(len(hb), np.uint8, (len(hb),))
-    p_offs, a_offs = pinned(4 * (n + 1), np.uint32, (n + 1,))
-    p_spans, a_spans = pinned(8 * n, np.uint32, (n, 2))
-    p_ids, a_ids = pinned(4 * ids_cap, np.uint32, (ids_cap,))
-    p_status, a_status = pinned(4 * n, np.int32, (n,))
-    a_blob[:] = hb
-    a_offs[:] = ho
+    desc_cap = int(desc_max * 1.25) + 1024
+    p_spans, _ = pin.alloc(8 * n, np.uint32, (n, 2))
+    p_status, _ = pin.alloc(4 * n, np.int32, (n,))
+    p_ids, _ = pin.alloc(4 * ids_cap, np.uint32, (ids_cap,))
+    p_desc, _ = pin.alloc(8 * desc_cap, np.uint32, (desc_cap, 2))
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
     need = C.c_uint64(0)
 
-    def e2e_step():
-        rc = lib.gm_match_batch(eng._h, p_blob, p_offs, n, p_spans, p_ids, ids_cap, C.byref(need), p_status)
+    def e2e_ids(k):
+        pb, po, _ = p_in[k % B]
+        rc = lib.gm_match_batch(eng._h, pb, po, n, p_spans, p_ids, ids_cap, C.byref(need), p_status)
         assert rc == 0, lib.gm_last_error(eng._h)
 
-    for _ in range(2):
-        e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    def e2e_desc(k):
+        pb, po, _ = p_in[k % B]
+        rc = lib.gm_match_batch_desc(eng._h, pb, po, n, p_spans, p_desc, desc_cap, C.byref(need), p_status)
+        assert rc == 0, lib.gm_last_error(eng._h)
+
+    def timed_host_loop(fn, steps):
+        for k in range(2):
+            fn(k)
+        sync_all()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            fn(k)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    s_ids = timed_host_loop(e2e_ids, e2e_steps)
+    need_ids = int(need.value)
+    s_desc = timed_host_loop(e2e_desc, e2e_steps)
+    need_desc = int(need.value)
+    h2d = int(np.mean([x[2] for x in p_in]) + 4 * (n + 1))
+    e2e = {"value": world * n * e2e_steps / s_desc, "unit": "topics/s", "mode": "descriptors (gm_match_batch_desc: per topic the matched value sets by reference, "
+           "8 B per matched filter; the host reads members from its mirror through gm_values_view)",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 + 4 * n + 8 * n + 8 * need_desc), "steps": e2e_steps,
+           "ids_mode": {"value": world * n * e2e_steps / s_ids, "unit": "topics/s", "entry": "gm_match_batch (every matched id materialised in host memory)",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 + 4 * n + 8 * n + 4 * need_ids)},
+           "buffers": f"pinned, NUMA node {lib.gm_device_numa_node(local)} (gm_host_alloc_near), {B} batches rotated"}
+
+    # ---- leg 3 (C5): the collective on the data path ---------------------------------------------------------------
+    # (a) weak + gather: every rank matches its own batch, then ONE all-gatherv makes every rank hold all world*n lists
+    # (b) strong: ONE mixed batch (identical on every rank, uniform over all roots) is partitioned by a device kernel,
+    #     every rank matches its share, the all-gatherv completes the batch on every rank
+    multi = None
+    parity = None
+    coll_steps = max(3, min(args.steps, 20))
+    mb, mo = wl.gen_topics(cfg, n, stream=424242)                         # the mixed batch: same bytes on every rank
+    d_mb, d_mo = torch.from_numpy(mb).to(dev), torch.from_numpy(mo.view(np.int32)).to(dev)
+    d_sel = torch.zeros(n, dtype=torch.int32, device=dev)
+    a_cap_t = world * n if world > 1 else n
+    a_idx = torch.empty(a_cap_t, dtype=torch.int32, device=dev)
+    a_spans = torch.empty((a_cap_t, 2), dtype=torch.int32, device=dev)
+    a_ids = torch.empty(int(needed_max * 1.3) * world + 4096, dtype=torch.int32, device=dev)
+    d_own_index = torch.arange(rank * n, (rank + 1) * n, dtype=torch.int32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    phase = np.zeros(3)
+    shard_counts = None
+
+    def strong_step(k, record=False):
+        nonlocal shard_counts
+        if record:
+            ev[0].record()
+        kk, shard_counts = eng.partition_batch_device(d_mb, d_mo, world, rank, d_sel, stream)
+        if record:
+            ev[1].record()
+        eng.match_batch_device_ex(d_mb, d_mo, d_spans, d_ids, d_needed, d_status, stream, d_sel=d_sel, n_sel=kk)
+        if record:
+            ev[2].record()
+        sizes = eng.allgatherv_device(d_sel, d_spans, kk, d_ids, d_needed, a_idx, a_spans, a_ids, stream)
+        if record:
+            ev[3].record()
+            torch.cuda.synchronize()
+            for j in range(3):
+                phase[j] += ev[j].elapsed_time(ev[j + 1])
+        return sizes
+
+    def weak_gather_step(k):
+        tb, to = d_batches[k % B]
+        eng.match_batch_device(tb, to, d_spans, d_ids, d_needed, d_status, stream)
+        eng.allgatherv_device(d_own_index, d_spans, n, d_ids, d_needed, a_idx, a_spans, a_ids, stream)
+
+    ms_strong = timed_device_loop(strong_step, coll_steps, 3)
+    for k in range(coll_steps):
+        strong_step(k, record=True)
+    ph = [max_over_ranks(float(x)) / coll_steps for x in phase]
+    sizes = strong_step(0)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    multi = {"strong": {"workload": f"one mixed {n}-topic batch (uniform over all roots, identical on every rank) partitioned on the device by root hash",
+                        "value": n * coll_steps / (ms_strong / 1e3), "unit": "topics/s", "ms_per_step": ms_strong / coll_steps, "steps": coll_steps,
+                        "phase_ms_max_over_ranks": {"partition": ph[0], "match": ph[1], "all_gatherv": ph[2]},
+                        "limiter": ["partition", "match", "all_gatherv"][int(np.argmax(ph))],
+                        "shard_load": {"max": int(shard_counts.max()), "mean": float(shard_counts.mean()), "per_shard": [int(x) for x in shard_counts]},
+                        "gathered_ids_per_step": int(sizes[:, 1].sum())}}
     if world > 1:
-        ts = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        e2e_s = float(ts.item())
-    e2e_value = world * n * e2e_steps / e2e_s
-    h2d = int(len(hb) + 4 * (n + 1))
-    d2h = int(8 + 4 * n + 8 * n + 4 * need.value)
-    for p in (p_blob, p_offs, p_spans, p_ids, p_status):
-        lib.gm_host_free(p)
+        ms_wg = timed_device_loop(weak_gather_step, coll_steps, 3)
+        multi["value_with_gather"] = world * n * coll_steps / (ms_wg / 1e3)
+        multi["weak_gather_ms_per_step"] = ms_wg / coll_steps
+        multi["collective"] = "gm_allgatherv_device: ncclAllGather of (topics, ids) per rank + one grouped launch of per-rank ncclBroadcasts out of the match kernels' buffers"
+
+    # ---- parity self-check of the sharded path: gathered lists of a >= 50 K-topic sample against the oracle (rank 0) ----
+    sizes = strong_step(0)
+    torch.cuda.synchronize()
+    if rank == 0:
+        from oracle import oracle as orc
+        orc.numa_interleave(True)
+        m_tot = int(sizes[:, 1].sum())
+        k_tot = int(sizes[:, 0].sum())
+        idx = a_idx[:k_tot].cpu().numpy()
+        sp = a_spans[:k_tot].cpu().numpy().view(np.uint32)
+        gi = a_ids[:m_tot].cpu().numpy().view(np.uint32)
+        ok = k_tot == n and (np.sort(idx) == np.arange(n)).all()
+        sample = min(n, 60_000)
+        fsb, fso, fsv = wl.gen_subs(cfg)
+        tree = orc.TopicTree()
+        tree.bulk_insert(fsb, fso, fsv, nthreads=min(orc.hardware_threads(), 64))
+        del fsb, fso
+        want = tree.match_batch(mb[:int(mo[sample])], mo[:sample + 1], nthreads=orc.hardware_threads(), want_ids=True)
+        del tree
+        if ok:
+            order = np.argsort(idx)[:sample]                      # rows of topics 0 .. sample-1
+            res = MatchResult(sp[order], gi, np.zeros(sample, np.int32), m_tot)
+            cg, ig = res.canonical()
+            seg = np.repeat(np.arange(sample, dtype=np.int64), np.maximum(want["counts"], 0))
+            iw = want["ids"][np.lexsort((want["ids"], seg))]
+            ok = bool((cg == want["counts"]).all() and len(ig) == len(iw) and (ig == iw).all())
+        parity = {"topics": sample, "ok": bool(ok), "path": f"gm_partition_batch_device -> gm_match_batch_device_ex -> gm_allgatherv_device over {world} rank(s), "
+                  "sorted id multiset of every sampled topic vs the oracle's TopicTree::matches"}
+    sync_all()
+    pin.free()
 
     if rank != 0:
         if world > 1:
@@ -305,56 +505,73 @@ def run_own(args):
     k_mean = kms.mean(axis=0) if len(kms) else np.zeros(3)
     k2_ms = float(k_mean[1])
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None
-    traffic = None
-    prof = ROOT / "profiles" / "k_match_fast_traffic.json"
+    traffic, traffic_src = None, "not measured in this run (ncu cannot run inside the timed bench)"
+    prof = ROOT / "profiles" / "k_match_fast_traffic.json"      # written next to the committed ncu report it was read from
     if prof.exists():
         try:
-            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            pj = json.loads(prof.read_text())
+            traffic, traffic_src = pj.get("dram_bytes_per_launch"), pj.get("source")
         except Exception:
             pass
-    if traffic is None:
-        traffic = 771856128   # dram__bytes_read.sum + dram__bytes_write.sum of k_match_fast, one C3 launch, profiles/r1_k2_windows.ncu-rep
+    kd = kms_desc.mean(axis=0) if len(kms_desc) else np.zeros(3)
     roofline = {"bound": "hbm", "kernel": "k_match_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k2_bytes, "kernel_ms": {"k_tokenize+k_bucket_scan+k_bucket_scatter": float(k_mean[0]), "k_match_fast": k2_ms, "k_match_slow": float(k_mean[2])},
                 "pipeline": {"algorithmic_bytes_per_step": k1_bytes + k2_bytes,
-                             "achieved": (k1_bytes + k2_bytes) / (float(k_mean.sum()) * 1e-3) / 1e9 if k_mean.sum() > 0 else None}}
+                             "achieved": (k1_bytes + k2_bytes) / (float(k_mean.sum()) * 1e-3) / 1e9 if k_mean.sum() > 0 else None,
+                             "frac_of_step": (k1_bytes + k2_bytes) / (ms / args.steps * 1e-3) / 1e9 / peak},
+                "descriptor_mode_kernel_ms": {"k_tokenize+k_bucket_scan+k_bucket_scatter": float(kd[0]), "k_match_fast": float(kd[1]), "k_match_slow": float(kd[2])}}
 
     # ---- CPU baseline: the oracle's DefaultRouter::_matches restatement on the host cores -----------
     cpu = None
+    c4 = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         threads = orc.hardware_threads()
+        orc.numa_interleave(True)
         sb, so, sv2 = wl.gen_subs(cfg)
         router = orc.Router()
         router.bulk_add(sb, so, sv2, nthreads=min(threads, 64))
         sample = min(n, 250_000)
         stb, sto = wl.gen_topics(cfg, sample)
         router.match_batch(stb, sto, nthreads=threads)
-        reps, secs = 0, 0.0
-        while secs < 4.0 and reps < 50:
-            secs += router.match_batch(stb, sto, nthreads=threads)["seconds"]
-            reps += 1
+        runs = []
+        secs = 0.0
+        while secs < 4.0 and len(runs) < 50:
+            r = router.match_batch(stb, sto, nthreads=threads)["seconds"]
+            runs.append(sample / r)
+            secs += r
         one = router.match_batch(stb[:int(sto[20000])], sto[:20001], nthreads=1)
-        cpu = {"value": sample * reps / secs, "unit": "topics/s", "cores": threads, "kind": "port",
-               "sample": f"{sample}-topic sample x {reps} reps of the same workload; C++ restatement of DefaultRouter::_matches "
-                         f"(oracle/oracle.cpp; the Rust reference cannot be built here: no cargo)",
-               "single_thread_value": 20000 / one["seconds"]}
+        cpu = {"value": sample * len(runs) / secs, "unit": "topics/s", "cores": threads, "kind": "port",
+               "sample": f"{sample}-topic sample x {len(runs)} reps of the same workload; C++ restatement of DefaultRouter::_matches "
+                         f"(oracle/oracle.cpp; the Rust reference cannot be built here: no cargo); reader threads pinned one per allowed CPU, "
+                         f"tree pages interleaved over NUMA nodes, work handed out in chunks",
+               "best_rep": max(runs), "worst_rep": min(runs), "single_thread_value": 20000 / one["seconds"]}
+        del router
+        if not args.no_c4:
+            c4 = _c4_leg(torch, dev, stream, peak, small)
 
     line = {
         "metric": "topic-matches/sec @10M subs", "value": value, "unit": "topics/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": _workload_desc(cfg, world), "l2": f"device tables {st['device_bytes'] / 1e9:.2f} GB >> 126 MB L2; {B} distinct topic batches rotated",
-                   "matched_ids_per_topic": W["ids"] / n, "visited_nodes_per_topic": W["visited"] / n, "deferred_topics_per_batch": W["deferred"], "probe_diag": diag,
+                   "matched_ids_per_topic": W["ids"] / n, "matched_filters_per_topic": W["filters"] / n, "visited_nodes_per_topic": W["visited"] / n,
+                   "deferred_topics_per_batch": W["deferred"], "probe_diag": diag,
                    "trie": {k: st[k] for k in ("values", "nodes", "edges", "edge_slots", "dict_entries", "plus_nodes", "device_bytes", "max_depth")},
-                   "build_s": round(build_s, 1), "e2e_timing": "perf_counter around synchronous gm_match_batch calls (pinned host buffers)"},
-        "e2e": {"value": e2e_value, "unit": "topics/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                   "build_s": round(build_s, 1), "e2e_timing": "perf_counter around synchronous C-ABI calls (pinned host buffers), max over ranks"},
+        "value_descriptor_mode": value_desc,
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "multi_gpu": multi,
+        "parity_check": parity,
+        "c4": c4,
         "clocks": clocks,
     }
+    if multi and "value_with_gather" in multi:
+        line["value_with_gather"] = multi["value_with_gather"]
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

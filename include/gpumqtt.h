@@ -36,7 +36,8 @@ typedef enum gm_status {
     GM_ERR_TOO_DEEP = -5,      /* filter has more levels than gm_config.max_levels (cf. listener max_topic_levels, rmqtt/src/session.rs:1275) */
     GM_ERR_NO_DEVICE = -6,     /* no CUDA device: there is NO CPU fallback */
     GM_ERR_TOO_LARGE = -7,     /* batch exceeds a 32-bit offset (blob >= 4 GiB or ids >= 2^32) */
-    GM_ERR_INTERNAL = -8
+    GM_ERR_INTERNAL = -8,
+    GM_ERR_COMM = -9           /* NCCL missing or a collective failed */
 } gm_status;
 
 typedef struct gm_config {
@@ -128,6 +129,42 @@ int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_topics_blob, uin
                                     uint32_t* d_out_ids, uint64_t cap_ids, uint64_t* d_needed,
                                     int32_t* d_status, void* stream, gm_work* work);
 
+/* ---- general device-buffer entry point: descriptor output, selection of a sub-batch, work counters ----------------
+ * d_blob must be readable in whole aligned 32-bit words (any cudaMalloc'd buffer or slice of one is).                */
+#define GM_MATCH_DESCRIPTORS 1u   /* d_out receives gm_desc[] (one per matched FILTER) instead of u32 ids; cap / needed count descriptors */
+typedef struct gm_desc {          /* reference to the value set of one matched filter node (rmqtt/src/trie.rs:70 BTreeSet<V>)             */
+    uint32_t ref;                 /* cnt == 1: the value itself; 2 <= cnt < 65535: values[ref .. ref+cnt); cnt == 65535: ranges[ref] = {off, cnt} */
+    uint32_t cnt;
+} gm_desc;
+typedef struct gm_match_args {
+    uint32_t struct_size, flags;  /* = sizeof(gm_match_args); GM_MATCH_* */
+    const void* d_blob; uint64_t blob_bytes;
+    const uint32_t* d_offsets; uint64_t n_entries;   /* the packed batch: n_entries + 1 offsets */
+    const uint32_t* d_sel;        /* NULL: match every entry (n = n_entries); else row t matches entry d_sel[t], t < n (a rank's share of a
+                                     mixed batch, see gm_partition_batch_device) */
+    uint64_t n;
+    gm_span* d_spans; void* d_out; uint64_t cap; uint64_t* d_needed; int32_t* d_status;
+    void* stream;
+    gm_work* work;                /* optional: exact work counters (instrumented, slower; synchronises the stream) */
+} gm_match_args;
+int32_t gm_match_batch_device_ex(gm_engine* e, const gm_match_args* a);
+
+/* ---- descriptor mode with host buffers: what DefaultRouter::_matches consumes is one relations entry per matched filter
+ *      (rmqtt/src/router.rs:166-182), so the engine can return the matched value SETS by reference (8 B per matched
+ *      filter, ~4x less D2H traffic than 4 B per matched id) and the host reads the members from its own mirror.     */
+int32_t gm_match_batch_desc(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
+                            gm_span* out_spans, gm_desc* out_descs, uint64_t cap_descs, uint64_t* needed, int32_t* status);
+typedef struct gm_values {        /* host mirror of the value-set storage.  The two base pointers never change for the lifetime of
+                                     the engine; entries a descriptor refers to stay intact while `epoch` is unchanged (mutations
+                                     only append; gm_compact / automatic value compaction bump the epoch).                           */
+    const uint32_t* values; uint64_t n_values;
+    const gm_span* ranges; uint64_t n_ranges;        /* {off, cnt} of sets with >= 65535 members */
+    uint64_t epoch;
+} gm_values;
+int32_t gm_values_view(gm_engine* e, gm_values* out);
+/* convenience: expand descriptors into ids on the host (memcpy out of the mirror) */
+int32_t gm_desc_expand(gm_engine* e, const gm_desc* descs, uint64_t n, uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed);
+
 /* ---- retained-message tree: RetainTree<u32> (rmqtt/src/retain.rs:202-257), driven by RetainStorage::set
  *      (rmqtt-plugins/rmqtt-retainer/src/ram.rs:55-73 -> rmqtt/src/retain.rs:131-149: remove, then insert unless the
  *      payload is empty).  `value` is the caller's handle of the retained message; set replaces (Option::replace).  */
@@ -181,6 +218,30 @@ int32_t gmr_matches_batch(gm_router* r, const gm_id* publishers, const char* top
                           uint64_t* needed_rels, uint64_t* needed_sub_ids, int32_t* status);
 int32_t gmr_relation(gm_router* r, uint32_t handle, const char** filter, uint32_t* filter_len, const char** client, uint32_t* client_len);
 
+/* ---- multi-GPU (BASELINE.json C5): one engine per GPU / process holds the filters of its root-hash shard
+ *      (gm_shard_of; root-wildcard filters are replicated).  The host layer distributes the communicator id (in rmqtt: the
+ *      cluster layer, rmqtt-plugins/rmqtt-cluster-raft; here torch.distributed or any channel).  libnccl is bound with
+ *      dlopen at the first gm_comm_* call: GM_ERR_COMM when it is missing.                                                   */
+#define GM_COMM_ID_BYTES 128
+int32_t gm_comm_unique_id(uint8_t* out_id /* [GM_COMM_ID_BYTES] */);                 /* rank 0: ncclGetUniqueId */
+int32_t gm_comm_init(gm_engine* e, const uint8_t* id, uint32_t rank, uint32_t world);  /* every rank, same id (collective) */
+int32_t gm_comm_destroy(gm_engine* e);
+/* Partition of a MIXED batch on the device: d_sel receives the entries whose root hashes to `rank` (order unspecified),
+ * *n_local how many; optional d_shard[n] = shard of every entry, shard_counts[n_shards] (host) = load of every shard.
+ * Feed d_sel / *n_local to gm_match_batch_device_ex.  Synchronises the stream (n_local is a host value).                   */
+int32_t gm_partition_batch_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offsets, uint64_t n,
+                                  uint32_t n_shards, uint32_t rank, uint32_t* d_sel, uint32_t* d_shard, uint64_t* n_local,
+                                  uint64_t* shard_counts, void* stream);
+/* The ONE collective of the path: all-gatherv of per-rank match lists, device buffers in, device buffers out, identical on
+ * every rank.  Local contribution: k topics with global indices d_index[k] (= d_sel), d_spans[k] into d_ids[*d_m] (*d_m is the
+ * DEVICE counter the match wrote: d_needed).  Output, rank-major: d_all_index / d_all_spans (re-based onto d_all_ids) /
+ * d_all_ids; sizes[2*r] = topics, sizes[2*r+1] = ids of rank r (host array, 2*world).  ncclAllGather of the sizes + one
+ * grouped launch of ncclBroadcasts reading the match kernels' own output buffers.  Collective: every rank must call it.
+ * GM_ERR_CAPACITY when an output is too small (sizes[] is valid then).  Asynchronous on `stream` after one host sync.      */
+int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_span* d_spans, uint64_t k, const uint32_t* d_ids,
+                             const uint64_t* d_m, uint32_t* d_all_index, gm_span* d_all_spans, uint64_t cap_topics,
+                             uint32_t* d_all_ids, uint64_t cap_ids, uint64_t* sizes, void* stream);
+
 /* ---- tokeniser only (Topic::from_str for a batch) — used by tests to pin the device dictionary.
  *      out_tokens: [max_tok][n] u32 (level-major), out_meta: [n] (bits 0..23 levels, bit 30 '$', bit 31 invalid) */
 int32_t gm_tokenize_batch(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
@@ -211,6 +272,13 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
 int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value);
 /* pinned host memory for the host-buffer entry points */
 void* gm_host_alloc(uint64_t bytes);
+/* the same, placed on the NUMA node the engine's GPU hangs off (its PCIe root): on a 2-socket server a pinned buffer on
+ * the far socket crosses the inter-socket link on every copy.  Falls back to gm_host_alloc placement without NUMA info. */
+void* gm_host_alloc_near(gm_engine* e, uint64_t bytes);
+int32_t gm_device_numa_node(int32_t device);            /* -1 unknown */
+/* restricts the CALLING thread (and threads it creates later) to the CPUs of the GPU's NUMA node and prefers that
+ * node for its allocations — what each per-GPU worker of a multi-GPU host should do once at start                      */
+int32_t gm_bind_thread_near_device(int32_t device);
 void gm_host_free(void* p);
 
 #ifdef __cplusplus

@@ -21,8 +21,15 @@
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load
 // this library.  It is "a C++ restatement of the reference algorithm", never "the reference binary".
+#include <pthread.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -424,14 +431,45 @@ struct RetainNode {
 using Tree = TrieNode<uint64_t>;
 using RTree = RetainNode<int64_t>;
 
+// CPUs this process may run on (cgroup cpuset / affinity mask), in order
+static const std::vector<int>& allowed_cpus() {
+    static const std::vector<int> cpus = [] {
+        std::vector<int> v;
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0)
+            for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &set)) v.push_back(c);
+        return v;
+    }();
+    return cpus;
+}
+static void pin_self(int k) {
+    const auto& cpus = allowed_cpus();
+    if (cpus.empty()) return;
+    cpu_set_t s;
+    CPU_ZERO(&s);
+    CPU_SET(cpus[static_cast<size_t>(k) % cpus.size()], &s);
+    pthread_setaffinity_np(pthread_self(), sizeof(s), &s);
+}
+
+// Reader threads over a batch: one thread per allowed CPU (pinned, so the measurement does not depend on where the
+// scheduler happens to put 128 threads), work handed out in small chunks from a shared counter (no straggler slice).
+// f(tid, b, e) may be called many times per thread.
 template <class F>
 static void parallel_for(uint64_t n, int nthreads, F&& f) {
     if (nthreads <= 1 || n < 64) { f(0, 0, n); return; }
     std::vector<std::thread> th;
-    uint64_t chunk = (n + nthreads - 1) / nthreads;
+    std::atomic<uint64_t> next{0};
+    const uint64_t grain = std::max<uint64_t>(16, std::min<uint64_t>(1024, n / (static_cast<uint64_t>(nthreads) * 16)));
     for (int t = 0; t < nthreads; ++t) {
-        uint64_t b = std::min<uint64_t>(n, t * chunk), e = std::min<uint64_t>(n, b + chunk);
-        th.emplace_back([=, &f] { f(t, b, e); });
+        th.emplace_back([=, &f, &next] {
+            pin_self(t);
+            for (;;) {
+                const uint64_t b = next.fetch_add(grain, std::memory_order_relaxed);
+                if (b >= n) break;
+                f(t, b, std::min<uint64_t>(n, b + grain));
+            }
+        });
     }
     for (auto& t : th) t.join();
 }
@@ -558,7 +596,7 @@ double orc_tree_match_batch(void* tp, const char* blob, const uint32_t* offs, ui
             });
             if (counts) counts[i] = static_cast<int64_t>(k);
         }
-        cs[tid] = c;
+        cs[tid].add(c);
     });
     double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     Counters tot; for (auto& c : cs) tot.add(c);
@@ -653,7 +691,7 @@ double orc_router_match_batch(void* rp, const char* blob, const uint32_t* offs, 
             if (counts) counts[i] = ok ? static_cast<int64_t>(v.size()) : -1;
             tot[tid] += v.size();
         }
-        cs[tid] = c;
+        cs[tid].add(c);
     });
     double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     Counters t; uint64_t s = 0;
@@ -714,7 +752,7 @@ double orc_retain_match_batch(void* tp, const char* blob, const uint32_t* offs, 
             if (counts) counts[i] = static_cast<int64_t>(v.size());
             if (out_ids) for (size_t k = 0; k < v.size(); ++k) out_ids[out_offs[i] + k] = static_cast<uint32_t>(v[k]);
         }
-        cs[tid] = c;
+        cs[tid].add(c);
     });
     double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     Counters tot; for (auto& c : cs) tot.add(c);
@@ -722,6 +760,36 @@ double orc_retain_match_batch(void* tp, const char* blob, const uint32_t* offs, 
     return dt;
 }
 
-int32_t orc_hardware_threads() { return static_cast<int32_t>(std::thread::hardware_concurrency()); }
+// threads the batch functions should use: the CPUs this process is allowed on (not the machine's total)
+int32_t orc_hardware_threads() {
+    const size_t n = allowed_cpus().size();
+    return static_cast<int32_t>(n ? n : std::thread::hardware_concurrency());
+}
+
+// Memory policy of the calling thread (inherited by the threads it creates): interleave new pages over all online
+// NUMA nodes — a tree built by one socket's threads and read by both otherwise makes the multi-threaded baseline
+// depend on where its pages happened to land.  Returns 0 on success, -1 if the kernel refused (harmless).
+int32_t orc_numa_interleave(int32_t on) {
+    unsigned long mask[16] = {0};
+    unsigned long maxnode = 0;
+    if (on) {
+        FILE* f = std::fopen("/sys/devices/system/node/online", "r");
+        if (!f) return -1;
+        char buf[256] = {0};
+        if (!std::fgets(buf, sizeof(buf), f)) { std::fclose(f); return -1; }
+        std::fclose(f);
+        for (char* p = buf; *p;) {                                    // "0-1,4" style list
+            char* e;
+            long a = std::strtol(p, &e, 10), b = a;
+            if (e == p) break;
+            if (*e == '-') { p = e + 1; b = std::strtol(p, &e, 10); }
+            for (long k = a; k <= b && k < 1024; ++k) { mask[k / (8 * sizeof(long))] |= 1ul << (k % (8 * sizeof(long))); maxnode = std::max<unsigned long>(maxnode, k + 1); }
+            p = (*e == ',') ? e + 1 : e;
+            if (*e != ',') break;
+        }
+        if (maxnode < 2) return 0;                                    // one node: nothing to interleave
+    }
+    return syscall(SYS_set_mempolicy, on ? 3 /* MPOL_INTERLEAVE */ : 0 /* MPOL_DEFAULT */, on ? mask : nullptr, on ? maxnode + 1 : 0) == 0 ? 0 : -1;
+}
 
 }  // extern "C"

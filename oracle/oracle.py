@@ -76,6 +76,7 @@ def lib():
         "orc_retain_match": (i64, [vp, cp, u32, P(i64), u64, P(Counters)]),
         "orc_retain_match_batch": (C.c_double, [vp, vp, vp, u64, C.c_int, vp, vp, vp, P(Counters)]),
         "orc_hardware_threads": (i32, []),
+        "orc_numa_interleave": (i32, [i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -124,7 +125,13 @@ def matches_str(filt, topic):
 
 
 def hardware_threads() -> int:
+    """CPUs this process may run on (affinity mask / cpuset) — what the multi-threaded batch calls should use."""
     return max(1, int(lib().orc_hardware_threads()))
+
+
+def numa_interleave(on: bool = True) -> bool:
+    """Interleave this thread's (and its future threads') new pages over all NUMA nodes; call before building a tree."""
+    return int(lib().orc_numa_interleave(1 if on else 0)) == 0
 
 
 class TopicTree:

@@ -17,6 +17,9 @@ GM_ERR_TOO_DEEP = -5
 GM_ERR_NO_DEVICE = -6
 GM_ERR_TOO_LARGE = -7
 GM_ERR_INTERNAL = -8
+GM_ERR_COMM = -9
+GM_MATCH_DESCRIPTORS = 1
+GM_COMM_ID_BYTES = 128
 GM_FLAG_MANUAL_FLUSH = 1
 GM_FLAG_HOST_ONLY = 2
 
@@ -59,6 +62,17 @@ class GmWork(C.Structure):
         return d
 
 
+class GmMatchArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("d_blob", C.c_void_p), ("blob_bytes", C.c_uint64),
+                ("d_offsets", C.c_void_p), ("n_entries", C.c_uint64), ("d_sel", C.c_void_p), ("n", C.c_uint64),
+                ("d_spans", C.c_void_p), ("d_out", C.c_void_p), ("cap", C.c_uint64), ("d_needed", C.c_void_p), ("d_status", C.c_void_p),
+                ("stream", C.c_void_p), ("work", C.POINTER(GmWork))]
+
+
+class GmValues(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("n_values", C.c_uint64), ("ranges", C.c_void_p), ("n_ranges", C.c_uint64), ("epoch", C.c_uint64)]
+
+
 # every symbol include/gpumqtt.h declares: name -> (restype, argtypes)
 _vp, _cp, _u32, _u64, _i32 = C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_int32
 _P = C.POINTER
@@ -75,6 +89,15 @@ SIGNATURES = {
     "gm_match_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
     "gm_match_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp]),
     "gm_match_batch_device_stats": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _vp, _vp, _P(GmWork)]),
+    "gm_match_batch_device_ex": (_i32, [_vp, _P(GmMatchArgs)]),
+    "gm_match_batch_desc": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
+    "gm_values_view": (_i32, [_vp, _P(GmValues)]),
+    "gm_desc_expand": (_i32, [_vp, _vp, _u64, _vp, _u64, _P(_u64)]),
+    "gm_comm_unique_id": (_i32, [_vp]),
+    "gm_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
+    "gm_comm_destroy": (_i32, [_vp]),
+    "gm_partition_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, _vp, _P(_u64), _vp, _vp]),
+    "gm_allgatherv_device": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
     "gm_retain_set": (_i32, [_vp, _cp, _u32, _u32, _P(_i32), _P(_u32)]),
     "gm_retain_remove": (_i32, [_vp, _cp, _u32, _P(_i32), _P(_u32)]),
     "gm_retain_bulk_load": (_i32, [_vp, _vp, _vp, _vp, _u64, _P(_u64)]),
@@ -97,6 +120,9 @@ SIGNATURES = {
     "gm_debug_table": (_i32, [_vp, _u32, _P(_vp), _P(_u64)]),
     "gm_debug_knob": (_i32, [_vp, C.c_char_p, C.c_int64]),
     "gm_host_alloc": (_vp, [_u64]),
+    "gm_host_alloc_near": (_vp, [_vp, _u64]),
+    "gm_device_numa_node": (_i32, [_i32]),
+    "gm_bind_thread_near_device": (_i32, [_i32]),
     "gm_host_free": (None, [_vp]),
 }
 

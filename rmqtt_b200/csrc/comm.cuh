@@ -1,0 +1,119 @@
+// Multi-GPU side of the path (BASELINE.json C5): the subscription set is sharded by the hash of the
+// topic root over the ranks (one process per GPU), a mixed PUBLISH batch is partitioned by the same hash ON THE
+// DEVICE, every rank matches its share, and ONE all-gatherv makes every rank hold every topic's match list —
+// the device-side analogue of results crossing nodes in rmqtt-cluster-raft/src/shared.rs:395-445.
+//
+// NCCL has no native all-gatherv: the collective is an ncclAllGather of the per-rank sizes (k topics, m ids)
+// followed by ONE grouped launch of per-rank ncclBroadcasts that read straight out of the buffers the match
+// kernels wrote (topic index, spans, ids) and land in pre-sized contiguous arrays; a small kernel re-bases the
+// received spans.  libnccl is bound at run time (dlopen) so that the library loads, and everything single-GPU
+// works, on hosts without NCCL; inside a torch process the already-loaded libnccl.so.2 is reused.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <mutex>
+#include <string>
+
+#include "layout.h"
+
+namespace gm {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    void* handle = nullptr;
+    std::string error;
+
+    static NcclApi& get() {
+        static NcclApi api;
+        static std::once_flag once;
+        std::call_once(once, [] { api.load(); });
+        return api;
+    }
+    bool ok() const { return handle != nullptr && error.empty(); }
+
+  private:
+    template <class F> void sym(F& f, const char* name) {
+        f = reinterpret_cast<F>(dlsym(handle, name));
+        if (!f && error.empty()) error = std::string("libnccl: missing symbol ") + name;
+    }
+    void load() {
+        // a library with this SONAME that the process already holds (torch's bundled NCCL) wins
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+            if (!handle) handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { error = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""); return; }
+        sym(GetUniqueId, "ncclGetUniqueId"); sym(CommInitRank, "ncclCommInitRank"); sym(CommDestroy, "ncclCommDestroy");
+        sym(AllGather, "ncclAllGather"); sym(Broadcast, "ncclBroadcast"); sym(GroupStart, "ncclGroupStart"); sym(GroupEnd, "ncclGroupEnd");
+        sym(GetErrorString, "ncclGetErrorString"); sym(GetVersion, "ncclGetVersion");
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Partition of a mixed batch: shard of every topic by its level-0 string — the SAME function the host uses to place
+// filters (HostTrie::level0_hash -> shard_of_hash, gm_shard_of) — and compaction of this rank's topics into `sel`.
+// Warp-aggregated append; the order inside `sel` is irrelevant (every row carries its global index).
+// counts[r] receives the number of topics of shard r (load report); counts[nshards] = rows appended to sel.
+__global__ void __launch_bounds__(256)
+k_partition(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__ offs, u32 n, u32 nshards, u32 rank, u32* __restrict__ sel,
+            u32* __restrict__ shard_out, u32* __restrict__ counts) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = threadIdx.x & 31;
+    u32 shard = 0xFFFFFFFFu;
+    if (t < n) {
+        const u32 b = offs[t], e = min(offs[t + 1], blob_bytes);
+        u32 h = FNV_INIT, l0 = 0;
+        for (u32 i = b; i < e; ++i) {
+            const u32 c = blob[i];
+            if (c == '/') break;
+            h = fnv_step(h, c);
+            ++l0;
+        }
+        // a literal "+" / "#" root goes to shard 0 (any shard holds the replicated root wildcards; sharding.py partition_topics)
+        const bool wild_root = l0 == 1 && (blob[b] == '+' || blob[b] == '#');
+        shard = wild_root ? 0u : shard_of_hash(dict_hash_finish(h, l0), nshards);
+        if (shard_out) shard_out[t] = shard;
+        atomicAdd(counts + shard, 1u);
+    }
+    const bool mine = shard == rank;
+    const u32 bal = __ballot_sync(0xFFFFFFFFu, mine);
+    if (bal) {
+        u32 base = 0;
+        const int leader = __ffs(bal) - 1;
+        if (static_cast<int>(lane) == leader) base = atomicAdd(counts + nshards, static_cast<u32>(__popc(bal)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (mine) sel[base + __popc(bal & ((1u << lane) - 1u))] = t;
+    }
+}
+
+// after the all-gatherv: spans of rank r's topics index rank r's id array; make them index the gathered array
+__global__ void k_rebase_spans(uint2* __restrict__ spans, const unsigned long long* __restrict__ sizes /* [world][2] = (k, m) */, u32 world, u32 total_topics) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_topics) return;
+    unsigned long long ko = 0, mo = 0;
+    for (u32 r = 0; r < world; ++r) {
+        const unsigned long long k = sizes[2 * r], m = sizes[2 * r + 1];
+        if (i < ko + k) break;
+        ko += k; mo += m;
+    }
+    if (mo) { uint2 s = spans[i]; s.x += static_cast<u32>(mo); spans[i] = s; }
+}
+
+// (k, m) of this rank into the send slot of the size exchange: m comes from the device cursor of the match
+__global__ void k_comm_sizes(unsigned long long* out, unsigned long long k, const unsigned long long* d_m) {
+    out[0] = k;
+    out[1] = *d_m;
+}
+
+}  // namespace gm

@@ -2,17 +2,23 @@
 // (kernels.cuh).  There is no CPU fallback: without a CUDA device every entry point that would match
 // returns GM_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/gpumqtt.h"
 #include "host_trie.h"
+#include "comm.cuh"
 #include "kernels.cuh"
 #include "retain_kernels.cuh"
 #include "retain_tree.h"
@@ -104,6 +110,11 @@ struct gm_engine {
     u32 r_cap_items = 1u << 22, r_cap_desc = 1u << 22;   // totals over the RQ slices of each queue
     u64 launches = 0;
     bool k2_attr_set = false;
+    // multi-GPU (comm.cuh): NCCL communicator of the root-hash shards, scratch of the size exchange
+    ncclComm_t comm = nullptr;
+    u32 comm_rank = 0, comm_world = 1;
+    DevBuf d_comm, d_part;
+    unsigned long long* h_comm = nullptr;   // pinned [2 * world + 64]
     // tuning / diagnostics knobs, read from the environment once at creation
     struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; } knobs;
     void read_knobs() {
@@ -136,8 +147,9 @@ struct gm_engine {
 
     // ---- flush: ship the staged mutations to HBM on the side stream -------------------------------
     // Scatter the listed (already final) host slots into the device copy of the table.
-    template <class T, class A>
-    int patch_table(DevBuf& buf, const std::vector<T, A>& host, std::vector<u32>& dirty) {
+    template <class V>
+    int patch_table(DevBuf& buf, const V& host, std::vector<u32>& dirty) {
+        using T = std::remove_cv_t<std::remove_reference_t<decltype(host[0])>>;
         std::sort(dirty.begin(), dirty.end());
         dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
         const u32 nd = static_cast<u32>(dirty.size());
@@ -174,8 +186,9 @@ struct gm_engine {
     }
 
     // Append-only arrays (plus, ranges, values, pool): copy the new tail; patch older entries that changed.
-    template <class T, class A>
-    int upload_appendable(DevBuf& buf, const std::vector<T, A>& host, size_t& up, std::vector<u32>* dirty) {
+    template <class V>
+    int upload_appendable(DevBuf& buf, const V& host, size_t& up, std::vector<u32>* dirty) {
+        using T = std::remove_cv_t<std::remove_reference_t<decltype(host[0])>>;
         const size_t bytes = host.size() * sizeof(T);
         if (bytes > buf.cap) {   // grow: re-ship the whole array from the mirror
             CUDA_TRY(buf.ensure(std::max(bytes * 2, size_t(4096))));
@@ -258,8 +271,11 @@ struct gm_engine {
     }
 
     // ---- the match pipeline, all on `s`, all buffers on the device ---------------------------------
-    int enqueue_match(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids,
-                      u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool keep_cursor = false) {
+    // `desc`: descriptor mode (d_ids_ is then a uint2 array of value-set references, cap_ids counts descriptors).
+    // `d_sel`: optional selection — row t matches entry d_sel[t] of the packed batch (n = number of selected rows).
+    int enqueue_match(const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, void* d_ids_, u64 cap_ids,
+                      u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool keep_cursor = false, bool desc = false,
+                      const u32* d_sel = nullptr) {
         if (n == 0) { if (d_needed) CUDA_TRY(cudaMemsetAsync(d_needed, 0, sizeof(u64), s)); return GM_OK; }
         if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
@@ -300,7 +316,7 @@ struct gm_engine {
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
         k_tokenize<<<(n32 + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-            static_cast<const u8*>(d_blob_), d_offs_, n32, tv, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, bkey, hist, site_bits, sub_bits);
+            static_cast<const u8*>(d_blob_), static_cast<u32>(blob_bytes), d_offs_, d_sel, n32, tv, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, bkey, hist, site_bits, sub_bits);
         k_bucket_scan<<<1, 1024, 0, s>>>(hist, bcursor, NBUCKETS);
         k_bucket_scatter<<<(n32 + 255) / 256, 256, 0, s>>>(bkey, bcursor, n32, perm, d_tok8.as<u32>(), d_meta.as<u32>(),
                                                             sorted_rows ? tok8_sorted : nullptr, meta_sorted);
@@ -309,24 +325,27 @@ struct gm_engine {
 
         MatchParams mp{};
         mp.tv = tv; mp.tok8 = d_tok8.as<u32>(); mp.tok = d_tok.as<u32>(); mp.meta = d_meta.as<u32>(); mp.n = n32; mp.tok_levels = S;
-        mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = d_ids_; mp.cap_ids = cap_ids;
+        mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = static_cast<u32*>(d_ids_); mp.out_desc = static_cast<uint2*>(d_ids_); mp.cap_ids = cap_ids;
+        mp.status = d_status_;
         mp.cursor = &ctrl->cursor; mp.slow_list = d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
         mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
         mp.flags = (sorted_rows ? MP_SORTED_ROWS : 0u) | knobs.diag_flags;
         mp.tile_chunk = knobs.tile_chunk;
         constexpr size_t k2_smem = k2_smem_bytes<K2_FAST_L, K2_THREADS>();
+        auto k2_ss = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true, false>;
+        auto k2_sd = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true, true>;
+        auto k2_ns = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, false>;
+        auto k2_nd = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, true>;
         if (!k2_attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
-            CUDA_TRY(cudaFuncSetAttribute(k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
+            for (auto k : {k2_ss, k2_sd, k2_ns, k2_nd}) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
             k2_attr_set = true;
         }
-        if (stats) k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true><<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
-        else k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false><<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
+        (stats ? (desc ? k2_sd : k2_ss) : (desc ? k2_nd : k2_ns))<<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[2], s));
-        if (stats) k_match_slow<true><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
-        else k_match_slow<false><<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
+        auto k3 = stats ? (desc ? k_match_slow<true, true> : k_match_slow<true, false>) : (desc ? k_match_slow<false, true> : k_match_slow<false, false>);
+        k3<<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[3], s));
         ring_n++;
@@ -340,7 +359,7 @@ struct gm_engine {
     // ---- retained lookup: tokenise filters -> frontier BFS (one step kernel per tree level) -> publish ----
     struct RCtl { unsigned long long grand; u32 err; u32 pad; u32 n_desc[RQ]; u32 counts[RQ]; };   // counts[(max_depth + 3) * RQ] follow
 
-    int enqueue_retain(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s) {
+    int enqueue_retain(const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s) {
         const u32 nq = static_cast<u32>(n);
         const u32 depth = dev_rview.max_depth;
         const u32 S = depth + 2;                       // the walk reads filter levels pos and pos+1 with pos <= tree depth
@@ -364,7 +383,7 @@ struct gm_engine {
         u32* qcur = qbase + nq;
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
-        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), d_offs_, nq, dev_view, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr, 0u, 0u);
+        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), static_cast<u32>(blob_bytes), d_offs_, nullptr, nq, dev_view, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr, 0u, 0u);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
         RetainParams rp{};
@@ -390,9 +409,9 @@ struct gm_engine {
     }
 
     // runs the pipeline, growing the frontier / descriptor scratch until nothing overflowed; leaves *total
-    int run_retain(const void* d_blob_, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s, u64* total) {
+    int run_retain(const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s, u64* total) {
         for (int attempt = 0; attempt < 12; ++attempt) {
-            int st = enqueue_retain(d_blob_, d_offs_, n, d_spans_, d_ids_, cap_ids, d_status_, s);
+            int st = enqueue_retain(d_blob_, blob_bytes, d_offs_, n, d_spans_, d_ids_, cap_ids, d_status_, s);
             if (st != GM_OK) return st;
             RCtl h{};
             CUDA_TRY(cudaMemcpyAsync(&h, d_rctl.p, sizeof(RCtl), cudaMemcpyDeviceToHost, s));
@@ -474,6 +493,9 @@ void gm_destroy(gm_engine* e) {
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
     for (int i = 0; i < gm_engine::MAXC; ++i) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]); }
     if (e->h_cur) cudaFreeHost(e->h_cur);
+    if (e->comm) { NcclApi::get().CommDestroy(e->comm); e->comm = nullptr; }
+    if (e->h_comm) cudaFreeHost(e->h_comm);
+    e->d_comm.release(); e->d_part.release();
     if (e->ev_flush) cudaEventDestroy(e->ev_flush);
     if (e->ev_match) cudaEventDestroy(e->ev_match);
     for (auto& q : e->ev_ring) for (auto& ev : q) if (ev) cudaEventDestroy(ev);
@@ -537,52 +559,64 @@ int32_t gm_flush(gm_engine* e) {
     return e->flush_locked();
 }
 
-int32_t gm_match_batch_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
-                              gm_span* d_spans, uint32_t* d_ids, uint64_t cap_ids, uint64_t* d_needed, int32_t* d_status, void* stream) {
+// shared implementation of the device-buffer entry points
+static int32_t match_device_impl(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n_entries, const uint32_t* d_sel,
+                                 uint64_t n, gm_span* d_spans, void* d_out, uint64_t cap, uint64_t* d_needed, int32_t* d_status, void* stream,
+                                 bool desc, gm_work* work) {
     if (!e || (n && (!d_offs || !d_spans || !d_status))) return GM_ERR_INVALID_ARG;
     if (blob_bytes > 0xFFFFFFFFull) { g_err = "topic blob >= 4 GiB"; return GM_ERR_TOO_LARGE; }
     std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
     if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
-    return e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, static_cast<cudaStream_t>(stream), false);
-}
-
-int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
-                                    gm_span* d_spans, uint32_t* d_ids, uint64_t cap_ids, uint64_t* d_needed, int32_t* d_status,
-                                    void* stream, gm_work* work) {
-    if (!e || !work || (n && (!d_offs || !d_spans || !d_status))) return GM_ERR_INVALID_ARG;
-    if (blob_bytes > 0xFFFFFFFFull) { g_err = "topic blob >= 4 GiB"; return GM_ERR_TOO_LARGE; }
-    std::lock_guard<std::mutex> g(e->mu);
-    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
-    CUDA_TRY(cudaSetDevice(e->device));
-    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int st = e->enqueue_match(d_blob, d_offs, n, d_spans, d_ids, cap_ids, d_needed, d_status, s, true);
-    if (st != GM_OK) return st;
+    int st = e->enqueue_match(d_blob, blob_bytes, d_offs, n, d_spans, d_out, cap, d_needed, d_status, s, work != nullptr, false, desc, d_sel);
+    if (st != GM_OK || !work) return st;
     std::memset(work, 0, sizeof(*work));
     if (n == 0) return GM_OK;
     Ctrl h{};
-    std::vector<u32> meta(n), offs(n + 1);
+    std::vector<u32> meta(n), offs(n_entries + 1), sel(d_sel ? n : 0);
     CUDA_TRY(cudaMemcpyAsync(&h, e->d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(meta.data(), e->d_meta.p, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(offs.data(), d_offs, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(offs.data(), d_offs, (n_entries + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    if (d_sel) CUDA_TRY(cudaMemcpyAsync(sel.data(), d_sel, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     work->visited = h.stats[0]; work->probed = h.stats[1]; work->filters = h.stats[2]; work->ids = h.stats[3];
     work->deferred = h.slow_count;
     for (int k = 0; k < 8; ++k) { work->probes_by_depth[k] = h.stats[4 + k]; work->misses_by_depth[k] = h.stats[12 + k]; }
     work->slot_loads = h.stats[20];
     for (uint64_t i = 0; i < n; ++i)
-        if (!(meta[i] & META_INVALID)) { work->levels += meta[i] & META_NLEV_MASK; work->bytes += offs[i + 1] - offs[i]; }
+        if (!(meta[i] & META_INVALID)) { const u64 j = d_sel ? sel[i] : i; work->levels += meta[i] & META_NLEV_MASK; work->bytes += offs[j + 1] - offs[j]; }
     return GM_OK;
 }
 
-int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, uint32_t* out_ids,
-                       uint64_t cap_ids, uint64_t* needed, int32_t* status) {
-    if (!e || (n && (!offsets || !out_spans || !status)) || (cap_ids && !out_ids)) return GM_ERR_INVALID_ARG;
+int32_t gm_match_batch_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
+                              gm_span* d_spans, uint32_t* d_ids, uint64_t cap_ids, uint64_t* d_needed, int32_t* d_status, void* stream) {
+    return match_device_impl(e, d_blob, blob_bytes, d_offs, n, nullptr, n, d_spans, d_ids, cap_ids, d_needed, d_status, stream, false, nullptr);
+}
+
+int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n,
+                                    gm_span* d_spans, uint32_t* d_ids, uint64_t cap_ids, uint64_t* d_needed, int32_t* d_status,
+                                    void* stream, gm_work* work) {
+    if (!work) return GM_ERR_INVALID_ARG;
+    return match_device_impl(e, d_blob, blob_bytes, d_offs, n, nullptr, n, d_spans, d_ids, cap_ids, d_needed, d_status, stream, false, work);
+}
+
+int32_t gm_match_batch_device_ex(gm_engine* e, const gm_match_args* a) {
+    if (!a || a->struct_size < sizeof(gm_match_args)) return GM_ERR_INVALID_ARG;
+    if (a->d_sel && a->n > a->n_entries) return GM_ERR_INVALID_ARG;
+    return match_device_impl(e, a->d_blob, a->blob_bytes, a->d_offsets, a->d_sel ? a->n_entries : a->n, a->d_sel, a->n, a->d_spans, a->d_out, a->cap,
+                             a->d_needed, a->d_status, a->stream, (a->flags & GM_MATCH_DESCRIPTORS) != 0, a->work);
+}
+
+// shared implementation of the host-buffer entry points; `elem` = bytes per output element (4: ids, 8: descriptors)
+static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, void* out, size_t elem,
+                               uint64_t cap_ids, uint64_t* needed, int32_t* status) {
+    if (!e || (n && (!offsets || !out_spans || !status)) || (cap_ids && !out)) return GM_ERR_INVALID_ARG;
     if (needed) *needed = 0;
     if (n == 0) return GM_OK;
     if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
+    const bool desc = elem == 8;
     std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
@@ -593,9 +627,9 @@ int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, 
     CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
     CUDA_TRY(e->d_spans.ensure(n * sizeof(gm_span)));
     CUDA_TRY(e->d_status.ensure(n * sizeof(int32_t)));
-    CUDA_TRY(e->d_ids.ensure(std::max<u64>(cap_ids, 1) * sizeof(u32)));
+    CUDA_TRY(e->d_ids.ensure(std::max<u64>(cap_ids, 1) * elem));
     // Pipelined in chunks over three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of
-    // chunk c.  All chunks share one bump cursor, so the ids of chunk c are the contiguous range
+    // chunk c.  All chunks share one bump cursor, so the output of chunk c is the contiguous range
     // [cursor after c-1, cursor after c) and can be copied out as soon as that chunk's kernels finished.
     const u64 chunk = std::max<u64>(131072, (n + gm_engine::MAXC - 1) / gm_engine::MAXC);
     const int nchunks = static_cast<int>((n + chunk - 1) / chunk);
@@ -611,8 +645,8 @@ int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, 
     for (int c = 0; c < nchunks; ++c) {
         const u64 c0 = c * chunk, c1 = std::min<u64>(n, c0 + chunk);
         CUDA_TRY(cudaStreamWaitEvent(sc, e->ev_h2d[c], 0));
-        int st = e->enqueue_match(e->d_blob.p, e->d_offs.as<u32>() + c0, c1 - c0, e->d_spans.as<gm_span>() + c0, e->d_ids.as<u32>(), cap_ids, nullptr,
-                                  e->d_status.as<int32_t>() + c0, sc, false, c != 0);
+        int st = e->enqueue_match(e->d_blob.p, offsets[c1], e->d_offs.as<u32>() + c0, c1 - c0, e->d_spans.as<gm_span>() + c0, e->d_ids.p, cap_ids, nullptr,
+                                  e->d_status.as<int32_t>() + c0, sc, false, c != 0, desc);
         if (st != GM_OK) return st;
         CUDA_TRY(cudaMemcpyAsync(&e->h_cur[c], &e->d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, sc));
         CUDA_TRY(cudaEventRecord(e->ev_comp[c], sc));
@@ -626,15 +660,55 @@ int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, 
         CUDA_TRY(cudaMemcpyAsync(status + c0, e->d_status.as<int32_t>() + c0, (c1 - c0) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
         const u64 hi = std::min<u64>(cur, cap_ids);
         if (hi > done) {
-            CUDA_TRY(cudaMemcpyAsync(out_ids + done, e->d_ids.as<u32>() + done, (hi - done) * sizeof(u32), cudaMemcpyDeviceToHost, e->s_d2h));
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + done * elem, static_cast<char*>(e->d_ids.p) + done * elem, (hi - done) * elem, cudaMemcpyDeviceToHost, e->s_d2h));
             done = hi;
         }
     }
     CUDA_TRY(cudaStreamSynchronize(e->s_d2h));
     const u64 total = e->h_cur[nchunks - 1];
     if (needed) *needed = total;
-    if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
-    if (total > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
+    if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 output elements: split it"; return GM_ERR_TOO_LARGE; }
+    if (total > cap_ids) { g_err = "output buffer too small"; return GM_ERR_CAPACITY; }
+    return GM_OK;
+}
+
+int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, uint32_t* out_ids,
+                       uint64_t cap_ids, uint64_t* needed, int32_t* status) {
+    return match_host_impl(e, blob, offsets, n, out_spans, out_ids, sizeof(uint32_t), cap_ids, needed, status);
+}
+
+int32_t gm_match_batch_desc(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, gm_desc* out_descs,
+                            uint64_t cap_descs, uint64_t* needed, int32_t* status) {
+    static_assert(sizeof(gm_desc) == 8, "descriptor = one 64-bit value-set reference");
+    return match_host_impl(e, blob, offsets, n, out_spans, out_descs, sizeof(gm_desc), cap_descs, needed, status);
+}
+
+int32_t gm_values_view(gm_engine* e, gm_values* out) {
+    if (!e || !out) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    out->values = e->trie.values.data(); out->n_values = e->trie.values.size();
+    out->ranges = reinterpret_cast<const gm_span*>(e->trie.ranges.data()); out->n_ranges = e->trie.ranges.size();
+    out->epoch = e->trie.values_epoch;
+    return GM_OK;
+}
+
+int32_t gm_desc_expand(gm_engine* e, const gm_desc* descs, uint64_t n, uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed) {
+    if (!e || (n && !descs) || (cap_ids && !out_ids)) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    const u32* vals = e->trie.values.data();
+    const u64 nvals = e->trie.values.size();
+    u64 w = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        u32 ref = descs[i].ref, cnt = descs[i].cnt;
+        if (cnt == 1) { if (w < cap_ids) out_ids[w] = ref; ++w; continue; }
+        u64 off = ref;
+        if (cnt == CNT_BIG) { if (ref >= e->trie.ranges.size()) { g_err = "gm_desc_expand: stale descriptor"; return GM_ERR_INVALID_ARG; } off = e->trie.ranges[ref].off; cnt = e->trie.ranges[ref].cnt; }
+        if (off + cnt > nvals) { g_err = "gm_desc_expand: stale descriptor (values were compacted since the match)"; return GM_ERR_INVALID_ARG; }
+        if (w + cnt <= cap_ids) std::memcpy(out_ids + w, vals + off, cnt * sizeof(u32));
+        w += cnt;
+    }
+    if (needed) *needed = w;
+    if (w > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
     return GM_OK;
 }
 
@@ -680,7 +754,7 @@ int32_t gm_retain_match_batch_device(gm_engine* e, const void* d_blob, uint64_t 
     CUDA_TRY(cudaSetDevice(e->device));
     if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_rnodes.p || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
     u64 total = 0;
-    int st = e->run_retain(d_blob, d_offs, n, d_spans, d_ids, std::min<u64>(cap_ids, 0xFFFFFFFFull), d_status, static_cast<cudaStream_t>(stream), &total);
+    int st = e->run_retain(d_blob, blob_bytes, d_offs, n, d_spans, d_ids, std::min<u64>(cap_ids, 0xFFFFFFFFull), d_status, static_cast<cudaStream_t>(stream), &total);
     if (st != GM_OK) return st;
     if (needed) *needed = total;
     if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
@@ -708,7 +782,7 @@ int32_t gm_retain_match_batch(gm_engine* e, const char* blob, const uint32_t* of
     if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
     u64 total = 0;
-    int st = e->run_retain(e->d_blob.p, e->d_offs.as<u32>(), n, e->d_spans.as<gm_span>(), e->d_ids.as<u32>(), std::min<u64>(cap_ids, 0xFFFFFFFFull),
+    int st = e->run_retain(e->d_blob.p, blob_bytes, e->d_offs.as<u32>(), n, e->d_spans.as<gm_span>(), e->d_ids.as<u32>(), std::min<u64>(cap_ids, 0xFFFFFFFFull),
                            e->d_status.as<int32_t>(), s, &total);
     if (st != GM_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(status, e->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -786,6 +860,117 @@ int32_t gmr_relation(gm_router* r, uint32_t handle, const char** filter, uint32_
     return GM_OK;
 }
 
+// ---- multi-GPU: NCCL communicator, device partition of a mixed batch, all-gatherv of match lists (comm.cuh) ----------
+#define NCCL_TRY(expr)                                                                          \
+    do {                                                                                        \
+        ncclResult_t _r = (expr);                                                               \
+        if (_r != ncclSuccess) { g_err = std::string(#expr) + ": " + nc.GetErrorString(_r); return GM_ERR_COMM; } \
+    } while (0)
+
+int32_t gm_comm_unique_id(uint8_t* out_id) {
+    if (!out_id) return GM_ERR_INVALID_ARG;
+    NcclApi& nc = NcclApi::get();
+    if (!nc.ok()) { g_err = nc.error; return GM_ERR_COMM; }
+    static_assert(GM_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "gm_comm_unique_id hands out an ncclUniqueId");
+    ncclUniqueId id;
+    NCCL_TRY(nc.GetUniqueId(&id));
+    std::memcpy(out_id, id.internal, GM_COMM_ID_BYTES);
+    return GM_OK;
+}
+
+int32_t gm_comm_init(gm_engine* e, const uint8_t* id128, uint32_t rank, uint32_t world) {
+    if (!e || !id128 || world == 0 || rank >= world) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine has no device to communicate from"; return GM_ERR_NO_DEVICE; }
+    NcclApi& nc = NcclApi::get();
+    if (!nc.ok()) { g_err = nc.error; return GM_ERR_COMM; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (e->comm) { nc.CommDestroy(e->comm); e->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(id.internal, id128, GM_COMM_ID_BYTES);
+    NCCL_TRY(nc.CommInitRank(&e->comm, static_cast<int>(world), id, static_cast<int>(rank)));
+    e->comm_rank = rank; e->comm_world = world;
+    CUDA_TRY(e->d_comm.ensure((2 + 2 * static_cast<size_t>(world)) * sizeof(unsigned long long) + (static_cast<size_t>(world) + 2) * sizeof(u32)));
+    if (e->h_comm) { cudaFreeHost(e->h_comm); e->h_comm = nullptr; }
+    CUDA_TRY(cudaMallocHost(&e->h_comm, (2 * static_cast<size_t>(world) + 64) * sizeof(unsigned long long)));
+    return GM_OK;
+}
+
+int32_t gm_comm_destroy(gm_engine* e) {
+    if (!e) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->comm) { cudaSetDevice(e->device); NcclApi::get().CommDestroy(e->comm); e->comm = nullptr; }
+    e->comm_world = 1; e->comm_rank = 0;
+    return GM_OK;
+}
+
+int32_t gm_partition_batch_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offsets, uint64_t n, uint32_t n_shards,
+                                  uint32_t rank, uint32_t* d_sel, uint32_t* d_shard, uint64_t* n_local, uint64_t* shard_counts, void* stream) {
+    if (!e || !n_local || n_shards == 0 || n_shards > 4096 || rank >= n_shards || (n && (!d_blob || !d_offsets || !d_sel))) return GM_ERR_INVALID_ARG;
+    if (blob_bytes > 0xFFFFFFFFull || n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
+    *n_local = 0;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine has no device"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DevBuf& cb = e->d_part;
+    CUDA_TRY(cb.ensure((static_cast<size_t>(n_shards) + 1) * sizeof(u32)));
+    CUDA_TRY(cudaMemsetAsync(cb.p, 0, (static_cast<size_t>(n_shards) + 1) * sizeof(u32), s));
+    if (n) {
+        k_partition<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<const u8*>(d_blob), static_cast<u32>(blob_bytes), d_offsets, static_cast<u32>(n),
+                                                                            n_shards, rank, d_sel, d_shard, cb.as<u32>());
+        e->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    std::vector<u32> h(n_shards + 1);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), cb.p, h.size() * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *n_local = h[n_shards];
+    if (shard_counts) for (u32 r = 0; r < n_shards; ++r) shard_counts[r] = h[r];
+    return GM_OK;
+}
+
+int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_span* d_spans, uint64_t k, const uint32_t* d_ids, const uint64_t* d_m,
+                             uint32_t* d_all_index, gm_span* d_all_spans, uint64_t cap_topics, uint32_t* d_all_ids, uint64_t cap_ids, uint64_t* sizes,
+                             void* stream) {
+    if (!e || !d_m || !sizes || (k && (!d_index || !d_spans)) || !d_all_index || !d_all_spans || !d_all_ids) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!e->comm) { g_err = "gm_allgatherv_device: call gm_comm_init first"; return GM_ERR_INVALID_ARG; }
+    NcclApi& nc = NcclApi::get();
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const u32 W = e->comm_world, R = e->comm_rank;
+    unsigned long long* d_send = e->d_comm.as<unsigned long long>();
+    unsigned long long* d_all = d_send + 2;
+    // 1. sizes: (k, m) of every rank.  m lives on the device (the match kernels' cursor): no host hop before the exchange.
+    k_comm_sizes<<<1, 1, 0, s>>>(d_send, k, reinterpret_cast<const unsigned long long*>(d_m));
+    NCCL_TRY(nc.AllGather(d_send, d_all, 2, ncclUint64, e->comm, s));
+    CUDA_TRY(cudaMemcpyAsync(e->h_comm, d_all, 2 * static_cast<size_t>(W) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));      // NCCL needs the counts on the host: the one host synchronisation of the collective
+    u64 K = 0, M = 0;
+    for (u32 r = 0; r < W; ++r) { sizes[2 * r] = e->h_comm[2 * r]; sizes[2 * r + 1] = e->h_comm[2 * r + 1]; K += sizes[2 * r]; M += sizes[2 * r + 1]; }
+    if (M > 0xFFFFFFFFull) { g_err = "gathered match lists exceed 2^32 ids: split the batch"; return GM_ERR_TOO_LARGE; }
+    if (K > cap_topics || M > cap_ids) { g_err = "gm_allgatherv_device: output too small (sizes[] holds what every rank contributes)"; return GM_ERR_CAPACITY; }
+    // 2. one grouped launch: every rank broadcasts its three arrays straight out of the buffers the match kernels wrote
+    NCCL_TRY(nc.GroupStart());
+    u64 ko = 0, mo = 0;
+    for (u32 r = 0; r < W; ++r) {
+        const u64 kr = sizes[2 * r], mr = sizes[2 * r + 1];
+        if (kr) {
+            NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_index) : d_all_index + ko, d_all_index + ko, kr, ncclUint32, static_cast<int>(r), e->comm, s));
+            NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_spans) : d_all_spans + ko, d_all_spans + ko, kr, ncclUint64, static_cast<int>(r), e->comm, s));
+        }
+        if (mr) NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_ids) : d_all_ids + mo, d_all_ids + mo, mr, ncclUint32, static_cast<int>(r), e->comm, s));
+        ko += kr; mo += mr;
+    }
+    NCCL_TRY(nc.GroupEnd());
+    // 3. spans of rank r index rank r's ids: re-base them onto the gathered id array
+    if (K) { k_rebase_spans<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint2*>(d_all_spans), d_all, W, static_cast<u32>(K)); e->launches++; }
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GM_OK;
+}
+
 int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, uint32_t max_tok, uint32_t* out_tokens, uint32_t* out_meta) {
     if (!e || !max_tok || (n && (!offsets || !out_tokens || !out_meta))) return GM_ERR_INVALID_ARG;
     if (n == 0) return GM_OK;
@@ -807,7 +992,7 @@ int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offset
     CUDA_TRY(cudaMemsetAsync(tok.p, 0, static_cast<size_t>(max_tok) * n * sizeof(u32), s));
     CUDA_TRY(cudaStreamWaitEvent(s, e->ev_flush, 0));
     k_tokenize<<<(static_cast<u32>(n) + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-        e->d_blob.as<u8>(), e->d_offs.as<u32>(), static_cast<u32>(n), e->dev_view, max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr, 0u, 0u);
+        e->d_blob.as<u8>(), static_cast<u32>(blob_bytes), e->d_offs.as<u32>(), nullptr, static_cast<u32>(n), e->dev_view, max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr, 0u, 0u);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_tokens, tok.p, static_cast<size_t>(max_tok) * n * sizeof(u32), cudaMemcpyDeviceToHost, s));
@@ -908,6 +1093,70 @@ int32_t gm_shard_of_batch(const char* blob, const uint32_t* offsets, uint64_t n,
     if ((n && (!blob || !offsets || !out_shard)) || n_shards == 0) return GM_ERR_INVALID_ARG;
     for (uint64_t i = 0; i < n; ++i) out_shard[i] = gm_shard_of(blob + offsets[i], offsets[i + 1] - offsets[i], n_shards);
     return GM_OK;
+}
+
+// ---- NUMA placement of the host side (2-socket GPU servers: a pinned buffer on the far socket halves the PCIe rate and
+//      makes 8 ranks contend for the inter-socket link) ------------------------------------------------------------------
+static int device_numa_node(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c) *c = static_cast<char>(tolower(*c));
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+int32_t gm_device_numa_node(int32_t device) {
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return -1;
+    return device_numa_node(device);
+}
+
+int32_t gm_bind_thread_near_device(int32_t device) {
+    const int node = gm_device_numa_node(device);
+    if (node < 0) return GM_OK;                       // no NUMA information: nothing to do
+    const std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return GM_OK;
+    char buf[4096] = {0};
+    const bool ok = fgets(buf, sizeof(buf), f) != nullptr;
+    fclose(f);
+    if (!ok) return GM_OK;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&allowed); CPU_ZERO(&want);
+    sched_getaffinity(0, sizeof(allowed), &allowed);
+    int n_want = 0;
+    for (char* p = buf; *p;) {
+        char* e;
+        long a = strtol(p, &e, 10), b = a;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long k = a; k <= b && k < CPU_SETSIZE; ++k) if (CPU_ISSET(k, &allowed)) { CPU_SET(k, &want); ++n_want; }
+        if (*e != ',') break;
+        p = e + 1;
+    }
+    if (n_want) sched_setaffinity(0, sizeof(want), &want);
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(long))] |= 1ul << (node % (8 * sizeof(long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, static_cast<unsigned long>(node + 2));
+    return GM_OK;
+}
+
+void* gm_host_alloc_near(gm_engine* e, uint64_t bytes) {
+    const int node = (e && !(e->flags & GM_FLAG_HOST_ONLY)) ? device_numa_node(e->device) : -1;
+    unsigned long mask[16] = {0};
+    if (node >= 0) {
+        mask[node / (8 * sizeof(long))] |= 1ul << (node % (8 * sizeof(long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, static_cast<unsigned long>(node + 2));
+    }
+    void* p = nullptr;
+    if (e && !(e->flags & GM_FLAG_HOST_ONLY)) cudaSetDevice(e->device);
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) p = nullptr;
+    if (node >= 0) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    return p;
 }
 
 void* gm_host_alloc(uint64_t bytes) {

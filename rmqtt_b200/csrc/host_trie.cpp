@@ -468,7 +468,7 @@ void HostTrie::make_ref(u32 node) {
     if (n.nvals == 1) { n.ref = n.v0; n.cnt16 = 1; return; }
     const std::vector<u32>& m = multi_[node];
     u32 off = static_cast<u32>(values.size());
-    values.insert(values.end(), m.begin(), m.end());
+    values.append(m.begin(), m.end());
     if (n.nvals < CNT_BIG) { n.ref = off; n.cnt16 = n.nvals; return; }
     n.ref = static_cast<u32>(ranges.size());
     n.cnt16 = CNT_BIG;

@@ -63,8 +63,8 @@ class HostTrie {
 
     // ---- device mirror -------------------------------------------------------------------------
     std::vector<EdgeSlot, HugeAlloc<EdgeSlot>> edges;
-    std::vector<Range> ranges;       // [0] reserved
-    std::vector<u32> values;
+    StableVec<Range> ranges;         // [0] reserved.  Both arrays never move in memory (gm_values_view hands out their base)
+    StableVec<u32> values;
     std::vector<DictSlot, HugeAlloc<DictSlot>> dict;
     std::vector<u8> pool;
     std::vector<u32> cfilter;        // child filter of wide nodes (layout.h)

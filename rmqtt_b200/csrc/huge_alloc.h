@@ -40,4 +40,46 @@ struct HugeAlloc {
     template <class U> bool operator!=(const HugeAlloc<U>&) const { return false; }
 };
 
+// Append-only array whose BASE ADDRESS NEVER MOVES: the whole 32-bit index space is reserved as virtual memory up
+// front (MAP_NORESERVE: pages materialise on first touch), so growing never re-allocates.  Used for the host mirror
+// of `values` / `ranges`: descriptor-mode match results (gm_desc, include/gpumqtt.h) are resolved by the caller
+// against these arrays through plain pointers (gm_values_view), concurrently with mutations that append.
+template <class T>
+class StableVec {
+  public:
+    StableVec() { reserve_space(); }
+    ~StableVec() { if (base_) munmap(base_, bytes_); }
+    StableVec(const StableVec&) = delete;
+    StableVec& operator=(const StableVec&) = delete;
+    StableVec(StableVec&& o) noexcept : base_(o.base_), bytes_(o.bytes_), size_(o.size_) { o.base_ = nullptr; o.size_ = 0; o.bytes_ = 0; }
+    // keeps THIS object's mapping (addresses handed out stay valid): the other array's content is copied in
+    StableVec& operator=(StableVec&& o) noexcept {
+        if (this != &o) { size_ = 0; append(o.begin(), o.end()); }
+        return *this;
+    }
+    size_t size() const { return size_; }
+    bool empty() const { return size_ == 0; }
+    T* data() { return base_; }
+    const T* data() const { return base_; }
+    T& operator[](size_t i) { return base_[i]; }
+    const T& operator[](size_t i) const { return base_[i]; }
+    const T* begin() const { return base_; }
+    const T* end() const { return base_ + size_; }
+    void clear() { size_ = 0; }
+    void push_back(const T& v) { base_[size_++] = v; }
+    template <class It> void append(It first, It last) { for (; first != last; ++first) base_[size_++] = *first; }
+    void assign(size_t n, const T& v) { size_ = 0; for (size_t i = 0; i < n; ++i) base_[size_++] = v; }
+    static constexpr size_t kMaxElems = (size_t(1) << 32) + 64;
+
+  private:
+    void reserve_space() {
+        bytes_ = HugeAlloc<T>::rounded(kMaxElems * sizeof(T));
+        void* p = mmap(nullptr, bytes_, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (p == MAP_FAILED) throw std::bad_alloc();
+        base_ = static_cast<T*>(p);
+    }
+    T* base_ = nullptr;
+    size_t bytes_ = 0, size_ = 0;
+};
+
 }  // namespace gm

@@ -39,6 +39,8 @@ struct MatchParams {
     const u32* tok8_sorted;   // [n][8] token rows copied into locality order (MP_SORTED_ROWS)
     const u32* meta_sorted;   // [n]
     u32 tile_chunk;           // tiles a CTA takes from the global counter at once (<= 1: one tile per warp per grab)
+    uint2* out_desc;          // DESCRIPTOR mode: matched value sets (ref, cnt16) per topic instead of expanded ids; spans index this array
+    int* status;              // [n] per-topic status (k_tokenize wrote it); the deferred kernel reports GM_ERR_INTERNAL here
 };
 constexpr u32 MP_DIAG_NO_PUBLISH = 2u;   // diagnostics only: skip the publish phase
 constexpr u32 MP_SORTED_ROWS = 1u;   // k_bucket_scatter also copies token rows + meta into sorted order (coalesced reads in k_match_fast)
@@ -110,15 +112,18 @@ __device__ __noinline__ u32 dict_lookup_long(const TrieView& tv, const u8* text,
     }
 }
 
+// `sel` (optional): row t tokenises entry sel[t] of the packed batch (this rank's topics of a mixed batch, gm_partition_batch_device).
+// `blob_bytes` bounds every text read: words that start at or beyond blob + blob_bytes are never dereferenced.
 __global__ void __launch_bounds__(TOK_THREADS)
-k_tokenize(const u8* __restrict__ blob, const u32* __restrict__ offs, u32 n, TrieView tv, u32 tok_levels,
+k_tokenize(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__ offs, const u32* __restrict__ sel, u32 n, TrieView tv, u32 tok_levels,
            u32* __restrict__ tok8, u32* __restrict__ tok, u32* __restrict__ meta, int* __restrict__ status, u32* __restrict__ bkey,
            u32* __restrict__ hist, u32 site_bits, u32 sub_bits) {
     const u32 t = blockIdx.x * TOK_THREADS + threadIdx.x;
     if (t >= n) return;
-    u32 pos = offs[t];
-    const u32 end = offs[t + 1];
-    const u8* limit = blob + ((static_cast<size_t>(offs[n]) + 3) & ~size_t(3));
+    const u32 src = sel ? sel[t] : t;
+    u32 pos = offs[src];
+    const u32 end = min(offs[src + 1], blob_bytes);
+    const u8* limit = blob + blob_bytes;
     u32 lev = 0;
     u32 tw[TOK8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tokens of levels 0..7 (static indexing only: stays in registers)
     bool invalid = false, dollar = false;
@@ -314,7 +319,11 @@ struct Desc { u32 ref, cnt; };
 //
 // (Round-1 history: a warp-shared ballot-compacted frontier queue ran at 344 warp-instructions per
 //  topic and 45 % issue utilisation — collective overhead, not memory, bound it; see profiles/.)
-template <int FAST_L, int THREADS, int CTAS_PER_SM, bool STATS>
+// DESC = descriptor mode: the publish phase writes each topic's matched value-set references (ref, cnt16) — 8 bytes per
+// matched FILTER instead of 4 bytes per matched id — and spans / cursor / cap count descriptors.  The host resolves
+// them against its mirror of `values` (gm_desc_resolve): this is what DefaultRouter::_matches consumes anyway, one
+// relations entry per matched filter (rmqtt/src/router.rs:166-182), and it cuts the D2H volume ~4x.
+template <int FAST_L, int THREADS, int CTAS_PER_SM, bool STATS, bool DESC>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
     constexpr u32 SD = K2_SMEM_DESCS;         // descriptors kept in shared memory per topic; later ones spill to dpool
@@ -433,8 +442,8 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
         }
 
         // ---- publish: one contiguous list per topic inside one chunk per tile ------------------------
-        const u32 mine = (active && !defer) ? total : 0u;
         const u32 nd = (active && !defer) ? ndesc : 0u;
+        const u32 mine = DESC ? nd : ((active && !defer) ? total : 0u);
         u32 inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += v; }
@@ -446,7 +455,17 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
         const bool fits = base + wtotal <= p.cap_ids;
         if (in_range && !defer) p.spans[t] = make_uint2(fits ? static_cast<u32>(base + pre) : 0u, mine);
         const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, nd);
-        if (fits && wtotal && !(p.flags & MP_DIAG_NO_PUBLISH)) {
+        if (DESC) {
+            if (fits && wtotal) {
+                uint2* __restrict__ outd = p.out_desc + base + pre;     // this topic's descriptors, contiguous
+                for (u32 k = 0; k < nd; ++k) {
+                    uint2 v;
+                    if (k < SD) v = s_desc[k][tid];
+                    else { const Desc dd = dpool[static_cast<size_t>(k - SD) * nthreads + gtid]; v = make_uint2(dd.ref, dd.cnt); }
+                    __stcs(outd + k, v);
+                }
+            }
+        } else if (fits && wtotal && !(p.flags & MP_DIAG_NO_PUBLISH)) {
             u32* __restrict__ out = p.out_ids + base;
             u32 cur = pre;                                    // this lane's write position inside the tile chunk
             for (u32 k = 0; k < maxd; ++k) {                  // row k: the k-th descriptor of every lane
@@ -509,7 +528,7 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
 // scratch (gstack, `stack_cap` items per warp: 32*(max_depth+2)+64 bounds the LIFO walk).
 // In STATS mode the counters of a deferred topic are taken here (the fast path's partial counts of
 // topics it later deferred are subtracted by never being added: see `stats_defer` below).
-template <bool STATS>
+template <bool STATS, bool DESC>
 __global__ void __launch_bounds__(256)
 k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
     const u32 lane = threadIdx.x & 31;
@@ -528,7 +547,7 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
         const bool dollar = (m & META_DOLLAR) != 0;
         unsigned long long base = 0;
         unsigned long long count = 0;
-        bool fits = true;
+        bool fits = true, bad_any = false;
         for (int pass = 0; pass < 2; ++pass) {
             u32 stack_n = 0;
             unsigned long long written = 0;
@@ -554,6 +573,13 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                     const u32 cn = round == 0 ? c1 : c2;
                     const u32 ref = round == 0 ? r.hash_ref : r.own_ref;
                     if (STATS && pass == 0) sF += (cn != 0);
+                    if (DESC) {                 // one (ref, cnt16) descriptor per matched value set; CNT_BIG sets resolve through `ranges` on the host
+                        const u32 bd = __ballot_sync(0xFFFFFFFFu, cn != 0);
+                        if (pass == 1 && cn != 0) p.out_desc[base + written + __popc(bd & lt)] = make_uint2(ref, cn);
+                        written += __popc(bd);
+                        if (STATS && pass == 0 && cn != 0) sM += cn == CNT_BIG ? tv.ranges[ref].cnt : cn;
+                        continue;
+                    }
                     u32 b = __ballot_sync(0xFFFFFFFFu, cn == 1);
                     if (pass == 1 && cn == 1) p.out_ids[base + written + __popc(b & lt)] = ref;
                     written += __popc(b);
@@ -608,14 +634,20 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
             }
             if (pass == 0) {
                 count = written;
-                if (STATS) sM += (lane == 0) ? count : 0;
+                if (STATS && !DESC) sM += (lane == 0) ? count : 0;
                 if (lane == 0 && count) base = atomicAdd(p.cursor, count);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                bad_any = bad;
                 fits = !bad && (base + count <= p.cap_ids) && count <= 0xFFFFFFFFull;
                 if (!fits) break;
             }
         }
-        if (lane == 0) p.spans[t] = make_uint2(fits ? static_cast<u32>(base) : 0u, static_cast<u32>(count));
+        if (lane == 0) {
+            // a frontier-stack overflow cannot happen within the documented bound; if it ever did, fail the topic loudly
+            // instead of aliasing another topic's list
+            if (bad_any) { p.spans[t] = make_uint2(0u, 0u); p.status[t] = -8; }   // GM_ERR_INTERNAL
+            else p.spans[t] = make_uint2(fits ? static_cast<u32>(base) : 0u, static_cast<u32>(count));
+        }
     }
     if (STATS) {
 #pragma unroll

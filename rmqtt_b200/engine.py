@@ -212,6 +212,107 @@ class Engine:
         self._check(self._lib.gm_match_batch_device(*args))
         return None
 
+    def match_batch_device_ex(self, d_blob, d_offs, d_spans, d_out, d_needed, d_status, stream: int, *, desc: bool = False, d_sel=None,
+                              n_sel: int | None = None, work: bool = False):
+        """gm_match_batch_device_ex: descriptor output (d_out = int64/uint2 tensor of gm_desc) and / or a selection of rows."""
+        n_entries = d_offs.numel() - 1
+        n = n_entries if d_sel is None else int(n_sel)
+        w = N.GmWork() if work else None
+        elem = 8 if desc else 4
+        a = N.GmMatchArgs(C.sizeof(N.GmMatchArgs), N.GM_MATCH_DESCRIPTORS if desc else 0, d_blob.data_ptr(), d_blob.numel(), d_offs.data_ptr(), n_entries,
+                          d_sel.data_ptr() if d_sel is not None else None, n, d_spans.data_ptr(), d_out.data_ptr(),
+                          d_out.numel() * d_out.element_size() // elem, d_needed.data_ptr(), d_status.data_ptr(), stream,
+                          C.pointer(w) if work else None)
+        self._check(self._lib.gm_match_batch_device_ex(self._h, C.byref(a)))
+        return w.as_dict() if work else None
+
+    # ---- descriptor mode (host buffers): matched value SETS by reference --------------------------------------
+    def match_batch_desc(self, blob: np.ndarray, offs: np.ndarray, cap: int | None = None):
+        """-> (spans uint32[n,2] into descs, descs uint32[m,2] = (ref, cnt), status, needed)"""
+        n = len(offs) - 1
+        spans = np.zeros((n, 2), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        c = int(cap) if cap is not None else max(1024, 16 * n)
+        while True:
+            descs = np.empty((c, 2), dtype=np.uint32)
+            needed = C.c_uint64(0)
+            rc = self._lib.gm_match_batch_desc(self._h, _vp(blob), _vp(offs), n, _vp(spans), _vp(descs), c, C.byref(needed), _vp(status))
+            if rc == N.GM_ERR_CAPACITY and cap is None:
+                c = int(needed.value)
+                continue
+            self._check(rc)
+            return spans, descs[:int(needed.value)], status, int(needed.value)
+
+    def values_view(self):
+        """Zero-copy numpy views of the host mirror of the value-set storage: (values uint32[], ranges uint32[k,2], epoch)."""
+        v = N.GmValues()
+        self._check(self._lib.gm_values_view(self._h, C.byref(v)))
+        vals = np.frombuffer((C.c_uint32 * int(v.n_values)).from_address(v.values), dtype=np.uint32) if v.n_values else np.zeros(0, np.uint32)
+        rng = np.frombuffer((C.c_uint32 * (2 * int(v.n_ranges))).from_address(v.ranges), dtype=np.uint32).reshape(-1, 2) if v.n_ranges else np.zeros((0, 2), np.uint32)
+        return vals, rng, int(v.epoch)
+
+    def desc_expand(self, descs: np.ndarray) -> np.ndarray:
+        descs = np.ascontiguousarray(descs, dtype=np.uint32)
+        n = len(descs)
+        needed = C.c_uint64(0)
+        cap = int(descs[:, 1].astype(np.int64).sum()) + 1024 if n else 1
+        while True:
+            out = np.empty(cap, dtype=np.uint32)
+            rc = self._lib.gm_desc_expand(self._h, _vp(descs), n, _vp(out), cap, C.byref(needed))
+            if rc == N.GM_ERR_CAPACITY:
+                cap = int(needed.value)
+                continue
+            self._check(rc)
+            return out[:int(needed.value)]
+
+    def match_batch_via_desc(self, blob: np.ndarray, offs: np.ndarray) -> "MatchResult":
+        """Descriptor-mode match expanded on the host (gm_desc_expand) into the MatchResult shape of match_batch (tests)."""
+        spans, descs, status, _ = self.match_batch_desc(blob, offs)
+        _, rng, _ = self.values_view()
+        cnt = descs[:, 1].astype(np.int64)
+        big = cnt == 0xFFFF
+        if big.any():
+            cnt[big] = rng[descs[big, 0], 1]
+        starts = np.zeros(len(descs) + 1, dtype=np.int64)
+        np.cumsum(cnt, out=starts[1:])
+        ids = self.desc_expand(descs)                 # ids in descriptor order; a topic's descriptors are contiguous
+        assert len(ids) == int(starts[-1])
+        d0 = spans[:, 0].astype(np.int64)
+        d1 = d0 + spans[:, 1].astype(np.int64)
+        ispans = np.stack([starts[d0], starts[d1] - starts[d0]], axis=1)
+        return MatchResult(ispans.astype(np.uint32), ids, status, len(ids))
+
+    # ---- multi-GPU: communicator, device partition, all-gatherv (include/gpumqtt.h, comm.cuh) --------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * N.GM_COMM_ID_BYTES)()
+        rc = N.lib().gm_comm_unique_id(buf)
+        if rc != N.GM_OK:
+            raise GpuMqttError(rc, N.lib().gm_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * N.GM_COMM_ID_BYTES).from_buffer_copy(uid)
+        self._check(self._lib.gm_comm_init(self._h, buf, rank, world))
+        self._world = world
+
+    def partition_batch_device(self, d_blob, d_offs, n_shards: int, rank: int, d_sel, stream: int, d_shard=None):
+        """-> (n_local, shard_counts int64[n_shards])"""
+        n = d_offs.numel() - 1
+        n_local = C.c_uint64(0)
+        counts = np.zeros(n_shards, dtype=np.uint64)
+        self._check(self._lib.gm_partition_batch_device(self._h, d_blob.data_ptr(), d_blob.numel(), d_offs.data_ptr(), n, n_shards, rank, d_sel.data_ptr(),
+                                                        d_shard.data_ptr() if d_shard is not None else None, C.byref(n_local), _vp(counts), stream))
+        return int(n_local.value), counts.astype(np.int64)
+
+    def allgatherv_device(self, d_index, d_spans, k: int, d_ids, d_m, d_all_index, d_all_spans, d_all_ids, stream: int):
+        """-> sizes int64[world, 2] = (topics, ids) contributed by every rank"""
+        sizes = np.zeros(2 * self._world, dtype=np.uint64)
+        self._check(self._lib.gm_allgatherv_device(self._h, d_index.data_ptr() if d_index is not None else None, d_spans.data_ptr(), k, d_ids.data_ptr(), d_m.data_ptr(),
+                                                   d_all_index.data_ptr(), d_all_spans.data_ptr(), d_all_index.numel(), d_all_ids.data_ptr(), d_all_ids.numel(),
+                                                   _vp(sizes), stream))
+        return sizes.astype(np.int64).reshape(-1, 2)
+
     # ---- tokeniser hook -------------------------------------------------------------------------------
     def tokenize(self, topics, max_tok: int = 16):
         blob, offs = pack(topics)

@@ -1,4 +1,6 @@
-"""GPU tier, 2 ranks (skipped on a 1-GPU box): root-hash sharded engines + NCCL all-gatherv == one unsharded engine."""
+"""GPU tier, 2 ranks (skipped on a 1-GPU box): root-hash sharded engines + the all-gatherv of libgpumqtt
+(gm_partition_batch_device -> gm_match_batch_device_ex -> gm_allgatherv_device, all device buffers, NCCL inside the
+library) == one unsharded engine, bit-exact per topic."""
 import os
 
 import numpy as np
@@ -8,28 +10,50 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from rmqtt_b200 import sharding, workload as wl
-from rmqtt_b200.engine import Engine, pack
+from rmqtt_b200.engine import Engine, MatchResult
 
 pytestmark = pytest.mark.gpu
+
+CFG = dict(n_subs=100_000, n_topics=20_000)
+
+
+def sharded_match_and_gather(eng, rank, world, d_blob, d_offs, dev, stream):
+    """The C5 data path of one rank; returns (index, spans, ids, sizes) of the gathered result (device tensors)."""
+    n = d_offs.numel() - 1
+    d_sel = torch.zeros(n, dtype=torch.int32, device=dev)
+    k, counts = eng.partition_batch_device(d_blob, d_offs, world, rank, d_sel, stream)
+    d_spans = torch.zeros((max(k, 1), 2), dtype=torch.int32, device=dev)
+    d_status = torch.zeros(max(k, 1), dtype=torch.int32, device=dev)
+    d_needed = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_ids = torch.empty(64 * max(k, 1) + 1024, dtype=torch.int32, device=dev)
+    eng.match_batch_device_ex(d_blob, d_offs, d_spans, d_ids, d_needed, d_status, stream, d_sel=d_sel, n_sel=k)
+    a_idx = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    a_spans = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+    a_ids = torch.empty(64 * n + 1024, dtype=torch.int32, device=dev)
+    sizes = eng.allgatherv_device(d_sel, d_spans, k, d_ids, d_needed, a_idx, a_spans, a_ids, stream)
+    torch.cuda.synchronize()
+    return a_idx, a_spans, a_ids, sizes, counts
 
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    cfg = wl.C2.scaled(n_subs=100_000, n_topics=20_000)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cuda", rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    cfg = wl.C2.scaled(**CFG)
     sb, so, sv = wl.gen_subs(cfg)
     tb, to = wl.gen_topics(cfg)
     fb, fo, fv, _ = sharding.partition_filters(sb, so, sv, rank, world)
-    stb, sto, tidx = sharding.partition_topics(tb, to, rank, world)
     eng = Engine(device=rank)
     eng.bulk_load(fb, fo, fv)
-    res = eng.match_batch(stb, sto)
-    counts, ids = res.canonical()
-    dev = torch.device("cuda", rank)
-    ti, ct, ia = sharding.all_gatherv_match_lists(torch.from_numpy(tidx.astype(np.int64)).to(dev), torch.from_numpy(counts).to(dev),
-                                                  torch.from_numpy(ids.astype(np.int64)).to(dev))
-    q.put((rank, ti.cpu().numpy(), ct.cpu().numpy(), ia.cpu().numpy()))
+    uid = [Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng.comm_init(uid[0], rank, world)
+    d_blob, d_offs = torch.from_numpy(tb).to(dev), torch.from_numpy(to.view(np.int32)).to(dev)
+    a_idx, a_spans, a_ids, sizes, counts = sharded_match_and_gather(eng, rank, world, d_blob, d_offs, dev, stream)
+    m = int(sizes[:, 1].sum())
+    q.put((rank, a_idx.cpu().numpy(), a_spans.cpu().numpy().view(np.uint32), a_ids[:m].cpu().numpy().view(np.uint32), sizes))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,18 +70,16 @@ def test_two_rank_sharded_equals_single_engine():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for a, b in zip(got[0][1:], got[1][1:]):
-        assert (a == b).all()
-    _, ti, ct, ia = got[0]
-    cfg = wl.C2.scaled(n_subs=100_000, n_topics=20_000)
+    for a, b in zip(got[0][1:], got[1][1:]):          # identical on every rank
+        assert (np.asarray(a) == np.asarray(b)).all()
+    _, idx, spans, ids, sizes = got[0]
+    cfg = wl.C2.scaled(**CFG)
     sb, so, sv = wl.gen_subs(cfg)
     tb, to = wl.gen_topics(cfg)
     eng = Engine(device=0)
     eng.bulk_load(sb, so, sv)
-    counts, ids = eng.match_batch(tb, to).canonical()
-    starts = np.concatenate([[0], np.cumsum(counts)])
-    gst = np.concatenate([[0], np.cumsum(ct)])
-    assert sorted(ti.tolist()) == list(range(len(counts)))
-    for k, t in enumerate(ti):
-        assert ct[k] == counts[t]
-        assert (ia[gst[k]:gst[k + 1]] == ids[starts[t]:starts[t + 1]]).all()
+    counts, want_ids = eng.match_batch(tb, to).canonical()
+    assert sorted(idx.tolist()) == list(range(cfg.n_topics)) and int(sizes[:, 0].sum()) == cfg.n_topics
+    order = np.argsort(idx)
+    c, i = MatchResult(spans[order], ids, np.zeros(cfg.n_topics, np.int32), len(ids)).canonical()
+    assert (c == counts).all() and (i == want_ids).all()
