@@ -65,9 +65,13 @@ struct NcclApi {
 // filters (HostTrie::level0_hash -> shard_of_hash, gm_shard_of) — and compaction of this rank's topics into `sel`.
 // Warp-aggregated append; the order inside `sel` is irrelevant (every row carries its global index).
 // counts[r] receives the number of topics of shard r (load report); counts[nshards] = rows appended to sel.
+constexpr u32 PART_SMEM_SHARDS = 1024;     // shard histograms up to this many shards are kept per CTA in shared memory
 __global__ void __launch_bounds__(256)
 k_partition(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__ offs, u32 n, u32 nshards, u32 rank, u32* __restrict__ sel,
             u32* __restrict__ shard_out, u32* __restrict__ counts) {
+    __shared__ u32 s_hist[PART_SMEM_SHARDS];
+    const bool smem_hist = nshards <= PART_SMEM_SHARDS;     // one global atomic per (CTA, shard) instead of one per topic
+    if (smem_hist) { for (u32 i = threadIdx.x; i < nshards; i += blockDim.x) s_hist[i] = 0u; __syncthreads(); }
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 lane = threadIdx.x & 31;
     u32 shard = 0xFFFFFFFFu;
@@ -84,7 +88,7 @@ k_partition(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__
         const bool wild_root = l0 == 1 && (blob[b] == '+' || blob[b] == '#');
         shard = wild_root ? 0u : shard_of_hash(dict_hash_finish(h, l0), nshards);
         if (shard_out) shard_out[t] = shard;
-        atomicAdd(counts + shard, 1u);
+        if (smem_hist) atomicAdd(s_hist + shard, 1u); else atomicAdd(counts + shard, 1u);
     }
     const bool mine = shard == rank;
     const u32 bal = __ballot_sync(0xFFFFFFFFu, mine);
@@ -94,6 +98,10 @@ k_partition(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__
         if (static_cast<int>(lane) == leader) base = atomicAdd(counts + nshards, static_cast<u32>(__popc(bal)));
         base = __shfl_sync(0xFFFFFFFFu, base, leader);
         if (mine) sel[base + __popc(bal & ((1u << lane) - 1u))] = t;
+    }
+    if (smem_hist) {
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < nshards; i += blockDim.x) { const u32 c = s_hist[i]; if (c) atomicAdd(counts + i, c); }
     }
 }
 

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -45,6 +46,9 @@ struct DevBuf {   // owning device allocation (freed on destruction, also on the
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; } return *this; }
+    void* detach() { void* q = p; p = nullptr; cap = 0; return q; }
     ~DevBuf() { release(); }
     cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t s = nullptr) {
         if (bytes <= cap) return cudaSuccess;
@@ -79,34 +83,76 @@ constexpr u32 K2_POOL_ROWS = 24;   // matched value sets per topic beyond the 8 
 
 }  // namespace
 
+struct SmallGraph;
+static void small_graph_destroy(SmallGraph* g);
+constexpr int GM_SMALL_NOT_APPLICABLE = 1000;     // internal: the small-batch fast path declined, take the pipelined path
+
+// One match CONTEXT = everything a match call needs besides the (read-only) tables: its own streams, events, kernel
+// scratch and staging buffers.  Host-buffer calls take a free context from the engine's pool, enqueue, RELEASE THE
+// ENGINE LOCK, and wait on their own events — so several batches are in flight at once (the reference serves many
+// concurrent readers under its RwLock, rmqtt/src/router.rs:166) and a mutation never waits behind a D2H copy.
+struct MatchCtx {
+    static constexpr int MAXC = 32;  // chunks per pipelined host call
+    cudaStream_t sc = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[MAXC] = {}, ev_comp[MAXC] = {};
+    cudaEvent_t ev_done = nullptr;   // after the last kernel of the last match enqueued with this context's scratch
+    bool recorded = false, busy = false;
+    unsigned long long* h_cur = nullptr;             // pinned: cursor snapshot after every chunk
+    DevBuf d_tok, d_tok8, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_sort, d_hist;   // kernel scratch
+    DevBuf d_blob, d_offs, d_spans, d_ids, d_status;                                   // staging of host-buffer calls
+    // small-batch fast path: the whole call (H2D, memsets, 5 kernels, D2H) as ONE CUDA-graph launch (see SmallGraph)
+    struct SmallGraph* small[2] = {nullptr, nullptr};
+    int init() {
+        CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < MAXC; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaMallocHost(&h_cur, MAXC * sizeof(unsigned long long)));
+        return GM_OK;
+    }
+    void destroy();
+};
+
 struct gm_engine {
-    std::mutex mu;
+    // LOCK ORDER: mu (host mirror: mutations, flush, statistics) -> mu_dev (device enqueue state: contexts, view, events).
+    // A match takes mu only to flush pending mutations (auto-flush engines) and mu_dev only while it ENQUEUES.
+    std::mutex mu, mu_dev, mu_ret;   // mu_ret serialises retained lookups (their scratch is engine-wide)
+    std::condition_variable cv_ctx;
     int device = 0;
     u32 flags = 0;
     int num_sms = 0;
     HostTrie trie;
     RetainTreeHost rtree{&trie};     // retained-message tree (shares the level dictionary)
-    cudaStream_t stream = nullptr;   // host-buffer matches
+    static constexpr int NCTX = 3;   // host-buffer matches in flight
+    MatchCtx ctxs[NCTX];
+    MatchCtx devctx;                 // scratch of the device-buffer entry points (they run on the CALLER's stream)
     cudaStream_t side = nullptr;     // flush
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host-buffer match
-    static constexpr int MAXC = 32;  // chunks per pipelined call
-    cudaEvent_t ev_h2d[MAXC] = {}, ev_comp[MAXC] = {};
-    unsigned long long* h_cur = nullptr;             // pinned: cursor snapshot after every chunk
+    static constexpr int MAXC = MatchCtx::MAXC;
     static constexpr int RING = 64;   // per-kernel timing events of the last RING match calls
-    cudaEvent_t ev_flush = nullptr, ev_match = nullptr;
+    cudaEvent_t ev_flush = nullptr;
     cudaEvent_t ev_ring[RING][4] = {};
     u64 ring_n = 0;
-    bool match_recorded = false;
+    u64 view_epoch = 0;               // bumped by every flush that changed what the kernels see
     // device tables
     DevBuf d_edges, d_ranges, d_values, d_dict, d_pool, d_cfilter;
     size_t up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
     u64 up_values_epoch = 0;
-    // scratch
-    DevBuf d_tok, d_tok8, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_patch_idx, d_patch_data, d_sort, d_hist;
-    DevBuf d_blob, d_offs, d_spans, d_ids, d_status;
+    // flush staging: patches are gathered into PINNED host memory and scattered by kernels on the side stream —
+    // the flush never synchronises the host with the device
+    DevBuf d_patch;
+    char* h_patch = nullptr; size_t h_patch_cap = 0;
+    cudaEvent_t ev_patch = nullptr;  // the previous flush has consumed h_patch
+    bool patch_pending = false;
+    struct Retired { void* p; u64 gen; };
+    std::vector<Retired> retired;    // table buffers replaced by an epoch swap: freed once every match that could see them is done
+    u64 flush_gen = 0;
     // retained tree (device copy of the flattened arrays) + scratch of the retained lookup
     DevBuf d_rnodes, d_rkids, d_redges, d_rvals;
-    DevBuf d_rfront[2], d_rdescs, d_rctl, d_rq;
+    DevBuf d_rfront[2], d_rdescs, d_rctl, d_rq, d_rstage[5];
     u32 r_cap_items = 1u << 22, r_cap_desc = 1u << 22;   // totals over the RQ slices of each queue
     u64 launches = 0;
     bool k2_attr_set = false;
@@ -116,13 +162,16 @@ struct gm_engine {
     DevBuf d_comm, d_part;
     unsigned long long* h_comm = nullptr;   // pinned [2 * world + 64]
     // tuning / diagnostics knobs, read from the environment once at creation
-    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; } knobs;
+    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 131072; bool small_graphs = true; } knobs;
     void read_knobs() {
         if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { knobs.site_bits = a; knobs.sub_bits = b; } }
         if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
         if (const char* ev = getenv("GM_K2_CTAS")) knobs.k2_ctas = atoi(ev);
         if (const char* ev = getenv("GM_TILE_CHUNK")) { int v = atoi(ev); if (v >= 1 && v <= 1024) knobs.tile_chunk = static_cast<u32>(v); }
         if (getenv("GM_DIAG_NO_PUBLISH")) knobs.diag_flags |= MP_DIAG_NO_PUBLISH;
+        if (const char* ev = getenv("GM_TOK_BULK")) knobs.tok_bulk = atoi(ev) != 0;
+        if (const char* ev = getenv("GM_SMALL_GRAPHS")) knobs.small_graphs = atoi(ev) != 0;
+        if (const char* ev = getenv("GM_E2E_CHUNK")) { int v = atoi(ev); if (v >= 1024) knobs.e2e_chunk = static_cast<u32>(v); }
     }
 
     explicit gm_engine(u32 max_levels) : trie(max_levels) {}
@@ -145,54 +194,96 @@ struct gm_engine {
         return v;
     }
 
-    // ---- flush: ship the staged mutations to HBM on the side stream -------------------------------
-    // Scatter the listed (already final) host slots into the device copy of the table.
+    // ---- flush: ship the staged mutations to HBM on the side stream WITHOUT stopping the matches ------------------------
+    // Phase A (no fence; only the host-mirror lock `mu` is held, matches keep running):
+    //   * a table that was re-hashed / outgrew its buffer / was compacted goes into a NEW device buffer (epoch swap);
+    //   * appended tails (values, ranges, string pool, retained child blocks / values) are copied behind the part the
+    //     running kernels can reach — no published record refers to them yet;
+    //   * changed 32-byte slots are gathered into PINNED memory and copied to a device staging area.
+    // Phase B (under mu_dev, microseconds of host time, no host<->device synchronisation):
+    //   * the side stream waits for every match enqueued so far (their ev_done), the new buffers are swapped in, the
+    //     staged slots are scattered by k_apply_patches, ev_flush is recorded; matches enqueued from now on wait for
+    //     ev_flush on the device and use the new view;
+    //   * replaced buffers are retired and freed by a later flush once that ev_flush has passed.
+    struct alignas(32) Blk32 { u32 w[8]; };
+    struct PatchJob { DevBuf* table; u32 elem, n; size_t off_idx, off_data; };
+    struct Swap { DevBuf* dst; DevBuf fresh; };
+    std::vector<PatchJob> jobs_;
+    std::vector<Swap> swaps_;
+    size_t stage_used_ = 0;
+    int arena_ = 0;
+    char* h_arena_[2] = {nullptr, nullptr}; size_t h_arena_cap_[2] = {0, 0};
+    cudaEvent_t ev_arena_[2] = {nullptr, nullptr}; bool arena_pending_[2] = {false, false};
+
+    int stage_reserve(size_t bytes) {
+        if (bytes <= h_arena_cap_[arena_]) return GM_OK;
+        size_t ncap = std::max(bytes, h_arena_cap_[arena_] * 2 + (size_t(1) << 20));
+        char* np = nullptr;
+        CUDA_TRY(cudaMallocHost(&np, ncap));
+        if (h_arena_[arena_]) { std::memcpy(np, h_arena_[arena_], stage_used_); cudaFreeHost(h_arena_[arena_]); }
+        h_arena_[arena_] = np; h_arena_cap_[arena_] = ncap;
+        return GM_OK;
+    }
+
+    // gather the listed (already final) host slots into the pinned arena; they are scattered in phase B
     template <class V>
-    int patch_table(DevBuf& buf, const V& host, std::vector<u32>& dirty) {
+    int stage_patches(DevBuf& buf, const V& host, std::vector<u32>& dirty) {
         using T = std::remove_cv_t<std::remove_reference_t<decltype(host[0])>>;
+        static_assert(sizeof(T) == 32 || sizeof(T) == 8 || sizeof(T) == 4 || sizeof(T) == 1, "patchable element sizes");
         std::sort(dirty.begin(), dirty.end());
         dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
         const u32 nd = static_cast<u32>(dirty.size());
         if (nd == 0) return GM_OK;
-        std::vector<T> data(nd);
+        const size_t off_idx = (stage_used_ + 31) & ~size_t(31);
+        const size_t off_data = (off_idx + nd * sizeof(u32) + 31) & ~size_t(31);
+        int st = stage_reserve(off_data + nd * sizeof(T));
+        if (st != GM_OK) return st;
+        char* base = h_arena_[arena_];
+        std::memcpy(base + off_idx, dirty.data(), nd * sizeof(u32));
+        T* data = reinterpret_cast<T*>(base + off_data);
         for (u32 i = 0; i < nd; ++i) data[i] = host[dirty[i]];
-        CUDA_TRY(d_patch_idx.ensure(nd * sizeof(u32)));
-        CUDA_TRY(d_patch_data.ensure(nd * sizeof(T)));
-        CUDA_TRY(cudaMemcpyAsync(d_patch_idx.p, dirty.data(), nd * sizeof(u32), cudaMemcpyHostToDevice, side));
-        CUDA_TRY(cudaMemcpyAsync(d_patch_data.p, data.data(), nd * sizeof(T), cudaMemcpyHostToDevice, side));
-        k_apply_patches<T><<<(nd + 255) / 256, 256, 0, side>>>(buf.as<T>(), d_patch_idx.as<u32>(), d_patch_data.as<T>(), nd);
-        launches++;
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(side));   // the staging vectors go out of scope
+        stage_used_ = off_data + nd * sizeof(T);
+        jobs_.push_back(PatchJob{&buf, static_cast<u32>(sizeof(T)), nd, off_idx, off_data});
         dirty.clear();
         return GM_OK;
     }
 
-    // Hash tables (edges, dict): whole-table copy after a re-hash or when most of it changed, else patches.
-    template <class Slot, class A>
-    int upload_table(DevBuf& buf, const std::vector<Slot, A>& host, bool& full, std::vector<u32>& dirty, size_t& up_slots) {
-        const size_t bytes = host.size() * sizeof(Slot);
+    // whole array into a fresh device buffer (swapped in at the fence)
+    template <class V>
+    int stage_fresh(DevBuf& buf, const V& host, size_t min_bytes, size_t slack_bytes = 0) {
+        using T = std::remove_cv_t<std::remove_reference_t<decltype(host[0])>>;
+        DevBuf fresh;
+        CUDA_TRY(fresh.ensure(std::max<size_t>(std::max(host.size() * sizeof(T) + slack_bytes, min_bytes), 256)));
+        if (host.size()) CUDA_TRY(cudaMemcpyAsync(fresh.p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, side));
+        swaps_.push_back(Swap{&buf, std::move(fresh)});
+        return GM_OK;
+    }
+
+    // Hash tables (edges, dict): whole table into a new buffer after a re-hash or when most of it changed, else patches.
+    template <class V>
+    int upload_table(DevBuf& buf, const V& host, bool& full, std::vector<u32>& dirty, size_t& up_slots) {
+        int st;
         if (full || up_slots != host.size() || dirty.size() * 8 > host.size()) {
-            CUDA_TRY(buf.ensure(bytes));
-            CUDA_TRY(cudaMemcpyAsync(buf.p, host.data(), bytes, cudaMemcpyHostToDevice, side));
+            if ((st = stage_fresh(buf, host, 0)) != GM_OK) return st;
             up_slots = host.size();
             dirty.clear();
-        } else {
-            int st = patch_table(buf, host, dirty);
-            if (st != GM_OK) return st;
-        }
+        } else if ((st = stage_patches(buf, host, dirty)) != GM_OK) return st;
         full = false;
         return GM_OK;
     }
 
-    // Append-only arrays (plus, ranges, values, pool): copy the new tail; patch older entries that changed.
+    // Append-only arrays (ranges, values, pool, retained child blocks / values): copy the new tail in place (no running
+    // kernel can reach it yet); a grown or rebuilt array goes into a new buffer; older entries that changed are patched.
     template <class V>
     int upload_appendable(DevBuf& buf, const V& host, size_t& up, std::vector<u32>* dirty) {
         using T = std::remove_cv_t<std::remove_reference_t<decltype(host[0])>>;
         const size_t bytes = host.size() * sizeof(T);
-        if (bytes > buf.cap) {   // grow: re-ship the whole array from the mirror
-            CUDA_TRY(buf.ensure(std::max(bytes * 2, size_t(4096))));
-            up = 0;
+        if ((up == 0 && (host.size() > 0 || !buf.p)) || bytes > buf.cap) {    // first shipment, rebuilt content, or out of room: new buffer with room to append
+            int st = stage_fresh(buf, host, std::max(bytes * 2, size_t(4096)));
+            if (st != GM_OK) return st;
+            up = host.size();
+            if (dirty) dirty->clear();
+            return GM_OK;
         }
         const size_t before = up;
         if (host.size() > up) {
@@ -201,7 +292,7 @@ struct gm_engine {
         }
         if (dirty) {
             dirty->erase(std::remove_if(dirty->begin(), dirty->end(), [&](u32 i) { return i >= before; }), dirty->end());
-            int st = patch_table(buf, host, *dirty);
+            int st = stage_patches(buf, host, *dirty);
             if (st != GM_OK) return st;
             dirty->clear();
         }
@@ -217,14 +308,14 @@ struct gm_engine {
         return v;
     }
 
-    template <class T, class A>
-    int upload_whole(DevBuf& buf, const std::vector<T, A>& host, size_t slack_elems = 0) {
-        CUDA_TRY(buf.ensure(std::max<size_t>((host.size() + slack_elems) * sizeof(T), 256)));
-        if (!host.empty()) CUDA_TRY(cudaMemcpyAsync(buf.p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, side));
-        return GM_OK;
+    void free_retired(bool all) {
+        if (retired.empty()) return;
+        if (!all && cudaEventQuery(ev_flush) != cudaSuccess) return;     // the last fence has not passed yet: some match may still read them
+        for (const Retired& r : retired) cudaFree(r.p);
+        retired.clear();
     }
 
-    int flush_locked() {
+    int flush_locked() {      // caller holds `mu`
         if (flags & GM_FLAG_HOST_ONLY) {
             if (!trie.sync()) { g_err = "more than 2^32 live value words"; return GM_ERR_TOO_LARGE; }
             if (rtree.dirty) { rtree.prepare_flush(); rtree.shipped(); }
@@ -234,15 +325,21 @@ struct gm_engine {
         CUDA_TRY(cudaSetDevice(device));
         if (!trie.sync()) { g_err = "more than 2^32 live value words"; return GM_ERR_TOO_LARGE; }
         if (trie.values_epoch != up_values_epoch) { up_values = up_ranges = 0; up_values_epoch = trie.values_epoch; }   // value sets were compacted: re-ship whole
-        if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(side, ev_match, 0));   // never patch under a running match
+        free_retired(false);
+        // ---------------- phase A ----------------
+        arena_ ^= 1;
+        if (arena_pending_[arena_]) { CUDA_TRY(cudaEventSynchronize(ev_arena_[arena_])); arena_pending_[arena_] = false; }   // two flushes ago: long done
+        jobs_.clear(); swaps_.clear(); stage_used_ = 0;
+        int rs;
+        bool r_shipped = false;
         if (rtree.dirty) {   // retained tree: whole arrays after a (re)flatten, else only the entries set / remove edited in place
             rtree.prepare_flush();
-            int rs;
             if (rtree.full) {
-                if ((rs = upload_whole(d_rnodes, std::vector<u32>{0u})) != GM_OK) return rs;   // marker: "retained tree shipped" (records travel in rkids / redges)
-                if ((rs = upload_whole(d_rkids, rtree.rkids, rtree.rkids.size() / 4 + 1024)) != GM_OK) return rs;   // room for in-place appends
-                if ((rs = upload_whole(d_redges, rtree.redges)) != GM_OK) return rs;
-                if ((rs = upload_whole(d_rvals, rtree.rvals)) != GM_OK) return rs;
+                const std::vector<u32> marker{0u};       // "retained tree shipped" (records travel in rkids / redges)
+                if ((rs = stage_fresh(d_rnodes, marker, 0)) != GM_OK) return rs;
+                if ((rs = stage_fresh(d_rkids, rtree.rkids, 0, (rtree.rkids.size() / 4 + 1024) * sizeof(RKid))) != GM_OK) return rs;   // room for in-place appends
+                if ((rs = stage_fresh(d_redges, rtree.redges, 0)) != GM_OK) return rs;
+                if ((rs = stage_fresh(d_rvals, rtree.rvals, 0, 4096)) != GM_OK) return rs;
                 up_rkids = rtree.rkids.size(); up_rvals = rtree.rvals.size(); up_redges_slots = rtree.redges.size();
             } else {
                 bool full_edges = false;
@@ -250,84 +347,119 @@ struct gm_engine {
                 if ((rs = upload_table(d_redges, rtree.redges, full_edges, rtree.dirty_edges, up_redges_slots)) != GM_OK) return rs;
                 if ((rs = upload_appendable(d_rvals, rtree.rvals, up_rvals, &rtree.dirty_vals)) != GM_OK) return rs;
             }
-            rtree.shipped();
+            r_shipped = true;
         }
-        int st;
-        if ((st = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return st;
-        if ((st = upload_table(d_dict, trie.dict, trie.full_dict, trie.dirty_dict, up_dict_slots)) != GM_OK) return st;
-        if ((st = upload_appendable(d_ranges, trie.ranges, up_ranges, nullptr)) != GM_OK) return st;
-        if ((st = upload_appendable(d_values, trie.values, up_values, nullptr)) != GM_OK) return st;
-        if ((st = upload_appendable(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return st;
-        if (trie.cfilter_dirty) {   // child filter of wide nodes: a few MB, shipped whole
-            if ((st = upload_whole(d_cfilter, trie.cfilter)) != GM_OK) return st;
+        if ((rs = upload_table(d_edges, trie.edges, trie.full_edges, trie.dirty_edges, up_edges_slots)) != GM_OK) return rs;
+        if ((rs = upload_table(d_dict, trie.dict, trie.full_dict, trie.dirty_dict, up_dict_slots)) != GM_OK) return rs;
+        if ((rs = upload_appendable(d_ranges, trie.ranges, up_ranges, nullptr)) != GM_OK) return rs;
+        if ((rs = upload_appendable(d_values, trie.values, up_values, nullptr)) != GM_OK) return rs;
+        if ((rs = upload_appendable(d_pool, trie.pool, up_pool, nullptr)) != GM_OK) return rs;
+        if (trie.cfilter_dirty) {   // child filter of wide nodes: a few MB, shipped whole into a new buffer (a rebuild changes its geometry)
+            if ((rs = stage_fresh(d_cfilter, trie.cfilter, 0)) != GM_OK) return rs;
             trie.cfilter_dirty = false;
         }
         trie.root_dirty = false;
-        dev_view = view();
-        dev_rview = rview();
-        CUDA_TRY(cudaEventRecord(ev_flush, side));
-        CUDA_TRY(cudaStreamSynchronize(side));
+        if (stage_used_) {
+            CUDA_TRY(d_patch.ensure(stage_used_));
+            CUDA_TRY(cudaMemcpyAsync(d_patch.p, h_arena_[arena_], stage_used_, cudaMemcpyHostToDevice, side));
+        }
+        // ---------------- phase B: the fence ----------------
+        {
+            std::lock_guard<std::mutex> gd(mu_dev);
+            for (MatchCtx* c : all_ctxs()) if (c->recorded) CUDA_TRY(cudaStreamWaitEvent(side, c->ev_done, 0));   // never patch under a running match
+            for (Swap& sw : swaps_) {
+                if (sw.dst->p) retired.push_back(Retired{sw.dst->detach(), flush_gen});
+                *sw.dst = std::move(sw.fresh);
+            }
+            swaps_.clear();
+            for (const PatchJob& j : jobs_) {
+                const u32* idx = reinterpret_cast<const u32*>(static_cast<char*>(d_patch.p) + j.off_idx);
+                const void* data = static_cast<char*>(d_patch.p) + j.off_data;
+                const unsigned grid = (j.n + 255) / 256;
+                if (j.elem == 32) k_apply_patches<Blk32><<<grid, 256, 0, side>>>(j.table->as<Blk32>(), idx, static_cast<const Blk32*>(data), j.n);
+                else if (j.elem == 8) k_apply_patches<Range><<<grid, 256, 0, side>>>(j.table->as<Range>(), idx, static_cast<const Range*>(data), j.n);
+                else if (j.elem == 4) k_apply_patches<u32><<<grid, 256, 0, side>>>(j.table->as<u32>(), idx, static_cast<const u32*>(data), j.n);
+                else k_apply_patches<u8><<<grid, 256, 0, side>>>(j.table->as<u8>(), idx, static_cast<const u8*>(data), j.n);
+                launches++;
+            }
+            CUDA_TRY(cudaGetLastError());
+            if (stage_used_) { CUDA_TRY(cudaEventRecord(ev_arena_[arena_], side)); arena_pending_[arena_] = true; }
+            dev_view = view();
+            dev_rview = rview();
+            view_epoch++;
+            CUDA_TRY(cudaEventRecord(ev_flush, side));
+            flush_gen++;
+        }
+        if (r_shipped) rtree.shipped();
         return GM_OK;
     }
 
-    // ---- the match pipeline, all on `s`, all buffers on the device ---------------------------------
+    std::vector<MatchCtx*> all_ctxs() { std::vector<MatchCtx*> v; for (auto& c : ctxs) v.push_back(&c); v.push_back(&devctx); return v; }
+
+    // ---- the match pipeline, all on `s`, all buffers on the device; scratch from context `c` (caller holds mu_dev) ----
     // `desc`: descriptor mode (d_ids_ is then a uint2 array of value-set references, cap_ids counts descriptors).
     // `d_sel`: optional selection — row t matches entry d_sel[t] of the packed batch (n = number of selected rows).
-    int enqueue_match(const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, void* d_ids_, u64 cap_ids,
+    // `hdr` (small-batch graphs only): device words {n, blob_bytes} read by the kernels at run time; n is then the CAPACITY.
+    int enqueue_match(MatchCtx& c, const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, void* d_ids_, u64 cap_ids,
                       u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool keep_cursor = false, bool desc = false,
-                      const u32* d_sel = nullptr) {
+                      const u32* d_sel = nullptr, u64 readable_bytes = 0, const u32* hdr = nullptr, bool timing = true, u32 site_bits_override = 0) {
         if (n == 0) { if (d_needed) CUDA_TRY(cudaMemsetAsync(d_needed, 0, sizeof(u64), s)); return GM_OK; }
         if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
         const u32 n32 = static_cast<u32>(n);
         const u32 S = std::max<u32>(1u, dev_view.max_depth);
-        CUDA_TRY(d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * n32 * sizeof(u32) : 256));
-        CUDA_TRY(d_tok8.ensure(static_cast<size_t>(n32) * TOK8 * sizeof(u32)));
-        CUDA_TRY(d_meta.ensure(n32 * sizeof(u32)));
-        CUDA_TRY(d_slow.ensure(n32 * sizeof(u32)));
-        CUDA_TRY(d_ctrl.ensure(sizeof(Ctrl)));
+        CUDA_TRY(c.d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * n32 * sizeof(u32) : 256));
+        CUDA_TRY(c.d_tok8.ensure(static_cast<size_t>(n32) * TOK8 * sizeof(u32)));
+        CUDA_TRY(c.d_meta.ensure(n32 * sizeof(u32)));
+        CUDA_TRY(c.d_slow.ensure(n32 * sizeof(u32)));
+        CUDA_TRY(c.d_ctrl.ensure(sizeof(Ctrl)));
         // locality pass scratch: bkey[n], perm[n]; hist + cursor [NBUCKETS] each
-        CUDA_TRY(d_sort.ensure(static_cast<size_t>(n32) * 11 * sizeof(u32) + 64));
-        const u32 site_bits = knobs.site_bits, sub_bits = knobs.sub_bits;
+        CUDA_TRY(c.d_sort.ensure(static_cast<size_t>(n32) * 11 * sizeof(u32) + 64));
+        const u32 site_bits = site_bits_override ? site_bits_override : knobs.site_bits, sub_bits = site_bits_override ? 0u : knobs.sub_bits;
         const u32 NBUCKETS = 1u << (site_bits + sub_bits);
-        CUDA_TRY(d_hist.ensure(2 * static_cast<size_t>(NBUCKETS) * sizeof(u32)));
-        u32* bkey = d_sort.as<u32>();
+        CUDA_TRY(c.d_hist.ensure(2 * static_cast<size_t>(NBUCKETS) * sizeof(u32)));
+        u32* bkey = c.d_sort.as<u32>();
         u32* perm = bkey + n32;
         u32* meta_sorted = perm + n32;
         u32* tok8_sorted = meta_sorted + n32 + ((8 - (3 * static_cast<size_t>(n32)) % 8) % 8);   // 32-byte aligned rows
         const bool sorted_rows = knobs.sorted_rows;
-        u32* hist = d_hist.as<u32>();
+        u32* hist = c.d_hist.as<u32>();
         u32* bcursor = hist + NBUCKETS;
-        const int k3_blocks = num_sms * 4;
+        const bool small = hdr != nullptr;
+        const int k3_blocks = small ? std::max(1, std::min<int>(num_sms, (n32 + 7) / 8)) : num_sms * 4;
         const u32 stack_cap = 32u * (dev_view.max_depth + 2u) + 64u;
-        CUDA_TRY(d_gstack.ensure(static_cast<size_t>(k3_blocks) * 8 * stack_cap * sizeof(u64)));
+        CUDA_TRY(c.d_gstack.ensure(static_cast<size_t>(num_sms) * 4 * 8 * stack_cap * sizeof(u64)));
         const int k2_ctas = (knobs.k2_ctas >= 1 && knobs.k2_ctas <= K2_CTAS_PER_SM) ? knobs.k2_ctas : K2_CTAS_PER_SM;
-        const int k2_grid = num_sms * k2_ctas;
-        CUDA_TRY(d_gpool.ensure(static_cast<size_t>(k2_grid) * K2_THREADS * K2_POOL_ROWS * sizeof(Desc)));
-        CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
-        if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(s, ev_match, 0));   // scratch is shared: one match in flight
+        const int k2_grid = small ? std::max(1, std::min<int>(num_sms * k2_ctas, (n32 + K2_THREADS - 1) / K2_THREADS)) : num_sms * k2_ctas;
+        CUDA_TRY(c.d_gpool.ensure(static_cast<size_t>(num_sms) * k2_ctas * K2_THREADS * K2_POOL_ROWS * sizeof(Desc)));
+        if (!small) {      // (a captured graph carries these dependencies as its launch order; events of other streams cannot be waited on while capturing)
+            CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
+            if (c.recorded) CUDA_TRY(cudaStreamWaitEvent(s, c.ev_done, 0));   // this context's scratch: one match at a time
+        }
         // the bump cursor over out_ids survives between the chunks of one pipelined host call
-        if (keep_cursor) CUDA_TRY(cudaMemsetAsync(static_cast<char*>(d_ctrl.p) + sizeof(unsigned long long), 0, sizeof(Ctrl) - sizeof(unsigned long long), s));
-        else CUDA_TRY(cudaMemsetAsync(d_ctrl.p, 0, sizeof(Ctrl), s));
+        if (keep_cursor) CUDA_TRY(cudaMemsetAsync(static_cast<char*>(c.d_ctrl.p) + sizeof(unsigned long long), 0, sizeof(Ctrl) - sizeof(unsigned long long), s));
+        else CUDA_TRY(cudaMemsetAsync(c.d_ctrl.p, 0, sizeof(Ctrl), s));
         CUDA_TRY(cudaMemsetAsync(hist, 0, NBUCKETS * sizeof(u32), s));
-        Ctrl* ctrl = d_ctrl.as<Ctrl>();
+        Ctrl* ctrl = c.d_ctrl.as<Ctrl>();
         const TrieView tv = dev_view;
 
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
-        CUDA_TRY(cudaEventRecord(ev_t[0], s));
-        k_tokenize<<<(n32 + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-            static_cast<const u8*>(d_blob_), static_cast<u32>(blob_bytes), d_offs_, d_sel, n32, tv, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, bkey, hist, site_bits, sub_bits);
+        if (timing) CUDA_TRY(cudaEventRecord(ev_t[0], s));
+        auto k1 = knobs.tok_bulk ? k_tokenize<true> : k_tokenize<false>;
+        k1<<<(n32 + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
+            static_cast<const u8*>(d_blob_), static_cast<u32>(blob_bytes), static_cast<u32>(std::max<u64>(blob_bytes, readable_bytes)), d_offs_, d_sel, n32, hdr, tv, S,
+            c.d_tok8.as<u32>(), c.d_tok.as<u32>(), c.d_meta.as<u32>(), d_status_, bkey, hist, site_bits, sub_bits);
         k_bucket_scan<<<1, 1024, 0, s>>>(hist, bcursor, NBUCKETS);
-        k_bucket_scatter<<<(n32 + 255) / 256, 256, 0, s>>>(bkey, bcursor, n32, perm, d_tok8.as<u32>(), d_meta.as<u32>(),
+        k_bucket_scatter<<<(n32 + 255) / 256, 256, 0, s>>>(bkey, bcursor, n32, hdr, perm, c.d_tok8.as<u32>(), c.d_meta.as<u32>(),
                                                             sorted_rows ? tok8_sorted : nullptr, meta_sorted);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(ev_t[1], s));
+        if (timing) CUDA_TRY(cudaEventRecord(ev_t[1], s));
 
         MatchParams mp{};
-        mp.tv = tv; mp.tok8 = d_tok8.as<u32>(); mp.tok = d_tok.as<u32>(); mp.meta = d_meta.as<u32>(); mp.n = n32; mp.tok_levels = S;
+        mp.tv = tv; mp.tok8 = c.d_tok8.as<u32>(); mp.tok = c.d_tok.as<u32>(); mp.meta = c.d_meta.as<u32>(); mp.n = n32; mp.n_ptr = hdr; mp.tok_levels = S;
         mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = static_cast<u32*>(d_ids_); mp.out_desc = static_cast<uint2*>(d_ids_); mp.cap_ids = cap_ids;
         mp.status = d_status_;
-        mp.cursor = &ctrl->cursor; mp.slow_list = d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
+        mp.cursor = &ctrl->cursor; mp.slow_list = c.d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
         mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
         mp.flags = (sorted_rows ? MP_SORTED_ROWS : 0u) | knobs.diag_flags;
@@ -341,40 +473,40 @@ struct gm_engine {
             for (auto k : {k2_ss, k2_sd, k2_ns, k2_nd}) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
             k2_attr_set = true;
         }
-        (stats ? (desc ? k2_sd : k2_ss) : (desc ? k2_nd : k2_ns))<<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, d_gpool.as<Desc>(), K2_POOL_ROWS);
+        (stats ? (desc ? k2_sd : k2_ss) : (desc ? k2_nd : k2_ns))<<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, c.d_gpool.as<Desc>(), K2_POOL_ROWS);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(ev_t[2], s));
+        if (timing) CUDA_TRY(cudaEventRecord(ev_t[2], s));
         auto k3 = stats ? (desc ? k_match_slow<true, true> : k_match_slow<true, false>) : (desc ? k_match_slow<false, true> : k_match_slow<false, false>);
-        k3<<<k3_blocks, 256, 0, s>>>(mp, d_gstack.as<u64>(), stack_cap);
+        k3<<<k3_blocks, 256, 0, s>>>(mp, c.d_gstack.as<u64>(), stack_cap);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(ev_t[3], s));
-        ring_n++;
+        if (timing) { CUDA_TRY(cudaEventRecord(ev_t[3], s)); ring_n++; }
         launches += 5;
         if (d_needed) CUDA_TRY(cudaMemcpyAsync(d_needed, &ctrl->cursor, sizeof(u64), cudaMemcpyDeviceToDevice, s));
-        CUDA_TRY(cudaEventRecord(ev_match, s));
-        match_recorded = true;
+        if (!small) { CUDA_TRY(cudaEventRecord(c.ev_done, s)); c.recorded = true; }
         return GM_OK;
     }
 
     // ---- retained lookup: tokenise filters -> frontier BFS (one step kernel per tree level) -> publish ----
-    struct RCtl { unsigned long long grand; u32 err; u32 pad; u32 n_desc[RQ]; u32 counts[RQ]; };   // counts[(max_depth + 3) * RQ] follow
+    struct RCtl { unsigned long long grand; unsigned long long stats[2]; u32 err; u32 pad; u32 n_desc[RQ]; u32 counts[RQ]; };   // counts[(max_depth + 3) * RQ] follow
 
     int enqueue_retain(const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s) {
+        std::lock_guard<std::mutex> gd(mu_dev);     // enqueue only; the caller (holding mu_ret) synchronises afterwards without it
+        MatchCtx& c = devctx;
         const u32 nq = static_cast<u32>(n);
         const u32 depth = dev_rview.max_depth;
         const u32 S = depth + 2;                       // the walk reads filter levels pos and pos+1 with pos <= tree depth
         const size_t ctl_bytes = sizeof(RCtl) + static_cast<size_t>(depth + 3) * RQ * sizeof(u32);
-        CUDA_TRY(d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * nq * sizeof(u32) : 256));
-        CUDA_TRY(d_tok8.ensure(static_cast<size_t>(nq) * TOK8 * sizeof(u32)));
-        CUDA_TRY(d_meta.ensure(nq * sizeof(u32)));
+        CUDA_TRY(c.d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * nq * sizeof(u32) : 256));
+        CUDA_TRY(c.d_tok8.ensure(static_cast<size_t>(nq) * TOK8 * sizeof(u32)));
+        CUDA_TRY(c.d_meta.ensure(nq * sizeof(u32)));
         CUDA_TRY(d_rq.ensure(static_cast<size_t>(nq) * 3 * sizeof(u32)));
         CUDA_TRY(d_rctl.ensure(ctl_bytes));
         const u32 slice_items = r_cap_items / RQ, slice_desc = r_cap_desc / RQ;   // queues are split into RQ slices
-        CUDA_TRY(d_rfront[0].ensure(static_cast<size_t>(slice_items) * RQ * sizeof(RItem)));
-        CUDA_TRY(d_rfront[1].ensure(static_cast<size_t>(slice_items) * RQ * sizeof(RItem)));
+        CUDA_TRY(d_rfront[0].ensure(static_cast<size_t>(slice_items) * RQ * sizeof(RTask)));
+        CUDA_TRY(d_rfront[1].ensure(static_cast<size_t>(slice_items) * RQ * sizeof(RTask)));
         CUDA_TRY(d_rdescs.ensure(static_cast<size_t>(slice_desc) * RQ * sizeof(RDesc)));
         CUDA_TRY(cudaStreamWaitEvent(s, ev_flush, 0));
-        if (match_recorded) CUDA_TRY(cudaStreamWaitEvent(s, ev_match, 0));
+        if (c.recorded) CUDA_TRY(cudaStreamWaitEvent(s, c.ev_done, 0));
         CUDA_TRY(cudaMemsetAsync(d_rctl.p, 0, ctl_bytes, s));
         CUDA_TRY(cudaMemsetAsync(d_rq.p, 0, static_cast<size_t>(nq) * 3 * sizeof(u32), s));
         RCtl* ctl = d_rctl.as<RCtl>();
@@ -383,28 +515,32 @@ struct gm_engine {
         u32* qcur = qbase + nq;
         cudaEvent_t* ev_t = ev_ring[ring_n % RING];
         CUDA_TRY(cudaEventRecord(ev_t[0], s));
-        k_tokenize<<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), static_cast<u32>(blob_bytes), d_offs_, nullptr, nq, dev_view, S, d_tok8.as<u32>(), d_tok.as<u32>(), d_meta.as<u32>(), d_status_, nullptr, nullptr, 0u, 0u);
+        k_tokenize<false><<<(nq + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(static_cast<const u8*>(d_blob_), static_cast<u32>(blob_bytes), static_cast<u32>(blob_bytes), d_offs_, nullptr, nq, nullptr, dev_view, S, c.d_tok8.as<u32>(), c.d_tok.as<u32>(), c.d_meta.as<u32>(), d_status_, nullptr, nullptr, 0u, 0u);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[1], s));
         RetainParams rp{};
-        rp.v = dev_rview; rp.qtok8 = d_tok8.as<u32>(); rp.qtok = d_tok.as<u32>(); rp.qmeta = d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
+        rp.v = dev_rview; rp.qtok8 = c.d_tok8.as<u32>(); rp.qtok = c.d_tok.as<u32>(); rp.qmeta = c.d_meta.as<u32>(); rp.nq = nq; rp.tok_levels = S;
         rp.descs = d_rdescs.as<RDesc>(); rp.n_desc = ctl->n_desc; rp.cap_items = slice_items; rp.cap_desc = slice_desc;
         rp.qtotal = qtotal; rp.err = &ctl->err;
-        k_retain_init<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RItem>(), &ctl->counts[0]);
+        // round 0 follows every filter's literal prefix; every later round expands the wildcard tasks the round before
+        // queued.  A task descends at least one tree level, so depth + 1 rounds drain every queue (late rounds find
+        // theirs empty and return at once).
+        rp.stats = ctl->stats;
+        k_retain_init<false><<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RTask>(), &ctl->counts[0]);
         const int grid = num_sms * 8;
         for (u32 lvl = 0; lvl <= depth; ++lvl)
-            k_retain_step<<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RItem>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RItem>(),
-                                               &ctl->counts[static_cast<size_t>(lvl + 1) * RQ]);
+            k_retain_round<false><<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RTask>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RTask>(),
+                                                       &ctl->counts[static_cast<size_t>(lvl + 1) * RQ]);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[2], s));
         k_retain_scan<<<1, 1024, 0, s>>>(qtotal, nq, qbase, reinterpret_cast<uint2*>(d_spans_), &ctl->grand);
-        k_retain_expand<<<grid, 256, 0, s>>>(d_rdescs.as<RDesc>(), ctl->n_desc, slice_desc, d_rvals.as<u32>(), qbase, qcur, d_ids_, cap_ids);
+        k_retain_expand<<<grid, 256, 0, s>>>(d_rdescs.as<RDesc>(), ctl->n_desc, slice_desc, dev_rview.vals, qbase, qcur, d_ids_, cap_ids);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[3], s));
         ring_n++;
         launches += 4 + depth + 1;
-        CUDA_TRY(cudaEventRecord(ev_match, s));
-        match_recorded = true;
+        CUDA_TRY(cudaEventRecord(c.ev_done, s));
+        c.recorded = true;
         return GM_OK;
     }
 
@@ -459,17 +595,10 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     cudaDeviceProp prop{};
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     eng->num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&eng->s_h2d, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&eng->s_d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < gm_engine::MAXC; ++i) {
-        CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_h2d[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_comp[i], cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaMallocHost(&eng->h_cur, gm_engine::MAXC * sizeof(unsigned long long)));
+    for (MatchCtx* cx : eng->all_ctxs()) { int st = cx->init(); if (st != GM_OK) return st; }
     CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_flush, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&eng->ev_match, cudaEventDisableTiming));
+    for (auto& ev : eng->ev_arena_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& q : eng->ev_ring) for (auto& ev : q) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaEventRecord(eng->ev_flush, eng->side));
     if (c.filters_hint) eng->trie.reserve(c.filters_hint);
@@ -477,27 +606,35 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     return GM_OK;
 }
 
+void MatchCtx::destroy() {
+    for (DevBuf* b : {&d_tok, &d_tok8, &d_meta, &d_slow, &d_ctrl, &d_gstack, &d_gpool, &d_sort, &d_hist, &d_blob, &d_offs, &d_spans, &d_ids, &d_status}) b->release();
+    for (auto& g : small) if (g) { small_graph_destroy(g); g = nullptr; }
+    if (sc) cudaStreamDestroy(sc);
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
+    for (int i = 0; i < MAXC; ++i) { if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]); if (ev_comp[i]) cudaEventDestroy(ev_comp[i]); }
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (h_cur) cudaFreeHost(h_cur);
+}
+
 void gm_destroy(gm_engine* e) {
     if (!e) return;
     if (e->flags & GM_FLAG_HOST_ONLY) { delete e; return; }
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&e->d_tok8, &e->d_cfilter, &e->d_edges, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_tok, &e->d_meta,
-                      &e->d_slow, &e->d_ctrl, &e->d_gstack, &e->d_gpool, &e->d_sort, &e->d_hist, &e->d_patch_idx, &e->d_patch_data, &e->d_blob, &e->d_offs,
-                      &e->d_spans, &e->d_ids, &e->d_status, &e->d_rnodes, &e->d_rkids, &e->d_redges, &e->d_rvals, &e->d_rfront[0],
-                      &e->d_rfront[1], &e->d_rdescs, &e->d_rctl, &e->d_rq})
+    e->free_retired(true);
+    for (MatchCtx* cx : e->all_ctxs()) cx->destroy();
+    for (DevBuf* b : {&e->d_cfilter, &e->d_edges, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_patch, &e->d_rnodes, &e->d_rkids, &e->d_redges,
+                      &e->d_rvals, &e->d_rfront[0], &e->d_rfront[1], &e->d_rdescs, &e->d_rctl, &e->d_rq, &e->d_rstage[0], &e->d_rstage[1], &e->d_rstage[2],
+                      &e->d_rstage[3], &e->d_rstage[4]})
         b->release();
-    if (e->stream) cudaStreamDestroy(e->stream);
     if (e->side) cudaStreamDestroy(e->side);
-    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
-    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
-    for (int i = 0; i < gm_engine::MAXC; ++i) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]); }
-    if (e->h_cur) cudaFreeHost(e->h_cur);
     if (e->comm) { NcclApi::get().CommDestroy(e->comm); e->comm = nullptr; }
     if (e->h_comm) cudaFreeHost(e->h_comm);
     e->d_comm.release(); e->d_part.release();
+    for (auto& hp : e->h_arena_) if (hp) cudaFreeHost(hp);
+    for (auto& ev : e->ev_arena_) if (ev) cudaEventDestroy(ev);
     if (e->ev_flush) cudaEventDestroy(e->ev_flush);
-    if (e->ev_match) cudaEventDestroy(e->ev_match);
     for (auto& q : e->ev_ring) for (auto& ev : q) if (ev) cudaEventDestroy(ev);
     delete e;
 }
@@ -559,25 +696,32 @@ int32_t gm_flush(gm_engine* e) {
     return e->flush_locked();
 }
 
+// pending mutations become visible before a match unless the caller fences explicitly (GM_FLAG_MANUAL_FLUSH)
+static int32_t auto_flush(gm_engine* e, bool need_retained = false) {
+    if ((e->flags & GM_FLAG_MANUAL_FLUSH) && e->d_edges.p && (!need_retained || e->d_rnodes.p)) return GM_OK;
+    std::lock_guard<std::mutex> g(e->mu);
+    return e->flush_locked();
+}
+
 // shared implementation of the device-buffer entry points
 static int32_t match_device_impl(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n_entries, const uint32_t* d_sel,
                                  uint64_t n, gm_span* d_spans, void* d_out, uint64_t cap, uint64_t* d_needed, int32_t* d_status, void* stream,
                                  bool desc, gm_work* work) {
     if (!e || (n && (!d_offs || !d_spans || !d_status))) return GM_ERR_INVALID_ARG;
     if (blob_bytes > 0xFFFFFFFFull) { g_err = "topic blob >= 4 GiB"; return GM_ERR_TOO_LARGE; }
-    std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
-    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    { int st = auto_flush(e); if (st != GM_OK) return st; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int st = e->enqueue_match(d_blob, blob_bytes, d_offs, n, d_spans, d_out, cap, d_needed, d_status, s, work != nullptr, false, desc, d_sel);
+    std::unique_lock<std::mutex> gd(e->mu_dev);
+    int st = e->enqueue_match(e->devctx, d_blob, blob_bytes, d_offs, n, d_spans, d_out, cap, d_needed, d_status, s, work != nullptr, false, desc, d_sel);
     if (st != GM_OK || !work) return st;
     std::memset(work, 0, sizeof(*work));
     if (n == 0) return GM_OK;
     Ctrl h{};
     std::vector<u32> meta(n), offs(n_entries + 1), sel(d_sel ? n : 0);
-    CUDA_TRY(cudaMemcpyAsync(&h, e->d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(meta.data(), e->d_meta.p, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&h, e->devctx.d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(meta.data(), e->devctx.d_meta.p, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(offs.data(), d_offs, (n_entries + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
     if (d_sel) CUDA_TRY(cudaMemcpyAsync(sel.data(), d_sel, n * sizeof(u32), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -609,6 +753,131 @@ int32_t gm_match_batch_device_ex(gm_engine* e, const gm_match_args* a) {
                              a->d_needed, a->d_status, a->stream, (a->flags & GM_MATCH_DESCRIPTORS) != 0, a->work);
 }
 
+}  // extern "C"
+
+// ---- small batches: one CUDA-graph launch per call ---------------------------------------------------------------------
+// A PUBLISH-sized batch (1 .. 2048 topics) costs the same five kernels, two memsets and four copies as a million-topic
+// batch: at that size the call is pure launch latency.  Per context and capacity tier the whole sequence
+//     H2D(pinned in-block) -> memsets -> k_tokenize -> k_bucket_scan -> k_bucket_scatter -> k_match_fast -> k_match_slow
+//     -> D2H(pinned out-block)
+// is captured ONCE into a CUDA graph sized for the tier's capacity; the real batch size and text length travel in the
+// first words of the in-block (`hdr`), which the kernels read at run time.  A call then is: fill the pinned in-block,
+// cudaGraphLaunch, wait for one event, copy the results out of the pinned out-block.  The kernels carry the table view
+// by value, so the graph is re-captured (cudaGraphExecUpdate) when a flush has changed the view.
+struct SmallGraph {
+    u32 cap_n = 0, cap_blob = 0, cap_out = 0;
+    size_t elem = 0;
+    u64 view_epoch = ~0ull;
+    cudaGraphExec_t exec = nullptr;
+    char *h_in = nullptr, *h_out = nullptr;
+    size_t in_bytes = 0, out_bytes = 0, off_offs = 0, off_blob = 0, off_spans = 0, off_status = 0, off_out = 0;
+    DevBuf d_in, d_out;
+    bool warmed = false;
+};
+static void small_graph_destroy(SmallGraph* g) {
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->h_in) cudaFreeHost(g->h_in);
+    if (g->h_out) cudaFreeHost(g->h_out);
+    delete g;
+}
+
+static int small_graph_match(gm_engine* e, MatchCtx& c, std::unique_lock<std::mutex>& gd, const char* blob, const uint32_t* offsets, uint64_t n,
+                             gm_span* out_spans, void* out, size_t elem, uint64_t cap_user, uint64_t* needed, int32_t* status) {
+    const u64 b0 = offsets[0], blob_bytes = offsets[n] - b0;
+    int tier;
+    if (n <= 64 && blob_bytes <= 8 * 1024) tier = 0;
+    else if (n <= 2048 && blob_bytes <= 192 * 1024) tier = 1;
+    else return GM_SMALL_NOT_APPLICABLE;
+    SmallGraph*& g = c.small[tier];
+    if (!g) {
+        g = new SmallGraph();
+        g->cap_n = tier == 0 ? 64u : 2048u; g->cap_blob = tier == 0 ? 8u * 1024u : 192u * 1024u; g->cap_out = tier == 0 ? 4096u : 128u * 1024u;
+        g->off_offs = 16; g->off_blob = (g->off_offs + (g->cap_n + 1) * sizeof(u32) + 255) & ~size_t(255);
+        g->in_bytes = g->off_blob + g->cap_blob + 32;
+        g->off_spans = 16; g->off_status = g->off_spans + g->cap_n * sizeof(gm_span); g->off_out = (g->off_status + g->cap_n * sizeof(int32_t) + 255) & ~size_t(255);
+        g->out_bytes = g->off_out + static_cast<size_t>(g->cap_out) * 8;
+        CUDA_TRY(cudaMallocHost(&g->h_in, g->in_bytes));
+        CUDA_TRY(cudaMallocHost(&g->h_out, g->out_bytes));
+        CUDA_TRY(g->d_in.ensure(g->in_bytes));
+        CUDA_TRY(g->d_out.ensure(g->out_bytes));
+        std::memset(g->h_in, 0, g->in_bytes);
+    }
+    const bool desc = elem == 8;
+    auto enqueue = [&](cudaStream_t s) -> int {
+        char* di = static_cast<char*>(g->d_in.p);
+        char* dout = static_cast<char*>(g->d_out.p);
+        return e->enqueue_match(c, di + g->off_blob, g->cap_blob, reinterpret_cast<const u32*>(di + g->off_offs), g->cap_n, reinterpret_cast<gm_span*>(dout + g->off_spans),
+                                dout + g->off_out, g->cap_out, reinterpret_cast<u64*>(dout), reinterpret_cast<int32_t*>(dout + g->off_status), s, false, false, desc,
+                                nullptr, g->cap_blob, reinterpret_cast<const u32*>(di), false, 10u);
+    };
+    if (!g->warmed) {      // allocate the scratch and set kernel attributes outside any capture: one empty (n = 0) pass
+        CUDA_TRY(cudaMemsetAsync(g->d_in.p, 0, g->in_bytes, c.sc));
+        int st = enqueue(c.sc);
+        if (st != GM_OK) return st;
+        CUDA_TRY(cudaStreamSynchronize(c.sc));
+        g->warmed = true;
+    }
+    if (!g->exec || g->view_epoch != e->view_epoch || g->elem != elem) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(c.sc, cudaStreamCaptureModeRelaxed));
+        cudaError_t ce = cudaMemcpyAsync(g->d_in.p, g->h_in, g->in_bytes, cudaMemcpyHostToDevice, c.sc);
+        int st = ce == cudaSuccess ? enqueue(c.sc) : GM_ERR_CUDA;
+        if (st == GM_OK) ce = cudaMemcpyAsync(g->h_out, g->d_out.p, g->out_bytes, cudaMemcpyDeviceToHost, c.sc);
+        cudaError_t ee = cudaStreamEndCapture(c.sc, &graph);
+        if (st != GM_OK || ce != cudaSuccess || ee != cudaSuccess) { if (graph) cudaGraphDestroy(graph); g_err = "small-batch graph capture failed"; return st != GM_OK ? st : GM_ERR_CUDA; }
+        bool ok = false;
+        if (g->exec) {
+            cudaGraphExecUpdateResultInfo info{};
+            ok = cudaGraphExecUpdate(g->exec, graph, &info) == cudaSuccess;
+            if (!ok) { cudaGetLastError(); cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+        }
+        if (!ok) CUDA_TRY(cudaGraphInstantiate(&g->exec, graph, 0));
+        cudaGraphDestroy(graph);
+        g->view_epoch = e->view_epoch; g->elem = elem;
+    }
+    // fill the pinned in-block: {n, text bytes} | offsets re-based to 0 | text
+    u32* hdr = reinterpret_cast<u32*>(g->h_in);
+    hdr[0] = static_cast<u32>(n); hdr[1] = static_cast<u32>(blob_bytes);
+    u32* ho = reinterpret_cast<u32*>(g->h_in + g->off_offs);
+    for (u64 i = 0; i <= n; ++i) ho[i] = static_cast<u32>(offsets[i] - b0);
+    if (blob_bytes) std::memcpy(g->h_in + g->off_blob, blob + b0, blob_bytes);
+    CUDA_TRY(cudaStreamWaitEvent(c.sc, e->ev_flush, 0));
+    CUDA_TRY(cudaGraphLaunch(g->exec, c.sc));
+    CUDA_TRY(cudaEventRecord(c.ev_done, c.sc));
+    c.recorded = true;
+    e->launches += 5;
+    gd.unlock();
+    CUDA_TRY(cudaEventSynchronize(c.ev_done));
+    const u64 total = *reinterpret_cast<const u64*>(g->h_out);
+    if (total > g->cap_out) return GM_SMALL_NOT_APPLICABLE;      // more output than the tier holds: the pipelined path handles it
+    if (needed) *needed = total;
+    std::memcpy(status, g->h_out + g->off_status, n * sizeof(int32_t));
+    if (total > cap_user) { g_err = "output buffer too small"; return GM_ERR_CAPACITY; }
+    std::memcpy(out_spans, g->h_out + g->off_spans, n * sizeof(gm_span));
+    if (total) std::memcpy(out, g->h_out + g->off_out, total * elem);
+    return GM_OK;
+}
+
+extern "C" {
+
+// a free context of the pool (blocks while all NCTX are in flight); release() hands it back
+struct CtxLease {
+    gm_engine* e; MatchCtx* c = nullptr;
+    explicit CtxLease(gm_engine* e_) : e(e_) {}
+    void acquire(std::unique_lock<std::mutex>& lk) {     // lk holds e->mu_dev
+        for (;;) {
+            for (auto& cx : e->ctxs) if (!cx.busy) { cx.busy = true; c = &cx; return; }
+            e->cv_ctx.wait(lk);
+        }
+    }
+    ~CtxLease() {
+        if (!c) return;
+        { std::lock_guard<std::mutex> g(e->mu_dev); c->busy = false; }
+        e->cv_ctx.notify_one();
+    }
+};
+
 // shared implementation of the host-buffer entry points; `elem` = bytes per output element (4: ids, 8: descriptors)
 static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, void* out, size_t elem,
                                uint64_t cap_ids, uint64_t* needed, int32_t* status) {
@@ -617,55 +886,64 @@ static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* o
     if (n == 0) return GM_OK;
     if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
     const bool desc = elem == 8;
-    std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
-    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    { int st = auto_flush(e); if (st != GM_OK) return st; }
     const u64 blob_bytes = offsets[n];
     if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;
-    CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
-    CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
-    CUDA_TRY(e->d_spans.ensure(n * sizeof(gm_span)));
-    CUDA_TRY(e->d_status.ensure(n * sizeof(int32_t)));
-    CUDA_TRY(e->d_ids.ensure(std::max<u64>(cap_ids, 1) * elem));
+    CtxLease lease(e);
+    std::unique_lock<std::mutex> gd(e->mu_dev);
+    lease.acquire(gd);
+    MatchCtx& c = *lease.c;
+    // ---- small batches: the whole call as ONE CUDA-graph launch (no per-kernel launch latency) ----
+    if (e->knobs.small_graphs) {
+        int st = small_graph_match(e, c, gd, blob, offsets, n, out_spans, out, elem, cap_ids, needed, status);
+        if (st != GM_SMALL_NOT_APPLICABLE) return st;       // (gd was released inside while waiting)
+        if (!gd.owns_lock()) gd.lock();
+    }
+    CUDA_TRY(c.d_blob.ensure(blob_bytes + 16));
+    CUDA_TRY(c.d_offs.ensure((n + 1) * sizeof(u32)));
+    CUDA_TRY(c.d_spans.ensure(n * sizeof(gm_span)));
+    CUDA_TRY(c.d_status.ensure(n * sizeof(int32_t)));
+    CUDA_TRY(c.d_ids.ensure(std::max<u64>(cap_ids, 1) * elem));
     // Pipelined in chunks over three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of
     // chunk c.  All chunks share one bump cursor, so the output of chunk c is the contiguous range
     // [cursor after c-1, cursor after c) and can be copied out as soon as that chunk's kernels finished.
-    const u64 chunk = std::max<u64>(131072, (n + gm_engine::MAXC - 1) / gm_engine::MAXC);
+    const u64 chunk = std::max<u64>(e->knobs.e2e_chunk, (n + gm_engine::MAXC - 1) / gm_engine::MAXC);
     const int nchunks = static_cast<int>((n + chunk - 1) / chunk);
-    cudaStream_t sc = e->stream;
-    if (e->match_recorded) CUDA_TRY(cudaStreamWaitEvent(e->s_h2d, e->ev_match, 0));   // previous call still reads d_blob / scratch
-    for (int c = 0; c < nchunks; ++c) {
-        const u64 c0 = c * chunk, c1 = std::min<u64>(n, c0 + chunk);
+    if (c.recorded) CUDA_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_done, 0));   // (cannot happen for a leased context; cheap insurance)
+    for (int k = 0; k < nchunks; ++k) {
+        const u64 c0 = k * chunk, c1 = std::min<u64>(n, c0 + chunk);
         const u64 b0 = offsets[c0], b1 = offsets[c1];
-        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(e->d_blob.p) + b0, blob + b0, b1 - b0, cudaMemcpyHostToDevice, e->s_h2d));
-        CUDA_TRY(cudaMemcpyAsync(e->d_offs.as<u32>() + c0, offsets + c0, (c1 - c0 + 1) * sizeof(u32), cudaMemcpyHostToDevice, e->s_h2d));
-        CUDA_TRY(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
+        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(c.d_blob.p) + b0, blob + b0, b1 - b0, cudaMemcpyHostToDevice, c.s_h2d));
+        CUDA_TRY(cudaMemcpyAsync(c.d_offs.as<u32>() + c0, offsets + c0, (c1 - c0 + 1) * sizeof(u32), cudaMemcpyHostToDevice, c.s_h2d));
+        CUDA_TRY(cudaEventRecord(c.ev_h2d[k], c.s_h2d));
     }
-    for (int c = 0; c < nchunks; ++c) {
-        const u64 c0 = c * chunk, c1 = std::min<u64>(n, c0 + chunk);
-        CUDA_TRY(cudaStreamWaitEvent(sc, e->ev_h2d[c], 0));
-        int st = e->enqueue_match(e->d_blob.p, offsets[c1], e->d_offs.as<u32>() + c0, c1 - c0, e->d_spans.as<gm_span>() + c0, e->d_ids.p, cap_ids, nullptr,
-                                  e->d_status.as<int32_t>() + c0, sc, false, c != 0, desc);
+    for (int k = 0; k < nchunks; ++k) {
+        const u64 c0 = k * chunk, c1 = std::min<u64>(n, c0 + chunk);
+        CUDA_TRY(cudaStreamWaitEvent(c.sc, c.ev_h2d[k], 0));
+        int st = e->enqueue_match(c, c.d_blob.p, offsets[c1], c.d_offs.as<u32>() + c0, c1 - c0, c.d_spans.as<gm_span>() + c0, c.d_ids.p, cap_ids, nullptr,
+                                  c.d_status.as<int32_t>() + c0, c.sc, false, k != 0, desc, nullptr, (offsets[c1] + 15) & ~u64(15));
         if (st != GM_OK) return st;
-        CUDA_TRY(cudaMemcpyAsync(&e->h_cur[c], &e->d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, sc));
-        CUDA_TRY(cudaEventRecord(e->ev_comp[c], sc));
+        CUDA_TRY(cudaMemcpyAsync(&c.h_cur[k], &c.d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, c.sc));
+        CUDA_TRY(cudaEventRecord(c.ev_comp[k], c.sc));
     }
+    gd.unlock();        // everything is enqueued: other calls (and flushes) proceed while this one waits for its copies
     u64 done = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const u64 c0 = c * chunk, c1 = std::min<u64>(n, c0 + chunk);
-        CUDA_TRY(cudaEventSynchronize(e->ev_comp[c]));
-        const u64 cur = e->h_cur[c];
-        CUDA_TRY(cudaMemcpyAsync(out_spans + c0, e->d_spans.as<gm_span>() + c0, (c1 - c0) * sizeof(gm_span), cudaMemcpyDeviceToHost, e->s_d2h));
-        CUDA_TRY(cudaMemcpyAsync(status + c0, e->d_status.as<int32_t>() + c0, (c1 - c0) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_d2h));
+    for (int k = 0; k < nchunks; ++k) {
+        const u64 c0 = k * chunk, c1 = std::min<u64>(n, c0 + chunk);
+        CUDA_TRY(cudaEventSynchronize(c.ev_comp[k]));
+        const u64 cur = c.h_cur[k];
+        CUDA_TRY(cudaMemcpyAsync(out_spans + c0, c.d_spans.as<gm_span>() + c0, (c1 - c0) * sizeof(gm_span), cudaMemcpyDeviceToHost, c.s_d2h));
+        CUDA_TRY(cudaMemcpyAsync(status + c0, c.d_status.as<int32_t>() + c0, (c1 - c0) * sizeof(int32_t), cudaMemcpyDeviceToHost, c.s_d2h));
         const u64 hi = std::min<u64>(cur, cap_ids);
         if (hi > done) {
-            CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + done * elem, static_cast<char*>(e->d_ids.p) + done * elem, (hi - done) * elem, cudaMemcpyDeviceToHost, e->s_d2h));
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + done * elem, static_cast<char*>(c.d_ids.p) + done * elem, (hi - done) * elem, cudaMemcpyDeviceToHost, c.s_d2h));
             done = hi;
         }
     }
-    CUDA_TRY(cudaStreamSynchronize(e->s_d2h));
-    const u64 total = e->h_cur[nchunks - 1];
+    CUDA_TRY(cudaStreamSynchronize(c.s_d2h));
+    const u64 total = c.h_cur[nchunks - 1];
     if (needed) *needed = total;
     if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 output elements: split it"; return GM_ERR_TOO_LARGE; }
     if (total > cap_ids) { g_err = "output buffer too small"; return GM_ERR_CAPACITY; }
@@ -749,10 +1027,10 @@ int32_t gm_retain_match_batch_device(gm_engine* e, const void* d_blob, uint64_t 
     if (needed) *needed = 0;
     if (n == 0) return GM_OK;
     if (blob_bytes > 0xFFFFFFFFull || n > 0xFFFFFFF0ull) { g_err = "filter batch too large"; return GM_ERR_TOO_LARGE; }
-    std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
-    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_rnodes.p || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    std::lock_guard<std::mutex> gr(e->mu_ret);      // the retained lookup's scratch is engine-wide: one lookup at a time
+    { int st = auto_flush(e, true); if (st != GM_OK) return st; }
     u64 total = 0;
     int st = e->run_retain(d_blob, blob_bytes, d_offs, n, d_spans, d_ids, std::min<u64>(cap_ids, 0xFFFFFFFFull), d_status, static_cast<cudaStream_t>(stream), &total);
     if (st != GM_OK) return st;
@@ -768,31 +1046,33 @@ int32_t gm_retain_match_batch(gm_engine* e, const char* blob, const uint32_t* of
     if (needed) *needed = 0;
     if (n == 0) return GM_OK;
     if (n > 0xFFFFFFF0ull) { g_err = "filter batch too large"; return GM_ERR_TOO_LARGE; }
-    std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
-    if (!(e->flags & GM_FLAG_MANUAL_FLUSH) || !e->d_rnodes.p || !e->d_edges.p) { int st = e->flush_locked(); if (st != GM_OK) return st; }
+    std::lock_guard<std::mutex> gr(e->mu_ret);
+    { int st = auto_flush(e, true); if (st != GM_OK) return st; }
     const u64 blob_bytes = offsets[n];
-    cudaStream_t s = e->stream;
-    CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
-    CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
-    CUDA_TRY(e->d_spans.ensure(n * sizeof(gm_span)));
-    CUDA_TRY(e->d_status.ensure(n * sizeof(int32_t)));
-    CUDA_TRY(e->d_ids.ensure(std::max<u64>(cap_ids, 1) * sizeof(u32)));
-    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
+    MatchCtx& c = e->devctx;                          // staging of the retained host call (guarded by mu_ret)
+    cudaStream_t s = c.sc;
+    DevBuf &rb = e->d_rstage[0], &ro = e->d_rstage[1], &rs = e->d_rstage[2], &rt = e->d_rstage[3], &ri = e->d_rstage[4];
+    CUDA_TRY(rb.ensure(blob_bytes + 16));
+    CUDA_TRY(ro.ensure((n + 1) * sizeof(u32)));
+    CUDA_TRY(rs.ensure(n * sizeof(gm_span)));
+    CUDA_TRY(rt.ensure(n * sizeof(int32_t)));
+    CUDA_TRY(ri.ensure(std::max<u64>(cap_ids, 1) * sizeof(u32)));
+    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(rb.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(ro.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
     u64 total = 0;
-    int st = e->run_retain(e->d_blob.p, blob_bytes, e->d_offs.as<u32>(), n, e->d_spans.as<gm_span>(), e->d_ids.as<u32>(), std::min<u64>(cap_ids, 0xFFFFFFFFull),
-                           e->d_status.as<int32_t>(), s, &total);
+    int st = e->run_retain(rb.p, blob_bytes, ro.as<u32>(), n, rs.as<gm_span>(), ri.as<u32>(), std::min<u64>(cap_ids, 0xFFFFFFFFull),
+                           rt.as<int32_t>(), s, &total);
     if (st != GM_OK) return st;
-    CUDA_TRY(cudaMemcpyAsync(status, e->d_status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_spans, e->d_spans.p, n * sizeof(gm_span), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status, rt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_spans, rs.p, n * sizeof(gm_span), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (needed) *needed = total;
     if (total > 0xFFFFFFFFull) { g_err = "batch produces >= 2^32 ids: split it"; return GM_ERR_TOO_LARGE; }
     if (total > cap_ids) { g_err = "out_ids too small"; return GM_ERR_CAPACITY; }
     if (total) {
-        CUDA_TRY(cudaMemcpyAsync(out_ids, e->d_ids.p, total * sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out_ids, ri.p, total * sizeof(u32), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
     }
     return GM_OK;
@@ -880,7 +1160,7 @@ int32_t gm_comm_unique_id(uint8_t* out_id) {
 
 int32_t gm_comm_init(gm_engine* e, const uint8_t* id128, uint32_t rank, uint32_t world) {
     if (!e || !id128 || world == 0 || rank >= world) return GM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> g(e->mu_dev);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine has no device to communicate from"; return GM_ERR_NO_DEVICE; }
     NcclApi& nc = NcclApi::get();
     if (!nc.ok()) { g_err = nc.error; return GM_ERR_COMM; }
@@ -898,7 +1178,7 @@ int32_t gm_comm_init(gm_engine* e, const uint8_t* id128, uint32_t rank, uint32_t
 
 int32_t gm_comm_destroy(gm_engine* e) {
     if (!e) return GM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> g(e->mu_dev);
     if (e->comm) { cudaSetDevice(e->device); NcclApi::get().CommDestroy(e->comm); e->comm = nullptr; }
     e->comm_world = 1; e->comm_rank = 0;
     return GM_OK;
@@ -909,7 +1189,7 @@ int32_t gm_partition_batch_device(gm_engine* e, const void* d_blob, uint64_t blo
     if (!e || !n_local || n_shards == 0 || n_shards > 4096 || rank >= n_shards || (n && (!d_blob || !d_offsets || !d_sel))) return GM_ERR_INVALID_ARG;
     if (blob_bytes > 0xFFFFFFFFull || n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
     *n_local = 0;
-    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> g(e->mu_dev);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine has no device"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -934,7 +1214,7 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
                              uint32_t* d_all_index, gm_span* d_all_spans, uint64_t cap_topics, uint32_t* d_all_ids, uint64_t cap_ids, uint64_t* sizes,
                              void* stream) {
     if (!e || !d_m || !sizes || (k && (!d_index || !d_spans)) || !d_all_index || !d_all_spans || !d_all_ids) return GM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> g(e->mu_dev);
     if (!e->comm) { g_err = "gm_allgatherv_device: call gm_comm_init first"; return GM_ERR_INVALID_ARG; }
     NcclApi& nc = NcclApi::get();
     CUDA_TRY(cudaSetDevice(e->device));
@@ -974,25 +1254,27 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
 int32_t gm_tokenize_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, uint32_t max_tok, uint32_t* out_tokens, uint32_t* out_meta) {
     if (!e || !max_tok || (n && (!offsets || !out_tokens || !out_meta))) return GM_ERR_INVALID_ARG;
     if (n == 0) return GM_OK;
-    std::lock_guard<std::mutex> g(e->mu);
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
     CUDA_TRY(cudaSetDevice(e->device));
-    { int st = e->flush_locked(); if (st != GM_OK) return st; }
-    cudaStream_t s = e->stream;
+    { std::lock_guard<std::mutex> g(e->mu); int st = e->flush_locked(); if (st != GM_OK) return st; }
+    std::lock_guard<std::mutex> g(e->mu_dev);
+    cudaStream_t s = e->devctx.sc;
+    DevBuf t_blob, t_offs;
     const u64 blob_bytes = offsets[n];
     DevBuf tok, tok8, meta, stat;
-    CUDA_TRY(e->d_blob.ensure(blob_bytes + 16));
-    CUDA_TRY(e->d_offs.ensure((n + 1) * sizeof(u32)));
+    CUDA_TRY(t_blob.ensure(blob_bytes + 16));
+    CUDA_TRY(t_offs.ensure((n + 1) * sizeof(u32)));
     CUDA_TRY(tok.ensure(static_cast<size_t>(max_tok) * n * sizeof(u32)));
     CUDA_TRY(tok8.ensure(static_cast<size_t>(n) * TOK8 * sizeof(u32)));
     CUDA_TRY(meta.ensure(n * sizeof(u32)));
     CUDA_TRY(stat.ensure(n * sizeof(int)));
-    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(e->d_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
+    if (blob_bytes) CUDA_TRY(cudaMemcpyAsync(t_blob.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(t_offs.p, offsets, (n + 1) * sizeof(u32), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(tok.p, 0, static_cast<size_t>(max_tok) * n * sizeof(u32), s));
     CUDA_TRY(cudaStreamWaitEvent(s, e->ev_flush, 0));
-    k_tokenize<<<(static_cast<u32>(n) + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
-        e->d_blob.as<u8>(), static_cast<u32>(blob_bytes), e->d_offs.as<u32>(), nullptr, static_cast<u32>(n), e->dev_view, max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr, 0u, 0u);
+    auto k1 = e->knobs.tok_bulk ? k_tokenize<true> : k_tokenize<false>;
+    k1<<<(static_cast<u32>(n) + TOK_THREADS - 1) / TOK_THREADS, TOK_THREADS, 0, s>>>(
+        t_blob.as<u8>(), static_cast<u32>(blob_bytes), static_cast<u32>((blob_bytes + 15) & ~u64(15)), t_offs.as<u32>(), nullptr, static_cast<u32>(n), nullptr, e->dev_view, max_tok, tok8.as<u32>(), tok.as<u32>(), meta.as<u32>(), stat.as<int>(), nullptr, nullptr, 0u, 0u);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_tokens, tok.p, static_cast<size_t>(max_tok) * n * sizeof(u32), cudaMemcpyDeviceToHost, s));
@@ -1025,7 +1307,7 @@ int32_t gm_get_stats(gm_engine* e, gm_stats* out) {
 
 int32_t gm_kernel_ms_ring(gm_engine* e, float* out_ms, uint32_t max_calls, uint32_t* n_calls) {
     if (!e || !out_ms || !n_calls) return GM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> g(e->mu_dev);
     *n_calls = 0;
     if (e->flags & GM_FLAG_HOST_ONLY) return GM_OK;
     CUDA_TRY(cudaSetDevice(e->device));
@@ -1070,13 +1352,16 @@ int32_t gm_debug_table(gm_engine* e, uint32_t which, const void** ptr, uint64_t*
 
 int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value) {
     if (!e || !name) return GM_ERR_INVALID_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
+    std::lock_guard<std::mutex> g(e->mu_dev);
     const std::string k(name);
     if (k == "tile_chunk" && value >= 1 && value <= 1024) e->knobs.tile_chunk = static_cast<u32>(value);
     else if (k == "k2_ctas" && value >= 0 && value <= 8) e->knobs.k2_ctas = static_cast<int>(value);
     else if (k == "sorted_rows") e->knobs.sorted_rows = value != 0;
     else if (k == "bucket_bits" && value / 100 >= 10 && value % 100 + value / 100 <= int64_t(MAX_BUCKET_BITS)) { e->knobs.site_bits = static_cast<u32>(value / 100); e->knobs.sub_bits = static_cast<u32>(value % 100); }
     else if (k == "diag_flags") e->knobs.diag_flags = static_cast<u32>(value);
+    else if (k == "tok_bulk") e->knobs.tok_bulk = value != 0;
+    else if (k == "small_graphs") e->knobs.small_graphs = value != 0;
+    else if (k == "e2e_chunk" && value >= 1024) e->knobs.e2e_chunk = static_cast<u32>(value);
     else return GM_ERR_INVALID_ARG;
     return GM_OK;
 }

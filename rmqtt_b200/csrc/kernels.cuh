@@ -39,6 +39,7 @@ struct MatchParams {
     const u32* tok8_sorted;   // [n][8] token rows copied into locality order (MP_SORTED_ROWS)
     const u32* meta_sorted;   // [n]
     u32 tile_chunk;           // tiles a CTA takes from the global counter at once (<= 1: one tile per warp per grab)
+    const u32* n_ptr;         // small-batch graphs: the real batch size lives in device memory (n is then the capacity = row stride of `tok`)
     uint2* out_desc;          // DESCRIPTOR mode: matched value sets (ref, cnt16) per topic instead of expanded ids; spans index this array
     int* status;              // [n] per-topic status (k_tokenize wrote it); the deferred kernel reports GM_ERR_INTERNAL here
 };
@@ -80,6 +81,37 @@ __device__ __forceinline__ u32 text4(const u8* a, const u8* limit) {
     return __funnelshift_r(lo, hi, 8u * static_cast<u32>(ai & 3));
 }
 
+// the same out of the CTA's shared-memory stage of the text slice (`sbase` = blob offset of stage byte 0, 16-byte aligned;
+// the stage is zero-padded past the copied bytes up to its capacity, so whole-word reads are always defined)
+__device__ __forceinline__ u32 text4_s(const u32* stage, u32 off) {
+    const u32 lo = stage[off >> 2], hi = stage[(off >> 2) + 1];
+    return __funnelshift_r(lo, hi, 8u * (off & 3u));
+}
+
+// ---- 1-D bulk asynchronous copy global -> shared (TMA engine, cp.async.bulk), completion on an mbarrier ----------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return static_cast<u32>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+    u32 done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
 __device__ __forceinline__ u32 dict_lookup_inline(const TrieView& tv, const u32 (&w)[7]) {
     u32 idx = dict_hash_words(w) & tv.dict_mask;
     for (;;) {
@@ -94,6 +126,9 @@ __device__ __forceinline__ u32 dict_lookup_inline(const TrieView& tv, const u32 
     }
 }
 
+// (a template only so that every kernel instantiation owns its private out-of-line copy: two kernels sharing one
+//  noinline function made ptxas 12.9 crash once one of them used the bulk-copy / mbarrier instructions)
+template <int OWNER>
 __device__ __noinline__ u32 dict_lookup_long(const TrieView& tv, const u8* text, u32 len) {
     u32 h = FNV_INIT;
     for (u32 i = 0; i < len; ++i) h = fnv_step(h, text[i]);
@@ -114,10 +149,45 @@ __device__ __noinline__ u32 dict_lookup_long(const TrieView& tv, const u8* text,
 
 // `sel` (optional): row t tokenises entry sel[t] of the packed batch (this rank's topics of a mixed batch, gm_partition_batch_device).
 // `blob_bytes` bounds every text read: words that start at or beyond blob + blob_bytes are never dereferenced.
+// BULK: the CTA's 256 topics are one contiguous slice of the blob (~12 KB on C3).  One elected thread asks the TMA engine
+// for the whole slice with ONE cp.async.bulk into shared memory (16-byte aligned superset of the slice, completion
+// counted in bytes on an mbarrier) and every thread then reads its topic's text from shared memory, instead of every
+// thread pulling its own unaligned 32-bit words through L1.  `readable_bytes` (>= blob_bytes) says how far the
+// allocation may be read; a CTA whose aligned slice does not fit the stage or the readable range, a blob pointer that is
+// not 16-byte aligned, or a selection (`sel`: rows are not contiguous) takes the plain global-load path.
+constexpr u32 TOK_STAGE_BYTES = 24 * 1024;    // 96 B per topic on average before a CTA falls back
+template <bool BULK>
 __global__ void __launch_bounds__(TOK_THREADS)
-k_tokenize(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__ offs, const u32* __restrict__ sel, u32 n, TrieView tv, u32 tok_levels,
+k_tokenize(const u8* __restrict__ blob, u32 blob_bytes, u32 readable_bytes, const u32* __restrict__ offs, const u32* __restrict__ sel, u32 n, const u32* __restrict__ hdr, TrieView tv, u32 tok_levels,
            u32* __restrict__ tok8, u32* __restrict__ tok, u32* __restrict__ meta, int* __restrict__ status, u32* __restrict__ bkey,
            u32* __restrict__ hist, u32 site_bits, u32 sub_bits) {
+    __shared__ __align__(128) u32 s_stage[BULK ? TOK_STAGE_BYTES / 4 + 2 : 1];
+    __shared__ __align__(8) unsigned long long s_bar;
+    // small-batch graphs: the launch is sized for a CAPACITY `n`; the real batch size and text length sit in device memory
+    const u32 stride = n;                        // row stride of the level-major `tok` array
+    if (hdr) { n = min(n, hdr[0]); blob_bytes = readable_bytes = hdr[1]; }
+    bool staged = false;
+    u32 sbase = 0;
+    if (BULK) {
+        const u32 t0 = blockIdx.x * TOK_THREADS, t1 = min(n, t0 + TOK_THREADS);
+        const bool any = t0 < n;                 // (a capacity-sized launch has CTAs beyond the real batch)
+        const u32 b0 = any ? offs[t0] & ~15u : 0u;
+        const u32 e0 = any ? (min(offs[t1], blob_bytes) + 15u) & ~15u : 0u;
+        staged = any && sel == nullptr && (reinterpret_cast<uintptr_t>(blob) & 15u) == 0 && e0 > b0 && e0 - b0 <= TOK_STAGE_BYTES && e0 <= readable_bytes;
+        if (staged) {           // uniform over the CTA
+            sbase = b0;
+            if (threadIdx.x == 0) {
+                mbar_init(&s_bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                mbar_expect_tx(&s_bar, e0 - b0);
+                bulk_g2s(s_stage, blob + b0, e0 - b0, &s_bar);
+            }
+            // the two words behind the copied bytes are read by text4_s of the last topic: define them
+            if (threadIdx.x == 1) { s_stage[(e0 - b0) >> 2] = 0u; s_stage[((e0 - b0) >> 2) + 1] = 0u; }
+            __syncthreads();    // barrier initialised before anyone polls it
+            mbar_wait(&s_bar, 0);
+        }
+    }
     const u32 t = blockIdx.x * TOK_THREADS + threadIdx.x;
     if (t >= n) return;
     const u32 src = sel ? sel[t] : t;
@@ -135,7 +205,7 @@ k_tokenize(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             if (!ended) {
-                u32 x = text4(blob + pos, limit);
+                u32 x = (BULK && staged) ? text4_s(s_stage, pos - sbase) : text4(blob + pos, limit);
                 const u32 z = swar_zero_bytes(x ^ 0x2F2F2F2Fu);                       // '/' bytes
                 u32 nb = z ? static_cast<u32>((__ffs(z) - 1) >> 3) : 4u;             // bytes before the first '/'
                 nb = min(nb, end - pos);                                             // ... and before the end of the topic
@@ -160,13 +230,13 @@ k_tokenize(const u8* __restrict__ blob, u32 blob_bytes, const u32* __restrict__ 
             if (c0 == '$') { if (lev > 0) invalid = true; else dollar = true; }           // topic.rs:210
             if (!invalid && lev < tok_levels) {
                 if (len <= DICT_INLINE_MAX) { w[6] |= len << 24; tk = dict_lookup_inline(tv, w); }
-                else tk = dict_lookup_long(tv, blob + start, len);
+                else tk = dict_lookup_long<BULK ? 1 : 0>(tv, blob + start, len);
             }
         }
         if (invalid) break;
 #pragma unroll
         for (u32 k = 0; k < TOK8; ++k) if (lev == k) tw[k] = tk;
-        if (lev >= TOK8 && lev < tok_levels) tok[static_cast<size_t>(lev) * n + t] = tk;
+        if (lev >= TOK8 && lev < tok_levels) tok[static_cast<size_t>(lev) * stride + t] = tk;
         ++lev;
         if (last) break;
         ++pos;   // skip '/'
@@ -225,9 +295,10 @@ k_bucket_scan(const u32* __restrict__ hist, u32* __restrict__ cursor, u32 nbucke
 }
 
 __global__ void __launch_bounds__(256)
-k_bucket_scatter(const u32* __restrict__ bkey, u32* __restrict__ cursor, u32 n, u32* __restrict__ perm,
+k_bucket_scatter(const u32* __restrict__ bkey, u32* __restrict__ cursor, u32 n, const u32* __restrict__ hdr, u32* __restrict__ perm,
                  const u32* __restrict__ tok8, const u32* __restrict__ meta, u32* __restrict__ tok8_sorted, u32* __restrict__ meta_sorted) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hdr) n = min(n, hdr[0]);
     if (t >= n) return;
     const u32 pos = atomicAdd(cursor + bkey[t], 1u);
     perm[pos] = t;
@@ -336,7 +407,8 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
     const u32 nthreads = gridDim.x * THREADS;
     const u32 gtid = blockIdx.x * THREADS + tid;
     const TrieView& tv = p.tv;
-    const u32 ntiles = (p.n + 31) >> 5;
+    const u32 n_act = p.n_ptr ? min(p.n, *p.n_ptr) : p.n;
+    const u32 ntiles = (n_act + 31) >> 5;
     unsigned long long sV = 0, sE = 0, sF = 0, sM = 0;
     __shared__ unsigned long long s_chunk;
     __shared__ u32 s_lock;
@@ -352,7 +424,7 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
         if (tile >= ntiles) break;
 
         const u32 pos = tile * 32 + lane;              // position in the locality-sorted order
-        const bool in_range = pos < p.n;
+        const bool in_range = pos < n_act;
         const u32 t = in_range ? p.perm[pos] : 0u;     // original topic index
         const bool rows = (p.flags & MP_SORTED_ROWS) != 0;
         const u32 m = in_range ? (rows ? __ldcs(p.meta_sorted + pos) : __ldcs(p.meta + t)) : META_INVALID;

@@ -2,12 +2,12 @@
 // rmqtt/src/retain.rs:291-367) for a batch of topic filters.
 //
 // A query is a FILTER, so its work is data dependent: an exact filter touches one path, `reg/+/+/...`
-// fans out to tens of thousands of nodes.  The batch is therefore walked as ONE level-synchronous
-// breadth-first frontier over all queries: an item is (query, node, position in the filter); every
-// step kernel moves the whole frontier one tree level down.  '+' fan-out is expanded load-balanced
-// across the warp (scan + binary search by shuffle) from the node's contiguous child block; '#' is a
-// single contiguous range of the pre-order value array (retain_tree.h).  Matched values are recorded as
-// descriptors and expanded into per-query contiguous lists by k_retain_expand.
+// fans out to tens of thousands of nodes.  The batch is walked in ROUNDS of wildcard expansions: round 0 follows
+// every filter's literal prefix from the root (one thread per query); a '+' (or a '#' that cannot use the range
+// shortcut) becomes TASKS — chunks of the node's contiguous child block — that the next round's warps read
+// coalesced, one child per lane, each lane then following the filter's exact levels below its child in place.
+// '#' is normally a single contiguous range of the pre-order value array (retain_tree.h).  Matched values are
+// recorded as descriptors and expanded into per-query contiguous lists by k_retain_expand.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -16,11 +16,20 @@
 
 namespace gm {
 
-struct alignas(32) RItem { u32 q, pos, node, first_kid, nk_flags, val, val_lo, val_hi; };   // the node's record travels with the item
 struct alignas(16) RDesc { u32 q, ref, cnt, kind; };   // kind 0: the value itself, 1: rvals[ref .. ref+cnt)
 
-// Work queues (frontier, descriptor list) are split into RQ slices with one counter each: with a single bump
-// counter, the ~10^7 warp-aggregated appends of a C4 batch serialise on one L2 atomic unit.
+// A TASK = "expand the child block [kb, kb+kn) of one node for query q whose filter is at position pos":
+//   mode 1  the filter level at pos is '+'   (retain.rs:324-342): every child continues at pos+1
+//   mode 2  the filter level at pos is '#' and a literal "#" child hides somewhere below (retain.rs:343-365): every child
+//           is emitted and continues at the SAME pos, one tree level per round
+// Tasks exist only at WILDCARD levels.  Everything between two wildcards — the chain of exact (literal) levels — is
+// followed inside the thread that holds the node (one hash probe per level, nothing written): round-1's kernel moved
+// every visited node through a global queue (32 B written + 32 B re-read per visit) and needed one launch per tree level.
+struct alignas(16) RTask { u32 q, pos_mode, kb, kn; };   // pos_mode = pos | mode << 30
+constexpr u32 RTASK_CHUNK = 256;                         // child-block entries per task: large blocks are split so that warps balance
+
+// Work queues (tasks, descriptor list) are split into RQ slices with one counter each: a single bump counter serialises
+// the appends of a C4 batch on one L2 atomic unit.
 constexpr u32 RQ = 64;
 
 struct RetainParams {
@@ -33,7 +42,8 @@ struct RetainParams {
     u32* n_desc;         // [RQ]
     u32 cap_items, cap_desc;   // per SLICE
     u32* qtotal;         // [nq] matched values per query
-    u32* err;            // bit 0: frontier overflow, bit 1: descriptor overflow
+    u32* err;            // bit 0: task-queue overflow, bit 1: descriptor overflow
+    unsigned long long* stats;   // optional [2]: nodes visited, hash probes issued (diagnostics)
 };
 
 __device__ __forceinline__ u32 retain_tok(const RetainParams& p, u32 q, u32 pos) {
@@ -48,20 +58,6 @@ __device__ __forceinline__ bool retain_child(const RetainView& v, u32 node, u32 
         if (s[2] == 0) return false;
         if (s[0] == node && s[1] == token) return true;
         idx = (idx + 1) & v.edge_mask;
-    }
-}
-
-// warp-aggregated append of one element per flagged lane into slice `sq` of a sliced queue
-template <class T>
-__device__ __forceinline__ void warp_append(bool want, const T& item, T* arr, u32* counters, u32 slice_cap, u32 sq, u32* err, u32 errbit, u32 lane, u32 lt) {
-    const u32 b = __ballot_sync(0xFFFFFFFFu, want);
-    if (!b) return;
-    u32 base = 0;
-    if (lane == static_cast<u32>(__ffs(b) - 1)) base = atomicAdd(counters + sq, static_cast<u32>(__popc(b)));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(b) - 1);
-    if (want) {
-        const u32 at = base + __popc(b & lt);
-        if (at < slice_cap) arr[static_cast<size_t>(sq) * slice_cap + at] = item; else atomicOr(err, errbit);
     }
 }
 
@@ -83,107 +79,121 @@ __device__ __forceinline__ size_t queue_locate(const u32* s_pre, u32 g, u32 slic
     return static_cast<size_t>(lo) * slice_cap + (g - s_pre[lo]);
 }
 
-__global__ void k_retain_init(RetainParams p, RItem* out, u32* n_out) {
-    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 lane = threadIdx.x & 31, lt = lanemask_lt();
-    const bool ok = q < p.nq && !(p.qmeta[q] & META_INVALID);
-    warp_append(ok, RItem{q, 0u, 0u, p.v.root_first_kid, p.v.root_nk_flags, 0u, 0u, p.v.root_plain_val_hi}, out, n_out, p.cap_items, (q >> 5) % RQ, p.err, 1u, lane, lt);
+// per-lane appends (called from divergent code): one atomic on the lane's slice counter
+__device__ __forceinline__ void emit_desc(const RetainParams& p, u32 sq, u32 q, u32 ref, u32 cnt, u32 kind) {
+    atomicAdd(p.qtotal + q, cnt);
+    const u32 at = atomicAdd(p.n_desc + sq, 1u);
+    if (at < p.cap_desc) p.descs[static_cast<size_t>(sq) * p.cap_desc + at] = RDesc{q, ref, cnt, kind}; else atomicOr(p.err, 2u);
+}
+__device__ __forceinline__ void push_tasks(const RetainParams& p, RTask* out, u32* n_out, u32 sq, u32 q, u32 pos, u32 mode, u32 kb, u32 kn) {
+    const u32 nt = (kn + RTASK_CHUNK - 1) / RTASK_CHUNK;
+    if (nt == 0) return;
+    const u32 at = atomicAdd(n_out + sq, nt);
+    if (at + nt > p.cap_items) { atomicOr(p.err, 1u); return; }
+    RTask* dst = out + static_cast<size_t>(sq) * p.cap_items + at;
+    for (u32 j = 0; j < nt; ++j) dst[j] = RTask{q, pos | (mode << 30), kb + j * RTASK_CHUNK, min(RTASK_CHUNK, kn - j * RTASK_CHUNK)};
 }
 
+// The record of the node a thread currently stands on.  `mask`: 32-bit Bloom mask over the tokens of its children (it
+// travels in the spare word of the parent's child-block entry; all ones when the record came from a hash slot, which
+// has no spare word): a clear bit proves the exact child does not exist and saves the probe — after a '+' expansion
+// most children do NOT continue the filter's next literal level.
+struct RRec { u32 node, first_kid, nk_flags, val, val_lo, val_hi, mask; };
+
+// RetainTree::_matches (retain.rs:298-367) from node `r` at filter position `pos`, following exact levels in place.
+template <bool STATS>
+__device__ __forceinline__ void retain_chain(const RetainParams& p, RTask* out, u32* n_out, u32 sq, u32 q, u32 L, u32 pos, RRec r,
+                                             unsigned long long& visited, unsigned long long& probes) {
+    const RetainView& v = p.v;
+    for (;;) {
+        if (STATS) ++visited;
+        const u32 nkids = r.nk_flags & RNK_MASK, flags = r.nk_flags >> 28;
+        if (nkids == 0 || pos == L) {                                        // retain.rs:305-311
+            if (pos == L && (flags & 8u)) emit_desc(p, sq, q, r.val, 1u, 0u);
+            return;
+        }
+        const u32 tok = retain_tok(p, q, pos);
+        const bool next_hash = (pos + 1 < L) && retain_tok(p, q, pos + 1) == TOK_HASH;
+        // precise matching first — Level equality, so a stored literal "+" / "#" child shadows the wildcard
+        // expansion (retain.rs:313)
+        const bool exact_try = tok >= TOK_BLANK || (tok == TOK_PLUS && (flags & RF_LIT_PLUS)) || (tok == TOK_HASH && (flags & RF_LIT_HASH));
+        u32 c[8];
+        bool found = false;
+        if (exact_try && (r.mask & retain_mask_bit(tok))) { if (STATS) ++probes; found = retain_child(v, r.node, tok, c); }
+        if (found) {
+            if (next_hash && ((c[4] >> 28) & 8u)) emit_desc(p, sq, q, c[5], 1u, 0u);   // '#' matches the parent, retain.rs:317-322
+            r = RRec{c[2], c[3], c[4], c[5], c[6], c[7], 0xFFFFFFFFu};
+            ++pos;
+            continue;
+        }
+        const bool root = r.node == 0;
+        if (tok == TOK_PLUS) {                                               // retain.rs:324-342
+            push_tasks(p, out, n_out, sq, q, pos, 1u, r.first_kid, root ? v.root_plain_kids : nkids);
+        } else if (tok == TOK_HASH) {                                        // retain.rs:343-365
+            if (!(flags & RF_SUB_LIT_HASH)) {       // every strict descendant (minus `$` subtrees at the root): one range
+                const u32 lo = r.val_lo + ((flags & 8u) ? 1u : 0u), hi = root ? v.root_plain_val_hi : r.val_hi;
+                if (hi > lo) emit_desc(p, sq, q, lo, hi - lo, 1u);
+            } else push_tasks(p, out, n_out, sq, q, pos, 2u, r.first_kid, root ? v.root_plain_kids : nkids);
+        }
+        return;
+    }
+}
+
+// round 0: one thread per query walks the literal prefix of its filter from the root
+template <bool STATS>
 __global__ void __launch_bounds__(256)
-k_retain_step(RetainParams p, const RItem* __restrict__ in, const u32* __restrict__ n_in_p, RItem* __restrict__ out, u32* n_out) {
-    const u32 lane = threadIdx.x & 31, lt = lanemask_lt();
+k_retain_init(RetainParams p, RTask* out, u32* n_out) {
+    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long visited = 0, probes = 0;
+    if (q < p.nq) {
+        const u32 m = p.qmeta[q];
+        if (!(m & META_INVALID))
+            retain_chain<STATS>(p, out, n_out, (q >> 5) % RQ, q, m & META_NLEV_MASK, 0u,
+                                RRec{0u, p.v.root_first_kid, p.v.root_nk_flags, 0u, 0u, p.v.root_plain_val_hi, 0xFFFFFFFFu}, visited, probes);
+    }
+    if (STATS && (visited | probes)) { atomicAdd(p.stats, visited); atomicAdd(p.stats + 1, probes); }
+}
+
+// round r >= 1: one warp per task; the child block is read coalesced (32 entries = 1 KB per step), every lane takes one
+// child and follows the filter's exact levels below it
+template <bool STATS>
+__global__ void __launch_bounds__(256)
+k_retain_round(RetainParams p, const RTask* __restrict__ in, const u32* __restrict__ n_in_p, RTask* __restrict__ out, u32* n_out) {
+    const u32 lane = threadIdx.x & 31;
     const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const RetainView& v = p.v;
     __shared__ u32 s_pre[RQ + 1];
     const u32 n_in = queue_prefix(n_in_p, p.cap_items, s_pre);
     const u32 sq = gwarp % RQ;                        // this warp appends to its own slice
-    for (u32 base = gwarp * 32; base < n_in; base += nwarps * 32) {
-        const u32 i = base + lane;
-        const bool have = i < n_in;
-        RItem it{};
-        if (have) { u32 w[8]; ld256(in + queue_locate(s_pre, i, p.cap_items), w); it = RItem{w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]}; }
-        u32 exp_kb = 0, exp_n = 0, exp_mode = 0;      // child-block expansion request: 1 = '+', 2 = '#' level by level
-        bool push1 = false, emit1 = false, next_hash = false;
-        RItem pitem{};
-        RDesc d1{};
-        u32 L = 0;
-        if (have) {
-            L = p.qmeta[it.q] & META_NLEV_MASK;
-            const u32 nkids = it.nk_flags & RNK_MASK, flags = it.nk_flags >> 28;
-            if (nkids == 0 || it.pos == L) {                                     // retain.rs:305-311
-                if (it.pos == L && (flags & 8u)) { emit1 = true; d1 = RDesc{it.q, it.val, 1u, 0u}; }
-            } else {
-                const u32 tok = retain_tok(p, it.q, it.pos);
-                next_hash = (it.pos + 1 < L) && retain_tok(p, it.q, it.pos + 1) == TOK_HASH;
-                // precise matching first — Level equality, so a stored literal "+" / "#" child shadows the
-                // wildcard expansion (retain.rs:313)
-                const bool exact_try = tok >= TOK_BLANK || (tok == TOK_PLUS && (flags & RF_LIT_PLUS)) || (tok == TOK_HASH && (flags & RF_LIT_HASH));
-                u32 c[8];
-                const bool found = exact_try && retain_child(v, it.node, tok, c);
-                const bool root = it.node == 0;
-                if (found) {
-                    if (next_hash && ((c[4] >> 28) & 8u)) { emit1 = true; d1 = RDesc{it.q, c[5], 1u, 0u}; }   // '#' matches the parent, retain.rs:317-322
-                    push1 = true; pitem = RItem{it.q, it.pos + 1, c[2], c[3], c[4], c[5], c[6], c[7]};
-                } else if (tok == TOK_PLUS) {                                    // retain.rs:324-342
-                    exp_kb = it.first_kid; exp_n = root ? v.root_plain_kids : nkids; exp_mode = 1;
-                } else if (tok == TOK_HASH) {                                    // retain.rs:343-365
-                    if (!(flags & RF_SUB_LIT_HASH)) {       // every strict descendant (minus `$` subtrees at the root): one range
-                        const u32 lo = it.val_lo + ((flags & 8u) ? 1u : 0u), hi = root ? v.root_plain_val_hi : it.val_hi;
-                        if (hi > lo) { emit1 = true; d1 = RDesc{it.q, lo, hi - lo, 1u}; }
-                    } else {
-                        exp_kb = it.first_kid; exp_n = root ? v.root_plain_kids : nkids; exp_mode = 2;
-                    }
+    unsigned long long visited = 0, probes = 0;
+    for (u32 ti = gwarp; ti < n_in; ti += nwarps) {
+        const uint4 tw = *reinterpret_cast<const uint4*>(in + queue_locate(s_pre, ti, p.cap_items));
+        const u32 q = tw.x, pos = tw.y & 0x3FFFFFFFu, mode = tw.y >> 30, kb = tw.z, kn = tw.w;
+        const u32 L = p.qmeta[q] & META_NLEV_MASK;
+        const bool next_hash = mode == 1u && (pos + 1 < L) && retain_tok(p, q, pos + 1) == TOK_HASH;
+        for (u32 e = lane; e < kn; e += 32) {
+            u32 kd[8];                                              // {token, child, first_kid, nk_flags, val, val_lo, val_hi, child-token mask}
+            ld256(v.kids + kb + e, kd);
+            if (STATS) ++visited;
+            const bool has_val = ((kd[3] >> 28) & 8u) != 0;
+            const u32 kkids = kd[3] & RNK_MASK;
+            const RRec r{kd[1], kd[2], kd[3], kd[4], kd[5], kd[6], kd[7]};
+            if (mode == 1u) {
+                if (pos + 1 == L) { if (has_val) emit_desc(p, sq, q, kd[4], 1u, 0u); }   // filter ends here: the child's own value
+                else {
+                    if (next_hash && has_val) emit_desc(p, sq, q, kd[4], 1u, 0u);        // `.../+/#` parent match
+                    if (kkids) retain_chain<STATS>(p, out, n_out, sq, q, L, pos + 1, r, visited, probes);
                 }
+            } else {                                                // '#' one level at a time (a literal "#" child hides below)
+                if (has_val) emit_desc(p, sq, q, kd[4], 1u, 0u);
+                if (kkids) retain_chain<STATS>(p, out, n_out, sq, q, L, pos, r, visited, probes);
             }
         }
-        if (emit1) atomicAdd(p.qtotal + d1.q, d1.cnt);
-        warp_append(emit1, d1, p.descs, p.n_desc, p.cap_desc, sq, p.err, 2u, lane, lt);
-        warp_append(push1, pitem, out, n_out, p.cap_items, sq, p.err, 1u, lane, lt);
-
-        // ---- load-balanced expansion of the requested child blocks
-        u32 sc = exp_n;
+    }
+    if (STATS) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xFFFFFFFFu, sc, o); if (lane >= o) sc += x; }
-        const u32 tot = __shfl_sync(0xFFFFFFFFu, sc, 31);
-        const u32 exc = sc - exp_n;
-        for (u32 e0 = 0; e0 < tot; e0 += 32) {
-            const u32 e = e0 + lane;
-            u32 lo = 0;
-#pragma unroll
-            for (int step = 16; step; step >>= 1) {
-                u32 x = __shfl_sync(0xFFFFFFFFu, exc, lo + step);
-                if (x <= e) lo += step;
-            }
-            const u32 o_exc = __shfl_sync(0xFFFFFFFFu, exc, lo);
-            const u32 o_kb = __shfl_sync(0xFFFFFFFFu, exp_kb, lo);
-            const u32 o_mode = __shfl_sync(0xFFFFFFFFu, exp_mode, lo);
-            const u32 o_q = __shfl_sync(0xFFFFFFFFu, it.q, lo);
-            const u32 o_pos = __shfl_sync(0xFFFFFFFFu, it.pos, lo);
-            const u32 o_L = __shfl_sync(0xFFFFFFFFu, L, lo);
-            const bool o_nh = __shfl_sync(0xFFFFFFFFu, next_hash ? 1u : 0u, lo) != 0;
-            bool em = false, pu = false;
-            RDesc d{};
-            RItem ni{};
-            if (e < tot) {
-                u32 kd[8];                                              // {token, child, first_kid, nk_flags, val, val_lo, val_hi, pad}
-                ld256(v.kids + o_kb + (e - o_exc), kd);
-                const bool has_val = ((kd[3] >> 28) & 8u) != 0;
-                const u32 kn = kd[3] & RNK_MASK;
-                if (o_mode == 1) {
-                    if (o_pos + 1 == o_L) em = has_val;                 // filter ends here: the child's own value
-                    else { em = o_nh && has_val; pu = kn > 0; }         // `.../+/#` parent match; descend only if the child has branches
-                    ni = RItem{o_q, o_pos + 1, kd[1], kd[2], kd[3], kd[4], kd[5], kd[6]};
-                } else {                                                // '#' one level at a time (a literal "#" child hides below)
-                    em = has_val; pu = kn > 0;
-                    ni = RItem{o_q, o_pos, kd[1], kd[2], kd[3], kd[4], kd[5], kd[6]};
-                }
-                d = RDesc{o_q, kd[4], 1u, 0u};
-            }
-            if (em) atomicAdd(p.qtotal + d.q, 1u);
-            warp_append(em, d, p.descs, p.n_desc, p.cap_desc, sq, p.err, 2u, lane, lt);
-            warp_append(pu, ni, out, n_out, p.cap_items, sq, p.err, 1u, lane, lt);
-        }
+        for (int o = 16; o; o >>= 1) { visited += __shfl_xor_sync(0xFFFFFFFFu, visited, o); probes += __shfl_xor_sync(0xFFFFFFFFu, probes, o); }
+        if (lane == 0 && (visited | probes)) { atomicAdd(p.stats, visited); atomicAdd(p.stats + 1, probes); }
     }
 }
 

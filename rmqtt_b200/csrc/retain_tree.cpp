@@ -107,7 +107,7 @@ void RetainTreeHost::write_record(u32 dev) {
     for (u32 j = 0; j < p.nkids; ++j) {
         RKid& k = rkids[p.first_kid + j];
         if (k.child != dev) continue;
-        k.first_kid = r.first_kid; k.nk_flags = r.nkids | (r.flags << 28); k.val = r.val; k.val_lo = r.val_lo; k.val_hi = r.val_hi;
+        k.first_kid = r.first_kid; k.nk_flags = r.nkids | (r.flags << 28); k.val = r.val; k.val_lo = r.val_lo; k.val_hi = r.val_hi; k.pad = r.pad;
         dirty_kids.push_back(p.first_kid + j);
         break;
     }
@@ -160,9 +160,10 @@ bool RetainTreeHost::dev_add_child(u32 pdev, u32 tok, u32 cdev) {
         if (root_plain_kids < p.nkids) { rkids[idx] = rkids[p.first_kid + root_plain_kids]; dirty_kids.push_back(idx); idx = p.first_kid + root_plain_kids; }
         root_plain_kids++;
     }
-    rkids[idx] = RKid{tok, cdev, c.first_kid, c.nkids | (c.flags << 28), c.val, c.val_lo, c.val_hi, 0};
+    rkids[idx] = RKid{tok, cdev, c.first_kid, c.nkids | (c.flags << 28), c.val, c.val_lo, c.val_hi, c.pad};
     dirty_kids.push_back(idx);
     p.nkids++;
+    p.pad |= retain_mask_bit(tok);
     const u32 mask = static_cast<u32>(redges.size() - 1);
     u32 s = redge_hash(pdev, tok) & mask;
     while (redges[s].child != 0) s = (s + 1) & mask;
@@ -272,6 +273,7 @@ void RetainTreeHost::flatten() {
         r.flags = h.has_val ? 8u : 0u;
         const Kids* order = host == 0 ? &root_order : &h.kids;       // no per-node copy: the host tree is not touched while flattening
         for (const auto& kv : *order) {
+            r.pad |= retain_mask_bit(kv.first);
             if (kv.first == TOK_PLUS) r.flags |= RF_LIT_PLUS;
             if (kv.first == TOK_HASH) r.flags |= RF_LIT_HASH | RF_SUB_LIT_HASH;
         }
@@ -314,7 +316,7 @@ void RetainTreeHost::flatten() {
     // child entries carry the complete record of the child (flags and value ranges are final only now)
     for (RKid& k : rkids) {
         const RNode& c = rnodes[k.child];
-        k.first_kid = c.first_kid; k.nk_flags = c.nkids | (c.flags << 28); k.val = c.val; k.val_lo = c.val_lo; k.val_hi = c.val_hi; k.pad = 0;
+        k.first_kid = c.first_kid; k.nk_flags = c.nkids | (c.flags << 28); k.val = c.val; k.val_lo = c.val_lo; k.val_hi = c.val_hi; k.pad = c.pad;
     }
     // exact-step hash table, load <= 0.25
     size_t cap = 1024;

@@ -43,13 +43,13 @@ struct alignas(32) RNode {
     u32 val_lo, val_hi;   // rvals[val_lo .. val_hi) = values of the subtree [n, sub_end) (own value first)
     u32 flags;
     u32 sub_end;
-    u32 pad;
+    u32 pad;              // Bloom mask over the tokens of this node's children (retain_mask_bit); stale bits after removals are harmless
 };
 // A node's record as the walk needs it: {first_kid, nk_flags, val, val_lo, val_hi} where nk_flags = #kids (28 bits) |
 // flags << 28 (RF_* and 8 = has value).  It travels WITH the reference to the node — inside the parent's child
 // block entry and inside the (parent, token) hash slot — so visiting a node costs no extra memory access.
 constexpr u32 RNK_MASK = 0x0FFFFFFFu;
-struct alignas(32) RKid { u32 token, child, first_kid, nk_flags, val, val_lo, val_hi, pad; };
+struct alignas(32) RKid { u32 token, child, first_kid, nk_flags, val, val_lo, val_hi, pad; };   // pad = the child's child-token mask
 struct alignas(32) REdge { u32 parent, token, child, first_kid, nk_flags, val, val_lo, val_hi; };   // child == 0: empty (root is node 0)
 
 struct RetainView {
@@ -63,6 +63,8 @@ struct RetainView {
     u32 max_depth;
 };
 
+// one of 32 bits for a child token: the Bloom mask over a node's children kept in RNode::pad / RKid::pad
+GM_HD u32 retain_mask_bit(u32 token) { return 1u << ((token * 0x9E3779B1u) >> 27); }
 GM_HD u32 redge_hash(u32 parent, u32 token) { return fmix32(parent * 0x85EBCA77u + (token ^ 0x2545F491u) * 0x9E3779B1u); }
 
 class RetainTreeHost {
