@@ -525,6 +525,8 @@ def run_own(args):
     # ---- CPU baseline: the oracle's DefaultRouter::_matches restatement on the host cores -----------
     cpu = None
     c4 = None
+    latency = None
+    churn = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         threads = orc.hardware_threads()
@@ -547,7 +549,51 @@ def run_own(args):
                          f"(oracle/oracle.cpp; the Rust reference cannot be built here: no cargo); reader threads pinned one per allowed CPU, "
                          f"tree pages interleaved over NUMA nodes, work handed out in chunks",
                "best_rep": max(runs), "worst_rep": min(runs), "single_thread_value": 20000 / one["seconds"]}
+        # the port's write-lock path: Router::remove + Router::add of existing subscriptions, one thread
+        nch = min(200_000, len(sv2))
+        port_churn_ops = 2 * nch / router.churn(sb, so, sv2[:nch])
         del router
+        # ---- churn: subscribe / unsubscribe load from a second thread while this thread keeps matching (device buffers) ----
+        churn = {"filters_cycled": nch, "port_single_thread_ops_per_s": port_churn_ops, "legs": [],
+                 "how": "gm_churn_probe in its own thread: remove + re-add of existing subscriptions at the target rate, gm_flush every 1 ms "
+                        "(asynchronous: patches are scattered on a side stream between match kernels; a re-hash goes to a second table + pointer swap); "
+                        "the bench thread runs the device-resident match loop meanwhile (auto-flush engine)"}
+        ch_steps = 1200
+        for label, rate in (("no churn", None), ("1%/s", 0.01 * cfg.n_subs), ("10%/s", 0.10 * cfg.n_subs), ("unthrottled", 0.0)):
+            out = N.GmChurn()
+            rcbox = []
+            th = None
+            if rate is not None:
+                th = threading.Thread(target=lambda: rcbox.append(lib.gm_churn_probe(eng._h, sb.ctypes.data, so.ctypes.data, sv2.ctypes.data, nch, float(rate), 1500, 1000, C.byref(out))))
+                th.start()
+                time.sleep(0.15)
+            ms_c = timed_device_loop(step, ch_steps, 3)
+            if th:
+                th.join()
+                assert rcbox == [0], lib.gm_last_error(eng._h)
+            d = out.as_dict()
+            churn["legs"].append({"churn": label, "target_ops_per_s": rate, "match_topics_per_s": n * ch_steps / (ms_c / 1e3),
+                                  "mutation_ops_per_s": d["ops_per_s"], "flushes_per_s": d["flushes_per_s"], "mean_flush_us": d["mean_flush_us"], "max_flush_us": d["max_flush_us"]})
+        base = churn["legs"][0]["match_topics_per_s"]
+        for leg in churn["legs"]:
+            leg["match_throughput_vs_no_churn"] = leg["match_topics_per_s"] / base
+        del sb, so
+        # ---- per-PUBLISH latency through the single-call front end (gm_submit -> batcher -> small-batch graph / pipelined path)
+        lat = N.GmLatency()
+        hb0, ho0 = host_batches[0]
+        table = []
+        for burst, rounds in ((1, 2000), (32, 400), (1024, 60), (32768, 12), (n, 4)):
+            burst = min(burst, n)
+            rc = lib.gm_batcher_probe(eng._h, hb0.ctypes.data, ho0.ctypes.data, n, burst, rounds, 0, C.byref(lat))
+            assert rc == 0, lib.gm_last_error(eng._h)
+            d = lat.as_dict()
+            table.append({"offered_burst": burst, "p50_us": d["p50_us"], "p99_us": d["p99_us"], "mean_us": d["mean_us"], "topics_per_s": d["topics_per_s"], "samples": d["samples"]})
+        cpu_lat_us = 1e6 / cpu["single_thread_value"]
+        cross = next((r["offered_burst"] for r in table if r["topics_per_s"] > cpu["single_thread_value"]), None)
+        latency = {"front_end": "gm_submit (MPSC queue) -> 2 dispatcher threads -> gm_match_batch; bursts <= 2048 topics run as ONE CUDA-graph launch; "
+                                "closed loop: the next burst is offered when every callback of the previous one has run; max_wait_us = 0",
+                   "table": table, "cpu_port_single_thread_us_per_publish": cpu_lat_us,
+                   "crossover": f"one CPU thread answers a PUBLISH in {cpu_lat_us:.1f} us; the GPU front end's throughput passes one CPU thread at an offered burst of {cross} topics"}
         if not args.no_c4:
             c4 = _c4_leg(torch, dev, stream, peak, small)
 
@@ -568,6 +614,8 @@ def run_own(args):
         "multi_gpu": multi,
         "parity_check": parity,
         "c4": c4,
+        "latency": latency,
+        "churn": churn,
         "clocks": clocks,
     }
     if multi and "value_with_gather" in multi:

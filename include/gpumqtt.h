@@ -218,6 +218,38 @@ int32_t gmr_matches_batch(gm_router* r, const gm_id* publishers, const char* top
                           uint64_t* needed_rels, uint64_t* needed_sub_ids, int32_t* status);
 int32_t gmr_relation(gm_router* r, uint32_t handle, const char** filter, uint32_t* filter_len, const char** client, uint32_t* client_len);
 
+/* ---- single-call front end: Router::matches is called once per PUBLISH from many tokio workers (rmqtt/src/router.rs:482-484,
+ *      caller rmqtt/src/shared.rs:601-636).  The batcher turns single submissions into device batches: a mutex-protected
+ *      MPSC queue, a size / time window, `dispatchers` threads so that one batch is collected while others are on the device
+ *      (the engine keeps several batches in flight and serves small ones as ONE CUDA-graph launch).  Completion is a
+ *      callback per topic, from a dispatcher thread — a Rust caller completes a oneshot / writes an eventfd there.            */
+typedef struct gm_batcher gm_batcher;
+typedef void (*gm_match_cb)(void* user, uint64_t cookie, int32_t status, const uint32_t* ids, uint32_t n_ids);   /* ids valid during the call only */
+typedef struct gm_batcher_config {
+    uint32_t struct_size;      /* = sizeof(gm_batcher_config) */
+    uint32_t max_batch;        /* dispatch when this many topics are queued (0 = default 4096) */
+    uint32_t max_wait_us;      /* ... or when the oldest queued topic has waited this long */
+    uint32_t dispatchers;      /* dispatch threads = batches in flight (0 = default 2) */
+    gm_match_cb on_match;
+    void* user;
+} gm_batcher_config;
+int32_t gm_batcher_create(gm_engine* e, const gm_batcher_config* cfg, gm_batcher** out);
+int32_t gm_submit(gm_batcher* b, const char* topic, uint32_t len, uint64_t cookie);   /* thread-safe; never waits for the device */
+int32_t gm_batcher_drain(gm_batcher* b);                                              /* everything submitted so far has been delivered */
+void gm_batcher_destroy(gm_batcher* b);
+/* Closed-loop latency probe of that front end: `rounds` times, submit `burst` topics (taken cyclically from the packed batch)
+ * one by one, wait until all their callbacks ran; per-topic latency = callback time - submit time.                             */
+typedef struct gm_latency { double p50_us, p99_us, mean_us, max_us, topics_per_s, ids_per_topic; uint64_t samples; } gm_latency;
+int32_t gm_batcher_probe(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, uint32_t burst, uint32_t rounds,
+                         uint32_t max_wait_us, gm_latency* out);
+
+/* Churn probe: remove + re-add the given (filter, value) pairs cyclically from the calling thread at `target_ops_per_s`
+ * (0 = unthrottled) for `duration_ms`, with a gm_flush every `flush_period_us` (0 = leave it to the matches' auto-flush).
+ * Run it in its own thread next to matching threads to measure mutation throughput and what it costs the matches.         */
+typedef struct gm_churn { double seconds, ops_per_s, flushes_per_s, mean_flush_us, max_flush_us; uint64_t ops, flushes; } gm_churn;
+int32_t gm_churn_probe(gm_engine* e, const char* blob, const uint32_t* offsets, const uint32_t* values, uint64_t n,
+                       double target_ops_per_s, uint32_t duration_ms, uint32_t flush_period_us, gm_churn* out);
+
 /* ---- multi-GPU (BASELINE.json C5): one engine per GPU / process holds the filters of its root-hash shard
  *      (gm_shard_of; root-wildcard filters are replicated).  The host layer distributes the communicator id (in rmqtt: the
  *      cluster layer, rmqtt-plugins/rmqtt-cluster-raft; here torch.distributed or any channel).  libnccl is bound with

@@ -669,6 +669,20 @@ int64_t orc_router_bulk_add(void* rp, const char* blob, const uint32_t* offs, co
     }
     return total;
 }
+// Router::remove then Router::add of the same subscription (the pairs orc_router_bulk_add created), one thread — the
+// reference's write-lock path (router.rs:417-479).  Returns seconds for n pairs (2n operations).
+double orc_router_churn(void* rp, const char* blob, const uint32_t* offs, const uint32_t* vals, uint64_t n) {
+    Router* r = static_cast<Router*>(rp);
+    char cid[32];
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t i = 0; i < n; ++i) {
+        std::string_view f(blob + offs[i], offs[i + 1] - offs[i]);
+        int cl = snprintf(cid, sizeof cid, "c%u", vals[i]);
+        r->remove(f, std::string_view(cid, cl), vals[i]);
+        r->add(f, std::string_view(cid, cl), vals[i], vals[i]);
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 int64_t orc_router_match(void* r, const char* s, uint32_t len, uint32_t* out, uint64_t cap, orc_counters* ctr) {
     std::vector<uint32_t> v; Counters c;
     if (!static_cast<Router*>(r)->matches(std::string_view(s, len), v, c)) return -1;

@@ -77,6 +77,7 @@ def lib():
         "orc_retain_match_batch": (C.c_double, [vp, vp, vp, u64, C.c_int, vp, vp, vp, P(Counters)]),
         "orc_hardware_threads": (i32, []),
         "orc_numa_interleave": (i32, [i32]),
+        "orc_router_churn": (C.c_double, [vp, vp, vp, vp, u64]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -260,6 +261,10 @@ class Router:
             if n <= cap:
                 return sorted(out[i] for i in range(n))
             cap = int(n)
+
+    def churn(self, blob, offs, vals) -> float:
+        """remove + re-add every listed subscription (single thread, the write-lock path); returns seconds."""
+        return float(lib().orc_router_churn(self._h, _ptr(blob), _ptr(offs), _ptr(vals), len(vals)))
 
     def match_batch(self, blob, offs, nthreads: int = 1):
         n = len(offs) - 1

@@ -69,6 +69,28 @@ class GmMatchArgs(C.Structure):
                 ("stream", C.c_void_p), ("work", C.POINTER(GmWork))]
 
 
+class GmLatency(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("p50_us", "p99_us", "mean_us", "max_us", "topics_per_s", "ids_per_topic")] + [("samples", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: float(getattr(self, n)) for n, _ in self._fields_[:-1]} | {"samples": int(self.samples)}
+
+
+class GmChurn(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("seconds", "ops_per_s", "flushes_per_s", "mean_flush_us", "max_flush_us")] + [("ops", C.c_uint64), ("flushes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: (float(getattr(self, n)) if t is C.c_double else int(getattr(self, n))) for n, t in self._fields_}
+
+
+GM_MATCH_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32), C.c_uint32)
+
+
+class GmBatcherConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32), ("dispatchers", C.c_uint32),
+                ("on_match", GM_MATCH_CB), ("user", C.c_void_p)]
+
+
 class GmValues(C.Structure):
     _fields_ = [("values", C.c_void_p), ("n_values", C.c_uint64), ("ranges", C.c_void_p), ("n_ranges", C.c_uint64), ("epoch", C.c_uint64)]
 
@@ -93,6 +115,12 @@ SIGNATURES = {
     "gm_match_batch_desc": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
     "gm_values_view": (_i32, [_vp, _P(GmValues)]),
     "gm_desc_expand": (_i32, [_vp, _vp, _u64, _vp, _u64, _P(_u64)]),
+    "gm_batcher_create": (_i32, [_vp, _P(GmBatcherConfig), _P(_vp)]),
+    "gm_submit": (_i32, [_vp, _cp, _u32, _u64]),
+    "gm_batcher_drain": (_i32, [_vp]),
+    "gm_batcher_destroy": (None, [_vp]),
+    "gm_batcher_probe": (_i32, [_vp, _vp, _vp, _u64, _u32, _u32, _u32, _P(GmLatency)]),
+    "gm_churn_probe": (_i32, [_vp, _vp, _vp, _vp, _u64, C.c_double, _u32, _u32, _P(GmChurn)]),
     "gm_comm_unique_id": (_i32, [_vp]),
     "gm_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
     "gm_comm_destroy": (_i32, [_vp]),

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -162,7 +163,7 @@ struct gm_engine {
     DevBuf d_comm, d_part;
     unsigned long long* h_comm = nullptr;   // pinned [2 * world + 64]
     // tuning / diagnostics knobs, read from the environment once at creation
-    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 131072; bool small_graphs = true; } knobs;
+    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 131072; bool small_graphs = true; bool retain_stats = false; } knobs;
     void read_knobs() {
         if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { knobs.site_bits = a; knobs.sub_bits = b; } }
         if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
@@ -526,11 +527,13 @@ struct gm_engine {
         // queued.  A task descends at least one tree level, so depth + 1 rounds drain every queue (late rounds find
         // theirs empty and return at once).
         rp.stats = ctl->stats;
-        k_retain_init<false><<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RTask>(), &ctl->counts[0]);
+        auto kri = knobs.retain_stats ? k_retain_init<true> : k_retain_init<false>;
+        auto krr = knobs.retain_stats ? k_retain_round<true> : k_retain_round<false>;
+        kri<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RTask>(), &ctl->counts[0]);
         const int grid = num_sms * 8;
         for (u32 lvl = 0; lvl <= depth; ++lvl)
-            k_retain_round<false><<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RTask>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RTask>(),
-                                                       &ctl->counts[static_cast<size_t>(lvl + 1) * RQ]);
+            krr<<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RTask>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RTask>(),
+                                     &ctl->counts[static_cast<size_t>(lvl + 1) * RQ]);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[2], s));
         k_retain_scan<<<1, 1024, 0, s>>>(qtotal, nq, qbase, reinterpret_cast<uint2*>(d_spans_), &ctl->grand);
@@ -552,6 +555,15 @@ struct gm_engine {
             RCtl h{};
             CUDA_TRY(cudaMemcpyAsync(&h, d_rctl.p, sizeof(RCtl), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
+            if (h.err == 0 && knobs.retain_stats) {      // diagnostics: work counters of the instrumented kernels + tasks per round
+                const u32 depth = dev_rview.max_depth;
+                std::vector<u32> cnt(static_cast<size_t>(depth + 3) * RQ);
+                CUDA_TRY(cudaMemcpy(cnt.data(), static_cast<char*>(d_rctl.p) + offsetof(RCtl, counts), cnt.size() * sizeof(u32), cudaMemcpyDeviceToHost));
+                fprintf(stderr, "retain stats: visited %llu probes %llu hits %llu; tasks per round:", h.stats[0], h.stats[1], h.grand);
+                for (u32 l = 0; l <= depth + 1; ++l) { unsigned long long t = 0; for (u32 k = 0; k < RQ; ++k) t += cnt[static_cast<size_t>(l) * RQ + k]; fprintf(stderr, " %llu", t); }
+                unsigned long long nd = 0; for (u32 k = 0; k < RQ; ++k) nd += h.n_desc[k];
+                fprintf(stderr, "; descriptors %llu\n", nd);
+            }
             if (h.err == 0) { *total = h.grand; return GM_OK; }
             if (h.err & 1u) { if (r_cap_items > (1u << 30)) break; r_cap_items *= 4; }
             if (h.err & 2u) { if (r_cap_desc > (1u << 30)) break; r_cap_desc *= 4; }
@@ -1361,6 +1373,7 @@ int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value) {
     else if (k == "diag_flags") e->knobs.diag_flags = static_cast<u32>(value);
     else if (k == "tok_bulk") e->knobs.tok_bulk = value != 0;
     else if (k == "small_graphs") e->knobs.small_graphs = value != 0;
+    else if (k == "retain_stats") e->knobs.retain_stats = value != 0;
     else if (k == "e2e_chunk" && value >= 1024) e->knobs.e2e_chunk = static_cast<u32>(value);
     else return GM_ERR_INVALID_ARG;
     return GM_OK;
