@@ -172,6 +172,11 @@ int32_t gm_retain_set(gm_engine* e, const char* topic, uint32_t len, uint32_t va
 int32_t gm_retain_remove(gm_engine* e, const char* topic, uint32_t len, int32_t* had_old, uint32_t* old_value);
 int32_t gm_retain_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets /* n+1 */, const uint32_t* values,
                             uint64_t n, uint64_t* n_set);
+/* Batch removal under ONE lock acquisition — the expiry sweep (remove_expired_messages / RetainTree::retain,
+ * rmqtt/src/retain.rs:118-128, 261-288: the host decides which retained topics expired).  old_values (optional, [n]) receives
+ * the removed handle or 0xFFFFFFFF where nothing was stored; invalid topics are skipped.                                        */
+int32_t gm_retain_remove_batch(gm_engine* e, const char* blob, const uint32_t* offsets /* n+1 */, uint64_t n, uint32_t* old_values,
+                               uint64_t* n_removed);
 /* RetainStorage::get (rmqtt/src/retain.rs:152-169 -> RetainTree::matches :291-367) for a batch of SUBSCRIBE topic
  * FILTERS: out_spans[i] locates the handles of the retained messages filter i matches (order unspecified).
  * Same capacity / status protocol as gm_match_batch.                                                          */
@@ -235,6 +240,12 @@ typedef struct gm_batcher_config {
 } gm_batcher_config;
 int32_t gm_batcher_create(gm_engine* e, const gm_batcher_config* cfg, gm_batcher** out);
 int32_t gm_submit(gm_batcher* b, const char* topic, uint32_t len, uint64_t cookie);   /* thread-safe; never waits for the device */
+/* Wire-side batching: the topic name of a raw MQTT PUBLISH packet, zero-copy (*topic points into `packet`).
+ * v3.1.1 and v5 share the layout — fixed header, remaining-length varint, u16-BE-prefixed topic (rmqtt-codec/src/v3/decode.rs:103-104,
+ * rmqtt-codec/src/v5/packet/publish.rs:27-28).  gm_submit_publish feeds it to the batcher: the decoded topic bytes are the only
+ * thing copied between the socket buffer and the device batch.  GM_ERR_INVALID_ARG: not a PUBLISH / malformed.                  */
+int32_t gm_publish_topic(const uint8_t* packet, uint32_t len, const char** topic, uint32_t* topic_len);
+int32_t gm_submit_publish(gm_batcher* b, const uint8_t* packet, uint32_t len, uint64_t cookie);
 int32_t gm_batcher_drain(gm_batcher* b);                                              /* everything submitted so far has been delivered */
 void gm_batcher_destroy(gm_batcher* b);
 /* Closed-loop latency probe of that front end: `rounds` times, submit `burst` topics (taken cyclically from the packed batch)

@@ -117,6 +117,8 @@ SIGNATURES = {
     "gm_desc_expand": (_i32, [_vp, _vp, _u64, _vp, _u64, _P(_u64)]),
     "gm_batcher_create": (_i32, [_vp, _P(GmBatcherConfig), _P(_vp)]),
     "gm_submit": (_i32, [_vp, _cp, _u32, _u64]),
+    "gm_publish_topic": (_i32, [_vp, _u32, _P(_cp), _P(_u32)]),
+    "gm_submit_publish": (_i32, [_vp, _vp, _u32, _u64]),
     "gm_batcher_drain": (_i32, [_vp]),
     "gm_batcher_destroy": (None, [_vp]),
     "gm_batcher_probe": (_i32, [_vp, _vp, _vp, _u64, _u32, _u32, _u32, _P(GmLatency)]),
@@ -128,6 +130,7 @@ SIGNATURES = {
     "gm_allgatherv_device": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
     "gm_retain_set": (_i32, [_vp, _cp, _u32, _u32, _P(_i32), _P(_u32)]),
     "gm_retain_remove": (_i32, [_vp, _cp, _u32, _P(_i32), _P(_u32)]),
+    "gm_retain_remove_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _P(_u64)]),
     "gm_retain_bulk_load": (_i32, [_vp, _vp, _vp, _vp, _u64, _P(_u64)]),
     "gm_retain_match_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
     "gm_retain_match_batch_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp, _vp]),

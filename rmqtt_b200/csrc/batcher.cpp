@@ -130,6 +130,38 @@ int32_t gm_submit(gm_batcher* b, const char* topic, uint32_t len, uint64_t cooki
     return GM_OK;
 }
 
+// ---- wire-side batching: the topic of a raw PUBLISH packet goes straight into the batch ----------------
+// MQTT 3.1.1 and 5 share the layout: fixed header (type 3 << 4 | flags), remaining-length varint (<= 4 bytes), then the
+// topic name as a u16-big-endian-prefixed string — the first field both decoders read
+// (rmqtt-codec/src/v3/decode.rs:103-104, rmqtt-codec/src/v5/packet/publish.rs:27-28; varint: rmqtt-codec/src/utils.rs:142-155).
+int32_t gm_publish_topic(const uint8_t* packet, uint32_t len, const char** topic, uint32_t* topic_len) {
+    if (!packet || !topic || !topic_len || len < 2) return GM_ERR_INVALID_ARG;
+    if ((packet[0] >> 4) != 3) return GM_ERR_INVALID_ARG;                 // not a PUBLISH
+    uint32_t pos = 1, rem = 0, shift = 0;
+    for (;;) {
+        if (pos >= len) return GM_ERR_INVALID_ARG;                        // MalformedPacket
+        const uint8_t v = packet[pos++];
+        rem += static_cast<uint32_t>(v & 0x7F) << shift;
+        if (!(v & 0x80)) break;
+        if (shift >= 21) return GM_ERR_INVALID_ARG;                       // InvalidLength
+        shift += 7;
+    }
+    if (rem < 2 || pos + 2 > len) return GM_ERR_INVALID_ARG;
+    const uint32_t tl = (static_cast<uint32_t>(packet[pos]) << 8) | packet[pos + 1];
+    pos += 2;
+    if (tl + 2 > rem || pos + tl > len) return GM_ERR_INVALID_ARG;
+    *topic = reinterpret_cast<const char*>(packet + pos);
+    *topic_len = tl;
+    return GM_OK;
+}
+
+int32_t gm_submit_publish(gm_batcher* b, const uint8_t* packet, uint32_t len, uint64_t cookie) {
+    const char* t = nullptr;
+    uint32_t tl = 0;
+    const int32_t rc = gm_publish_topic(packet, len, &t, &tl);
+    return rc == GM_OK ? gm_submit(b, t, tl, cookie) : rc;
+}
+
 int32_t gm_batcher_drain(gm_batcher* b) {
     if (!b) return GM_ERR_INVALID_ARG;
     std::unique_lock<std::mutex> lk(b->mu);

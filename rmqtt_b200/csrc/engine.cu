@@ -1023,6 +1023,20 @@ int32_t gm_retain_remove(gm_engine* e, const char* topic, uint32_t len, int32_t*
     return map_parse(st, "gm_retain_remove");
 }
 
+int32_t gm_retain_remove_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, uint32_t* old_values, uint64_t* n_removed) {
+    if (!e || (n && (!blob || !offsets))) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    uint64_t removed = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        bool had = false; u32 old = 0;
+        const int st = e->rtree.remove(blob + offsets[i], offsets[i + 1] - offsets[i], &had, &old);
+        if (old_values) old_values[i] = (st == PARSE_OK && had) ? old : 0xFFFFFFFFu;
+        removed += (st == PARSE_OK && had) ? 1 : 0;
+    }
+    if (n_removed) *n_removed = removed;
+    return GM_OK;
+}
+
 int32_t gm_retain_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets, const uint32_t* values, uint64_t n, uint64_t* n_set) {
     if (!e || (n && (!blob || !offsets || !values))) return GM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);

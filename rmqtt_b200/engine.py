@@ -169,6 +169,14 @@ class Engine:
         self._check(self._lib.gm_retain_remove(self._h, b, len(b), C.byref(had), C.byref(old)))
         return int(old.value) if had.value else None
 
+    def retain_remove_batch(self, blob: np.ndarray, offs: np.ndarray):
+        """-> (old handles uint32[n] with 0xFFFFFFFF where nothing was stored, number removed)"""
+        n = len(offs) - 1
+        old = np.empty(n, dtype=np.uint32)
+        cnt = C.c_uint64(0)
+        self._check(self._lib.gm_retain_remove_batch(self._h, _vp(blob), _vp(offs), n, _vp(old), C.byref(cnt)))
+        return old, int(cnt.value)
+
     def retain_bulk_load(self, blob: np.ndarray, offs: np.ndarray, values: np.ndarray) -> int:
         n_set = C.c_uint64(0)
         self._check(self._lib.gm_retain_bulk_load(self._h, _vp(blob), _vp(offs), _vp(values), len(values), C.byref(n_set)))

@@ -78,3 +78,35 @@ def test_error_codes_of_the_boundary_host_only():
     assert lib.gm_flush(h) == N.GM_OK and lib.gm_compact(h) == N.GM_OK
     with pytest.raises(GpuMqttError):
         eng.add("$SYS/a/$b", 1)                 # Metadata level below the root (topic.rs:357-359)
+
+
+def test_publish_topic_decoder_matches_the_mqtt_fixed_header_layout():
+    """gm_publish_topic: fixed header, remaining-length varint, u16-BE-prefixed topic (rmqtt-codec/src/v3/decode.rs:103-104,
+    rmqtt-codec/src/v5/packet/publish.rs:27-28, utils.rs:142-155).  Pure host function: no GPU needed."""
+    import ctypes as C
+    from rmqtt_b200 import _native as N
+    lib = N.lib()
+
+    def varint(x):
+        out = bytearray()
+        while True:
+            b = x & 0x7F
+            x >>= 7
+            out.append(b | (0x80 if x else 0))
+            if not x:
+                return bytes(out)
+
+    def publish(topic: bytes, payload: bytes, qos=0, v5=False):
+        var = len(topic).to_bytes(2, "big") + topic + (b"\x00\x07" if qos else b"") + (b"\x00" if v5 else b"") + payload
+        return bytes([0x30 | (qos << 1)]) + varint(len(var)) + var
+
+    for topic, payload, qos, v5 in ((b"a/b", b"x", 0, False), (b"reg-01/site-0001/dev-0000001/sen-1", b"p" * 300, 1, True), (b"", b"", 0, False), (b"t", b"z" * 20000, 2, False)):
+        pkt = publish(topic, payload, qos, v5)
+        tp, tl = C.c_char_p(), C.c_uint32(0)
+        buf = (C.c_uint8 * len(pkt)).from_buffer_copy(pkt)
+        assert lib.gm_publish_topic(buf, len(pkt), C.byref(tp), C.byref(tl)) == 0
+        assert C.string_at(C.cast(tp, C.c_void_p).value, tl.value) == topic
+    for bad in (b"\x10\x02\x00\x00", b"\x30", b"\x30\x05\x00\x09abc", b"\x30\xff\xff\xff\xff\x01"):
+        buf = (C.c_uint8 * len(bad)).from_buffer_copy(bad)
+        tp, tl = C.c_char_p(), C.c_uint32(0)
+        assert lib.gm_publish_topic(buf, len(bad), C.byref(tp), C.byref(tl)) == N.GM_ERR_INVALID_ARG

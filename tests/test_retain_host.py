@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from rmqtt_b200.engine import Engine, GpuMqttError
+from rmqtt_b200.engine import Engine, GpuMqttError, pack
 
 from _gen import rand_filter, rand_topic
 from _retainwalk import RetainTables
@@ -207,3 +207,24 @@ def test_incremental_updates_edit_the_image_in_place():
     assert tb["rstats"].tolist()[0] == s[0] + 1
     for f in ("a/+/c", "a/#", "+/+/c", "#", "a/b/#"):
         assert R.match(f.encode()) == tree.matches(f), f
+
+
+def test_batch_removal_is_the_expiry_sweep():
+    """gm_retain_remove_batch == n calls of gm_retain_remove (remove_expired_messages, retain.rs:118-128)."""
+    eng, tree = Engine(host_only=True), orc.RetainTree()
+    topics = [f"a/{i % 7}/b{i}" for i in range(300)]
+    for i, t in enumerate(topics):
+        eng.retain_set(t, i); tree.insert(t, i)
+    victims = topics[::3] + ["a/none/here", "bad/#/x", "a/0"]
+    blob, offs = pack(victims)
+    old, removed = eng.retain_remove_batch(blob, offs)
+    want = []
+    for t in victims:
+        try:
+            want.append(tree.remove(t))
+        except ValueError:
+            want.append(None)
+    assert removed == sum(w is not None for w in want)
+    assert [None if o == 0xFFFFFFFF else int(o) for o in old] == want
+    st = eng.stats()
+    assert st["retained_values"] == tree.values_size() and st["retained_nodes"] == tree.nodes_size()
