@@ -214,6 +214,13 @@ int32_t gmr_create(gm_engine* e, gm_router** out);   /* the router uses, but doe
 void gmr_destroy(gm_router* r);
 int32_t gmr_add(gm_router* r, const char* filter, uint32_t len, const gm_id* id, const gm_sub_opts* opts);   /* Router::add */
 int32_t gmr_remove(gm_router* r, const char* filter, uint32_t len, const gm_id* id, int32_t* removed);       /* Router::remove */
+/* Router::add for n subscriptions at once (snapshot restore, rmqtt-cluster-raft/src/router.rs:557-561) with numbered clients:
+ * subscription i = (filter i, Id{node_ids[i], "c<client_nums[i]>", tag = client_nums[i]}, opts from flags[i] (bit 0 v5, bit 1 no_local)
+ * and sub_ids[i]).  Invalid filters are skipped; *n_added counts the rest.                                                        */
+int32_t gmr_add_batch_numbered(gm_router* r, const char* blob, const uint32_t* offsets, uint64_t n, const uint64_t* node_ids,
+                               const uint32_t* client_nums, const uint8_t* flags, const uint32_t* sub_ids, uint64_t* n_added);
+/* wall-clock split of the last gmr_matches_batch: device part (H2D, match + relation kernels, D2H) and host assembly, in ms */
+int32_t gmr_last_timing(gm_router* r, double* device_ms, double* host_ms);
 int64_t gmr_topics(gm_router* r);
 int64_t gmr_routes(gm_router* r);
 /* Router::matches for a batch; publishers[i] is the `this_id` of PUBLISH i (NULL: no no_local filtering).
@@ -284,6 +291,38 @@ int32_t gm_partition_batch_device(gm_engine* e, const void* d_blob, uint64_t blo
 int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_span* d_spans, uint64_t k, const uint32_t* d_ids,
                              const uint64_t* d_m, uint32_t* d_all_index, gm_span* d_all_spans, uint64_t cap_topics,
                              uint32_t* d_all_ids, uint64_t cap_ids, uint64_t* sizes, void* stream);
+
+/* ---- device-side relation expansion: what DefaultRouter::_matches does with every matched relation after the
+ *      trie walk — `no_local` (rmqtt/src/router.rs:184-189), pass-through of shared-group members (router.rs:192-200; the random
+ *      pick of one member, :224-238, stays with the caller) and the per-client de-dup of v5 relations with accumulation of
+ *      subscription identifiers (rmqtt/src/types.rs:488-506) — for a whole batch, on the match kernels' own device output.     */
+typedef struct gm_rel {           /* one subscription relation, indexed by its handle (the value stored in the trie) */
+    uint32_t client_key;          /* index of the (node id, client id) pair: the v5 de-dup key */
+    uint32_t id_idx;              /* index of the subscriber's full Id: no_local compares Ids (types.rs:1746-1757) */
+    uint32_t sub_id;              /* v5 subscription identifier, 0 = none */
+    uint32_t flags;               /* GM_REL_* | shared-group id << 8 (0 = not a shared subscription) */
+} gm_rel;
+#define GM_REL_LIVE 1u
+#define GM_REL_V5 2u
+#define GM_REL_NO_LOCAL 4u
+typedef struct gm_rel_extra {     /* a v5 client that matched through MORE THAN ONE filter: its accumulated subscription ids */
+    uint32_t rel_pos;             /* index in d_handles of the client's single surviving relation */
+    uint32_t sub_off, sub_cnt;    /* d_sub_ids[sub_off .. sub_off + sub_cnt) */
+    uint32_t client_key;
+} gm_rel_extra;
+typedef struct gm_rel_out {
+    gm_span* d_spans;             /* [n] per topic: its surviving relation handles in d_handles */
+    uint32_t* d_handles; uint64_t cap_handles;
+    gm_rel_extra* d_extras; uint64_t cap_extras;
+    uint32_t* d_sub_ids; uint64_t cap_sub_ids;
+    uint64_t* d_needed;           /* device [3]: handles, extras, sub ids produced (capacity protocol: compare on the host, retry) */
+    int32_t* d_status;            /* [n]: set to 1 where a topic had more v5 relations than the kernel stages (256): that topic's list is
+                                     complete but NOT de-duplicated — the caller finishes it */
+} gm_rel_out;
+/* d_spans / d_ids: the output of gm_match_batch_device* (ids mode); d_publishers[n]: id_idx of every PUBLISH's sender or 0xFFFFFFFF
+ * (NULL: no no_local filtering); d_rels[n_rels]: the relation table.  Asynchronous on `stream`.                                   */
+int32_t gm_relations_expand_device(gm_engine* e, const gm_span* d_spans, const uint32_t* d_ids, uint64_t n, const uint32_t* d_publishers,
+                                   const gm_rel* d_rels, uint64_t n_rels, const gm_rel_out* out, void* stream);
 
 /* ---- tokeniser only (Topic::from_str for a batch) — used by tests to pin the device dictionary.
  *      out_tokens: [max_tok][n] u32 (level-major), out_meta: [n] (bits 0..23 levels, bit 30 '$', bit 31 invalid) */

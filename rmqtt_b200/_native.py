@@ -123,6 +123,7 @@ SIGNATURES = {
     "gm_batcher_destroy": (None, [_vp]),
     "gm_batcher_probe": (_i32, [_vp, _vp, _vp, _u64, _u32, _u32, _u32, _P(GmLatency)]),
     "gm_churn_probe": (_i32, [_vp, _vp, _vp, _vp, _u64, C.c_double, _u32, _u32, _P(GmChurn)]),
+    "gm_relations_expand_device": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp, _vp]),
     "gm_comm_unique_id": (_i32, [_vp]),
     "gm_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
     "gm_comm_destroy": (_i32, [_vp]),
@@ -138,6 +139,8 @@ SIGNATURES = {
     "gmr_destroy": (None, [_vp]),
     "gmr_add": (_i32, [_vp, _cp, _u32, _P(GmId), _P(GmSubOpts)]),
     "gmr_remove": (_i32, [_vp, _cp, _u32, _P(GmId), _P(_i32)]),
+    "gmr_add_batch_numbered": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _P(_u64)]),
+    "gmr_last_timing": (_i32, [_vp, _P(C.c_double), _P(C.c_double)]),
     "gmr_topics": (C.c_int64, [_vp]),
     "gmr_routes": (C.c_int64, [_vp]),
     "gmr_matches_batch": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _P(_u64), _P(_u64), _vp]),

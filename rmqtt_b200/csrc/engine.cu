@@ -22,6 +22,7 @@
 #include "host_trie.h"
 #include "comm.cuh"
 #include "kernels.cuh"
+#include "relations.cuh"
 #include "retain_kernels.cuh"
 #include "retain_tree.h"
 #include "router_host.h"
@@ -1136,6 +1137,31 @@ int32_t gmr_remove(gm_router* r, const char* filter, uint32_t len, const gm_id* 
     if (removed) *removed = rm ? 1 : 0;
     return rc;
 }
+int32_t gmr_add_batch_numbered(gm_router* r, const char* blob, const uint32_t* offsets, uint64_t n, const uint64_t* node_ids, const uint32_t* client_nums,
+                               const uint8_t* flags, const uint32_t* sub_ids, uint64_t* n_added) {
+    if (!r || (n && (!blob || !offsets || !client_nums))) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    uint64_t ok = 0;
+    char cid[24];
+    for (uint64_t i = 0; i < n; ++i) {
+        GpuRouter::Id id;
+        id.node_id = node_ids ? node_ids[i] : 1; id.tag = client_nums[i];
+        id.client_id.assign(cid, static_cast<size_t>(snprintf(cid, sizeof cid, "c%u", client_nums[i])));
+        GpuRouter::Opts o;
+        if (flags) { o.is_v5 = flags[i] & 1; o.no_local = (flags[i] >> 1) & 1; }
+        if (sub_ids) o.sub_id = sub_ids[i];
+        if (r->impl.add(blob + offsets[i], offsets[i + 1] - offsets[i], id, o) == GM_OK) ++ok;
+    }
+    if (n_added) *n_added = ok;
+    return GM_OK;
+}
+int32_t gmr_last_timing(gm_router* r, double* device_ms, double* host_ms) {
+    if (!r) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    if (device_ms) *device_ms = r->impl.last_device_ms;
+    if (host_ms) *host_ms = r->impl.last_host_ms;
+    return GM_OK;
+}
 int64_t gmr_topics(gm_router* r) { return r ? r->impl.topics() : 0; }
 int64_t gmr_routes(gm_router* r) { return r ? r->impl.routes() : 0; }
 
@@ -1273,6 +1299,28 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
     // 3. spans of rank r index rank r's ids: re-base them onto the gathered id array
     if (K) { k_rebase_spans<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint2*>(d_all_spans), d_all, W, static_cast<u32>(K)); e->launches++; }
     e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GM_OK;
+}
+
+int32_t gm_relations_expand_device(gm_engine* e, const gm_span* d_spans, const uint32_t* d_ids, uint64_t n, const uint32_t* d_publishers,
+                                   const gm_rel* d_rels, uint64_t n_rels, const gm_rel_out* o, void* stream) {
+    if (!e || !o || !o->d_needed || (n && (!d_spans || !o->d_spans || !o->d_status))) return GM_ERR_INVALID_ARG;
+    if (n > 0xFFFFFFF0ull || n_rels > 0xFFFFFFFFull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine has no device"; return GM_ERR_NO_DEVICE; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(o->d_needed, 0, 3 * sizeof(uint64_t), s));
+    if (n == 0) return GM_OK;
+    RelParams rp{};
+    rp.spans = reinterpret_cast<const uint2*>(d_spans); rp.ids = d_ids; rp.n = static_cast<u32>(n); rp.pubs = d_publishers;
+    rp.rels = d_rels; rp.n_rels = static_cast<u32>(n_rels);
+    rp.out_spans = reinterpret_cast<uint2*>(o->d_spans); rp.out_handles = o->d_handles; rp.cap_handles = o->cap_handles;
+    rp.out_extras = o->d_extras; rp.cap_extras = o->cap_extras; rp.out_sub_ids = o->d_sub_ids; rp.cap_sub_ids = o->cap_sub_ids;
+    rp.needed = reinterpret_cast<unsigned long long*>(o->d_needed); rp.status = o->d_status;
+    const unsigned grid = static_cast<unsigned>(std::min<u64>((n + 7) / 8, static_cast<u64>(e->num_sms) * 8));
+    k_relations<<<grid, 256, 0, s>>>(rp);
+    { std::lock_guard<std::mutex> g(e->mu_dev); e->launches++; }
     CUDA_TRY(cudaGetLastError());
     return GM_OK;
 }

@@ -154,15 +154,24 @@ k_retain_init(RetainParams p, RTask* out, u32* n_out) {
     if (STATS && (visited | probes)) { atomicAdd(p.stats, visited); atomicAdd(p.stats + 1, probes); }
 }
 
-// round r >= 1: one warp per task; the child block is read coalesced (32 entries = 1 KB per step), every lane takes one
-// child and follows the filter's exact levels below it
+// round r >= 1: one warp per task.  The child block is read coalesced (32 entries = 1 KB per step), every lane takes one
+// child.  What follows below a child is a run of EXACT filter levels, the same for every child of the task — so the
+// warp walks it in LOCK STEP instead of lane by lane: children whose Bloom mask admits the next level are compacted
+// (ballot) into a per-warp list of node ids in shared memory; the list is then probed 32 nodes per instruction, the
+// nodes that exist and go on form the next list, and so on down the exact run.  Every probe instruction therefore has
+// (nearly) all 32 lanes busy and 32 independent random loads in flight; the lane-by-lane version measured 13.7 of 32
+// active lanes and half the random-access rate of the part (profiles/r2_retain_round_v1.ncu-rep).  Anything that is
+// not an exact level (the next '+', a '#', a stored literal wildcard) goes through retain_chain as before.
+constexpr u32 RLIST = 256;    // = RTASK_CHUNK: at most one survivor per child of the task
 template <bool STATS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_retain_round(RetainParams p, const RTask* __restrict__ in, const u32* __restrict__ n_in_p, RTask* __restrict__ out, u32* n_out) {
-    const u32 lane = threadIdx.x & 31;
+    static_assert(RLIST >= RTASK_CHUNK, "the survivor list holds one entry per child of a task");
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = lanemask_lt();
     const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const RetainView& v = p.v;
     __shared__ u32 s_pre[RQ + 1];
+    __shared__ u32 s_list[8][2][RLIST];
     const u32 n_in = queue_prefix(n_in_p, p.cap_items, s_pre);
     const u32 sq = gwarp % RQ;                        // this warp appends to its own slice
     unsigned long long visited = 0, probes = 0;
@@ -171,24 +180,70 @@ k_retain_round(RetainParams p, const RTask* __restrict__ in, const u32* __restri
         const u32 q = tw.x, pos = tw.y & 0x3FFFFFFFu, mode = tw.y >> 30, kb = tw.z, kn = tw.w;
         const u32 L = p.qmeta[q] & META_NLEV_MASK;
         const bool next_hash = mode == 1u && (pos + 1 < L) && retain_tok(p, q, pos + 1) == TOK_HASH;
-        for (u32 e = lane; e < kn; e += 32) {
-            u32 kd[8];                                              // {token, child, first_kid, nk_flags, val, val_lo, val_hi, child-token mask}
-            ld256(v.kids + kb + e, kd);
-            if (STATS) ++visited;
-            const bool has_val = ((kd[3] >> 28) & 8u) != 0;
-            const u32 kkids = kd[3] & RNK_MASK;
-            const RRec r{kd[1], kd[2], kd[3], kd[4], kd[5], kd[6], kd[7]};
-            if (mode == 1u) {
-                if (pos + 1 == L) { if (has_val) emit_desc(p, sq, q, kd[4], 1u, 0u); }   // filter ends here: the child's own value
-                else {
-                    if (next_hash && has_val) emit_desc(p, sq, q, kd[4], 1u, 0u);        // `.../+/#` parent match
-                    if (kkids) retain_chain<STATS>(p, out, n_out, sq, q, L, pos + 1, r, visited, probes);
+        // the filter position the children continue at, and the level found there (uniform over the warp)
+        u32 P = mode == 1u ? pos + 1 : pos;
+        u32 tokP = P < L ? retain_tok(p, q, P) : TOK_UNKNOWN;
+        u32 cur = 0, cnt = 0;
+        // ---- stage A: the children ----
+        for (u32 e0 = 0; e0 < kn; e0 += 32) {
+            const u32 e = e0 + lane;
+            bool want = false;
+            u32 wnode = 0;
+            if (e < kn) {
+                u32 kd[8];                                          // {token, child, first_kid, nk_flags, val, val_lo, val_hi, child-token mask}
+                ld256(v.kids + kb + e, kd);
+                if (STATS) ++visited;
+                const bool has_val = ((kd[3] >> 28) & 8u) != 0;
+                const u32 kkids = kd[3] & RNK_MASK;
+                bool go = false;
+                if (mode == 1u) {
+                    if (pos + 1 == L) { if (has_val) emit_desc(p, sq, q, kd[4], 1u, 0u); }   // filter ends here: the child's own value
+                    else {
+                        if (next_hash && has_val) emit_desc(p, sq, q, kd[4], 1u, 0u);        // `.../+/#` parent match
+                        go = kkids != 0;
+                    }
+                } else {                                            // '#' one level at a time (a literal "#" child hides below)
+                    if (has_val) emit_desc(p, sq, q, kd[4], 1u, 0u);
+                    go = kkids != 0;
                 }
-            } else {                                                // '#' one level at a time (a literal "#" child hides below)
-                if (has_val) emit_desc(p, sq, q, kd[4], 1u, 0u);
-                if (kkids) retain_chain<STATS>(p, out, n_out, sq, q, L, pos, r, visited, probes);
+                if (go) {
+                    if (tokP >= TOK_BLANK) { want = (kd[7] & retain_mask_bit(tokP)) != 0; wnode = kd[1]; }   // exact level: lock-step list
+                    else retain_chain<STATS>(p, out, n_out, sq, q, L, P, RRec{kd[1], kd[2], kd[3], kd[4], kd[5], kd[6], kd[7]}, visited, probes);
+                }
             }
+            const u32 bal = __ballot_sync(0xFFFFFFFFu, want);
+            if (want) s_list[wid][cur][cnt + __popc(bal & lt)] = wnode;
+            cnt += __popc(bal);
         }
+        // ---- stage B: down the run of exact levels, 32 nodes per probe instruction ----
+        while (cnt) {                                               // (uniform: cnt, P, tokP are warp-wide values)
+            const bool nh = (P + 1 < L) && retain_tok(p, q, P + 1) == TOK_HASH;
+            const u32 P1 = P + 1;
+            const u32 tok1 = P1 < L ? retain_tok(p, q, P1) : TOK_UNKNOWN;
+            u32 ncnt = 0;
+            __syncwarp();
+            for (u32 b0 = 0; b0 < cnt; b0 += 32) {
+                bool want = false;
+                u32 wnode = 0;
+                if (b0 + lane < cnt) {
+                    const u32 node = s_list[wid][cur][b0 + lane];
+                    u32 c[8];
+                    if (STATS) { ++probes; ++visited; }
+                    if (retain_child(v, node, tokP, c)) {
+                        const u32 fl = c[4] >> 28, nk = c[4] & RNK_MASK;
+                        if (nh && (fl & 8u)) emit_desc(p, sq, q, c[5], 1u, 0u);              // '#' matches the parent, retain.rs:317-322
+                        if (nk == 0 || P1 == L) { if (P1 == L && (fl & 8u)) emit_desc(p, sq, q, c[5], 1u, 0u); }   // retain.rs:305-311
+                        else if (tok1 >= TOK_BLANK) { want = true; wnode = c[2]; }             // another exact level (a hash slot has no mask)
+                        else retain_chain<STATS>(p, out, n_out, sq, q, L, P1, RRec{c[2], c[3], c[4], c[5], c[6], c[7], 0xFFFFFFFFu}, visited, probes);
+                    }
+                }
+                const u32 bal = __ballot_sync(0xFFFFFFFFu, want);
+                if (want) s_list[wid][cur ^ 1][ncnt + __popc(bal & lt)] = wnode;
+                ncnt += __popc(bal);
+            }
+            cur ^= 1; cnt = ncnt; P = P1; tokP = tok1;
+        }
+        __syncwarp();
     }
     if (STATS) {
 #pragma unroll

@@ -1,9 +1,49 @@
 // GpuRouter — see router_host.h.
 #include "router_host.h"
 
+#include <cuda_runtime.h>
+
 #include <algorithm>
+#include <chrono>
 
 namespace gm {
+
+namespace {
+std::string ckey(uint64_t node, const std::string& client) { std::string k = std::to_string(node); k.push_back('\0'); k += client; return k; }
+std::string ikey(uint64_t node, const std::string& client, uint64_t tag) { std::string k = ckey(node, client); k.push_back('\0'); k += std::to_string(tag); return k; }
+}  // namespace
+
+GpuRouter::~GpuRouter() {
+    for (Dev* d : {&d_rels_, &d_blob_, &d_offs_, &d_spans_, &d_status_, &d_ids_, &d_needed_, &d_pubs_, &d_ospans_, &d_handles_, &d_extras_, &d_subs_})
+        if (d->p) cudaFree(d->p);
+    if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
+}
+
+int32_t GpuRouter::ensure(Dev& d, size_t bytes) {
+    if (bytes <= d.cap) return GM_OK;
+    size_t ncap = std::max(bytes, d.cap + d.cap / 2 + 4096);
+    void* np = nullptr;
+    if (cudaMalloc(&np, ncap) != cudaSuccess) return GM_ERR_CUDA;
+    if (d.p) { cudaMemcpy(np, d.p, d.cap, cudaMemcpyDeviceToDevice); cudaFree(d.p); }
+    d.p = np; d.cap = ncap;
+    return GM_OK;
+}
+
+// the device record of a relation: everything k_relations needs to apply router.rs:184-200 and types.rs:488-506
+void GpuRouter::set_rel(uint32_t handle, const Rel& r) {
+    if (rel_host_.size() <= handle) rel_host_.resize(handle + 1, gm_rel{0, 0, 0, 0});
+    gm_rel d{0, 0, 0, 0};
+    if (r.live) {
+        d.client_key = intern(client_key_, ckey(r.id.node_id, r.client));
+        d.id_idx = intern(id_idx_, ikey(r.id.node_id, r.id.client_id, r.id.tag));
+        d.sub_id = r.opts.sub_id;
+        uint32_t group = 0;
+        if (!r.opts.group.empty()) { std::string key = filter_names_[r.filter_idx]; key.push_back('\0'); key += r.opts.group; group = group_index_.emplace(key, static_cast<uint32_t>(group_index_.size() + 1)).first->second; }
+        d.flags = GM_REL_LIVE | (r.opts.is_v5 ? GM_REL_V5 : 0u) | (r.opts.no_local ? GM_REL_NO_LOCAL : 0u) | (group << 8);
+    }
+    rel_host_[handle] = d;
+    rel_dirty_lo_ = std::min(rel_dirty_lo_, handle); rel_dirty_hi_ = std::max(rel_dirty_hi_, handle + 1);
+}
 
 int32_t GpuRouter::add(const char* filter, uint32_t len, const Id& id, const Opts& opts) {
     std::string f(filter, len);
@@ -36,6 +76,7 @@ int32_t GpuRouter::add(const char* filter, uint32_t len, const Id& id, const Opt
     Rel& r = by_handle_[handle];
     r.filter_idx = fi; r.client = id.client_id; r.id = id; r.opts = opts; r.live = true;
     if (clients.emplace(id.client_id, handle).second) routes_++;     // HashMap::insert: replace keeps the count (router.rs:430-433)
+    set_rel(handle, r);
     return GM_OK;
 }
 
@@ -53,6 +94,7 @@ int32_t GpuRouter::remove(const char* filter, uint32_t len, const Id& id, bool* 
     routes_--;
     if (rit->second.empty()) { relations_.erase(rit); topics_--; }    // router.rs:466-473
     by_handle_[handle].live = false;
+    set_rel(handle, by_handle_[handle]);
     free_handles_.push_back(handle);
     int32_t changed = 0;
     int32_t rc = gm_sub_remove(e_, filter, len, handle, &changed);
@@ -68,60 +110,131 @@ bool GpuRouter::relation(uint32_t handle, const std::string** filter, const std:
     return true;
 }
 
+// per-client de-dup of ONE topic on the host — only for topics the kernel flagged (more v5 relations than it stages)
+int32_t GpuRouter::host_dedup_topic(const gm_id*, const uint32_t* hs, uint32_t cnt, std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids) {
+    struct V5Entry { size_t rel_pos; std::vector<uint32_t> ids; };
+    std::unordered_map<uint32_t, V5Entry> v5;                 // client_key -> (its relation, accumulated ids)
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t h = hs[k];
+        const Rel& r = by_handle_[h];
+        const gm_rel& d = rel_host_[h];
+        if (!(d.flags & GM_REL_V5) || (d.flags >> 8)) { rels.push_back(gm_sub_relation{r.id.node_id, h, d.flags >> 8, 0, 0}); continue; }
+        auto it = v5.find(d.client_key);
+        if (it == v5.end()) { V5Entry e{rels.size(), {}}; if (d.sub_id) e.ids.push_back(d.sub_id); rels.push_back(gm_sub_relation{r.id.node_id, h, 0, 0, 0}); v5.emplace(d.client_key, std::move(e)); }
+        else if (d.sub_id) it->second.ids.push_back(d.sub_id);
+    }
+    for (auto& kv : v5) {
+        gm_sub_relation& sr = rels[kv.second.rel_pos];
+        sr.sub_ids_off = static_cast<uint32_t>(sub_ids.size()); sr.sub_ids_cnt = static_cast<uint32_t>(kv.second.ids.size());
+        sub_ids.insert(sub_ids.end(), kv.second.ids.begin(), kv.second.ids.end());
+    }
+    return GM_OK;
+}
+
+#define R_CUDA(expr) do { cudaError_t _ce = (expr); if (_ce != cudaSuccess) return (_ce == cudaErrorNoDevice || _ce == cudaErrorInsufficientDriver) ? GM_ERR_NO_DEVICE : GM_ERR_CUDA; } while (0)
+#define R_TRY(expr) do { int32_t _rc = (expr); if (_rc != GM_OK) return _rc; } while (0)
+
 int32_t GpuRouter::matches_batch(const gm_id* publishers, const char* blob, const uint32_t* offs, uint64_t n, std::vector<gm_span>& spans,
                                  std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids, std::vector<int32_t>& status) {
     spans.assign(n, gm_span{0, 0});
     status.assign(n, 0);
     rels.clear(); sub_ids.clear();
     if (n == 0) return GM_OK;
-    tmp_spans_.assign(n, gm_span{0, 0});
-    uint64_t needed = 0;
-    if (tmp_ids_.size() < 1024) tmp_ids_.resize(std::max<size_t>(1024, 32 * n));
-    for (;;) {
-        int32_t rc = gm_match_batch(e_, blob, offs, n, tmp_spans_.data(), tmp_ids_.data(), tmp_ids_.size(), &needed, status.data());
-        if (rc == GM_ERR_CAPACITY) { tmp_ids_.resize(needed + 1024); continue; }
-        if (rc != GM_OK) return rc;
-        break;
+    using Clk = std::chrono::steady_clock;
+    const auto t0 = Clk::now();
+    if (!stream_) { cudaStream_t s; R_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); stream_ = s; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    // ---- the relation table: ship what changed since the last call
+    if (rel_dirty_hi_ > rel_dirty_lo_) {
+        R_TRY(ensure(d_rels_, std::max<size_t>(rel_host_.size(), 1024) * sizeof(gm_rel)));
+        R_CUDA(cudaMemcpyAsync(static_cast<gm_rel*>(d_rels_.p) + rel_dirty_lo_, rel_host_.data() + rel_dirty_lo_, (rel_dirty_hi_ - rel_dirty_lo_) * sizeof(gm_rel), cudaMemcpyHostToDevice, s));
+        rel_dirty_lo_ = 0xFFFFFFFFu; rel_dirty_hi_ = 0;
     }
-    struct V5Entry { size_t rel_pos; std::vector<uint32_t> ids; };
+    // ---- topics and publishers to the device, match (ids = relation handles stay in HBM)
+    const uint64_t blob_bytes = offs[n];
+    R_TRY(ensure(d_blob_, blob_bytes + 16)); R_TRY(ensure(d_offs_, (n + 1) * 4)); R_TRY(ensure(d_spans_, n * 8)); R_TRY(ensure(d_status_, n * 4));
+    R_TRY(ensure(d_needed_, 4 * 8)); R_TRY(ensure(d_ospans_, n * 8));
+    if (blob_bytes) R_CUDA(cudaMemcpyAsync(d_blob_.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
+    R_CUDA(cudaMemcpyAsync(d_offs_.p, offs, (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    std::vector<uint32_t> pubs;
+    if (publishers) {
+        pubs.resize(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            auto it = id_idx_.find(ikey(publishers[i].node_id, publishers[i].client_id ? std::string(publishers[i].client_id, publishers[i].client_len) : std::string(), publishers[i].tag));
+            pubs[i] = it == id_idx_.end() ? 0xFFFFFFFFu : it->second;       // an Id no subscriber holds cannot equal any relation's Id
+        }
+        R_TRY(ensure(d_pubs_, n * 4));
+        R_CUDA(cudaMemcpyAsync(d_pubs_.p, pubs.data(), n * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (d_ids_.cap < 4096) R_TRY(ensure(d_ids_, std::max<size_t>(4096, 32 * n) * 4));
+    uint64_t need[4] = {0, 0, 0, 0};
+    for (;;) {
+        gm_match_args a{};
+        a.struct_size = sizeof(a); a.d_blob = d_blob_.p; a.blob_bytes = blob_bytes; a.d_offsets = static_cast<const uint32_t*>(d_offs_.p); a.n_entries = n; a.n = n;
+        a.d_spans = static_cast<gm_span*>(d_spans_.p); a.d_out = d_ids_.p; a.cap = d_ids_.cap / 4; a.d_needed = static_cast<uint64_t*>(d_needed_.p) + 3;
+        a.d_status = static_cast<int32_t*>(d_status_.p); a.stream = s;
+        R_TRY(gm_match_batch_device_ex(e_, &a));
+        R_CUDA(cudaMemcpyAsync(&need[3], static_cast<uint64_t*>(d_needed_.p) + 3, 8, cudaMemcpyDeviceToHost, s));
+        R_CUDA(cudaStreamSynchronize(s));
+        if (need[3] > 0xFFFFFFFFull) return GM_ERR_TOO_LARGE;
+        if (need[3] * 4 <= d_ids_.cap) break;
+        R_TRY(ensure(d_ids_, (need[3] + 1024) * 4));
+    }
+    // ---- relation expansion on the device
+    R_TRY(ensure(d_handles_, std::max<uint64_t>(need[3], 1) * 4));
+    if (d_extras_.cap < 4096) { R_TRY(ensure(d_extras_, 4096 * sizeof(gm_rel_extra))); R_TRY(ensure(d_subs_, 16384 * 4)); }
+    for (;;) {
+        gm_rel_out o{};
+        o.d_spans = static_cast<gm_span*>(d_ospans_.p); o.d_handles = static_cast<uint32_t*>(d_handles_.p); o.cap_handles = d_handles_.cap / 4;
+        o.d_extras = static_cast<gm_rel_extra*>(d_extras_.p); o.cap_extras = d_extras_.cap / sizeof(gm_rel_extra);
+        o.d_sub_ids = static_cast<uint32_t*>(d_subs_.p); o.cap_sub_ids = d_subs_.cap / 4;
+        o.d_needed = static_cast<uint64_t*>(d_needed_.p); o.d_status = static_cast<int32_t*>(d_status_.p);
+        R_TRY(gm_relations_expand_device(e_, static_cast<const gm_span*>(d_spans_.p), static_cast<const uint32_t*>(d_ids_.p), n, publishers ? static_cast<const uint32_t*>(d_pubs_.p) : nullptr,
+                                         static_cast<const gm_rel*>(d_rels_.p), rel_host_.size(), &o, s));
+        R_CUDA(cudaMemcpyAsync(need, d_needed_.p, 3 * 8, cudaMemcpyDeviceToHost, s));
+        R_CUDA(cudaStreamSynchronize(s));
+        if (need[1] * sizeof(gm_rel_extra) <= d_extras_.cap && need[2] * 4 <= d_subs_.cap) break;      // (handles always fit: at most one per matched id)
+        R_TRY(ensure(d_extras_, (need[1] + 64) * sizeof(gm_rel_extra))); R_TRY(ensure(d_subs_, (need[2] + 64) * 4));
+    }
+    tmp_spans_.resize(n); tmp_ids_.resize(need[0]);
+    std::vector<gm_rel_extra> extras(need[1]);
+    std::vector<uint32_t> xsubs(need[2]);
+    R_CUDA(cudaMemcpyAsync(tmp_spans_.data(), d_ospans_.p, n * 8, cudaMemcpyDeviceToHost, s));
+    R_CUDA(cudaMemcpyAsync(status.data(), d_status_.p, n * 4, cudaMemcpyDeviceToHost, s));
+    if (need[0]) R_CUDA(cudaMemcpyAsync(tmp_ids_.data(), d_handles_.p, need[0] * 4, cudaMemcpyDeviceToHost, s));
+    if (need[1]) R_CUDA(cudaMemcpyAsync(extras.data(), d_extras_.p, need[1] * sizeof(gm_rel_extra), cudaMemcpyDeviceToHost, s));
+    if (need[2]) R_CUDA(cudaMemcpyAsync(xsubs.data(), d_subs_.p, need[2] * 4, cudaMemcpyDeviceToHost, s));
+    R_CUDA(cudaStreamSynchronize(s));
+    const auto t1 = Clk::now();
+    // ---- host: handles -> gm_sub_relation records (table look-ups only; no hashing, no strings)
+    std::sort(extras.begin(), extras.end(), [](const gm_rel_extra& a, const gm_rel_extra& b) { return a.rel_pos < b.rel_pos; });
+    size_t xi = 0;
+    rels.reserve(need[0]);
     for (uint64_t i = 0; i < n; ++i) {
         const size_t begin = rels.size();
-        if (status[i] == 0) {
-            const Id pub{publishers ? publishers[i].node_id : 0, publishers && publishers[i].client_id ? std::string(publishers[i].client_id, publishers[i].client_len) : std::string(),
-                         publishers ? publishers[i].tag : 0};
-            std::unordered_map<std::string, V5Entry> v5;     // key: node id + client id (one collector per node, types.rs:466)
-            const uint32_t* hs = tmp_ids_.data() + tmp_spans_[i].off;
-            for (uint32_t k = 0; k < tmp_spans_[i].cnt; ++k) {
-                const uint32_t h = hs[k];
-                if (h >= by_handle_.size() || !by_handle_[h].live) continue;
-                const Rel& r = by_handle_[h];
-                if (r.opts.is_v5 && r.opts.no_local && publishers && pub == r.id) continue;                      // router.rs:184-189
-                if (!r.opts.group.empty()) {                                                                      // router.rs:192-200
-                    std::string key = filter_names_[r.filter_idx]; key.push_back('\0'); key += r.opts.group;
-                    auto g = group_index_.emplace(key, static_cast<uint32_t>(group_index_.size() + 1)).first->second;
-                    rels.push_back(gm_sub_relation{r.id.node_id, h, g, 0, 0});
-                } else if (!r.opts.is_v5) {                                                                       // types.rs:486-487
-                    rels.push_back(gm_sub_relation{r.id.node_id, h, 0, 0, 0});
-                } else {                                                                                          // types.rs:488-506
-                    std::string key = std::to_string(r.id.node_id); key.push_back('\0'); key += r.client;
-                    auto it = v5.find(key);
-                    if (it == v5.end()) {
-                        V5Entry e{rels.size(), {}};
-                        if (r.opts.sub_id) e.ids.push_back(r.opts.sub_id);
-                        rels.push_back(gm_sub_relation{r.id.node_id, h, 0, 0, 0});
-                        v5.emplace(std::move(key), std::move(e));
-                    } else if (r.opts.sub_id) it->second.ids.push_back(r.opts.sub_id);
+        const uint32_t off = tmp_spans_[i].off, cnt = tmp_spans_[i].cnt;
+        if (status[i] == 1) {                          // flagged by the kernel: complete but not de-duplicated
+            status[i] = 0;
+            R_TRY(host_dedup_topic(publishers ? publishers + i : nullptr, tmp_ids_.data() + off, cnt, rels, sub_ids));
+        } else if (status[i] == 0) {
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const uint32_t h = tmp_ids_[off + k];
+                const gm_rel& d = rel_host_[h];
+                gm_sub_relation sr{by_handle_[h].id.node_id, h, d.flags >> 8, 0, 0};
+                if ((d.flags & GM_REL_V5) && !(d.flags >> 8)) {
+                    while (xi < extras.size() && extras[xi].rel_pos < off + k) ++xi;
+                    if (xi < extras.size() && extras[xi].rel_pos == off + k) {      // matched through several filters: accumulated ids
+                        sr.sub_ids_off = static_cast<uint32_t>(sub_ids.size()); sr.sub_ids_cnt = extras[xi].sub_cnt;
+                        sub_ids.insert(sub_ids.end(), xsubs.begin() + extras[xi].sub_off, xsubs.begin() + extras[xi].sub_off + extras[xi].sub_cnt);
+                    } else if (d.sub_id) { sr.sub_ids_off = static_cast<uint32_t>(sub_ids.size()); sr.sub_ids_cnt = 1; sub_ids.push_back(d.sub_id); }
                 }
-            }
-            for (auto& kv : v5) {
-                gm_sub_relation& sr = rels[kv.second.rel_pos];
-                sr.sub_ids_off = static_cast<uint32_t>(sub_ids.size());
-                sr.sub_ids_cnt = static_cast<uint32_t>(kv.second.ids.size());
-                sub_ids.insert(sub_ids.end(), kv.second.ids.begin(), kv.second.ids.end());
+                rels.push_back(sr);
             }
         }
         spans[i] = gm_span{static_cast<uint32_t>(begin), static_cast<uint32_t>(rels.size() - begin)};
     }
+    last_device_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    last_host_ms = std::chrono::duration<double, std::milli>(Clk::now() - t1).count();
     return GM_OK;
 }
 

@@ -7,11 +7,12 @@
 //             the trie of the reference (`topics: TopicTree<()>`) is the device-resident trie of the engine;
 //             its values are relation handles (one u32 per (filter, client))
 //   add       router.rs:417-436        remove    router.rs:439-479 (Id-equality rule)
-//   matches   router.rs:162-248 for a batch of PUBLISHes: engine match -> relation lookup -> no_local (:184-189)
-//             -> shared-group bucketing (:192-200) -> SubscriptioRelationsCollector::add (types.rs:478-508:
-//             v3 one relation per (filter, client); v5 per-client de-dup, subscription identifiers accumulate)
-//             The shared-subscription *choice* is rand::random in the reference (subscribe.rs:88): members are
-//             returned, not chosen.
+//   matches   router.rs:162-248 for a batch of PUBLISHes, ON THE DEVICE: engine match (gm_match_batch_device_ex) ->
+//             k_relations (relations.cuh): no_local (:184-189), shared-group members passed through (:192-200),
+//             v5 per-client de-dup with accumulation of subscription identifiers (types.rs:488-506) -> the host only
+//             turns the surviving handles into gm_sub_relation records.  The router keeps a 16-byte gm_rel record per
+//             handle in HBM (shipped incrementally).  The shared-subscription *choice* is rand::random in the
+//             reference (subscribe.rs:88): members are returned, not chosen.
 #pragma once
 #include <cstdint>
 #include <mutex>
@@ -30,6 +31,9 @@ class GpuRouter {
     struct Opts { uint8_t qos = 0, is_v5 = 0, no_local = 0; uint32_t sub_id = 0; std::string group; };                          // types.rs:565-718
 
     explicit GpuRouter(gm_engine* e) : e_(e) {}
+    ~GpuRouter();
+    // timing of the last matches_batch call (milliseconds): device (H2D + match + relation kernel + D2H), host assembly
+    double last_device_ms = 0, last_host_ms = 0;
 
     int32_t add(const char* filter, uint32_t len, const Id& id, const Opts& opts);
     int32_t remove(const char* filter, uint32_t len, const Id& id, bool* removed);
@@ -52,6 +56,17 @@ class GpuRouter {
     int64_t topics_ = 0, routes_ = 0;
     std::vector<gm_span> tmp_spans_;
     std::vector<uint32_t> tmp_ids_;
+    // ---- device side of the relation expansion ----
+    std::vector<gm_rel> rel_host_;                                     // handle -> record, mirrored in HBM
+    uint32_t rel_dirty_lo_ = 0xFFFFFFFFu, rel_dirty_hi_ = 0;           // handles changed since the last upload
+    std::unordered_map<std::string, uint32_t> client_key_, id_idx_;    // "node\0client" -> key, "node\0client\0tag" -> idx
+    struct Dev { void* p = nullptr; size_t cap = 0; };
+    Dev d_rels_, d_blob_, d_offs_, d_spans_, d_status_, d_ids_, d_needed_, d_pubs_, d_ospans_, d_handles_, d_extras_, d_subs_;
+    void* stream_ = nullptr;
+    int32_t ensure(Dev& d, size_t bytes);
+    uint32_t intern(std::unordered_map<std::string, uint32_t>& m, const std::string& k) { return m.emplace(k, static_cast<uint32_t>(m.size())).first->second; }
+    void set_rel(uint32_t handle, const Rel& r);
+    int32_t host_dedup_topic(const gm_id* publisher, const uint32_t* hs, uint32_t cnt, std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids);
 };
 
 }  // namespace gm

@@ -97,3 +97,37 @@ def test_random_differential_vs_oracle_router(seed):
                 got_members = sorted(m for ms in groups.values() for m in ms)
                 want_members = sorted(m for w in wg for m in w.split(";"))
                 assert got_members == want_members, t
+
+
+@pytest.mark.parametrize("n_clients,per_client", [(60, 3), (300, 2), (5, 40)])
+def test_v5_per_client_dedup_on_the_device_and_its_host_fallback(n_clients, per_client):
+    """types.rs:488-506 on the device (k_relations): a v5 client matching through several filters gets ONE relation with all
+    its subscription identifiers; a topic with more v5 relations than the kernel stages (256) is finished on the host."""
+    r, o = GpuRouter(), orc.Router()
+    filters = ["t/+/x", "t/a/+", "t/#", "+/a/x", "t/a/x", "#", "t/+/+", "+/+/x", "+/a/+", "+/+/+"]
+    filters += [f"t/a/x/{k}/#" for k in range(40)]           # do not match the probe topic
+    filters = (filters[:10] * 4)[:per_client] if per_client <= 10 else [f"t/a/x" if k == 0 else (filters[k % 10] if k < 10 else f"q{k}/+/x") for k in range(per_client)]
+    filters = list(dict.fromkeys(filters))                    # distinct filters per client
+    rel = 0
+    v5flag = {}
+    for c in range(n_clients):
+        cid = Id(1 + c % 2, f"c{c}", 500 + c)
+        for j, f in enumerate(filters):
+            rel += 1
+            v5 = c % 5 != 0                                    # every fifth client is v3: no de-dup for it
+            opts = SubscriptionOptions(qos=1, is_v5=v5, no_local=v5 and c % 7 == 0, sub_id=(1 + (c + j) % 9) if v5 and (c + j) % 3 else 0)
+            r.add(f, cid, opts)
+            assert o.add_full(f, cid.client_id, rel, cid.tag, cid.node_id, opts.is_v5, opts.no_local, opts.sub_id, "")
+            v5flag[(f, cid.client_id)] = v5
+    topics = ["t/a/x", "t/b/x", "z/a/x", "nomatch"]
+    pubs = [Id(1, "c0", 500), Id(2, "c7", 507), Id(1, "c14", 514), Id(9, "nobody", 1)]      # c7 and c14 are v5 + no_local: dropped for their own PUBLISH
+    got = r.matches_batch(topics, pubs)
+    for t, p, g in zip(topics, pubs, got):
+        want = o.matches_full(t, p.node_id, p.client_id, p.tag)
+        lines = []
+        for x in g:
+            if v5flag[(x.topic_filter, x.client_id)]:
+                lines.append(f"5|{x.node_id}|{x.client_id}|" + ",".join(str(s) for s in sorted(x.sub_ids)))
+            else:
+                lines.append(f"3|{x.node_id}|{x.topic_filter}|{x.client_id}")
+        assert sorted(lines) == want, t
