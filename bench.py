@@ -231,6 +231,52 @@ def _c4_leg(torch, dev, stream, peak, small: bool):
             "count_parity": bool((counts == o["counts"]).all()), "build_s": round(build_s, 1)}
 
 
+def _relations_leg(small: bool):
+    """Router::matches END TO END at the router level (config C2: 1 M subscriptions, 100 K-topic batch): engine match +
+    device-side relation expansion (k_relations: no_local, v5 per-client de-dup) + host assembly of gm_sub_relation records."""
+    from rmqtt_b200 import workload as wl
+    from rmqtt_b200 import _native as N
+    from rmqtt_b200.router import GpuRouter
+    cfg = wl.C2.scaled(n_subs=100_000, n_topics=20_000, name="C2-scaled") if small else wl.C2
+    sb, so, sv = wl.gen_subs(cfg)
+    tb, to = wl.gen_topics(cfg)
+    n = cfg.n_topics
+    r = GpuRouter()
+    lib = N.lib()
+    rng = np.random.default_rng(7)
+    nodes = rng.integers(1, 4, size=len(sv)).astype(np.uint64)
+    clients = (sv // 2).astype(np.uint32)                      # every client holds two subscriptions: de-dup has work to do
+    flags = (rng.random(len(sv)) < 0.5).astype(np.uint8)       # half of the clients speak v5
+    flags = flags[clients % len(flags)] | ((rng.random(len(sv)) < 0.1).astype(np.uint8) << 1)
+    sub_ids = np.where(flags & 1, 1 + (sv % 7), 0).astype(np.uint32)
+    added = C.c_uint64(0)
+    t0 = time.time()
+    rc = lib.gmr_add_batch_numbered(r._h, sb.ctypes.data, so.ctypes.data, len(sv), nodes.ctypes.data, clients.ctypes.data, flags.ctypes.data, sub_ids.ctypes.data, C.byref(added))
+    assert rc == 0
+    build_s = time.time() - t0
+    spans = np.zeros((n, 2), dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    cap_r, cap_s = 64 * n, 16 * n
+    rels = (N.GmSubRelation * cap_r)()
+    sids = np.zeros(cap_s, dtype=np.uint32)
+    nr, ns = C.c_uint64(0), C.c_uint64(0)
+    dev_ms, host_ms, wall = [], [], []
+    for k in range(6):
+        t0 = time.perf_counter()
+        rc = lib.gmr_matches_batch(r._h, None, tb.ctypes.data, to.ctypes.data, n, spans.ctypes.data, rels, cap_r, sids.ctypes.data, cap_s, C.byref(nr), C.byref(ns), status.ctypes.data)
+        assert rc == 0, rc
+        wall.append((time.perf_counter() - t0) * 1e3)
+        d, h = C.c_double(0), C.c_double(0)
+        lib.gmr_last_timing(r._h, C.byref(d), C.byref(h))
+        dev_ms.append(d.value); host_ms.append(h.value)
+    return {"workload": f"{cfg.name}: {int(added.value)} subscriptions (every client subscribes twice, half of them v5, 10% no_local), {n}-topic batch, host buffers",
+            "relations_per_batch": int(nr.value), "sub_ids_per_batch": int(ns.value),
+            "device_ms": float(np.median(dev_ms[1:])), "host_assembly_ms": float(np.median(host_ms[1:])), "call_ms": float(np.median(wall[1:])),
+            "topics_per_s": n / (float(np.median(wall[1:])) * 1e-3), "relations_per_s": int(nr.value) / (float(np.median(wall[1:])) * 1e-3),
+            "device_part": "H2D topics, k_tokenize..k_match_fast, k_relations (no_local, v5 per-client de-dup, sub-id accumulation), D2H handles",
+            "host_part": "handle -> gm_sub_relation{node_id, handle, group, sub ids}: table look-ups only", "router_build_s": round(build_s, 1)}
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
@@ -458,7 +504,14 @@ def run_own(args):
         ms_wg = timed_device_loop(weak_gather_step, coll_steps, 3)
         multi["value_with_gather"] = world * n * coll_steps / (ms_wg / 1e3)
         multi["weak_gather_ms_per_step"] = ms_wg / coll_steps
-        multi["collective"] = "gm_allgatherv_device: ncclAllGather of (topics, ids) per rank + one grouped launch of per-rank ncclBroadcasts out of the match kernels' buffers"
+        multi["collective"] = "gm_allgatherv_device: ncclAllGather of (topics, ids) per rank + one grouped launch of ncclSend/ncclRecv pairs out of the match kernels' buffers"
+        # A/B of the data movement inside the collective: per-rank ncclBroadcasts instead of point-to-point pairs
+        eng.debug_knob("gather_bcast", 1)
+        phase[:] = 0
+        for k in range(coll_steps):
+            strong_step(k, record=True)
+        multi["strong"]["all_gatherv_ms_with_broadcasts"] = max_over_ranks(float(phase[2])) / coll_steps
+        eng.debug_knob("gather_bcast", 0)
 
     # ---- parity self-check of the sharded path: gathered lists of a >= 50 K-topic sample against the oracle (rank 0) ----
     sizes = strong_step(0)
@@ -527,6 +580,7 @@ def run_own(args):
     c4 = None
     latency = None
     churn = None
+    relations = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         threads = orc.hardware_threads()
@@ -596,6 +650,7 @@ def run_own(args):
                    "crossover": f"one CPU thread answers a PUBLISH in {cpu_lat_us:.1f} us; the GPU front end's throughput passes one CPU thread at an offered burst of {cross} topics"}
         if not args.no_c4:
             c4 = _c4_leg(torch, dev, stream, peak, small)
+        relations = _relations_leg(small)
 
     line = {
         "metric": "topic-matches/sec @10M subs", "value": value, "unit": "topics/s", "n_gpus": world, "steps": args.steps,
@@ -616,6 +671,7 @@ def run_own(args):
         "c4": c4,
         "latency": latency,
         "churn": churn,
+        "relations": relations,
         "clocks": clocks,
     }
     if multi and "value_with_gather" in multi:

@@ -1,11 +1,8 @@
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/gpus2.txt
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/pytest_multi.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi.txt; tail -8 gpurun_out/pytest_multi.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench2 exit $?"; tail -5 gpurun_out/bench_n2.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_n2.json'))
-for k in ('value','value_with_gather','value_descriptor_mode','e2e','multi_gpu','parity_check'):
-    print(k, json.dumps(d.get(k))[:1500])
+timeout 900 python -m pytest tests/test_gpu_router.py tests/test_gpu_retain.py tests/test_gpu_hypothesis.py tests/test_gpu_batcher.py "tests/test_gpu_fullsize.py::test_retained_full_size_every_filter_bit_exact" -m gpu -x -q > gpurun_out/pytest_gpu4.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu4.txt; tail -12 gpurun_out/pytest_gpu4.txt
+python tools/c4_once.py stats > gpurun_out/c4_stats2.txt 2>&1; tail -4 gpurun_out/c4_stats2.txt
+python - <<'PY' > gpurun_out/relations_leg.json 2> gpurun_out/relations_leg.err
+import json, bench
+print(json.dumps(bench._relations_leg(False)))
 PY
-./tools/randbench6 > gpurun_out/randbench6.txt 2>&1; cat gpurun_out/randbench6.txt
+cat gpurun_out/relations_leg.json; tail -3 gpurun_out/relations_leg.err

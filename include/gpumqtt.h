@@ -228,6 +228,15 @@ int64_t gmr_routes(gm_router* r);
 int32_t gmr_matches_batch(gm_router* r, const gm_id* publishers, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
                           gm_span* out_spans, gm_sub_relation* out_rels, uint64_t cap_rels, uint32_t* out_sub_ids, uint64_t cap_sub_ids,
                           uint64_t* needed_rels, uint64_t* needed_sub_ids, int32_t* status);
+/* The secondary readers of the same tree — _has_matches (rmqtt/src/router.rs:139-142), _get_routes (:145-158), Router::get
+ * (:522-546), _query_subscriptions_for_matches (:315-363) — all need the UNIQUE matched FILTERS of a topic.  Served by the
+ * engine in descriptor mode (one descriptor per matched filter node; its first handle names the filter): out_spans[i] locates
+ * topic i's unique matched filter indices in out_filters; gmr_filter gives a filter's string and the distinct node ids of its
+ * relations.  No second CPU trie is needed for these calls.                                                                     */
+int32_t gmr_matched_filters_batch(gm_router* r, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n, gm_span* out_spans,
+                                  uint32_t* out_filters, uint64_t cap_filters, uint64_t* needed, int32_t* status);
+int32_t gmr_filter(gm_router* r, uint32_t filter_idx, const char** filter, uint32_t* filter_len, uint64_t* out_node_ids, uint32_t cap_nodes,
+                   uint32_t* n_nodes);
 int32_t gmr_relation(gm_router* r, uint32_t handle, const char** filter, uint32_t* filter_len, const char** client, uint32_t* client_len);
 
 /* ---- single-call front end: Router::matches is called once per PUBLISH from many tokio workers (rmqtt/src/router.rs:482-484,
@@ -286,7 +295,7 @@ int32_t gm_partition_batch_device(gm_engine* e, const void* d_blob, uint64_t blo
  * every rank.  Local contribution: k topics with global indices d_index[k] (= d_sel), d_spans[k] into d_ids[*d_m] (*d_m is the
  * DEVICE counter the match wrote: d_needed).  Output, rank-major: d_all_index / d_all_spans (re-based onto d_all_ids) /
  * d_all_ids; sizes[2*r] = topics, sizes[2*r+1] = ids of rank r (host array, 2*world).  ncclAllGather of the sizes + one
- * grouped launch of ncclBroadcasts reading the match kernels' own output buffers.  Collective: every rank must call it.
+ * grouped launch of ncclSend/ncclRecv pairs reading the match kernels' own output buffers.  Collective: every rank must call it.
  * GM_ERR_CAPACITY when an output is too small (sizes[] is valid then).  Asynchronous on `stream` after one host sync.      */
 int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_span* d_spans, uint64_t k, const uint32_t* d_ids,
                              const uint64_t* d_m, uint32_t* d_all_index, gm_span* d_all_spans, uint64_t cap_topics,

@@ -330,6 +330,34 @@ struct Router {
         std::sort(lines.begin(), lines.end());
         return true;
     }
+    // Secondary readers of the same tree, canonicalised as sorted text lines:
+    //   kind 0  _has_matches (router.rs:139-142 -> trie.rs:138-140): one line "1" if any filter matches
+    //   kind 1  _get_routes  (router.rs:145-158): "filter" per UNIQUE matched filter (the caller adds its own node id)
+    //   kind 2  get          (router.rs:522-546): "node|filter" per unique matched filter and unique node id among its relations
+    bool readers(std::string_view topic, int kind, std::vector<std::string>& lines) const {
+        Topic t;
+        if (!parse_topic(topic, t)) return false;
+        Counters c;
+        std::vector<const Level*> sp;
+        std::set<std::string> uniq;                                  // itertools .unique() over the matched filter paths
+        std::string fs;
+        trie_walk(&topics, t, 0, sp, c, [&](const std::vector<const Level*>& fp, const std::set<char>&) {
+            fs.clear();
+            for (size_t k = 0; k < fp.size(); ++k) { if (k) fs += '/'; level_to_string(*fp[k], fs); }
+            uniq.insert(fs);
+        });
+        if (kind == 0) { if (!uniq.empty()) lines.push_back("1"); return true; }
+        for (const std::string& f : uniq) {
+            if (kind == 1) { lines.push_back(f); continue; }
+            auto it = relations.find(f);
+            if (it == relations.end()) continue;
+            std::set<uint64_t> nodes;
+            for (auto& kv : it->second) nodes.insert(kv.second.node_id);
+            for (uint64_t nid : nodes) lines.push_back(std::to_string(nid) + "|" + f);
+        }
+        std::sort(lines.begin(), lines.end());
+        return true;
+    }
     // router.rs:439-479  (returns 1 removed, 0 not removed, -1 invalid filter on the prune path)
     int remove(std::string_view filter, std::string_view client, uint64_t id_tag) {
         auto it = relations.find(std::string(filter));
@@ -624,6 +652,15 @@ int32_t orc_router_add_full(void* r, const char* f, uint32_t flen, const char* c
 int64_t orc_router_match_full(void* r, const char* s, uint32_t len, uint64_t pub_node, const char* pub_client, uint32_t pclen, uint64_t pub_tag, char* out, uint64_t cap) {
     std::vector<std::string> lines;
     if (!static_cast<Router*>(r)->matches_full(std::string_view(s, len), pub_node, std::string_view(pub_client, pclen), pub_tag, lines)) return -1;
+    std::string all;
+    for (size_t i = 0; i < lines.size(); ++i) { if (i) all += '\n'; all += lines[i]; }
+    if (all.size() <= cap) std::memcpy(out, all.data(), all.size());
+    return static_cast<int64_t>(all.size());
+}
+// canonical text of a secondary reader (Router::readers) into out; returns needed bytes, or -1 for an invalid topic
+int64_t orc_router_readers(void* r, const char* s, uint32_t len, int32_t kind, char* out, uint64_t cap) {
+    std::vector<std::string> lines;
+    if (!static_cast<Router*>(r)->readers(std::string_view(s, len), kind, lines)) return -1;
     std::string all;
     for (size_t i = 0; i < lines.size(); ++i) { if (i) all += '\n'; all += lines[i]; }
     if (all.size() <= cap) std::memcpy(out, all.data(), all.size());

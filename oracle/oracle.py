@@ -77,6 +77,7 @@ def lib():
         "orc_retain_match_batch": (C.c_double, [vp, vp, vp, u64, C.c_int, vp, vp, vp, P(Counters)]),
         "orc_hardware_threads": (i32, []),
         "orc_numa_interleave": (i32, [i32]),
+        "orc_router_readers": (i64, [vp, cp, u32, i32, vp, u64]),
         "orc_router_churn": (C.c_double, [vp, vp, vp, vp, u64]),
     }
     for name, (res, args) in sig.items():
@@ -260,6 +261,20 @@ class Router:
                 return None
             if n <= cap:
                 return sorted(out[i] for i in range(n))
+            cap = int(n)
+
+    def readers(self, topic, kind: int):
+        """Secondary readers, canonical sorted lines: kind 0 _has_matches (["1"] or []), 1 _get_routes (unique matched filters),
+        2 get ("node|filter").  None for an invalid topic."""
+        t = _b(topic)
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            n = lib().orc_router_readers(self._h, t, len(t), kind, buf, cap)
+            if n < 0:
+                return None
+            if n <= cap:
+                return buf.raw[:n].decode().split("\n") if n else []
             cap = int(n)
 
     def churn(self, blob, offs, vals) -> float:

@@ -144,6 +144,8 @@ SIGNATURES = {
     "gmr_topics": (C.c_int64, [_vp]),
     "gmr_routes": (C.c_int64, [_vp]),
     "gmr_matches_batch": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _P(_u64), _P(_u64), _vp]),
+    "gmr_matched_filters_batch": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
+    "gmr_filter": (_i32, [_vp, _u32, _P(_cp), _P(_u32), _vp, _u32, _P(_u32)]),
     "gmr_relation": (_i32, [_vp, _u32, _P(_cp), _P(_u32), _P(_cp), _P(_u32)]),
     "gm_tokenize_batch": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gm_get_stats": (_i32, [_vp, _P(GmStats)]),

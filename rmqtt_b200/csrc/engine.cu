@@ -164,7 +164,7 @@ struct gm_engine {
     DevBuf d_comm, d_part;
     unsigned long long* h_comm = nullptr;   // pinned [2 * world + 64]
     // tuning / diagnostics knobs, read from the environment once at creation
-    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 131072; bool small_graphs = true; bool retain_stats = false; } knobs;
+    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 131072; bool small_graphs = true; bool retain_stats = false; bool gather_bcast = false; } knobs;
     void read_knobs() {
         if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { knobs.site_bits = a; knobs.sub_bits = b; } }
         if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
@@ -172,6 +172,7 @@ struct gm_engine {
         if (const char* ev = getenv("GM_TILE_CHUNK")) { int v = atoi(ev); if (v >= 1 && v <= 1024) knobs.tile_chunk = static_cast<u32>(v); }
         if (getenv("GM_DIAG_NO_PUBLISH")) knobs.diag_flags |= MP_DIAG_NO_PUBLISH;
         if (const char* ev = getenv("GM_TOK_BULK")) knobs.tok_bulk = atoi(ev) != 0;
+        if (const char* ev = getenv("GM_ALLGATHERV")) knobs.gather_bcast = std::string(ev) == "bcast";
         if (const char* ev = getenv("GM_SMALL_GRAPHS")) knobs.small_graphs = atoi(ev) != 0;
         if (const char* ev = getenv("GM_E2E_CHUNK")) { int v = atoi(ev); if (v >= 1024) knobs.e2e_chunk = static_cast<u32>(v); }
     }
@@ -1183,6 +1184,33 @@ int32_t gmr_matches_batch(gm_router* r, const gm_id* publishers, const char* blo
     return GM_OK;
 }
 
+int32_t gmr_matched_filters_batch(gm_router* r, const char* blob, const uint32_t* offs, uint64_t n, gm_span* out_spans, uint32_t* out_filters, uint64_t cap_filters,
+                                  uint64_t* needed, int32_t* status) {
+    if (!r || (n && (!offs || !out_spans || !status))) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    std::vector<gm_span> spans; std::vector<uint32_t> fl; std::vector<int32_t> st;
+    const int32_t rc = r->impl.matched_filters_batch(blob, offs, n, spans, fl, st);
+    if (rc != GM_OK) return rc;
+    if (needed) *needed = fl.size();
+    std::copy(st.begin(), st.end(), status);
+    if (fl.size() > cap_filters) { g_err = "gmr_matched_filters_batch: output too small"; return GM_ERR_CAPACITY; }
+    std::copy(spans.begin(), spans.end(), out_spans);
+    std::copy(fl.begin(), fl.end(), out_filters);
+    return GM_OK;
+}
+
+int32_t gmr_filter(gm_router* r, uint32_t filter_idx, const char** filter, uint32_t* filter_len, uint64_t* out_node_ids, uint32_t cap_nodes, uint32_t* n_nodes) {
+    if (!r || !filter || !filter_len) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(r->impl.mu);
+    const std::string* f;
+    std::vector<uint64_t> nodes;
+    if (!r->impl.filter(filter_idx, &f, nodes)) return GM_ERR_INVALID_ARG;
+    *filter = f->data(); *filter_len = static_cast<uint32_t>(f->size());
+    if (n_nodes) *n_nodes = static_cast<uint32_t>(nodes.size());
+    if (out_node_ids) for (uint32_t k = 0; k < nodes.size() && k < cap_nodes; ++k) out_node_ids[k] = nodes[k];
+    return GM_OK;
+}
+
 int32_t gmr_relation(gm_router* r, uint32_t handle, const char** filter, uint32_t* filter_len, const char** client, uint32_t* client_len) {
     if (!r || !filter || !filter_len || !client || !client_len) return GM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(r->impl.mu);
@@ -1283,19 +1311,45 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
     for (u32 r = 0; r < W; ++r) { sizes[2 * r] = e->h_comm[2 * r]; sizes[2 * r + 1] = e->h_comm[2 * r + 1]; K += sizes[2 * r]; M += sizes[2 * r + 1]; }
     if (M > 0xFFFFFFFFull) { g_err = "gathered match lists exceed 2^32 ids: split the batch"; return GM_ERR_TOO_LARGE; }
     if (K > cap_topics || M > cap_ids) { g_err = "gm_allgatherv_device: output too small (sizes[] holds what every rank contributes)"; return GM_ERR_CAPACITY; }
-    // 2. one grouped launch: every rank broadcasts its three arrays straight out of the buffers the match kernels wrote
-    NCCL_TRY(nc.GroupStart());
+    // 2. one grouped launch, straight out of the buffers the match kernels wrote.  Default: point-to-point (every rank sends
+    //    its three arrays to every peer and receives theirs — each pair has its own NVSwitch path); GM_ALLGATHERV=bcast
+    //    selects one ncclBroadcast per (rank, array) instead (A/B, profiles/).
     u64 ko = 0, mo = 0;
-    for (u32 r = 0; r < W; ++r) {
-        const u64 kr = sizes[2 * r], mr = sizes[2 * r + 1];
-        if (kr) {
-            NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_index) : d_all_index + ko, d_all_index + ko, kr, ncclUint32, static_cast<int>(r), e->comm, s));
-            NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_spans) : d_all_spans + ko, d_all_spans + ko, kr, ncclUint64, static_cast<int>(r), e->comm, s));
+    std::vector<u64> kof(W + 1, 0), mof(W + 1, 0);
+    for (u32 r = 0; r < W; ++r) { kof[r + 1] = kof[r] + sizes[2 * r]; mof[r + 1] = mof[r] + sizes[2 * r + 1]; }
+    (void)ko; (void)mo;
+    if (e->knobs.gather_bcast) {
+        NCCL_TRY(nc.GroupStart());
+        for (u32 r = 0; r < W; ++r) {
+            const u64 kr = sizes[2 * r], mr = sizes[2 * r + 1];
+            if (kr) {
+                NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_index) : d_all_index + kof[r], d_all_index + kof[r], kr, ncclUint32, static_cast<int>(r), e->comm, s));
+                NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_spans) : d_all_spans + kof[r], d_all_spans + kof[r], kr, ncclUint64, static_cast<int>(r), e->comm, s));
+            }
+            if (mr) NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_ids) : d_all_ids + mof[r], d_all_ids + mof[r], mr, ncclUint32, static_cast<int>(r), e->comm, s));
         }
-        if (mr) NCCL_TRY(nc.Broadcast(r == R ? static_cast<const void*>(d_ids) : d_all_ids + mo, d_all_ids + mo, mr, ncclUint32, static_cast<int>(r), e->comm, s));
-        ko += kr; mo += mr;
+        NCCL_TRY(nc.GroupEnd());
+    } else {
+        const u64 kR = sizes[2 * R], mR = sizes[2 * R + 1];
+        // own part: device-to-device copies on the same stream
+        if (kR) {
+            CUDA_TRY(cudaMemcpyAsync(d_all_index + kof[R], d_index, kR * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(d_all_spans + kof[R], d_spans, kR * sizeof(gm_span), cudaMemcpyDeviceToDevice, s));
+        }
+        if (mR) CUDA_TRY(cudaMemcpyAsync(d_all_ids + mof[R], d_ids, mR * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+        if (W > 1) {
+            NCCL_TRY(nc.GroupStart());
+            for (u32 d = 1; d < W; ++d) {
+                const u32 to = (R + d) % W, from = (R + W - d) % W;          // staggered pairs: no two ranks target the same peer first
+                if (kR) { NCCL_TRY(nc.Send(d_index, kR, ncclUint32, static_cast<int>(to), e->comm, s)); NCCL_TRY(nc.Send(d_spans, kR, ncclUint64, static_cast<int>(to), e->comm, s)); }
+                if (mR) NCCL_TRY(nc.Send(d_ids, mR, ncclUint32, static_cast<int>(to), e->comm, s));
+                const u64 kf = sizes[2 * from], mf = sizes[2 * from + 1];
+                if (kf) { NCCL_TRY(nc.Recv(d_all_index + kof[from], kf, ncclUint32, static_cast<int>(from), e->comm, s)); NCCL_TRY(nc.Recv(d_all_spans + kof[from], kf, ncclUint64, static_cast<int>(from), e->comm, s)); }
+                if (mf) NCCL_TRY(nc.Recv(d_all_ids + mof[from], mf, ncclUint32, static_cast<int>(from), e->comm, s));
+            }
+            NCCL_TRY(nc.GroupEnd());
+        }
     }
-    NCCL_TRY(nc.GroupEnd());
     // 3. spans of rank r index rank r's ids: re-base them onto the gathered id array
     if (K) { k_rebase_spans<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint2*>(d_all_spans), d_all, W, static_cast<u32>(K)); e->launches++; }
     e->launches++;
@@ -1435,6 +1489,7 @@ int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value) {
     else if (k == "diag_flags") e->knobs.diag_flags = static_cast<u32>(value);
     else if (k == "tok_bulk") e->knobs.tok_bulk = value != 0;
     else if (k == "small_graphs") e->knobs.small_graphs = value != 0;
+    else if (k == "gather_bcast") e->knobs.gather_bcast = value != 0;
     else if (k == "retain_stats") e->knobs.retain_stats = value != 0;
     else if (k == "e2e_chunk" && value >= 1024) e->knobs.e2e_chunk = static_cast<u32>(value);
     else return GM_ERR_INVALID_ARG;

@@ -13,6 +13,8 @@ std::string ckey(uint64_t node, const std::string& client) { std::string k = std
 std::string ikey(uint64_t node, const std::string& client, uint64_t tag) { std::string k = ckey(node, client); k.push_back('\0'); k += std::to_string(tag); return k; }
 }  // namespace
 
+#define R_TRY0(expr) do { int32_t _rc = (expr); if (_rc != GM_OK) return _rc; } while (0)
+
 GpuRouter::~GpuRouter() {
     for (Dev* d : {&d_rels_, &d_blob_, &d_offs_, &d_spans_, &d_status_, &d_ids_, &d_needed_, &d_pubs_, &d_ospans_, &d_handles_, &d_extras_, &d_subs_})
         if (d->p) cudaFree(d->p);
@@ -107,6 +109,51 @@ bool GpuRouter::relation(uint32_t handle, const std::string** filter, const std:
     if (handle >= by_handle_.size() || !by_handle_[handle].live) return false;
     *filter = &filter_names_[by_handle_[handle].filter_idx];
     *client = &by_handle_[handle].client;
+    return true;
+}
+
+int32_t GpuRouter::matched_filters_batch(const char* blob, const uint32_t* offs, uint64_t n, std::vector<gm_span>& spans, std::vector<uint32_t>& filters,
+                                         std::vector<int32_t>& status) {
+    spans.assign(n, gm_span{0, 0}); status.assign(n, 0); filters.clear();
+    if (n == 0) return GM_OK;
+    std::vector<gm_span> dsp(n);
+    std::vector<gm_desc> descs(std::max<uint64_t>(64, 8 * n));
+    uint64_t needed = 0;
+    for (;;) {
+        const int32_t rc = gm_match_batch_desc(e_, blob, offs, n, dsp.data(), descs.data(), descs.size(), &needed, status.data());
+        if (rc == GM_ERR_CAPACITY) { descs.resize(needed + 64); continue; }
+        if (rc != GM_OK) return rc;
+        break;
+    }
+    gm_values vv{};
+    R_TRY0(gm_values_view(e_, &vv));
+    for (uint64_t i = 0; i < n; ++i) {
+        const size_t begin = filters.size();
+        if (status[i] == 0) {
+            for (uint32_t k = 0; k < dsp[i].cnt; ++k) {
+                const gm_desc& d = descs[dsp[i].off + k];
+                uint32_t h;                                                   // any member of the set names the filter
+                if (d.cnt == 1) h = d.ref;
+                else if (d.cnt == 0xFFFFu) h = vv.values[vv.ranges[d.ref].off];
+                else h = vv.values[d.ref];
+                if (h < by_handle_.size()) filters.push_back(by_handle_[h].filter_idx);
+            }
+            std::sort(filters.begin() + begin, filters.end());                 // .unique(): a literal '+' / '#' topic level visits a wildcard child twice
+            filters.erase(std::unique(filters.begin() + begin, filters.end()), filters.end());
+        }
+        spans[i] = gm_span{static_cast<uint32_t>(begin), static_cast<uint32_t>(filters.size() - begin)};
+    }
+    return GM_OK;
+}
+
+bool GpuRouter::filter(uint32_t fi, const std::string** name, std::vector<uint64_t>& node_ids) const {
+    if (fi >= filter_names_.size()) return false;
+    *name = &filter_names_[fi];
+    node_ids.clear();
+    auto it = relations_.find(fi);
+    if (it != relations_.end()) for (const auto& kv : it->second) node_ids.push_back(by_handle_[kv.second].id.node_id);
+    std::sort(node_ids.begin(), node_ids.end());
+    node_ids.erase(std::unique(node_ids.begin(), node_ids.end()), node_ids.end());
     return true;
 }
 

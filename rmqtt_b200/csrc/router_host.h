@@ -42,6 +42,10 @@ class GpuRouter {
     int32_t matches_batch(const gm_id* publishers, const char* blob, const uint32_t* offs, uint64_t n, std::vector<gm_span>& spans,
                           std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids, std::vector<int32_t>& status);
     bool relation(uint32_t handle, const std::string** filter, const std::string** client) const;
+    // unique matched filters per topic, through the engine's descriptor mode (router.rs:139-158, 315-363, 522-546)
+    int32_t matched_filters_batch(const char* blob, const uint32_t* offs, uint64_t n, std::vector<gm_span>& spans, std::vector<uint32_t>& filters,
+                                  std::vector<int32_t>& status);
+    bool filter(uint32_t filter_idx, const std::string** name, std::vector<uint64_t>& node_ids) const;
     std::mutex mu;
 
   private:

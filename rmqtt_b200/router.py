@@ -132,5 +132,55 @@ class GpuRouter:
             out.append(lst)
         return out
 
+    # ---- secondary readers (router.rs:139-158, 522-546): unique matched filters through the engine's descriptor mode ----
+    def matched_filters_batch(self, topics):
+        """-> per topic the sorted list of unique matched filter strings, or None for an invalid topic."""
+        blob, offs = pack(topics)
+        n = len(topics)
+        spans = np.zeros((n, 2), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        cap = max(64, 8 * n)
+        while True:
+            fl = np.zeros(cap, dtype=np.uint32)
+            need = C.c_uint64(0)
+            rc = self._lib.gmr_matched_filters_batch(self._h, blob.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), n, spans.ctypes.data_as(C.c_void_p),
+                                                     fl.ctypes.data_as(C.c_void_p), cap, C.byref(need), status.ctypes.data_as(C.c_void_p))
+            if rc == N.GM_ERR_CAPACITY:
+                cap = int(need.value) + 16
+                continue
+            self._check(rc)
+            break
+        out = []
+        for i in range(n):
+            out.append(None if status[i] != 0 else [int(x) for x in fl[int(spans[i, 0]):int(spans[i, 0] + spans[i, 1])]])
+        return out
+
+    def _filter(self, idx: int):
+        f, fl, nn = C.c_char_p(), C.c_uint32(0), C.c_uint32(0)
+        nodes = np.zeros(64, dtype=np.uint64)
+        self._check(self._lib.gmr_filter(self._h, idx, C.byref(f), C.byref(fl), nodes.ctypes.data_as(C.c_void_p), 64, C.byref(nn)))
+        return C.string_at(f, fl.value).decode(), [int(x) for x in nodes[:min(64, nn.value)]]
+
+    def has_matches(self, topic):
+        """DefaultRouter::_has_matches (router.rs:139-142)."""
+        m = self.matched_filters_batch([topic])[0]
+        return None if m is None else len(m) > 0
+
+    def get_routes(self, topic, node_id: int):
+        """DefaultRouter::_get_routes (router.rs:145-158): Route{this node, filter} per unique matched filter."""
+        m = self.matched_filters_batch([topic])[0]
+        return None if m is None else sorted((node_id, self._filter(i)[0]) for i in m)
+
+    def get(self, topic):
+        """Router::get (router.rs:522-546): Route{node, filter} per unique matched filter and distinct node id among its relations."""
+        m = self.matched_filters_batch([topic])[0]
+        if m is None:
+            return None
+        out = []
+        for i in m:
+            f, nodes = self._filter(i)
+            out += [(nid, f) for nid in nodes]
+        return sorted(out)
+
     def matches(self, id: Id, topic):
         return self.matches_batch([topic], [id])[0]

@@ -131,3 +131,30 @@ def test_v5_per_client_dedup_on_the_device_and_its_host_fallback(n_clients, per_
             else:
                 lines.append(f"3|{x.node_id}|{x.topic_filter}|{x.client_id}")
         assert sorted(lines) == want, t
+
+
+def test_secondary_readers_through_descriptor_mode():
+    """_has_matches / _get_routes / Router::get (router.rs:139-158, 522-546) answered by the engine (descriptor mode: one
+    descriptor per matched filter), against the oracle's restatement — no second CPU trie."""
+    rng = random.Random(77)
+    r, o = GpuRouter(), orc.Router()
+    clients = [Id(rng.randint(1, 4), f"c{k}", 100 + k) for k in range(30)]
+    rel = 0
+    for _ in range(600):
+        f = rand_filter(rng, 5)
+        cid = rng.choice(clients)
+        rel += 1
+        try:
+            r.add(f, cid)
+        except GpuMqttError:
+            continue
+        assert o.add_full(f, cid.client_id, rel, cid.tag, cid.node_id, False, False, 0, "")
+    topics = [rand_topic(rng, 6) for _ in range(400)] + ["+/a", "a/#", "bad/#/x", "$SYS/x"]
+    for t in topics:
+        want_has, want_routes, want_get = o.readers(t, 0), o.readers(t, 1), o.readers(t, 2)
+        if want_has is None:
+            assert r.has_matches(t) is None and r.get(t) is None, t
+            continue
+        assert r.has_matches(t) == (want_has == ["1"]), t
+        assert [f for _, f in r.get_routes(t, 5)] == want_routes, t
+        assert [f"{n}|{f}" for n, f in r.get(t)] == want_get, t
