@@ -49,6 +49,8 @@ typedef struct gm_config {
 } gm_config;
 
 #define GM_FLAG_MANUAL_FLUSH 1u /* matches do NOT flush pending mutations implicitly (caller fences with gm_flush) */
+#define GM_FLAG_L2_FETCH_32 4u  /* ask the CUDA context for 32-byte L2 fetches (cudaLimitMaxL2FetchGranularity): every hot access of the
+                                   engine is a random 32-byte slot; the default 64-byte fetch wastes half the DRAM traffic.  Context-wide. */
 #define GM_FLAG_HOST_ONLY 2u    /* staging mirror only, no CUDA context: add/remove/stats work, every match returns
                                    GM_ERR_NO_DEVICE (used by the CPU-side tests of the host logic) */
 
@@ -97,6 +99,14 @@ const char* gm_version(void);
  *      Mutations are staged on the host and shipped to HBM by gm_flush (side stream).                     */
 int32_t gm_sub_add(gm_engine* e, const char* filter, uint32_t len, uint32_t value, int32_t* changed);
 int32_t gm_sub_remove(gm_engine* e, const char* filter, uint32_t len, uint32_t value, int32_t* changed);
+/* Further TopicTree<V>s of the broker that are asked on every PUBLISH / SUBSCRIBE — ACL rule trees
+ * (rmqtt-plugins/rmqtt-acl/src/config.rs:291-326, asked at rmqtt-acl/src/lib.rs:225,280), topic-rewrite rules
+ * (rmqtt-topic-rewrite/src/lib.rs:138-155), bridge routing tables — live in the SAME engine as extra trie roots: `tree` 1..4095
+ * names one (0 = the subscription trie; gm_sub_add == gm_sub_add_tree(0)).  A batch may mix rows of different trees
+ * (gm_match_batch_trees / gm_match_args.d_trees): the PUBLISH match and its ACL check ride in one set of launches.
+ * `is_match` (rmqtt/src/trie.rs:138-140) == the row's list is non-empty.  gm_get_stats counts all trees together.          */
+int32_t gm_sub_add_tree(gm_engine* e, uint32_t tree, const char* filter, uint32_t len, uint32_t value, int32_t* changed);
+int32_t gm_sub_remove_tree(gm_engine* e, uint32_t tree, const char* filter, uint32_t len, uint32_t value, int32_t* changed);
 /* n filters at once (cluster restore re-inserts every filter, rmqtt-cluster-raft/src/router.rs:557-561).
  * Invalid filters are skipped; *n_changed = number of inserts that changed the tree.                      */
 int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets /* n+1 */, const uint32_t* values,
@@ -116,6 +126,10 @@ int32_t gm_compact(gm_engine* e);
 int32_t gm_match_batch(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,
                        gm_span* out_spans, uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed,
                        int32_t* status);
+
+/* gm_match_batch with a tree per row: topic i is matched against tree trees[i] (an unknown tree matches nothing). */
+int32_t gm_match_batch_trees(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, const uint32_t* trees, uint64_t n,
+                             gm_span* out_spans, uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed, int32_t* status);
 
 /* Same, with every buffer already in device memory, asynchronous on `stream` (a cudaStream_t).
  * d_needed (device u64) receives the number of ids produced; nothing is copied to the host.            */
@@ -146,6 +160,7 @@ typedef struct gm_match_args {
     gm_span* d_spans; void* d_out; uint64_t cap; uint64_t* d_needed; int32_t* d_status;
     void* stream;
     gm_work* work;                /* optional: exact work counters (instrumented, slower; synchronises the stream) */
+    const uint32_t* d_trees;      /* optional [n]: the tree every row is matched against (0 = the subscription trie), see gm_sub_add_tree */
 } gm_match_args;
 int32_t gm_match_batch_device_ex(gm_engine* e, const gm_match_args* a);
 
@@ -305,7 +320,8 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
  *      trie walk — `no_local` (rmqtt/src/router.rs:184-189), pass-through of shared-group members (router.rs:192-200; the random
  *      pick of one member, :224-238, stays with the caller) and the per-client de-dup of v5 relations with accumulation of
  *      subscription identifiers (rmqtt/src/types.rs:488-506) — for a whole batch, on the match kernels' own device output.     */
-typedef struct gm_rel {           /* one subscription relation, indexed by its handle (the value stored in the trie) */
+typedef struct gm_rel {           /* one subscription relation, indexed by its handle (the value stored in the trie); 24 bytes */
+    uint64_t node_id;             /* Id::node_id of the subscriber (SubRelationsMap is keyed by it, rmqtt/src/types.rs:466) */
     uint32_t client_key;          /* index of the (node id, client id) pair: the v5 de-dup key */
     uint32_t id_idx;              /* index of the subscriber's full Id: no_local compares Ids (types.rs:1746-1757) */
     uint32_t sub_id;              /* v5 subscription identifier, 0 = none */
@@ -314,17 +330,11 @@ typedef struct gm_rel {           /* one subscription relation, indexed by its h
 #define GM_REL_LIVE 1u
 #define GM_REL_V5 2u
 #define GM_REL_NO_LOCAL 4u
-typedef struct gm_rel_extra {     /* a v5 client that matched through MORE THAN ONE filter: its accumulated subscription ids */
-    uint32_t rel_pos;             /* index in d_handles of the client's single surviving relation */
-    uint32_t sub_off, sub_cnt;    /* d_sub_ids[sub_off .. sub_off + sub_cnt) */
-    uint32_t client_key;
-} gm_rel_extra;
 typedef struct gm_rel_out {
-    gm_span* d_spans;             /* [n] per topic: its surviving relation handles in d_handles */
-    uint32_t* d_handles; uint64_t cap_handles;
-    gm_rel_extra* d_extras; uint64_t cap_extras;
+    gm_span* d_spans;             /* [n] per topic: its relations in d_rels */
+    gm_sub_relation* d_rels; uint64_t cap_rels;      /* finished records: node id, handle, group, sub-id range */
     uint32_t* d_sub_ids; uint64_t cap_sub_ids;
-    uint64_t* d_needed;           /* device [3]: handles, extras, sub ids produced (capacity protocol: compare on the host, retry) */
+    uint64_t* d_needed;           /* device [3]: relations, sub ids produced, (unused) — capacity protocol: compare on the host, retry */
     int32_t* d_status;            /* [n]: set to 1 where a topic had more v5 relations than the kernel stages (256): that topic's list is
                                      complete but NOT de-duplicated — the caller finishes it */
 } gm_rel_out;

@@ -22,6 +22,7 @@ GM_MATCH_DESCRIPTORS = 1
 GM_COMM_ID_BYTES = 128
 GM_FLAG_MANUAL_FLUSH = 1
 GM_FLAG_HOST_ONLY = 2
+GM_FLAG_L2_FETCH_32 = 4
 
 
 class GmConfig(C.Structure):
@@ -66,7 +67,7 @@ class GmMatchArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("d_blob", C.c_void_p), ("blob_bytes", C.c_uint64),
                 ("d_offsets", C.c_void_p), ("n_entries", C.c_uint64), ("d_sel", C.c_void_p), ("n", C.c_uint64),
                 ("d_spans", C.c_void_p), ("d_out", C.c_void_p), ("cap", C.c_uint64), ("d_needed", C.c_void_p), ("d_status", C.c_void_p),
-                ("stream", C.c_void_p), ("work", C.POINTER(GmWork))]
+                ("stream", C.c_void_p), ("work", C.POINTER(GmWork)), ("d_trees", C.c_void_p)]
 
 
 class GmLatency(C.Structure):
@@ -105,6 +106,9 @@ SIGNATURES = {
     "gm_version": (_cp, []),
     "gm_sub_add": (_i32, [_vp, _cp, _u32, _u32, _P(_i32)]),
     "gm_sub_remove": (_i32, [_vp, _cp, _u32, _u32, _P(_i32)]),
+    "gm_sub_add_tree": (_i32, [_vp, _u32, _cp, _u32, _u32, _P(_i32)]),
+    "gm_sub_remove_tree": (_i32, [_vp, _u32, _cp, _u32, _u32, _P(_i32)]),
+    "gm_match_batch_trees": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _P(_u64), _vp]),
     "gm_bulk_load": (_i32, [_vp, _vp, _vp, _vp, _u64, _P(_u64)]),
     "gm_flush": (_i32, [_vp]),
     "gm_compact": (_i32, [_vp]),

@@ -101,7 +101,7 @@ struct MatchCtx {
     bool recorded = false, busy = false;
     unsigned long long* h_cur = nullptr;             // pinned: cursor snapshot after every chunk
     DevBuf d_tok, d_tok8, d_meta, d_slow, d_ctrl, d_gstack, d_gpool, d_sort, d_hist;   // kernel scratch
-    DevBuf d_blob, d_offs, d_spans, d_ids, d_status;                                   // staging of host-buffer calls
+    DevBuf d_blob, d_offs, d_spans, d_ids, d_status, d_trees;                          // staging of host-buffer calls
     // small-batch fast path: the whole call (H2D, memsets, 5 kernels, D2H) as ONE CUDA-graph launch (see SmallGraph)
     struct SmallGraph* small[2] = {nullptr, nullptr};
     int init() {
@@ -140,7 +140,7 @@ struct gm_engine {
     u64 ring_n = 0;
     u64 view_epoch = 0;               // bumped by every flush that changed what the kernels see
     // device tables
-    DevBuf d_edges, d_ranges, d_values, d_dict, d_pool, d_cfilter;
+    DevBuf d_edges, d_ranges, d_values, d_dict, d_pool, d_cfilter, d_tree_slots;
     size_t up_ranges = 0, up_values = 0, up_pool = 0, up_edges_slots = 0, up_dict_slots = 0;
     u64 up_values_epoch = 0;
     // flush staging: patches are gathered into PINNED host memory and scattered by kernels on the side stream —
@@ -194,6 +194,7 @@ struct gm_engine {
         v.dict_mask = static_cast<u32>(trie.dict.size() - 1);
         v.root_plus = trie.root_plus; v.root_hash_ref = trie.root_hash_ref; v.root_hash_cnt = trie.root_hash_cnt; v.root_mask = trie.root_mask;
         v.max_depth = trie.max_depth;
+        v.tree_slots = d_tree_slots.as<u32>(); v.n_trees = d_tree_slots.p ? static_cast<u32>(trie.tree_slots.size()) : 0u;
         return v;
     }
 
@@ -361,6 +362,10 @@ struct gm_engine {
             if ((rs = stage_fresh(d_cfilter, trie.cfilter, 0)) != GM_OK) return rs;
             trie.cfilter_dirty = false;
         }
+        if (trie.trees_dirty) {      // root records of the extra trees (ACL rules, rewrite rules, ...): a tiny array, shipped whole
+            if ((rs = stage_fresh(d_tree_slots, trie.tree_slots, 0)) != GM_OK) return rs;
+            trie.trees_dirty = false;
+        }
         trie.root_dirty = false;
         if (stage_used_) {
             CUDA_TRY(d_patch.ensure(stage_used_));
@@ -405,7 +410,8 @@ struct gm_engine {
     // `hdr` (small-batch graphs only): device words {n, blob_bytes} read by the kernels at run time; n is then the CAPACITY.
     int enqueue_match(MatchCtx& c, const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, void* d_ids_, u64 cap_ids,
                       u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool keep_cursor = false, bool desc = false,
-                      const u32* d_sel = nullptr, u64 readable_bytes = 0, const u32* hdr = nullptr, bool timing = true, u32 site_bits_override = 0) {
+                      const u32* d_sel = nullptr, u64 readable_bytes = 0, const u32* hdr = nullptr, bool timing = true, u32 site_bits_override = 0,
+                      const u32* d_trees = nullptr) {
         if (n == 0) { if (d_needed) CUDA_TRY(cudaMemsetAsync(d_needed, 0, sizeof(u64), s)); return GM_OK; }
         if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
@@ -462,6 +468,7 @@ struct gm_engine {
         mp.tv = tv; mp.tok8 = c.d_tok8.as<u32>(); mp.tok = c.d_tok.as<u32>(); mp.meta = c.d_meta.as<u32>(); mp.n = n32; mp.n_ptr = hdr; mp.tok_levels = S;
         mp.spans = reinterpret_cast<uint2*>(d_spans_); mp.out_ids = static_cast<u32*>(d_ids_); mp.out_desc = static_cast<uint2*>(d_ids_); mp.cap_ids = cap_ids;
         mp.status = d_status_;
+        mp.trees = d_trees;
         mp.cursor = &ctrl->cursor; mp.slow_list = c.d_slow.as<u32>(); mp.slow_count = &ctrl->slow_count;
         mp.tile_counter = &ctrl->tile_counter; mp.stats = ctrl->stats;
         mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
@@ -615,13 +622,18 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     for (auto& ev : eng->ev_arena_) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& q : eng->ev_ring) for (auto& ev : q) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaEventRecord(eng->ev_flush, eng->side));
+    // L2 fetch granularity: a miss on one 32-byte sector makes the L2 fetch 64 bytes from HBM by default.  Every hot access
+    // of this engine is a RANDOM 32-byte slot, so the second half of each fetch is wasted DRAM bandwidth; GM_L2_FETCH=32
+    // (or gm_config.flags & GM_FLAG_L2_FETCH_32) asks for 32-byte fetches.  It is a per-context limit, hence opt-in.
+    if (const char* ev = getenv("GM_L2_FETCH")) { const int v = atoi(ev); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(v)); }
+    else if (c.flags & GM_FLAG_L2_FETCH_32) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     if (c.filters_hint) eng->trie.reserve(c.filters_hint);
     *out = eng;
     return GM_OK;
 }
 
 void MatchCtx::destroy() {
-    for (DevBuf* b : {&d_tok, &d_tok8, &d_meta, &d_slow, &d_ctrl, &d_gstack, &d_gpool, &d_sort, &d_hist, &d_blob, &d_offs, &d_spans, &d_ids, &d_status}) b->release();
+    for (DevBuf* b : {&d_tok, &d_tok8, &d_meta, &d_slow, &d_ctrl, &d_gstack, &d_gpool, &d_sort, &d_hist, &d_blob, &d_offs, &d_spans, &d_ids, &d_status, &d_trees}) b->release();
     for (auto& g : small) if (g) { small_graph_destroy(g); g = nullptr; }
     if (sc) cudaStreamDestroy(sc);
     if (s_h2d) cudaStreamDestroy(s_h2d);
@@ -638,7 +650,7 @@ void gm_destroy(gm_engine* e) {
     cudaDeviceSynchronize();
     e->free_retired(true);
     for (MatchCtx* cx : e->all_ctxs()) cx->destroy();
-    for (DevBuf* b : {&e->d_cfilter, &e->d_edges, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_patch, &e->d_rnodes, &e->d_rkids, &e->d_redges,
+    for (DevBuf* b : {&e->d_cfilter, &e->d_tree_slots, &e->d_edges, &e->d_ranges, &e->d_values, &e->d_dict, &e->d_pool, &e->d_patch, &e->d_rnodes, &e->d_rkids, &e->d_redges,
                       &e->d_rvals, &e->d_rfront[0], &e->d_rfront[1], &e->d_rdescs, &e->d_rctl, &e->d_rq, &e->d_rstage[0], &e->d_rstage[1], &e->d_rstage[2],
                       &e->d_rstage[3], &e->d_rstage[4]})
         b->release();
@@ -676,6 +688,24 @@ int32_t gm_sub_remove(gm_engine* e, const char* filter, uint32_t len, uint32_t v
     int st = e->trie.remove(filter, len, value, &ch);
     if (changed) *changed = ch ? 1 : 0;
     return map_parse(st, "gm_sub_remove");
+}
+
+int32_t gm_sub_add_tree(gm_engine* e, uint32_t tree, const char* filter, uint32_t len, uint32_t value, int32_t* changed) {
+    if (!e || (!filter && len) || tree >= HostTrie::MAX_TREES) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    bool ch = false;
+    int st = e->trie.insert(filter, len, value, &ch, tree);
+    if (changed) *changed = ch ? 1 : 0;
+    return map_parse(st, "gm_sub_add_tree");
+}
+
+int32_t gm_sub_remove_tree(gm_engine* e, uint32_t tree, const char* filter, uint32_t len, uint32_t value, int32_t* changed) {
+    if (!e || (!filter && len) || tree >= HostTrie::MAX_TREES) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    bool ch = false;
+    int st = e->trie.remove(filter, len, value, &ch, tree);
+    if (changed) *changed = ch ? 1 : 0;
+    return map_parse(st, "gm_sub_remove_tree");
 }
 
 int32_t gm_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets, const uint32_t* values, uint64_t n, uint64_t* n_changed) {
@@ -720,7 +750,7 @@ static int32_t auto_flush(gm_engine* e, bool need_retained = false) {
 // shared implementation of the device-buffer entry points
 static int32_t match_device_impl(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offs, uint64_t n_entries, const uint32_t* d_sel,
                                  uint64_t n, gm_span* d_spans, void* d_out, uint64_t cap, uint64_t* d_needed, int32_t* d_status, void* stream,
-                                 bool desc, gm_work* work) {
+                                 bool desc, gm_work* work, const uint32_t* d_trees = nullptr) {
     if (!e || (n && (!d_offs || !d_spans || !d_status))) return GM_ERR_INVALID_ARG;
     if (blob_bytes > 0xFFFFFFFFull) { g_err = "topic blob >= 4 GiB"; return GM_ERR_TOO_LARGE; }
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine cannot match: there is no CPU fallback"; return GM_ERR_NO_DEVICE; }
@@ -728,7 +758,8 @@ static int32_t match_device_impl(gm_engine* e, const void* d_blob, uint64_t blob
     { int st = auto_flush(e); if (st != GM_OK) return st; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     std::unique_lock<std::mutex> gd(e->mu_dev);
-    int st = e->enqueue_match(e->devctx, d_blob, blob_bytes, d_offs, n, d_spans, d_out, cap, d_needed, d_status, s, work != nullptr, false, desc, d_sel);
+    int st = e->enqueue_match(e->devctx, d_blob, blob_bytes, d_offs, n, d_spans, d_out, cap, d_needed, d_status, s, work != nullptr, false, desc, d_sel, 0, nullptr, true, 0,
+                              d_trees);
     if (st != GM_OK || !work) return st;
     std::memset(work, 0, sizeof(*work));
     if (n == 0) return GM_OK;
@@ -761,10 +792,11 @@ int32_t gm_match_batch_device_stats(gm_engine* e, const void* d_blob, uint64_t b
 }
 
 int32_t gm_match_batch_device_ex(gm_engine* e, const gm_match_args* a) {
-    if (!a || a->struct_size < sizeof(gm_match_args)) return GM_ERR_INVALID_ARG;
+    if (!a || a->struct_size < offsetof(gm_match_args, d_trees)) return GM_ERR_INVALID_ARG;
     if (a->d_sel && a->n > a->n_entries) return GM_ERR_INVALID_ARG;
     return match_device_impl(e, a->d_blob, a->blob_bytes, a->d_offsets, a->d_sel ? a->n_entries : a->n, a->d_sel, a->n, a->d_spans, a->d_out, a->cap,
-                             a->d_needed, a->d_status, a->stream, (a->flags & GM_MATCH_DESCRIPTORS) != 0, a->work);
+                             a->d_needed, a->d_status, a->stream, (a->flags & GM_MATCH_DESCRIPTORS) != 0, a->work,
+                             a->struct_size >= offsetof(gm_match_args, d_trees) + sizeof(a->d_trees) ? a->d_trees : nullptr);
 }
 
 }  // extern "C"
@@ -784,7 +816,7 @@ struct SmallGraph {
     u64 view_epoch = ~0ull;
     cudaGraphExec_t exec = nullptr;
     char *h_in = nullptr, *h_out = nullptr;
-    size_t in_bytes = 0, out_bytes = 0, off_offs = 0, off_blob = 0, off_spans = 0, off_status = 0, off_out = 0;
+    size_t in_bytes = 0, out_bytes = 0, off_offs = 0, off_trees = 0, off_blob = 0, off_spans = 0, off_status = 0, off_out = 0;
     DevBuf d_in, d_out;
     bool warmed = false;
 };
@@ -797,7 +829,7 @@ static void small_graph_destroy(SmallGraph* g) {
 }
 
 static int small_graph_match(gm_engine* e, MatchCtx& c, std::unique_lock<std::mutex>& gd, const char* blob, const uint32_t* offsets, uint64_t n,
-                             gm_span* out_spans, void* out, size_t elem, uint64_t cap_user, uint64_t* needed, int32_t* status) {
+                             gm_span* out_spans, void* out, size_t elem, uint64_t cap_user, uint64_t* needed, int32_t* status, const uint32_t* trees) {
     const u64 b0 = offsets[0], blob_bytes = offsets[n] - b0;
     int tier;
     if (n <= 64 && blob_bytes <= 8 * 1024) tier = 0;
@@ -807,7 +839,7 @@ static int small_graph_match(gm_engine* e, MatchCtx& c, std::unique_lock<std::mu
     if (!g) {
         g = new SmallGraph();
         g->cap_n = tier == 0 ? 64u : 2048u; g->cap_blob = tier == 0 ? 8u * 1024u : 192u * 1024u; g->cap_out = tier == 0 ? 4096u : 128u * 1024u;
-        g->off_offs = 16; g->off_blob = (g->off_offs + (g->cap_n + 1) * sizeof(u32) + 255) & ~size_t(255);
+        g->off_offs = 16; g->off_trees = g->off_offs + (g->cap_n + 1) * sizeof(u32); g->off_blob = (g->off_trees + g->cap_n * sizeof(u32) + 255) & ~size_t(255);
         g->in_bytes = g->off_blob + g->cap_blob + 32;
         g->off_spans = 16; g->off_status = g->off_spans + g->cap_n * sizeof(gm_span); g->off_out = (g->off_status + g->cap_n * sizeof(int32_t) + 255) & ~size_t(255);
         g->out_bytes = g->off_out + static_cast<size_t>(g->cap_out) * 8;
@@ -823,7 +855,7 @@ static int small_graph_match(gm_engine* e, MatchCtx& c, std::unique_lock<std::mu
         char* dout = static_cast<char*>(g->d_out.p);
         return e->enqueue_match(c, di + g->off_blob, g->cap_blob, reinterpret_cast<const u32*>(di + g->off_offs), g->cap_n, reinterpret_cast<gm_span*>(dout + g->off_spans),
                                 dout + g->off_out, g->cap_out, reinterpret_cast<u64*>(dout), reinterpret_cast<int32_t*>(dout + g->off_status), s, false, false, desc,
-                                nullptr, g->cap_blob, reinterpret_cast<const u32*>(di), false, 10u);
+                                nullptr, g->cap_blob, reinterpret_cast<const u32*>(di), false, 10u, reinterpret_cast<const u32*>(di + g->off_trees));
     };
     if (!g->warmed) {      // allocate the scratch and set kernel attributes outside any capture: one empty (n = 0) pass
         CUDA_TRY(cudaMemsetAsync(g->d_in.p, 0, g->in_bytes, c.sc));
@@ -856,6 +888,7 @@ static int small_graph_match(gm_engine* e, MatchCtx& c, std::unique_lock<std::mu
     u32* ho = reinterpret_cast<u32*>(g->h_in + g->off_offs);
     for (u64 i = 0; i <= n; ++i) ho[i] = static_cast<u32>(offsets[i] - b0);
     if (blob_bytes) std::memcpy(g->h_in + g->off_blob, blob + b0, blob_bytes);
+    if (trees) std::memcpy(g->h_in + g->off_trees, trees, n * sizeof(u32)); else std::memset(g->h_in + g->off_trees, 0, n * sizeof(u32));
     CUDA_TRY(cudaStreamWaitEvent(c.sc, e->ev_flush, 0));
     CUDA_TRY(cudaGraphLaunch(g->exec, c.sc));
     CUDA_TRY(cudaEventRecord(c.ev_done, c.sc));
@@ -894,7 +927,7 @@ struct CtxLease {
 
 // shared implementation of the host-buffer entry points; `elem` = bytes per output element (4: ids, 8: descriptors)
 static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, void* out, size_t elem,
-                               uint64_t cap_ids, uint64_t* needed, int32_t* status) {
+                               uint64_t cap_ids, uint64_t* needed, int32_t* status, const uint32_t* trees = nullptr) {
     if (!e || (n && (!offsets || !out_spans || !status)) || (cap_ids && !out)) return GM_ERR_INVALID_ARG;
     if (needed) *needed = 0;
     if (n == 0) return GM_OK;
@@ -911,7 +944,7 @@ static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* o
     MatchCtx& c = *lease.c;
     // ---- small batches: the whole call as ONE CUDA-graph launch (no per-kernel launch latency) ----
     if (e->knobs.small_graphs) {
-        int st = small_graph_match(e, c, gd, blob, offsets, n, out_spans, out, elem, cap_ids, needed, status);
+        int st = small_graph_match(e, c, gd, blob, offsets, n, out_spans, out, elem, cap_ids, needed, status, trees);
         if (st != GM_SMALL_NOT_APPLICABLE) return st;       // (gd was released inside while waiting)
         if (!gd.owns_lock()) gd.lock();
     }
@@ -920,6 +953,7 @@ static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* o
     CUDA_TRY(c.d_spans.ensure(n * sizeof(gm_span)));
     CUDA_TRY(c.d_status.ensure(n * sizeof(int32_t)));
     CUDA_TRY(c.d_ids.ensure(std::max<u64>(cap_ids, 1) * elem));
+    if (trees) { CUDA_TRY(c.d_trees.ensure(n * sizeof(u32))); CUDA_TRY(cudaMemcpyAsync(c.d_trees.p, trees, n * sizeof(u32), cudaMemcpyHostToDevice, c.s_h2d)); }
     // Pipelined in chunks over three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of
     // chunk c.  All chunks share one bump cursor, so the output of chunk c is the contiguous range
     // [cursor after c-1, cursor after c) and can be copied out as soon as that chunk's kernels finished.
@@ -937,7 +971,8 @@ static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* o
         const u64 c0 = k * chunk, c1 = std::min<u64>(n, c0 + chunk);
         CUDA_TRY(cudaStreamWaitEvent(c.sc, c.ev_h2d[k], 0));
         int st = e->enqueue_match(c, c.d_blob.p, offsets[c1], c.d_offs.as<u32>() + c0, c1 - c0, c.d_spans.as<gm_span>() + c0, c.d_ids.p, cap_ids, nullptr,
-                                  c.d_status.as<int32_t>() + c0, c.sc, false, k != 0, desc, nullptr, (offsets[c1] + 15) & ~u64(15));
+                                  c.d_status.as<int32_t>() + c0, c.sc, false, k != 0, desc, nullptr, (offsets[c1] + 15) & ~u64(15), nullptr, true, 0,
+                                  trees ? c.d_trees.as<u32>() + c0 : nullptr);
         if (st != GM_OK) return st;
         CUDA_TRY(cudaMemcpyAsync(&c.h_cur[k], &c.d_ctrl.as<Ctrl>()->cursor, sizeof(u64), cudaMemcpyDeviceToHost, c.sc));
         CUDA_TRY(cudaEventRecord(c.ev_comp[k], c.sc));
@@ -967,6 +1002,11 @@ static int32_t match_host_impl(gm_engine* e, const char* blob, const uint32_t* o
 int32_t gm_match_batch(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, uint32_t* out_ids,
                        uint64_t cap_ids, uint64_t* needed, int32_t* status) {
     return match_host_impl(e, blob, offsets, n, out_spans, out_ids, sizeof(uint32_t), cap_ids, needed, status);
+}
+
+int32_t gm_match_batch_trees(gm_engine* e, const char* blob, const uint32_t* offsets, const uint32_t* trees, uint64_t n, gm_span* out_spans, uint32_t* out_ids,
+                             uint64_t cap_ids, uint64_t* needed, int32_t* status) {
+    return match_host_impl(e, blob, offsets, n, out_spans, out_ids, sizeof(uint32_t), cap_ids, needed, status, trees);
 }
 
 int32_t gm_match_batch_desc(gm_engine* e, const char* blob, const uint32_t* offsets, uint64_t n, gm_span* out_spans, gm_desc* out_descs,
@@ -1171,17 +1211,9 @@ int32_t gmr_matches_batch(gm_router* r, const gm_id* publishers, const char* blo
                           uint64_t* needed_sub_ids, int32_t* status) {
     if (!r || (n && (!offs || !out_spans || !status))) return GM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(r->impl.mu);
-    std::vector<gm_span> spans; std::vector<gm_sub_relation> rels; std::vector<uint32_t> ids; std::vector<int32_t> st;
-    int32_t rc = r->impl.matches_batch(publishers, blob, offs, n, spans, rels, ids, st);
-    if (rc != GM_OK) return rc;
-    if (needed_rels) *needed_rels = rels.size();
-    if (needed_sub_ids) *needed_sub_ids = ids.size();
-    std::copy(st.begin(), st.end(), status);
-    if (rels.size() > cap_rels || ids.size() > cap_sub_ids) { g_err = "gmr_matches_batch: output too small"; return GM_ERR_CAPACITY; }
-    std::copy(spans.begin(), spans.end(), out_spans);
-    std::copy(rels.begin(), rels.end(), out_rels);
-    std::copy(ids.begin(), ids.end(), out_sub_ids);
-    return GM_OK;
+    const int32_t rc = r->impl.matches_batch(publishers, blob, offs, n, out_spans, out_rels, cap_rels, out_sub_ids, cap_sub_ids, needed_rels, needed_sub_ids, status);
+    if (rc == GM_ERR_CAPACITY) g_err = "gmr_matches_batch: output too small";
+    return rc;
 }
 
 int32_t gmr_matched_filters_batch(gm_router* r, const char* blob, const uint32_t* offs, uint64_t n, gm_span* out_spans, uint32_t* out_filters, uint64_t cap_filters,
@@ -1369,8 +1401,8 @@ int32_t gm_relations_expand_device(gm_engine* e, const gm_span* d_spans, const u
     RelParams rp{};
     rp.spans = reinterpret_cast<const uint2*>(d_spans); rp.ids = d_ids; rp.n = static_cast<u32>(n); rp.pubs = d_publishers;
     rp.rels = d_rels; rp.n_rels = static_cast<u32>(n_rels);
-    rp.out_spans = reinterpret_cast<uint2*>(o->d_spans); rp.out_handles = o->d_handles; rp.cap_handles = o->cap_handles;
-    rp.out_extras = o->d_extras; rp.cap_extras = o->cap_extras; rp.out_sub_ids = o->d_sub_ids; rp.cap_sub_ids = o->cap_sub_ids;
+    rp.out_spans = reinterpret_cast<uint2*>(o->d_spans); rp.out_rels = o->d_rels; rp.cap_rels = o->cap_rels;
+    rp.out_sub_ids = o->d_sub_ids; rp.cap_sub_ids = o->cap_sub_ids;
     rp.needed = reinterpret_cast<unsigned long long*>(o->d_needed); rp.status = o->d_status;
     const unsigned grid = static_cast<unsigned>(std::min<u64>((n + 7) / 8, static_cast<u64>(e->num_sms) * 8));
     k_relations<<<grid, 256, 0, s>>>(rp);

@@ -350,11 +350,31 @@ bool HostTrie::add_value(u32 node, u32 value) {
     return ch;
 }
 
-int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed) {
+// Extra trees are children of the global root under a reserved level string that no topic or filter can produce (it
+// contains '/', and levels are what is left after splitting on '/').  Nothing can walk into them from tree 0; the kernels
+// start a row's walk at its tree's root record (TrieView::tree_slots).
+u32 HostTrie::tree_root(u32 tree, bool create) {
+    if (tree == 0) return 0;
+    if (tree < tree_nodes_.size() && tree_nodes_[tree]) return tree_nodes_[tree];
+    if (!create || tree >= MAX_TREES) return 0;
+    char name[32];
+    const int nl = snprintf(name, sizeof name, "/tree/%u", tree);
+    const u32 tok = intern(name, static_cast<u32>(nl), true);
+    const u32 slot = find_edge(0, tok, nodes_[0].wtag);
+    const u32 id = slot == NOSLOT ? add_edge(0, tok) : edges[slot].child;
+    if (tree_nodes_.size() <= tree) tree_nodes_.resize(tree + 1, 0u);
+    tree_nodes_[tree] = id;
+    tree_of_token_[tok] = tree;
+    trees_dirty = true;
+    return id;
+}
+
+int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed, u32 tree) {
     if (changed) *changed = false;
+    if (tree >= MAX_TREES) return PARSE_INVALID;
     int st = parse(filter, len, true, scratch_toks_);
     if (st != PARSE_OK) return st;
-    u32 node = 0, tag = 0;     // the window tag of a node travels in its record (mask word): no lookup in nodes_ per level
+    u32 node = tree_root(tree, true), tag = nodes_[node].wtag;     // the window tag of a node travels in its record (mask word): no lookup in nodes_ per level
     for (u32 tok : scratch_toks_) {
         u32 slot = find_edge(node, tok, tag);
         if (slot == NOSLOT) { node = add_edge(node, tok); tag = nodes_[node].wtag; }
@@ -419,11 +439,13 @@ u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* valu
     return changed;
 }
 
-int HostTrie::remove(const char* filter, u32 len, u32 value, bool* changed) {
+int HostTrie::remove(const char* filter, u32 len, u32 value, bool* changed, u32 tree) {
     if (changed) *changed = false;
     int st = parse(filter, len, false, scratch_toks_);
     if (st != PARSE_OK) return st;
-    u32 node = 0, tag = 0;
+    u32 node = tree_root(tree, false);
+    if (tree && !node) return PARSE_OK;              // no such tree: nothing to remove
+    u32 tag = nodes_[node].wtag;
     for (u32 tok : scratch_toks_) {
         if (tok == TOK_UNKNOWN) return PARSE_OK;
         u32 slot = find_edge(node, tok, tag);
@@ -509,11 +531,15 @@ void HostTrie::compact(const std::vector<u32>* keep, std::vector<u32>* remap) {
         if (n.nvals == 0) continue;
         path.clear();
         for (u32 x = id; x != 0; x = nodes_[x].parent) path.push_back(nodes_[x].token);
+        u32 tree = 0;
+        auto tt = tree_of_token_.find(path.back());
+        if (tt != tree_of_token_.end()) { tree = tt->second; path.pop_back(); }      // the reserved root level of an extra tree
+        if (path.empty()) continue;
         f.clear();
         for (size_t k = path.size(); k-- > 0;) { f += tok_str[path[k]]; if (k) f += '/'; }
         bool ch;
-        if (n.nvals == 1) fresh.insert(f.data(), static_cast<u32>(f.size()), n.v0, &ch);
-        else for (u32 v : multi_[id]) fresh.insert(f.data(), static_cast<u32>(f.size()), v, &ch);
+        if (n.nvals == 1) fresh.insert(f.data(), static_cast<u32>(f.size()), n.v0, &ch, tree);
+        else for (u32 v : multi_[id]) fresh.insert(f.data(), static_cast<u32>(f.size()), v, &ch, tree);
     }
     if (remap) remap->assign(next_token_, 0u);
     if (keep)
@@ -577,6 +603,11 @@ bool HostTrie::sync() {
         nodes_[id].dirty = 0;
     }
     dirty_nodes_.clear();
+    if (tree_nodes_.size() > 1) {                     // root records of the extra trees: their slots move with every re-hash
+        std::vector<u32> ts(tree_nodes_.size(), 0xFFFFFFFFu);
+        for (size_t k = 1; k < tree_nodes_.size(); ++k) if (tree_nodes_[k]) ts[k] = nodes_[tree_nodes_[k]].edge_slot;
+        if (ts != tree_slots) { tree_slots.swap(ts); trees_dirty = true; }
+    }
     return true;
 }
 

@@ -42,8 +42,15 @@ class HostTrie {
     explicit HostTrie(u32 max_levels);
 
     // TopicTree::insert / remove.  Return ParseStatus; *changed mirrors the reference's bool.
-    int insert(const char* filter, u32 len, u32 value, bool* changed);
-    int remove(const char* filter, u32 len, u32 value, bool* changed);
+    // `tree`: which TopicTree of this engine (0 = the subscription trie).  The reference keeps further, small TopicTree<V>s
+    // that are asked on every PUBLISH / SUBSCRIBE too — ACL rule trees (rmqtt-plugins/rmqtt-acl/src/config.rs:291-326),
+    // topic-rewrite rules, bridge routing tables: they live in the same device tables as extra ROOTS and are matched in
+    // the same batch (every row of a batch names its tree).
+    int insert(const char* filter, u32 len, u32 value, bool* changed, u32 tree = 0);
+    int remove(const char* filter, u32 len, u32 value, bool* changed, u32 tree = 0);
+    static constexpr u32 MAX_TREES = 4096;
+    std::vector<u32> tree_slots{0xFFFFFFFFu};   // device mirror: tree id -> edge slot holding its root record (0xFFFFFFFF = no such tree); [0] unused
+    bool trees_dirty = false;
     // n inserts (invalid filters are skipped); returns how many changed the set.  Same result as one-by-one insert().
     u64 insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n);
     void reserve(u64 n_filters);
@@ -82,7 +89,7 @@ class HostTrie {
     std::vector<u32> dirty_edges, dirty_ranges, dirty_dict;
     bool full_edges = true, full_dict = true;   // table re-hashed / never uploaded: ship whole table
     bool any_dirty() const { return !dirty_nodes_.empty() || !dirty_edges.empty() ||
-                                    !dirty_ranges.empty() || !dirty_dict.empty() || full_edges || full_dict || root_dirty || cfilter_dirty ||
+                                    !dirty_ranges.empty() || !dirty_dict.empty() || full_edges || full_dict || root_dirty || cfilter_dirty || trees_dirty ||
                                     cfilter_rebuild_; }
     bool root_dirty = true;
     u64 garbage_values = 0;
@@ -101,6 +108,9 @@ class HostTrie {
 
   private:
     u32 intern(const char* s, u32 len, bool create);
+    u32 tree_root(u32 tree, bool create);               // node id of an extra tree's root (0 = none)
+    std::vector<u32> tree_nodes_{0u};                    // tree id -> node id
+    std::unordered_map<u32, u32> tree_of_token_;         // reserved level token of a tree root -> tree id
     u32 find_edge(u32 parent, u32 token, u32 wtag) const;   // returns slot index or ~0u; wtag = window tag of `parent`
     u32 add_edge(u32 parent, u32 token);                // creates the child node, returns its id
     bool add_value(u32 node, u32 value);                // BTreeSet::insert on the node's value set

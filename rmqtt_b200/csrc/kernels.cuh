@@ -39,6 +39,7 @@ struct MatchParams {
     const u32* tok8_sorted;   // [n][8] token rows copied into locality order (MP_SORTED_ROWS)
     const u32* meta_sorted;   // [n]
     u32 tile_chunk;           // tiles a CTA takes from the global counter at once (<= 1: one tile per warp per grab)
+    const u32* trees;         // [n] optional: the tree every row is matched against (0 = the subscription trie)
     const u32* n_ptr;         // small-batch graphs: the real batch size lives in device memory (n is then the capacity = row stride of `tok`)
     uint2* out_desc;          // DESCRIPTOR mode: matched value sets (ref, cnt16) per topic instead of expanded ids; spans index this array
     int* status;              // [n] per-topic status (k_tokenize wrote it); the deferred kernel reports GM_ERR_INTERNAL here
@@ -445,6 +446,14 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                 for (int l = 0; l < FAST_L; ++l) s_tok[l][tid] = w[l];
             }
             NodeRec r{0u, tv.root_plus, tv.root_hash_ref, 0u, tv.root_mask, tv.root_hash_cnt};
+            if (p.trees) {                             // an extra tree of the engine: start at ITS root record
+                const u32 tr = p.trees[t];
+                if (tr) {
+                    const u32 slot = tr < tv.n_trees ? tv.tree_slots[tr] : 0xFFFFFFFFu;
+                    r = NodeRec{0u, 0u, 0u, 0u, 0u, 0u};                     // no such tree: nothing can match
+                    if (slot != 0xFFFFFFFFu) { u32 s8[8]; ld256(tv.edges + slot, s8); r = NodeRec{s8[2], s8[3], s8[4], s8[5], s8[6], s8[7]}; }
+                }
+            }
             u32 d = 0, pmask = 0;
             bool droot = (m & META_DOLLAR) != 0;      // `$`-rule: root wildcards skipped (trie.rs:312-318)
             u32 lV = 0, lE = 0, lF = 0;
@@ -684,6 +693,12 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
             };
             {
                 NodeRec r{0u, tv.root_plus, tv.root_hash_ref, 0u, tv.root_mask, tv.root_hash_cnt};
+                const u32 tr = p.trees ? p.trees[t] : 0u;
+                if (tr) {
+                    const u32 slot = tr < tv.n_trees ? tv.tree_slots[tr] : 0xFFFFFFFFu;
+                    r = NodeRec{0u, 0u, 0u, 0u, 0u, 0u};
+                    if (slot != 0xFFFFFFFFu) { u32 s8[8]; ld256(tv.edges + slot, s8); r = NodeRec{s8[2], s8[3], s8[4], s8[5], s8[6], s8[7]}; }
+                }
                 consume(lane == 0, 0u, r, dollar);
             }
             while (stack_n) {

@@ -116,6 +116,8 @@ struct TrieView {
     u32 dict_mask;
     u32 root_plus, root_hash_ref, root_hash_cnt, root_mask;
     u32 max_depth;      // deepest filter in the trie (levels)
+    const u32* tree_slots;  // extra trees of the engine (ACL rules, rewrite rules, ...): tree id -> edge slot of its root record
+    u32 n_trees;            // entries in tree_slots (index 0 unused: tree 0's root record travels above)
 };
 
 // Per-topic word written by the tokeniser: bits 0..23 level count, bit 30 level 0 is Metadata ('$...'),

@@ -16,7 +16,7 @@ std::string ikey(uint64_t node, const std::string& client, uint64_t tag) { std::
 #define R_TRY0(expr) do { int32_t _rc = (expr); if (_rc != GM_OK) return _rc; } while (0)
 
 GpuRouter::~GpuRouter() {
-    for (Dev* d : {&d_rels_, &d_blob_, &d_offs_, &d_spans_, &d_status_, &d_ids_, &d_needed_, &d_pubs_, &d_ospans_, &d_handles_, &d_extras_, &d_subs_})
+    for (Dev* d : {&d_rels_, &d_blob_, &d_offs_, &d_spans_, &d_status_, &d_ids_, &d_needed_, &d_pubs_, &d_ospans_, &d_orels_, &d_subs_})
         if (d->p) cudaFree(d->p);
     if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
 }
@@ -33,9 +33,10 @@ int32_t GpuRouter::ensure(Dev& d, size_t bytes) {
 
 // the device record of a relation: everything k_relations needs to apply router.rs:184-200 and types.rs:488-506
 void GpuRouter::set_rel(uint32_t handle, const Rel& r) {
-    if (rel_host_.size() <= handle) rel_host_.resize(handle + 1, gm_rel{0, 0, 0, 0});
-    gm_rel d{0, 0, 0, 0};
+    if (rel_host_.size() <= handle) rel_host_.resize(handle + 1, gm_rel{0, 0, 0, 0, 0});
+    gm_rel d{0, 0, 0, 0, 0};
     if (r.live) {
+        d.node_id = r.id.node_id;
         d.client_key = intern(client_key_, ckey(r.id.node_id, r.client));
         d.id_idx = intern(id_idx_, ikey(r.id.node_id, r.id.client_id, r.id.tag));
         d.sub_id = r.opts.sub_id;
@@ -158,16 +159,15 @@ bool GpuRouter::filter(uint32_t fi, const std::string** name, std::vector<uint64
 }
 
 // per-client de-dup of ONE topic on the host — only for topics the kernel flagged (more v5 relations than it stages)
-int32_t GpuRouter::host_dedup_topic(const gm_id*, const uint32_t* hs, uint32_t cnt, std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids) {
+int32_t GpuRouter::host_dedup_topic(const gm_sub_relation* in, uint32_t cnt, std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids) {
     struct V5Entry { size_t rel_pos; std::vector<uint32_t> ids; };
     std::unordered_map<uint32_t, V5Entry> v5;                 // client_key -> (its relation, accumulated ids)
     for (uint32_t k = 0; k < cnt; ++k) {
-        const uint32_t h = hs[k];
-        const Rel& r = by_handle_[h];
+        const uint32_t h = in[k].handle;
         const gm_rel& d = rel_host_[h];
-        if (!(d.flags & GM_REL_V5) || (d.flags >> 8)) { rels.push_back(gm_sub_relation{r.id.node_id, h, d.flags >> 8, 0, 0}); continue; }
+        if (!(d.flags & GM_REL_V5) || (d.flags >> 8)) { rels.push_back(gm_sub_relation{d.node_id, h, d.flags >> 8, 0, 0}); continue; }
         auto it = v5.find(d.client_key);
-        if (it == v5.end()) { V5Entry e{rels.size(), {}}; if (d.sub_id) e.ids.push_back(d.sub_id); rels.push_back(gm_sub_relation{r.id.node_id, h, 0, 0, 0}); v5.emplace(d.client_key, std::move(e)); }
+        if (it == v5.end()) { V5Entry e{rels.size(), {}}; if (d.sub_id) e.ids.push_back(d.sub_id); rels.push_back(gm_sub_relation{d.node_id, h, 0, 0, 0}); v5.emplace(d.client_key, std::move(e)); }
         else if (d.sub_id) it->second.ids.push_back(d.sub_id);
     }
     for (auto& kv : v5) {
@@ -181,11 +181,14 @@ int32_t GpuRouter::host_dedup_topic(const gm_id*, const uint32_t* hs, uint32_t c
 #define R_CUDA(expr) do { cudaError_t _ce = (expr); if (_ce != cudaSuccess) return (_ce == cudaErrorNoDevice || _ce == cudaErrorInsufficientDriver) ? GM_ERR_NO_DEVICE : GM_ERR_CUDA; } while (0)
 #define R_TRY(expr) do { int32_t _rc = (expr); if (_rc != GM_OK) return _rc; } while (0)
 
-int32_t GpuRouter::matches_batch(const gm_id* publishers, const char* blob, const uint32_t* offs, uint64_t n, std::vector<gm_span>& spans,
-                                 std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids, std::vector<int32_t>& status) {
-    spans.assign(n, gm_span{0, 0});
-    status.assign(n, 0);
-    rels.clear(); sub_ids.clear();
+// Router::matches for a batch.  Everything per relation happens on the device (engine match, then k_relations writes the
+// finished gm_sub_relation records); the records are copied straight into the caller's arrays.  Returns GM_ERR_CAPACITY with
+// *needed_* set when an output is too small.
+int32_t GpuRouter::matches_batch(const gm_id* publishers, const char* blob, const uint32_t* offs, uint64_t n, gm_span* out_spans,
+                                 gm_sub_relation* out_rels, uint64_t cap_rels, uint32_t* out_sub_ids, uint64_t cap_sub_ids,
+                                 uint64_t* needed_rels, uint64_t* needed_sub_ids, int32_t* status) {
+    if (needed_rels) *needed_rels = 0;
+    if (needed_sub_ids) *needed_sub_ids = 0;
     if (n == 0) return GM_OK;
     using Clk = std::chrono::steady_clock;
     const auto t0 = Clk::now();
@@ -203,15 +206,14 @@ int32_t GpuRouter::matches_batch(const gm_id* publishers, const char* blob, cons
     R_TRY(ensure(d_needed_, 4 * 8)); R_TRY(ensure(d_ospans_, n * 8));
     if (blob_bytes) R_CUDA(cudaMemcpyAsync(d_blob_.p, blob, blob_bytes, cudaMemcpyHostToDevice, s));
     R_CUDA(cudaMemcpyAsync(d_offs_.p, offs, (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    std::vector<uint32_t> pubs;
     if (publishers) {
-        pubs.resize(n);
+        pubs_.resize(n);
         for (uint64_t i = 0; i < n; ++i) {
             auto it = id_idx_.find(ikey(publishers[i].node_id, publishers[i].client_id ? std::string(publishers[i].client_id, publishers[i].client_len) : std::string(), publishers[i].tag));
-            pubs[i] = it == id_idx_.end() ? 0xFFFFFFFFu : it->second;       // an Id no subscriber holds cannot equal any relation's Id
+            pubs_[i] = it == id_idx_.end() ? 0xFFFFFFFFu : it->second;       // an Id no subscriber holds cannot equal any relation's Id
         }
         R_TRY(ensure(d_pubs_, n * 4));
-        R_CUDA(cudaMemcpyAsync(d_pubs_.p, pubs.data(), n * 4, cudaMemcpyHostToDevice, s));
+        R_CUDA(cudaMemcpyAsync(d_pubs_.p, pubs_.data(), n * 4, cudaMemcpyHostToDevice, s));
     }
     if (d_ids_.cap < 4096) R_TRY(ensure(d_ids_, std::max<size_t>(4096, 32 * n) * 4));
     uint64_t need[4] = {0, 0, 0, 0};
@@ -227,59 +229,57 @@ int32_t GpuRouter::matches_batch(const gm_id* publishers, const char* blob, cons
         if (need[3] * 4 <= d_ids_.cap) break;
         R_TRY(ensure(d_ids_, (need[3] + 1024) * 4));
     }
-    // ---- relation expansion on the device
-    R_TRY(ensure(d_handles_, std::max<uint64_t>(need[3], 1) * 4));
-    if (d_extras_.cap < 4096) { R_TRY(ensure(d_extras_, 4096 * sizeof(gm_rel_extra))); R_TRY(ensure(d_subs_, 16384 * 4)); }
-    for (;;) {
-        gm_rel_out o{};
-        o.d_spans = static_cast<gm_span*>(d_ospans_.p); o.d_handles = static_cast<uint32_t*>(d_handles_.p); o.cap_handles = d_handles_.cap / 4;
-        o.d_extras = static_cast<gm_rel_extra*>(d_extras_.p); o.cap_extras = d_extras_.cap / sizeof(gm_rel_extra);
-        o.d_sub_ids = static_cast<uint32_t*>(d_subs_.p); o.cap_sub_ids = d_subs_.cap / 4;
-        o.d_needed = static_cast<uint64_t*>(d_needed_.p); o.d_status = static_cast<int32_t*>(d_status_.p);
-        R_TRY(gm_relations_expand_device(e_, static_cast<const gm_span*>(d_spans_.p), static_cast<const uint32_t*>(d_ids_.p), n, publishers ? static_cast<const uint32_t*>(d_pubs_.p) : nullptr,
-                                         static_cast<const gm_rel*>(d_rels_.p), rel_host_.size(), &o, s));
-        R_CUDA(cudaMemcpyAsync(need, d_needed_.p, 3 * 8, cudaMemcpyDeviceToHost, s));
-        R_CUDA(cudaStreamSynchronize(s));
-        if (need[1] * sizeof(gm_rel_extra) <= d_extras_.cap && need[2] * 4 <= d_subs_.cap) break;      // (handles always fit: at most one per matched id)
-        R_TRY(ensure(d_extras_, (need[1] + 64) * sizeof(gm_rel_extra))); R_TRY(ensure(d_subs_, (need[2] + 64) * 4));
-    }
-    tmp_spans_.resize(n); tmp_ids_.resize(need[0]);
-    std::vector<gm_rel_extra> extras(need[1]);
-    std::vector<uint32_t> xsubs(need[2]);
-    R_CUDA(cudaMemcpyAsync(tmp_spans_.data(), d_ospans_.p, n * 8, cudaMemcpyDeviceToHost, s));
-    R_CUDA(cudaMemcpyAsync(status.data(), d_status_.p, n * 4, cudaMemcpyDeviceToHost, s));
-    if (need[0]) R_CUDA(cudaMemcpyAsync(tmp_ids_.data(), d_handles_.p, need[0] * 4, cudaMemcpyDeviceToHost, s));
-    if (need[1]) R_CUDA(cudaMemcpyAsync(extras.data(), d_extras_.p, need[1] * sizeof(gm_rel_extra), cudaMemcpyDeviceToHost, s));
-    if (need[2]) R_CUDA(cudaMemcpyAsync(xsubs.data(), d_subs_.p, need[2] * 4, cudaMemcpyDeviceToHost, s));
+    // ---- relation expansion on the device: at most one record and one sub id per matched id
+    R_TRY(ensure(d_orels_, std::max<uint64_t>(need[3], 1) * sizeof(gm_sub_relation)));
+    R_TRY(ensure(d_subs_, std::max<uint64_t>(need[3], 1) * 4));
+    gm_rel_out o{};
+    o.d_spans = static_cast<gm_span*>(d_ospans_.p); o.d_rels = static_cast<gm_sub_relation*>(d_orels_.p); o.cap_rels = d_orels_.cap / sizeof(gm_sub_relation);
+    o.d_sub_ids = static_cast<uint32_t*>(d_subs_.p); o.cap_sub_ids = d_subs_.cap / 4;
+    o.d_needed = static_cast<uint64_t*>(d_needed_.p); o.d_status = static_cast<int32_t*>(d_status_.p);
+    R_TRY(gm_relations_expand_device(e_, static_cast<const gm_span*>(d_spans_.p), static_cast<const uint32_t*>(d_ids_.p), n, publishers ? static_cast<const uint32_t*>(d_pubs_.p) : nullptr,
+                                     static_cast<const gm_rel*>(d_rels_.p), rel_host_.size(), &o, s));
+    R_CUDA(cudaMemcpyAsync(need, d_needed_.p, 2 * 8, cudaMemcpyDeviceToHost, s));
+    R_CUDA(cudaMemcpyAsync(status, d_status_.p, n * 4, cudaMemcpyDeviceToHost, s));
+    R_CUDA(cudaMemcpyAsync(out_spans, d_ospans_.p, n * 8, cudaMemcpyDeviceToHost, s));
     R_CUDA(cudaStreamSynchronize(s));
+    bool flagged = false;
+    for (uint64_t i = 0; i < n && !flagged; ++i) flagged = status[i] == 1;
+    if (!flagged) {      // the common case: the device's records ARE the result
+        if (needed_rels) *needed_rels = need[0];
+        if (needed_sub_ids) *needed_sub_ids = need[1];
+        if (need[0] > cap_rels || need[1] > cap_sub_ids) return GM_ERR_CAPACITY;
+        if (need[0]) R_CUDA(cudaMemcpyAsync(out_rels, d_orels_.p, need[0] * sizeof(gm_sub_relation), cudaMemcpyDeviceToHost, s));
+        if (need[1]) R_CUDA(cudaMemcpyAsync(out_sub_ids, d_subs_.p, need[1] * 4, cudaMemcpyDeviceToHost, s));
+        R_CUDA(cudaStreamSynchronize(s));
+        last_device_ms = std::chrono::duration<double, std::milli>(Clk::now() - t0).count();
+        last_host_ms = 0;
+        return GM_OK;
+    }
+    // ---- some topic had more v5 relations than the kernel stages: finish those on the host and re-assemble
     const auto t1 = Clk::now();
-    // ---- host: handles -> gm_sub_relation records (table look-ups only; no hashing, no strings)
-    std::sort(extras.begin(), extras.end(), [](const gm_rel_extra& a, const gm_rel_extra& b) { return a.rel_pos < b.rel_pos; });
-    size_t xi = 0;
+    std::vector<gm_sub_relation> dev(need[0]), rels;
+    std::vector<uint32_t> dsub(need[1]), sub_ids;
+    if (need[0]) R_CUDA(cudaMemcpyAsync(dev.data(), d_orels_.p, need[0] * sizeof(gm_sub_relation), cudaMemcpyDeviceToHost, s));
+    if (need[1]) R_CUDA(cudaMemcpyAsync(dsub.data(), d_subs_.p, need[1] * 4, cudaMemcpyDeviceToHost, s));
+    R_CUDA(cudaStreamSynchronize(s));
     rels.reserve(need[0]);
     for (uint64_t i = 0; i < n; ++i) {
         const size_t begin = rels.size();
-        const uint32_t off = tmp_spans_[i].off, cnt = tmp_spans_[i].cnt;
-        if (status[i] == 1) {                          // flagged by the kernel: complete but not de-duplicated
-            status[i] = 0;
-            R_TRY(host_dedup_topic(publishers ? publishers + i : nullptr, tmp_ids_.data() + off, cnt, rels, sub_ids));
-        } else if (status[i] == 0) {
+        const uint32_t off = out_spans[i].off, cnt = out_spans[i].cnt;
+        if (status[i] == 1) { status[i] = 0; R_TRY(host_dedup_topic(dev.data() + off, cnt, rels, sub_ids)); }
+        else if (status[i] == 0)
             for (uint32_t k = 0; k < cnt; ++k) {
-                const uint32_t h = tmp_ids_[off + k];
-                const gm_rel& d = rel_host_[h];
-                gm_sub_relation sr{by_handle_[h].id.node_id, h, d.flags >> 8, 0, 0};
-                if ((d.flags & GM_REL_V5) && !(d.flags >> 8)) {
-                    while (xi < extras.size() && extras[xi].rel_pos < off + k) ++xi;
-                    if (xi < extras.size() && extras[xi].rel_pos == off + k) {      // matched through several filters: accumulated ids
-                        sr.sub_ids_off = static_cast<uint32_t>(sub_ids.size()); sr.sub_ids_cnt = extras[xi].sub_cnt;
-                        sub_ids.insert(sub_ids.end(), xsubs.begin() + extras[xi].sub_off, xsubs.begin() + extras[xi].sub_off + extras[xi].sub_cnt);
-                    } else if (d.sub_id) { sr.sub_ids_off = static_cast<uint32_t>(sub_ids.size()); sr.sub_ids_cnt = 1; sub_ids.push_back(d.sub_id); }
-                }
+                gm_sub_relation sr = dev[off + k];
+                if (sr.sub_ids_cnt) { const uint32_t so = static_cast<uint32_t>(sub_ids.size()); sub_ids.insert(sub_ids.end(), dsub.begin() + sr.sub_ids_off, dsub.begin() + sr.sub_ids_off + sr.sub_ids_cnt); sr.sub_ids_off = so; }
                 rels.push_back(sr);
             }
-        }
-        spans[i] = gm_span{static_cast<uint32_t>(begin), static_cast<uint32_t>(rels.size() - begin)};
+        out_spans[i] = gm_span{static_cast<uint32_t>(begin), static_cast<uint32_t>(rels.size() - begin)};
     }
+    if (needed_rels) *needed_rels = rels.size();
+    if (needed_sub_ids) *needed_sub_ids = sub_ids.size();
+    if (rels.size() > cap_rels || sub_ids.size() > cap_sub_ids) return GM_ERR_CAPACITY;
+    std::copy(rels.begin(), rels.end(), out_rels);
+    std::copy(sub_ids.begin(), sub_ids.end(), out_sub_ids);
     last_device_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     last_host_ms = std::chrono::duration<double, std::milli>(Clk::now() - t1).count();
     return GM_OK;

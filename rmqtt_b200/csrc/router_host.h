@@ -10,7 +10,7 @@
 //   matches   router.rs:162-248 for a batch of PUBLISHes, ON THE DEVICE: engine match (gm_match_batch_device_ex) ->
 //             k_relations (relations.cuh): no_local (:184-189), shared-group members passed through (:192-200),
 //             v5 per-client de-dup with accumulation of subscription identifiers (types.rs:488-506) -> the host only
-//             turns the surviving handles into gm_sub_relation records.  The router keeps a 16-byte gm_rel record per
+//             receives the finished gm_sub_relation records by DMA.  The router keeps a 24-byte gm_rel record per
 //             handle in HBM (shipped incrementally).  The shared-subscription *choice* is rand::random in the
 //             reference (subscribe.rs:88): members are returned, not chosen.
 #pragma once
@@ -39,8 +39,9 @@ class GpuRouter {
     int32_t remove(const char* filter, uint32_t len, const Id& id, bool* removed);
     int64_t topics() const { return topics_; }                // Router::topics  (router.rs:554-556)
     int64_t routes() const { return routes_; }                // Router::routes
-    int32_t matches_batch(const gm_id* publishers, const char* blob, const uint32_t* offs, uint64_t n, std::vector<gm_span>& spans,
-                          std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids, std::vector<int32_t>& status);
+    int32_t matches_batch(const gm_id* publishers, const char* blob, const uint32_t* offs, uint64_t n, gm_span* out_spans,
+                          gm_sub_relation* out_rels, uint64_t cap_rels, uint32_t* out_sub_ids, uint64_t cap_sub_ids,
+                          uint64_t* needed_rels, uint64_t* needed_sub_ids, int32_t* status);
     bool relation(uint32_t handle, const std::string** filter, const std::string** client) const;
     // unique matched filters per topic, through the engine's descriptor mode (router.rs:139-158, 315-363, 522-546)
     int32_t matched_filters_batch(const char* blob, const uint32_t* offs, uint64_t n, std::vector<gm_span>& spans, std::vector<uint32_t>& filters,
@@ -65,12 +66,13 @@ class GpuRouter {
     uint32_t rel_dirty_lo_ = 0xFFFFFFFFu, rel_dirty_hi_ = 0;           // handles changed since the last upload
     std::unordered_map<std::string, uint32_t> client_key_, id_idx_;    // "node\0client" -> key, "node\0client\0tag" -> idx
     struct Dev { void* p = nullptr; size_t cap = 0; };
-    Dev d_rels_, d_blob_, d_offs_, d_spans_, d_status_, d_ids_, d_needed_, d_pubs_, d_ospans_, d_handles_, d_extras_, d_subs_;
+    Dev d_rels_, d_blob_, d_offs_, d_spans_, d_status_, d_ids_, d_needed_, d_pubs_, d_ospans_, d_orels_, d_subs_;
+    std::vector<uint32_t> pubs_;
     void* stream_ = nullptr;
     int32_t ensure(Dev& d, size_t bytes);
     uint32_t intern(std::unordered_map<std::string, uint32_t>& m, const std::string& k) { return m.emplace(k, static_cast<uint32_t>(m.size())).first->second; }
     void set_rel(uint32_t handle, const Rel& r);
-    int32_t host_dedup_topic(const gm_id* publisher, const uint32_t* hs, uint32_t cnt, std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids);
+    int32_t host_dedup_topic(const gm_sub_relation* in, uint32_t cnt, std::vector<gm_sub_relation>& rels, std::vector<uint32_t>& sub_ids);
 };
 
 }  // namespace gm

@@ -118,6 +118,37 @@ class Engine:
         self._check(self._lib.gm_sub_remove(self._h, b, len(b), value, C.byref(ch)))
         return bool(ch.value)
 
+    # ---- further TopicTree<V>s in the same engine (ACL rule trees, rewrite rules, ...): extra trie roots ------------
+    def add_tree(self, tree: int, filt, value: int) -> bool:
+        b = _b(filt)
+        ch = C.c_int32(0)
+        self._check(self._lib.gm_sub_add_tree(self._h, tree, b, len(b), value, C.byref(ch)))
+        return bool(ch.value)
+
+    def remove_tree(self, tree: int, filt, value: int) -> bool:
+        b = _b(filt)
+        ch = C.c_int32(0)
+        self._check(self._lib.gm_sub_remove_tree(self._h, tree, b, len(b), value, C.byref(ch)))
+        return bool(ch.value)
+
+    def match_batch_trees(self, blob: np.ndarray, offs: np.ndarray, trees: np.ndarray) -> MatchResult:
+        """Row i is matched against tree trees[i] (0 = the subscription trie): mixed batches in one set of launches."""
+        n = len(offs) - 1
+        trees = np.ascontiguousarray(trees, dtype=np.uint32)
+        assert len(trees) == n
+        spans = np.zeros((n, 2), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        cap = max(1024, 32 * n)
+        while True:
+            ids = np.empty(cap, dtype=np.uint32)
+            needed = C.c_uint64(0)
+            rc = self._lib.gm_match_batch_trees(self._h, _vp(blob), _vp(offs), _vp(trees), n, _vp(spans), _vp(ids), cap, C.byref(needed), _vp(status))
+            if rc == N.GM_ERR_CAPACITY:
+                cap = int(needed.value)
+                continue
+            self._check(rc)
+            return MatchResult(spans, ids[:int(needed.value)], status, int(needed.value))
+
     def bulk_load(self, blob: np.ndarray, offs: np.ndarray, values: np.ndarray) -> int:
         assert blob.dtype == np.uint8 and offs.dtype == np.uint32 and values.dtype == np.uint32
         n_changed = C.c_uint64(0)

@@ -265,6 +265,52 @@ def test_acl_rule_tree_shape():
         assert ((got > 0) == (want > 0)).all() and (got == want).all()
 
 
+def test_extra_trees_ride_in_the_same_batch():
+    """SURVEY §8(f) rank 2 as the survey words it: the ACL allow / deny rule trees are EXTRA ROOTS of the same engine
+    (gm_sub_add_tree) and a PUBLISH's subscription match and its two ACL checks are three rows of ONE batch
+    (gm_match_batch_trees) — one set of launches, not one engine and five launches per tree."""
+    rng = random.Random(19)
+    eng = Engine()
+    trees = {0: orc.TopicTree(), 1: orc.TopicTree(), 2: orc.TopicTree(), 7: orc.TopicTree()}
+    v = 0
+    for _ in range(900):
+        f = rand_filter(rng, 4)
+        tr = rng.choice([0, 0, 1, 2, 7])
+        v += 1
+        try:
+            ch = eng.add_tree(tr, f, v) if tr else eng.add(f, v)
+        except GpuMqttError:
+            continue
+        assert ch == trees[tr].insert(f, v)
+    for tr in (1, 2):                                   # root wildcards of an extra tree obey the `$`-rule at THEIR root
+        for f in ("#", "+/x", "$SYS/#"):
+            v += 1
+            assert eng.add_tree(tr, f, v) == trees[tr].insert(f, v)
+    topics = [rand_topic(rng, 5) for _ in range(1500)] + ["$SYS/x", "$SYS", "a/x", "x"]
+
+    def check():
+        rows, row_tree = [], []
+        for t in topics:
+            for tr in (0, 1, 2, 7, 9):                  # 9: a tree that does not exist -> empty list
+                rows.append(t); row_tree.append(tr)
+        tb, to = pack(rows)
+        res = eng.match_batch_trees(tb, to, np.asarray(row_tree, dtype=np.uint32))
+        for i, (t, tr) in enumerate(zip(rows, row_tree)):
+            want = trees[tr].matches(t) if tr in trees else []
+            assert res.sorted_list(i) == (sorted(want) if want is not None else None), (t, tr)
+        # tree 0 through the ordinary entry point is unaffected by its neighbours
+        tb0, to0 = pack(topics)
+        _assert_same(eng.match_batch(tb0, to0), trees[0].match_batch(tb0, to0))
+
+    check()
+    for f, val in (("#", 100001), ("+/x", 100002)):     # mutate an extra tree, flush, re-check; then compact (trees survive)
+        assert eng.add_tree(7, f, val) == trees[7].insert(f, val)
+    assert eng.remove_tree(1, "#", v - 5) == trees[1].remove("#", v - 5)
+    check()
+    eng.compact()
+    check()
+
+
 def test_full_size_properties_c3_shape():
     """Size-independent properties at a large size (no oracle): match counts are invariant under batch order;
     adding a `#` subscriber raises every non-`$` topic's count by exactly one; removing it restores them."""

@@ -270,3 +270,30 @@ def test_child_adds_do_not_recopy_the_value_set_and_churn_is_compacted():
     T = Tables(eng.debug_tables())
     for t in ("pop/x", "pop/x/c7", "pop/x/c199", "pop"):
         assert T.match(t.encode())[0] == tree.matches(t), t
+
+
+def test_extra_trees_do_not_leak_into_the_subscription_trie():
+    """gm_sub_add_tree keeps further TopicTrees as extra roots in the same tables; tree 0 (walked here from the global
+    root by the Python model of the kernels) must not see them, before and after a compaction."""
+    rng = random.Random(23)
+    eng, tree = Engine(host_only=True), orc.TopicTree()
+    v = 0
+    for _ in range(400):
+        f = rand_filter(rng)
+        v += 1
+        try:
+            if rng.random() < 0.5:
+                assert eng.add(f, v) == tree.insert(f, v)
+            else:
+                eng.add_tree(1 + v % 3, f, v)
+        except GpuMqttError:
+            pass
+    for rnd in range(2):
+        T = Tables(eng.debug_tables())
+        for _ in range(300):
+            t = rand_topic(rng)
+            want = tree.matches(t)
+            if want is not None:
+                assert T.match(t.encode())[0] == want, t
+        eng.compact()
+    assert eng.stats()["values"] > tree.values_size()            # the extra trees' values are counted too
