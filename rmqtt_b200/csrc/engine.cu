@@ -497,7 +497,7 @@ struct gm_engine {
     }
 
     // ---- retained lookup: tokenise filters -> frontier BFS (one step kernel per tree level) -> publish ----
-    struct RCtl { unsigned long long grand; unsigned long long stats[2]; u32 err; u32 pad; u32 n_desc[RQ]; u32 counts[RQ]; };   // counts[(max_depth + 3) * RQ] follow
+    struct RCtl { unsigned long long grand; unsigned long long stats[2]; u32 err; u32 pad; u32 n_desc[RQ]; u32 counts[RQ]; };   // counts[(max_depth + 3) * RQ], then claim[max_depth + 3] follow   // counts[(max_depth + 3) * RQ] follow
 
     int enqueue_retain(const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, u32* d_ids_, u64 cap_ids, int32_t* d_status_, cudaStream_t s) {
         std::lock_guard<std::mutex> gd(mu_dev);     // enqueue only; the caller (holding mu_ret) synchronises afterwards without it
@@ -505,7 +505,7 @@ struct gm_engine {
         const u32 nq = static_cast<u32>(n);
         const u32 depth = dev_rview.max_depth;
         const u32 S = depth + 2;                       // the walk reads filter levels pos and pos+1 with pos <= tree depth
-        const size_t ctl_bytes = sizeof(RCtl) + static_cast<size_t>(depth + 3) * RQ * sizeof(u32);
+        const size_t ctl_bytes = sizeof(RCtl) + static_cast<size_t>(depth + 3) * RQ * sizeof(u32) + static_cast<size_t>(depth + 3) * sizeof(u32);
         CUDA_TRY(c.d_tok.ensure(S > TOK8 ? static_cast<size_t>(S) * nq * sizeof(u32) : 256));
         CUDA_TRY(c.d_tok8.ensure(static_cast<size_t>(nq) * TOK8 * sizeof(u32)));
         CUDA_TRY(c.d_meta.ensure(nq * sizeof(u32)));
@@ -540,9 +540,10 @@ struct gm_engine {
         auto krr = knobs.retain_stats ? k_retain_round<true> : k_retain_round<false>;
         kri<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RTask>(), &ctl->counts[0]);
         const int grid = num_sms * 8;
+        const int rgrid = num_sms * 6;            // exactly the resident CTAs (40 registers x 256 threads): tasks are claimed dynamically
         for (u32 lvl = 0; lvl <= depth; ++lvl)
-            krr<<<grid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RTask>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RTask>(),
-                                     &ctl->counts[static_cast<size_t>(lvl + 1) * RQ]);
+            krr<<<rgrid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RTask>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RTask>(),
+                                      &ctl->counts[static_cast<size_t>(lvl + 1) * RQ], &ctl->counts[static_cast<size_t>(depth + 3) * RQ + lvl]);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev_t[2], s));
         k_retain_scan<<<1, 1024, 0, s>>>(qtotal, nq, qbase, reinterpret_cast<uint2*>(d_spans_), &ctl->grand);

@@ -165,7 +165,7 @@ k_retain_init(RetainParams p, RTask* out, u32* n_out) {
 constexpr u32 RLIST = 256;    // = RTASK_CHUNK: at most one survivor per child of the task
 template <bool STATS>
 __global__ void __launch_bounds__(256, 6)
-k_retain_round(RetainParams p, const RTask* __restrict__ in, const u32* __restrict__ n_in_p, RTask* __restrict__ out, u32* n_out) {
+k_retain_round(RetainParams p, const RTask* __restrict__ in, const u32* __restrict__ n_in_p, RTask* __restrict__ out, u32* n_out, u32* __restrict__ claim) {
     static_assert(RLIST >= RTASK_CHUNK, "the survivor list holds one entry per child of a task");
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = lanemask_lt();
     const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -175,7 +175,14 @@ k_retain_round(RetainParams p, const RTask* __restrict__ in, const u32* __restri
     const u32 n_in = queue_prefix(n_in_p, p.cap_items, s_pre);
     const u32 sq = gwarp % RQ;                        // this warp appends to its own slice
     unsigned long long visited = 0, probes = 0;
-    for (u32 ti = gwarp; ti < n_in; ti += nwarps) {
+    // tasks differ in size by two orders of magnitude (1 .. 256 children, 0 .. 3 probe levels below): warps CLAIM them one
+    // at a time from a shared counter instead of taking a fixed stride
+    (void)nwarps;
+    for (;;) {
+        u32 ti = 0;
+        if (lane == 0) ti = atomicAdd(claim, 1u);
+        ti = __shfl_sync(0xFFFFFFFFu, ti, 0);
+        if (ti >= n_in) break;
         const uint4 tw = *reinterpret_cast<const uint4*>(in + queue_locate(s_pre, ti, p.cap_items));
         const u32 q = tw.x, pos = tw.y & 0x3FFFFFFFu, mode = tw.y >> 30, kb = tw.z, kn = tw.w;
         const u32 L = p.qmeta[q] & META_NLEV_MASK;
