@@ -1,11 +1,5 @@
 mkdir -p gpurun_out
-python tools/c4_once.py 2>&1 | grep "kernel ms" > gpurun_out/c4_dyn.txt; cat gpurun_out/c4_dyn.txt
-timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/pytest_gpu6.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu6.txt; tail -16 gpurun_out/pytest_gpu6.txt
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1_c.json 2> gpurun_out/bench_n1_c.err; echo "bench exit $?"; tail -3 gpurun_out/bench_n1_c.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_n1_c.json'))
-for k in ('value','value_descriptor_mode','e2e','c4','relations'):
-    print(k, json.dumps(d.get(k))[:900])
-print('latency', [(r['offered_burst'], round(r['p50_us'],1), round(r['p99_us'],1), int(r['topics_per_s'])) for r in d['latency']['table']])
-PY
+for i in 1 2 3; do timeout 300 python -m pytest tests/test_gpu_batcher.py -m gpu -x -q 2>&1 | tail -15; done > gpurun_out/batcher_repeat2.txt 2>&1
+grep -c " passed" gpurun_out/batcher_repeat2.txt; grep -B2 -A12 "libgpumqtt batcher\|FAILED\|Error" gpurun_out/batcher_repeat2.txt | head -60
+timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python tools/memcheck_workload.py > gpurun_out/memcheck_workload.txt 2>&1; tail -4 gpurun_out/memcheck_workload.txt
+timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python tools/memcheck_workload.py > gpurun_out/racecheck_workload.txt 2>&1; tail -4 gpurun_out/racecheck_workload.txt

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -82,6 +83,10 @@ struct gm_batcher {
             for (;;) {
                 rc = gm_match_batch(e, local.blob.data(), local.offs.data(), n, spans.data(), ids, ids_cap, &needed, status.data());
                 if (rc != GM_ERR_CAPACITY || !grow_ids(needed)) break;
+            }
+            if (rc != GM_OK) {                      // the whole batch failed: every topic gets the error; say why (first few times)
+                static std::atomic<int> shown{0};
+                if (shown.fetch_add(1) < 5) fprintf(stderr, "libgpumqtt batcher: gm_match_batch(%llu topics) failed with %d: %s\n", (unsigned long long)n, rc, gm_last_error(e));
             }
             for (uint64_t i = 0; i < n; ++i) {
                 const int32_t st = rc == GM_OK ? status[i] : rc;

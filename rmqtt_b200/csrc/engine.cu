@@ -104,6 +104,12 @@ struct MatchCtx {
     DevBuf d_blob, d_offs, d_spans, d_ids, d_status, d_trees;                          // staging of host-buffer calls
     // small-batch fast path: the whole call (H2D, memsets, 5 kernels, D2H) as ONE CUDA-graph launch (see SmallGraph)
     struct SmallGraph* small[2] = {nullptr, nullptr};
+    // the scratch pointers a captured graph has baked in: a later, larger call may re-allocate any of them
+    u64 scratch_sig() const {
+        u64 h = 0x9E3779B97F4A7C15ull;
+        for (const DevBuf* b : {&d_tok, &d_tok8, &d_meta, &d_slow, &d_ctrl, &d_gstack, &d_gpool, &d_sort, &d_hist}) h = (h ^ reinterpret_cast<uintptr_t>(b->p)) * 0x100000001B3ull;
+        return h;
+    }
     int init() {
         CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
@@ -164,7 +170,7 @@ struct gm_engine {
     DevBuf d_comm, d_part;
     unsigned long long* h_comm = nullptr;   // pinned [2 * world + 64]
     // tuning / diagnostics knobs, read from the environment once at creation
-    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 131072; bool small_graphs = true; bool retain_stats = false; bool gather_bcast = false; } knobs;
+    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 262144; bool small_graphs = true; bool retain_stats = false; bool gather_bcast = false; } knobs;
     void read_knobs() {
         if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { knobs.site_bits = a; knobs.sub_bits = b; } }
         if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
@@ -814,7 +820,7 @@ int32_t gm_match_batch_device_ex(gm_engine* e, const gm_match_args* a) {
 struct SmallGraph {
     u32 cap_n = 0, cap_blob = 0, cap_out = 0;
     size_t elem = 0;
-    u64 view_epoch = ~0ull;
+    u64 view_epoch = ~0ull, scratch_sig = 0;
     cudaGraphExec_t exec = nullptr;
     char *h_in = nullptr, *h_out = nullptr;
     size_t in_bytes = 0, out_bytes = 0, off_offs = 0, off_trees = 0, off_blob = 0, off_spans = 0, off_status = 0, off_out = 0;
@@ -865,7 +871,13 @@ static int small_graph_match(gm_engine* e, MatchCtx& c, std::unique_lock<std::mu
         CUDA_TRY(cudaStreamSynchronize(c.sc));
         g->warmed = true;
     }
-    if (!g->exec || g->view_epoch != e->view_epoch || g->elem != elem) {
+    if (g->exec && g->scratch_sig != c.scratch_sig()) {      // a larger call re-allocated this context's scratch since the capture:
+        CUDA_TRY(cudaMemsetAsync(g->d_in.p, 0, g->in_bytes, c.sc));   // size it again (empty pass), then re-capture with the new pointers
+        int st = enqueue(c.sc);
+        if (st != GM_OK) return st;
+        CUDA_TRY(cudaStreamSynchronize(c.sc));
+    }
+    if (!g->exec || g->view_epoch != e->view_epoch || g->elem != elem || g->scratch_sig != c.scratch_sig()) {
         cudaGraph_t graph = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(c.sc, cudaStreamCaptureModeRelaxed));
         cudaError_t ce = cudaMemcpyAsync(g->d_in.p, g->h_in, g->in_bytes, cudaMemcpyHostToDevice, c.sc);
@@ -881,7 +893,7 @@ static int small_graph_match(gm_engine* e, MatchCtx& c, std::unique_lock<std::mu
         }
         if (!ok) CUDA_TRY(cudaGraphInstantiate(&g->exec, graph, 0));
         cudaGraphDestroy(graph);
-        g->view_epoch = e->view_epoch; g->elem = elem;
+        g->view_epoch = e->view_epoch; g->elem = elem; g->scratch_sig = c.scratch_sig();
     }
     // fill the pinned in-block: {n, text bytes} | offsets re-based to 0 | text
     u32* hdr = reinterpret_cast<u32*>(g->h_in);

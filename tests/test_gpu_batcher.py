@@ -85,6 +85,18 @@ def test_small_batch_graph_path_equals_pipelined_path_across_flushes():
             c0, i0 = eng.match_batch(sb, so).canonical()
             assert (c1 == c0).all() and (i1 == i0).all() and (d1 == c0).all() and (j1 == i0).all()
             assert (c1 == want["counts"]).all()
+        # a batch beyond the graph tiers takes the pipelined path on the same context and re-allocates its (larger) scratch:
+        # the captured graphs hold the old pointers and must be re-captured (regression: stale scratch after growth)
+        big = (topics * (5 + rnd))[:6000 + 3000 * rnd]
+        bb, bo = pack(big)
+        eng.debug_knob("small_graphs", 1)
+        cb_, ib_ = eng.match_batch(bb, bo).canonical()
+        wb = tree.match_batch(bb, bo)
+        assert (cb_ == wb["counts"]).all()
+        for sz in (1, 64, 700):
+            sb, so = pack(topics[:sz])
+            c1, i1 = eng.match_batch(sb, so).canonical()
+            assert (c1 == tree.match_batch(sb, so)["counts"]).all()
         for k in range(50):                       # mutate, so that the next round runs on a new view
             f = rand_filter(rng, 5)
             try:

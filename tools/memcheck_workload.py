@@ -29,6 +29,14 @@ for rnd in range(4):
     res = eng.match_batch(tb, to)
     for i, t in enumerate(ts):
         assert res.sorted_list(i) == tree.matches(t), t
+    c1, i1 = res.canonical()
+    c2, i2 = eng.match_batch_via_desc(tb, to).canonical()            # descriptor mode (small-batch graph)
+    assert (c1 == c2).all() and (i1 == i2).all()
+    big = ts * 5                                                      # 3000 topics: the pipelined (chunked) path
+    bb, bo = pack(big)
+    rb = eng.match_batch(bb, bo)
+    for i in range(0, len(big), 97):
+        assert rb.sorted_list(i) == tree.matches(big[i])
     fs = [f for f in (rand_filter(rng, 6) for _ in range(300)) if orc.topic_parse(f) is not None]
     fb, fo = pack(fs)
     rr = eng.retain_match_batch(fb, fo)
