@@ -1,5 +1,9 @@
 mkdir -p gpurun_out
-for i in 1 2 3; do timeout 300 python -m pytest tests/test_gpu_batcher.py -m gpu -x -q 2>&1 | tail -15; done > gpurun_out/batcher_repeat2.txt 2>&1
-grep -c " passed" gpurun_out/batcher_repeat2.txt; grep -B2 -A12 "libgpumqtt batcher\|FAILED\|Error" gpurun_out/batcher_repeat2.txt | head -60
-timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python tools/memcheck_workload.py > gpurun_out/memcheck_workload.txt 2>&1; tail -4 gpurun_out/memcheck_workload.txt
-timeout 900 compute-sanitizer --tool racecheck --print-limit 5 python tools/memcheck_workload.py > gpurun_out/racecheck_workload.txt 2>&1; tail -4 gpurun_out/racecheck_workload.txt
+nvidia-smi -L | wc -l
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; echo "bench8 exit $?"; tail -4 gpurun_out/bench_n8.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_n8.json'))
+for k in ('value','value_with_gather','value_descriptor_mode','e2e','multi_gpu','parity_check'):
+    print(k, json.dumps(d.get(k))[:1600])
+PY
