@@ -315,6 +315,7 @@ struct gm_engine {
         v.edge_mask = static_cast<u32>(rtree.redges.size() - 1);
         if (!rtree.rnodes.empty()) { v.root_first_kid = rtree.rnodes[0].first_kid; v.root_nk_flags = rtree.rnodes[0].nkids | (rtree.rnodes[0].flags << 28); }
         v.root_plain_kids = rtree.root_plain_kids; v.root_plain_val_hi = rtree.root_plain_val_hi; v.max_depth = rtree.max_depth;
+        v.n_kids = static_cast<u32>(rtree.rkids.size());
         return v;
     }
 

@@ -85,9 +85,15 @@ __device__ __forceinline__ void emit_desc(const RetainParams& p, u32 sq, u32 q, 
     const u32 at = atomicAdd(p.n_desc + sq, 1u);
     if (at < p.cap_desc) p.descs[static_cast<size_t>(sq) * p.cap_desc + at] = RDesc{q, ref, cnt, kind}; else atomicOr(p.err, 2u);
 }
-__device__ __forceinline__ void push_tasks(const RetainParams& p, RTask* out, u32* n_out, u32 sq, u32 q, u32 pos, u32 mode, u32 kb, u32 kn) {
+// LOCALITY: a task goes into the queue slice of its child block's POSITION IN THE TREE (child blocks are laid out in tree
+// pre-order), not of the warp that produced it.  The next round consumes the slices one after another, so all the tasks
+// that expand the same part of the tree — dozens of filters such as `+/+/+/…` and `reg/+/+/…` cover every site block — run
+// close together in time and share the child blocks and the hash slots of the nodes below through L2, instead of each
+// filter streaming the whole tree from HBM again (measured: 9.75 GB of DRAM reads per C4 batch, L2 hit rate 13 %).
+__device__ __forceinline__ void push_tasks(const RetainParams& p, RTask* out, u32* n_out, u32, u32 q, u32 pos, u32 mode, u32 kb, u32 kn) {
     const u32 nt = (kn + RTASK_CHUNK - 1) / RTASK_CHUNK;
     if (nt == 0) return;
+    const u32 sq = min(RQ - 1u, static_cast<u32>((static_cast<unsigned long long>(kb) * RQ) / max(p.v.n_kids, 1u)));
     const u32 at = atomicAdd(n_out + sq, nt);
     if (at + nt > p.cap_items) { atomicOr(p.err, 1u); return; }
     RTask* dst = out + static_cast<size_t>(sq) * p.cap_items + at;

@@ -61,6 +61,7 @@ struct RetainView {
     u32 root_plain_kids;     // root children whose level does not start with '$' (ordered first)
     u32 root_plain_val_hi;   // rvals[0 .. root_plain_val_hi) = values below those children
     u32 max_depth;
+    u32 n_kids;              // entries in `kids` (child blocks are laid out in tree pre-order: position in `kids` = position in the tree)
 };
 
 // one of 32 bits for a child token: the Bloom mask over a node's children kept in RNode::pad / RKid::pad

@@ -62,7 +62,12 @@ int32_t GpuRouter::add(const char* filter, uint32_t len, const Id& id, const Opt
         if (cit != rit->second.end()) { handle = cit->second; existing = true; }
     }
     if (!existing) {
-        if (!free_handles_.empty()) { handle = free_handles_.back(); }
+        if (!free_handles_.empty()) {
+            // a handle freed by remove() may still be in the DEVICE trie of an engine that only flushes on demand
+            // (GM_FLAG_MANUAL_FLUSH): ship the pending removals before the handle can mean another subscription
+            if (unflushed_removes_) { const int32_t frc = gm_flush(e_); if (frc != GM_OK) return frc; unflushed_removes_ = false; }
+            handle = free_handles_.back();
+        }
         else handle = static_cast<uint32_t>(by_handle_.size());
     }
     // Topic::from_str + topics.insert (router.rs:419-421): an invalid filter is an Err before any state changes
@@ -99,6 +104,7 @@ int32_t GpuRouter::remove(const char* filter, uint32_t len, const Id& id, bool* 
     by_handle_[handle].live = false;
     set_rel(handle, by_handle_[handle]);
     free_handles_.push_back(handle);
+    unflushed_removes_ = true;
     int32_t changed = 0;
     int32_t rc = gm_sub_remove(e_, filter, len, handle, &changed);
     if (rc != GM_OK) return rc;

@@ -58,6 +58,7 @@ class GpuRouter {
     std::unordered_map<std::string, uint32_t> group_index_;                                // "filter\0group" -> 1-based id
     std::vector<Rel> by_handle_;
     std::vector<uint32_t> free_handles_;
+    bool unflushed_removes_ = false;
     int64_t topics_ = 0, routes_ = 0;
     std::vector<gm_span> tmp_spans_;
     std::vector<uint32_t> tmp_ids_;
