@@ -343,6 +343,30 @@ typedef struct gm_rel_out {
 int32_t gm_relations_expand_device(gm_engine* e, const gm_span* d_spans, const uint32_t* d_ids, uint64_t n, const uint32_t* d_publishers,
                                    const gm_rel* d_rels, uint64_t n_rels, const gm_rel_out* out, void* stream);
 
+/* ---- the same exchange FUSED into the match kernels over peer memory (NVLink / NVSwitch): the publish phase of the match writes
+ *      every topic's span, global index and ids directly into the gathered arrays of ALL ranks while the walk of the next tiles is
+ *      still running — no separate collective, no host synchronisation; a one-warp kernel ends the step with the contribution
+ *      counts and a flag barrier.  Layout: every rank owns one device block with a fixed SLAB per rank (slab_topics rows, slab_ids
+ *      ids): rank r's rows are [r * slab_topics, r * slab_topics + counts[2r]) of d_index / d_spans (spans are absolute offsets
+ *      into d_ids, rank r's ids start at r * slab_ids).  Needs peer-to-peer access between the GPUs (CUDA IPC): gm_gather_connect
+ *      returns GM_ERR_COMM where that is unavailable — use gm_allgatherv_device (NCCL) there.  world <= 8.                         */
+#define GM_IPC_HANDLE_BYTES 64
+int32_t gm_gather_create(gm_engine* e, uint32_t world, uint32_t rank, uint64_t slab_topics, uint64_t slab_ids,
+                         uint8_t* out_handle /* [GM_IPC_HANDLE_BYTES]: give it to every other rank */);
+int32_t gm_gather_connect(gm_engine* e, const uint8_t* handles /* [world][GM_IPC_HANDLE_BYTES], rank order */);
+/* match this rank's rows (d_sel / n as in gm_match_args) and publish into every rank's block.  Collective in effect: every rank
+ * calls it once per step; asynchronous on `stream`; when the stream has passed it on a rank, ALL ranks' results are in its block. */
+int32_t gm_match_gather_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offsets, uint64_t n_entries,
+                               const uint32_t* d_sel, uint64_t n, int32_t* d_status, void* stream);
+typedef struct gm_gather_view {
+    const uint32_t* d_index; const gm_span* d_spans; const uint32_t* d_ids;
+    const uint64_t* d_counts;     /* device [world][2]: rows, ids contributed by every rank in the last step */
+    uint64_t slab_topics, slab_ids; uint32_t world, rank;
+} gm_gather_view;
+int32_t gm_gather_get(gm_engine* e, gm_gather_view* out, void* stream);   /* synchronises `stream`; GM_ERR_COMM if a rank missed the barrier */
+int32_t gm_gather_destroy(gm_engine* e);
+int32_t gm_device_read(gm_engine* e, const void* d_src, void* h_dst, uint64_t bytes);   /* convenience: device -> host copy (tests, tools) */
+
 /* ---- tokeniser only (Topic::from_str for a batch) — used by tests to pin the device dictionary.
  *      out_tokens: [max_tok][n] u32 (level-major), out_meta: [n] (bits 0..23 levels, bit 30 '$', bit 31 invalid) */
 int32_t gm_tokenize_batch(gm_engine* e, const char* topics_blob, const uint32_t* topic_offsets, uint64_t n,

@@ -20,6 +20,7 @@ GM_ERR_INTERNAL = -8
 GM_ERR_COMM = -9
 GM_MATCH_DESCRIPTORS = 1
 GM_COMM_ID_BYTES = 128
+GM_IPC_HANDLE_BYTES = 64
 GM_FLAG_MANUAL_FLUSH = 1
 GM_FLAG_HOST_ONLY = 2
 GM_FLAG_L2_FETCH_32 = 4
@@ -92,6 +93,11 @@ class GmBatcherConfig(C.Structure):
                 ("on_match", GM_MATCH_CB), ("user", C.c_void_p)]
 
 
+class GmGatherView(C.Structure):
+    _fields_ = [("d_index", C.c_void_p), ("d_spans", C.c_void_p), ("d_ids", C.c_void_p), ("d_counts", C.c_void_p),
+                ("slab_topics", C.c_uint64), ("slab_ids", C.c_uint64), ("world", C.c_uint32), ("rank", C.c_uint32)]
+
+
 class GmValues(C.Structure):
     _fields_ = [("values", C.c_void_p), ("n_values", C.c_uint64), ("ranges", C.c_void_p), ("n_ranges", C.c_uint64), ("epoch", C.c_uint64)]
 
@@ -128,6 +134,12 @@ SIGNATURES = {
     "gm_batcher_probe": (_i32, [_vp, _vp, _vp, _u64, _u32, _u32, _u32, _P(GmLatency)]),
     "gm_churn_probe": (_i32, [_vp, _vp, _vp, _vp, _u64, C.c_double, _u32, _u32, _P(GmChurn)]),
     "gm_relations_expand_device": (_i32, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _vp, _vp]),
+    "gm_gather_create": (_i32, [_vp, _u32, _u32, _u64, _u64, _vp]),
+    "gm_gather_connect": (_i32, [_vp, _vp]),
+    "gm_match_gather_device": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "gm_gather_get": (_i32, [_vp, _P(GmGatherView), _vp]),
+    "gm_gather_destroy": (_i32, [_vp]),
+    "gm_device_read": (_i32, [_vp, _vp, _vp, _u64]),
     "gm_comm_unique_id": (_i32, [_vp]),
     "gm_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
     "gm_comm_destroy": (_i32, [_vp]),

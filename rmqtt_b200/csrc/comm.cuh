@@ -121,6 +121,28 @@ __global__ void k_rebase_spans(uint2* __restrict__ spans, const unsigned long lo
     if (mo) { uint2 s = spans[i]; s.x += static_cast<u32>(mo); spans[i] = s; }
 }
 
+// End of a fused-gather step: tell every rank how much this rank contributed and wait until every rank has said so —
+// one warp, lane w talks to rank w.  The match kernels of this rank have completed (stream order), so its posted stores
+// into the peers' buffers are performed before the release store of the flag; a rank that sees all flags of the epoch
+// therefore sees all data.  A peer that never arrives (a failed rank) must not hang the GPU: the wait is bounded.
+__global__ void k_gather_finish(unsigned long long* const* counts /* [world] peers' counts arrays [world][2] */, u32* const* flags /* [world] peers' flag arrays [world] */,
+                                u32* my_flags, u32 rank, u32 world, unsigned long long k, const unsigned long long* d_m, u32 epoch, u32* err) {
+    const u32 w = threadIdx.x;
+    if (w >= world) return;
+    counts[w][2 * rank] = k;
+    counts[w][2 * rank + 1] = *d_m;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags[w] + rank), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+        u32 f;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(my_flags + w) : "memory");
+        if (static_cast<int>(f - epoch) >= 0) break;
+        if (clock64() - t0 > 6000000000ll) { atomicOr(err, 1u); break; }     // ~3 s at 2 GHz: give up, the host reports GM_ERR_COMM
+        __nanosleep(200);
+    }
+}
+
 // (k, m) of this rank into the send slot of the size exchange: m comes from the device cursor of the match
 __global__ void k_comm_sizes(unsigned long long* out, unsigned long long k, const unsigned long long* d_m) {
     out[0] = k;

@@ -164,6 +164,16 @@ struct gm_engine {
     u32 r_cap_items = 1u << 22, r_cap_desc = 1u << 22;   // totals over the RQ slices of each queue
     u64 launches = 0;
     bool k2_attr_set = false;
+    // fused gather over peer memory (comm.cuh): one block per rank holding every rank's slab; the peers' blocks are opened by CUDA IPC
+    struct Gather {
+        char* block = nullptr; size_t bytes = 0;
+        u32 world = 0, rank = 0, epoch = 0;
+        u64 slab_topics = 0, slab_ids = 0;
+        size_t off_spans = 0, off_index = 0, off_counts = 0, off_flags = 0;
+        char* peer[8] = {};
+        DevBuf d_ptrs;      // device arrays for k_gather_finish: counts pointers [8], flags pointers [8]
+        bool connected = false;
+    } gather;
     // multi-GPU (comm.cuh): NCCL communicator of the root-hash shards, scratch of the size exchange
     ncclComm_t comm = nullptr;
     u32 comm_rank = 0, comm_world = 1;
@@ -418,7 +428,7 @@ struct gm_engine {
     int enqueue_match(MatchCtx& c, const void* d_blob_, u64 blob_bytes, const u32* d_offs_, u64 n, gm_span* d_spans_, void* d_ids_, u64 cap_ids,
                       u64* d_needed, int32_t* d_status_, cudaStream_t s, bool stats, bool keep_cursor = false, bool desc = false,
                       const u32* d_sel = nullptr, u64 readable_bytes = 0, const u32* hdr = nullptr, bool timing = true, u32 site_bits_override = 0,
-                      const u32* d_trees = nullptr) {
+                      const u32* d_trees = nullptr, bool gather_mode = false) {
         if (n == 0) { if (d_needed) CUDA_TRY(cudaMemsetAsync(d_needed, 0, sizeof(u64), s)); return GM_OK; }
         if (n > 0xFFFFFFF0ull) { g_err = "batch too large"; return GM_ERR_TOO_LARGE; }
         if (cap_ids > 0xFFFFFFFFull) cap_ids = 0xFFFFFFFFull;   // spans carry 32-bit offsets
@@ -481,19 +491,29 @@ struct gm_engine {
         mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
         mp.flags = (sorted_rows ? MP_SORTED_ROWS : 0u) | knobs.diag_flags;
         mp.tile_chunk = knobs.tile_chunk;
+        if (gather_mode) {
+            const Gather& g = gather;
+            mp.g_world = g.world; mp.g_base_topics = static_cast<u32>(g.rank * g.slab_topics); mp.g_base_ids = g.rank * g.slab_ids; mp.g_sel = d_sel;
+            for (u32 w = 0; w < g.world; ++w) {
+                mp.g_ids[w] = reinterpret_cast<u32*>(g.peer[w]); mp.g_spans[w] = reinterpret_cast<uint2*>(g.peer[w] + g.off_spans);
+                mp.g_index[w] = reinterpret_cast<u32*>(g.peer[w] + g.off_index);
+            }
+        }
         constexpr size_t k2_smem = k2_smem_bytes<K2_FAST_L, K2_THREADS>();
         auto k2_ss = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true, false>;
         auto k2_sd = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true, true>;
         auto k2_ns = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, false>;
         auto k2_nd = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, true>;
+        auto k2_g = k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, false, true>;
         if (!k2_attr_set) {
-            for (auto k : {k2_ss, k2_sd, k2_ns, k2_nd}) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
+            for (auto k : {k2_ss, k2_sd, k2_ns, k2_nd, k2_g}) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(k2_smem)));
             k2_attr_set = true;
         }
-        (stats ? (desc ? k2_sd : k2_ss) : (desc ? k2_nd : k2_ns))<<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, c.d_gpool.as<Desc>(), K2_POOL_ROWS);
+        (gather_mode ? k2_g : stats ? (desc ? k2_sd : k2_ss) : (desc ? k2_nd : k2_ns))<<<k2_grid, K2_THREADS, k2_smem, s>>>(mp, c.d_gpool.as<Desc>(), K2_POOL_ROWS);
         CUDA_TRY(cudaGetLastError());
         if (timing) CUDA_TRY(cudaEventRecord(ev_t[2], s));
-        auto k3 = stats ? (desc ? k_match_slow<true, true> : k_match_slow<true, false>) : (desc ? k_match_slow<false, true> : k_match_slow<false, false>);
+        auto k3 = gather_mode ? k_match_slow<false, false, true>
+                              : stats ? (desc ? k_match_slow<true, true> : k_match_slow<true, false>) : (desc ? k_match_slow<false, true> : k_match_slow<false, false>);
         k3<<<k3_blocks, 256, 0, s>>>(mp, c.d_gstack.as<u64>(), stack_cap);
         CUDA_TRY(cudaGetLastError());
         if (timing) { CUDA_TRY(cudaEventRecord(ev_t[3], s)); ring_n++; }
@@ -666,6 +686,8 @@ void gm_destroy(gm_engine* e) {
     if (e->comm) { NcclApi::get().CommDestroy(e->comm); e->comm = nullptr; }
     if (e->h_comm) cudaFreeHost(e->h_comm);
     e->d_comm.release(); e->d_part.release();
+    if (e->gather.block) { for (u32 w = 0; w < e->gather.world; ++w) if (w != e->gather.rank && e->gather.peer[w]) cudaIpcCloseMemHandle(e->gather.peer[w]); cudaFree(e->gather.block); e->gather.block = nullptr; }
+    e->gather.d_ptrs.release();
     for (auto& hp : e->h_arena_) if (hp) cudaFreeHost(hp);
     for (auto& ev : e->ev_arena_) if (ev) cudaEventDestroy(ev);
     if (e->ev_flush) cudaEventDestroy(e->ev_flush);
@@ -1400,6 +1422,122 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
     if (K) { k_rebase_spans<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint2*>(d_all_spans), d_all, W, static_cast<u32>(K)); e->launches++; }
     e->launches++;
     CUDA_TRY(cudaGetLastError());
+    return GM_OK;
+}
+
+// ---- fused gather over peer memory ------------------------------------------------------------------------------------
+int32_t gm_gather_create(gm_engine* e, uint32_t world, uint32_t rank, uint64_t slab_topics, uint64_t slab_ids, uint8_t* out_handle) {
+    if (!e || !out_handle || world == 0 || world > 8 || rank >= world || slab_topics == 0 || slab_ids == 0) return GM_ERR_INVALID_ARG;
+    if (slab_ids * world > 0xFFFFFFFFull || slab_topics * world > 0xFFFFFFF0ull) { g_err = "gathered arrays exceed 32-bit offsets"; return GM_ERR_TOO_LARGE; }
+    if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine has no device"; return GM_ERR_NO_DEVICE; }
+    std::lock_guard<std::mutex> g(e->mu_dev);
+    CUDA_TRY(cudaSetDevice(e->device));
+    gm_engine::Gather& G = e->gather;
+    if (G.block) { g_err = "gm_gather_create: already created (gm_gather_destroy first)"; return GM_ERR_INVALID_ARG; }
+    G.world = world; G.rank = rank; G.slab_topics = slab_topics; G.slab_ids = slab_ids; G.epoch = 0; G.connected = false;
+    const size_t a = 256;
+    G.off_spans = (static_cast<size_t>(world) * slab_ids * 4 + a - 1) / a * a;
+    G.off_index = G.off_spans + static_cast<size_t>(world) * slab_topics * 8;
+    G.off_counts = (G.off_index + static_cast<size_t>(world) * slab_topics * 4 + a - 1) / a * a;
+    G.off_flags = G.off_counts + static_cast<size_t>(world) * 16;
+    G.bytes = G.off_flags + 256;
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, G.bytes));
+    G.block = static_cast<char*>(p);
+    CUDA_TRY(cudaMemset(G.block + G.off_counts, 0, G.bytes - G.off_counts));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == GM_IPC_HANDLE_BYTES, "gm_gather_create hands out a cudaIpcMemHandle_t");
+    CUDA_TRY(cudaIpcGetMemHandle(&h, G.block));
+    std::memcpy(out_handle, &h, sizeof(h));
+    return GM_OK;
+}
+
+int32_t gm_gather_connect(gm_engine* e, const uint8_t* handles) {
+    if (!e || !handles) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu_dev);
+    gm_engine::Gather& G = e->gather;
+    if (!G.block) { g_err = "gm_gather_connect: gm_gather_create first"; return GM_ERR_INVALID_ARG; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    for (u32 w = 0; w < G.world; ++w) {
+        if (w == G.rank) { G.peer[w] = G.block; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + static_cast<size_t>(w) * GM_IPC_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) { g_err = std::string("cudaIpcOpenMemHandle (peer-to-peer access between the ranks' GPUs is required): ") + cudaGetErrorString(ce); cudaGetLastError(); return GM_ERR_COMM; }
+        G.peer[w] = static_cast<char*>(p);
+    }
+    void* ptrs[16] = {};
+    for (u32 w = 0; w < G.world; ++w) { ptrs[w] = G.peer[w] + G.off_counts; ptrs[8 + w] = G.peer[w] + G.off_flags; }
+    CUDA_TRY(G.d_ptrs.ensure(sizeof(ptrs)));
+    CUDA_TRY(cudaMemcpy(G.d_ptrs.p, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+    G.connected = true;
+    return GM_OK;
+}
+
+int32_t gm_match_gather_device(gm_engine* e, const void* d_blob, uint64_t blob_bytes, const uint32_t* d_offsets, uint64_t n_entries, const uint32_t* d_sel,
+                               uint64_t n, int32_t* d_status, void* stream) {
+    if (!e || (n && (!d_offsets || !d_status))) return GM_ERR_INVALID_ARG;
+    if (blob_bytes > 0xFFFFFFFFull) { g_err = "topic blob >= 4 GiB"; return GM_ERR_TOO_LARGE; }
+    if (d_sel && n > n_entries) return GM_ERR_INVALID_ARG;
+    gm_engine::Gather& G = e->gather;
+    if (!G.connected) { g_err = "gm_match_gather_device: gm_gather_create + gm_gather_connect first"; return GM_ERR_INVALID_ARG; }
+    if (n > G.slab_topics) { g_err = "gm_match_gather_device: more rows than this rank's slab holds"; return GM_ERR_CAPACITY; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    { int st = auto_flush(e); if (st != GM_OK) return st; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    std::lock_guard<std::mutex> gd(e->mu_dev);
+    int st = e->enqueue_match(e->devctx, d_blob, blob_bytes, d_offsets, n, nullptr, nullptr, G.slab_ids, nullptr, d_status, s, false, false, false, d_sel, 0, nullptr, true, 0,
+                              nullptr, true);
+    if (st != GM_OK) return st;
+    // contribution (rows, ids) into every rank's counts + the epoch barrier: when it has passed on a rank, all ranks' data is there
+    G.epoch++;
+    static unsigned long long zero_m_host = 0; (void)zero_m_host;
+    const unsigned long long* d_m = n ? &e->devctx.d_ctrl.as<Ctrl>()->cursor : nullptr;
+    if (!d_m) { CUDA_TRY(e->devctx.d_ctrl.ensure(sizeof(Ctrl))); CUDA_TRY(cudaMemsetAsync(e->devctx.d_ctrl.p, 0, sizeof(Ctrl), s)); d_m = &e->devctx.d_ctrl.as<Ctrl>()->cursor; }
+    void** dp = G.d_ptrs.as<void*>();
+    k_gather_finish<<<1, 32, 0, s>>>(reinterpret_cast<unsigned long long* const*>(dp), reinterpret_cast<u32* const*>(dp + 8), reinterpret_cast<u32*>(G.block + G.off_flags),
+                                     G.rank, G.world, n, d_m, G.epoch, reinterpret_cast<u32*>(G.block + G.off_flags) + 32);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e->devctx.ev_done, s));
+    e->devctx.recorded = true;
+    return GM_OK;
+}
+
+int32_t gm_gather_get(gm_engine* e, gm_gather_view* out, void* stream) {
+    if (!e || !out) return GM_ERR_INVALID_ARG;
+    gm_engine::Gather& G = e->gather;
+    if (!G.block) return GM_ERR_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    u32 err = 0;
+    CUDA_TRY(cudaMemcpy(&err, G.block + G.off_flags + 32 * 4, 4, cudaMemcpyDeviceToHost));
+    out->d_ids = reinterpret_cast<const uint32_t*>(G.block); out->d_spans = reinterpret_cast<const gm_span*>(G.block + G.off_spans);
+    out->d_index = reinterpret_cast<const uint32_t*>(G.block + G.off_index); out->d_counts = reinterpret_cast<const uint64_t*>(G.block + G.off_counts);
+    out->slab_topics = G.slab_topics; out->slab_ids = G.slab_ids; out->world = G.world; out->rank = G.rank;
+    if (err) { g_err = "fused gather: a rank did not reach the end-of-step barrier"; return GM_ERR_COMM; }
+    return GM_OK;
+}
+
+int32_t gm_gather_destroy(gm_engine* e) {
+    if (!e) return GM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->mu_dev);
+    gm_engine::Gather& G = e->gather;
+    if (!G.block) return GM_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (u32 w = 0; w < G.world; ++w) if (w != G.rank && G.peer[w]) cudaIpcCloseMemHandle(G.peer[w]);
+    cudaFree(G.block);
+    G = gm_engine::Gather{};
+    return GM_OK;
+}
+
+int32_t gm_device_read(gm_engine* e, const void* d_src, void* h_dst, uint64_t bytes) {
+    if (!e || !d_src || !h_dst) return GM_ERR_INVALID_ARG;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
     return GM_OK;
 }
 

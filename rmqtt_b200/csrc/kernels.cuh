@@ -39,6 +39,16 @@ struct MatchParams {
     const u32* tok8_sorted;   // [n][8] token rows copied into locality order (MP_SORTED_ROWS)
     const u32* meta_sorted;   // [n]
     u32 tile_chunk;           // tiles a CTA takes from the global counter at once (<= 1: one tile per warp per grab)
+    // FUSED GATHER (peer memory): the publish phase writes every result DIRECTLY into the gathered buffers of all ranks
+    // (own included) over NVLink — no separate collective, the transfer overlaps the walk tile by tile.  Rank r's rows
+    // occupy the fixed slab [r * slab_topics, ...) / ids [r * slab_ids, ...) of every rank's buffers.
+    u32* g_ids[8];            // gathered id arrays of ranks 0..g_world-1 (peer pointers, CUDA IPC)
+    uint2* g_spans[8];
+    u32* g_index[8];
+    u32 g_world;              // 0 = off
+    u32 g_base_topics;        // this rank's slab start, in rows
+    unsigned long long g_base_ids;   // ... and in ids
+    const u32* g_sel;         // row -> global topic index (the selection of gm_partition_batch_device), null: identity
     const u32* trees;         // [n] optional: the tree every row is matched against (0 = the subscription trie)
     const u32* n_ptr;         // small-batch graphs: the real batch size lives in device memory (n is then the capacity = row stride of `tok`)
     uint2* out_desc;          // DESCRIPTOR mode: matched value sets (ref, cnt16) per topic instead of expanded ids; spans index this array
@@ -395,9 +405,10 @@ struct Desc { u32 ref, cnt; };
 // matched FILTER instead of 4 bytes per matched id — and spans / cursor / cap count descriptors.  The host resolves
 // them against its mirror of `values` (gm_desc_resolve): this is what DefaultRouter::_matches consumes anyway, one
 // relations entry per matched filter (rmqtt/src/router.rs:166-182), and it cuts the D2H volume ~4x.
-template <int FAST_L, int THREADS, int CTAS_PER_SM, bool STATS, bool DESC>
+template <int FAST_L, int THREADS, int CTAS_PER_SM, bool STATS, bool DESC, bool GATHER = false>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
+    static_assert(!(GATHER && DESC), "the fused gather publishes ids");
     constexpr u32 SD = K2_SMEM_DESCS;         // descriptors kept in shared memory per topic; later ones spill to dpool
     extern __shared__ __align__(16) unsigned char k2_smem[];   // 64 KB: above the 48 KB static limit -> dynamic
     u32 (*s_tok)[THREADS] = reinterpret_cast<u32 (*)[THREADS]>(k2_smem);                                  // tokens of this thread's topic (column = thread: conflict-free)
@@ -534,7 +545,13 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
         if (lane == 0 && wtotal) base = atomicAdd(p.cursor, static_cast<unsigned long long>(wtotal));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         const bool fits = base + wtotal <= p.cap_ids;
-        if (in_range && !defer) p.spans[t] = make_uint2(fits ? static_cast<u32>(base + pre) : 0u, mine);
+        if (in_range && !defer) {
+            if (GATHER) {        // span (absolute in the gathered id array) + global topic index into this rank's slab on EVERY rank
+                const uint2 gsp = make_uint2(fits ? static_cast<u32>(p.g_base_ids + base + pre) : 0u, mine);
+                const u32 gi = p.g_sel ? p.g_sel[t] : t;
+                for (u32 w = 0; w < p.g_world; ++w) { p.g_spans[w][p.g_base_topics + t] = gsp; p.g_index[w][p.g_base_topics + t] = gi; }
+            } else p.spans[t] = make_uint2(fits ? static_cast<u32>(base + pre) : 0u, mine);
+        }
         const u32 maxd = __reduce_max_sync(0xFFFFFFFFu, nd);
         if (DESC) {
             if (fits && wtotal) {
@@ -566,6 +583,11 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                 for (int o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xFFFFFFFFu, sc, o); if (lane >= o) sc += v; }
                 const u32 tot = __shfl_sync(0xFFFFFFFFu, sc, 31);
                 const u32 exc = sc - ni;
+                // flat index e of the row -> owner lane by binary search over `exc`; with owner o: output position = e +
+                // (dst_o - exc_o), source index = e + (ref_o - exc_o); a single-value set has e == exc_o, so its value
+                // ref_o = e + (ref_o - exc_o) too — two broadcasts per element instead of four
+                const u32 delta = dst - exc, gamma = dsc.ref - exc;
+                const u32 single = __ballot_sync(0xFFFFFFFFu, ni == 1u);
                 for (u32 e0 = 0; e0 < tot; e0 += 32) {
                     const u32 e = e0 + lane;
                     u32 lo = 0;
@@ -574,13 +596,15 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
                         u32 v = __shfl_sync(0xFFFFFFFFu, exc, lo + step);
                         if (v <= e) lo += step;
                     }
-                    const u32 o_exc = __shfl_sync(0xFFFFFFFFu, exc, lo);
-                    const u32 o_ref = __shfl_sync(0xFFFFFFFFu, dsc.ref, lo);
-                    const u32 o_n = __shfl_sync(0xFFFFFFFFu, ni, lo);
-                    const u32 o_dst = __shfl_sync(0xFFFFFFFFu, dst, lo);
+                    const u32 o_delta = __shfl_sync(0xFFFFFFFFu, delta, lo);
+                    const u32 o_gamma = __shfl_sync(0xFFFFFFFFu, gamma, lo);
                     if (e < tot) {
-                        const u32 kk = e - o_exc;
-                        __stcs(out + o_dst + kk, (o_n == 1) ? o_ref : tv.values[o_ref + kk]);   // streaming store: written once
+                        const u32 src = e + o_gamma;
+                        const u32 val = ((single >> lo) & 1u) ? src : tv.values[src];
+                        if (GATHER) {        // posted stores into every rank's gathered array (NVLink for the peers)
+                            const unsigned long long at = p.g_base_ids + base + e + o_delta;
+                            for (u32 w = 0; w < p.g_world; ++w) p.g_ids[w][at] = val;
+                        } else __stcs(out + e + o_delta, val);   // streaming store: written once
                     }
                 }
             }
@@ -609,9 +633,13 @@ k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
 // scratch (gstack, `stack_cap` items per warp: 32*(max_depth+2)+64 bounds the LIFO walk).
 // In STATS mode the counters of a deferred topic are taken here (the fast path's partial counts of
 // topics it later deferred are subtracted by never being added: see `stats_defer` below).
-template <bool STATS, bool DESC>
+template <bool STATS, bool DESC, bool GATHER = false>
 __global__ void __launch_bounds__(256)
 k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
+    auto put = [&](unsigned long long at, u32 v) {       // one result id: local array, or every rank's gathered array
+        if (GATHER) { for (u32 w = 0; w < p.g_world; ++w) p.g_ids[w][p.g_base_ids + at] = v; }
+        else p.out_ids[at] = v;
+    };
     const u32 lane = threadIdx.x & 31;
     const u32 lt = lanemask_lt();
     const u32 gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -662,7 +690,7 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                         continue;
                     }
                     u32 b = __ballot_sync(0xFFFFFFFFu, cn == 1);
-                    if (pass == 1 && cn == 1) p.out_ids[base + written + __popc(b & lt)] = ref;
+                    if (pass == 1 && cn == 1) put(base + written + __popc(b & lt), ref);
                     written += __popc(b);
                     u32 rb = __ballot_sync(0xFFFFFFFFu, cn > 1);
                     while (rb) {     // warp-cooperative copy of one value set at a time
@@ -673,7 +701,7 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
                         u32 off = rr;
                         if (rc == CNT_BIG) { Range rg = tv.ranges[rr]; off = rg.off; rc = rg.cnt; }
                         if (pass == 1)
-                            for (u32 i = lane; i < rc; i += 32) p.out_ids[base + written + i] = tv.values[off + i];
+                            for (u32 i = lane; i < rc; i += 32) put(base + written + i, tv.values[off + i]);
                         written += rc;
                     }
                 }
@@ -732,8 +760,13 @@ k_match_slow(MatchParams p, u64* __restrict__ gstack, u32 stack_cap) {
         if (lane == 0) {
             // a frontier-stack overflow cannot happen within the documented bound; if it ever did, fail the topic loudly
             // instead of aliasing another topic's list
-            if (bad_any) { p.spans[t] = make_uint2(0u, 0u); p.status[t] = -8; }   // GM_ERR_INTERNAL
-            else p.spans[t] = make_uint2(fits ? static_cast<u32>(base) : 0u, static_cast<u32>(count));
+            uint2 sp = make_uint2(fits ? static_cast<u32>(base) : 0u, static_cast<u32>(count));
+            if (bad_any) { sp = make_uint2(0u, 0u); p.status[t] = -8; }   // GM_ERR_INTERNAL
+            if (GATHER) {
+                if (fits && !bad_any) sp.x = static_cast<u32>(p.g_base_ids + base);
+                const u32 gi = p.g_sel ? p.g_sel[t] : t;
+                for (u32 w = 0; w < p.g_world; ++w) { p.g_spans[w][p.g_base_topics + t] = sp; p.g_index[w][p.g_base_topics + t] = gi; }
+            } else p.spans[t] = sp;
         }
     }
     if (STATS) {

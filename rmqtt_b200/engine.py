@@ -352,6 +352,44 @@ class Engine:
                                                    _vp(sizes), stream))
         return sizes.astype(np.int64).reshape(-1, 2)
 
+    # ---- fused gather over peer memory (the match kernels publish straight into every rank's gathered arrays) -----------
+    def gather_create(self, world: int, rank: int, slab_topics: int, slab_ids: int) -> bytes:
+        buf = (C.c_uint8 * N.GM_IPC_HANDLE_BYTES)()
+        self._check(self._lib.gm_gather_create(self._h, world, rank, slab_topics, slab_ids, buf))
+        self._gworld = world
+        return bytes(buf)
+
+    def gather_connect(self, handles):
+        """handles: list of `world` byte strings in rank order (this rank's own entry is ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == self._gworld * N.GM_IPC_HANDLE_BYTES
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.gm_gather_connect(self._h, buf))
+
+    def match_gather_device(self, d_blob, d_offs, d_status, stream: int, d_sel=None, n_sel: int | None = None):
+        n_entries = d_offs.numel() - 1
+        n = n_entries if d_sel is None else int(n_sel)
+        self._check(self._lib.gm_match_gather_device(self._h, d_blob.data_ptr(), d_blob.numel(), d_offs.data_ptr(), n_entries,
+                                                     d_sel.data_ptr() if d_sel is not None else None, n, d_status.data_ptr(), stream))
+
+    def gather_result(self, stream: int):
+        """Synchronises and copies this rank's gathered block to the host:
+        -> (counts int64[world,2], index uint32[K], spans uint32[K,2] (absolute into ids), ids uint32[world*slab_ids])"""
+        v = N.GmGatherView()
+        self._check(self._lib.gm_gather_get(self._h, C.byref(v), stream))
+        W, T, I = int(v.world), int(v.slab_topics), int(v.slab_ids)
+        counts = np.zeros((W, 2), dtype=np.uint64)
+        self._check(self._lib.gm_device_read(self._h, v.d_counts, _vp(counts), counts.nbytes))
+        idx = np.zeros(W * T, dtype=np.uint32); sp = np.zeros((W * T, 2), dtype=np.uint32); ids = np.zeros(W * I, dtype=np.uint32)
+        self._check(self._lib.gm_device_read(self._h, v.d_index, _vp(idx), idx.nbytes))
+        self._check(self._lib.gm_device_read(self._h, v.d_spans, _vp(sp), sp.nbytes))
+        self._check(self._lib.gm_device_read(self._h, v.d_ids, _vp(ids), ids.nbytes))
+        rows = np.concatenate([np.arange(r * T, r * T + int(counts[r, 0])) for r in range(W)]) if W else np.zeros(0, np.int64)
+        return counts.astype(np.int64), idx[rows], sp[rows], ids
+
+    def gather_destroy(self):
+        self._check(self._lib.gm_gather_destroy(self._h))
+
     # ---- tokeniser hook -------------------------------------------------------------------------------
     def tokenize(self, topics, max_tok: int = 16):
         blob, offs = pack(topics)

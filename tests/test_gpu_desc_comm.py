@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import oracle as orc
+from rmqtt_b200 import _native as N
 from rmqtt_b200 import sharding, workload as wl
 from rmqtt_b200.engine import Engine, MatchResult, pack
 
@@ -156,3 +157,36 @@ def test_allgatherv_entry_point_on_a_one_rank_communicator():
     order = np.argsort(idx)
     res = MatchResult(sp[order], ids, np.zeros(n, np.int32), m)
     _assert_same(res, want)
+
+
+def test_fused_gather_on_one_rank_equals_the_oracle():
+    """gm_match_gather_device: the match kernels publish straight into the gathered block (world 1: this rank's own block;
+    the peer-memory path proper needs 2 GPUs, tests/test_gpu_multi.py).  Includes deferred (slow-kernel) topics."""
+    cfg = wl.C2.scaled(n_subs=60_000, n_topics=6_000)
+    sb, so, sv = wl.gen_subs(cfg)
+    tb, to = wl.gen_topics(cfg)
+    eng, tree = Engine(filters_hint=cfg.n_subs), orc.TopicTree()
+    eng.bulk_load(sb, so, sv); tree.bulk_insert(sb, so, sv)
+    deep = "/".join(f"l{i}" for i in range(12))
+    for i, f in enumerate([deep, deep + "/#", "#"]):
+        assert eng.add(f, 9_000_000 + i) == tree.insert(f, 9_000_000 + i)
+    xb, xo = pack(wl.unpack(tb, to) + [deep.encode(), (deep + "/x").encode(), b"bad/#/x"])
+    n = len(xo) - 1
+    dev = torch.device("cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    d_blob, d_offs = torch.from_numpy(xb).to(dev), torch.from_numpy(xo.view(np.int32)).to(dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_sel = torch.zeros(n, dtype=torch.int32, device=dev)
+    k, _ = eng.partition_batch_device(d_blob, d_offs, 1, 0, d_sel, stream)
+    eng.gather_create(1, 0, n, 64 * n)
+    eng.gather_connect([b"\0" * N.GM_IPC_HANDLE_BYTES])
+    for _ in range(2):                                       # two steps: the epoch barrier must pass both times
+        eng.match_gather_device(d_blob, d_offs, d_status, stream, d_sel=d_sel, n_sel=k)
+    counts, idx, spans, ids = eng.gather_result(stream)
+    assert counts.tolist() == [[n, int(spans[:, 1].sum())]]
+    order = np.argsort(idx)
+    assert (idx[order] == np.arange(n)).all()
+    st = d_status.cpu().numpy()[np.argsort(d_sel.cpu().numpy()[:k])]      # status is per ROW; back to topic order
+    res = MatchResult(spans[order], ids, st, int(counts[0, 1]))
+    _assert_same(res, tree.match_batch(xb, xo))
+    eng.gather_destroy()

@@ -53,7 +53,21 @@ def _worker(rank, world, port, q):
     d_blob, d_offs = torch.from_numpy(tb).to(dev), torch.from_numpy(to.view(np.int32)).to(dev)
     a_idx, a_spans, a_ids, sizes, counts = sharded_match_and_gather(eng, rank, world, d_blob, d_offs, dev, stream)
     m = int(sizes[:, 1].sum())
-    q.put((rank, a_idx.cpu().numpy(), a_spans.cpu().numpy().view(np.uint32), a_ids[:m].cpu().numpy().view(np.uint32), sizes))
+    # the same exchange fused into the match kernels over peer memory (CUDA IPC between the two processes)
+    n = d_offs.numel() - 1
+    h = eng.gather_create(world, rank, n, 64 * n)
+    hs = [None] * world
+    dist.all_gather_object(hs, h)
+    eng.gather_connect(hs)
+    d_sel = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    fused = None
+    for _ in range(3):
+        k, _c = eng.partition_batch_device(d_blob, d_offs, world, rank, d_sel, stream)
+        eng.match_gather_device(d_blob, d_offs, d_status, stream, d_sel=d_sel, n_sel=k)
+        fused = eng.gather_result(stream)
+        dist.barrier()                                     # nobody starts the next step while a peer still reads its block
+    q.put((rank, a_idx.cpu().numpy(), a_spans.cpu().numpy().view(np.uint32), a_ids[:m].cpu().numpy().view(np.uint32), sizes, fused))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,9 +84,9 @@ def test_two_rank_sharded_equals_single_engine():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for a, b in zip(got[0][1:], got[1][1:]):          # identical on every rank
+    for a, b in zip(got[0][1:5], got[1][1:5]):        # identical on every rank
         assert (np.asarray(a) == np.asarray(b)).all()
-    _, idx, spans, ids, sizes = got[0]
+    _, idx, spans, ids, sizes, _f = got[0]
     cfg = wl.C2.scaled(**CFG)
     sb, so, sv = wl.gen_subs(cfg)
     tb, to = wl.gen_topics(cfg)
@@ -83,3 +97,9 @@ def test_two_rank_sharded_equals_single_engine():
     order = np.argsort(idx)
     c, i = MatchResult(spans[order], ids, np.zeros(cfg.n_topics, np.int32), len(ids)).canonical()
     assert (c == counts).all() and (i == want_ids).all()
+    for g in got:                                      # the fused (peer-memory) gather: complete and bit-exact on EVERY rank
+        fcounts, fidx, fspans, fids = g[5]
+        assert int(fcounts[:, 0].sum()) == cfg.n_topics and sorted(fidx.tolist()) == list(range(cfg.n_topics))
+        fo = np.argsort(fidx)
+        c2, i2 = MatchResult(fspans[fo], fids, np.zeros(cfg.n_topics, np.int32), int(fcounts[:, 1].sum())).canonical()
+        assert (c2 == counts).all() and (i2 == want_ids).all()
