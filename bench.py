@@ -517,6 +517,10 @@ def run_own(args):
     fused_res = None
     try:
         slab_ids = int(needed_max * 1.3) + 4096
+        if world > 1:                                         # the block layout must be identical on every rank
+            t_sl = torch.tensor([slab_ids], dtype=torch.int64, device=dev)
+            dist.all_reduce(t_sl, op=dist.ReduceOp.MAX)
+            slab_ids = int(t_sl.item())
         hnd = eng.gather_create(world, rank, n, slab_ids)
         hs = [hnd]
         if world > 1:

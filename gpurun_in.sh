@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_multi.py "tests/test_gpu_desc_comm.py::test_fused_gather_on_one_rank_equals_the_oracle" -m gpu -x -q > gpurun_out/pytest_multi2.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi2.txt; tail -25 gpurun_out/pytest_multi2.txt
+timeout 600 python -m pytest tests/test_gpu_multi.py "tests/test_gpu_desc_comm.py::test_fused_gather_on_one_rank_equals_the_oracle" -m gpu -x -q > gpurun_out/pytest_multi2.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi2.txt; tail -6 gpurun_out/pytest_multi2.txt
+
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2_b.json 2> gpurun_out/bench_n2_b.err; echo "bench2 exit $?"; tail -5 gpurun_out/bench_n2_b.err
 python - <<'PY'
 import json

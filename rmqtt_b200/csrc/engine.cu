@@ -169,6 +169,7 @@ struct gm_engine {
         char* block = nullptr; size_t bytes = 0;
         u32 world = 0, rank = 0, epoch = 0;
         u64 slab_topics = 0, slab_ids = 0;
+        static constexpr size_t off_ids = 256;      // the block starts with a 256-byte header {world, slab_topics, slab_ids}
         size_t off_spans = 0, off_index = 0, off_counts = 0, off_flags = 0;
         char* peer[8] = {};
         DevBuf d_ptrs;      // device arrays for k_gather_finish: counts pointers [8], flags pointers [8]
@@ -495,7 +496,7 @@ struct gm_engine {
             const Gather& g = gather;
             mp.g_world = g.world; mp.g_base_topics = static_cast<u32>(g.rank * g.slab_topics); mp.g_base_ids = g.rank * g.slab_ids; mp.g_sel = d_sel;
             for (u32 w = 0; w < g.world; ++w) {
-                mp.g_ids[w] = reinterpret_cast<u32*>(g.peer[w]); mp.g_spans[w] = reinterpret_cast<uint2*>(g.peer[w] + g.off_spans);
+                mp.g_ids[w] = reinterpret_cast<u32*>(g.peer[w] + Gather::off_ids); mp.g_spans[w] = reinterpret_cast<uint2*>(g.peer[w] + g.off_spans);
                 mp.g_index[w] = reinterpret_cast<u32*>(g.peer[w] + g.off_index);
             }
         }
@@ -1436,7 +1437,7 @@ int32_t gm_gather_create(gm_engine* e, uint32_t world, uint32_t rank, uint64_t s
     if (G.block) { g_err = "gm_gather_create: already created (gm_gather_destroy first)"; return GM_ERR_INVALID_ARG; }
     G.world = world; G.rank = rank; G.slab_topics = slab_topics; G.slab_ids = slab_ids; G.epoch = 0; G.connected = false;
     const size_t a = 256;
-    G.off_spans = (static_cast<size_t>(world) * slab_ids * 4 + a - 1) / a * a;
+    G.off_spans = (gm_engine::Gather::off_ids + static_cast<size_t>(world) * slab_ids * 4 + a - 1) / a * a;
     G.off_index = G.off_spans + static_cast<size_t>(world) * slab_topics * 8;
     G.off_counts = (G.off_index + static_cast<size_t>(world) * slab_topics * 4 + a - 1) / a * a;
     G.off_flags = G.off_counts + static_cast<size_t>(world) * 16;
@@ -1445,6 +1446,8 @@ int32_t gm_gather_create(gm_engine* e, uint32_t world, uint32_t rank, uint64_t s
     CUDA_TRY(cudaMalloc(&p, G.bytes));
     G.block = static_cast<char*>(p);
     CUDA_TRY(cudaMemset(G.block + G.off_counts, 0, G.bytes - G.off_counts));
+    const unsigned long long geo[3] = {world, slab_topics, slab_ids};       // the layout must be the same on every rank: checked at connect
+    CUDA_TRY(cudaMemcpy(G.block, geo, sizeof(geo), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     static_assert(sizeof(h) == GM_IPC_HANDLE_BYTES, "gm_gather_create hands out a cudaIpcMemHandle_t");
@@ -1467,6 +1470,12 @@ int32_t gm_gather_connect(gm_engine* e, const uint8_t* handles) {
         cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (ce != cudaSuccess) { g_err = std::string("cudaIpcOpenMemHandle (peer-to-peer access between the ranks' GPUs is required): ") + cudaGetErrorString(ce); cudaGetLastError(); return GM_ERR_COMM; }
         G.peer[w] = static_cast<char*>(p);
+        unsigned long long geo[3] = {0, 0, 0};
+        CUDA_TRY(cudaMemcpy(geo, G.peer[w], sizeof(geo), cudaMemcpyDeviceToHost));
+        if (geo[0] != G.world || geo[1] != G.slab_topics || geo[2] != G.slab_ids) {
+            g_err = "gm_gather_connect: rank " + std::to_string(w) + " created its block with a different (world, slab_topics, slab_ids): the layout must be identical on every rank";
+            return GM_ERR_INVALID_ARG;
+        }
     }
     void* ptrs[16] = {};
     for (u32 w = 0; w < G.world; ++w) { ptrs[w] = G.peer[w] + G.off_counts; ptrs[8 + w] = G.peer[w] + G.off_flags; }
@@ -1514,7 +1523,7 @@ int32_t gm_gather_get(gm_engine* e, gm_gather_view* out, void* stream) {
     CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     u32 err = 0;
     CUDA_TRY(cudaMemcpy(&err, G.block + G.off_flags + 32 * 4, 4, cudaMemcpyDeviceToHost));
-    out->d_ids = reinterpret_cast<const uint32_t*>(G.block); out->d_spans = reinterpret_cast<const gm_span*>(G.block + G.off_spans);
+    out->d_ids = reinterpret_cast<const uint32_t*>(G.block + gm_engine::Gather::off_ids); out->d_spans = reinterpret_cast<const gm_span*>(G.block + G.off_spans);
     out->d_index = reinterpret_cast<const uint32_t*>(G.block + G.off_index); out->d_counts = reinterpret_cast<const uint64_t*>(G.block + G.off_counts);
     out->slab_topics = G.slab_topics; out->slab_ids = G.slab_ids; out->world = G.world; out->rank = G.rank;
     if (err) { g_err = "fused gather: a rank did not reach the end-of-step barrier"; return GM_ERR_COMM; }
