@@ -1,10 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_multi.py "tests/test_gpu_desc_comm.py::test_fused_gather_on_one_rank_equals_the_oracle" -m gpu -x -q > gpurun_out/pytest_multi2.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi2.txt; tail -6 gpurun_out/pytest_multi2.txt
-
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2_b.json 2> gpurun_out/bench_n2_b.err; echo "bench2 exit $?"; tail -5 gpurun_out/bench_n2_b.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_n2_b.json'))
-for k in ('value','value_with_gather','e2e','multi_gpu','parity_check'):
-    print(k, json.dumps(d.get(k))[:1800])
-PY
+python tools/c4_once.py stats 2>&1 | grep "kernel ms\|retain stats" > gpurun_out/c4_locality.txt; cat gpurun_out/c4_locality.txt
+timeout 1500 python -m pytest tests -m gpu -x -q --durations=6 > gpurun_out/pytest_gpu7.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu7.txt; tail -14 gpurun_out/pytest_gpu7.txt
+python tools/ab_round2.py tok 2>/dev/null | head -2

@@ -61,3 +61,48 @@ extern "C" {
     pub fn gm_host_alloc(bytes: u64) -> *mut c_void;
     pub fn gm_host_free(p: *mut c_void);
 }
+
+// ---- round-2 additions of include/gpumqtt.h (same caveat: untested source) -------------------------------------------
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct gm_desc {
+    pub r#ref: u32, // cnt == 1: the value itself; 2..65534: values[ref .. ref+cnt); 65535: ranges[ref]
+    pub cnt: u32,
+}
+#[repr(C)]
+pub struct gm_values {
+    pub values: *const u32,
+    pub n_values: u64,
+    pub ranges: *const gm_span,
+    pub n_ranges: u64,
+    pub epoch: u64,
+}
+#[repr(C)]
+pub struct gm_batcher {
+    _private: [u8; 0],
+}
+pub type gm_match_cb = extern "C" fn(user: *mut c_void, cookie: u64, status: i32, ids: *const u32, n_ids: u32);
+#[repr(C)]
+pub struct gm_batcher_config {
+    pub struct_size: u32,
+    pub max_batch: u32,
+    pub max_wait_us: u32,
+    pub dispatchers: u32,
+    pub on_match: gm_match_cb,
+    pub user: *mut c_void,
+}
+extern "C" {
+    pub fn gm_match_batch_desc(e: *mut gm_engine, topics_blob: *const u8, topic_offsets: *const u32, n: u64, out_spans: *mut gm_span,
+                               out_descs: *mut gm_desc, cap_descs: u64, needed: *mut u64, status: *mut i32) -> i32;
+    pub fn gm_values_view(e: *mut gm_engine, out: *mut gm_values) -> i32;
+    pub fn gm_batcher_create(e: *mut gm_engine, cfg: *const gm_batcher_config, out: *mut *mut gm_batcher) -> i32;
+    pub fn gm_submit(b: *mut gm_batcher, topic: *const u8, len: u32, cookie: u64) -> i32;
+    pub fn gm_submit_publish(b: *mut gm_batcher, packet: *const u8, len: u32, cookie: u64) -> i32;
+    pub fn gm_batcher_drain(b: *mut gm_batcher) -> i32;
+    pub fn gm_batcher_destroy(b: *mut gm_batcher);
+    pub fn gm_sub_add_tree(e: *mut gm_engine, tree: u32, filter: *const u8, len: u32, value: u32, changed: *mut i32) -> i32;
+    pub fn gm_sub_remove_tree(e: *mut gm_engine, tree: u32, filter: *const u8, len: u32, value: u32, changed: *mut i32) -> i32;
+    pub fn gm_match_batch_trees(e: *mut gm_engine, topics_blob: *const u8, topic_offsets: *const u32, trees: *const u32, n: u64,
+                                out_spans: *mut gm_span, out_ids: *mut u32, cap_ids: u64, needed: *mut u64, status: *mut i32) -> i32;
+    pub fn gm_retain_remove_batch(e: *mut gm_engine, blob: *const u8, offsets: *const u32, n: u64, old_values: *mut u32, n_removed: *mut u64) -> i32;
+}
