@@ -118,7 +118,8 @@ def _workload_desc(cfg, world):
     return (f"{cfg.name}: {cfg.n_subs} subscriptions (30% '+', 5% '#', 0.6% root '+'), 6-level IoT topics "
             f"reg/site/dev/sen/met/ch over R{cfg.R}xS{cfg.S}xD{cfg.D}xK{cfg.K}xM{cfg.M}xF{cfg.F}, "
             f"{cfg.n_topics}-topic uniform batch per GPU, seed {cfg.seed:#x}"
-            + (f", subscriptions sharded by topic-root hash over {world} GPUs (root-wildcards replicated)" if world > 1 else ""))
+            + (f", subscriptions sharded by topic-root hash over {world} GPUs (root-wildcards replicated)" if world > 1 else "")
+            + "; L2: the device tables (GBs) and the rotated distinct batches are far larger than the 126 MB L2, no flush between steps")
 
 
 # ======================================================================================================
@@ -154,8 +155,9 @@ def run_reference(args):
         "impl": "reference", "metric": "topic-matches/sec @10M subs", "value": value, "unit": "topics/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": _workload_desc(cfg, 1), "sample": f"{sample} topics of the batch per step", "oracle_build_s": round(build_s, 1),
-                   "matched_ids_per_topic": ids / sample},
+        "config": {"workload": _workload_desc(cfg, max(1, args.gpus))},      # the same workload definition as the own arm's line
+        "details": {"sample": f"{sample} topics of the batch per step, matched against the whole (unsharded) subscription set on the host cores",
+                    "oracle_build_s": round(build_s, 1), "matched_ids_per_topic": ids / sample},
         "cpu_baseline": {"value": value, "unit": "topics/s", "cores": threads, "kind": "port",
                          "sample": f"{sample}-topic sample x {args.steps} steps, C++ restatement of DefaultRouter::_matches (Rust reference not buildable here: no cargo)"},
         "e2e": {"value": value, "unit": "topics/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -702,7 +704,8 @@ def run_own(args):
         "metric": "topic-matches/sec @10M subs", "value": value, "unit": "topics/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": _workload_desc(cfg, world), "l2": f"device tables {st['device_bytes'] / 1e9:.2f} GB >> 126 MB L2; {B} distinct topic batches rotated",
+        "config": {"workload": _workload_desc(cfg, world)},
+        "details": {"l2": f"device tables {st['device_bytes'] / 1e9:.2f} GB >> 126 MB L2; {B} distinct topic batches rotated",
                    "matched_ids_per_topic": W["ids"] / n, "matched_filters_per_topic": W["filters"] / n, "visited_nodes_per_topic": W["visited"] / n,
                    "deferred_topics_per_batch": W["deferred"], "probe_diag": diag,
                    "trie": {k: st[k] for k in ("values", "nodes", "edges", "edge_slots", "dict_entries", "plus_nodes", "device_bytes", "max_depth")},
