@@ -119,3 +119,40 @@ def test_latency_probe_reports_sane_numbers():
         assert rc == 0
         d = lat.as_dict()
         assert d["samples"] == burst * rounds and 0 < d["p50_us"] <= d["p99_us"] <= d["max_us"] < 5e6 and d["topics_per_s"] > 0
+
+
+def test_submit_publish_takes_the_raw_packet():
+    """gm_submit_publish: the topic is taken straight out of the PUBLISH packet (v3.1.1 / v5 layout) into the batch."""
+    rng, eng, tree = _setup(800, seed=3)
+    topics = [rand_topic(rng, 5) for _ in range(300)]
+    got = {}
+
+    @N.GM_MATCH_CB
+    def cb(user, cookie, status, ids, n_ids):
+        got[cookie] = sorted(ids[i] for i in range(n_ids)) if status == 0 else None
+
+    cfg = N.GmBatcherConfig(C.sizeof(N.GmBatcherConfig), 32, 100, 2, cb, None)
+    h = C.c_void_p()
+    lib = N.lib()
+    assert lib.gm_batcher_create(eng._h, C.byref(cfg), C.byref(h)) == 0
+    for i, t in enumerate(topics):
+        tb = t.encode()
+        qos = i % 3
+        var = len(tb).to_bytes(2, "big") + tb + (b"\x00\x09" if qos else b"") + (b"\x00" if i % 2 else b"") + b"payload" * (i % 5)
+        rem, enc = len(var), bytearray()
+        while True:
+            b = rem & 0x7F
+            rem >>= 7
+            enc.append(b | (0x80 if rem else 0))
+            if not rem:
+                break
+        pkt = bytes([0x30 | (qos << 1)]) + bytes(enc) + var
+        buf = (C.c_uint8 * len(pkt)).from_buffer_copy(pkt)
+        assert lib.gm_submit_publish(h, buf, len(pkt), i) == 0
+    bad = (C.c_uint8 * 4).from_buffer_copy(b"\x82\x02\x00\x01")        # a SUBSCRIBE is not a PUBLISH
+    assert lib.gm_submit_publish(h, bad, 4, 999) == N.GM_ERR_INVALID_ARG
+    assert lib.gm_batcher_drain(h) == 0
+    lib.gm_batcher_destroy(h)
+    for i, t in enumerate(topics):
+        want = tree.matches(t)
+        assert got[i] == (sorted(want) if want is not None else None), t
