@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-python tools/c4_once.py stats 2>&1 | grep "kernel ms\|retain stats" > gpurun_out/c4_inline.txt; cat gpurun_out/c4_inline.txt
-python tools/c4_once.py 2>&1 | grep "kernel ms" >> gpurun_out/c4_inline.txt; tail -1 gpurun_out/c4_inline.txt
-timeout 900 python -m pytest tests/test_gpu_retain.py tests/test_gpu_hypothesis.py tests/test_gpu_batcher.py "tests/test_gpu_fullsize.py::test_retained_full_size_every_filter_bit_exact" -m gpu -x -q > gpurun_out/pytest_gpu8.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu8.txt; tail -6 gpurun_out/pytest_gpu8.txt
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/pytest_multi3.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi3.txt; tail -5 gpurun_out/pytest_multi3.txt
+
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2_b.json 2> gpurun_out/bench_n2_b.err; echo "bench2 exit $?"; tail -5 gpurun_out/bench_n2_b.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_n2_b.json'))
+for k in ('value','value_with_gather','e2e','multi_gpu','parity_check'):
+    print(k, json.dumps(d.get(k))[:1800])
+PY
