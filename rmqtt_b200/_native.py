@@ -185,6 +185,15 @@ def lib():
     """Loads libgpumqtt.so.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
     global _lib
     if _lib is None:
+        import os
+        path = Path(os.environ["GM_LIB"]) if os.environ.get("GM_LIB") else LIB_PATH      # A/B builds of the same library (tools/)
+        if path != LIB_PATH and path.exists():
+            L = C.CDLL(str(path))
+            for name, (res, args) in SIGNATURES.items():
+                f = getattr(L, name)
+                f.restype, f.argtypes = res, args
+            _lib = L
+            return _lib
         if not LIB_PATH.exists():
             raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no fallback path")
         L = C.CDLL(str(LIB_PATH))

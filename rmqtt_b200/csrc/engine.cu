@@ -568,7 +568,7 @@ struct gm_engine {
         auto krr = knobs.retain_stats ? k_retain_round<true> : k_retain_round<false>;
         kri<<<(nq + 255) / 256, 256, 0, s>>>(rp, d_rfront[0].as<RTask>(), &ctl->counts[0]);
         const int grid = num_sms * 8;
-        const int rgrid = num_sms * 6;            // exactly the resident CTAs (40 registers x 256 threads): tasks are claimed dynamically
+        const int rgrid = num_sms * GM_RETAIN_CTAS;   // exactly the resident CTAs (launch bound of k_retain_round): tasks are claimed dynamically
         for (u32 lvl = 0; lvl <= depth; ++lvl)
             krr<<<rgrid, 256, 0, s>>>(rp, d_rfront[lvl & 1].as<RTask>(), &ctl->counts[static_cast<size_t>(lvl) * RQ], d_rfront[(lvl + 1) & 1].as<RTask>(),
                                       &ctl->counts[static_cast<size_t>(lvl + 1) * RQ], &ctl->counts[static_cast<size_t>(depth + 3) * RQ + lvl]);
@@ -1383,10 +1383,8 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
     // 2. one grouped launch, straight out of the buffers the match kernels wrote.  Default: point-to-point (every rank sends
     //    its three arrays to every peer and receives theirs — each pair has its own NVSwitch path); GM_ALLGATHERV=bcast
     //    selects one ncclBroadcast per (rank, array) instead (A/B, profiles/).
-    u64 ko = 0, mo = 0;
     std::vector<u64> kof(W + 1, 0), mof(W + 1, 0);
     for (u32 r = 0; r < W; ++r) { kof[r + 1] = kof[r] + sizes[2 * r]; mof[r + 1] = mof[r] + sizes[2 * r + 1]; }
-    (void)ko; (void)mo;
     if (e->knobs.gather_bcast) {
         NCCL_TRY(nc.GroupStart());
         for (u32 r = 0; r < W; ++r) {
@@ -1502,7 +1500,6 @@ int32_t gm_match_gather_device(gm_engine* e, const void* d_blob, uint64_t blob_b
     if (st != GM_OK) return st;
     // contribution (rows, ids) into every rank's counts + the epoch barrier: when it has passed on a rank, all ranks' data is there
     G.epoch++;
-    static unsigned long long zero_m_host = 0; (void)zero_m_host;
     const unsigned long long* d_m = n ? &e->devctx.d_ctrl.as<Ctrl>()->cursor : nullptr;
     if (!d_m) { CUDA_TRY(e->devctx.d_ctrl.ensure(sizeof(Ctrl))); CUDA_TRY(cudaMemsetAsync(e->devctx.d_ctrl.p, 0, sizeof(Ctrl), s)); d_m = &e->devctx.d_ctrl.as<Ctrl>()->cursor; }
     void** dp = G.d_ptrs.as<void*>();

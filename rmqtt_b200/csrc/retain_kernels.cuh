@@ -210,8 +210,11 @@ k_retain_init(RetainParams p, RTask* out, u32* n_out) {
 // active lanes and half the random-access rate of the part (profiles/r2_retain_round_v1.ncu-rep).  Anything that is
 // not an exact level (the next '+', a '#', a stored literal wildcard) goes through retain_chain as before.
 constexpr u32 RLIST = 256;    // = RTASK_CHUNK: at most one survivor per child of the task
+#ifndef GM_RETAIN_CTAS
+#define GM_RETAIN_CTAS 6
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, GM_RETAIN_CTAS)
 k_retain_round(RetainParams p, const RTask* __restrict__ in, const u32* __restrict__ n_in_p, RTask* __restrict__ out, u32* n_out, u32* __restrict__ claim) {
     static_assert(RLIST >= RTASK_CHUNK, "the survivor list holds one entry per child of a task");
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt = lanemask_lt();

@@ -3,8 +3,11 @@ the hash of the topic root (level 0), filters whose level 0 is '+' or '#' replic
 topic routed to the single shard of its own root.  The `$`-rule (trie.rs:312-318) is evaluated locally and
 identically, so the union over shards of per-topic match lists equals the unsharded result.
 
-The only collective is an all-gatherv of per-rank match lists, used when a consumer needs every result on
-every rank; it is issued on the process group given (NCCL over NVLink on GPUs, gloo in the CPU tests).
+The data path of the multi-GPU layout (device partition of a mixed batch, match of the share, all-gatherv of the
+match lists — NCCL or fused into the match kernels over peer memory) lives in libgpumqtt (include/gpumqtt.h:
+gm_partition_batch_device, gm_allgatherv_device, gm_gather_*).  What is here is the HOST-side placement logic (which
+filters / retained topics a rank stores, which queries it answers) and a torch.distributed reference of the
+all-gatherv that the CPU tests (gloo, world size 2) use to check that the union over shards equals the unsharded result.
 """
 from __future__ import annotations
 
@@ -86,7 +89,8 @@ def partition_retain_filters(blob, offs, rank: int, world: int):
 
 
 def all_gatherv_match_lists(topic_index: torch.Tensor, counts: torch.Tensor, ids: torch.Tensor, group=None):
-    """All-gatherv of per-rank match lists.
+    """All-gatherv of per-rank match lists — host-side reference used by the gloo tests; the product path is
+    gm_allgatherv_device / gm_match_gather_device inside the library.
 
     topic_index int64[k]  global index of each local topic, counts int64[k] matches per local topic,
     ids int32/uint32[sum(counts)] the match lists concatenated in local topic order.
