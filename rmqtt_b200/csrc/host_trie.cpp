@@ -4,6 +4,8 @@
 #include "host_trie.h"
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
@@ -253,16 +255,19 @@ void HostTrie::cfilter_insert(u32 parent, u32 token) {
 }
 
 void HostTrie::cfilter_rebuild() {
+    // every child edge of a wide node; walked over the node array (sequential, one entry per edge) — the edge table itself
+    // is mostly empty slots (load 0.2) and several GB at scale
     u64 n = 0;
-    for (const EdgeSlot& e : edges) if (e.child != 0 && nodes_[e.parent].wide) ++n;
+    for (size_t id = 1; id < nodes_.size(); ++id) if (nodes_[nodes_[id].parent].wide) ++n;
     size_t words = 1u << 10;
     while (words * 32 < n * 20) words <<= 1;                        // ~20 bits per edge after a rebuild
     cfilter.assign(words, 0u);
     const u32 mask = static_cast<u32>(words - 1);
-    for (const EdgeSlot& e : edges) {
-        if (e.child == 0 || !nodes_[e.parent].wide) continue;
+    for (size_t id = 1; id < nodes_.size(); ++id) {
+        const HNode& c = nodes_[id];
+        if (!nodes_[c.parent].wide) continue;
         u32 w, bits;
-        cfilter_pos(e.parent, e.token, mask, w, bits);
+        cfilter_pos(c.parent, c.token, mask, w, bits);
         cfilter[w] |= bits;
     }
     cfilter_keys_ = n;
@@ -393,6 +398,9 @@ int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed, u32 
 u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n) {
     constexpr u32 G = 64;
     u64 changed = 0;
+    const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
+    double t_parse = 0, t_walk = 0, t_val = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     std::vector<u32> toks;                    // tokens of the group, concatenated
     u32 t_off[G + 1], node[G], tag[G];
     u64 idx[G];
@@ -401,6 +409,7 @@ u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* valu
         toks.clear();
         u32 m = 0, deepest = 0;
         t_off[0] = 0;
+        double ta = prof ? now() : 0;
         for (u32 j = 0; j < g; ++j) {           // dictionary slots of every level of the group: prefetch before the real parse
             const char* f = blob + offsets[base + j];
             const u32 len = offsets[base + j + 1] - offsets[base + j];
@@ -421,6 +430,7 @@ u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* valu
             deepest = std::max<u32>(deepest, static_cast<u32>(scratch_toks_.size()));
             ++m;
         }
+        double tb = prof ? now() : 0;
         for (u32 d = 0; d < deepest; ++d) {
             const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
             for (u32 j = 0; j < m; ++j)
@@ -434,8 +444,11 @@ u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* valu
             }
         }
         max_depth = std::max<u32>(max_depth, deepest);
+        double tc = prof ? now() : 0;
         for (u32 j = 0; j < m; ++j) changed += add_value(node[j], values[idx[j]]) ? 1 : 0;
+        if (prof) { const double td = now(); t_parse += tb - ta; t_walk += tc - tb; t_val += td - tc; }
     }
+    if (prof) fprintf(stderr, "insert_batch: %llu filters: parse+intern %.2f s, edge walk %.2f s, values %.2f s\n", (unsigned long long)n, t_parse, t_walk, t_val);
     return changed;
 }
 
@@ -577,6 +590,9 @@ bool HostTrie::sync() {
         add_words = pending_words();
         if (add_words > 0xFFFFFFF0ull) return false;   // more than 2^32 value words live: references would wrap
     }
+    const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = prof ? now() : 0;
     if (cfilter_rebuild_) {
         // nodes that just became wide must republish their record (flag)
         for (u32 id = 0; id < nodes_.size(); ++id) if (nodes_[id].wide && !nodes_[id].dirty) { nodes_[id].dirty = 1; dirty_nodes_.push_back(id); }
@@ -585,6 +601,7 @@ bool HostTrie::sync() {
     // pass 1: value-set references (a '#' node's parent reads the child's fresh ref in pass 2).  Sets with more than
     // one value are appended to `values`; they are appended grouped by (window, depth-2 subtree) so that the sets
     // one tile of the match kernel expands (same level0/level1 subtree) are neighbours in `values` as well.
+    const double t1 = prof ? now() : 0;
     std::vector<std::pair<u64, u32>> multi;
     for (u32 id : dirty_nodes_) {
         if (!(nodes_[id].dirty & 2)) continue;             // record-only change: the published set stays
@@ -596,12 +613,35 @@ bool HostTrie::sync() {
     }
     std::sort(multi.begin(), multi.end());
     for (const auto& m : multi) make_ref(m.second);
-    for (size_t i = 0; i < dirty_nodes_.size(); ++i) {
-        if (i + 16 < dirty_nodes_.size()) __builtin_prefetch(&edges[nodes_[dirty_nodes_[i + 16]].edge_slot], 1);   // records land in random slots
-        const u32 id = dirty_nodes_[i];
-        write_record(id);
-        nodes_[id].dirty = 0;
-    }
+    // pass 2: records.  Every node writes its OWN slot (the root: the root record) from refs that pass 1 has settled, so after a
+    // bulk load / re-hash (the whole table ships anyway: no per-slot dirty list to append to) the millions of random
+    // slot writes are spread over the host cores.
+    const double t2 = prof ? now() : 0;
+    const size_t nd = dirty_nodes_.size();
+    auto write_range = [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            if (i + 16 < e) __builtin_prefetch(&edges[nodes_[dirty_nodes_[i + 16]].edge_slot], 1);   // records land in random slots
+            const u32 id = dirty_nodes_[i];
+            write_record(id);
+            nodes_[id].dirty = 0;
+        }
+    };
+    const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    if (full_edges && nd >= (size_t(1) << 18) && hw > 1 && !getenv("GM_SYNC_SERIAL")) {
+        size_t root_at = nd;                              // the root record is shared state (root_*): its node is written by this thread
+        for (size_t i = 0; i < nd; ++i) if (dirty_nodes_[i] == 0) { root_at = i; break; }
+        if (root_at != nd) std::swap(dirty_nodes_[root_at], dirty_nodes_[nd - 1]);
+        const size_t npar = root_at != nd ? nd - 1 : nd;
+        std::vector<std::thread> th;
+        const size_t chunk = (npar + hw - 1) / hw;
+        for (unsigned t = 0; t < hw; ++t) {
+            const size_t b = std::min(npar, t * chunk), e = std::min(npar, b + chunk);
+            if (b < e) th.emplace_back(write_range, b, e);
+        }
+        for (auto& t : th) t.join();
+        write_range(npar, nd);
+    } else write_range(0, nd);
+    if (prof && nd > 100000) fprintf(stderr, "sync: %zu dirty nodes: child filter %.2f s, value refs %.2f s, records %.2f s\n", nd, t1 - t0, t2 - t1, now() - t2);
     dirty_nodes_.clear();
     if (tree_nodes_.size() > 1) {                     // root records of the extra trees: their slots move with every re-hash
         std::vector<u32> ts(tree_nodes_.size(), 0xFFFFFFFFu);
