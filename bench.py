@@ -585,9 +585,18 @@ def run_own(args):
         fused_step(0)
         sync_all()
         fused_res = eng.gather_result(stream) if rank == 0 else None
-        multi["strong_fused"] = {"how": "gm_match_gather_device: the publish phase of k_match_fast / k_match_slow stores every span, index and id straight into the "
-                                        "gathered block of EVERY rank (peer pointers over NVLink, CUDA IPC), then a one-warp kernel writes the counts and runs a flag "
-                                        "barrier; no NCCL call, no host synchronisation, the transfer overlaps the walk",
+        ms_direct = None
+        if world > 1:                                         # A/B: the publish phase storing into every rank's block itself
+            eng.debug_knob("gather_direct", 1)
+            ms_direct = timed_device_loop(fused_step, coll_steps, 2)
+            eng.debug_knob("gather_direct", 0)
+            fused_step(0)
+            sync_all()
+            fused_res = eng.gather_result(stream) if rank == 0 else None
+        multi["strong_fused"] = {"how": "gm_match_gather_device over peer memory (CUDA IPC): the match kernels publish this rank's rows into its own block, "
+                                        "k_gather_push copies the slab into every peer's block with 16-byte stores over NVLink, a one-warp kernel writes the counts "
+                                        "and runs a flag barrier; no NCCL call, no host synchronisation",
+                                 "ms_per_step_direct_stores": (ms_direct / coll_steps) if ms_direct else None,
                                  "value": n * coll_steps / (ms_fused / 1e3), "unit": "topics/s", "ms_per_step": ms_fused / coll_steps, "steps": coll_steps,
                                  "vs_nccl_step": (ms_strong / coll_steps) / (ms_fused / coll_steps)}
         sync_all()

@@ -121,6 +121,30 @@ __global__ void k_rebase_spans(uint2* __restrict__ spans, const unsigned long lo
     if (mo) { uint2 s = spans[i]; s.x += static_cast<u32>(mo); spans[i] = s; }
 }
 
+// PUSH form of the peer-memory gather: the match kernels published this rank's rows / ids into ITS OWN block; this kernel
+// copies the slab to the same place in every peer's block with 16-byte loads and stores (NVLink writes in full 128-byte
+// packets, every SM busy), still without a collective call or a host synchronisation.  Measured against the direct form
+// (the publish phase storing every id into all blocks itself): see DESIGN.md §6.
+__global__ void __launch_bounds__(256)
+k_gather_push(char* const* blocks /* [world] */, u32 rank, u32 world, size_t off_ids, size_t off_spans, size_t off_index,
+              unsigned long long base_topics, unsigned long long base_ids, unsigned long long k, const unsigned long long* d_m) {
+    const unsigned long long m = *d_m;
+    const char* own = blocks[rank];
+    // three byte ranges of the own block, each copied to every peer: ids, spans, index (starts are 16-byte aligned by layout)
+    const size_t start[3] = {off_ids + base_ids * 4, off_spans + base_topics * 8, off_index + base_topics * 4};
+    const size_t bytes[3] = {static_cast<size_t>(m) * 4, static_cast<size_t>(k) * 8, static_cast<size_t>(k) * 4};
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, nth = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (int a = 0; a < 3; ++a) {
+        const size_t lo = start[a] & ~size_t(15), hi = (start[a] + bytes[a] + 15) & ~size_t(15);      // whole 16-byte words (the slack belongs to this rank's slab)
+        const size_t nvec = (hi - lo) / 16;
+        const uint4* src = reinterpret_cast<const uint4*>(own + lo);
+        for (size_t i = tid; i < nvec; i += nth) {
+            const uint4 v = src[i];
+            for (u32 w = 0; w < world; ++w) if (w != rank) reinterpret_cast<uint4*>(blocks[w] + lo)[i] = v;
+        }
+    }
+}
+
 // End of a fused-gather step: tell every rank how much this rank contributed and wait until every rank has said so —
 // one warp, lane w talks to rank w.  The match kernels of this rank have completed (stream order), so its posted stores
 // into the peers' buffers are performed before the release store of the flag; a rank that sees all flags of the epoch

@@ -181,7 +181,7 @@ struct gm_engine {
     DevBuf d_comm, d_part;
     unsigned long long* h_comm = nullptr;   // pinned [2 * world + 64]
     // tuning / diagnostics knobs, read from the environment once at creation
-    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 262144; bool small_graphs = true; bool retain_stats = false; bool gather_bcast = false; } knobs;
+    struct Knobs { u32 site_bits = 14, sub_bits = 0; bool sorted_rows = true; int k2_ctas = 0; u32 diag_flags = 0; u32 tile_chunk = 1; bool tok_bulk = true; u32 e2e_chunk = 262144; bool small_graphs = true; bool retain_stats = false; bool gather_bcast = false; bool gather_direct = false; } knobs;
     void read_knobs() {
         if (const char* ev = getenv("GM_BUCKET_BITS")) { int a = 14, b = 0; if (sscanf(ev, "%d,%d", &a, &b) >= 1 && a >= 10 && b >= 0 && a + b <= int(MAX_BUCKET_BITS)) { knobs.site_bits = a; knobs.sub_bits = b; } }
         if (const char* ev = getenv("GM_SORTED_ROWS")) knobs.sorted_rows = atoi(ev) != 0;
@@ -190,6 +190,7 @@ struct gm_engine {
         if (getenv("GM_DIAG_NO_PUBLISH")) knobs.diag_flags |= MP_DIAG_NO_PUBLISH;
         if (const char* ev = getenv("GM_TOK_BULK")) knobs.tok_bulk = atoi(ev) != 0;
         if (const char* ev = getenv("GM_ALLGATHERV")) knobs.gather_bcast = std::string(ev) == "bcast";
+        if (const char* ev = getenv("GM_GATHER_DIRECT")) knobs.gather_direct = atoi(ev) != 0;
         if (const char* ev = getenv("GM_SMALL_GRAPHS")) knobs.small_graphs = atoi(ev) != 0;
         if (const char* ev = getenv("GM_E2E_CHUNK")) { int v = atoi(ev); if (v >= 1024) knobs.e2e_chunk = static_cast<u32>(v); }
     }
@@ -494,10 +495,17 @@ struct gm_engine {
         mp.tile_chunk = knobs.tile_chunk;
         if (gather_mode) {
             const Gather& g = gather;
-            mp.g_world = g.world; mp.g_base_topics = static_cast<u32>(g.rank * g.slab_topics); mp.g_base_ids = g.rank * g.slab_ids; mp.g_sel = d_sel;
-            for (u32 w = 0; w < g.world; ++w) {
-                mp.g_ids[w] = reinterpret_cast<u32*>(g.peer[w] + Gather::off_ids); mp.g_spans[w] = reinterpret_cast<uint2*>(g.peer[w] + g.off_spans);
-                mp.g_index[w] = reinterpret_cast<u32*>(g.peer[w] + g.off_index);
+            mp.g_base_topics = static_cast<u32>(g.rank * g.slab_topics); mp.g_base_ids = g.rank * g.slab_ids; mp.g_sel = d_sel;
+            if (knobs.gather_direct) {          // the publish phase stores into every rank's block itself
+                mp.g_world = g.world;
+                for (u32 w = 0; w < g.world; ++w) {
+                    mp.g_ids[w] = reinterpret_cast<u32*>(g.peer[w] + Gather::off_ids); mp.g_spans[w] = reinterpret_cast<uint2*>(g.peer[w] + g.off_spans);
+                    mp.g_index[w] = reinterpret_cast<u32*>(g.peer[w] + g.off_index);
+                }
+            } else {                            // ... into its own block only; k_gather_push copies the slab to the peers
+                mp.g_world = 1;
+                mp.g_ids[0] = reinterpret_cast<u32*>(g.block + Gather::off_ids); mp.g_spans[0] = reinterpret_cast<uint2*>(g.block + g.off_spans);
+                mp.g_index[0] = reinterpret_cast<u32*>(g.block + g.off_index);
             }
         }
         constexpr size_t k2_smem = k2_smem_bytes<K2_FAST_L, K2_THREADS>();
@@ -1427,6 +1435,7 @@ int32_t gm_allgatherv_device(gm_engine* e, const uint32_t* d_index, const gm_spa
 // ---- fused gather over peer memory ------------------------------------------------------------------------------------
 int32_t gm_gather_create(gm_engine* e, uint32_t world, uint32_t rank, uint64_t slab_topics, uint64_t slab_ids, uint8_t* out_handle) {
     if (!e || !out_handle || world == 0 || world > 8 || rank >= world || slab_topics == 0 || slab_ids == 0) return GM_ERR_INVALID_ARG;
+    slab_topics = (slab_topics + 3) & ~uint64_t(3); slab_ids = (slab_ids + 3) & ~uint64_t(3);       // every slab starts on a 16-byte boundary
     if (slab_ids * world > 0xFFFFFFFFull || slab_topics * world > 0xFFFFFFF0ull) { g_err = "gathered arrays exceed 32-bit offsets"; return GM_ERR_TOO_LARGE; }
     if (e->flags & GM_FLAG_HOST_ONLY) { g_err = "host-only engine has no device"; return GM_ERR_NO_DEVICE; }
     std::lock_guard<std::mutex> g(e->mu_dev);
@@ -1475,8 +1484,8 @@ int32_t gm_gather_connect(gm_engine* e, const uint8_t* handles) {
             return GM_ERR_INVALID_ARG;
         }
     }
-    void* ptrs[16] = {};
-    for (u32 w = 0; w < G.world; ++w) { ptrs[w] = G.peer[w] + G.off_counts; ptrs[8 + w] = G.peer[w] + G.off_flags; }
+    void* ptrs[24] = {};
+    for (u32 w = 0; w < G.world; ++w) { ptrs[w] = G.peer[w] + G.off_counts; ptrs[8 + w] = G.peer[w] + G.off_flags; ptrs[16 + w] = G.peer[w]; }
     CUDA_TRY(G.d_ptrs.ensure(sizeof(ptrs)));
     CUDA_TRY(cudaMemcpy(G.d_ptrs.p, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
     G.connected = true;
@@ -1503,6 +1512,11 @@ int32_t gm_match_gather_device(gm_engine* e, const void* d_blob, uint64_t blob_b
     const unsigned long long* d_m = n ? &e->devctx.d_ctrl.as<Ctrl>()->cursor : nullptr;
     if (!d_m) { CUDA_TRY(e->devctx.d_ctrl.ensure(sizeof(Ctrl))); CUDA_TRY(cudaMemsetAsync(e->devctx.d_ctrl.p, 0, sizeof(Ctrl), s)); d_m = &e->devctx.d_ctrl.as<Ctrl>()->cursor; }
     void** dp = G.d_ptrs.as<void*>();
+    if (!e->knobs.gather_direct && G.world > 1) {
+        k_gather_push<<<e->num_sms * 4, 256, 0, s>>>(reinterpret_cast<char* const*>(dp + 16), G.rank, G.world, gm_engine::Gather::off_ids, G.off_spans, G.off_index,
+                                                     G.rank * G.slab_topics, G.rank * G.slab_ids, n, d_m);
+        e->launches++;
+    }
     k_gather_finish<<<1, 32, 0, s>>>(reinterpret_cast<unsigned long long* const*>(dp), reinterpret_cast<u32* const*>(dp + 8), reinterpret_cast<u32*>(G.block + G.off_flags),
                                      G.rank, G.world, n, d_m, G.epoch, reinterpret_cast<u32*>(G.block + G.off_flags) + 32);
     e->launches++;
@@ -1680,6 +1694,7 @@ int32_t gm_debug_knob(gm_engine* e, const char* name, int64_t value) {
     else if (k == "tok_bulk") e->knobs.tok_bulk = value != 0;
     else if (k == "small_graphs") e->knobs.small_graphs = value != 0;
     else if (k == "gather_bcast") e->knobs.gather_bcast = value != 0;
+    else if (k == "gather_direct") e->knobs.gather_direct = value != 0;
     else if (k == "retain_stats") e->knobs.retain_stats = value != 0;
     else if (k == "e2e_chunk" && value >= 1024) e->knobs.e2e_chunk = static_cast<u32>(value);
     else return GM_ERR_INVALID_ARG;
