@@ -2,6 +2,7 @@
 // rmqtt/src/trie.rs:99-135 (insert / remove with bottom-up pruning) and the filter validation of
 // rmqtt/src/topic.rs:326-363 (Level::from_str, Topic::from_str, Topic::is_valid).
 #include "host_trie.h"
+#include "host_par.h"
 
 #include <algorithm>
 #include <chrono>
@@ -39,8 +40,8 @@ inline bool dict_slot_equals(const DictSlot& d, const u8* pool, const char* s, u
 }  // namespace
 
 HostTrie::HostTrie(u32 max_levels) : max_levels_(max_levels) {
-    edges.assign(1u << 10, EdgeSlot{});
-    dict.assign(1u << 10, DictSlot{});
+    edges.assign_zero(1u << 10);
+    dict.assign_zero(1u << 10);
     ranges.assign(1, Range{0, 0});
     cfilter.assign(1u << 10, 0u);
     nodes_.emplace_back();   // root = node 0
@@ -62,9 +63,15 @@ void HostTrie::reserve(u64 n_filters) {
     u64 want_e = 1; while (want_e < n_filters * per_filter) want_e <<= 1;
     u64 want_d = 1; while (want_d < n_filters / 2 + 1024) want_d <<= 1;
     want_e = std::min<u64>(want_e, 1ull << 31);
+    const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if (edges.size() < want_e) rehash_edges(static_cast<size_t>(want_e));
+    const double t1 = now();
     while (dict.size() < want_d && dict.size() < (1ull << 31)) grow_dict();
+    const double t2 = now();
     nodes_.reserve(nodes_.size() + n_filters * 3 + n_filters / 2);
+    if (prof) fprintf(stderr, "reserve: edge table %.2f s, dictionary %.2f s, nodes %.2f s\n", t1 - t0, t2 - t1, now() - t2);
 }
 
 u32 HostTrie::level0_hash(const char* s, u32 len) {
@@ -116,9 +123,9 @@ u32 HostTrie::intern(const char* s, u32 len, bool create) {
 }
 
 void HostTrie::grow_dict() {
-    std::vector<DictSlot, HugeAlloc<DictSlot>> old;
+    ZeroTable<DictSlot> old;
     old.swap(dict);
-    dict.assign(old.size() * 2, DictSlot{});
+    dict.assign_zero(old.size() * 2);
     u32 mask = static_cast<u32>(dict.size() - 1);
     for (const DictSlot& d : old) {
         if (d.w[0] == 0) continue;
@@ -146,9 +153,9 @@ u32 HostTrie::find_edge(u32 parent, u32 token, u32 wtag) const {
 // Re-place every edge into a table of `new_size` slots cut into as many windows as the cap and the minimum
 // window size allow.  Tags stay; the effective window is tag & (nwin - 1).
 void HostTrie::rehash_edges(size_t new_size) {
-    std::vector<EdgeSlot, HugeAlloc<EdgeSlot>> old;
+    ZeroTable<EdgeSlot> old;
     old.swap(edges);
-    edges.assign(new_size, EdgeSlot{});
+    edges.assign_zero(new_size);
     u32 bits = 0; while ((size_t(1) << bits) < new_size) ++bits;
     table_log2 = bits;
     nwin_log2 = std::min(nwin_cap_log2_, bits > win_min_log2_ ? bits - win_min_log2_ : 0u);
@@ -256,20 +263,30 @@ void HostTrie::cfilter_insert(u32 parent, u32 token) {
 
 void HostTrie::cfilter_rebuild() {
     // every child edge of a wide node; walked over the node array (sequential, one entry per edge) — the edge table itself
-    // is mostly empty slots (load 0.2) and several GB at scale
+    // is mostly empty slots (load 0.2) and several GB at scale.  Big tries: all host threads, bits set with atomic ORs.
+    const size_t nn = nodes_.size();
+    const unsigned T = nn >= host_par_min(size_t(1) << 18) ? host_threads() : 1u;
+    std::vector<u64> cnt(T, 0);
+    parallel_chunks(nn, T, [&](unsigned tid, size_t b, size_t e) {
+        u64 c = 0;
+        for (size_t id = std::max<size_t>(b, 1); id < e; ++id) if (nodes_[nodes_[id].parent].wide) ++c;
+        cnt[tid] = c;
+    });
     u64 n = 0;
-    for (size_t id = 1; id < nodes_.size(); ++id) if (nodes_[nodes_[id].parent].wide) ++n;
+    for (u64 c : cnt) n += c;
     size_t words = 1u << 10;
     while (words * 32 < n * 20) words <<= 1;                        // ~20 bits per edge after a rebuild
     cfilter.assign(words, 0u);
     const u32 mask = static_cast<u32>(words - 1);
-    for (size_t id = 1; id < nodes_.size(); ++id) {
-        const HNode& c = nodes_[id];
-        if (!nodes_[c.parent].wide) continue;
-        u32 w, bits;
-        cfilter_pos(c.parent, c.token, mask, w, bits);
-        cfilter[w] |= bits;
-    }
+    parallel_chunks(nn, T, [&](unsigned, size_t b, size_t e) {
+        for (size_t id = std::max<size_t>(b, 1); id < e; ++id) {
+            const HNode& c = nodes_[id];
+            if (!nodes_[c.parent].wide) continue;
+            u32 w, bits;
+            cfilter_pos(c.parent, c.token, mask, w, bits);
+            if (T > 1) __atomic_fetch_or(&cfilter[w], bits, __ATOMIC_RELAXED); else cfilter[w] |= bits;
+        }
+    });
     cfilter_keys_ = n;
     cfilter_rebuild_ = false;
     cfilter_dirty = true;
@@ -396,6 +413,7 @@ int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed, u32 
 // random probes of the multi-GB edge table overlap: pass 1 of a level prefetches every filter's first probe slot,
 // pass 2 resolves them in order (creating nodes exactly as the one-by-one path would).
 u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n) {
+    if (n >= host_par_min(1u << 16) && host_threads() > 1 && !getenv("GM_BULK_SERIAL")) return insert_batch_parallel(blob, offsets, values, n, host_threads());
     constexpr u32 G = 64;
     u64 changed = 0;
     const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
@@ -449,6 +467,396 @@ u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* valu
         if (prof) { const double td = now(); t_parse += tb - ta; t_walk += tc - tb; t_val += td - tc; }
     }
     if (prof) fprintf(stderr, "insert_batch: %llu filters: parse+intern %.2f s, edge walk %.2f s, values %.2f s\n", (unsigned long long)n, t_parse, t_walk, t_val);
+    return changed;
+}
+
+// ------------------------------------------------------------------------------- parallel bulk insert
+// The same trie CONTENT as n calls of insert() (same dictionary numbering too: tokens are assigned in the order of first
+// occurrence), built by all host threads.  Node numbers differ from the one-by-one path: they follow the sorted
+// (parent, token) order of every level — deterministic, independent of the thread count.
+//
+//   A  levels -> tokens: every thread validates its share of the filters (Topic::from_str rules, topic.rs:326-363) and
+//      collects the level strings the dictionary does not hold in a private set, remembering where each first occurred;
+//      the sets are merged in first-occurrence order (serial: ~0.1 string per filter), then every thread resolves its levels.
+//   B  one pass per level: (1) every filter looks its edge up (read-only probes of the edge table); the misses are new
+//      edges — (2) their keys are sorted and made unique over all threads, (3) node numbers, window tags and room in the
+//      table are settled serially, (4) every WINDOW of the table is owned by one thread, which places the new edges of its
+//      windows and updates their parents (all children of a node live in one window: no two threads touch the same parent
+//      or the same region of the table), (5) the filters that missed look their edge up again.
+//   C  values, in filter order (the multi-value sets are a host map).
+namespace {
+struct LocalStrings {        // level strings one thread met that the dictionary did not hold (open addressing over `ents`)
+    struct Ent { const char* s; u32 len, hash; u64 ord; u32 tok; };
+    std::vector<Ent> ents;
+    std::vector<u32> index;  // hash -> entry + 1
+    std::vector<std::vector<u32>> parts;   // entries by partition of the hash space (filled once the set is complete)
+    LocalStrings() { index.assign(1u << 12, 0u); }
+    static unsigned part_of(u32 hash, unsigned nparts) { return (hash >> 7) % nparts; }
+    void partition(unsigned nparts) {
+        parts.assign(nparts, {});
+        for (u32 k = 0; k < ents.size(); ++k) parts[part_of(ents[k].hash, nparts)].push_back(k);
+    }
+    u32 add(const char* s, u32 len, u32 h, u64 ord) {
+        if ((ents.size() + 1) * 2 > index.size()) {
+            std::vector<u32> bigger(index.size() * 2, 0u);
+            const size_t m = bigger.size() - 1;
+            for (u32 k = 0; k < ents.size(); ++k) { size_t i = ents[k].hash & m; while (bigger[i]) i = (i + 1) & m; bigger[i] = k + 1; }
+            index.swap(bigger);
+        }
+        const size_t m = index.size() - 1;
+        for (size_t i = h & m;; i = (i + 1) & m) {
+            if (!index[i]) { ents.push_back(Ent{s, len, h, ord, 0u}); index[i] = static_cast<u32>(ents.size()); return static_cast<u32>(ents.size() - 1); }
+            const Ent& e = ents[index[i] - 1];
+            if (e.hash == h && e.len == len && std::memcmp(e.s, s, len) == 0) return index[i] - 1;   // first occurrence stays: a chunk is walked in order
+        }
+    }
+};
+constexpr u32 TOK_LOCAL = 0x80000000u;   // provisional token: index into the thread's LocalStrings
+}  // namespace
+
+u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const u32* values, u64 n, unsigned T) {
+    const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    // ---- A0: level offsets (levels of filter i = its '/' count + 1)
+    std::vector<u64> lvl_off(n + 1, 0);
+    parallel_chunks(n, T, [&](unsigned, size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            const char* f = blob + offsets[i];
+            const u32 len = offsets[i + 1] - offsets[i];
+            u64 c = 1;
+            for (u32 k = 0; k < len; ++k) c += f[k] == '/';
+            lvl_off[i + 1] = c;
+        }
+    });
+    for (u64 i = 0; i < n; ++i) lvl_off[i + 1] += lvl_off[i];
+    std::vector<u32> toks(lvl_off[n]);
+    std::vector<uint16_t> depth(n, 0);          // 0 = invalid / too deep: skipped like insert()
+    // ---- A1: validate + tokens the dictionary already holds
+    std::vector<LocalStrings> locals(T);
+    std::vector<std::pair<size_t, size_t>> chunk_of(T, {0, 0});
+    const bool dict_empty = dict_count_ == 0;
+    parallel_chunks(n, T, [&](unsigned tid, size_t b, size_t e) {
+        chunk_of[tid] = {b, e};
+        LocalStrings L;                          // thread-private while it grows (the objects of `locals` share cache lines)
+        for (size_t i = b; i < e; ++i) {
+            const char* f = blob + offsets[i];
+            const u32 len = offsets[i + 1] - offsets[i];
+            u32* out = toks.data() + lvl_off[i];
+            // pass 1: shape (an invalid filter never reaches the dictionary)
+            bool ok = true;
+            u32 nl = 0;
+            for (u32 start = 0;;) {
+                u32 end = start;
+                bool wild = false;
+                while (end < len && f[end] != '/') { wild |= (f[end] == '+' || f[end] == '#'); ++end; }
+                const u32 l = end - start;
+                const bool last = end >= len;
+                if (l == 0) out[nl] = TOK_BLANK;
+                else if (l == 1 && f[start] == '+') out[nl] = TOK_PLUS;
+                else if (l == 1 && f[start] == '#') { if (!last) { ok = false; break; } out[nl] = TOK_HASH; }
+                else if (wild) { ok = false; break; }
+                else { if (f[start] == '$' && nl) { ok = false; break; } out[nl] = TOK_UNKNOWN; }
+                if (++nl > max_levels_) { ok = false; break; }
+                if (last) break;
+                start = end + 1;
+            }
+            if (!ok) continue;
+            depth[i] = static_cast<uint16_t>(nl);
+            // pass 2: literal levels
+            u32 k = 0;
+            for (u32 start = 0; k < nl; ++k) {
+                u32 end = start;
+                while (end < len && f[end] != '/') ++end;
+                if (out[k] == TOK_UNKNOWN) {
+                    const u32 l = end - start;
+                    u32 t = dict_empty ? TOK_UNKNOWN : lookup_token(f + start, l);
+                    if (t == TOK_UNKNOWN) t = TOK_LOCAL | L.add(f + start, l, dict_index_hash(f + start, l), (static_cast<u64>(i) << 16) | std::min<u32>(k, 65535u));
+                    out[k] = t;
+                }
+                start = end + 1;
+            }
+        }
+        L.partition(T);
+        locals[tid] = std::move(L);
+    });
+    const double t_a1 = now();
+    // ---- A2: new level strings enter the dictionary in the order of their first occurrence (what one-by-one inserts do).
+    //      The threads' sets overlap (a device name is met by every thread): partition r of the hash space is made unique by
+    //      thread r (smallest first occurrence wins); what is left is one entry per new string, interned serially in order.
+    {
+        struct New { u64 ord; const char* s; u32 len; };
+        std::vector<std::vector<New>> uniq(T);
+        parallel_threads(T, [&](unsigned r) {
+            LocalStrings U;
+            for (const LocalStrings& L : locals) {
+                if (L.parts.size() != T) continue;        // a thread without a chunk
+                for (u32 idx : L.parts[r]) {
+                    const auto& e = L.ents[idx];
+                    const u32 k = U.add(e.s, e.len, e.hash, e.ord);
+                    if (e.ord < U.ents[k].ord) { U.ents[k].ord = e.ord; U.ents[k].s = e.s; }
+                }
+            }
+            std::vector<New> out;
+            out.reserve(U.ents.size());
+            for (const auto& e : U.ents) out.push_back(New{e.ord, e.s, e.len});
+            std::sort(out.begin(), out.end(), [](const New& a, const New& b) { return a.ord < b.ord; });
+            uniq[r].swap(out);
+        });
+        std::vector<New> news;
+        size_t total = 0;
+        for (const auto& u : uniq) total += u.size();
+        news.reserve(total);
+        for (const auto& u : uniq) news.insert(news.end(), u.begin(), u.end());
+        std::sort(news.begin(), news.end(), [](const New& a, const New& b) { return a.ord < b.ord; });
+        for (size_t k = 0; k < news.size(); ++k) {
+            if (k + 8 < news.size()) __builtin_prefetch(&dict[dict_index_hash(news[k + 8].s, news[k + 8].len) & (dict.size() - 1)], 1);
+            intern(news[k].s, news[k].len, true);
+        }
+    }
+    const double t_a2 = now();
+    // ---- A3: resolve the provisional tokens
+    parallel_threads(T, [&](unsigned tid) {
+        LocalStrings& L = locals[tid];
+        for (auto& e : L.ents) e.tok = lookup_token(e.s, e.len);
+        for (size_t i = chunk_of[tid].first; i < chunk_of[tid].second; ++i) {
+            u32* out = toks.data() + lvl_off[i];
+            for (u32 k = 0; k < depth[i]; ++k) if (out[k] & TOK_LOCAL) out[k] = L.ents[out[k] & ~TOK_LOCAL].tok;
+        }
+    });
+    locals.clear(); locals.shrink_to_fit();
+    const double t_a3 = now();
+
+    // ---- B: level-synchronous edges
+    std::vector<u32> cur(n, 0u);
+    std::vector<u8> ctag(n, nodes_[0].wtag);
+    u32 deepest = 0;
+    for (u64 i = 0; i < n; ++i) deepest = std::max<u32>(deepest, depth[i]);
+    std::vector<std::vector<u64>> mkeys(T);
+    std::vector<std::vector<u32>> midx(T);
+    double t_find = 0, t_sort = 0, t_serial = 0, t_place = 0, t_lsort = 0, t_find0 = 0, t_refind = 0;
+    u64 new_edges_total = 0;
+    std::vector<u32> revive_parents;           // dead nodes that gained a (live) child
+    for (u32 d = 0; d < deepest; ++d) {
+        const double tb0 = now();
+        // (1) look-ups
+        {
+            const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
+            parallel_chunks(n, T, [&](unsigned tid, size_t b, size_t e) {
+                std::vector<u64> mk; std::vector<u32> mi;       // thread-private while they grow; the capacity of the last level is reused
+                mk.swap(mkeys[tid]); mi.swap(midx[tid]);
+                mk.clear(); mi.clear();
+                constexpr size_t G = 32;
+                for (size_t g0 = b; g0 < e; g0 += G) {
+                    const size_t g1 = std::min(e, g0 + G);
+                    for (size_t i = g0; i < g1; ++i)
+                        if (depth[i] > d) __builtin_prefetch(&edges[edge_slot0(cur[i], toks[lvl_off[i] + d], ctag[i], wm, ws, nm)]);
+                    for (size_t i = g0; i < g1; ++i) {
+                        if (depth[i] <= d) continue;
+                        const u32 tok = toks[lvl_off[i] + d];
+                        const u32 slot = find_edge(cur[i], tok, ctag[i]);
+                        if (slot == NOSLOT) { mk.push_back((static_cast<u64>(cur[i]) << 32) | tok); mi.push_back(static_cast<u32>(i)); }
+                        else { cur[i] = edges[slot].child; ctag[i] = static_cast<u8>(edges[slot].mask >> WTAG_SHIFT); }
+                    }
+                }
+                const double ts0 = tid == 0 ? now() : 0;
+                std::sort(mk.begin(), mk.end());
+                mk.erase(std::unique(mk.begin(), mk.end()), mk.end());
+                if (tid == 0) { t_lsort += now() - ts0; t_find0 += ts0 - tb0; }
+                if (prof && getenv("GM_BULK_PROFILE_LEVELS")) fprintf(stderr, "  level %u thread %u: done +%.3f (%zu misses)\n", d, tid, now() - tb0, mi.size());
+                mk.swap(mkeys[tid]); mi.swap(midx[tid]);
+            });
+        }
+        const double tb1 = now();
+        t_find += tb1 - tb0;
+        // (2) new edges of this level: sorted, unique over all threads.  Key ranges are cut at sampled splitters; the thread of a
+        //     range pulls its part out of every thread's sorted list.
+        std::vector<u64> ukeys;
+        {
+            std::vector<u64> samples;
+            for (const auto& mk : mkeys) { constexpr size_t S = 64; if (!mk.empty()) for (size_t k = 0; k < S; ++k) samples.push_back(mk[(mk.size() * (2 * k + 1)) / (2 * S)]); }
+            if (samples.empty()) continue;                 // every edge of this level existed
+            std::sort(samples.begin(), samples.end());
+            std::vector<u64> split(T + 1, 0);              // range r = [split[r], split[r + 1]), the last one unbounded above
+            for (unsigned r = 1; r < T; ++r) split[r] = samples[(samples.size() * r) / T];
+            std::vector<std::vector<u64>> seg(T);
+            parallel_threads(T, [&](unsigned r) {
+                std::vector<u64>& out = seg[r];
+                for (const auto& mk : mkeys) {
+                    auto a = r == 0 ? mk.begin() : std::lower_bound(mk.begin(), mk.end(), split[r]);
+                    auto b = r + 1 == T ? mk.end() : std::lower_bound(mk.begin(), mk.end(), split[r + 1]);
+                    if (a < b) out.insert(out.end(), a, b);
+                }
+                std::sort(out.begin(), out.end());
+                out.erase(std::unique(out.begin(), out.end()), out.end());
+            });
+            std::vector<size_t> base(T + 1, 0);
+            for (unsigned r = 0; r < T; ++r) base[r + 1] = base[r] + seg[r].size();
+            ukeys.resize(base[T]);
+            parallel_threads(T, [&](unsigned r) { std::copy(seg[r].begin(), seg[r].end(), ukeys.begin() + base[r]); });
+        }
+        const size_t nu = ukeys.size();
+        const double tb2 = now();
+        t_sort += tb2 - tb1;
+        // (3) serial: node numbers, window tags of new depth-2 subtrees, room in the table
+        const size_t first_new = nodes_.size();
+        if (first_new + nu > 0xFFFFFFF0ull) { fprintf(stderr, "gpumqtt: bulk load exceeds 2^32 trie nodes\n"); std::abort(); }
+        nodes_.resize(first_new + nu);
+        if (d == 1) for (size_t g = 0; g < nu; ++g) nodes_[first_new + g].wtag = static_cast<u8>(pick_tag());
+        std::vector<u8> own(nu);
+        std::vector<u64> add_w;
+        for (;;) {
+            const u32 nm = nwin_mask();
+            std::vector<std::vector<u64>> hist(T, std::vector<u64>(size_t(nm) + 1, 0));
+            parallel_chunks(nu, T, [&](unsigned tid, size_t b, size_t e) {
+                for (size_t g = b; g < e; ++g) { const u32 w = nodes_[ukeys[g] >> 32].wtag & nm; own[g] = static_cast<u8>(w); hist[tid][w]++; }
+            });
+            add_w.assign(size_t(nm) + 1, 0);
+            for (const auto& h : hist) for (size_t w = 0; w <= nm; ++w) add_w[w] += h[w];
+            const u64 win_slots = edges.size() >> nwin_log2;
+            bool fits = (edge_count_ + nu) * 2 <= edges.size();
+            for (size_t w = 0; fits && w <= nm; ++w) fits = (win_count_[w] + add_w[w]) * 2 <= win_slots;
+            if (fits) break;
+            if ((edge_count_ + nu) * 4 > edges.size() || nwin_log2 == 0) rehash_edges(edges.size() * 2);
+            else { win_min_log2_ = win_shift() + 2; rehash_edges(edges.size()); }
+        }
+        const double tb3 = now();
+        t_serial += tb3 - tb2;
+        // (4) every window belongs to one thread
+        {
+            const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
+            std::vector<std::vector<u32>> t_dirty(T);
+            std::vector<u64> t_plus(T, 0);
+            std::vector<u8> t_cf(T, 0);
+            const u32 child_depth = d + 1;
+            std::vector<std::vector<u64>> t_tag(T), t_win(T);
+            std::vector<std::vector<u32>> t_revive(T);
+            parallel_threads(T, [&](unsigned tid) {
+                std::vector<u32> mine;
+                for (size_t g = 0; g < nu; ++g) if (own[g] % T == tid) mine.push_back(static_cast<u32>(g));
+                // everything this thread counts stays private until the join (neighbouring counters of other threads share cache lines)
+                std::vector<u32> dl, rv;
+                std::vector<u64> l_tag(WTAG_COUNT, 0), l_win(size_t(nm) + 1, 0);
+                u64 l_plus = 0; u8 l_cf = 0;
+                for (size_t q = 0; q < mine.size(); ++q) {
+                    if (q + 8 < mine.size()) {
+                        const u64 k8 = ukeys[mine[q + 8]];
+                        const u32 p8 = static_cast<u32>(k8 >> 32);
+                        __builtin_prefetch(&edges[edge_slot0(p8, static_cast<u32>(k8), nodes_[p8].wtag, wm, ws, nm)], 1);
+                    }
+                    const size_t g = mine[q];
+                    const u32 parent = static_cast<u32>(ukeys[g] >> 32), token = static_cast<u32>(ukeys[g]);
+                    const u32 id = static_cast<u32>(first_new + g);
+                    HNode& pn = nodes_[parent];
+                    const u32 ptag = pn.wtag;
+                    HNode& c = nodes_[id];
+                    c.parent = parent; c.token = token; c.depth = static_cast<uint16_t>(child_depth);
+                    if (child_depth <= 1) c.wtag = 0; else if (child_depth != 2) c.wtag = static_cast<u8>(ptag);   // depth 2: picked in (3)
+                    u32 i = edge_slot0(parent, token, ptag, wm, ws, nm);
+                    while (edges[i].child != 0) i = edge_next(i, wm);
+                    EdgeSlot es{};
+                    es.parent = parent; es.token = token; es.child = id;
+                    es.plus = 0; es.hash_ref = 0; es.own_ref = 0; es.mask = static_cast<u32>(c.wtag) << WTAG_SHIFT; es.cnts = 0;
+                    edges[i] = es;
+                    c.edge_slot = i;
+                    l_tag[ptag]++;
+                    l_win[ptag & nm]++;
+                    pn.mask |= mask_bit(token);
+                    if (token != TOK_PLUS && token != TOK_HASH) pn.lit_children++;
+                    if (pn.wide) l_cf = 1;
+                    else if (pn.lit_children > WIDE_FANOUT) { pn.wide = 1; l_cf = 1; }
+                    if (token == TOK_PLUS) { pn.plus_child = id; l_plus++; }
+                    else if (token == TOK_HASH) pn.hash_child = id;
+                    if (!pn.dirty) dl.push_back(parent);
+                    pn.dirty |= 1;
+                    // a bulk-created node always ends up alive (a value is stored at or below it): born alive, counted by its parent;
+                    // a DEAD parent (pruned earlier, trie.rs:126-128) is revived after the join
+                    c.alive = 1;
+                    pn.live_children++;
+                    if (!pn.alive) rv.push_back(parent);
+                }
+                t_revive[tid].swap(rv);
+                t_dirty[tid].swap(dl); t_tag[tid].swap(l_tag); t_win[tid].swap(l_win); t_plus[tid] = l_plus; t_cf[tid] = l_cf;
+            });
+            for (unsigned t = 0; t < T; ++t) {
+                for (size_t k = 0; k < t_tag[t].size(); ++k) tag_count_[k] += t_tag[t][k];
+                for (size_t k = 0; k < t_win[t].size(); ++k) win_count_[k] += t_win[t][k];
+                dirty_nodes_.insert(dirty_nodes_.end(), t_dirty[t].begin(), t_dirty[t].end());
+                plus_count_ += t_plus[t];
+                if (t_cf[t]) cfilter_rebuild_ = true;     // the child filter is rebuilt from the nodes by the next sync()
+            }
+            for (unsigned t = 0; t < T; ++t) revive_parents.insert(revive_parents.end(), t_revive[t].begin(), t_revive[t].end());
+            edge_count_ += nu;
+            live_nodes_ += nu;
+            new_edges_total += nu;
+        }
+        const double tb4 = now();
+        t_place += tb4 - tb3;
+        // (5) the filters that missed walk their new edge
+        parallel_threads(T, [&](unsigned tid) {
+            for (u32 i : midx[tid]) {
+                const u32 slot = find_edge(cur[i], toks[lvl_off[i] + d], ctag[i]);
+                cur[i] = edges[slot].child; ctag[i] = static_cast<u8>(edges[slot].mask >> WTAG_SHIFT);
+            }
+        });
+        t_refind += now() - tb4;
+    }
+    if (new_edges_total) { full_edges = true; dirty_edges.clear(); }   // the placed slots were not listed one by one: the next flush ships the table
+    max_depth = std::max<u32>(max_depth, deepest);
+    // ---- C: values.  A node belongs to one thread (blocks of 64 node numbers): it applies the node's values in filter order;
+    //      what reaches beyond the node — the host map of multi-value sets, the parent of a '#' node, dead ancestors to
+    //      revive — is collected per thread and settled after the join.
+    const double t_c = now();
+    u64 changed = 0;
+    {
+        using Multi = std::unordered_map<u32, std::vector<u32>>;
+        std::vector<Multi> t_multi(T);
+        std::vector<std::vector<u32>> t_dirty(T), t_hashpar(T), t_revive(T);
+        std::vector<u64> t_changed(T, 0);
+        parallel_threads(T, [&](unsigned tid) {
+            Multi lm; std::vector<u32> dl, hp, rv; u64 ch = 0;
+            for (u64 i = 0; i < n; ++i) {
+                if (!depth[i]) continue;
+                const u32 node = cur[i];
+                if ((node >> 6) % T != tid) continue;
+                HNode& nd = nodes_[node];
+                const u32 value = values[i];
+                bool c = false;
+                if (nd.nvals == 0) { nd.v0 = value; nd.nvals = 1; c = true; }
+                else {
+                    std::vector<u32>* m = nullptr;
+                    if (nd.nvals >= 2) { auto it = lm.find(node); m = it != lm.end() ? &it->second : &multi_.find(node)->second; }   // an older set lives in the shared map: found, never inserted, by its only writer
+                    if (nd.nvals == 1) {
+                        if (nd.v0 != value) { lm[node] = {std::min(nd.v0, value), std::max(nd.v0, value)}; nd.nvals = 2; c = true; }
+                    } else {
+                        auto it = std::lower_bound(m->begin(), m->end(), value);
+                        if (it == m->end() || *it != value) { m->insert(it, value); nd.nvals++; c = true; }
+                    }
+                }
+                if (!c) continue;
+                ++ch;
+                if (!nd.dirty) dl.push_back(node);
+                nd.dirty |= 3;
+                if (nd.token == TOK_HASH) hp.push_back(nd.parent);
+                if (!nd.alive) rv.push_back(node);
+            }
+            t_multi[tid].swap(lm); t_dirty[tid].swap(dl); t_hashpar[tid].swap(hp); t_revive[tid].swap(rv); t_changed[tid] = ch;
+        });
+        for (unsigned t = 0; t < T; ++t) {
+            changed += t_changed[t];
+            multi_.merge(t_multi[t]);
+            dirty_nodes_.insert(dirty_nodes_.end(), t_dirty[t].begin(), t_dirty[t].end());
+            for (u32 p : t_hashpar[t]) mark(p);
+            for (u32 x : t_revive[t])
+                for (; x != 0 && !nodes_[x].alive; x = nodes_[x].parent) { nodes_[x].alive = 1; nodes_[nodes_[x].parent].live_children++; live_nodes_++; }
+        }
+        for (u32 x : revive_parents)
+            for (; x != 0 && !nodes_[x].alive; x = nodes_[x].parent) { nodes_[x].alive = 1; nodes_[nodes_[x].parent].live_children++; live_nodes_++; }
+        values_size_ += changed;
+    }
+    if (prof)
+        fprintf(stderr, "insert_batch (%u threads): %llu filters: tokens %.2f s (classify %.2f, dictionary %.2f, resolve %.2f), edges %.2f s (look-ups %.2f [thread 0: probes %.2f, local sort %.2f], re-find %.2f, sort %.2f, serial %.2f, place %.2f), values %.2f s\n",
+                T, (unsigned long long)n, t_a3 - t_begin, t_a1 - t_begin, t_a2 - t_a1, t_a3 - t_a2, t_c - t_a3, t_find, t_find0, t_lsort, t_refind, t_sort, t_serial, t_place, now() - t_c);
     return changed;
 }
 
@@ -582,7 +990,18 @@ void HostTrie::compact_values() {
 bool HostTrie::sync() {
     // value words this flush appends; replaced copies become garbage.  Auto-compaction keeps both bounded: churn on
     // one popular filter would otherwise grow `values` without limit and finally wrap the 32-bit references.
-    auto pending_words = [&]() { u64 w = 0; for (u32 id : dirty_nodes_) if ((nodes_[id].dirty & 2) && nodes_[id].nvals >= 2) w += nodes_[id].nvals; return w; };
+    auto pending_words = [&]() {
+        const unsigned TT = dirty_nodes_.size() >= host_par_min(size_t(1) << 18) ? host_threads() : 1u;
+        std::vector<u64> part(TT, 0);
+        parallel_chunks(dirty_nodes_.size(), TT, [&](unsigned tid, size_t b, size_t e) {
+            u64 w = 0;
+            for (size_t k = b; k < e; ++k) { const HNode& n = nodes_[dirty_nodes_[k]]; if ((n.dirty & 2) && n.nvals >= 2) w += n.nvals; }
+            part[tid] = w;
+        });
+        u64 w = 0;
+        for (u64 x : part) w += x;
+        return w;
+    };
     u64 add_words = pending_words();
     const u64 live_words = values.size() - std::min<u64>(garbage_values, values.size());
     if (garbage_values > live_words + 65536 || values.size() + add_words > 0xFFFFFFF0ull) {
@@ -593,9 +1012,16 @@ bool HostTrie::sync() {
     const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = prof ? now() : 0;
+    const unsigned T = dirty_nodes_.size() >= host_par_min(size_t(1) << 18) || nodes_.size() >= host_par_min(size_t(1) << 20) ? host_threads() : 1u;
     if (cfilter_rebuild_) {
         // nodes that just became wide must republish their record (flag)
-        for (u32 id = 0; id < nodes_.size(); ++id) if (nodes_[id].wide && !nodes_[id].dirty) { nodes_[id].dirty = 1; dirty_nodes_.push_back(id); }
+        std::vector<std::vector<u32>> found(T);
+        parallel_chunks(nodes_.size(), T, [&](unsigned tid, size_t b, size_t e) {
+            std::vector<u32> f;
+            for (size_t id = b; id < e; ++id) if (nodes_[id].wide && !nodes_[id].dirty) { nodes_[id].dirty = 1; f.push_back(static_cast<u32>(id)); }
+            found[tid].swap(f);
+        });
+        for (const auto& f : found) dirty_nodes_.insert(dirty_nodes_.end(), f.begin(), f.end());
         cfilter_rebuild();
     }
     // pass 1: value-set references (a '#' node's parent reads the child's fresh ref in pass 2).  Sets with more than
@@ -603,13 +1029,28 @@ bool HostTrie::sync() {
     // one tile of the match kernel expands (same level0/level1 subtree) are neighbours in `values` as well.
     const double t1 = prof ? now() : 0;
     std::vector<std::pair<u64, u32>> multi;
-    for (u32 id : dirty_nodes_) {
-        if (!(nodes_[id].dirty & 2)) continue;             // record-only change: the published set stays
-        if (nodes_[id].nvals < 2) { make_ref(id); continue; }
-        u32 a = id;
-        while (nodes_[a].depth > 2) a = nodes_[a].parent;
-        const u32 tag = id == 0 ? 0u : nodes_[nodes_[id].parent].wtag;
-        multi.emplace_back((static_cast<u64>(tag) << 32) | a, id);
+    {
+        std::vector<std::vector<std::pair<u64, u32>>> t_multi(T);
+        std::vector<u64> t_garbage(T, 0);
+        parallel_chunks(dirty_nodes_.size(), T, [&](unsigned tid, size_t b, size_t e) {
+            std::vector<std::pair<u64, u32>> lm; u64 garbage = 0;
+            for (size_t k = b; k < e; ++k) {
+                const u32 id = dirty_nodes_[k];
+                HNode& n = nodes_[id];
+                if (!(n.dirty & 2)) continue;             // record-only change: the published set stays
+                if (n.nvals < 2) {                        // make_ref without the shared counters
+                    if (n.cnt16 >= 2) garbage += (n.cnt16 == CNT_BIG) ? ranges[n.ref].cnt : n.cnt16;
+                    if (n.nvals == 0) { n.ref = 0; n.cnt16 = 0; } else { n.ref = n.v0; n.cnt16 = 1; }
+                    continue;
+                }
+                u32 a = id;
+                while (nodes_[a].depth > 2) a = nodes_[a].parent;
+                const u32 tag = id == 0 ? 0u : nodes_[nodes_[id].parent].wtag;
+                lm.emplace_back((static_cast<u64>(tag) << 32) | a, id);
+            }
+            t_multi[tid].swap(lm); t_garbage[tid] = garbage;
+        });
+        for (unsigned t = 0; t < T; ++t) { multi.insert(multi.end(), t_multi[t].begin(), t_multi[t].end()); garbage_values += t_garbage[t]; }
     }
     std::sort(multi.begin(), multi.end());
     for (const auto& m : multi) make_ref(m.second);
@@ -626,8 +1067,8 @@ bool HostTrie::sync() {
             nodes_[id].dirty = 0;
         }
     };
-    const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-    if (full_edges && nd >= (size_t(1) << 18) && hw > 1 && !getenv("GM_SYNC_SERIAL")) {
+    const unsigned hw = host_threads();
+    if (full_edges && nd >= host_par_min(size_t(1) << 18) && hw > 1 && !getenv("GM_SYNC_SERIAL")) {
         size_t root_at = nd;                              // the root record is shared state (root_*): its node is written by this thread
         for (size_t i = 0; i < nd; ++i) if (dirty_nodes_[i] == 0) { root_at = i; break; }
         if (root_at != nd) std::swap(dirty_nodes_[root_at], dirty_nodes_[nd - 1]);

@@ -53,6 +53,7 @@ class HostTrie {
     bool trees_dirty = false;
     // n inserts (invalid filters are skipped); returns how many changed the set.  Same result as one-by-one insert().
     u64 insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n);
+    u64 insert_batch_parallel(const char* blob, const u32* offsets, const u32* values, u64 n, unsigned threads);   // same content, all host threads
     void reserve(u64 n_filters);
 
     // Resolve dirty nodes into slot patches (called by flush).  false: more than 2^32 live value words (references would wrap).
@@ -69,10 +70,10 @@ class HostTrie {
     u64 nodes_size() const { return live_nodes_; }     // trie.rs:154-157
 
     // ---- device mirror -------------------------------------------------------------------------
-    std::vector<EdgeSlot, HugeAlloc<EdgeSlot>> edges;
+    ZeroTable<EdgeSlot> edges;
     StableVec<Range> ranges;         // [0] reserved.  Both arrays never move in memory (gm_values_view hands out their base)
     StableVec<u32> values;
-    std::vector<DictSlot, HugeAlloc<DictSlot>> dict;
+    ZeroTable<DictSlot> dict;
     std::vector<u8> pool;
     std::vector<u32> cfilter;        // child filter of wide nodes (layout.h)
     bool cfilter_dirty = true;

@@ -241,6 +241,111 @@ def test_bulk_load_equals_one_by_one_inserts():
         assert T.match(t.encode())[0] == tree.matches(t), t
 
 
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_parallel_bulk_load_builds_the_same_trie(monkeypatch, threads):
+    """gm_bulk_load of a big batch runs on all host threads (host_trie.cpp insert_batch_parallel: per-thread tokenising with a
+    first-occurrence merge of the new level strings, level-synchronous edges with one owner thread per window of the table,
+    per-node-owner values) and the first flush after it too (child filter, value references, records).  GM_HOST_PAR_MIN=1
+    sends a small batch down those paths: same reference statistics and token numbering as one-by-one inserts, same matches
+    as the oracle, also when the batch lands on a trie that already holds filters, pruned nodes and multi-value sets."""
+    import numpy as np
+    from rmqtt_b200.engine import pack
+    rng = random.Random(97 + threads)
+    first = [rand_filter(rng) for _ in range(1500)] + ["keep/a", "keep/a", "gone/x/y", "gone/x/z"]
+    fs = [rand_filter(rng) for _ in range(6000)] + ["a/b/#/c", "x/+y", "dup/f", "dup/f", "r/s/t", "r/s/t", "gone/x/y/deeper", "keep/a", "$SYS/x", "a/$b", "+/+/#", "#", ""]
+    rng.shuffle(fs)
+    fvals = [rng.randint(0, 20) for _ in first]
+    vals = [rng.randint(0, 20) for _ in fs]
+    tree = orc.TopicTree()
+    one = Engine(host_only=True)
+    for f, v in zip(first, fvals):
+        try:
+            one.add(f, v)
+        except GpuMqttError:
+            continue
+        tree.insert(f, v)
+    for f in ("gone/x/y", "gone/x/z"):                     # prune a branch: the bulk load below revives part of it
+        for v in range(21):
+            one.remove(f, v); tree.remove(f, v)
+    n_changed = 0
+    for f, v in zip(fs, vals):
+        try:
+            n_changed += bool(one.add(f, v))
+        except GpuMqttError:
+            continue
+        tree.insert(f, v)
+    one.flush()
+
+    monkeypatch.setenv("GM_HOST_PAR_MIN", "1")
+    monkeypatch.setenv("GM_HOST_THREADS", str(threads))
+    bulk = Engine(host_only=True)
+    b0, o0 = pack(first)
+    bulk.bulk_load(b0, o0, np.asarray(fvals, dtype=np.uint32))
+    bulk.flush()
+    for f in ("gone/x/y", "gone/x/z"):
+        for v in range(21):
+            bulk.remove(f, v)
+    blob, offs = pack(fs)
+    assert bulk.bulk_load(blob, offs, np.asarray(vals, dtype=np.uint32)) == n_changed
+    bulk.flush()
+    sa, sb = one.stats(), bulk.stats()
+    for k in ("values", "nodes", "edges", "dict_entries", "plus_nodes", "max_depth"):
+        assert sa[k] == sb[k], k
+    assert sa["value_words"] - sa["garbage_value_words"] == sb["value_words"] - sb["garbage_value_words"]   # live words of the multi-value sets
+    assert sb["values"] == tree.values_size() and sb["nodes"] == tree.nodes_size()
+    ta, tb = one.debug_tables(), bulk.debug_tables()
+    da, db = ta["dict"], tb["dict"]                        # tokens are numbered by first occurrence, as one-by-one inserts number them:
+    da, db = da[da[:, 0] != 0], db[db[:, 0] != 0]          # the same (token, level string) rows, whatever the table sizes
+    assert np.array_equal(da[np.argsort(da[:, 0])], db[np.argsort(db[:, 0])])
+    T = Tables(tb)
+    for _ in range(600):
+        t = rand_topic(rng)
+        assert T.match(t.encode())[0] == tree.matches(t), t
+    # and mutations keep working on the bulk-built tables
+    for f, v in list(zip(fs, vals))[:200]:
+        try:
+            got = bulk.remove(f, v)
+        except GpuMqttError:
+            continue
+        assert got == tree.remove(f, v)
+    bulk.flush()
+    T = Tables(bulk.debug_tables())
+    assert bulk.stats()["nodes"] == tree.nodes_size()
+    for _ in range(300):
+        t = rand_topic(rng)
+        assert T.match(t.encode())[0] == tree.matches(t), t
+
+
+def test_parallel_bulk_load_makes_room_by_rehashing(monkeypatch):
+    """The parallel bulk path settles room for a whole level of new edges at once (more windows / wider windows / a bigger
+    table, host_trie.cpp step B3): a deliberately tight table (3 slots per filter, 8-slot windows) must re-hash on the way
+    and still hold every edge where the walk looks for it."""
+    import numpy as np
+    from rmqtt_b200.engine import pack
+    monkeypatch.setenv("GM_HOST_PAR_MIN", "1")
+    monkeypatch.setenv("GM_HOST_THREADS", "4")
+    monkeypatch.setenv("GM_EDGE_SLOTS_PER_FILTER", "3")
+    monkeypatch.setenv("GM_WIN_MIN_SLOTS_LOG2", "3")
+    monkeypatch.setenv("GM_EDGE_WINDOWS_LOG2", "5")
+    rng = random.Random(5)
+    fs = ["/".join([f"r{rng.randrange(6)}", f"s{rng.randrange(6)}"] + [f"x{rng.randrange(40)}" for _ in range(rng.randrange(1, 5))]) for _ in range(4000)]
+    vals = [rng.randint(0, 9) for _ in fs]
+    tree = orc.TopicTree()
+    for f, v in zip(fs, vals):
+        tree.insert(f, v)
+    eng = Engine(host_only=True)
+    blob, offs = pack(fs)
+    eng.bulk_load(blob, offs, np.asarray(vals, dtype=np.uint32))
+    eng.flush()
+    st = eng.stats()
+    assert st["values"] == tree.values_size() and st["nodes"] == tree.nodes_size()
+    assert st["edge_slots"] > 16384                        # it grew beyond what the hint reserved (3 x 4000 -> 16384 slots)
+    T = Tables(eng.debug_tables())
+    for _ in range(400):
+        t = "/".join([f"r{rng.randrange(6)}", f"s{rng.randrange(6)}"] + [f"x{rng.randrange(40)}" for _ in range(rng.randrange(0, 5))])
+        assert T.match(t.encode())[0] == tree.matches(t), t
+
+
 def test_child_adds_do_not_recopy_the_value_set_and_churn_is_compacted():
     """ADVICE r1 (host_trie.cpp make_ref): a node's multi-value set is re-published only when the SET changed, not when
     the node merely gained a child edge; replaced copies are garbage that auto-compaction bounds."""
