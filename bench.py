@@ -306,10 +306,17 @@ def run_own(args):
         sb, so, sv = wl.gen_subs(cfg)
     else:
         sb, so, sv = wl.gen_subs_sharded(cfg, regions)
+    t1 = time.time()
     eng = Engine(device=local, filters_hint=len(sv))
+    t2 = time.time()
     eng.bulk_load(sb, so, sv)
+    t3 = time.time()
     eng.flush()
     build_s = time.time() - t0
+    # gm_bulk_load + the first gm_flush are the library's build (all host threads, host_trie.cpp insert_batch_parallel); the
+    # generator of the synthetic filters is single-threaded and not part of it
+    build_parts = {"generate_filters_s": round(t1 - t0, 2), "create_and_reserve_s": round(t2 - t1, 2), "bulk_load_s": round(t3 - t2, 2),
+                   "flush_s": round(time.time() - t3, 2), "host_threads": min(64, os.cpu_count() or 1)}
     st = eng.stats()
     del sb, so
     uid = [Engine.comm_unique_id() if rank == 0 else None]
@@ -757,7 +764,7 @@ def run_own(args):
                    "matched_ids_per_topic": W["ids"] / n, "matched_filters_per_topic": W["filters"] / n, "visited_nodes_per_topic": W["visited"] / n,
                    "deferred_topics_per_batch": W["deferred"], "probe_diag": diag,
                    "trie": {k: st[k] for k in ("values", "nodes", "edges", "edge_slots", "dict_entries", "plus_nodes", "device_bytes", "max_depth")},
-                   "build_s": round(build_s, 1), "e2e_timing": "perf_counter around synchronous C-ABI calls (pinned host buffers), max over ranks"},
+                   "build_s": round(build_s, 1), "build": build_parts, "e2e_timing": "perf_counter around synchronous C-ABI calls (pinned host buffers), max over ranks"},
         "value_descriptor_mode": value_desc,
         "e2e": e2e,
         "gpu_launches": int(launches),

@@ -48,7 +48,7 @@ def build_engine(force: bool = False, verbose: bool = False) -> Path:
 def build_workload(force: bool = False) -> Path:
     src = CSRC / "workload.cpp"
     if force or _newer(WL_LIB, [src]):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(WL_LIB), str(src)])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", str(WL_LIB), str(src)])
     return WL_LIB
 
 

@@ -1127,9 +1127,7 @@ int32_t gm_retain_remove_batch(gm_engine* e, const char* blob, const uint32_t* o
 int32_t gm_retain_bulk_load(gm_engine* e, const char* blob, const uint32_t* offsets, const uint32_t* values, uint64_t n, uint64_t* n_set) {
     if (!e || (n && (!blob || !offsets || !values))) return GM_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(e->mu);
-    uint64_t ok = 0;
-    for (uint64_t i = 0; i < n; ++i)
-        if (e->rtree.set(blob + offsets[i], offsets[i + 1] - offsets[i], values[i], nullptr, nullptr) == PARSE_OK) ok++;
+    const uint64_t ok = e->rtree.set_batch(blob, offsets, values, n);
     if (n_set) *n_set = ok;
     return GM_OK;
 }

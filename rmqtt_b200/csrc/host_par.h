@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cstddef>
+#include <cstdint>
 #include <cstdlib>
 #include <thread>
 #include <vector>
@@ -48,6 +49,35 @@ inline void parallel_threads(unsigned threads, F&& fn) {
     for (unsigned t = 1; t < threads; ++t) th.emplace_back([&fn, t] { fn(t); });
     fn(0u);
     for (auto& t : th) t.join();
+}
+
+// out = the sorted, duplicate-free union of per-thread lists that are each sorted and duplicate-free.  The key space is cut
+// at sampled splitters; the thread of a range pulls its part out of every list (binary searches), sorts and de-duplicates it.
+inline void merge_sorted_unique(const std::vector<std::vector<uint64_t>>& lists, unsigned T, std::vector<uint64_t>& out) {
+    out.clear();
+    std::vector<uint64_t> samples;
+    for (const auto& l : lists) { constexpr size_t S = 64; if (!l.empty()) for (size_t k = 0; k < S; ++k) samples.push_back(l[(l.size() * (2 * k + 1)) / (2 * S)]); }
+    if (samples.empty()) return;
+    T = std::max(1u, T);
+    std::sort(samples.begin(), samples.end());
+    std::vector<uint64_t> split(T + 1, 0);             // range r = [split[r], split[r + 1]), the last one unbounded above
+    for (unsigned r = 1; r < T; ++r) split[r] = samples[(samples.size() * r) / T];
+    std::vector<std::vector<uint64_t>> seg(T);
+    parallel_threads(T, [&](unsigned r) {
+        std::vector<uint64_t> mine;
+        for (const auto& l : lists) {
+            auto a = r == 0 ? l.begin() : std::lower_bound(l.begin(), l.end(), split[r]);
+            auto b = r + 1 == T ? l.end() : std::lower_bound(l.begin(), l.end(), split[r + 1]);
+            if (a < b) mine.insert(mine.end(), a, b);
+        }
+        std::sort(mine.begin(), mine.end());
+        mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+        seg[r].swap(mine);
+    });
+    std::vector<size_t> base(T + 1, 0);
+    for (unsigned r = 0; r < T; ++r) base[r + 1] = base[r] + seg[r].size();
+    out.resize(base[T]);
+    parallel_threads(T, [&](unsigned r) { std::copy(seg[r].begin(), seg[r].end(), out.begin() + base[r]); });
 }
 
 }  // namespace gm

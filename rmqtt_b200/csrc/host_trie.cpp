@@ -514,12 +514,13 @@ struct LocalStrings {        // level strings one thread met that the dictionary
 constexpr u32 TOK_LOCAL = 0x80000000u;   // provisional token: index into the thread's LocalStrings
 }  // namespace
 
-u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const u32* values, u64 n, unsigned T) {
-    const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
+// Phase A of the bulk paths (also used by the retained tree's bulk load): level strings -> tokens on all threads.
+void HostTrie::tokenize_batch(const char* blob, const u32* offsets, u64 n, unsigned T, TokenizedBatch& tb) {
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     // ---- A0: level offsets (levels of filter i = its '/' count + 1)
-    std::vector<u64> lvl_off(n + 1, 0);
+    BigVec<u64>& lvl_off = tb.lvl_off;
+    lvl_off.assign(n + 1, 0);
     parallel_chunks(n, T, [&](unsigned, size_t b, size_t e) {
         for (size_t i = b; i < e; ++i) {
             const char* f = blob + offsets[i];
@@ -530,8 +531,10 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
         }
     });
     for (u64 i = 0; i < n; ++i) lvl_off[i + 1] += lvl_off[i];
-    std::vector<u32> toks(lvl_off[n]);
-    std::vector<uint16_t> depth(n, 0);          // 0 = invalid / too deep: skipped like insert()
+    BigVec<u32>& toks = tb.toks;
+    BigVec<uint16_t>& depth = tb.depth;
+    toks.assign(lvl_off[n], 0u);
+    depth.assign(n, 0);                         // 0 = invalid / too deep: skipped like insert()
     // ---- A1: validate + tokens the dictionary already holds
     std::vector<LocalStrings> locals(T);
     std::vector<std::pair<size_t, size_t>> chunk_of(T, {0, 0});
@@ -624,12 +627,24 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
             for (u32 k = 0; k < depth[i]; ++k) if (out[k] & TOK_LOCAL) out[k] = L.ents[out[k] & ~TOK_LOCAL].tok;
         }
     });
-    locals.clear(); locals.shrink_to_fit();
+    tb.t_classify = t_a1 - t_begin; tb.t_dictionary = t_a2 - t_a1; tb.t_resolve = now() - t_a2;
+}
+
+
+u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const u32* values, u64 n, unsigned T) {
+    const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    TokenizedBatch tb;
+    tokenize_batch(blob, offsets, n, T, tb);
+    const BigVec<u64>& lvl_off = tb.lvl_off;
+    const BigVec<u32>& toks = tb.toks;
+    const BigVec<uint16_t>& depth = tb.depth;
     const double t_a3 = now();
 
     // ---- B: level-synchronous edges
-    std::vector<u32> cur(n, 0u);
-    std::vector<u8> ctag(n, nodes_[0].wtag);
+    BigVec<u32> cur(n, 0u);
+    BigVec<u8> ctag(n, nodes_[0].wtag);
     u32 deepest = 0;
     for (u64 i = 0; i < n; ++i) deepest = std::max<u32>(deepest, depth[i]);
     std::vector<std::vector<u64>> mkeys(T);
@@ -672,29 +687,8 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
         // (2) new edges of this level: sorted, unique over all threads.  Key ranges are cut at sampled splitters; the thread of a
         //     range pulls its part out of every thread's sorted list.
         std::vector<u64> ukeys;
-        {
-            std::vector<u64> samples;
-            for (const auto& mk : mkeys) { constexpr size_t S = 64; if (!mk.empty()) for (size_t k = 0; k < S; ++k) samples.push_back(mk[(mk.size() * (2 * k + 1)) / (2 * S)]); }
-            if (samples.empty()) continue;                 // every edge of this level existed
-            std::sort(samples.begin(), samples.end());
-            std::vector<u64> split(T + 1, 0);              // range r = [split[r], split[r + 1]), the last one unbounded above
-            for (unsigned r = 1; r < T; ++r) split[r] = samples[(samples.size() * r) / T];
-            std::vector<std::vector<u64>> seg(T);
-            parallel_threads(T, [&](unsigned r) {
-                std::vector<u64>& out = seg[r];
-                for (const auto& mk : mkeys) {
-                    auto a = r == 0 ? mk.begin() : std::lower_bound(mk.begin(), mk.end(), split[r]);
-                    auto b = r + 1 == T ? mk.end() : std::lower_bound(mk.begin(), mk.end(), split[r + 1]);
-                    if (a < b) out.insert(out.end(), a, b);
-                }
-                std::sort(out.begin(), out.end());
-                out.erase(std::unique(out.begin(), out.end()), out.end());
-            });
-            std::vector<size_t> base(T + 1, 0);
-            for (unsigned r = 0; r < T; ++r) base[r + 1] = base[r] + seg[r].size();
-            ukeys.resize(base[T]);
-            parallel_threads(T, [&](unsigned r) { std::copy(seg[r].begin(), seg[r].end(), ukeys.begin() + base[r]); });
-        }
+        merge_sorted_unique(mkeys, T, ukeys);
+        if (ukeys.empty()) continue;                   // every edge of this level existed
         const size_t nu = ukeys.size();
         const double tb2 = now();
         t_sort += tb2 - tb1;
@@ -703,7 +697,7 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
         if (first_new + nu > 0xFFFFFFF0ull) { fprintf(stderr, "gpumqtt: bulk load exceeds 2^32 trie nodes\n"); std::abort(); }
         nodes_.resize(first_new + nu);
         if (d == 1) for (size_t g = 0; g < nu; ++g) nodes_[first_new + g].wtag = static_cast<u8>(pick_tag());
-        std::vector<u8> own(nu);
+        BigVec<u8> own(nu);
         std::vector<u64> add_w;
         for (;;) {
             const u32 nm = nwin_mask();
@@ -856,7 +850,7 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
     }
     if (prof)
         fprintf(stderr, "insert_batch (%u threads): %llu filters: tokens %.2f s (classify %.2f, dictionary %.2f, resolve %.2f), edges %.2f s (look-ups %.2f [thread 0: probes %.2f, local sort %.2f], re-find %.2f, sort %.2f, serial %.2f, place %.2f), values %.2f s\n",
-                T, (unsigned long long)n, t_a3 - t_begin, t_a1 - t_begin, t_a2 - t_a1, t_a3 - t_a2, t_c - t_a3, t_find, t_find0, t_lsort, t_refind, t_sort, t_serial, t_place, now() - t_c);
+                T, (unsigned long long)n, t_a3 - t_begin, tb.t_classify, tb.t_dictionary, tb.t_resolve, t_c - t_a3, t_find, t_find0, t_lsort, t_refind, t_sort, t_serial, t_place, now() - t_c);
     return changed;
 }
 

@@ -53,6 +53,10 @@ class HostTrie {
     bool trees_dirty = false;
     // n inserts (invalid filters are skipped); returns how many changed the set.  Same result as one-by-one insert().
     u64 insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n);
+    // Levels of a whole batch as tokens (new level strings are interned in first-occurrence order, as parse() would do one by
+    // one): toks[lvl_off[i] .. +depth[i]) for filter i; depth 0 = invalid or too deep.
+    struct TokenizedBatch { BigVec<u64> lvl_off; BigVec<u32> toks; BigVec<uint16_t> depth; double t_classify = 0, t_dictionary = 0, t_resolve = 0; };
+    void tokenize_batch(const char* blob, const u32* offsets, u64 n, unsigned threads, TokenizedBatch& out);
     u64 insert_batch_parallel(const char* blob, const u32* offsets, const u32* values, u64 n, unsigned threads);   // same content, all host threads
     void reserve(u64 n_filters);
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <utility>
+#include <vector>
 
 #include "host_par.h"
 
@@ -19,7 +20,7 @@ template <class T>
 struct HugeAlloc {
     using value_type = T;
     static constexpr size_t kHugeThreshold = size_t(4) << 20;
-    static constexpr size_t kTouchThreshold = size_t(64) << 20;
+    static constexpr size_t kTouchThreshold = size_t(8) << 20;
     static constexpr size_t kAlign = alignof(T) > 64 ? alignof(T) : 64;
     HugeAlloc() = default;
     template <class U> HugeAlloc(const HugeAlloc<U>&) {}
@@ -50,6 +51,9 @@ struct HugeAlloc {
     template <class U> bool operator==(const HugeAlloc<U>&) const { return true; }
     template <class U> bool operator!=(const HugeAlloc<U>&) const { return false; }
 };
+
+// std::vector for the multi-MB working arrays of the bulk paths: its pages are first touched by all host threads
+template <class T> using BigVec = std::vector<T, HugeAlloc<T>>;
 
 // Fixed-size table of plain records whose empty state is all-zero bytes (the open-addressing tables: edges, dictionary):
 // `assign_zero` takes fresh zero pages from the allocator — the parallel first touch above IS the initialisation, there is

@@ -76,6 +76,10 @@ class RetainTreeHost {
     int set(const char* topic, u32 len, u32 value, bool* had_old, u32* old);
     // RetainTree::remove (retain.rs:237-257) with bottom-up pruning.
     int remove(const char* topic, u32 len, bool* had_old, u32* old);
+    // n sets (start-up / restore: every retained message re-enters the tree, rmqtt-retainer/src/retainer.rs load path).
+    // Returns the number of valid topics.  Into an EMPTY tree the host tree and its device image are built together, level
+    // by level, on all host threads (set_batch_build); otherwise one by one.
+    u64 set_batch(const char* blob, const u32* offsets, const u32* values, u64 n);
 
     // Dictionary compaction (HostTrie::compact): the level tokens this tree holds, and their replacement.
     std::vector<u32> used_tokens() const;
@@ -91,7 +95,7 @@ class RetainTreeHost {
     void flatten();                                     // host tree -> device-layout arrays below
     std::vector<RNode, HugeAlloc<RNode>> rnodes;        // host bookkeeping, one per device node (not shipped)
     std::vector<RKid, HugeAlloc<RKid>> rkids;
-    std::vector<REdge, HugeAlloc<REdge>> redges;
+    ZeroTable<REdge> redges;                            // empty slot = all-zero bytes (child == 0)
     std::vector<u32, HugeAlloc<u32>> rvals;
     std::vector<u32> dirty_kids, dirty_edges, dirty_vals;   // entries changed in place since the last flush
     u32 root_plain_kids = 0, root_plain_val_hi = 0, max_depth = 0;
@@ -109,8 +113,8 @@ class RetainTreeHost {
     // ---- in-place maintenance of the device image ----------------------------------------------
     static constexpr u32 NODEV = 0xFFFFFFFFu;
     bool flat_valid_ = false;                    // the arrays mirror the host tree (else: flatten at the next flush)
-    std::vector<u32> rparent_, rtoken_, rcap_;   // per device node: parent, level token, capacity of its child block
-    std::vector<u8> in_rvals_;                   // per device node: its value sits at rvals[val_lo] (it had one at flatten time)
+    BigVec<u32> rparent_, rtoken_, rcap_;        // per device node: parent, level token, capacity of its child block
+    BigVec<u8> in_rvals_;                   // per device node: its value sits at rvals[val_lo] (it had one at flatten time)
     u64 garbage_kids_ = 0, dead_nodes_ = 0, live_edges_ = 0;
     void give_up() { flat_valid_ = false; dirty = true; }
     u32 edge_slot_of(u32 parent_dev, u32 token) const;          // slot in redges or NODEV
@@ -120,10 +124,11 @@ class RetainTreeHost {
     bool dev_add_child(u32 parent_dev, u32 token, u32 child_dev);
     void dev_set(u32 host_node, bool had_val, u32 value, u32 depth);
     void dev_unset(u32 host_node);
+    u64 set_batch_build(const char* blob, const u32* offsets, const u32* values, u64 n, unsigned threads);
     int parse(const char* s, u32 len, bool create, std::vector<u32>& toks);
     u32 child_of(u32 node, u32 token) const;
     HostTrie* dict_;
-    std::vector<HN> nodes_;
+    BigVec<HN> nodes_;
     std::vector<u32> free_;
     std::vector<u32> toks_;
     u64 n_values_ = 0, n_nodes_ = 0;

@@ -8,7 +8,9 @@
 // Every item i draws from its own splitmix64 stream seeded by (seed, i): generation is order-free.
 #include <cmath>
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -114,6 +116,44 @@ constexpr int kMaxLen = 64;
 
 }  // namespace
 
+// ---- the big generators on all host threads -------------------------------------------------------------------------
+// Items are order-free (own random stream per index): every thread generates a contiguous share into private buffers, the
+// shares are stitched together at their byte offsets — the same bytes the serial loop writes.
+template <class Gen>   // gen(first, count, blob, offs, values or nullptr) -> items kept; *bytes
+static uint64_t stitched(uint64_t first, uint64_t n, char* blob, uint32_t* offs, uint32_t* values, uint64_t* bytes_out, Gen gen) {
+    const unsigned T = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(std::min(64u, std::max(1u, std::thread::hardware_concurrency())), n / 100000)));
+    if (T <= 1) { uint64_t b = 0; const uint64_t k = gen(first, n, blob, offs, values, &b); if (bytes_out) *bytes_out = b; return k; }
+    struct Part { std::vector<char> blob; std::vector<uint32_t> offs, values; uint64_t kept = 0, bytes = 0, b = 0, e = 0; };
+    std::vector<Part> parts(T);
+    const uint64_t chunk = (n + T - 1) / T;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) {
+        Part& pt = parts[t];
+        pt.b = std::min<uint64_t>(n, t * chunk); pt.e = std::min<uint64_t>(n, pt.b + chunk);
+        th.emplace_back([&pt, &gen, first, values] {
+            const uint64_t cnt = pt.e - pt.b;
+            pt.blob.resize(cnt * kMaxLen + 16); pt.offs.resize(cnt + 1);
+            if (values) pt.values.resize(cnt);
+            pt.kept = gen(first + pt.b, cnt, pt.blob.data(), pt.offs.data(), values ? pt.values.data() : nullptr, &pt.bytes);
+        });
+    }
+    for (auto& x : th) x.join();
+    th.clear();
+    std::vector<uint64_t> kbase(T + 1, 0), bbase(T + 1, 0);
+    for (unsigned t = 0; t < T; ++t) { kbase[t + 1] = kbase[t] + parts[t].kept; bbase[t + 1] = bbase[t] + parts[t].bytes; }
+    for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+            const Part& pt = parts[t];
+            std::memcpy(blob + bbase[t], pt.blob.data(), pt.bytes);
+            for (uint64_t k = 0; k < pt.kept; ++k) offs[kbase[t] + k] = pt.offs[k] + static_cast<uint32_t>(bbase[t]);
+            if (values) std::memcpy(values + kbase[t], pt.values.data(), pt.kept * sizeof(uint32_t));
+        });
+    for (auto& x : th) x.join();
+    offs[kbase[T]] = static_cast<uint32_t>(bbase[T]);
+    if (bytes_out) *bytes_out = bbase[T];
+    return kbase[T];
+}
+
 extern "C" {
 
 struct wl_params {
@@ -130,7 +170,7 @@ uint32_t wl_max_len() { return kMaxLen; }
 // Subscriptions [first, first+n).  blob must hold n*wl_max_len() bytes, offs n+1 entries.  Returns bytes written.
 // Mix: u<p_plus: replace 1 (80%) or 2 (20%) distinct levels of {1..5} by '+' (and with
 // p_root_plus also level 0); p_plus<=u<p_plus+p_hash: truncate to depth d (2:5% 3:45% 4:30% 5:20%) + '#'; else exact.
-uint64_t wl_gen_subs(const wl_params* w, uint64_t first, uint64_t n, char* blob, uint32_t* offs) {
+static uint64_t gen_subs_serial(const wl_params* w, uint64_t first, uint64_t n, char* blob, uint32_t* offs) {
     Params p = cvt(w);
     char* o = blob;
     for (uint64_t k = 0; k < n; ++k) {
@@ -158,7 +198,7 @@ uint64_t wl_gen_subs(const wl_params* w, uint64_t first, uint64_t n, char* blob,
 // Root-hash shard of the subscription set: keeps subscription i iff its level 0 is '+' (replicated on every
 // shard) or its region is flagged in region_keep[R].  values[k] = original subscription index.
 // Returns the number kept; *bytes = blob bytes written.
-uint64_t wl_gen_subs_sharded(const wl_params* w, uint64_t first, uint64_t n, const uint8_t* region_keep,
+static uint64_t gen_subs_sharded_serial(const wl_params* w, uint64_t first, uint64_t n, const uint8_t* region_keep,
                              char* blob, uint32_t* offs, uint32_t* values, uint64_t* bytes) {
     Params p = cvt(w);
     char* o = blob;
@@ -192,7 +232,7 @@ uint64_t wl_gen_subs_sharded(const wl_params* w, uint64_t first, uint64_t n, con
 // Publish topics [first, first+n).  frac_from_subs of them re-use the concrete topic of a uniformly drawn
 // subscription in [0, n_subs) (C1: 0.5); the rest are uniform over the topic space, optionally restricted to
 // the given regions (multi-GPU partitioning by root).  `stream` separates independent batches.
-uint64_t wl_gen_topics(const wl_params* w, uint64_t first, uint64_t n, double frac_from_subs, uint64_t n_subs,
+static uint64_t gen_topics_serial(const wl_params* w, uint64_t first, uint64_t n, double frac_from_subs, uint64_t n_subs,
                        const uint32_t* regions, uint32_t nreg, uint64_t stream, char* blob, uint32_t* offs) {
     Params p = cvt(w);
     char* o = blob;
@@ -232,7 +272,7 @@ uint64_t wl_gen_topics_zipf(const wl_params* w, uint64_t first, uint64_t n, uint
 }
 
 // Retained topics: n DISTINCT topics sampled without replacement (item i -> permute(i)).
-uint64_t wl_gen_retained(const wl_params* w, uint64_t first, uint64_t n, char* blob, uint32_t* offs) {
+static uint64_t gen_retained_serial(const wl_params* w, uint64_t first, uint64_t n, char* blob, uint32_t* offs) {
     Params p = cvt(w);
     char* o = blob;
     uint64_t N = space(p);
@@ -267,6 +307,26 @@ uint64_t wl_gen_retain_filters(const wl_params* w, uint64_t first, uint64_t n, c
     }
     offs[n] = static_cast<uint32_t>(o - blob);
     return static_cast<uint64_t>(o - blob);
+}
+
+// ---- the big generators on all host threads: see `stitched` above ----
+uint64_t wl_gen_subs(const wl_params* w, uint64_t first, uint64_t n, char* blob, uint32_t* offs) {
+    uint64_t bytes = 0;
+    stitched(first, n, blob, offs, nullptr, &bytes, [w](uint64_t f, uint64_t c, char* b, uint32_t* o, uint32_t*, uint64_t* by) { *by = gen_subs_serial(w, f, c, b, o); return c; });
+    return bytes;
+}
+uint64_t wl_gen_subs_sharded(const wl_params* w, uint64_t first, uint64_t n, const uint8_t* region_keep, char* blob, uint32_t* offs, uint32_t* values, uint64_t* bytes) {
+    return stitched(first, n, blob, offs, values, bytes, [w, region_keep](uint64_t f, uint64_t c, char* b, uint32_t* o, uint32_t* v, uint64_t* by) { return gen_subs_sharded_serial(w, f, c, region_keep, b, o, v, by); });
+}
+uint64_t wl_gen_topics(const wl_params* w, uint64_t first, uint64_t n, double frac_from_subs, uint64_t n_subs, const uint32_t* regions, uint32_t nreg, uint64_t stream, char* blob, uint32_t* offs) {
+    uint64_t bytes = 0;
+    stitched(first, n, blob, offs, nullptr, &bytes, [=](uint64_t f, uint64_t c, char* b, uint32_t* o, uint32_t*, uint64_t* by) { *by = gen_topics_serial(w, f, c, frac_from_subs, n_subs, regions, nreg, stream, b, o); return c; });
+    return bytes;
+}
+uint64_t wl_gen_retained(const wl_params* w, uint64_t first, uint64_t n, char* blob, uint32_t* offs) {
+    uint64_t bytes = 0;
+    stitched(first, n, blob, offs, nullptr, &bytes, [w](uint64_t f, uint64_t c, char* b, uint32_t* o, uint32_t*, uint64_t* by) { *by = gen_retained_serial(w, f, c, b, o); return c; });
+    return bytes;
 }
 
 // level-0 string of region r ("reg-%02d"); returns length

@@ -92,6 +92,68 @@ def test_random_differential(seed):
                 assert got == want, f
 
 
+@pytest.mark.parametrize("threads", [2, 5])
+def test_bulk_load_builds_tree_and_image_level_by_level(monkeypatch, threads):
+    """gm_retain_bulk_load into an empty tree builds the host tree and its device image together on all host threads
+    (retain_tree.cpp set_batch_build: sorted (parent, token) keys per level, pre-order numbers from subtree sizes).  The image
+    must be the one set() x n + flatten() produce — array for array — and the tree must keep working incrementally."""
+    rng = random.Random(300 + threads)
+    topics = [rand_topic(rng, max_depth=5) if rng.random() < 0.9 else rand_filter(rng, 5) for _ in range(5000)]
+    topics += ["$SYS/broker/up", "$SYS/broker/load", "$q/x", "", "/", "a//b", "dup/t", "dup/t", "lit/#", "lit/+/x", "bad/#/x", "a/$b"]
+    rng.shuffle(topics)
+    vals = [rng.randint(0, 2**32 - 2) for _ in topics]
+    one, tree = Engine(host_only=True), orc.RetainTree()
+    n_ok = 0
+    for t, v in zip(topics, vals):
+        try:
+            one.retain_set(t, v)
+        except GpuMqttError:
+            continue
+        tree.remove(t); tree.insert(t, v)
+        n_ok += 1
+    ta = one.debug_tables()                               # flushes: flatten()
+    monkeypatch.setenv("GM_HOST_PAR_MIN", "1")
+    monkeypatch.setenv("GM_HOST_THREADS", str(threads))
+    bulk = Engine(host_only=True)
+    blob, offs = pack(topics)
+    assert bulk.retain_bulk_load(blob, offs, np.asarray(vals, dtype=np.uint32)) == n_ok
+    tb = bulk.debug_tables()
+    assert int(tb["rstats"][0]) == 1 and int(tb["rstats"][5]) == 1       # built once, image valid: the flush had nothing to flatten
+    for name in ("rnodes", "rkids", "rvals"):
+        assert np.array_equal(ta[name], tb[name]), name
+    ea, eb = ta["redges"], tb["redges"]                   # the hash table: the same entries (colliding ones may sit in other slots)
+    ea, eb = ea[ea[:, 2] != 0], eb[eb[:, 2] != 0]
+    assert np.array_equal(ea[np.lexsort(ea.T[::-1])], eb[np.lexsort(eb.T[::-1])])
+    sa, sb = one.stats(), bulk.stats()
+    assert sa["retained_values"] == sb["retained_values"] == tree.values_size() and sa["retained_nodes"] == sb["retained_nodes"] == tree.nodes_size()
+    R, t = _tables(bulk)
+    _plain_split(bulk, R, t, ["$SYS", "$q", "$share"])
+    for _ in range(300):
+        f = rand_filter(rng, 6)
+        assert R.match(f.encode()) == tree.matches(f), f
+    # incremental edits on the bulk-built tree (in-place patches, then a re-pack)
+    for t_ in topics[:300]:
+        try:
+            got = bulk.retain_remove(t_)
+        except GpuMqttError:
+            continue
+        assert got == tree.remove(t_)
+    for k in range(200):
+        t_, v = rand_topic(rng, max_depth=5), rng.randint(0, 2**32 - 2)
+        try:
+            old = bulk.retain_set(t_, v)
+        except GpuMqttError:
+            continue
+        prev = tree.remove(t_); tree.insert(t_, v)
+        assert old == prev
+    R, t = _tables(bulk)
+    _plain_split(bulk, R, t, ["$SYS", "$q", "$share"])
+    assert bulk.stats()["retained_nodes"] == tree.nodes_size()
+    for _ in range(300):
+        f = rand_filter(rng, 6)
+        assert R.match(f.encode()) == tree.matches(f), f
+
+
 def test_republish_with_the_same_handle_does_not_dirty_the_device_copy():
     eng = Engine(host_only=True)
     eng.retain_set("a/b", 7)
