@@ -292,6 +292,7 @@ def run_own(args):
     lib = N.lib()
     if world > 1:
         lib.gm_bind_thread_near_device(local)      # one process per GPU: its host threads and buffers live next to its GPU (2-socket hosts)
+        os.environ.setdefault("GM_HOST_THREADS", str(max(1, min(64, (os.cpu_count() or 1) // world))))   # the bulk build of every rank runs at the same time
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -316,7 +317,7 @@ def run_own(args):
     # gm_bulk_load + the first gm_flush are the library's build (all host threads, host_trie.cpp insert_batch_parallel); the
     # generator of the synthetic filters is single-threaded and not part of it
     build_parts = {"generate_filters_s": round(t1 - t0, 2), "create_and_reserve_s": round(t2 - t1, 2), "bulk_load_s": round(t3 - t2, 2),
-                   "flush_s": round(time.time() - t3, 2), "host_threads": min(64, os.cpu_count() or 1)}
+                   "flush_s": round(time.time() - t3, 2), "host_threads": int(os.environ.get("GM_HOST_THREADS", min(64, os.cpu_count() or 1)))}
     st = eng.stats()
     del sb, so
     uid = [Engine.comm_unique_id() if rank == 0 else None]
