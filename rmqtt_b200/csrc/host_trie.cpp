@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <queue>
 #include <thread>
 #include <cstdlib>
 #include <cstring>
@@ -642,15 +643,19 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
     const BigVec<uint16_t>& depth = tb.depth;
     const double t_a3 = now();
 
-    // ---- B: level-synchronous edges
+    // ---- B: nodes, level by level.  Nodes created by this batch (number >= bulk_first) have no edge in the table until the
+    //      placement at the end: a look-up below one of them is a miss without a probe.
+    const u32 bulk_first = static_cast<u32>(nodes_.size());
     BigVec<u32> cur(n, 0u);
     BigVec<u8> ctag(n, nodes_[0].wtag);
     u32 deepest = 0;
     for (u64 i = 0; i < n; ++i) deepest = std::max<u32>(deepest, depth[i]);
-    std::vector<std::vector<u64>> mkeys(T);
-    std::vector<std::vector<u32>> midx(T);
-    double t_find = 0, t_sort = 0, t_serial = 0, t_place = 0, t_lsort = 0, t_find0 = 0, t_refind = 0;
-    u64 new_edges_total = 0;
+    std::vector<std::vector<std::pair<u64, u32>>> pairs(T);     // per thread: (edge key, filter) of the misses, sorted by key
+    std::vector<std::vector<u64>> mkeys(T);                      // ... their distinct keys
+    std::vector<std::vector<u32>> mcount(T);                     // ... and how many filters of the thread wait for each
+    BigVec<u32> new_weight;                                      // per new node: filters of the batch that run through its edge
+    new_weight.reserve(std::min<u64>(toks.size(), n * 3 + 1024));
+    double t_find = 0, t_sort = 0, t_serial = 0, t_nodes = 0, t_lsort = 0, t_find0 = 0, t_assign = 0;
     std::vector<u32> revive_parents;           // dead nodes that gained a (live) child
     for (u32 d = 0; d < deepest; ++d) {
         const double tb0 = now();
@@ -658,103 +663,90 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
         {
             const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
             parallel_chunks(n, T, [&](unsigned tid, size_t b, size_t e) {
-                std::vector<u64> mk; std::vector<u32> mi;       // thread-private while they grow; the capacity of the last level is reused
-                mk.swap(mkeys[tid]); mi.swap(midx[tid]);
-                mk.clear(); mi.clear();
+                std::vector<std::pair<u64, u32>> pr; std::vector<u64> mk; std::vector<u32> mc;   // thread-private while they grow; capacity of the last level reused
+                pr.swap(pairs[tid]); mk.swap(mkeys[tid]); mc.swap(mcount[tid]);
+                pr.clear(); mk.clear(); mc.clear();
                 constexpr size_t G = 32;
                 for (size_t g0 = b; g0 < e; g0 += G) {
                     const size_t g1 = std::min(e, g0 + G);
                     for (size_t i = g0; i < g1; ++i)
-                        if (depth[i] > d) __builtin_prefetch(&edges[edge_slot0(cur[i], toks[lvl_off[i] + d], ctag[i], wm, ws, nm)]);
+                        if (depth[i] > d && cur[i] < bulk_first) __builtin_prefetch(&edges[edge_slot0(cur[i], toks[lvl_off[i] + d], ctag[i], wm, ws, nm)]);
                     for (size_t i = g0; i < g1; ++i) {
                         if (depth[i] <= d) continue;
                         const u32 tok = toks[lvl_off[i] + d];
-                        const u32 slot = find_edge(cur[i], tok, ctag[i]);
-                        if (slot == NOSLOT) { mk.push_back((static_cast<u64>(cur[i]) << 32) | tok); mi.push_back(static_cast<u32>(i)); }
+                        const u32 slot = cur[i] < bulk_first ? find_edge(cur[i], tok, ctag[i]) : NOSLOT;
+                        if (slot == NOSLOT) pr.emplace_back((static_cast<u64>(cur[i]) << 32) | tok, static_cast<u32>(i));
                         else { cur[i] = edges[slot].child; ctag[i] = static_cast<u8>(edges[slot].mask >> WTAG_SHIFT); }
                     }
                 }
                 const double ts0 = tid == 0 ? now() : 0;
-                std::sort(mk.begin(), mk.end());
-                mk.erase(std::unique(mk.begin(), mk.end()), mk.end());
+                std::sort(pr.begin(), pr.end());
+                for (size_t k = 0; k < pr.size(); ++k) { if (k && pr[k].first == pr[k - 1].first) mc.back()++; else { mk.push_back(pr[k].first); mc.push_back(1u); } }
                 if (tid == 0) { t_lsort += now() - ts0; t_find0 += ts0 - tb0; }
-                if (prof && getenv("GM_BULK_PROFILE_LEVELS")) fprintf(stderr, "  level %u thread %u: done +%.3f (%zu misses)\n", d, tid, now() - tb0, mi.size());
-                mk.swap(mkeys[tid]); mi.swap(midx[tid]);
+                pr.swap(pairs[tid]); mk.swap(mkeys[tid]); mc.swap(mcount[tid]);
             });
         }
         const double tb1 = now();
         t_find += tb1 - tb0;
-        // (2) new edges of this level: sorted, unique over all threads.  Key ranges are cut at sampled splitters; the thread of a
-        //     range pulls its part out of every thread's sorted list.
+        // (2) new edges of this level: sorted, unique over all threads
         std::vector<u64> ukeys;
         merge_sorted_unique(mkeys, T, ukeys);
         if (ukeys.empty()) continue;                   // every edge of this level existed
         const size_t nu = ukeys.size();
         const double tb2 = now();
         t_sort += tb2 - tb1;
-        // (3) serial: node numbers, window tags of new depth-2 subtrees, room in the table
+        // (3) node numbers; weights; window tags of new depth-2 subtrees
         const size_t first_new = nodes_.size();
         if (first_new + nu > 0xFFFFFFF0ull) { fprintf(stderr, "gpumqtt: bulk load exceeds 2^32 trie nodes\n"); std::abort(); }
         nodes_.resize(first_new + nu);
-        if (d == 1) for (size_t g = 0; g < nu; ++g) nodes_[first_new + g].wtag = static_cast<u8>(pick_tag());
-        BigVec<u8> own(nu);
-        std::vector<u64> add_w;
-        for (;;) {
-            const u32 nm = nwin_mask();
-            std::vector<std::vector<u64>> hist(T, std::vector<u64>(size_t(nm) + 1, 0));
-            parallel_chunks(nu, T, [&](unsigned tid, size_t b, size_t e) {
-                for (size_t g = b; g < e; ++g) { const u32 w = nodes_[ukeys[g] >> 32].wtag & nm; own[g] = static_cast<u8>(w); hist[tid][w]++; }
-            });
-            add_w.assign(size_t(nm) + 1, 0);
-            for (const auto& h : hist) for (size_t w = 0; w <= nm; ++w) add_w[w] += h[w];
-            const u64 win_slots = edges.size() >> nwin_log2;
-            bool fits = (edge_count_ + nu) * 2 <= edges.size();
-            for (size_t w = 0; fits && w <= nm; ++w) fits = (win_count_[w] + add_w[w]) * 2 <= win_slots;
-            if (fits) break;
-            if ((edge_count_ + nu) * 4 > edges.size() || nwin_log2 == 0) rehash_edges(edges.size() * 2);
-            else { win_min_log2_ = win_shift() + 2; rehash_edges(edges.size()); }
+        new_weight.resize(first_new - bulk_first + nu, 0u);
+        u32* weight = new_weight.data() + (first_new - bulk_first);
+        parallel_threads(T, [&](unsigned tid) {
+            const auto& mk = mkeys[tid]; const auto& mc = mcount[tid];
+            if (mk.empty()) return;
+            size_t g = static_cast<size_t>(std::lower_bound(ukeys.begin(), ukeys.end(), mk[0]) - ukeys.begin());
+            for (size_t k = 0; k < mk.size(); ++k) { while (ukeys[g] != mk[k]) ++g; __atomic_fetch_add(&weight[g], mc[k], __ATOMIC_RELAXED); }
+        });
+        if (d == 1) {
+            // Window tags of the new depth-2 subtrees.  One-by-one inserts must pick a tag before they know how big a subtree
+            // becomes (pick_tag); here every filter of the batch is known: a subtree weighs the filters that run through it, and
+            // the heaviest goes first to the least-loaded tag (LPT).  Balanced windows = short probe chains in the match kernel.
+            std::vector<u32> order(nu);
+            for (size_t g = 0; g < nu; ++g) order[g] = static_cast<u32>(g);
+            std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return weight[a] > weight[b]; });
+            using Load = std::pair<u64, u32>;
+            std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+            for (u32 t = 1; t < WTAG_COUNT; ++t) heap.push(Load{tag_count_[t] + 64u * tag_anchors_[t], t});
+            for (u32 g : order) {
+                Load l = heap.top(); heap.pop();
+                nodes_[first_new + g].wtag = static_cast<u8>(l.second);
+                tag_anchors_[l.second]++; anchors_++;
+                l.first += 64u + 3ull * weight[g];           // ~3 edges per filter below depth 2 on IoT-shaped sets; what matters is the proportion
+                heap.push(l);
+            }
         }
         const double tb3 = now();
         t_serial += tb3 - tb2;
-        // (4) every window belongs to one thread
+        // (4) the new nodes and what they change in their parents.  The keys are sorted by parent: a thread takes a run of whole
+        //     parents, so nothing here is shared between threads.
         {
-            const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
-            std::vector<std::vector<u32>> t_dirty(T);
+            std::vector<std::vector<u32>> t_dirty(T), t_revive(T);
             std::vector<u64> t_plus(T, 0);
             std::vector<u8> t_cf(T, 0);
             const u32 child_depth = d + 1;
-            std::vector<std::vector<u64>> t_tag(T), t_win(T);
-            std::vector<std::vector<u32>> t_revive(T);
-            parallel_threads(T, [&](unsigned tid) {
-                std::vector<u32> mine;
-                for (size_t g = 0; g < nu; ++g) if (own[g] % T == tid) mine.push_back(static_cast<u32>(g));
-                // everything this thread counts stays private until the join (neighbouring counters of other threads share cache lines)
-                std::vector<u32> dl, rv;
-                std::vector<u64> l_tag(WTAG_COUNT, 0), l_win(size_t(nm) + 1, 0);
-                u64 l_plus = 0; u8 l_cf = 0;
-                for (size_t q = 0; q < mine.size(); ++q) {
-                    if (q + 8 < mine.size()) {
-                        const u64 k8 = ukeys[mine[q + 8]];
-                        const u32 p8 = static_cast<u32>(k8 >> 32);
-                        __builtin_prefetch(&edges[edge_slot0(p8, static_cast<u32>(k8), nodes_[p8].wtag, wm, ws, nm)], 1);
-                    }
-                    const size_t g = mine[q];
-                    const u32 parent = static_cast<u32>(ukeys[g] >> 32), token = static_cast<u32>(ukeys[g]);
+            parallel_chunks(nu, T, [&](unsigned tid, size_t b, size_t e) {
+                auto parent_of = [&](size_t g) { return static_cast<u32>(ukeys[g] >> 32); };
+                while (b > 0 && b < nu && parent_of(b) == parent_of(b - 1)) ++b;       // the run of a parent belongs to the chunk it starts in
+                while (e > 0 && e < nu && parent_of(e) == parent_of(e - 1)) ++e;
+                std::vector<u32> dl, rv; u64 l_plus = 0; u8 l_cf = 0;
+                for (size_t g = b; g < e; ++g) {
+                    const u32 parent = parent_of(g), token = static_cast<u32>(ukeys[g]);
                     const u32 id = static_cast<u32>(first_new + g);
                     HNode& pn = nodes_[parent];
-                    const u32 ptag = pn.wtag;
                     HNode& c = nodes_[id];
                     c.parent = parent; c.token = token; c.depth = static_cast<uint16_t>(child_depth);
-                    if (child_depth <= 1) c.wtag = 0; else if (child_depth != 2) c.wtag = static_cast<u8>(ptag);   // depth 2: picked in (3)
-                    u32 i = edge_slot0(parent, token, ptag, wm, ws, nm);
-                    while (edges[i].child != 0) i = edge_next(i, wm);
-                    EdgeSlot es{};
-                    es.parent = parent; es.token = token; es.child = id;
-                    es.plus = 0; es.hash_ref = 0; es.own_ref = 0; es.mask = static_cast<u32>(c.wtag) << WTAG_SHIFT; es.cnts = 0;
-                    edges[i] = es;
-                    c.edge_slot = i;
-                    l_tag[ptag]++;
-                    l_win[ptag & nm]++;
+                    if (child_depth <= 1) c.wtag = 0; else if (child_depth != 2) c.wtag = pn.wtag;   // depth 2: picked in (3)
+                    c.edge_slot = NOSLOT;                  // placed at the end
                     pn.mask |= mask_bit(token);
                     if (token != TOK_PLUS && token != TOK_HASH) pn.lit_children++;
                     if (pn.wide) l_cf = 1;
@@ -769,33 +761,89 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
                     pn.live_children++;
                     if (!pn.alive) rv.push_back(parent);
                 }
-                t_revive[tid].swap(rv);
-                t_dirty[tid].swap(dl); t_tag[tid].swap(l_tag); t_win[tid].swap(l_win); t_plus[tid] = l_plus; t_cf[tid] = l_cf;
+                t_revive[tid].swap(rv); t_dirty[tid].swap(dl); t_plus[tid] = l_plus; t_cf[tid] = l_cf;
             });
             for (unsigned t = 0; t < T; ++t) {
-                for (size_t k = 0; k < t_tag[t].size(); ++k) tag_count_[k] += t_tag[t][k];
-                for (size_t k = 0; k < t_win[t].size(); ++k) win_count_[k] += t_win[t][k];
                 dirty_nodes_.insert(dirty_nodes_.end(), t_dirty[t].begin(), t_dirty[t].end());
+                revive_parents.insert(revive_parents.end(), t_revive[t].begin(), t_revive[t].end());
                 plus_count_ += t_plus[t];
                 if (t_cf[t]) cfilter_rebuild_ = true;     // the child filter is rebuilt from the nodes by the next sync()
             }
-            for (unsigned t = 0; t < T; ++t) revive_parents.insert(revive_parents.end(), t_revive[t].begin(), t_revive[t].end());
-            edge_count_ += nu;
             live_nodes_ += nu;
-            new_edges_total += nu;
         }
         const double tb4 = now();
-        t_place += tb4 - tb3;
-        // (5) the filters that missed walk their new edge
+        t_nodes += tb4 - tb3;
+        // (5) the filters that missed step onto their new node: their sorted (key, filter) pairs against the sorted level
         parallel_threads(T, [&](unsigned tid) {
-            for (u32 i : midx[tid]) {
-                const u32 slot = find_edge(cur[i], toks[lvl_off[i] + d], ctag[i]);
-                cur[i] = edges[slot].child; ctag[i] = static_cast<u8>(edges[slot].mask >> WTAG_SHIFT);
+            const auto& pr = pairs[tid];
+            if (pr.empty()) return;
+            size_t g = static_cast<size_t>(std::lower_bound(ukeys.begin(), ukeys.end(), pr[0].first) - ukeys.begin());
+            for (size_t k = 0; k < pr.size(); ++k) {
+                while (ukeys[g] != pr[k].first) ++g;
+                const u32 id = static_cast<u32>(first_new + g);
+                cur[pr[k].second] = id; ctag[pr[k].second] = nodes_[id].wtag;
             }
         });
-        t_refind += now() - tb4;
+        t_assign += now() - tb4;
     }
-    if (new_edges_total) { full_edges = true; dirty_edges.clear(); }   // the placed slots were not listed one by one: the next flush ships the table
+    // ---- placement of the new edges.  Linear probing gives the home slot to whoever comes first: one-by-one inserts place an
+    //      edge when its first filter arrives, so the edges many filters share sit at home and the rare ones are displaced —
+    //      and the edges many filters share are the ones PUBLISH topics walk most.  Same rule here, exactly: every window's new
+    //      edges go in by descending weight (filters of the batch running through the edge).  Every window belongs to one thread.
+    const double t_p0 = now();
+    const size_t NB = nodes_.size() - bulk_first;
+    if (NB) {
+        BigVec<u8> own(NB);
+        for (;;) {                                           // room for all of them (more / wider windows, or a bigger table)
+            const u32 nm = nwin_mask();
+            std::vector<std::vector<u64>> hist(T, std::vector<u64>(size_t(nm) + 1, 0));
+            parallel_chunks(NB, T, [&](unsigned tid, size_t b, size_t e) {
+                std::vector<u64>& h = hist[tid];
+                for (size_t k = b; k < e; ++k) { const u32 w = nodes_[nodes_[bulk_first + k].parent].wtag & nm; own[k] = static_cast<u8>(w); h[w]++; }
+            });
+            std::vector<u64> add_w(size_t(nm) + 1, 0);
+            for (const auto& h : hist) for (size_t w = 0; w <= nm; ++w) add_w[w] += h[w];
+            const u64 win_slots = edges.size() >> nwin_log2;
+            bool fits = (edge_count_ + NB) * 2 <= edges.size();
+            for (size_t w = 0; fits && w <= nm; ++w) fits = (win_count_[w] + add_w[w]) * 2 <= win_slots;
+            if (fits) break;
+            if ((edge_count_ + NB) * 4 > edges.size() || nwin_log2 == 0) rehash_edges(edges.size() * 2);
+            else { win_min_log2_ = win_shift() + 2; rehash_edges(edges.size()); }
+        }
+        const u32 wm = win_mask(), ws = win_shift(), nm = nwin_mask();
+        std::vector<std::vector<u64>> t_tag(T), t_win(T);
+        parallel_threads(T, [&](unsigned tid) {
+            std::vector<u64> mine;                           // (~weight, node) of this thread's windows: ascending = heaviest first, ties by node number
+            for (size_t k = 0; k < NB; ++k) if (own[k] % T == tid) mine.push_back((static_cast<u64>(~new_weight[k]) << 32) | static_cast<u32>(bulk_first + k));
+            std::sort(mine.begin(), mine.end());
+            std::vector<u64> l_tag(WTAG_COUNT, 0), l_win(size_t(nm) + 1, 0);   // private until the join (neighbouring counters share cache lines)
+            for (size_t q = 0; q < mine.size(); ++q) {
+                if (q + 8 < mine.size()) {
+                    const HNode& c8 = nodes_[static_cast<u32>(mine[q + 8])];
+                    __builtin_prefetch(&edges[edge_slot0(c8.parent, c8.token, nodes_[c8.parent].wtag, wm, ws, nm)], 1);
+                }
+                const u32 id = static_cast<u32>(mine[q]);
+                HNode& c = nodes_[id];
+                const u32 ptag = nodes_[c.parent].wtag;
+                u32 i = edge_slot0(c.parent, c.token, ptag, wm, ws, nm);
+                while (edges[i].child != 0) i = edge_next(i, wm);
+                EdgeSlot es{};
+                es.parent = c.parent; es.token = c.token; es.child = id;
+                es.plus = 0; es.hash_ref = 0; es.own_ref = 0; es.mask = static_cast<u32>(c.wtag) << WTAG_SHIFT; es.cnts = 0;
+                edges[i] = es;
+                c.edge_slot = i;
+                l_tag[ptag]++; l_win[ptag & nm]++;
+            }
+            t_tag[tid].swap(l_tag); t_win[tid].swap(l_win);
+        });
+        for (unsigned t = 0; t < T; ++t) {
+            for (size_t k = 0; k < t_tag[t].size(); ++k) tag_count_[k] += t_tag[t][k];
+            for (size_t k = 0; k < t_win[t].size(); ++k) win_count_[k] += t_win[t][k];
+        }
+        edge_count_ += NB;
+        full_edges = true; dirty_edges.clear();              // the placed slots were not listed one by one: the next flush ships the table
+    }
+    const double t_place = now() - t_p0;
     max_depth = std::max<u32>(max_depth, deepest);
     // ---- C: values.  A node belongs to one thread (blocks of 64 node numbers): it applies the node's values in filter order;
     //      what reaches beyond the node — the host map of multi-value sets, the parent of a '#' node, dead ancestors to
@@ -849,8 +897,8 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
         values_size_ += changed;
     }
     if (prof)
-        fprintf(stderr, "insert_batch (%u threads): %llu filters: tokens %.2f s (classify %.2f, dictionary %.2f, resolve %.2f), edges %.2f s (look-ups %.2f [thread 0: probes %.2f, local sort %.2f], re-find %.2f, sort %.2f, serial %.2f, place %.2f), values %.2f s\n",
-                T, (unsigned long long)n, t_a3 - t_begin, tb.t_classify, tb.t_dictionary, tb.t_resolve, t_c - t_a3, t_find, t_find0, t_lsort, t_refind, t_sort, t_serial, t_place, now() - t_c);
+        fprintf(stderr, "insert_batch (%u threads): %llu filters: tokens %.2f s (classify %.2f, dictionary %.2f, resolve %.2f), edges %.2f s (look-ups %.2f [thread 0: probes %.2f, local sort %.2f], merge %.2f, numbers + tags %.2f, nodes %.2f, step %.2f, placement %.2f), values %.2f s\n",
+                T, (unsigned long long)n, t_a3 - t_begin, tb.t_classify, tb.t_dictionary, tb.t_resolve, t_c - t_a3, t_find, t_find0, t_lsort, t_sort, t_serial, t_nodes, t_assign, t_place, now() - t_c);
     return changed;
 }
 

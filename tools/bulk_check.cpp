@@ -76,6 +76,13 @@ int main(int argc, char** argv) {
                (unsigned long long)changed[par], t.nodes_.size(), (unsigned long long)t.dict_count_, (unsigned long long)t.plus_count_, (unsigned long long)t.values_size_, (unsigned long long)t.live_nodes_);
         u64 s[6] = {t.nodes_.size(), t.dict_count_, t.plus_count_, t.values_size_, t.live_nodes_, t.values.size()};
         std::memcpy(stats[par], s, sizeof s);
+        {   // balance of the windows / tags (what the match kernel's probe length depends on)
+            u64 wmax = 0, wsum = 0, tmax = 0, tsum = 0; size_t nz = 0;
+            for (u64 c : t.win_count_) { wmax = std::max(wmax, c); wsum += c; }
+            for (size_t k = 1; k < t.tag_count_.size(); ++k) { tmax = std::max(tmax, t.tag_count_[k]); tsum += t.tag_count_[k]; nz += t.tag_count_[k] != 0; }
+            printf("  windows %zu: max / mean edges %.3f; tags (without the hot tag 0): max / mean %.3f over %zu used tags; table load %.3f\n", t.win_count_.size(), wmax / (double(wsum) / t.win_count_.size()),
+                   tmax / (double(tsum) / std::max<size_t>(1, nz)), nz, double(t.edge_count_) / t.edges.size());
+        }
         fp[par] = fingerprint(t);
         printf("  fingerprint sum %016llx xor %016llx over %llu nodes, invariants %s\n", (unsigned long long)fp[par].sum, (unsigned long long)fp[par].xr, (unsigned long long)fp[par].nodes, fp[par].ok ? "ok" : "BROKEN");
     }

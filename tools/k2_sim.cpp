@@ -52,6 +52,7 @@ int main(int argc, char** argv) {
     std::vector<u32> iters(n_top);
     std::vector<std::vector<u32>> descs(n_top);
     u64 loads = 0, probe_steps = 0;
+    u64 fail_loads[9] = {0}, fail_probes[9] = {0}, hit_extra[9] = {0}, hit_probes[9] = {0};   // by depth of the probing node
     for (u64 i = 0; i < n_top; ++i) {
         const Top& q = tops[i];
         Rec r{0, t.root_plus, t.root_hash_ref, 0, t.root_mask, t.root_hash_cnt};
@@ -69,13 +70,14 @@ int main(int argc, char** argv) {
                 if ((r.mask & MASK_BLOOM) && tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) { probe = true; kt = tk; nd = d + 1; idx = edge_slot0(r.node, tk, r.mask >> WTAG_SHIFT, wm, ws, nm); }
             }
             bool done = false; const EdgeSlot* e = nullptr;
+            u32 steps = 0;
             for (;;) {
                 if (!probe) { if (!pmask) { done = true; break; } u32 pd = 31 - __builtin_clz(pmask); pmask &= ~(1u << pd); idx = pend[pd] - 1; nd = pd + 1; }
                 e = &t.edges[idx]; ++loads;
                 if (!probe) break;
-                ++probe_steps;
-                if (e->child == 0) { probe = false; continue; }
-                if (e->parent == r.node && e->token == kt) break;
+                ++probe_steps; ++steps;
+                if (e->child == 0) { probe = false; fail_loads[std::min(d, 8u)] += steps; fail_probes[std::min(d, 8u)]++; continue; }
+                if (e->parent == r.node && e->token == kt) { hit_extra[std::min(d, 8u)] += steps - 1; hit_probes[std::min(d, 8u)]++; break; }
                 idx = edge_next(idx, wm);
             }
             if (done) break;
@@ -111,6 +113,8 @@ int main(int argc, char** argv) {
     const double T = static_cast<double>(ntiles);
     printf("C3 replay: %llu subscriptions, %llu topics, %llu tiles; table %zu slots in %u windows\n", (unsigned long long)n_subs, (unsigned long long)n_top, (unsigned long long)ntiles, t.edges.size(), nm + 1);
     printf("walk   : %.2f loop iterations per topic (= node visits), %.2f slot loads per topic (%.3f loads per literal probe)\n", sum_it / (T * 32), double(loads) / n_top, double(loads) / std::max<u64>(1, probe_steps));
+    printf("         literal probes by depth of the probing node [hits: probes/topic, extra loads/probe | misses (Bloom false positives): probes/topic, loads/probe]:\n");
+    for (int dd = 0; dd < 8; ++dd) if (hit_probes[dd] + fail_probes[dd]) printf("           depth %d: hits %.3f x %.3f extra | misses %.3f x %.3f\n", dd, double(hit_probes[dd]) / n_top, double(hit_extra[dd]) / std::max<u64>(1, hit_probes[dd]), double(fail_probes[dd]) / n_top, double(fail_loads[dd]) / std::max<u64>(1, fail_probes[dd]));
     printf("         per tile: mean of lanes %.1f, max lane %.1f -> lane utilisation of the walk loop %.1f %%\n", sum_it / (T * 32), sum_max / T, 100.0 * sum_it / (32.0 * sum_max));
     printf("         tiles by max-lane iterations [0-7,8-15,...,64+]:");
     for (int b = 0; b < 9; ++b) printf(" %.1f%%", 100.0 * hist[b] / T);
