@@ -607,15 +607,64 @@ void HostTrie::tokenize_batch(const char* blob, const u32* offsets, u64 n, unsig
             std::sort(out.begin(), out.end(), [](const New& a, const New& b) { return a.ord < b.ord; });
             uniq[r].swap(out);
         });
-        std::vector<New> news;
-        size_t total = 0;
-        for (const auto& u : uniq) total += u.size();
-        news.reserve(total);
-        for (const auto& u : uniq) news.insert(news.end(), u.begin(), u.end());
-        std::sort(news.begin(), news.end(), [](const New& a, const New& b) { return a.ord < b.ord; });
-        for (size_t k = 0; k < news.size(); ++k) {
-            if (k + 8 < news.size()) __builtin_prefetch(&dict[dict_index_hash(news[k + 8].s, news[k + 8].len) & (dict.size() - 1)], 1);
-            intern(news[k].s, news[k].len, true);
+        // token of a new string = next_token_ + its rank in first-occurrence order; the strings enter the table on all threads
+        // (a slot is claimed by a CAS on its token word: nobody reads the table during this phase, and all strings are distinct)
+        std::vector<std::vector<u64>> ords(T);
+        parallel_threads(T, [&](unsigned r) { ords[r].reserve(uniq[r].size()); for (const New& x : uniq[r]) ords[r].push_back(x.ord); });
+        std::vector<u64> all_ord;
+        merge_sorted_unique(ords, T, all_ord);
+        const size_t total = all_ord.size();
+        if (total) {
+            if (static_cast<u64>(next_token_) + total >= TOK_LOCAL) { fprintf(stderr, "gpumqtt: more than 2^31 level strings\n"); std::abort(); }
+            while ((dict_count_ + total) * 2 > dict.size()) grow_dict();
+            // long strings live in the pool, in token order, each padded to 16 bytes (as intern() lays them out)
+            BigVec<u32> plen(total, 0u);
+            std::vector<std::vector<u32>> rank(T);
+            parallel_threads(T, [&](unsigned r) {
+                rank[r].resize(uniq[r].size());
+                size_t g = 0;
+                for (size_t k = 0; k < uniq[r].size(); ++k) {                      // both sorted by first occurrence
+                    while (all_ord[g] != uniq[r][k].ord) ++g;
+                    rank[r][k] = static_cast<u32>(g);
+                    if (uniq[r][k].len > DICT_INLINE_MAX) plen[g] = (uniq[r][k].len + 15u) & ~15u;
+                }
+            });
+            const size_t pool_base = pool.size();
+            u64 run = 0;
+            for (size_t g = 0; g < total; ++g) { const u32 l = plen[g]; plen[g] = static_cast<u32>(run); run += l; }
+            if (pool_base + run > 0xFFFFFFF0ull) { fprintf(stderr, "gpumqtt: level-string pool exceeds 4 GiB\n"); std::abort(); }
+            pool.resize(pool_base + run, 0);
+            tok_dollar_.resize(std::max<size_t>(tok_dollar_.size(), static_cast<size_t>(next_token_) + total), 0);
+            const u32 dmask = static_cast<u32>(dict.size() - 1);
+            const u32 tok0 = next_token_;
+            std::vector<std::vector<u32>> t_dirty(T);
+            parallel_threads(T, [&](unsigned r) {
+                std::vector<u32> dl;
+                for (size_t k = 0; k < uniq[r].size(); ++k) {
+                    const New& x = uniq[r][k];
+                    const u32 tok = tok0 + rank[r][k];
+                    DictSlot d{};
+                    d.w[0] = tok;
+                    if (x.len <= DICT_INLINE_MAX) { u32 w[7]; pack_words(x.s, x.len, w); std::memcpy(&d.w[1], w, 28); }
+                    else {
+                        const u32 off = static_cast<u32>(pool_base + plen[rank[r][k]]);
+                        d.w[7] = 0xFFu << 24; d.w[1] = x.len; d.w[2] = off; d.w[3] = fnv(x.s, x.len);
+                        std::memcpy(pool.data() + off, x.s, x.len);
+                    }
+                    u32 i = dict_index_hash(x.s, x.len) & dmask;
+                    for (;; i = (i + 1) & dmask) {
+                        u32 expect = 0;
+                        if (__atomic_compare_exchange_n(&dict[i].w[0], &expect, tok, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
+                    }
+                    std::memcpy(&dict[i].w[1], &d.w[1], 28);
+                    tok_dollar_[tok] = (x.len > 0 && x.s[0] == '$') ? 1 : 0;
+                    if (!full_dict) dl.push_back(i);
+                }
+                t_dirty[r].swap(dl);
+            });
+            for (const auto& dl : t_dirty) dirty_dict.insert(dirty_dict.end(), dl.begin(), dl.end());
+            dict_count_ += total;
+            next_token_ += static_cast<u32>(total);
         }
     }
     const double t_a2 = now();

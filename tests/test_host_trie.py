@@ -297,6 +297,7 @@ def test_parallel_bulk_load_builds_the_same_trie(monkeypatch, threads):
     da, db = ta["dict"], tb["dict"]                        # tokens are numbered by first occurrence, as one-by-one inserts number them:
     da, db = da[da[:, 0] != 0], db[db[:, 0] != 0]          # the same (token, level string) rows, whatever the table sizes
     assert np.array_equal(da[np.argsort(da[:, 0])], db[np.argsort(db[:, 0])])
+    assert np.array_equal(ta["pool"], tb["pool"]) and len(tb["pool"]) > 0     # long level strings: same pool layout (token order)
     T = Tables(tb)
     for _ in range(600):
         t = rand_topic(rng)

@@ -6,6 +6,7 @@
 #define private public
 #include "../rmqtt_b200/csrc/host_trie.h"
 #undef private
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -62,6 +63,7 @@ int main(int argc, char** argv) {
     // a few invalid / duplicate / odd filters in the middle
     setenv("GM_BULK_PROFILE", "1", 1);
     Print fp[2]; u64 changed[2]; u64 stats[2][6];
+    std::vector<std::array<u32, 8>> dict_rows[2]; std::vector<u8> pools[2]; std::vector<u8> dollars[2];
     for (int par = 0; par < 2; ++par) {
         if (par) unsetenv("GM_BULK_SERIAL"); else setenv("GM_BULK_SERIAL", "1", 1);
         HostTrie t(128);
@@ -83,10 +85,16 @@ int main(int argc, char** argv) {
             printf("  windows %zu: max / mean edges %.3f; tags (without the hot tag 0): max / mean %.3f over %zu used tags; table load %.3f\n", t.win_count_.size(), wmax / (double(wsum) / t.win_count_.size()),
                    tmax / (double(tsum) / std::max<size_t>(1, nz)), nz, double(t.edge_count_) / t.edges.size());
         }
-        fp[par] = fingerprint(t);
+        for (const DictSlot& d : t.dict) if (d.w[0]) { std::array<u32, 8> r; std::memcpy(r.data(), d.w, 32); dict_rows[par].push_back(r); }
+        std::sort(dict_rows[par].begin(), dict_rows[par].end());
+        pools[par] = t.pool; dollars[par] = t.tok_dollar_;
+        for (const auto& r : dict_rows[par]) if (t.lookup_token((r[7] >> 24) == 0xFF ? reinterpret_cast<const char*>(t.pool.data() + r[2]) : reinterpret_cast<const char*>(&r[1]), (r[7] >> 24) == 0xFF ? r[1] : (r[7] >> 24)) != r[0]) { printf("  dictionary: token %u is not found by its string\n", r[0]); fp[par].ok = false; break; }
+        { const bool keep_ok = fp[par].ok; fp[par] = fingerprint(t); fp[par].ok &= keep_ok; }
         printf("  fingerprint sum %016llx xor %016llx over %llu nodes, invariants %s\n", (unsigned long long)fp[par].sum, (unsigned long long)fp[par].xr, (unsigned long long)fp[par].nodes, fp[par].ok ? "ok" : "BROKEN");
     }
-    const bool same = fp[0].sum == fp[1].sum && fp[0].xr == fp[1].xr && fp[0].nodes == fp[1].nodes && changed[0] == changed[1] && std::memcmp(stats[0], stats[1], sizeof stats[0]) == 0 && fp[0].ok && fp[1].ok;
+    const bool dict_same = dict_rows[0] == dict_rows[1] && pools[0] == pools[1] && dollars[0] == dollars[1];
+    if (!dict_same) printf("dictionary / pool / '$' flags differ (%zu vs %zu entries)\n", dict_rows[0].size(), dict_rows[1].size());
+    const bool same = dict_same && fp[0].sum == fp[1].sum && fp[0].xr == fp[1].xr && fp[0].nodes == fp[1].nodes && changed[0] == changed[1] && std::memcmp(stats[0], stats[1], sizeof stats[0]) == 0 && fp[0].ok && fp[1].ok;
     printf("%s\n", same ? "IDENTICAL CONTENT" : "MISMATCH");
     return same ? 0 : 1;
 }
