@@ -50,3 +50,25 @@ def test_zipf_over_devices_is_skewed_and_deterministic():
     top = c.most_common(1)[0][1]
     assert top > 0.02 * len(t) and len(c) > 5_000          # one hot device, a long tail
     assert all(x.count(b"/") == 5 for x in t)
+
+
+def test_big_batches_are_stitched_from_per_thread_shares_with_the_same_bytes():
+    """Above 200 K items the generators run on all host threads (workload.cpp `stitched`): every thread generates a contiguous
+    share, the shares are concatenated at their byte offsets.  Items are order-free, so the result must be the bytes of the
+    same range generated in two halves (each below the threshold: the serial loop)."""
+    cfg = wl.C3.scaled(n_subs=260_000, n_topics=260_000)
+    blob, offs, vals = wl.gen_subs(cfg)
+    b0, o0, v0 = wl.gen_subs(cfg, n=130_000)
+    b1, o1, v1 = wl.gen_subs(cfg, n=130_000, first=130_000)
+    assert np.array_equal(blob, np.concatenate([b0, b1]))
+    assert np.array_equal(offs, np.concatenate([o0[:-1], o1 + o0[-1]]))
+    assert np.array_equal(vals, np.concatenate([v0, v1]))
+    tb, to = wl.gen_topics(cfg, stream=2)
+    t0, u0 = wl.gen_topics(cfg, n=130_000, stream=2)
+    t1, u1 = wl.gen_topics(cfg, n=130_000, first=130_000, stream=2)
+    assert np.array_equal(tb, np.concatenate([t0, t1])) and np.array_equal(to, np.concatenate([u0[:-1], u1 + u0[-1]]))
+    sb, so, sv = wl.gen_subs_sharded(cfg, [1, 5, 9, 33])
+    s0, p0, w0 = wl.gen_subs_sharded(cfg, [1, 5, 9, 33], n=130_000)
+    s1, p1, w1 = wl.gen_subs_sharded(cfg, [1, 5, 9, 33], n=130_000, first=130_000)
+    assert np.array_equal(sb, np.concatenate([s0, s1])) and np.array_equal(sv, np.concatenate([w0, w1]))
+    assert np.array_equal(so, np.concatenate([p0[:-1], p1 + p0[-1]]))
