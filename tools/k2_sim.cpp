@@ -48,6 +48,9 @@ int main(int argc, char** argv) {
     std::sort(tops.begin(), tops.end(), [](const Top& a, const Top& b) { return a.key < b.key; });
     const u32 wm = t.win_mask(), ws = t.win_shift(), nm = t.nwin_mask();
     auto rec_of = [&](const EdgeSlot& e) { return Rec{e.child, e.plus, e.hash_ref, e.own_ref, e.mask, e.cnts}; };
+    const u32 cf_mask = static_cast<u32>(t.cfilter.size() - 1);
+    u64 cf_loads = 0;
+    auto cf_maybe = [&](u32 parent, u32 token) { u32 w, bits; cfilter_pos(parent, token, cf_mask, w, bits); ++cf_loads; return (t.cfilter[w] & bits) == bits; };   // the child filter of wide nodes (kernels.cuh cfilter_maybe)
     // per-topic replay
     std::vector<u32> iters(n_top);
     std::vector<std::vector<u32>> descs(n_top);
@@ -67,7 +70,7 @@ int main(int argc, char** argv) {
             if (d < q.L) {
                 if (r.plus) { pend[d] = r.plus; pmask |= 1u << d; }
                 const u32 tk = q.tok[d];
-                if ((r.mask & MASK_BLOOM) && tk != TOK_UNKNOWN && (r.mask & mask_bit(tk))) { probe = true; kt = tk; nd = d + 1; idx = edge_slot0(r.node, tk, r.mask >> WTAG_SHIFT, wm, ws, nm); }
+                if ((r.mask & MASK_BLOOM) && tk != TOK_UNKNOWN && (r.mask & mask_bit(tk)) && (!(r.mask & MASK_WIDE_FLAG) || cf_maybe(r.node, tk))) { probe = true; kt = tk; nd = d + 1; idx = edge_slot0(r.node, tk, r.mask >> WTAG_SHIFT, wm, ws, nm); }
             }
             bool done = false; const EdgeSlot* e = nullptr;
             u32 steps = 0;
@@ -113,6 +116,7 @@ int main(int argc, char** argv) {
     const double T = static_cast<double>(ntiles);
     printf("C3 replay: %llu subscriptions, %llu topics, %llu tiles; table %zu slots in %u windows\n", (unsigned long long)n_subs, (unsigned long long)n_top, (unsigned long long)ntiles, t.edges.size(), nm + 1);
     printf("walk   : %.2f loop iterations per topic (= node visits), %.2f slot loads per topic (%.3f loads per literal probe)\n", sum_it / (T * 32), double(loads) / n_top, double(loads) / std::max<u64>(1, probe_steps));
+    printf("         child-filter words read: %.2f per topic (a few MB, L2-resident)\n", double(cf_loads) / n_top);
     printf("         literal probes by depth of the probing node [hits: probes/topic, extra loads/probe | misses (Bloom false positives): probes/topic, loads/probe]:\n");
     for (int dd = 0; dd < 8; ++dd) if (hit_probes[dd] + fail_probes[dd]) printf("           depth %d: hits %.3f x %.3f extra | misses %.3f x %.3f\n", dd, double(hit_probes[dd]) / n_top, double(hit_extra[dd]) / std::max<u64>(1, hit_probes[dd]), double(fail_probes[dd]) / n_top, double(fail_loads[dd]) / std::max<u64>(1, fail_probes[dd]));
     printf("         per tile: mean of lanes %.1f, max lane %.1f -> lane utilisation of the walk loop %.1f %%\n", sum_it / (T * 32), sum_max / T, 100.0 * sum_it / (32.0 * sum_max));
