@@ -647,6 +647,7 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     if (dev >= ndev) { g_err = "device ordinal out of range"; return GM_ERR_INVALID_ARG; }
     CUDA_TRY(cudaSetDevice(dev));
     gm_engine* eng = new gm_engine(c.max_levels ? c.max_levels : 128u);
+    struct Guard { gm_engine* e; ~Guard() { if (e) gm_destroy(e); } } guard{eng};   // a failing CUDA call below must not leak the half-built engine
     eng->device = dev;
     eng->flags = c.flags;
     eng->read_knobs();
@@ -665,6 +666,7 @@ int32_t gm_create(const gm_config* cfg, gm_engine** out) {
     if (const char* ev = getenv("GM_L2_FETCH")) { const int v = atoi(ev); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(v)); }
     else if (c.flags & GM_FLAG_L2_FETCH_32) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     if (c.filters_hint) eng->trie.reserve(c.filters_hint);
+    guard.e = nullptr;
     *out = eng;
     return GM_OK;
 }
