@@ -110,3 +110,51 @@ def test_publish_topic_decoder_matches_the_mqtt_fixed_header_layout():
         buf = (C.c_uint8 * len(bad)).from_buffer_copy(bad)
         tp, tl = C.c_char_p(), C.c_uint32(0)
         assert lib.gm_publish_topic(buf, len(bad), C.byref(tp), C.byref(tl)) == N.GM_ERR_INVALID_ARG
+
+
+def _split_params(s: str):
+    s = s.strip()
+    if s in ("", "void"):
+        return []
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_sys_crate_declares_every_function_of_the_header():
+    """The Rust `-sys` crate under integration/ cannot be compiled here (no cargo): at least keep it mechanically in step with
+    the header — every function present with the same number of parameters, every struct with the same number of fields."""
+    hdr = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "gpumqtt.h").read_text(), flags=re.S)
+    rs = re.sub(r"//[^\n]*", "", (ROOT / "integration" / "gpumqtt-sys" / "src" / "lib.rs").read_text())
+    c_fns = {m.group(1): _split_params(m.group(2)) for m in re.finditer(r"\b(gmr?_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)}
+    r_fns = {m.group(1): _split_params(m.group(2)) for m in re.finditer(r"\bfn\s+(gmr?_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->\s*[^;]+)?;", rs, flags=re.S)}
+    assert set(c_fns) == set(_declared())
+    assert sorted(set(c_fns) - set(r_fns)) == [], "declared in include/gpumqtt.h but missing from the sys crate"
+    assert sorted(set(r_fns) - set(c_fns)) == [], "the sys crate declares functions the header does not have"
+    for name, params in c_fns.items():
+        assert len(params) == len(r_fns[name]), f"{name}: {len(params)} parameters in the header, {len(r_fns[name])} in the sys crate"
+    # structs: `typedef struct X { ... } X;` with fields vs `pub struct X { pub a: T, ... }`
+    c_structs = {}
+    for m in re.finditer(r"typedef\s+struct\s+(gm_[a-z_]+)\s*\{(.*?)\}\s*\1\s*;", hdr, flags=re.S):
+        n = 0
+        for decl in m.group(2).split(";"):
+            decl = decl.strip()
+            if decl:
+                n += len(_split_params(decl))                   # `uint64_t a, b` declares two fields
+        c_structs[m.group(1)] = n
+    r_structs = {m.group(1): len(re.findall(r"\bpub\s+(?:r#)?[a-z_0-9]+\s*:", m.group(2)))
+                 for m in re.finditer(r"pub\s+struct\s+(gm_[a-z_]+)\s*\{(.*?)\n\}", rs, flags=re.S)}
+    for name, n in c_structs.items():
+        assert name in r_structs, f"struct {name} missing from the sys crate"
+        assert r_structs[name] == n, f"struct {name}: {n} fields in the header, {r_structs[name]} in the sys crate"
