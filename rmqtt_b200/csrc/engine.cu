@@ -338,7 +338,22 @@ struct gm_engine {
         retired.clear();
     }
 
+    // A flush that fails half-way (a cudaMalloc of a fresh table buffer, a copy) has already advanced the "shipped up to here"
+    // marks and cleared dirty lists for the parts it handled: nothing may be assumed about what reached the device any more.
+    // The next flush therefore ships every table whole into new buffers; until then the kernels keep the last complete view.
     int flush_locked() {      // caller holds `mu`
+        const int st = flush_impl();
+        if (st != GM_OK && !(flags & GM_FLAG_HOST_ONLY) && st != GM_ERR_TOO_LARGE) {
+            jobs_.clear(); swaps_.clear(); stage_used_ = 0;               // (fresh buffers not yet swapped in are freed here)
+            up_ranges = up_values = up_pool = 0; up_edges_slots = up_dict_slots = 0;
+            trie.full_edges = trie.full_dict = true; trie.cfilter_dirty = true; trie.trees_dirty = true; trie.root_dirty = true;
+            up_rkids = up_rvals = up_redges_slots = 0;
+            rtree.dirty = true; rtree.full = true;
+        }
+        return st;
+    }
+
+    int flush_impl() {        // caller holds `mu`
         if (flags & GM_FLAG_HOST_ONLY) {
             if (!trie.sync()) { g_err = "more than 2^32 live value words"; return GM_ERR_TOO_LARGE; }
             if (rtree.dirty) { rtree.prepare_flush(); rtree.shipped(); }
