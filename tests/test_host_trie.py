@@ -241,7 +241,7 @@ def test_bulk_load_equals_one_by_one_inserts():
         assert T.match(t.encode())[0] == tree.matches(t), t
 
 
-@pytest.mark.parametrize("threads", [2, 3, 8])
+@pytest.mark.parametrize("threads", [2, 3, 8, 64])
 def test_parallel_bulk_load_builds_the_same_trie(monkeypatch, threads):
     """gm_bulk_load of a big batch runs on all host threads (host_trie.cpp insert_batch_parallel: per-thread tokenising with a
     first-occurrence merge of the new level strings, level-synchronous edges with one owner thread per window of the table,

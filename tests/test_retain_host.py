@@ -92,7 +92,7 @@ def test_random_differential(seed):
                 assert got == want, f
 
 
-@pytest.mark.parametrize("threads", [2, 5])
+@pytest.mark.parametrize("threads", [2, 5, 64])
 def test_bulk_load_builds_tree_and_image_level_by_level(monkeypatch, threads):
     """gm_retain_bulk_load into an empty tree builds the host tree and its device image together on all host threads
     (retain_tree.cpp set_batch_build: sorted (parent, token) keys per level, pre-order numbers from subtree sizes).  The image
