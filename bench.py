@@ -526,6 +526,13 @@ def run_own(args):
                              "achieved": (k1_bytes + k2_bytes) / (float(k_mean.sum()) * 1e-3) / 1e9 if k_mean.sum() > 0 else None,
                              "frac_of_step": (k1_bytes + k2_bytes) / (ms / args.steps * 1e-3) / 1e9 / peak},
                 "descriptor_mode_kernel_ms": {"k_tokenize+k_bucket_scan+k_bucket_scatter": float(kd[0]), "k_match_fast": float(kd[1]), "k_match_slow": float(kd[2])}}
+    # the same kernel in descriptor mode (the mode the e2e path runs): the publish phase writes one 8-byte value-set reference per
+    # matched filter instead of 4 bytes per matched id, everything else is the same walk
+    k2_bytes_desc = 16 * W["visited"] + 16 * W["probed"] + 8 * W["filters"] + 8 * W["filters"] + 8 * n
+    if kd[1] > 0:
+        ach_d = k2_bytes_desc / (float(kd[1]) * 1e-3) / 1e9
+        roofline["descriptor_mode"] = {"kernel": "k_match_fast<DESC>", "algorithmic_bytes_per_launch": k2_bytes_desc, "achieved": ach_d, "unit": "GB/s",
+                                       "frac": ach_d / peak}
 
     # ---- the headline is complete here: keep it where the watchdog / exception path finds it (rank 0) -------------------
     if rank == 0:

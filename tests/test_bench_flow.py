@@ -207,6 +207,7 @@ def test_run_own_walks_every_leg_and_isolates_the_failing_ones(fake_gpu):
         assert k in d["e2e"], k
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["kernel"] == "k_match_fast" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["descriptor_mode"]["frac"] - r["descriptor_mode"]["achieved"] / r["peak"]) < 1e-12
     assert d["parity_check"]["ok"] is True and d["parity_check"]["topics"] == 2000          # the oracle-backed fake really was compared
     assert "unavailable" in d["multi_gpu"]["strong_fused"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
