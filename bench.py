@@ -285,6 +285,37 @@ def _relations_leg(small: bool):
             "host_part": "handle -> gm_sub_relation{node_id, handle, group, sub ids}: table look-ups only", "router_build_s": round(build_s, 1)}
 
 
+def _configs_leg(torch, eng, cfg, dev, stream, timed_device_loop, d_spans, d_ids, d_needed, d_status, small: bool):
+    """The other single-GPU rows of BASELINE.json in the same run: C1 and C2 through tools/bench_configs.py (own engines; kernel
+    times from the engine's ring, the CPU port on 1 and all threads beside them, count parity of every topic), and the secondary
+    publish distribution of SURVEY §8(d) — Zipf(1.0) over devices — as one more batch on the C3 engine."""
+    from rmqtt_b200 import workload as wl
+    sys.path.insert(0, str(ROOT / "tools"))
+    import bench_configs as bc
+    bc.dev, bc.stream = dev, stream          # the tool's module-level device / stream: this process's
+    out = {}
+    for name in ("C1", "C2"):
+        c = wl.CONFIGS[name]
+        if small and name == "C2":
+            c = c.scaled(n_subs=100_000, n_topics=20_000, name="C2-scaled")
+        out[name] = bc.publish_config(c, reps=20)
+    zb, zo = wl.gen_topics_zipf(cfg)
+    n = len(zo) - 1
+    d_zb, d_zo = torch.from_numpy(zb).to(dev), torch.from_numpy(zo.view(np.int32)).to(dev)
+    ids = d_ids
+    eng.match_batch_device(d_zb, d_zo, d_spans, ids, d_needed, d_status, stream)
+    need = int(d_needed.item())
+    if need > ids.numel():
+        ids = torch.empty(need + 1024, dtype=torch.int32, device=dev)
+    steps = 20
+    ms_z = timed_device_loop(lambda k: eng.match_batch_device(d_zb, d_zo, d_spans, ids, d_needed, d_status, stream), steps, 3)
+    kz = eng.kernel_ms(steps).mean(axis=0)
+    out["C3-zipf"] = {"workload": f"{cfg.name} subscriptions, {n}-topic batch drawn Zipf(1.0) over devices (SURVEY 8d, secondary distribution)",
+                      "topics_per_s": n * steps / (ms_z / 1e3), "ms_per_step": ms_z / steps, "ids_per_topic": need / n,
+                      "kernel_ms": {"k_tokenize+k_bucket_scan+k_bucket_scatter": float(kz[0]), "k_match_fast": float(kz[1]), "k_match_slow": float(kz[2])}}
+    return out
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
@@ -550,7 +581,7 @@ def run_own(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "cpu_baseline": None, "multi_gpu": None, "parity_check": None, "c4": None, "latency": None, "churn": None, "relations": None,
+            "cpu_baseline": None, "multi_gpu": None, "parity_check": None, "c4": None, "latency": None, "churn": None, "relations": None, "configs": None,
             "clocks": clocks,
         })
 
@@ -819,6 +850,7 @@ def run_own(args):
         if not args.no_c4:
             _PARTIAL["c4"] = _leg("c4", lambda: _c4_leg(torch, dev, stream, peak, small), errors)
         _PARTIAL["relations"] = _leg("relations", lambda: _relations_leg(small), errors)
+        _PARTIAL["configs"] = _leg("configs", lambda: _configs_leg(torch, eng, cfg, dev, stream, timed_device_loop, d_spans, d_ids, d_needed, d_status, small), errors)
 
     line = dict(_PARTIAL)
     if errors:

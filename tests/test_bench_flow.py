@@ -216,6 +216,9 @@ def test_run_own_walks_every_leg_and_isolates_the_failing_ones(fake_gpu):
     # the two legs the fake cannot serve (retained tree, GpuRouter): reported, not fatal
     assert d["c4"] is None and d["relations"] is None
     assert set(d["errors"]) == {"c4", "relations"}, d["errors"]
+    # C1 / C2 through tools/bench_configs.py and the Zipf batch ride on the fake too (count parity is real: oracle vs oracle-backed fake)
+    assert set(d["configs"]) == {"C1", "C2", "C3-zipf"} and d["configs"]["C1"]["count_parity"] is True and d["configs"]["C2"]["count_parity"] is True
+    assert d["configs"]["C3-zipf"]["topics_per_s"] > 0
 
 
 def test_run_own_without_the_cpu_legs(fake_gpu):
