@@ -47,3 +47,21 @@ def test_parallel_bulk_paths_under_sanitizers(tmp_path, san):
     run = subprocess.run([str(exe), "par"], capture_output=True, text=True, timeout=900, env=env)
     assert run.returncode == 0, (run.stdout[-1000:], run.stderr[-4000:])
     assert run.stdout.count(" ok:") == 3 and "WARNING: ThreadSanitizer" not in run.stderr
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+@pytest.mark.parametrize("san", ["address,undefined", "thread"])
+def test_batcher_front_end_under_sanitizers(tmp_path, san):
+    """rmqtt_b200/csrc/batcher.cpp (gm_submit / dispatchers / callbacks / drain / destroy) against a stubbed engine: several
+    producer threads, every cookie answered exactly once with its own topic's ids, the capacity-retry and failing-batch paths."""
+    exe = tmp_path / ("batcher_" + san.split(",")[0])
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", f"-fsanitize={san}", "-fno-omit-frame-pointer", "-o", str(exe),
+           str(ROOT / "tests" / "native" / "batcher_stress.cpp"), str(CSRC / "batcher.cpp")]
+    build = subprocess.run(cmd, capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr and "cannot find" in build.stderr:
+        pytest.skip("sanitizer runtime not installed")
+    assert build.returncode == 0, build.stderr[-2000:]
+    env = {"PATH": "/usr/bin:/bin", "ASAN_OPTIONS": "detect_leaks=1", "TSAN_OPTIONS": "halt_on_error=1"}
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600, env=env)
+    assert run.returncode == 0, (run.stdout[-1500:], run.stderr[-3000:])
+    assert run.stdout.count("-> ok:") == 4 and "WARNING: ThreadSanitizer" not in run.stderr
