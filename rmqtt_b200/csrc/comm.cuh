@@ -145,6 +145,14 @@ k_gather_push(char* const* blocks /* [world] */, u32 rank, u32 world, size_t off
     }
 }
 
+#ifndef GM_CPU_EMU
+__device__ __forceinline__ void st_release_sys(u32* p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_acquire_sys(const u32* p) { u32 f; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(p) : "memory"); return f; }
+#else
+inline void st_release_sys(u32* p, u32 v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline u32 ld_acquire_sys(const u32* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+#endif
+
 // End of a fused-gather step: tell every rank how much this rank contributed and wait until every rank has said so —
 // one warp, lane w talks to rank w.  The match kernels of this rank have completed (stream order), so its posted stores
 // into the peers' buffers are performed before the release store of the flag; a rank that sees all flags of the epoch
@@ -156,11 +164,11 @@ __global__ void k_gather_finish(unsigned long long* const* counts /* [world] pee
     counts[w][2 * rank] = k;
     counts[w][2 * rank + 1] = *d_m;
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags[w] + rank), "r"(epoch) : "memory");
+    st_release_sys(flags[w] + rank, epoch);
     const long long t0 = clock64();
     for (;;) {
         u32 f;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(my_flags + w) : "memory");
+        f = ld_acquire_sys(my_flags + w);
         if (static_cast<int>(f - epoch) >= 0) break;
         if (clock64() - t0 > 6000000000ll) { atomicOr(err, 1u); break; }     // ~3 s at 2 GHz: give up, the host reports GM_ERR_COMM
         __nanosleep(200);

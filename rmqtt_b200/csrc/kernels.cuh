@@ -62,16 +62,26 @@ constexpr u32 K2_SMEM_DESCS = 8;     // value-set descriptors per topic held in 
 template <int FAST_L, int THREADS> constexpr size_t k2_smem_bytes() { return (2 * sizeof(u32) * FAST_L + sizeof(uint2) * K2_SMEM_DESCS) * THREADS; }
 
 // ------------------------------------------------------------------------------------------------
+// (GM_CPU_EMU: tests/native/emu runs these kernels on the CPU under the sanitizers — the few PTX helpers have plain C++ twins)
+#ifndef GM_CPU_EMU
 __device__ __forceinline__ void ld256(const void* p, u32 (&w)[8]) {
     asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                  : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const u32 (&w)[8]) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 __device__ __forceinline__ u32 lanemask_lt() {
     u32 m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+#else
+inline void ld256(const void* p, u32 (&w)[8]) { __builtin_memcpy(w, p, 32); }
+inline void st256(void* p, const u32 (&w)[8]) { __builtin_memcpy(p, w, 32); }
+inline u32 lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // K1: tokeniser.  One thread per topic, FOUR text bytes per step: the level text is read with aligned
@@ -100,6 +110,7 @@ __device__ __forceinline__ u32 text4_s(const u32* stage, u32 off) {
 }
 
 // ---- 1-D bulk asynchronous copy global -> shared (TMA engine, cp.async.bulk), completion on an mbarrier ----------------
+#ifndef GM_CPU_EMU
 __device__ __forceinline__ u32 smem_u32(const void* p) { return static_cast<u32>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -122,6 +133,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#else      // the bulk copy completes at once; the barrier has nothing to wait for
+inline void mbar_init(unsigned long long*, u32) {}
+inline void mbar_expect_tx(unsigned long long*, u32) {}
+inline void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, unsigned long long*) { __builtin_memcpy(dst_smem, src_gmem, bytes); }
+inline void mbar_wait(unsigned long long*, u32) {}
+inline void mbar_fence_init() {}
+#endif
 
 __device__ __forceinline__ u32 dict_lookup_inline(const TrieView& tv, const u32 (&w)[7]) {
     u32 idx = dict_hash_words(w) & tv.dict_mask;
@@ -189,7 +208,7 @@ k_tokenize(const u8* __restrict__ blob, u32 blob_bytes, u32 readable_bytes, cons
             sbase = b0;
             if (threadIdx.x == 0) {
                 mbar_init(&s_bar, 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                mbar_fence_init();
                 mbar_expect_tx(&s_bar, e0 - b0);
                 bulk_g2s(s_stage, blob + b0, e0 - b0, &s_bar);
             }
@@ -254,8 +273,7 @@ k_tokenize(const u8* __restrict__ blob, u32 blob_bytes, u32 readable_bytes, cons
     }
     meta[t] = invalid ? META_INVALID : (lev | (dollar ? META_DOLLAR : 0u));
     status[t] = invalid ? -2 : 0;   // GM_ERR_INVALID_TOPIC: Topic::from_str would return Err
-    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(tok8 + static_cast<size_t>(t) * TOK8), "r"(tw[0]), "r"(tw[1]), "r"(tw[2]),
-                 "r"(tw[3]), "r"(tw[4]), "r"(tw[5]), "r"(tw[6]), "r"(tw[7]) : "memory");
+    st256(tok8 + static_cast<size_t>(t) * TOK8, tw);
     if (bkey) {   // locality bucket: topics that share their first two levels share the upper subtrees of the trie
         // major key: the first two levels (shared upper subtrees); minor key: a few bits of the third (neighbouring
         // tiles then also share the cold per-device chains when a device shows up more than once in the batch)
@@ -316,8 +334,7 @@ k_bucket_scatter(const u32* __restrict__ bkey, u32* __restrict__ cursor, u32 n, 
     if (tok8_sorted) {
         u32 w[8];
         ld256(tok8 + static_cast<size_t>(t) * TOK8, w);
-        asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(tok8_sorted + static_cast<size_t>(pos) * TOK8), "r"(w[0]), "r"(w[1]),
-                     "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        st256(tok8_sorted + static_cast<size_t>(pos) * TOK8, w);
         meta_sorted[pos] = meta[t];
     }
 }
