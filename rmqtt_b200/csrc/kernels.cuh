@@ -427,7 +427,11 @@ __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_match_fast(MatchParams p, Desc* __restrict__ dpool, u32 pool_rows) {
     static_assert(!(GATHER && DESC), "the fused gather publishes ids");
     constexpr u32 SD = K2_SMEM_DESCS;         // descriptors kept in shared memory per topic; later ones spill to dpool
+#ifndef GM_CPU_EMU
     extern __shared__ __align__(16) unsigned char k2_smem[];   // 64 KB: above the 48 KB static limit -> dynamic
+#else
+    unsigned char* k2_smem = emu::dyn_smem();
+#endif
     u32 (*s_tok)[THREADS] = reinterpret_cast<u32 (*)[THREADS]>(k2_smem);                                  // tokens of this thread's topic (column = thread: conflict-free)
     u32 (*s_pend)[THREADS] = reinterpret_cast<u32 (*)[THREADS]>(k2_smem + sizeof(u32) * FAST_L * THREADS);   // parked '+' child per depth
     uint2 (*s_desc)[THREADS] = reinterpret_cast<uint2 (*)[THREADS]>(k2_smem + 2 * sizeof(u32) * FAST_L * THREADS);   // matched value sets (ref, cnt)

@@ -1,0 +1,241 @@
+// TEST INFRASTRUCTURE: the match and retained-lookup pipelines of engine.cu (enqueue_match / enqueue_retain) over HOST
+// memory, with the REAL kernel sources (kernels.cuh, retain_kernels.cuh, relations.cuh compiled with -DGM_CPU_EMU) run
+// by the CPU emulation in cuda_runtime.h.  Exposed as a small C interface for tests/test_emu_kernels.py, which compares
+// the results with the oracle.  Build (tests/test_emu_kernels.py does it):
+//   g++ -O1 -g -std=c++17 -DGM_CPU_EMU -Itests/native/emu -Irmqtt_b200/csrc -shared -fPIC tests/native/emu/emu_driver.cpp \
+//       rmqtt_b200/csrc/host_trie.cpp rmqtt_b200/csrc/retain_tree.cpp -o <out>.so     (+ -fsanitize=address,undefined for the ASan run)
+#include <cuda_runtime.h>      // the emulation (this directory is first on the include path)
+
+#include <cstring>
+#include <vector>
+
+#include "../../../include/gpumqtt.h"
+#include "host_trie.h"
+#include "kernels.cuh"
+#include "relations.cuh"
+#include "retain_kernels.cuh"
+#include "retain_tree.h"
+
+using namespace gm;
+
+namespace {
+
+struct Ctrl { unsigned long long cursor; unsigned long long stats[24]; u32 slow_count; u32 tile_counter; };   // engine.cu's control block
+
+constexpr int K2_FAST_L = 8, K2_THREADS = 512, K2_CTAS_PER_SM = 3;
+constexpr u32 EMU_SMS = 2;               // the emulated part has two SMs: several CTAs per kernel, dynamic tile hand-out exercised
+
+struct EmuEngine {
+    HostTrie trie{128};
+    RetainTreeHost rtree{&trie};
+    u32 pool_rows = 24;                  // engine.cu K2_POOL_ROWS (tests lower it to push topics onto the deferred kernel)
+    u32 site_bits = 10;
+
+    TrieView view() {                    // engine.cu gm_engine::view(), host pointers instead of device pointers
+        TrieView v{};
+        v.edges = trie.edges.data(); v.ranges = trie.ranges.data(); v.values = trie.values.data(); v.dict = trie.dict.data(); v.pool = trie.pool.data();
+        v.cfilter = trie.cfilter.data(); v.cfilter_mask = static_cast<u32>(trie.cfilter.size() - 1);
+        v.edge_mask = static_cast<u32>(trie.edges.size() - 1);
+        v.win_mask = trie.win_mask(); v.win_shift = trie.win_shift(); v.nwin_mask = trie.nwin_mask();
+        v.dict_mask = static_cast<u32>(trie.dict.size() - 1);
+        v.root_plus = trie.root_plus; v.root_hash_ref = trie.root_hash_ref; v.root_hash_cnt = trie.root_hash_cnt; v.root_mask = trie.root_mask;
+        v.max_depth = trie.max_depth;
+        v.tree_slots = trie.tree_slots.data(); v.n_trees = static_cast<u32>(trie.tree_slots.size());
+        return v;
+    }
+    RetainView rview() {                 // engine.cu gm_engine::rview()
+        RetainView v{};
+        v.kids = rtree.rkids.data(); v.edges = rtree.redges.data(); v.vals = rtree.rvals.data();
+        v.edge_mask = static_cast<u32>(rtree.redges.size() - 1);
+        if (!rtree.rnodes.empty()) { v.root_first_kid = rtree.rnodes[0].first_kid; v.root_nk_flags = rtree.rnodes[0].nkids | (rtree.rnodes[0].flags << 28); }
+        v.root_plain_kids = rtree.root_plain_kids; v.root_plain_val_hi = rtree.root_plain_val_hi; v.max_depth = rtree.max_depth;
+        v.n_kids = static_cast<u32>(rtree.rkids.size());
+        return v;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+void* emu_new() { return new EmuEngine(); }
+void emu_free(void* h) { delete static_cast<EmuEngine*>(h); }
+void emu_set_pool_rows(void* h, uint32_t rows) { static_cast<EmuEngine*>(h)->pool_rows = rows; }
+
+int32_t emu_sub_add(void* h, const char* f, uint32_t len, uint32_t value, uint32_t tree) {
+    bool ch = false;
+    return static_cast<EmuEngine*>(h)->trie.insert(f, len, value, &ch, tree);
+}
+int32_t emu_sub_remove(void* h, const char* f, uint32_t len, uint32_t value, uint32_t tree) {
+    bool ch = false;
+    return static_cast<EmuEngine*>(h)->trie.remove(f, len, value, &ch, tree);
+}
+int32_t emu_retain_set(void* h, const char* t, uint32_t len, uint32_t value) {
+    bool had; u32 old;
+    return static_cast<EmuEngine*>(h)->rtree.set(t, len, value, &had, &old);
+}
+int32_t emu_retain_remove(void* h, const char* t, uint32_t len) {
+    bool had; u32 old;
+    return static_cast<EmuEngine*>(h)->rtree.remove(t, len, &had, &old);
+}
+
+// Router::matches for a batch through k_tokenize -> k_bucket_scan -> k_bucket_scatter -> k_match_fast -> k_match_slow.
+// flags: bit 0 descriptor mode (the descriptors are expanded here from the host mirror, so `out_ids` holds ids either way),
+//        bit 1 the bulk-staged tokeniser, bit 2 the instrumented (STATS) instantiations; work[4] = V, E, F, M then.
+// Returns 0, or -3 with *needed when cap_ids is too small (the engine's capacity protocol).
+int32_t emu_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n64, const uint32_t* trees, uint32_t flags, gm_span* out_spans, uint32_t* out_ids,
+                  uint64_t cap_ids, uint64_t* needed, int32_t* status, uint64_t* work, uint32_t* deferred) {
+    EmuEngine& e = *static_cast<EmuEngine*>(h);
+    const bool desc = flags & 1u, bulk = flags & 2u, stats = flags & 4u;
+    const u32 n = static_cast<u32>(n64);
+    *needed = 0;
+    if (n == 0) return 0;
+    if (!e.trie.sync()) return -7;
+    const TrieView tv = e.view();
+    const u32 blob_bytes = offs[n];
+    // the bulk stage wants a 16-byte aligned blob that may be read up to a 16-byte boundary
+    const size_t readable = (static_cast<size_t>(blob_bytes) + 15) & ~size_t(15);
+    std::vector<u8> blob_store(readable + 64, 0);
+    u8* blob = blob_store.data() + ((16 - (reinterpret_cast<uintptr_t>(blob_store.data()) & 15)) & 15);
+    std::memcpy(blob, blob_in, blob_bytes);
+    const u32 S = std::max<u32>(1u, tv.max_depth);
+    std::vector<u32> tok(S > TOK8 ? static_cast<size_t>(S) * n : 64), meta(n), slow(n);
+    std::vector<u32> tok8_store(static_cast<size_t>(n) * TOK8 + 16), sort_store(static_cast<size_t>(n) * 11 + 64);
+    u32* tok8 = tok8_store.data() + ((32 - (reinterpret_cast<uintptr_t>(tok8_store.data()) & 31)) & 31) / 4;
+    u32* sortb = sort_store.data() + ((32 - (reinterpret_cast<uintptr_t>(sort_store.data()) & 31)) & 31) / 4;
+    Ctrl ctrl{};
+    const u32 NB = 1u << e.site_bits;
+    std::vector<u32> hist_store(2 * static_cast<size_t>(NB) + 16, 0);
+    u32* hist = hist_store.data() + ((16 - (reinterpret_cast<uintptr_t>(hist_store.data()) & 15)) & 15) / 4;
+    u32* bcursor = hist + NB;
+    u32* bkey = sortb; u32* perm = bkey + n; u32* meta_sorted = perm + n;
+    u32* tok8_sorted = meta_sorted + n + ((8 - (3 * static_cast<size_t>(n)) % 8) % 8);
+    const u32 stack_cap = 32u * (tv.max_depth + 2u) + 64u;
+    const int k3_blocks = EMU_SMS * 4;
+    std::vector<u64> gstack(static_cast<size_t>(k3_blocks) * 8 * stack_cap);
+    const int k2_grid = EMU_SMS * K2_CTAS_PER_SM;
+    std::vector<Desc> gpool(static_cast<size_t>(k2_grid) * K2_THREADS * std::max<u32>(e.pool_rows, 1u));
+    std::vector<uint2> descs;
+    std::vector<u32> ids_tmp;
+    void* d_out = out_ids;
+    u64 cap = cap_ids;
+    if (desc) { descs.resize(cap_ids + 1); d_out = descs.data(); }
+
+    for (u32 i = 0; i < n; ++i) status[i] = 0x7F7F7F7F;        // every row must be written by the tokeniser
+    emu::launch(dim3((n + TOK_THREADS - 1) / TOK_THREADS), dim3(TOK_THREADS), [&] {
+        if (bulk) k_tokenize<true>(blob, blob_bytes, static_cast<u32>(readable), offs, nullptr, n, nullptr, tv, S, tok8, tok.data(), meta.data(), status, bkey, hist, e.site_bits, 0u);
+        else k_tokenize<false>(blob, blob_bytes, static_cast<u32>(readable), offs, nullptr, n, nullptr, tv, S, tok8, tok.data(), meta.data(), status, bkey, hist, e.site_bits, 0u);
+    });
+    emu::launch(dim3(1), dim3(1024), [&] { k_bucket_scan(hist, bcursor, NB); });
+    emu::launch(dim3((n + 255) / 256), dim3(256), [&] { k_bucket_scatter(bkey, bcursor, n, nullptr, perm, tok8, meta.data(), tok8_sorted, meta_sorted); });
+
+    MatchParams mp{};
+    mp.tv = tv; mp.tok8 = tok8; mp.tok = tok.data(); mp.meta = meta.data(); mp.n = n; mp.n_ptr = nullptr; mp.tok_levels = S;
+    mp.spans = reinterpret_cast<uint2*>(out_spans); mp.out_ids = static_cast<u32*>(d_out); mp.out_desc = static_cast<uint2*>(d_out); mp.cap_ids = cap;
+    mp.status = status; mp.trees = trees;
+    mp.cursor = &ctrl.cursor; mp.slow_list = slow.data(); mp.slow_count = &ctrl.slow_count; mp.tile_counter = &ctrl.tile_counter; mp.stats = ctrl.stats;
+    mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
+    mp.flags = MP_SORTED_ROWS; mp.tile_chunk = 1;
+    emu::launch(dim3(k2_grid), dim3(K2_THREADS), [&] {
+        if (stats) { if (desc) k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true, true>(mp, gpool.data(), e.pool_rows); else k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, true, false>(mp, gpool.data(), e.pool_rows); }
+        else { if (desc) k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, true>(mp, gpool.data(), e.pool_rows); else k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, false>(mp, gpool.data(), e.pool_rows); }
+    });
+    emu::launch(dim3(k3_blocks), dim3(256), [&] {
+        if (stats) { if (desc) k_match_slow<true, true>(mp, gstack.data(), stack_cap); else k_match_slow<true, false>(mp, gstack.data(), stack_cap); }
+        else { if (desc) k_match_slow<false, true>(mp, gstack.data(), stack_cap); else k_match_slow<false, false>(mp, gstack.data(), stack_cap); }
+    });
+    if (deferred) *deferred = ctrl.slow_count;
+    if (work) for (int k = 0; k < 4; ++k) work[k] = ctrl.stats[k];
+    *needed = ctrl.cursor;
+    if (ctrl.cursor > cap_ids) return -3;
+    if (!desc) return 0;
+    // descriptor mode: expand (ref, cnt) into ids out of the host mirror, per topic, so that the caller compares id lists
+    u64 w = 0;
+    for (u32 t = 0; t < n; ++t) {
+        const u32 off = out_spans[t].off, cnt = out_spans[t].cnt;
+        const u64 begin = w;
+        for (u32 k = 0; k < cnt; ++k) {
+            const uint2 d = descs[off + k];
+            if (d.y == 1) ids_tmp.push_back(d.x);
+            else {
+                u64 o = d.x, c = d.y;
+                if (d.y == CNT_BIG) { o = e.trie.ranges[d.x].off; c = e.trie.ranges[d.x].cnt; }
+                for (u64 j = 0; j < c; ++j) ids_tmp.push_back(e.trie.values[o + j]);
+            }
+        }
+        w = ids_tmp.size();
+        out_spans[t] = gm_span{static_cast<u32>(begin), static_cast<u32>(w - begin)};
+    }
+    *needed = w;                      // (in descriptor mode the capacity the caller must offer is the expanded size)
+    if (w > cap_ids) return -3;
+    std::memcpy(out_ids, ids_tmp.data(), w * sizeof(u32));
+    return 0;
+}
+
+// RetainStorage::get for a batch of filters through k_tokenize -> k_retain_init -> k_retain_round x (depth + 1) -> k_retain_scan -> k_retain_expand
+int32_t emu_retain_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n64, uint32_t stats_on, uint32_t cap_items, uint32_t cap_desc, gm_span* out_spans,
+                         uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed, int32_t* status, uint64_t* work) {
+    EmuEngine& e = *static_cast<EmuEngine*>(h);
+    const u32 nq = static_cast<u32>(n64);
+    *needed = 0;
+    if (nq == 0) return 0;
+    if (!e.trie.sync()) return -7;
+    e.rtree.prepare_flush();
+    e.rtree.shipped();
+    const TrieView tv = e.view();
+    const RetainView rv = e.rview();
+    const u32 depth = rv.max_depth, S = depth + 2;
+    const u32 blob_bytes = offs[nq];
+    std::vector<u8> blob_store(static_cast<size_t>(blob_bytes) + 64, 0);
+    u8* blob = blob_store.data() + ((16 - (reinterpret_cast<uintptr_t>(blob_store.data()) & 15)) & 15);
+    std::memcpy(blob, blob_in, blob_bytes);
+    std::vector<u32> tok(S > TOK8 ? static_cast<size_t>(S) * nq : 64), meta(nq);
+    std::vector<u32> tok8_store(static_cast<size_t>(nq) * TOK8 + 16);
+    u32* tok8 = tok8_store.data() + ((32 - (reinterpret_cast<uintptr_t>(tok8_store.data()) & 31)) & 31) / 4;
+    struct RCtl { unsigned long long grand; unsigned long long stats[2]; u32 err; u32 pad; u32 n_desc[RQ]; };
+    RCtl ctl{};
+    std::vector<u32> counts(static_cast<size_t>(depth + 3) * RQ + (depth + 3), 0);
+    std::vector<u32> rq(static_cast<size_t>(nq) * 3, 0);
+    u32* qtotal = rq.data(); u32* qbase = qtotal + nq; u32* qcur = qbase + nq;
+    const u32 slice_items = std::max<u32>(1u, cap_items / RQ), slice_desc = std::max<u32>(1u, cap_desc / RQ);
+    std::vector<RTask> front[2] = {std::vector<RTask>(static_cast<size_t>(slice_items) * RQ), std::vector<RTask>(static_cast<size_t>(slice_items) * RQ)};
+    std::vector<RDesc> rdescs(static_cast<size_t>(slice_desc) * RQ);
+    for (u32 i = 0; i < nq; ++i) status[i] = 0x7F7F7F7F;
+    emu::launch(dim3((nq + TOK_THREADS - 1) / TOK_THREADS), dim3(TOK_THREADS), [&] {
+        k_tokenize<false>(blob, blob_bytes, blob_bytes, offs, nullptr, nq, nullptr, tv, S, tok8, tok.data(), meta.data(), status, nullptr, nullptr, 0u, 0u);
+    });
+    RetainParams rp{};
+    rp.v = rv; rp.qtok8 = tok8; rp.qtok = tok.data(); rp.qmeta = meta.data(); rp.nq = nq; rp.tok_levels = S;
+    rp.descs = rdescs.data(); rp.n_desc = ctl.n_desc; rp.cap_items = slice_items; rp.cap_desc = slice_desc;
+    rp.qtotal = qtotal; rp.err = &ctl.err; rp.stats = ctl.stats;
+    emu::launch(dim3((nq + 255) / 256), dim3(256), [&] { if (stats_on) k_retain_init<true>(rp, front[0].data(), &counts[0]); else k_retain_init<false>(rp, front[0].data(), &counts[0]); });
+    const int rgrid = EMU_SMS * GM_RETAIN_CTAS;
+    for (u32 lvl = 0; lvl <= depth; ++lvl)
+        emu::launch(dim3(rgrid), dim3(256), [&] {
+            u32* claim = &counts[static_cast<size_t>(depth + 3) * RQ + lvl];
+            if (stats_on) k_retain_round<true>(rp, front[lvl & 1].data(), &counts[static_cast<size_t>(lvl) * RQ], front[(lvl + 1) & 1].data(), &counts[static_cast<size_t>(lvl + 1) * RQ], claim);
+            else k_retain_round<false>(rp, front[lvl & 1].data(), &counts[static_cast<size_t>(lvl) * RQ], front[(lvl + 1) & 1].data(), &counts[static_cast<size_t>(lvl + 1) * RQ], claim);
+        });
+    emu::launch(dim3(1), dim3(1024), [&] { k_retain_scan(qtotal, nq, qbase, reinterpret_cast<uint2*>(out_spans), &ctl.grand); });
+    emu::launch(dim3(EMU_SMS * 8), dim3(256), [&] { k_retain_expand(rdescs.data(), ctl.n_desc, slice_desc, rv.vals, qbase, qcur, out_ids, cap_ids); });
+    if (work) { work[0] = ctl.stats[0]; work[1] = ctl.stats[1]; }
+    if (ctl.err) return -100 - static_cast<int32_t>(ctl.err);      // scratch overflow: bit 0 tasks, bit 1 descriptors (the engine grows and retries)
+    *needed = ctl.grand;
+    return ctl.grand > cap_ids ? -3 : 0;
+}
+
+// gm_relations_expand_device over host arrays (k_relations)
+int32_t emu_relations(const gm_span* spans, const uint32_t* ids, uint64_t n, const uint32_t* pubs, const gm_rel* rels, uint64_t n_rels, gm_span* out_spans,
+                      gm_sub_relation* out_rels, uint64_t cap_rels, uint32_t* out_sub_ids, uint64_t cap_sub_ids, uint64_t* needed3, int32_t* status) {
+    needed3[0] = needed3[1] = needed3[2] = 0;
+    if (n == 0) return 0;
+    RelParams rp{};
+    rp.spans = reinterpret_cast<const uint2*>(spans); rp.ids = ids; rp.n = static_cast<u32>(n); rp.pubs = pubs; rp.rels = rels; rp.n_rels = static_cast<u32>(n_rels);
+    rp.out_spans = reinterpret_cast<uint2*>(out_spans); rp.out_rels = out_rels; rp.cap_rels = cap_rels; rp.out_sub_ids = out_sub_ids; rp.cap_sub_ids = cap_sub_ids;
+    rp.needed = reinterpret_cast<unsigned long long*>(needed3); rp.status = status;
+    const unsigned grid = static_cast<unsigned>(std::min<u64>((n + 7) / 8, static_cast<u64>(EMU_SMS) * 8));
+    emu::launch(dim3(grid), dim3(256), [&] { k_relations(rp); });
+    return 0;
+}
+
+}  // extern "C"

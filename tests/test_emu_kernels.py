@@ -1,0 +1,314 @@
+"""CPU tier: the REAL kernel sources (rmqtt_b200/csrc/kernels.cuh, retain_kernels.cuh, relations.cuh) executed on the CPU by
+the small CUDA-model emulation under tests/native/emu (threads of a CTA as fibers, warp collectives and barriers as
+rendezvous points), driven like engine.cu drives them, and compared with the oracle — bit-exact sorted multisets, plus the
+exact work counters V / E / F / M of the instrumented instantiations.
+
+What this tier adds to the GPU tier: it runs HERE (no device), so a logic or indexing regression in a kernel shows up in the
+`-m "not gpu"` suite; and the second build puts the kernels under AddressSanitizer + UBSan (out-of-bounds shared / global
+accesses, misaligned vector accesses, shifts).  What it cannot see: memory ordering, scheduling, performance — the GPU tier
+and compute-sanitizer cover those.  The product (`libgpumqtt.so`) is built from the same sources without GM_CPU_EMU and never
+contains any of this."""
+import ctypes as C
+import random
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from rmqtt_b200.engine import MatchResult, pack
+
+from _gen import rand_filter, rand_topic
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "rmqtt_b200" / "csrc"
+EMU = ROOT / "tests" / "native" / "emu"
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+
+
+class Span(C.Structure):
+    _fields_ = [("off", C.c_uint32), ("cnt", C.c_uint32)]
+
+
+def _build(tmp, san: bool):
+    out = tmp / ("libemu_asan.so" if san else "libemu.so")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-DGM_CPU_EMU", f"-I{EMU}", f"-I{CSRC}", "-shared", "-fPIC", "-pthread", "-fno-omit-frame-pointer",
+           *(["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] if san else []),
+           "-o", str(out), str(EMU / "emu_driver.cpp"), str(CSRC / "host_trie.cpp"), str(CSRC / "retain_tree.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr and "cannot find" in r.stderr:
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-3000:]
+    return out
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    lib = C.CDLL(str(_build(tmp_path_factory.mktemp("emu"), san=False)))
+    lib.emu_new.restype = C.c_void_p
+    for f in ("emu_sub_add", "emu_sub_remove", "emu_retain_set", "emu_retain_remove", "emu_match", "emu_retain_match", "emu_relations"):
+        getattr(lib, f).restype = C.c_int32
+    return lib
+
+
+class Emu:
+    def __init__(self, lib):
+        self.lib, self.h = lib, C.c_void_p(lib.emu_new())
+
+    def close(self):
+        if self.h:
+            self.lib.emu_free(self.h)
+            self.h = None
+
+    def add(self, f, v, tree=0):
+        b = f.encode() if isinstance(f, str) else f
+        return self.lib.emu_sub_add(self.h, b, len(b), v, tree)
+
+    def remove(self, f, v, tree=0):
+        b = f.encode() if isinstance(f, str) else f
+        return self.lib.emu_sub_remove(self.h, b, len(b), v, tree)
+
+    def retain_set(self, t, v):
+        b = t.encode()
+        return self.lib.emu_retain_set(self.h, b, len(b), v)
+
+    def retain_remove(self, t):
+        b = t.encode()
+        return self.lib.emu_retain_remove(self.h, b, len(b))
+
+    def match(self, blob, offs, flags=0, trees=None):
+        n = len(offs) - 1
+        spans = np.zeros((n, 2), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        work = np.zeros(4, dtype=np.uint64)
+        deferred, needed = C.c_uint32(0), C.c_uint64(0)
+        cap = 1024
+        blob = np.ascontiguousarray(blob if len(blob) else np.zeros(1, np.uint8))
+        while True:
+            ids = np.zeros(cap, dtype=np.uint32)
+            rc = self.lib.emu_match(self.h, C.c_void_p(blob.ctypes.data), C.c_void_p(offs.ctypes.data), C.c_uint64(n), C.c_void_p(trees.ctypes.data) if trees is not None else None, flags,
+                                    C.c_void_p(spans.ctypes.data), C.c_void_p(ids.ctypes.data), C.c_uint64(cap), C.byref(needed), C.c_void_p(status.ctypes.data), C.c_void_p(work.ctypes.data), C.byref(deferred))
+            if rc == -3:
+                cap = int(needed.value) + 16
+                continue
+            assert rc == 0, rc
+            return MatchResult(spans, ids[:int(needed.value)], status, int(needed.value)), work, int(deferred.value)
+
+    def retain_match(self, blob, offs, stats=0, cap_items=1 << 14, cap_desc=1 << 14):
+        n = len(offs) - 1
+        spans = np.zeros((n, 2), dtype=np.uint32)
+        status = np.zeros(n, dtype=np.int32)
+        work = np.zeros(2, dtype=np.uint64)
+        needed = C.c_uint64(0)
+        cap, grew = 1024, 0
+        blob = np.ascontiguousarray(blob if len(blob) else np.zeros(1, np.uint8))
+        while True:
+            ids = np.zeros(cap, dtype=np.uint32)
+            rc = self.lib.emu_retain_match(self.h, C.c_void_p(blob.ctypes.data), C.c_void_p(offs.ctypes.data), C.c_uint64(n), stats, cap_items, cap_desc, C.c_void_p(spans.ctypes.data), C.c_void_p(ids.ctypes.data),
+                                           C.c_uint64(cap), C.byref(needed), C.c_void_p(status.ctypes.data), C.c_void_p(work.ctypes.data))
+            if rc == -3:
+                cap = int(needed.value) + 16
+                continue
+            if rc <= -100:                       # scratch overflow bits: grow like gm_engine::run_retain does
+                err = -rc - 100
+                cap_items *= 4 if err & 1 else 1
+                cap_desc *= 4 if err & 2 else 1
+                grew += 1
+                assert grew < 12
+                continue
+            assert rc == 0, rc
+            return MatchResult(spans, ids[:int(needed.value)], status, int(needed.value)), work, grew
+
+
+def _canon(want):
+    ids = want["ids"].copy()
+    o = want["offsets"]
+    for i in range(len(o) - 1):
+        ids[o[i]:o[i + 1]].sort()
+    return want["counts"], ids
+
+
+def _same(res, want):
+    counts, ids = res.canonical()
+    wc, wi = _canon(want)
+    assert (counts == wc).all(), f"counts differ at {np.nonzero(counts != wc)[0][:5]}: {counts[counts != wc][:5]} vs {wc[counts != wc][:5]}"
+    assert len(ids) == len(wi) and (ids == wi).all()
+
+
+def _random_trie(e, tree, rng, n_filters, removals=0):
+    fs = []
+    for _ in range(n_filters):
+        f, v = rand_filter(rng), rng.randint(0, 40)
+        ok = e.add(f, v) == 0
+        try:
+            tree.insert(f, v)
+            assert ok, f
+            fs.append((f, v))
+        except ValueError:
+            assert not ok, f
+    for f, v in rng.sample(fs, min(removals, len(fs))):
+        assert e.remove(f, v) == 0
+        tree.remove(f, v)
+
+
+@pytest.mark.parametrize("seed,flags", [(1, 0), (2, 1), (3, 2), (4, 3), (5, 4), (6, 5)])
+def test_publish_pipeline_on_the_emulator_equals_the_oracle(emu, seed, flags):
+    """k_tokenize (plain and bulk-staged) -> k_bucket_scan -> k_bucket_scatter -> k_match_fast (ids / descriptors, plain /
+    instrumented) -> k_match_slow over a random trie with every special case of SURVEY §8a in the alphabet."""
+    rng = random.Random(seed)
+    e, tree = Emu(emu), orc.TopicTree()
+    # (removals leave pruned nodes behind as dead device records until gm_compact: results are unaffected, but the kernels then
+    #  VISIT more nodes than the reference algorithm — the exact-counter runs therefore use a trie without removals)
+    _random_trie(e, tree, rng, 1500, removals=0 if flags & 4 else 200)
+    topics = [rand_topic(rng) for _ in range(1500)] + ["", "/", "//", "$SYS", "$SYS/a", "+", "#", "a/+", "a/#", "a/#/b", "a+/b", "x" * 200, "/".join(["a"] * 9)]
+    tb, to = pack(topics)
+    res, work, _ = e.match(tb, to, flags)
+    want = tree.match_batch(tb, to)
+    _same(res, want)
+    assert (res.status[want["counts"] < 0] == -2).all() and (res.status[want["counts"] >= 0] == 0).all()
+    if flags & 4:                                # the instrumented instantiations count exactly what the reference algorithm does
+        c = want["counters"]
+        assert [int(x) for x in work] == [c["V"], c["E"], c["F"], c["M"]]
+    e.close()
+
+
+def test_deferred_kernel_deep_topics_heavy_hitters_and_huge_sets(emu):
+    """Everything k_match_fast hands to k_match_slow: more than 8 levels, more matched value sets than the staging pool holds
+    (pool_rows lowered to 1: 9 sets), a value set of >= 65535 members (the `ranges` indirection) — in ids and descriptor mode."""
+    e, tree = Emu(emu), orc.TopicTree()
+    emu.emu_set_pool_rows(e.h, 1)
+    deep = "/".join(f"l{i}" for i in range(20))
+    fl = [deep, "/".join(["+"] * 20), "l0/l1/#", deep + "/#", "/".join(["l0"] + ["+"] * 10) + "/#", "#", "+/#", "l0/#", "l0/+/#", "l0/l1/+/#", "l0/l1/l2/#",
+          "l0/l1/l2/+/#", "+/l1/#", "+/+/l2/#", "+/+/+/#", "l0/+/l2/#"]
+    for i, f in enumerate(fl):
+        assert e.add(f, i) == 0
+        tree.insert(f, i)
+    for v in range(66000):
+        e.add("hot/+", v)
+    tree.bulk_insert(*pack(["hot/+"] * 66000), np.arange(66000, dtype=np.uint32))
+    for v in range(300):
+        e.add("warm/#", v); tree.insert("warm/#", v)
+    topics = [deep, deep + "/x", "l0/l1", "hot/a", "hot", "warm/x/y", "l0/" + "/".join(["q"] * 19), "l0/l1/l2/l3/l4"] * 9
+    tb, to = pack(topics)
+    for flags in (0, 1, 4, 5):
+        res, work, deferred = e.match(tb, to, flags)
+        want = tree.match_batch(tb, to)
+        _same(res, want)
+        assert deferred >= 9 * 5                  # the deep ones, the 9+-set ones and the huge set really took the deferred kernel
+        if flags & 4:
+            c = want["counters"]
+            assert [int(x) for x in work] == [c["V"], c["E"], c["F"], c["M"]]
+    e.close()
+
+
+def test_extra_trees_rows_of_the_same_batch(emu):
+    """gm_match_batch_trees: a row names the tree it is matched against; the `$`-rule applies at each tree's own root."""
+    rng = random.Random(77)
+    e = Emu(emu)
+    trees = {0: orc.TopicTree(), 1: orc.TopicTree(), 5: orc.TopicTree()}
+    for k, t in trees.items():
+        for _ in range(300):
+            f, v = rand_filter(rng), rng.randint(0, 20)
+            try:
+                t.insert(f, v)
+            except ValueError:
+                continue
+            assert e.add(f, v, tree=k) == 0
+    topics = [rand_topic(rng) for _ in range(600)]
+    rows = np.asarray([rng.choice([0, 1, 5, 9]) for _ in topics], dtype=np.uint32)       # 9: no such tree -> nothing matches
+    tb, to = pack(topics)
+    res, _, _ = e.match(tb, to, 0, trees=rows)
+    for i, (t, k) in enumerate(zip(topics, rows)):
+        if orc.topic_parse(t) is None:
+            want = None                               # Topic::from_str Err: whatever the tree
+        else:
+            want = sorted(trees[int(k)].matches(t)) if int(k) in trees else []
+        assert res.sorted_list(i) == want, (t, k)
+    e.close()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_retained_pipeline_on_the_emulator_equals_the_oracle(emu, seed):
+    """k_tokenize -> k_retain_init -> k_retain_round x (depth + 1) -> k_retain_scan -> k_retain_expand over a random retained
+    tree (bulk-built image, then in-place edits), incl. literal '+' / '#' levels that shadow wildcard expansion and a scratch
+    that starts too small (the overflow bits make the caller grow it, as gm_engine::run_retain does)."""
+    rng = random.Random(seed)
+    e, tree = Emu(emu), orc.RetainTree()
+    names = []
+    for i in range(2500):
+        t = rand_topic(rng, max_depth=6) if rng.random() < 0.93 else rand_filter(rng, 5)
+        if e.retain_set(t, i) != 0:
+            with pytest.raises(ValueError):
+                tree.insert(t, i)
+            continue
+        tree.remove(t)
+        tree.insert(t, i)
+        names.append(t)
+    filters = [rand_filter(rng, 7) for _ in range(700)] + ["#", "+/#", "+", "$SYS/#", "+/+/+/+/+/+", "a/+/#", "+/+/#", "a/#"]
+    fb, fo = pack(filters)
+    res, work, grew = e.retain_match(fb, fo, stats=1, cap_items=64, cap_desc=64)
+    assert grew >= 1
+    _same(res, tree.match_batch(fb, fo))
+    for t in rng.sample(names, 400):              # in-place edits of the image, then again
+        e.retain_remove(t)
+        tree.remove(t)
+    for i in range(300):
+        t = rand_topic(rng, max_depth=6)
+        if e.retain_set(t, 100000 + i) == 0:
+            tree.remove(t)
+            tree.insert(t, 100000 + i)
+    res, _, _ = e.retain_match(fb, fo)
+    _same(res, tree.match_batch(fb, fo))
+    e.close()
+
+
+def test_kernels_under_asan_ubsan(tmp_path):
+    """The same pipelines, kernels and host builders compiled with AddressSanitizer + UBSan, in a subprocess (the sanitizer
+    runtime must be loaded first): a mixed publish batch incl. the deferred path, and a retained batch."""
+    so = _build(tmp_path, san=True)
+    script = tmp_path / "run.py"
+    script.write_text(f"""
+import sys, random, ctypes as C
+sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r})
+import numpy as np
+import test_emu_kernels as T
+from oracle import oracle as orc
+from rmqtt_b200.engine import pack
+lib = C.CDLL({str(so)!r})
+lib.emu_new.restype = C.c_void_p
+for f in ("emu_sub_add", "emu_sub_remove", "emu_retain_set", "emu_retain_remove", "emu_match", "emu_retain_match"):
+    getattr(lib, f).restype = C.c_int32
+rng = random.Random(5)
+e, tree = T.Emu(lib), orc.TopicTree()
+lib.emu_set_pool_rows(e.h, 2)
+T._random_trie(e, tree, rng, 800, removals=100)
+for v in range(40):
+    e.add("+/#", 1000 + v); tree.insert("+/#", 1000 + v)
+topics = [T.rand_topic(rng) for _ in range(700)] + ["", "x" * 300, "/".join(["a"] * 12)]
+tb, to = pack(topics)
+for flags in (0, 1, 2, 3, 4):
+    res, _, _ = e.match(tb, to, flags)
+    T._same(res, tree.match_batch(tb, to))
+rt = orc.RetainTree()
+for i in range(1200):
+    t = T.rand_topic(rng, max_depth=6)
+    if e.retain_set(t, i) == 0:
+        rt.remove(t); rt.insert(t, i)
+fb, fo = pack([T.rand_filter(rng, 7) for _ in range(300)] + ["#", "+/#", "+/+/+"])
+res, _, _ = e.retain_match(fb, fo, cap_items=128, cap_desc=128)
+T._same(res, rt.match_batch(fb, fo))
+e.close()
+print("asan run ok")
+""")
+    libasan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    env = {"PATH": "/usr/bin:/bin", "LD_PRELOAD": libasan, "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0", "PYTHONPATH": str(ROOT)}
+    import os
+    import sys
+    for k in ("HOME", "LD_LIBRARY_PATH", "VIRTUAL_ENV"):
+        if k in os.environ:
+            env[k] = os.environ[k]
+    run = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=1500, env=env)
+    assert run.returncode == 0 and "asan run ok" in run.stdout, (run.stdout[-1500:], run.stderr[-4000:])
