@@ -312,3 +312,86 @@ print("asan run ok")
             env[k] = os.environ[k]
     run = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=1500, env=env)
     assert run.returncode == 0 and "asan run ok" in run.stdout, (run.stdout[-1500:], run.stderr[-4000:])
+
+
+def test_relation_expansion_kernel_against_a_python_model(emu):
+    """k_relations (router.rs:182-239 + types.rs:478-508 on the device): no_local, pass-through of v3 / shared-group members,
+    per-client de-dup of v5 relations with accumulation of subscription identifiers, the > 256-relation hand-over — on synthetic
+    match lists (duplicates, dead and out-of-range handles included) against a direct Python restatement."""
+    from rmqtt_b200 import _native as N
+
+    class GmRel(C.Structure):                               # include/gpumqtt.h gm_rel (24 bytes)
+        _fields_ = [("node_id", C.c_uint64), ("client_key", C.c_uint32), ("id_idx", C.c_uint32), ("sub_id", C.c_uint32), ("flags", C.c_uint32)]
+
+    rng = random.Random(99)
+    n_rels = 900
+    rels = (GmRel * n_rels)()
+    table = []
+    for h in range(n_rels):
+        live = rng.random() < 0.9
+        v5 = rng.random() < 0.6
+        group = rng.choice([0, 0, 0, 1, 2])
+        flags = (1 if live else 0) | (2 if v5 else 0) | (4 if rng.random() < 0.3 else 0) | (group << 8)
+        r = dict(node_id=rng.randint(1, 3), client_key=rng.randint(0, 120), id_idx=rng.randint(0, 200), sub_id=rng.choice([0, 0, 3, 7, 9]), flags=flags)
+        table.append(r)
+        rels[h].node_id, rels[h].client_key, rels[h].id_idx, rels[h].sub_id, rels[h].flags = r["node_id"], r["client_key"], r["id_idx"], r["sub_id"], r["flags"]
+    lists = []
+    for t in range(120):
+        k = rng.choice([0, 1, 5, 40, 300, 700]) if t % 10 else 700
+        lst = [rng.randint(0, n_rels + 20) for _ in range(k)]
+        if lst and rng.random() < 0.5:
+            lst += lst[:3]                                  # the same handle twice (literal '+' / '#' topic levels)
+        lists.append(lst)
+    n = len(lists)
+    spans = np.zeros((n, 2), dtype=np.uint32)
+    ids = np.asarray([h for l in lists for h in l] + [0], dtype=np.uint32)
+    o = 0
+    for i, l in enumerate(lists):
+        spans[i] = (o, len(l)); o += len(l)
+    pubs = np.asarray([rng.choice([0xFFFFFFFF, rng.randint(0, 200)]) for _ in range(n)], dtype=np.uint32)
+    cap_r, cap_s = len(ids) + 8, len(ids) + 8
+    out_spans = np.zeros((n, 2), dtype=np.uint32)
+    out_rels = (N.GmSubRelation * cap_r)()
+    out_subs = np.zeros(cap_s, dtype=np.uint32)
+    needed = np.zeros(3, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    rc = emu.emu_relations(C.c_void_p(spans.ctypes.data), C.c_void_p(ids.ctypes.data), C.c_uint64(n), C.c_void_p(pubs.ctypes.data), rels, C.c_uint64(n_rels),
+                           C.c_void_p(out_spans.ctypes.data), out_rels, C.c_uint64(cap_r), C.c_void_p(out_subs.ctypes.data), C.c_uint64(cap_s),
+                           C.c_void_p(needed.ctypes.data), C.c_void_p(status.ctypes.data))
+    assert rc == 0
+    tot_r = tot_s = 0
+    flagged = 0
+    for t, lst in enumerate(lists):
+        direct, v5 = [], []
+        for h in lst:
+            if h >= n_rels:
+                continue
+            r = table[h]
+            if not r["flags"] & 1:
+                continue
+            if (r["flags"] & 2) and (r["flags"] & 4) and pubs[t] != 0xFFFFFFFF and r["id_idx"] == pubs[t]:
+                continue                                    # no_local: the publisher's own subscription
+            (v5 if (r["flags"] & 2) and (r["flags"] >> 8) == 0 else direct).append(h)
+        want = [(table[h]["node_id"], h, table[h]["flags"] >> 8, ()) for h in direct]
+        if len(v5) > 256:                                   # handed over un-deduplicated, the topic is flagged
+            want += [(table[h]["node_id"], h, 0, ()) for h in v5]
+            assert status[t] == 1
+            flagged += 1
+        else:
+            assert status[t] == 0
+            by_client = {}
+            for h in v5:
+                by_client.setdefault(table[h]["client_key"], []).append(h)
+            for key, hs in by_client.items():
+                rep = min(hs)
+                subs = tuple(table[h]["sub_id"] for h in hs if table[h]["sub_id"])
+                want.append((table[rep]["node_id"], rep, 0, subs))
+                tot_s += len(subs)
+        off, cnt = int(out_spans[t, 0]), int(out_spans[t, 1])
+        got = []
+        for k in range(cnt):
+            sr = out_rels[off + k]
+            got.append((sr.node_id, sr.handle, sr.group, tuple(int(x) for x in out_subs[sr.sub_ids_off:sr.sub_ids_off + sr.sub_ids_cnt])))
+        assert sorted(got) == sorted(want), t
+        tot_r += cnt
+    assert flagged >= 1 and int(needed[0]) == tot_r and int(needed[1]) == tot_s
