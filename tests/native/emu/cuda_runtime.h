@@ -199,7 +199,7 @@ inline void __threadfence() {}
 inline void __threadfence_block() {}
 inline void __threadfence_system() {}
 inline void __nanosleep(unsigned) { emu::S().progress++; emu::yield(); }      // (a polling loop: let the others run)
-inline long long clock64() { static long long c = 0; return c += 1000; }
+inline long long clock64() { static long long c = 0; return c += 20000000; }   // (bounded device-side waits end after a few hundred polls)
 
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int = 32) {
     static_assert(sizeof(T) <= 8, "shuffle of up to 64 bits");

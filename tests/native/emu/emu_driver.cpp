@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../../include/gpumqtt.h"
+#include "comm.cuh"
 #include "host_trie.h"
 #include "kernels.cuh"
 #include "relations.cuh"
@@ -83,16 +84,29 @@ int32_t emu_retain_remove(void* h, const char* t, uint32_t len) {
 // flags: bit 0 descriptor mode (the descriptors are expanded here from the host mirror, so `out_ids` holds ids either way),
 //        bit 1 the bulk-staged tokeniser, bit 2 the instrumented (STATS) instantiations; work[4] = V, E, F, M then.
 // Returns 0, or -3 with *needed when cap_ids is too small (the engine's capacity protocol).
-int32_t emu_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n64, const uint32_t* trees, uint32_t flags, gm_span* out_spans, uint32_t* out_ids,
-                  uint64_t cap_ids, uint64_t* needed, int32_t* status, uint64_t* work, uint32_t* deferred) {
+//        bit 3 the batch is a SELECTION: row t matches entry sel[t] of the packed batch (n rows, n_entries entries; gm_match_args.d_sel),
+//        bit 4 the small-batch-graph form: the kernels are launched for a CAPACITY larger than the batch and read the real
+//              batch size / text length from a header in memory (engine.cu small_graph_match).
+int32_t emu_match_ex(void* h, const char* blob_in, const uint32_t* offs, uint64_t n_entries, const uint32_t* sel, uint64_t n64, const uint32_t* trees, uint32_t flags,
+                     gm_span* out_spans, uint32_t* out_ids, uint64_t cap_ids, uint64_t* needed, int32_t* status, uint64_t* work, uint32_t* deferred) {
     EmuEngine& e = *static_cast<EmuEngine*>(h);
-    const bool desc = flags & 1u, bulk = flags & 2u, stats = flags & 4u;
-    const u32 n = static_cast<u32>(n64);
+    const bool desc = flags & 1u, bulk = flags & 2u, stats = flags & 4u, graph_form = flags & 16u;
+    if (!(flags & 8u)) sel = nullptr;
+    const u32 n_real = static_cast<u32>(n64);
     *needed = 0;
-    if (n == 0) return 0;
+    if (n_real == 0) return 0;
     if (!e.trie.sync()) return -7;
     const TrieView tv = e.view();
-    const u32 blob_bytes = offs[n];
+    const u32 blob_bytes = offs[n_entries];
+    const u32 n = graph_form ? n_real + 37u : n_real;            // launch size (rows beyond the real batch must stay untouched)
+    u32 hdr_store[4] = {n_real, blob_bytes, 0u, 0u};
+    const u32* hdr = graph_form ? hdr_store : nullptr;
+    std::vector<u32> offs_cap;
+    if (graph_form) {                                             // the in-block holds capacity + 1 offsets; the tail is never read
+        offs_cap.assign(offs, offs + n_entries + 1);
+        offs_cap.resize(static_cast<size_t>(n) + 1, 0xDEADBEEFu);
+        offs = offs_cap.data();
+    }
     // the bulk stage wants a 16-byte aligned blob that may be read up to a 16-byte boundary
     const size_t readable = (static_cast<size_t>(blob_bytes) + 15) & ~size_t(15);
     std::vector<u8> blob_store(readable + 64, 0);
@@ -121,18 +135,28 @@ int32_t emu_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n
     u64 cap = cap_ids;
     if (desc) { descs.resize(cap_ids + 1); d_out = descs.data(); }
 
-    for (u32 i = 0; i < n; ++i) status[i] = 0x7F7F7F7F;        // every row must be written by the tokeniser
+    std::vector<int32_t> status_cap;
+    int32_t* status_k = status;
+    if (graph_form) { status_cap.assign(n, 0x7F7F7F7F); status_k = status_cap.data(); }
+    for (u32 i = 0; i < n_real; ++i) status[i] = 0x7F7F7F7F;   // every row must be written by the tokeniser
     emu::launch(dim3((n + TOK_THREADS - 1) / TOK_THREADS), dim3(TOK_THREADS), [&] {
-        if (bulk) k_tokenize<true>(blob, blob_bytes, static_cast<u32>(readable), offs, nullptr, n, nullptr, tv, S, tok8, tok.data(), meta.data(), status, bkey, hist, e.site_bits, 0u);
-        else k_tokenize<false>(blob, blob_bytes, static_cast<u32>(readable), offs, nullptr, n, nullptr, tv, S, tok8, tok.data(), meta.data(), status, bkey, hist, e.site_bits, 0u);
+        if (bulk) k_tokenize<true>(blob, blob_bytes, static_cast<u32>(readable), offs, sel, n, hdr, tv, S, tok8, tok.data(), meta.data(), status_k, bkey, hist, e.site_bits, 0u);
+        else k_tokenize<false>(blob, blob_bytes, static_cast<u32>(readable), offs, sel, n, hdr, tv, S, tok8, tok.data(), meta.data(), status_k, bkey, hist, e.site_bits, 0u);
     });
     emu::launch(dim3(1), dim3(1024), [&] { k_bucket_scan(hist, bcursor, NB); });
-    emu::launch(dim3((n + 255) / 256), dim3(256), [&] { k_bucket_scatter(bkey, bcursor, n, nullptr, perm, tok8, meta.data(), tok8_sorted, meta_sorted); });
+    emu::launch(dim3((n + 255) / 256), dim3(256), [&] { k_bucket_scatter(bkey, bcursor, n, hdr, perm, tok8, meta.data(), tok8_sorted, meta_sorted); });
+    if (graph_form) {
+        for (u32 i = n_real; i < n; ++i) if (status_cap[i] != 0x7F7F7F7F) return -50;      // a row beyond the real batch was touched
+        std::memcpy(status, status_cap.data(), n_real * sizeof(int32_t));
+    }
+    std::vector<gm_span> spans_cap;
+    gm_span* spans_k = out_spans;
+    if (graph_form) { spans_cap.assign(n, gm_span{0xABABABABu, 0xABABABABu}); spans_k = spans_cap.data(); }
 
     MatchParams mp{};
-    mp.tv = tv; mp.tok8 = tok8; mp.tok = tok.data(); mp.meta = meta.data(); mp.n = n; mp.n_ptr = nullptr; mp.tok_levels = S;
-    mp.spans = reinterpret_cast<uint2*>(out_spans); mp.out_ids = static_cast<u32*>(d_out); mp.out_desc = static_cast<uint2*>(d_out); mp.cap_ids = cap;
-    mp.status = status; mp.trees = trees;
+    mp.tv = tv; mp.tok8 = tok8; mp.tok = tok.data(); mp.meta = meta.data(); mp.n = n; mp.n_ptr = hdr; mp.tok_levels = S;
+    mp.spans = reinterpret_cast<uint2*>(spans_k); mp.out_ids = static_cast<u32*>(d_out); mp.out_desc = static_cast<uint2*>(d_out); mp.cap_ids = cap;
+    mp.status = status_k; mp.trees = trees;
     mp.cursor = &ctrl.cursor; mp.slow_list = slow.data(); mp.slow_count = &ctrl.slow_count; mp.tile_counter = &ctrl.tile_counter; mp.stats = ctrl.stats;
     mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
     mp.flags = MP_SORTED_ROWS; mp.tile_chunk = 1;
@@ -144,6 +168,10 @@ int32_t emu_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n
         if (stats) { if (desc) k_match_slow<true, true>(mp, gstack.data(), stack_cap); else k_match_slow<true, false>(mp, gstack.data(), stack_cap); }
         else { if (desc) k_match_slow<false, true>(mp, gstack.data(), stack_cap); else k_match_slow<false, false>(mp, gstack.data(), stack_cap); }
     });
+    if (graph_form) {
+        for (u32 i = n_real; i < n; ++i) if (spans_cap[i].off != 0xABABABABu) return -51;
+        std::memcpy(out_spans, spans_cap.data(), n_real * sizeof(gm_span));
+    }
     if (deferred) *deferred = ctrl.slow_count;
     if (work) for (int k = 0; k < 4; ++k) work[k] = ctrl.stats[k];
     *needed = ctrl.cursor;
@@ -151,7 +179,7 @@ int32_t emu_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n
     if (!desc) return 0;
     // descriptor mode: expand (ref, cnt) into ids out of the host mirror, per topic, so that the caller compares id lists
     u64 w = 0;
-    for (u32 t = 0; t < n; ++t) {
+    for (u32 t = 0; t < n_real; ++t) {
         const u32 off = out_spans[t].off, cnt = out_spans[t].cnt;
         const u64 begin = w;
         for (u32 k = 0; k < cnt; ++k) {
@@ -170,6 +198,145 @@ int32_t emu_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n
     if (w > cap_ids) return -3;
     std::memcpy(out_ids, ids_tmp.data(), w * sizeof(u32));
     return 0;
+}
+
+int32_t emu_match(void* h, const char* blob_in, const uint32_t* offs, uint64_t n64, const uint32_t* trees, uint32_t flags, gm_span* out_spans, uint32_t* out_ids,
+                  uint64_t cap_ids, uint64_t* needed, int32_t* status, uint64_t* work, uint32_t* deferred) {
+    return emu_match_ex(h, blob_in, offs, n64, nullptr, n64, trees, flags & ~8u, out_spans, out_ids, cap_ids, needed, status, work, deferred);
+}
+
+// gm_partition_batch_device: k_partition.  counts[n_shards + 1] (the last entry = rows appended to sel)
+int32_t emu_partition(const char* blob, const uint32_t* offs, uint64_t n, uint32_t n_shards, uint32_t rank, uint32_t* sel, uint32_t* shard_out, uint32_t* counts) {
+    std::memset(counts, 0, (static_cast<size_t>(n_shards) + 1) * sizeof(u32));
+    if (n == 0) return 0;
+    const u32 blob_bytes = offs[n];
+    emu::launch(dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), [&] {
+        k_partition(reinterpret_cast<const u8*>(blob), blob_bytes, offs, static_cast<u32>(n), n_shards, rank, sel, shard_out, counts);
+    });
+    return 0;
+}
+
+// ---- the fused gather over "peer memory": every rank's block lives in host memory of this one process ---------------------------
+struct GatherWorld {
+    u32 world = 0; u64 slab_topics = 0, slab_ids = 0;
+    static constexpr size_t off_ids = 256;
+    size_t off_spans = 0, off_index = 0, off_counts = 0, off_flags = 0, bytes = 0;
+    std::vector<std::vector<char>> store;
+    std::vector<char*> block;
+    std::vector<u32> epoch;
+    std::vector<unsigned long long> cursor;      // the match cursor of every rank's last step (k_gather_push / k_gather_finish read it)
+};
+void* emu_gather_new(uint32_t world, uint64_t slab_topics, uint64_t slab_ids) {       // engine.cu gm_gather_create's layout
+    GatherWorld* g = new GatherWorld();
+    slab_topics = (slab_topics + 3) & ~uint64_t(3); slab_ids = (slab_ids + 3) & ~uint64_t(3);
+    g->world = world; g->slab_topics = slab_topics; g->slab_ids = slab_ids;
+    const size_t a = 256;
+    g->off_spans = (GatherWorld::off_ids + static_cast<size_t>(world) * slab_ids * 4 + a - 1) / a * a;
+    g->off_index = g->off_spans + static_cast<size_t>(world) * slab_topics * 8;
+    g->off_counts = (g->off_index + static_cast<size_t>(world) * slab_topics * 4 + a - 1) / a * a;
+    g->off_flags = g->off_counts + static_cast<size_t>(world) * 16;
+    g->bytes = g->off_flags + 256;
+    g->store.resize(world); g->block.resize(world); g->epoch.assign(world, 0); g->cursor.assign(world, 0);
+    for (u32 w = 0; w < world; ++w) {
+        g->store[w].assign(g->bytes + 256, static_cast<char>(0xEE));        // (stale bytes must never be read as results)
+        g->block[w] = g->store[w].data() + ((256 - (reinterpret_cast<uintptr_t>(g->store[w].data()) & 255)) & 255);
+        std::memset(g->block[w] + g->off_counts, 0, g->bytes - g->off_counts);
+    }
+    return g;
+}
+void emu_gather_free(void* p) { delete static_cast<GatherWorld*>(p); }
+uint64_t emu_gather_slab_ids(void* p) { return static_cast<GatherWorld*>(p)->slab_ids; }
+uint64_t emu_gather_slab_topics(void* p) { return static_cast<GatherWorld*>(p)->slab_topics; }
+
+// gm_match_gather_device of ONE rank: its rows (sel / n) through the GATHER instantiations of the match kernels, then — push form —
+// k_gather_push copies the rank's slab into every peer's block.  direct != 0: the publish phase stores into every block itself.
+int32_t emu_match_gather(void* gw, uint32_t rank, void* h, const char* blob_in, const uint32_t* offs, uint64_t n_entries, const uint32_t* sel, uint64_t n64,
+                         uint32_t direct, int32_t* status) {
+    GatherWorld& G = *static_cast<GatherWorld*>(gw);
+    EmuEngine& e = *static_cast<EmuEngine*>(h);
+    const u32 n = static_cast<u32>(n64);
+    if (n > G.slab_topics) return -3;
+    G.cursor[rank] = 0;
+    if (n) {
+        if (!e.trie.sync()) return -7;
+        const TrieView tv = e.view();
+        const u32 blob_bytes = offs[n_entries];
+        const size_t readable = (static_cast<size_t>(blob_bytes) + 15) & ~size_t(15);
+        std::vector<u8> blob_store(readable + 64, 0);
+        u8* blob = blob_store.data() + ((16 - (reinterpret_cast<uintptr_t>(blob_store.data()) & 15)) & 15);
+        std::memcpy(blob, blob_in, blob_bytes);
+        const u32 S = std::max<u32>(1u, tv.max_depth);
+        std::vector<u32> tok(S > TOK8 ? static_cast<size_t>(S) * n : 64), meta(n), slow(n);
+        std::vector<u32> tok8_store(static_cast<size_t>(n) * TOK8 + 16), sort_store(static_cast<size_t>(n) * 11 + 64);
+        u32* tok8 = tok8_store.data() + ((32 - (reinterpret_cast<uintptr_t>(tok8_store.data()) & 31)) & 31) / 4;
+        u32* sortb = sort_store.data() + ((32 - (reinterpret_cast<uintptr_t>(sort_store.data()) & 31)) & 31) / 4;
+        Ctrl ctrl{};
+        const u32 NB = 1u << e.site_bits;
+        std::vector<u32> hist_store(2 * static_cast<size_t>(NB) + 16, 0);
+        u32* hist = hist_store.data() + ((16 - (reinterpret_cast<uintptr_t>(hist_store.data()) & 15)) & 15) / 4;
+        u32* bcursor = hist + NB;
+        u32* bkey = sortb; u32* perm = bkey + n; u32* meta_sorted = perm + n;
+        u32* tok8_sorted = meta_sorted + n + ((8 - (3 * static_cast<size_t>(n)) % 8) % 8);
+        const u32 stack_cap = 32u * (tv.max_depth + 2u) + 64u;
+        const int k3_blocks = EMU_SMS * 4, k2_grid = EMU_SMS * K2_CTAS_PER_SM;
+        std::vector<u64> gstack(static_cast<size_t>(k3_blocks) * 8 * stack_cap);
+        std::vector<Desc> gpool(static_cast<size_t>(k2_grid) * K2_THREADS * std::max<u32>(e.pool_rows, 1u));
+        emu::launch(dim3((n + TOK_THREADS - 1) / TOK_THREADS), dim3(TOK_THREADS), [&] {
+            k_tokenize<false>(blob, blob_bytes, static_cast<u32>(readable), offs, sel, n, nullptr, tv, S, tok8, tok.data(), meta.data(), status, bkey, hist, e.site_bits, 0u);
+        });
+        emu::launch(dim3(1), dim3(1024), [&] { k_bucket_scan(hist, bcursor, NB); });
+        emu::launch(dim3((n + 255) / 256), dim3(256), [&] { k_bucket_scatter(bkey, bcursor, n, nullptr, perm, tok8, meta.data(), tok8_sorted, meta_sorted); });
+        MatchParams mp{};
+        mp.tv = tv; mp.tok8 = tok8; mp.tok = tok.data(); mp.meta = meta.data(); mp.n = n; mp.tok_levels = S;
+        mp.cap_ids = G.slab_ids; mp.status = status;
+        mp.cursor = &ctrl.cursor; mp.slow_list = slow.data(); mp.slow_count = &ctrl.slow_count; mp.tile_counter = &ctrl.tile_counter; mp.stats = ctrl.stats;
+        mp.perm = perm; mp.tok8_sorted = tok8_sorted; mp.meta_sorted = meta_sorted;
+        mp.flags = MP_SORTED_ROWS; mp.tile_chunk = 1;
+        mp.g_base_topics = static_cast<u32>(rank * G.slab_topics); mp.g_base_ids = rank * G.slab_ids; mp.g_sel = sel;     // engine.cu enqueue_match, gather_mode
+        if (direct) {
+            mp.g_world = G.world;
+            for (u32 w = 0; w < G.world; ++w) {
+                mp.g_ids[w] = reinterpret_cast<u32*>(G.block[w] + GatherWorld::off_ids); mp.g_spans[w] = reinterpret_cast<uint2*>(G.block[w] + G.off_spans);
+                mp.g_index[w] = reinterpret_cast<u32*>(G.block[w] + G.off_index);
+            }
+        } else {
+            mp.g_world = 1;
+            mp.g_ids[0] = reinterpret_cast<u32*>(G.block[rank] + GatherWorld::off_ids); mp.g_spans[0] = reinterpret_cast<uint2*>(G.block[rank] + G.off_spans);
+            mp.g_index[0] = reinterpret_cast<u32*>(G.block[rank] + G.off_index);
+        }
+        emu::launch(dim3(k2_grid), dim3(K2_THREADS), [&] { k_match_fast<K2_FAST_L, K2_THREADS, K2_CTAS_PER_SM, false, false, true>(mp, gpool.data(), e.pool_rows); });
+        emu::launch(dim3(k3_blocks), dim3(256), [&] { k_match_slow<false, false, true>(mp, gstack.data(), stack_cap); });
+        G.cursor[rank] = ctrl.cursor;
+        if (ctrl.cursor > G.slab_ids) return -3;
+    }
+    if (!direct && G.world > 1)
+        emu::launch(dim3(EMU_SMS * 4), dim3(256), [&] {
+            k_gather_push(G.block.data(), rank, G.world, GatherWorld::off_ids, G.off_spans, G.off_index, rank * G.slab_topics, rank * G.slab_ids, n, &G.cursor[rank]);
+        });
+    return 0;
+}
+
+// the end-of-step kernel of one rank (counts + flag to every block, bounded wait for the others' flags); returns the rank's error word
+int32_t emu_gather_finish(void* gw, uint32_t rank, uint64_t n, uint32_t new_epoch) {
+    GatherWorld& G = *static_cast<GatherWorld*>(gw);
+    if (new_epoch) G.epoch[rank]++;
+    std::vector<unsigned long long*> counts(G.world);
+    std::vector<u32*> flags(G.world);
+    for (u32 w = 0; w < G.world; ++w) { counts[w] = reinterpret_cast<unsigned long long*>(G.block[w] + G.off_counts); flags[w] = reinterpret_cast<u32*>(G.block[w] + G.off_flags); }
+    u32* my_flags = reinterpret_cast<u32*>(G.block[rank] + G.off_flags);
+    my_flags[32] = 0;                                                                 // the error word
+    emu::launch(dim3(1), dim3(32), [&] { k_gather_finish(counts.data(), flags.data(), my_flags, rank, G.world, n, &G.cursor[rank], G.epoch[rank], my_flags + 32); });
+    return static_cast<int32_t>(my_flags[32]);
+}
+
+// one rank's view of the gathered arrays (gm_gather_get + the copies Engine.gather_result makes)
+void emu_gather_read(void* gw, uint32_t rank, uint64_t* counts, uint32_t* index, gm_span* spans, uint32_t* ids) {
+    GatherWorld& G = *static_cast<GatherWorld*>(gw);
+    const char* b = G.block[rank];
+    std::memcpy(counts, b + G.off_counts, static_cast<size_t>(G.world) * 16);
+    std::memcpy(index, b + G.off_index, static_cast<size_t>(G.world) * G.slab_topics * 4);
+    std::memcpy(spans, b + G.off_spans, static_cast<size_t>(G.world) * G.slab_topics * 8);
+    std::memcpy(ids, b + GatherWorld::off_ids, static_cast<size_t>(G.world) * G.slab_ids * 4);
 }
 
 // RetainStorage::get for a batch of filters through k_tokenize -> k_retain_init -> k_retain_round x (depth + 1) -> k_retain_scan -> k_retain_expand

@@ -49,7 +49,7 @@ def _build(tmp, san: bool):
 def emu(tmp_path_factory):
     lib = C.CDLL(str(_build(tmp_path_factory.mktemp("emu"), san=False)))
     lib.emu_new.restype = C.c_void_p
-    for f in ("emu_sub_add", "emu_sub_remove", "emu_retain_set", "emu_retain_remove", "emu_match", "emu_retain_match", "emu_relations"):
+    for f in ("emu_sub_add", "emu_sub_remove", "emu_retain_set", "emu_retain_remove", "emu_match", "emu_retain_match", "emu_relations", "emu_partition"):
         getattr(lib, f).restype = C.c_int32
     return lib
 
@@ -279,7 +279,7 @@ from oracle import oracle as orc
 from rmqtt_b200.engine import pack
 lib = C.CDLL({str(so)!r})
 lib.emu_new.restype = C.c_void_p
-for f in ("emu_sub_add", "emu_sub_remove", "emu_retain_set", "emu_retain_remove", "emu_match", "emu_retain_match"):
+for f in ("emu_sub_add", "emu_sub_remove", "emu_retain_set", "emu_retain_remove", "emu_match", "emu_retain_match", "emu_relations", "emu_partition"):
     getattr(lib, f).restype = C.c_int32
 rng = random.Random(5)
 e, tree = T.Emu(lib), orc.TopicTree()
@@ -301,6 +301,12 @@ fb, fo = pack([T.rand_filter(rng, 7) for _ in range(300)] + ["#", "+/#", "+/+/+"
 res, _, _ = e.retain_match(fb, fo, cap_items=128, cap_desc=128)
 T._same(res, rt.match_batch(fb, fo))
 e.close()
+# the other entry points of the driver, through the test functions themselves
+T.test_selection_and_capacity_sized_launches(lib, 25)
+T.test_partition_kernel_equals_the_host_shard_function(lib)
+T.test_fused_gather_over_emulated_peer_memory(lib, 3, 0)
+T.test_fused_gather_over_emulated_peer_memory(lib, 3, 1)
+T.test_relation_expansion_kernel_against_a_python_model(lib)
 print("asan run ok")
 """)
     libasan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
@@ -395,3 +401,143 @@ def test_relation_expansion_kernel_against_a_python_model(emu):
         assert sorted(got) == sorted(want), t
         tot_r += cnt
     assert flagged >= 1 and int(needed[0]) == tot_r and int(needed[1]) == tot_s
+
+
+def _match_ex(e, blob, offs, sel, flags):
+    n_entries, n = len(offs) - 1, len(sel)
+    spans = np.zeros((n, 2), dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    needed = C.c_uint64(0)
+    cap = 1024
+    e.lib.emu_match_ex.restype = C.c_int32
+    while True:
+        ids = np.zeros(cap, dtype=np.uint32)
+        rc = e.lib.emu_match_ex(e.h, C.c_void_p(blob.ctypes.data), C.c_void_p(offs.ctypes.data), C.c_uint64(n_entries), C.c_void_p(sel.ctypes.data), C.c_uint64(n), None, flags,
+                                C.c_void_p(spans.ctypes.data), C.c_void_p(ids.ctypes.data), C.c_uint64(cap), C.byref(needed), C.c_void_p(status.ctypes.data), None, None)
+        if rc == -3:
+            cap = int(needed.value) + 16
+            continue
+        assert rc == 0, rc
+        return MatchResult(spans, ids[:int(needed.value)], status, int(needed.value))
+
+
+@pytest.mark.parametrize("flags", [8, 9, 16, 17, 24])
+def test_selection_and_capacity_sized_launches(emu, flags):
+    """gm_match_args.d_sel (row t = entry sel[t]: a rank's share of a mixed batch) and the small-batch-graph form (kernels launched
+    for a capacity, the real batch size read from a header; rows beyond the batch must stay untouched)."""
+    rng = random.Random(200 + flags)
+    e, tree = Emu(emu), orc.TopicTree()
+    _random_trie(e, tree, rng, 900)
+    topics = [rand_topic(rng) for _ in range(500)]
+    tb, to = pack(topics)
+    rows = np.asarray(rng.sample(range(len(topics)), 180) if flags & 8 else list(range(len(topics))), dtype=np.uint32)
+    res = _match_ex(e, tb, to, rows, flags)
+    for t, ent in enumerate(rows):
+        w = tree.matches(topics[int(ent)])
+        assert res.sorted_list(t) == (None if w is None else sorted(w)), topics[int(ent)]
+    e.close()
+
+
+def _shard_of(s, world):
+    from rmqtt_b200 import _native as N
+    b = s.encode()
+    return int(N.lib().gm_shard_of(b, len(b), world))
+
+
+def test_partition_kernel_equals_the_host_shard_function(emu):
+    rng = random.Random(31)
+    topics = [rand_topic(rng) for _ in range(1000)] + ["+", "#", "+/a", "#/x", "", "/a"]
+    tb, to = pack(topics)
+    n = len(topics)
+    for world in (1, 2, 8, 1500):                     # 1500 shards: the histogram leaves shared memory
+        for rank in (0, world - 1):
+            sel = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
+            shard = np.zeros(n, dtype=np.uint32)
+            counts = np.zeros(world + 1, dtype=np.uint32)
+            assert emu.emu_partition(C.c_void_p(tb.ctypes.data), C.c_void_p(to.ctypes.data), C.c_uint64(n), world, rank, C.c_void_p(sel.ctypes.data), C.c_void_p(shard.ctypes.data),
+                                     C.c_void_p(counts.ctypes.data)) == 0
+            want = np.asarray([0 if t.split("/")[0] in ("+", "#") else _shard_of(t, world) for t in topics], dtype=np.uint32)
+            assert (shard == want).all()
+            assert (counts[:world] == np.bincount(want, minlength=world)).all()
+            k = int(counts[world])
+            assert sorted(sel[:k].tolist()) == np.nonzero(want == rank)[0].tolist() and (sel[k:] == 0xFFFFFFFF).all()
+
+
+@pytest.mark.parametrize("world,direct", [(2, 0), (2, 1), (8, 0), (8, 1), (5, 0)])
+def test_fused_gather_over_emulated_peer_memory(emu, world, direct):
+    """The multi-GPU step with the exchange fused into the match kernels, ALL ranks emulated in this process (a peer's block is
+    just another host buffer): k_partition -> k_match_fast<GATHER> / k_match_slow<GATHER> -> k_gather_push (push form) or stores
+    into every block from the publish phase (direct form) -> k_gather_finish.  Every rank's block must then hold every topic's
+    list exactly once, equal to the unsharded oracle — at 2, 5 and 8 ranks (the 8-rank push form had no GPU run of its own)."""
+    for f in ("emu_match_gather", "emu_gather_finish"):
+        getattr(emu, f).restype = C.c_int32
+    emu.emu_gather_new.restype = C.c_void_p
+    emu.emu_gather_slab_ids.restype = C.c_uint64
+    emu.emu_gather_slab_topics.restype = C.c_uint64
+    rng = random.Random(1000 + 10 * world + direct)
+    tree = orc.TopicTree()
+    engines = [Emu(emu) for _ in range(world)]
+    for en in engines:
+        emu.emu_set_pool_rows(en.h, 2)                # some topics take the deferred kernel on every rank
+    roots = ["a", "b", "c", "d", "e", "f", "g", "h", "r1", "r2", "r3", "r4", "r5", "r6", "r7", "r8", "", "$SYS"]
+    for _ in range(2500):
+        f, v = rand_filter(rng), rng.randint(0, 30)
+        if rng.random() < 0.7:
+            f = rng.choice(roots) + "/" + f
+        try:
+            tree.insert(f, v)
+        except ValueError:
+            continue
+        s = _shard_of(f, world)
+        for r, en in enumerate(engines):
+            if s == 0xFFFFFFFF or s == r:             # root wildcards are replicated on every shard
+                assert en.add(f, v) == 0
+    for v in range(40):                               # a replicated filter with many values: > 2 + 8 matched sets for deep topics
+        tree.insert("+/#", 5000 + v)
+        for en in engines:
+            en.add("+/#", 5000 + v)
+    topics = [(rng.choice(roots) + "/" if rng.random() < 0.7 else "") + rand_topic(rng) for _ in range(1200)] + ["+/a", "#", "/".join(["a"] * 11)]
+    tb, to = pack(topics)
+    n = len(topics)
+    want = tree.match_batch(tb, to)
+    gw = C.c_void_p(emu.emu_gather_new(world, n, int(want["counts"].clip(0).sum()) + 64))
+    slab_t, slab_i = int(emu.emu_gather_slab_topics(gw)), int(emu.emu_gather_slab_ids(gw))
+    n_local = []
+    for r, en in enumerate(engines):
+        sel = np.zeros(n, dtype=np.uint32)
+        counts = np.zeros(world + 1, dtype=np.uint32)
+        emu.emu_partition(C.c_void_p(tb.ctypes.data), C.c_void_p(to.ctypes.data), C.c_uint64(n), world, r, C.c_void_p(sel.ctypes.data), None, C.c_void_p(counts.ctypes.data))
+        k = int(counts[world])
+        n_local.append(k)
+        status = np.zeros(max(k, 1), dtype=np.int32)
+        rc = emu.emu_match_gather(gw, r, en.h, C.c_void_p(tb.ctypes.data), C.c_void_p(to.ctypes.data), C.c_uint64(n), C.c_void_p(sel.ctypes.data), C.c_uint64(k), direct,
+                                  C.c_void_p(status.ctypes.data))
+        assert rc == 0, rc
+    assert sum(n_local) == n
+    # end of step: on a real node the ranks run this concurrently; here one after the other — the early ones give up waiting
+    # (bounded spin, error word set), the last one sees every flag; a second look at the same epoch then passes everywhere
+    first = [emu.emu_gather_finish(gw, r, C.c_uint64(n_local[r]), 1) for r in range(world)]
+    assert first[-1] == 0 and (world == 1 or first[0] == 1)
+    assert [emu.emu_gather_finish(gw, r, C.c_uint64(n_local[r]), 0) for r in range(world)] == [0] * world
+    wc, wi = _canon(want)
+    blocks = []
+    for r in range(world):
+        counts = np.zeros((world, 2), dtype=np.uint64)
+        index = np.zeros(world * slab_t, dtype=np.uint32)
+        spans = np.zeros((world * slab_t, 2), dtype=np.uint32)
+        ids = np.zeros(world * slab_i, dtype=np.uint32)
+        emu.emu_gather_read(gw, r, C.c_void_p(counts.ctypes.data), C.c_void_p(index.ctypes.data), C.c_void_p(spans.ctypes.data), C.c_void_p(ids.ctypes.data))
+        assert [int(c) for c in counts[:, 0]] == n_local
+        rows = np.concatenate([np.arange(q * slab_t, q * slab_t + n_local[q]) for q in range(world)])
+        idx = index[rows]
+        assert sorted(idx.tolist()) == list(range(n))                       # every topic exactly once
+        order = np.argsort(idx)
+        got = MatchResult(spans[rows][order], ids, np.where(wc < 0, -2, 0).astype(np.int32), 0)
+        cg, ig = got.canonical()
+        assert (cg == wc).all() and len(ig) == len(wi) and (ig == wi).all(), f"rank {r}"
+        blocks.append((idx, spans[rows], [int(c) for c in counts[:, 1]]))
+    for r in range(1, world):                                               # and every rank holds the same thing
+        assert (blocks[r][0] == blocks[0][0]).all() and (blocks[r][1] == blocks[0][1]).all() and blocks[r][2] == blocks[0][2]
+    emu.emu_gather_free(gw)
+    for en in engines:
+        en.close()
