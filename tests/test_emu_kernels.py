@@ -541,3 +541,48 @@ def test_fused_gather_over_emulated_peer_memory(emu, world, direct):
     emu.emu_gather_free(gw)
     for en in engines:
         en.close()
+
+
+# ---- hypothesis-driven (the strategies of tests/test_hypothesis_cpu.py): arbitrary add / remove interleavings, matched by the
+#      emulated kernels — the CPU twin of tests/test_gpu_hypothesis.py ------------------------------------------------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st          # noqa: E402
+
+from test_hypothesis_cpu import ops as hyp_ops, path as hyp_path, retain_ops as hyp_retain_ops   # noqa: E402
+
+_HYP = dict(deadline=None, max_examples=40, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+
+
+@settings(**_HYP)
+@given(ops=hyp_ops, topics=st.lists(hyp_path, min_size=1, max_size=30), flags=st.sampled_from([0, 1, 2]))
+def test_hypothesis_subscription_trie_emulated_kernels_vs_oracle(emu, ops, topics, flags):
+    e, tree = Emu(emu), orc.TopicTree()
+    for op, f, v in ops:
+        rc = e.add(f, v) if op == "add" else e.remove(f, v)
+        if rc != 0:
+            continue
+        tree.insert(f, v) if op == "add" else tree.remove(f, v)
+    tb, to = pack(topics)
+    res, _, _ = e.match(tb, to, flags)
+    for i, t in enumerate(topics):
+        assert res.sorted_list(i) == tree.matches(t), t
+    e.close()
+
+
+@settings(**_HYP)
+@given(ops=hyp_retain_ops, filters=st.lists(hyp_path, min_size=1, max_size=30))
+def test_hypothesis_retained_tree_emulated_kernels_vs_oracle(emu, ops, filters):
+    e, tree = Emu(emu), orc.RetainTree()
+    fb0, fo0 = pack(["#"])
+    for op, t, v in ops:
+        if op == "flush":                            # make the image current (later operations edit it in place)
+            e.retain_match(fb0, fo0)
+            continue
+        rc = e.retain_set(t, v) if op == "set" else e.retain_remove(t)
+        if rc != 0:
+            continue
+        tree.insert(t, v) if op == "set" else tree.remove(t)
+    fb, fo = pack(filters)
+    res, _, _ = e.retain_match(fb, fo)
+    for i, f in enumerate(filters):
+        assert res.sorted_list(i) == tree.matches(f), f
+    e.close()
