@@ -80,6 +80,16 @@ int32_t emu_retain_remove(void* h, const char* t, uint32_t len) {
     return static_cast<EmuEngine*>(h)->rtree.remove(t, len, &had, &old);
 }
 
+// gm_bulk_load / gm_retain_bulk_load: the all-host-threads builds (host_trie.cpp insert_batch_parallel, retain_tree.cpp set_batch_build)
+uint64_t emu_bulk_load(void* h, const char* blob, const uint32_t* offs, const uint32_t* vals, uint64_t n) {
+    EmuEngine& e = *static_cast<EmuEngine*>(h);
+    e.trie.reserve(n);
+    return e.trie.insert_batch(blob, offs, vals, n);
+}
+uint64_t emu_retain_bulk_load(void* h, const char* blob, const uint32_t* offs, const uint32_t* vals, uint64_t n) {
+    return static_cast<EmuEngine*>(h)->rtree.set_batch(blob, offs, vals, n);
+}
+
 // Router::matches for a batch through k_tokenize -> k_bucket_scan -> k_bucket_scatter -> k_match_fast -> k_match_slow.
 // flags: bit 0 descriptor mode (the descriptors are expanded here from the host mirror, so `out_ids` holds ids either way),
 //        bit 1 the bulk-staged tokeniser, bit 2 the instrumented (STATS) instantiations; work[4] = V, E, F, M then.

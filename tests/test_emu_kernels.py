@@ -586,3 +586,33 @@ def test_hypothesis_retained_tree_emulated_kernels_vs_oracle(emu, ops, filters):
     for i, f in enumerate(filters):
         assert res.sorted_list(i) == tree.matches(f), f
     e.close()
+
+
+def test_workload_generator_shapes_on_parallel_built_tables(emu):
+    """C3- and C4-shaped data from the workload generator (64-way fan-out at the top: wide nodes with the child filter, several
+    windows of the edge table, the locality sort with populated buckets), the tables built by the all-host-threads bulk paths —
+    the emulated kernels against the oracle, exact work counters included."""
+    from rmqtt_b200 import workload as wl
+    emu.emu_bulk_load.restype = C.c_uint64
+    emu.emu_retain_bulk_load.restype = C.c_uint64
+    cfg = wl.C3.scaled(n_subs=300_000, n_topics=8_000)
+    sb, so, sv = wl.gen_subs(cfg)
+    tb, to = wl.gen_topics(cfg)
+    e, tree = Emu(emu), orc.TopicTree()
+    assert emu.emu_bulk_load(e.h, C.c_void_p(sb.ctypes.data), C.c_void_p(so.ctypes.data), C.c_void_p(sv.ctypes.data), C.c_uint64(len(sv))) == len(sv)
+    tree.bulk_insert(sb, so, sv, nthreads=4)
+    want = tree.match_batch(tb, to, nthreads=4)
+    for flags in (4, 1):
+        res, work, _ = e.match(tb, to, flags)
+        _same(res, want)
+        if flags & 4:
+            c = want["counters"]
+            assert [int(x) for x in work] == [c["V"], c["E"], c["F"], c["M"]]
+    rcfg = wl.C4.scaled(n_subs=200_000, n_topics=1_000)
+    rb, ro, rv = wl.gen_retained(rcfg)
+    fb, fo = wl.gen_retain_filters(rcfg)
+    rt = orc.RetainTree()
+    assert emu.emu_retain_bulk_load(e.h, C.c_void_p(rb.ctypes.data), C.c_void_p(ro.ctypes.data), C.c_void_p(rv.ctypes.data), C.c_uint64(len(rv))) == rt.bulk_insert(rb, ro, rv)
+    res, _, _ = e.retain_match(fb, fo)
+    _same(res, rt.match_batch(fb, fo, nthreads=4))
+    e.close()
