@@ -214,7 +214,6 @@ int32_t gm_batcher_probe(gm_engine* e, const char* blob, const uint32_t* offsets
     if (rc != GM_OK) return rc;
     // warm-up round (graph capture, scratch allocation) — not measured
     {
-        std::vector<Clock::time_point> keep = p.t_submit;
         for (uint32_t i = 0; i < burst; ++i) { const uint64_t t = i % n; p.t_submit[i] = Clock::now(); gm_submit(b, blob + offsets[t], offsets[t + 1] - offsets[t], i); }
         gm_batcher_drain(b);
         p.done.store(0); p.ids.store(0);

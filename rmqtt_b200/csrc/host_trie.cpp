@@ -413,8 +413,8 @@ int HostTrie::insert(const char* filter, u32 len, u32 value, bool* changed, u32 
 // result as n calls of insert(), but walked LEVEL-SYNCHRONOUSLY in groups of 64 filters so that the dependent
 // random probes of the multi-GB edge table overlap: pass 1 of a level prefetches every filter's first probe slot,
 // pass 2 resolves them in order (creating nodes exactly as the one-by-one path would).
-u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* values, u64 n) {
-    if (n >= host_par_min(1u << 16) && host_threads() > 1 && !getenv("GM_BULK_SERIAL")) return insert_batch_parallel(blob, offsets, values, n, host_threads());
+u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* vals, u64 n) {
+    if (n >= host_par_min(1u << 16) && host_threads() > 1 && !getenv("GM_BULK_SERIAL")) return insert_batch_parallel(blob, offsets, vals, n, host_threads());
     constexpr u32 G = 64;
     u64 changed = 0;
     const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
@@ -464,7 +464,7 @@ u64 HostTrie::insert_batch(const char* blob, const u32* offsets, const u32* valu
         }
         max_depth = std::max<u32>(max_depth, deepest);
         double tc = prof ? now() : 0;
-        for (u32 j = 0; j < m; ++j) changed += add_value(node[j], values[idx[j]]) ? 1 : 0;
+        for (u32 j = 0; j < m; ++j) changed += add_value(node[j], vals[idx[j]]) ? 1 : 0;
         if (prof) { const double td = now(); t_parse += tb - ta; t_walk += tc - tb; t_val += td - tc; }
     }
     if (prof) fprintf(stderr, "insert_batch: %llu filters: parse+intern %.2f s, edge walk %.2f s, values %.2f s\n", (unsigned long long)n, t_parse, t_walk, t_val);
@@ -681,7 +681,7 @@ void HostTrie::tokenize_batch(const char* blob, const u32* offsets, u64 n, unsig
 }
 
 
-u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const u32* values, u64 n, unsigned T) {
+u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const u32* vals, u64 n, unsigned T) {
     const bool prof = getenv("GM_BULK_PROFILE") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
@@ -911,7 +911,7 @@ u64 HostTrie::insert_batch_parallel(const char* blob, const u32* offsets, const 
                 const u32 node = cur[i];
                 if ((node >> 6) % T != tid) continue;
                 HNode& nd = nodes_[node];
-                const u32 value = values[i];
+                const u32 value = vals[i];
                 bool c = false;
                 if (nd.nvals == 0) { nd.v0 = value; nd.nvals = 1; c = true; }
                 else {
