@@ -91,10 +91,10 @@ class HostTrie {
     u32 nwin_mask() const { return (1u << nwin_log2) - 1u; }
 
     // ---- dirty tracking (consumed and cleared by the engine's flush) ---------------------------
-    std::vector<u32> dirty_edges, dirty_ranges, dirty_dict;
+    std::vector<u32> dirty_edges, dirty_dict;       // (`ranges` / `values` / `pool` are append-only between compactions: shipped as tails)
     bool full_edges = true, full_dict = true;   // table re-hashed / never uploaded: ship whole table
     bool any_dirty() const { return !dirty_nodes_.empty() || !dirty_edges.empty() ||
-                                    !dirty_ranges.empty() || !dirty_dict.empty() || full_edges || full_dict || root_dirty || cfilter_dirty || trees_dirty ||
+                                    !dirty_dict.empty() || full_edges || full_dict || root_dirty || cfilter_dirty || trees_dirty ||
                                     cfilter_rebuild_; }
     bool root_dirty = true;
     u64 garbage_values = 0;

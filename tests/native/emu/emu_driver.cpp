@@ -26,13 +26,94 @@ struct Ctrl { unsigned long long cursor; unsigned long long stats[24]; u32 slow_
 constexpr int K2_FAST_L = 8, K2_THREADS = 512, K2_CTAS_PER_SM = 3;
 constexpr u32 EMU_SMS = 2;               // the emulated part has two SMs: several CTAs per kernel, dynamic tile hand-out exercised
 
+// A "device copy" of one table, maintained ONLY by what gm_engine::flush_impl would ship (engine.cu upload_table /
+// upload_appendable / stage_patches): whole arrays after a re-hash or for the first shipment, appended tails, and the slots the
+// host mirror listed as dirty.  A slot the mirror changed without listing it stays stale here — and shows up as a wrong match.
+template <class T> struct ImgBuf {
+    std::vector<T> v;                    // v.size() plays the role of DevBuf::cap (elements)
+    size_t up = 0;                       // shipped up to here (appendable arrays) / shipped size (tables)
+    bool have = false;
+    template <class H> void fresh(const H& host, size_t min_elems) {
+        v.assign(std::max(std::max(host.size(), min_elems), size_t(8)), T{});
+        std::memset(static_cast<void*>(v.data()), 0xCD, v.size() * sizeof(T));          // never-shipped bytes are garbage on a device
+        if (host.size()) std::memcpy(static_cast<void*>(v.data()), host.data(), host.size() * sizeof(T));
+        up = host.size(); have = true;
+    }
+    template <class H> void patch(const H& host, std::vector<u32>& dirty) {
+        for (u32 i : dirty) v[i] = host[i];
+        dirty.clear();
+    }
+    template <class H> void table(const H& host, bool& full, std::vector<u32>& dirty) {       // engine.cu upload_table
+        if (full || !have || up != host.size() || dirty.size() * 8 > host.size()) { fresh(host, 0); dirty.clear(); }
+        else patch(host, dirty);
+        full = false;
+    }
+    template <class H> void appendable(const H& host, std::vector<u32>* dirty) {              // engine.cu upload_appendable
+        if ((up == 0 && (host.size() > 0 || !have)) || host.size() > v.size()) { fresh(host, std::max(host.size() * 2, size_t(1024))); if (dirty) dirty->clear(); return; }
+        const size_t before = up;
+        if (host.size() > up) { std::memcpy(static_cast<void*>(v.data() + up), host.data() + up, (host.size() - up) * sizeof(T)); up = host.size(); }
+        if (dirty) {
+            dirty->erase(std::remove_if(dirty->begin(), dirty->end(), [&](u32 i) { return i >= before; }), dirty->end());
+            patch(host, *dirty);
+        }
+    }
+};
+
 struct EmuEngine {
     HostTrie trie{128};
     RetainTreeHost rtree{&trie};
     u32 pool_rows = 24;                  // engine.cu K2_POOL_ROWS (tests lower it to push topics onto the deferred kernel)
     u32 site_bits = 10;
+    // optional device image (emu_use_image): the kernels then read copies that only flush() updates
+    bool image = false, manual_flush = false;
+    ImgBuf<EdgeSlot> i_edges; ImgBuf<DictSlot> i_dict; ImgBuf<Range> i_ranges; ImgBuf<u32> i_values, i_cfilter, i_tree_slots, i_rvals; ImgBuf<u8> i_pool;
+    ImgBuf<RKid> i_rkids; ImgBuf<REdge> i_redges;
+    u64 up_values_epoch = 0;
+    TrieView dev_view{}; RetainView dev_rview{};
+    u64 flushes = 0;
 
-    TrieView view() {                    // engine.cu gm_engine::view(), host pointers instead of device pointers
+    bool flush() {                       // engine.cu gm_engine::flush_impl, shipping policy only
+        if (!trie.any_dirty() && !rtree.dirty && flushes) return true;
+        if (!trie.sync()) return false;
+        if (trie.values_epoch != up_values_epoch) { i_values.up = i_ranges.up = 0; up_values_epoch = trie.values_epoch; }
+        if (rtree.dirty || !flushes) {
+            rtree.prepare_flush();
+            if (rtree.full || !i_rkids.have) { i_rkids.fresh(rtree.rkids, rtree.rkids.size() + rtree.rkids.size() / 4 + 1024); i_redges.fresh(rtree.redges, 0); i_rvals.fresh(rtree.rvals, rtree.rvals.size() + 1024); }
+            else {
+                bool full_edges = false;
+                i_rkids.appendable(rtree.rkids, &rtree.dirty_kids);
+                i_redges.table(rtree.redges, full_edges, rtree.dirty_edges);
+                i_rvals.appendable(rtree.rvals, &rtree.dirty_vals);
+            }
+            rtree.shipped();
+        }
+        i_edges.table(trie.edges, trie.full_edges, trie.dirty_edges);
+        i_dict.table(trie.dict, trie.full_dict, trie.dirty_dict);
+        i_ranges.appendable(trie.ranges, nullptr);
+        i_values.appendable(trie.values, nullptr);
+        i_pool.appendable(trie.pool, nullptr);
+        if (trie.cfilter_dirty || !i_cfilter.have) { i_cfilter.fresh(trie.cfilter, 0); trie.cfilter_dirty = false; }
+        if (trie.trees_dirty || !i_tree_slots.have) { i_tree_slots.fresh(trie.tree_slots, 0); trie.trees_dirty = false; }
+        trie.root_dirty = false;
+        dev_view = host_view();
+        dev_view.edges = i_edges.v.data(); dev_view.ranges = i_ranges.v.data(); dev_view.values = i_values.v.data(); dev_view.dict = i_dict.v.data();
+        dev_view.pool = i_pool.v.data(); dev_view.cfilter = i_cfilter.v.data(); dev_view.tree_slots = i_tree_slots.v.data();
+        dev_rview = host_rview();
+        dev_rview.kids = i_rkids.v.data(); dev_rview.edges = i_redges.v.data(); dev_rview.vals = i_rvals.v.data();
+        flushes++;
+        return true;
+    }
+    // what a match sees: the live host arrays, or — with the device image — the copies as of the last flush (auto-flush engines
+    // flush before every match, GM_FLAG_MANUAL_FLUSH ones only when told to)
+    bool prepare(bool retained) {
+        if (!image) { if (!trie.sync()) return false; if (retained) { rtree.prepare_flush(); rtree.shipped(); } return true; }
+        if (!manual_flush || !flushes) return flush();
+        return true;
+    }
+    TrieView view() { return image ? dev_view : host_view(); }
+    RetainView rview() { return image ? dev_rview : host_rview(); }
+
+    TrieView host_view() {               // engine.cu gm_engine::view(), host pointers instead of device pointers
         TrieView v{};
         v.edges = trie.edges.data(); v.ranges = trie.ranges.data(); v.values = trie.values.data(); v.dict = trie.dict.data(); v.pool = trie.pool.data();
         v.cfilter = trie.cfilter.data(); v.cfilter_mask = static_cast<u32>(trie.cfilter.size() - 1);
@@ -44,7 +125,7 @@ struct EmuEngine {
         v.tree_slots = trie.tree_slots.data(); v.n_trees = static_cast<u32>(trie.tree_slots.size());
         return v;
     }
-    RetainView rview() {                 // engine.cu gm_engine::rview()
+    RetainView host_rview() {            // engine.cu gm_engine::rview()
         RetainView v{};
         v.kids = rtree.rkids.data(); v.edges = rtree.redges.data(); v.vals = rtree.rvals.data();
         v.edge_mask = static_cast<u32>(rtree.redges.size() - 1);
@@ -62,6 +143,20 @@ extern "C" {
 void* emu_new() { return new EmuEngine(); }
 void emu_free(void* h) { delete static_cast<EmuEngine*>(h); }
 void emu_set_pool_rows(void* h, uint32_t rows) { static_cast<EmuEngine*>(h)->pool_rows = rows; }
+// the kernels read a device IMAGE that only flushes update (manual != 0: only emu_flush, like GM_FLAG_MANUAL_FLUSH)
+void emu_use_image(void* h, uint32_t manual) { EmuEngine* e = static_cast<EmuEngine*>(h); e->image = true; e->manual_flush = manual != 0; }
+void emu_retain_counters(void* h, uint64_t* out6) { uint64_t o[6]; static_cast<EmuEngine*>(h)->rtree.debug_stats(o); std::memcpy(out6, o, sizeof(o)); }   // {full rebuilds, in-place patches, ...}
+int32_t emu_flush(void* h) { return static_cast<EmuEngine*>(h)->flush() ? 0 : -7; }
+int32_t emu_compact(void* h) {           // gm_compact: dictionary + value compaction, the retained tree re-labelled
+    EmuEngine* e = static_cast<EmuEngine*>(h);
+    const std::vector<u32> keep = e->rtree.used_tokens();
+    std::vector<u32> remap;
+    e->trie.compact(&keep, &remap);
+    e->rtree.remap_tokens(remap);
+    e->i_ranges.up = e->i_values.up = e->i_pool.up = 0; e->up_values_epoch = e->trie.values_epoch;
+    e->i_edges.have = e->i_dict.have = false;
+    return 0;
+}
 
 int32_t emu_sub_add(void* h, const char* f, uint32_t len, uint32_t value, uint32_t tree) {
     bool ch = false;
@@ -105,7 +200,7 @@ int32_t emu_match_ex(void* h, const char* blob_in, const uint32_t* offs, uint64_
     const u32 n_real = static_cast<u32>(n64);
     *needed = 0;
     if (n_real == 0) return 0;
-    if (!e.trie.sync()) return -7;
+    if (!e.prepare(false)) return -7;
     const TrieView tv = e.view();
     const u32 blob_bytes = offs[n_entries];
     const u32 n = graph_form ? n_real + 37u : n_real;            // launch size (rows beyond the real batch must stay untouched)
@@ -268,7 +363,7 @@ int32_t emu_match_gather(void* gw, uint32_t rank, void* h, const char* blob_in, 
     if (n > G.slab_topics) return -3;
     G.cursor[rank] = 0;
     if (n) {
-        if (!e.trie.sync()) return -7;
+        if (!e.prepare(false)) return -7;
         const TrieView tv = e.view();
         const u32 blob_bytes = offs[n_entries];
         const size_t readable = (static_cast<size_t>(blob_bytes) + 15) & ~size_t(15);
@@ -356,9 +451,7 @@ int32_t emu_retain_match(void* h, const char* blob_in, const uint32_t* offs, uin
     const u32 nq = static_cast<u32>(n64);
     *needed = 0;
     if (nq == 0) return 0;
-    if (!e.trie.sync()) return -7;
-    e.rtree.prepare_flush();
-    e.rtree.shipped();
+    if (!e.prepare(true)) return -7;
     const TrieView tv = e.view();
     const RetainView rv = e.rview();
     const u32 depth = rv.max_depth, S = depth + 2;

@@ -616,3 +616,96 @@ def test_workload_generator_shapes_on_parallel_built_tables(emu):
     res, _, _ = e.retain_match(fb, fo)
     _same(res, rt.match_batch(fb, fo, nthreads=4))
     e.close()
+
+
+@pytest.mark.parametrize("seed,tiny", [(41, False), (42, True), (43, False)])
+def test_device_image_is_kept_current_by_the_dirty_lists_alone(emu, seed, tiny, monkeypatch):
+    """The kernels read a COPY of every table that only the shipping policy of gm_engine::flush_impl updates (whole table after a
+    re-hash, appended tails, the 32-byte slots the host mirror listed as dirty — tests/native/emu/emu_driver.cpp ImgBuf).  A slot
+    the mirror changed without listing it would stay stale in the copy and show up as a wrong match.  Rounds of single
+    add / remove, a bulk load in between (tables re-hashed), a compaction; subscription trie and retained tree."""
+    if tiny:
+        monkeypatch.setenv("GM_WIN_MIN_SLOTS_LOG2", "3")
+    rng = random.Random(seed)
+    for f in ("emu_flush", "emu_compact"):
+        getattr(emu, f).restype = C.c_int32
+    emu.emu_bulk_load.restype = C.c_uint64
+    e, tree, rt = Emu(emu), orc.TopicTree(), orc.RetainTree()
+    emu.emu_use_image(e.h, 0)
+    live, names, hist = [], [], []
+    for rnd in range(7):
+        for _ in range(400):
+            r = rng.random()
+            if r < 0.45 or not live:
+                f, v = rand_filter(rng), rng.randint(0, 30)
+                if e.add(f, v) == 0:
+                    tree.insert(f, v); live.append((f, v))
+            elif r < 0.7:
+                f, v = live.pop(rng.randrange(len(live)))
+                assert e.remove(f, v) == 0
+                tree.remove(f, v)
+            elif r < 0.9 or not names:
+                # (plain levels except in round 5: a stored literal '+' / '#' level makes the host give the in-place image up
+                #  and re-flatten — shipped whole — which would hide the patch path this test is about)
+                t = rand_topic(rng, max_depth=6) if rnd == 5 else "/".join(rng.choice(["a", "b", "c", "d", "", "x" * 30, "$SYS"]) for _ in range(rng.randint(1, 5)))
+                v = rng.randint(0, 10**6)
+                if e.retain_set(t, v) == 0:
+                    rt.insert(t, v); names.append(t)
+            else:
+                t = names.pop(rng.randrange(len(names)))
+                e.retain_remove(t); rt.remove(t)
+        if rnd == 2:                                   # a bulk load through the all-threads path: edge table re-hashed, shipped whole
+            monkeypatch.setenv("GM_HOST_PAR_MIN", "1"); monkeypatch.setenv("GM_HOST_THREADS", "4")
+            fs = [rand_filter(rng) for _ in range(3000)]
+            ok = []
+            for f in fs:
+                try:
+                    tree.insert(f, 77); ok.append(f)
+                except ValueError:
+                    pass
+            fb, fo = pack(fs)
+            assert emu.emu_bulk_load(e.h, C.c_void_p(fb.ctypes.data), C.c_void_p(fo.ctypes.data), C.c_void_p(np.full(len(fs), 77, np.uint32).ctypes.data), C.c_uint64(len(fs))) >= 1
+            live += [(f, 77) for f in set(ok)]
+            monkeypatch.delenv("GM_HOST_PAR_MIN"); monkeypatch.delenv("GM_HOST_THREADS")
+        if rnd == 4:
+            assert emu.emu_compact(e.h) == 0
+        topics = [rand_topic(rng) for _ in range(300)]
+        tb, to = pack(topics)
+        res, _, _ = e.match(tb, to, rnd % 2)           # ids and descriptor mode alternate
+        _same(res, tree.match_batch(tb, to))
+        filters = [rand_filter(rng, 6) for _ in range(150)] + ["#", "+/#"]
+        qb, qo = pack(filters)
+        rres, _, _ = e.retain_match(qb, qo)
+        _same(rres, rt.match_batch(qb, qo))
+        ctr = np.zeros(6, dtype=np.uint64)
+        emu.emu_retain_counters(e.h, C.c_void_p(ctr.ctypes.data))
+        hist.append((int(ctr[0]), int(ctr[1])))
+    # some round of plain topics edited the shipped image in place without a re-flatten (re-packs happen too: garbage, the compaction)
+    assert any(b[0] == a[0] and b[1] > a[1] for a, b in zip(hist, hist[1:])), hist
+    e.close()
+
+
+def test_manual_flush_engines_match_the_last_shipped_snapshot(emu):
+    """GM_FLAG_MANUAL_FLUSH: between fences the kernels keep matching the tables as of the last flush, whatever the host mirror has
+    become meanwhile (new filters, a table that grew and re-hashed)."""
+    emu.emu_flush.restype = C.c_int32
+    rng = random.Random(7)
+    e, tree = Emu(emu), orc.TopicTree()
+    emu.emu_use_image(e.h, 1)
+    _random_trie(e, tree, rng, 600)
+    topics = [rand_topic(rng) for _ in range(300)]
+    tb, to = pack(topics)
+    res, _, _ = e.match(tb, to, 0)                     # (first match ships the tables)
+    before = tree.match_batch(tb, to)
+    _same(res, before)
+    for f, v in [(rand_filter(rng), rng.randint(0, 9)) for _ in range(5000)]:      # enough to grow and re-hash the edge table
+        if e.add(f, v) == 0:
+            tree.insert(f, v)
+    res, _, _ = e.match(tb, to, 0)
+    _same(res, before)                                 # not flushed: the old snapshot answers
+    assert emu.emu_flush(e.h) == 0
+    res, _, _ = e.match(tb, to, 0)
+    after = tree.match_batch(tb, to)
+    assert int(after["counts"].clip(0).sum()) > int(before["counts"].clip(0).sum())
+    _same(res, after)
+    e.close()
