@@ -709,3 +709,77 @@ def test_manual_flush_engines_match_the_last_shipped_snapshot(emu):
     assert int(after["counts"].clip(0).sum()) > int(before["counts"].clip(0).sum())
     _same(res, after)
     e.close()
+
+
+# ---- the reference's own unit-test vectors (tests/golden/reference_asserts.json: trie.rs:417-498, retain.rs:451-475 and the derived
+#      `$` / literal-wildcard cases) replayed through the emulated kernels --------------------------------------------------------------
+def _emu_matches(e, topic, flags=0):
+    tb, to = pack([topic])
+    res, _, _ = e.match(tb, to, flags)
+    return res.sorted_list(0)
+
+
+def _emu_retain_matches(e, filt):
+    fb, fo = pack([filt])
+    res, _, _ = e.retain_match(fb, fo)
+    return res.sorted_list(0)
+
+
+def test_golden_trie_vectors_through_the_emulated_kernels(emu, golden):
+    g = golden["trie_A1"]
+    e = Emu(emu)
+    for f, v in g["inserts"]:
+        assert e.add(f, v) == 0
+    for topic, want in g["matches"]:
+        assert _emu_matches(e, topic) == sorted(want), topic
+    for topic, bad in g["not_matches"]:
+        assert _emu_matches(e, topic) != sorted(bad)
+    for f, v, _want in g["removes"]:
+        e.remove(f, v)
+    for topic, want in g["after_remove_matches"]:
+        assert _emu_matches(e, topic, 1) == sorted(want), topic
+    e.close()
+    g = golden["trie_A2"]
+    e = Emu(emu)
+    for f, v in g["inserts"]:
+        e.add(f, v)
+    r = g["range_inserts"]
+    for v in range(r["lo"], r["hi"]):
+        e.add(r["pattern_each"].format(v=v), v)
+    for v in range(r["lo"], r["hi"]):
+        e.add(r["pattern_same"], v)
+    for topic, want in g["matches"]:
+        assert _emu_matches(e, topic) == sorted(want), topic
+    assert _emu_matches(e, "/iot/x") == sorted(list(range(1, 10000)) + [3])      # 10 000 ids in one set
+    for f, v in g["stage2_inserts"]:
+        e.add(f, v)
+    for topic, want in g["stage2_matches"]:
+        assert _emu_matches(e, topic) == sorted(want), topic
+    for f, v in g["stage3_inserts"]:
+        e.add(f, v)
+    for topic, want in g["stage3_matches"]:
+        assert _emu_matches(e, topic) == sorted(want), topic                     # the same id under two filters is reported twice
+    e.close()
+    g = golden["derived_A5"]["trie"]
+    e = Emu(emu)
+    for f, v in g["inserts"]:
+        e.add(f, v)
+    for topic, want in g["matches"]:
+        assert _emu_matches(e, topic) == sorted(want), topic
+    e.close()
+
+
+def test_golden_retain_vectors_through_the_emulated_kernels(emu, golden):
+    g = golden["retain_A3"]
+    e = Emu(emu)
+    for topic, v in g["inserts"]:
+        assert e.retain_set(topic, v & 0xFFFFFFFF) == 0
+    for f, want in g["matches"]:
+        assert _emu_retain_matches(e, f) == sorted(w & 0xFFFFFFFF for w in want), f
+    for f, bad in g["not_matches"]:
+        assert _emu_retain_matches(e, f) != sorted(bad)
+    for topic, v in g["more_inserts"]:
+        e.retain_set(topic, v & 0xFFFFFFFF)
+    for f, want in g["more_matches"] + golden["derived_A5"]["retain_on_A3"]:
+        assert _emu_retain_matches(e, f) == sorted(w & 0xFFFFFFFF for w in want), f
+    e.close()
