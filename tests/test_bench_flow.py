@@ -205,6 +205,8 @@ def test_run_own_walks_every_leg_and_isolates_the_failing_ones(fake_gpu):
     assert d["value"] > 0 and d["gpu_launches"] == 15
     for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step", "ids_mode", "single_caller"):
         assert k in d["e2e"], k
+    assert set(d["e2e"]["by_caller_threads"]) == {"2", "3"} and d["e2e"]["value"] == max(d["e2e"]["by_caller_threads"].values())
+    assert d["e2e"]["caller_threads"] in (2, 3)
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["kernel"] == "k_match_fast" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert abs(r["descriptor_mode"]["frac"] - r["descriptor_mode"]["achieved"] / r["peak"]) < 1e-12
