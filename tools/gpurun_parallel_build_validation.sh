@@ -1,3 +1,4 @@
+# The command list of the last gpurun call of round 2 (validation of the parallel host builds on the GPU box): kept for the record.
 mkdir -p gpurun_out
 nproc > gpurun_out/r2_hostbuild_box.txt; lscpu | grep -i "model name\|socket\|numa node(s)" >> gpurun_out/r2_hostbuild_box.txt
 GM_BULK_PROFILE=1 timeout 220 python -m pytest tests/test_gpu_fullsize.py -x -q -s --durations=5 > gpurun_out/r2_pytest_fullsize_parallel_build.txt 2>&1; echo "pytest exit $?" >> gpurun_out/r2_pytest_fullsize_parallel_build.txt
