@@ -551,15 +551,20 @@ def run_own(args):
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None
     traffic, traffic_src = None, "not measured in this run (ncu cannot run inside the timed bench)"
     prof = ROOT / "profiles" / "k_match_fast_traffic.json"      # written next to the committed ncu report it was read from
+    traffic_same_build = None
     if prof.exists():
         try:
             pj = json.loads(prof.read_text())
             traffic, traffic_src = pj.get("dram_bytes_per_launch"), pj.get("source")
+            if rank == 0 and pj.get("library_sass_md5"):        # is the library that just ran the one that was profiled?  (machine code, not timestamps)
+                import hashlib
+                sass = subprocess.run(["cuobjdump", "-sass", str(ROOT / "rmqtt_b200" / "libgpumqtt.so")], capture_output=True, timeout=120).stdout
+                traffic_same_build = bool(sass) and hashlib.md5(sass).hexdigest() == pj["library_sass_md5"]
         except Exception:
             pass
     kd = kms_desc.mean(axis=0) if len(kms_desc) else np.zeros(3)
     roofline = {"bound": "hbm", "kernel": "k_match_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "traffic_same_machine_code": traffic_same_build, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k2_bytes, "kernel_ms": {"k_tokenize+k_bucket_scan+k_bucket_scatter": float(k_mean[0]), "k_match_fast": k2_ms, "k_match_slow": float(k_mean[2])},
                 "pipeline": {"algorithmic_bytes_per_step": k1_bytes + k2_bytes,
                              "achieved": (k1_bytes + k2_bytes) / (float(k_mean.sum()) * 1e-3) / 1e9 if k_mean.sum() > 0 else None,
