@@ -549,7 +549,9 @@ from hypothesis import HealthCheck, given, settings, strategies as st          #
 
 from test_hypothesis_cpu import ops as hyp_ops, path as hyp_path, retain_ops as hyp_retain_ops   # noqa: E402
 
-_HYP = dict(deadline=None, max_examples=40, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+import os as _os                                                                  # noqa: E402
+
+_HYP = dict(deadline=None, max_examples=int(_os.environ.get("GM_HYP_EMU_EXAMPLES", "40")), suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 
 
 @settings(**_HYP)
