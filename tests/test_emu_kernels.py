@@ -785,3 +785,46 @@ def test_golden_retain_vectors_through_the_emulated_kernels(emu, golden):
     for f, want in g["more_matches"] + golden["derived_A5"]["retain_on_A3"]:
         assert _emu_retain_matches(e, f) == sorted(w & 0xFFFFFFFF for w in want), f
     e.close()
+
+
+def test_value_set_size_boundary_wide_nodes_tiny_windows_and_an_empty_spill_pool(emu, monkeypatch):
+    """Edges of the layout: a value set of 65534 members is the largest that stays in-line for the fast kernel, 65535 goes through
+    the `ranges` indirection on the deferred kernel; nodes with more than 48 children (child filter) in 8-slot windows (linear
+    probing wraps, windows overflow and the table re-hashes); no spill rows for matched sets (the 9th set defers the topic)."""
+    emu.emu_bulk_load.restype = C.c_uint64
+    for nset, want_deferred in ((65534, 0), (65535, 3)):
+        e, tree = Emu(emu), orc.TopicTree()
+        fb, fo = pack(["big/+", "big/#"] * nset)
+        vals = np.repeat(np.arange(nset, dtype=np.uint32), 2)
+        assert emu.emu_bulk_load(e.h, C.c_void_p(fb.ctypes.data), C.c_void_p(fo.ctypes.data), C.c_void_p(vals.ctypes.data), C.c_uint64(len(vals))) == len(vals)
+        tree.bulk_insert(fb, fo, vals)
+        e.add("big/x", 7); tree.insert("big/x", 7)
+        tb, to = pack(["big/x", "big", "big/x/y", "small"])
+        for flags in (0, 1, 5):
+            res, work, deferred = e.match(tb, to, flags)
+            want = tree.match_batch(tb, to)
+            _same(res, want)
+            assert deferred == want_deferred
+            if flags & 4:
+                c = want["counters"]
+                assert [int(x) for x in work] == [c["V"], c["E"], c["F"], c["M"]]
+        e.close()
+    monkeypatch.setenv("GM_WIN_MIN_SLOTS_LOG2", "3")
+    rng = random.Random(3)
+    e, tree = Emu(emu), orc.TopicTree()
+    emu.emu_set_pool_rows(e.h, 0)
+    for _ in range(3000):
+        f = f"w/{rng.randrange(200)}/{rng.choice(['+', 'a', 'b', '#'])}" if rng.random() < 0.7 else f"{rng.randrange(120)}/x/{rng.randrange(5)}"
+        v = rng.randrange(50)
+        tree.insert(f, v)
+        assert e.add(f, v) == 0
+    for v in range(12):
+        for f in ("#", "+/#", "w/#", "w/+/#", "w/+/+", "+/+/+", "+/+/#", "w/+/a", "+/5/+", "w/5/#"):
+            tree.insert(f, 1000 + v); e.add(f, 1000 + v)
+    topics = [f"w/{rng.randrange(220)}/{rng.choice(['a', 'b', 'c'])}" for _ in range(1200)] + [f"{rng.randrange(130)}/x/{rng.randrange(6)}" for _ in range(400)]
+    tb, to = pack(topics)
+    for flags in (0, 1, 2):
+        res, _, deferred = e.match(tb, to, flags)
+        _same(res, tree.match_batch(tb, to))
+        assert deferred > 500                     # more than 8 matched sets and nowhere to spill them
+    e.close()
