@@ -828,3 +828,39 @@ def test_value_set_size_boundary_wide_nodes_tiny_windows_and_an_empty_spill_pool
         _same(res, tree.match_batch(tb, to))
         assert deferred > 500                     # more than 8 matched sets and nowhere to spill them
     e.close()
+
+
+def test_retained_lookup_beyond_the_eight_level_token_row(emu):
+    """Retained topics and filters of up to 14 levels (levels >= 8 live in the level-major token array), literal '+' / '#' levels
+    that shadow wildcard expansion, `$` roots, removals — scratch starting small."""
+    rng = random.Random(8)
+    e, rt = Emu(emu), orc.RetainTree()
+
+    def deep_topic():
+        lv = [rng.choice(["a", "b", "c", "", "dd"]) if rng.random() < 0.93 else rng.choice(["+", "#"]) for _ in range(rng.randint(1, 14))]
+        if rng.random() < 0.1:
+            lv[0] = "$x"
+        return "/".join(lv)
+
+    def deep_filter():
+        lv = [rng.choice(["a", "b", "c", "", "dd", "+", "+"]) for _ in range(rng.randint(1, 14))]
+        if rng.random() < 0.3:
+            lv[-1] = "#"
+        if rng.random() < 0.05:
+            lv[0] = "$x"
+        return "/".join(lv)
+
+    for i in range(5000):
+        t = deep_topic()
+        if e.retain_set(t, i) == 0:
+            rt.insert(t, i)
+        if i % 7 == 3:
+            t2 = deep_topic()
+            if e.retain_remove(t2) == 0:
+                rt.remove(t2)
+    fl = [deep_filter() for _ in range(1200)] + ["#", "+/#", "+/+/+/+/+/+/+/+/+/#", "a/a/a/a/a/a/a/a/a/a/+", "/".join(["+"] * 12)]
+    fb, fo = pack(fl)
+    res, _, grew = e.retain_match(fb, fo, cap_items=256, cap_desc=256)
+    assert grew >= 1
+    _same(res, rt.match_batch(fb, fo))
+    e.close()
