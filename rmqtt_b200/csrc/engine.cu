@@ -1532,6 +1532,9 @@ int32_t gm_match_gather_device(gm_engine* e, const void* d_blob, uint64_t blob_b
                                                      G.rank * G.slab_topics, G.rank * G.slab_ids, n, d_m);
         e->launches++;
     }
+    // the error word reports on THIS step only: a straggler of an earlier step (a rank that arrived after the bounded wait) must not
+    // make every later gm_gather_get fail (only this rank's own k_gather_finish ever writes the word)
+    CUDA_TRY(cudaMemsetAsync(reinterpret_cast<u32*>(G.block + G.off_flags) + 32, 0, sizeof(u32), s));
     k_gather_finish<<<1, 32, 0, s>>>(reinterpret_cast<unsigned long long* const*>(dp), reinterpret_cast<u32* const*>(dp + 8), reinterpret_cast<u32*>(G.block + G.off_flags),
                                      G.rank, G.world, n, d_m, G.epoch, reinterpret_cast<u32*>(G.block + G.off_flags) + 32);
     e->launches++;
