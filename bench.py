@@ -693,10 +693,18 @@ def run_own(args):
                 kk, _ = eng.partition_batch_device(d_mb, d_mo, world, rank, d_sel, stream)
                 eng.match_gather_device(d_mb, d_mo, d_status, stream, d_sel=d_sel, n_sel=kk)
 
+            def read_back():                                      # rank 0's gathered block; a barrier a rank missed is reported, the timings stand
+                try:
+                    return eng.gather_result(stream) if rank == 0 else None
+                except Exception as ex:                           # noqa: BLE001
+                    gather_get_errors.append(f"{type(ex).__name__}: {ex}"[:200])
+                    return None
+
+            gather_get_errors = []
             ms_fused = timed_device_loop(fused_step, coll_steps, 3)
             fused_step(0)
             sync_all()
-            fused_res = eng.gather_result(stream) if rank == 0 else None
+            fused_res = read_back()
             ms_direct = None
             if world > 1:                                         # A/B: the publish phase storing into every rank's block itself
                 eng.debug_knob("gather_direct", 1)
@@ -704,13 +712,15 @@ def run_own(args):
                 eng.debug_knob("gather_direct", 0)
                 fused_step(0)
                 sync_all()
-                fused_res = eng.gather_result(stream) if rank == 0 else None
+                fused_res = read_back()
             multi["strong_fused"] = {"how": "gm_match_gather_device over peer memory (CUDA IPC): the match kernels publish this rank's rows into its own block, "
                                             "k_gather_push copies the slab into every peer's block with 16-byte stores over NVLink, a one-warp kernel writes the counts "
                                             "and runs a flag barrier; no NCCL call, no host synchronisation",
                                      "ms_per_step_direct_stores": (ms_direct / coll_steps) if ms_direct else None,
                                      "value": n * coll_steps / (ms_fused / 1e3), "unit": "topics/s", "ms_per_step": ms_fused / coll_steps, "steps": coll_steps,
                                      "vs_nccl_step": (ms_strong / coll_steps) / (ms_fused / coll_steps)}
+            if gather_get_errors:
+                multi["strong_fused"]["gather_get_errors"] = gather_get_errors
             sync_all()
         except Exception as ex:                               # noqa: BLE001 - e.g. GM_ERR_COMM from the flag barrier: reported, the NCCL numbers stand
             traceback.print_exc(file=sys.stderr)

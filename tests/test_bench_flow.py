@@ -93,8 +93,28 @@ class _FakeEngine:
         a_ids.numpy()[:m] = d_ids.numpy()[:m]
         return np.array([[k, m]], dtype=np.int64)
 
+    peer_memory = True                   # class switch: False = gm_gather_connect fails (no peer-to-peer access)
+
     def gather_create(self, world, rank, slab_topics, slab_ids):
-        raise RuntimeError("no peer memory on a CPU box")
+        if not self.peer_memory:
+            raise RuntimeError("no peer memory on a CPU box")
+        self._slab_ids = slab_ids
+        return b"\0" * 64
+
+    def gather_connect(self, handles):
+        pass
+
+    def match_gather_device(self, d_blob, d_offs, d_status, stream, d_sel=None, n_sel=None):
+        self._gathered = self._match(d_blob, d_offs)
+        self.launches += 7
+
+    def gather_result(self, stream):
+        r = self._gathered
+        n, m = len(r["counts"]), int(r["offsets"][-1])
+        spans = np.stack([r["offsets"][:-1].astype(np.uint32), np.maximum(r["counts"], 0).astype(np.uint32)], axis=1)
+        ids = np.zeros(max(self._slab_ids, m), dtype=np.uint32)
+        ids[:m] = r["ids"]
+        return np.array([[n, m]], dtype=np.int64), np.arange(n, dtype=np.uint32), spans, ids
 
     def debug_knob(self, name, value):
         pass
@@ -211,7 +231,7 @@ def test_run_own_walks_every_leg_and_isolates_the_failing_ones(fake_gpu):
     assert r["bound"] == "hbm" and r["kernel"] == "k_match_fast" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert abs(r["descriptor_mode"]["frac"] - r["descriptor_mode"]["achieved"] / r["peak"]) < 1e-12
     assert d["parity_check"]["ok"] is True and d["parity_check"]["topics"] == 2000          # the oracle-backed fake really was compared
-    assert "unavailable" in d["multi_gpu"]["strong_fused"]
+    assert d["multi_gpu"]["strong_fused"]["value"] > 0 and d["parity_check"]["fused_ok"] is True      # the peer-memory leg and its self-check
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     assert len(d["churn"]["legs"]) == 4 and d["churn"]["port_single_thread_ops_per_s"] > 0
     assert len(d["latency"]["table"]) == 5
@@ -223,11 +243,13 @@ def test_run_own_walks_every_leg_and_isolates_the_failing_ones(fake_gpu):
     assert d["configs"]["C3-zipf"]["topics_per_s"] > 0
 
 
-def test_run_own_without_the_cpu_legs(fake_gpu):
+def test_run_own_without_the_cpu_legs(fake_gpu, monkeypatch):
     bench, out = fake_gpu
+    monkeypatch.setattr(_FakeEngine, "peer_memory", False)          # GPUs without peer access: the NCCL path only
     bench.run_own(_ns(no_cpu_baseline=True))
     d = json.loads(out.getvalue())
     assert d["cpu_baseline"] is None and d["churn"] is None and "errors" not in d and d["parity_check"]["ok"] is True
+    assert "unavailable" in d["multi_gpu"]["strong_fused"] and "fused_ok" not in d["parity_check"]
 
 
 def test_an_exception_after_the_headline_still_leaves_the_headline(fake_gpu, monkeypatch):
@@ -279,3 +301,16 @@ def test_abnormal_ends_print_the_partial_line_once(mode, env, rc, printed, tmp_p
     if printed:
         d = json.loads(lines[0])
         assert d["value"] == 1.5 and "bench" in d["errors"]
+
+
+def test_a_missed_gather_barrier_keeps_the_fused_timings(fake_gpu, monkeypatch):
+    bench, out = fake_gpu
+
+    def boom(self, stream):
+        raise RuntimeError("fused gather: a rank did not reach the end-of-step barrier")
+
+    monkeypatch.setattr(_FakeEngine, "gather_result", boom)
+    bench.run_own(_ns(no_cpu_baseline=True))
+    d = json.loads(out.getvalue())
+    f = d["multi_gpu"]["strong_fused"]
+    assert f["value"] > 0 and f["gather_get_errors"] and "fused_ok" not in d["parity_check"] and d["parity_check"]["ok"] is True
