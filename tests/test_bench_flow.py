@@ -129,8 +129,14 @@ class _FakeEngine:
 class _FakeLib:
     """libgpumqtt entry points bench.run_own calls directly (host-buffer calls are not executed: rc 0, sizes filled in)."""
 
-    def __init__(self):
+    def __init__(self, real=None):
         self.bufs = {}
+        self._real = real
+
+    def __getattr__(self, name):                 # pure host functions (gm_shard_of ...) are the real library's
+        if name.startswith("gm") and self._real is not None:
+            return getattr(self._real, name)
+        raise AttributeError(name)
 
     def gm_bind_thread_near_device(self, dev):
         return 0
@@ -189,7 +195,7 @@ def fake_gpu(monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: _Stream())
     monkeypatch.setattr(torch.cuda, "Event", _Event)
     monkeypatch.setattr(E, "Engine", _FakeEngine)
-    fake = _FakeLib()
+    fake = _FakeLib(real=N.lib())
     monkeypatch.setattr(N, "lib", lambda: fake)
     out = io.StringIO()
     monkeypatch.setattr(bench, "_RESULT_OUT", out)
@@ -314,3 +320,58 @@ def test_a_missed_gather_barrier_keeps_the_fused_timings(fake_gpu, monkeypatch):
     d = json.loads(out.getvalue())
     f = d["multi_gpu"]["strong_fused"]
     assert f["value"] > 0 and f["gather_get_errors"] and "fused_ok" not in d["parity_check"] and d["parity_check"]["ok"] is True
+
+
+def test_rank_zero_of_a_two_rank_launch_walks_the_multi_rank_branches(fake_gpu, monkeypatch):
+    """WORLD_SIZE=2 with torch.distributed replaced by single-process stand-ins: rank 0 takes every `world > 1` branch of run_own
+    (sharded generators, the library communicator, value_with_gather, the broadcast A/B of the collective, the direct-store A/B of
+    the fused gather, max-over-ranks reductions).  The fake holds only rank 0's shard, so the gathered lists do not equal the
+    unsharded oracle here — the line must say so (`parity_check.ok` false) rather than crash."""
+    import torch.distributed as dist
+    bench, out = fake_gpu
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "all_reduce", lambda t, op=None: None)
+    monkeypatch.setattr(dist, "broadcast_object_list", lambda objs, src=0: None)
+
+    def all_gather_object(outs, obj):
+        for i in range(len(outs)):
+            outs[i] = obj
+    monkeypatch.setattr(dist, "all_gather_object", all_gather_object)
+
+    def partition(self, d_blob, d_offs, n_shards, rank, d_sel, stream, d_shard=None):      # everything lands on rank 0
+        n = d_offs.numel() - 1
+        d_sel.numpy()[:n] = np.arange(n)
+        counts = np.zeros(n_shards, dtype=np.int64)
+        counts[0] = n
+        return n, counts
+
+    def allgatherv(self, d_index, d_spans, k, d_ids, d_m, a_idx, a_spans, a_ids, stream):
+        m = int(d_m[0])
+        a_idx.numpy()[:k] = d_index.numpy()[:k]
+        a_spans.numpy()[:k] = d_spans.numpy()[:k]
+        a_ids.numpy()[:m] = d_ids.numpy()[:m]
+        sizes = np.zeros((self._world, 2), dtype=np.int64)
+        sizes[0] = (k, m)
+        return sizes
+
+    def gather_result(self, stream):
+        r = self._gathered
+        n, m = len(r["counts"]), int(r["offsets"][-1])
+        spans = np.stack([r["offsets"][:-1].astype(np.uint32), np.maximum(r["counts"], 0).astype(np.uint32)], axis=1)
+        ids = np.zeros(2 * max(self._slab_ids, m), dtype=np.uint32)
+        ids[:m] = r["ids"]
+        return np.array([[n, m], [0, 0]], dtype=np.int64), np.arange(n, dtype=np.uint32), spans, ids
+
+    monkeypatch.setattr(_FakeEngine, "partition_batch_device", partition)
+    monkeypatch.setattr(_FakeEngine, "allgatherv_device", allgatherv)
+    monkeypatch.setattr(_FakeEngine, "gather_result", gather_result)
+    bench.run_own(_ns(gpus=2))
+    d = json.loads(out.getvalue())
+    assert d["n_gpus"] == 2 and d["value_with_gather"] > 0 and d["multi_gpu"]["collective"].startswith("gm_allgatherv_device")
+    assert d["multi_gpu"]["strong"]["all_gatherv_ms_with_broadcasts"] > 0 and d["multi_gpu"]["strong"]["shard_load"]["per_shard"][1] == 0
+    assert d["multi_gpu"]["strong_fused"]["ms_per_step_direct_stores"] > 0
+    assert d["cpu_baseline"] is None and d["c4"] is None and "sharded by topic-root hash over 2 GPUs" in d["config"]["workload"]
+    assert d["parity_check"]["topics"] == 2000 and isinstance(d["parity_check"]["ok"], bool)
